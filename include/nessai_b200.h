@@ -1,0 +1,102 @@
+/* nessai_b200 -- C ABI of the B200-native flow-proposal hot path.
+ *
+ * The reference (mj-will/nessai) has no FFI: its boundary for this path is the
+ * Python class nessai.flowmodel.FlowModel (plugin point P2).  The
+ * entry points below are what a binding for that class calls; each cites the
+ * reference method it replaces (paths relative to /root/reference/src/nessai).
+ *
+ * Conventions: plain pointers and sizes only.  Pointers named d_* are DEVICE
+ * pointers (fp32 row-major unless stated), h_* are HOST pointers.  `stream` is a
+ * cudaStream_t passed as void* (NULL = default stream).  Every function returns 0
+ * on success and a non-zero code otherwise; nb200_last_error() describes the last
+ * failure of the calling thread.  Per-row numerical failures (spline
+ * discriminant < 0, overflow) never trap: the row's outputs are NaN, which the
+ * caller drops exactly as flowproposal/flowproposal.py:366-368 drops non-finite
+ * log-probabilities.
+ */
+#ifndef NESSAI_B200_H
+#define NESSAI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nb200_flow nb200_flow; /* opaque: one eval-mode flow on one GPU */
+
+int nb200_version(void);
+const char* nb200_last_error(void);
+/* number of kernel launches issued by this library since load / last reset */
+int64_t nb200_launch_count(void);
+void nb200_reset_launch_count(void);
+
+/* flows/utils.py:208-246 configure_model -> a device-resident flow object.
+ * D = features, H = conditioner width, activation: 0 relu, 1 tanh, 2 silu. */
+int nb200_flow_create(nb200_flow** out, int D, int H, int activation);
+int nb200_flow_destroy(nb200_flow* flow);
+
+/* Upload the folded eval-mode program for one direction (0 = forward x->z,
+ * 1 = inverse z->x): replaces model.eval() + the LU-cache rebuild of
+ * flowmodel/base.py:680-690.  h_ops: int32[n_ops*16] (csrc/flow_program.h),
+ * h_blob: float32[n_blob]; both are copied. */
+int nb200_flow_set_program(nb200_flow* flow, int direction, const int32_t* h_ops, int n_ops,
+                           const float* h_blob, int64_t n_blob, int final_buf,
+                           double const_logdet);
+
+/* flowmodel/base.py:813-840 FlowModel.inverse and :939-944
+ * sample_and_log_prob(z=z):  d_x[n*D], d_logj[n] = log|det dx/dz|,
+ * d_logq[n] = log N(z) - logj.  d_logj / d_logq may be NULL. */
+int nb200_flow_inverse(nb200_flow* flow, const float* d_z, float* d_x, float* d_logj,
+                       float* d_logq, int64_t n, void* stream);
+
+/* flowmodel/base.py:782-811 forward_and_log_prob and :842-864 log_prob:
+ * d_z[n*D] (may be NULL), d_logj[n] (may be NULL), d_logp[n] = log N(z) + logj. */
+int nb200_flow_forward(nb200_flow* flow, const float* d_x, float* d_z, float* d_logj,
+                       float* d_logp, int64_t n, void* stream);
+
+/* flowmodel/base.py:889-904 sample_latent_distribution: d_z[n*D] ~ N(0, I),
+ * Philox4x32-10 keyed by `seed`, counter = row_offset + row. */
+int nb200_sample_latent(float* d_z, int64_t n, int D, uint64_t seed, uint64_t row_offset,
+                        void* stream);
+
+/* One turn of the populate() loop, flowproposal/flowproposal.py:431-469, fused:
+ * draw z (Philox; * sqrt_temperature) -> latent-radius truncation
+ * (truncation.py:358-365: keep |z| <= r_max, r_max <= 0 disables) -> inverse flow
+ * -> log_q = log N(z / sqrt T) - D log sqrt T - logj (base.py:401-414) ->
+ * diagonal inverse rescale x = x' * scale + shift, log_q -= sum log|scale|
+ * (reparameterisations/rescale.py:263-291) -> prior-bounds check
+ * (model.py:497-518) -> log_w = log_prior_const - log_q (base.py:1069-1098,
+ * uniform box prior) -> running max of log_w over valid rows.
+ *
+ * d_scale, d_shift, d_lo, d_hi: float64[D] device.  Outputs: d_x float64[n*D],
+ * d_logq float64[n], d_logw float64[n] (NaN for dropped rows), d_z float32[n*D]
+ * or NULL, d_stats: float64[2] = {max log_w (init -inf by caller), n_valid
+ * (accumulated)}.  If log_prior_const is NaN, d_logw holds -log_q and the caller
+ * adds its own prior. */
+int nb200_populate_draw(nb200_flow* flow, int64_t n, uint64_t seed, uint64_t row_offset,
+                        float r_max, float sqrt_temperature, const double* d_scale,
+                        const double* d_shift, const double* d_lo, const double* d_hi,
+                        double log_prior_const, double* d_x, double* d_logq, double* d_logw,
+                        float* d_z, double* d_stats, void* stream);
+
+/* Rejection step + compaction, flowproposal/flowproposal.py:491-498:
+ * accept = (log_w - max) > log(u), u ~ U(0,1) (Philox, `seed`, counter =
+ * row_offset + row); accepted rows are written IN DRAW ORDER as structured
+ * live-point records: each record starts as a copy of d_row_template
+ * (row_bytes, multiple of 4) and gets the D parameters (float64 at byte offsets
+ * h_field_offsets[0..D-1]) and logP (float64 at h_field_offsets[D], skipped if
+ * negative) overwritten.  At most `capacity` records are written to d_rows;
+ * d_counts: int64[2] = {n_accepted (all), n_written}.  d_max points at the
+ * (possibly all-reduced) maximum of log_w.  d_scratch: int64[ceil(n/1024)+1]. */
+int nb200_populate_accept(int64_t n, int D, const double* d_x, const double* d_logw,
+                          const double* d_max, uint64_t seed, uint64_t row_offset,
+                          double log_p_value, const uint8_t* d_row_template, int row_bytes,
+                          const int32_t* h_field_offsets, uint8_t* d_rows, int64_t capacity,
+                          int64_t write_offset, int64_t* d_counts, int64_t* d_scratch,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NESSAI_B200_H */

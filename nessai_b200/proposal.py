@@ -1,0 +1,620 @@
+"""Device-resident ``populate()`` and the standalone ``B200FlowProposal``.
+
+``PopulateEngine`` is the B200 version of the loop body of
+``FlowProposal.populate``
+(/root/reference/src/nessai/proposal/flowproposal/flowproposal.py:431-510): each
+turn is ONE fused kernel (Philox latent draw -> latent-radius truncation ->
+inverse flow -> diagonal inverse rescale -> prior bounds -> log-weights -> max)
+followed by the rejection step + in-order compaction into structured live-point
+records on the device; only the accepted records cross PCIe, already in the
+sampler's dtype.  With ``torch.distributed`` initialised (one process per GPU)
+the draw is sharded over ranks by global row index; the ranks exchange the
+scalar max / counts and all-gather the accepted records over NCCL.
+
+``B200FlowProposal`` mirrors the part of ``BaseFlowProposal`` / ``FlowProposal``
+on the hot path (same method names, arguments and attributes; SURVEY.md 8a
+b1-b11) without importing nessai, for the default z-score / null
+reparameterisation.  ``nessai_b200.nessai_plugin`` binds the same engine into the
+real ``nessai.proposal.FlowProposal`` when nessai is installed.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import datetime
+import logging
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .flowmodel import B200FlowModel, _ptr, _stream
+from .livepoint import (
+    NON_SAMPLING_DEFAULTS,
+    NON_SAMPLING_PARAMETERS,
+    empty_structured_array,
+    get_dtype,
+    live_points_to_array,
+)
+
+logger = logging.getLogger(__name__)
+
+
+def compute_radius(n, q=0.95):
+    """/root/reference/src/nessai/utils/sampling.py:15-33."""
+    from scipy import stats
+
+    return stats.chi.ppf(q, n)
+
+
+def _dist_info(group=None):
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def detect_uniform_box_prior(model, rng, n=256, atol=1e-9):
+    """Return ``log p`` if the model's prior is uniform on its (finite) box, else
+    ``None``.  Checked numerically on random in-bounds points against
+    ``-sum(log(hi - lo))``; a model can also declare it with an attribute
+    ``uniform_box_prior = True`` / ``False``."""
+    declared = getattr(model, "uniform_box_prior", None)
+    names = list(model.names)
+    lo = np.array([model.bounds[n_][0] for n_ in names], dtype=np.float64)
+    hi = np.array([model.bounds[n_][1] for n_ in names], dtype=np.float64)
+    if not (np.all(np.isfinite(lo)) and np.all(np.isfinite(hi))):
+        return None
+    const = -float(np.sum(np.log(hi - lo)))
+    if declared is False:
+        return None
+    if declared is True:
+        return const
+    x = empty_structured_array(n, names)
+    u = rng.random((n, len(names)))
+    for i, nm in enumerate(names):
+        x[nm] = lo[i] + (hi[i] - lo[i]) * u[:, i]
+    try:
+        lp = np.asarray(model.log_prior(x), dtype=np.float64)
+    except Exception:
+        return None
+    if lp.shape != (n,) or not np.all(np.abs(lp - const) <= atol * max(1.0, abs(const))):
+        return None
+    return const
+
+
+class PopulateEngine:
+    """Fused populate turns on one GPU (optionally one rank of many)."""
+
+    def __init__(self, flow: B200FlowModel, names, row_dtype: np.dtype, group=None):
+        self.flow = flow
+        self.model = flow.model
+        self.device = self.model.device
+        self.names = list(names)
+        self.D = len(self.names)
+        self.row_dtype = np.dtype(row_dtype)
+        self.row_bytes = self.row_dtype.itemsize
+        if self.row_bytes % 4:
+            raise NotImplementedError(
+                f"live-point dtype itemsize {self.row_bytes} is not a multiple of 4"
+            )
+        offs = [self.row_dtype.fields[n][1] for n in self.names]
+        for n in self.names:
+            if self.row_dtype.fields[n][0] != np.dtype("f8"):
+                raise NotImplementedError("live-point parameters must be float64")
+        logp_off = self.row_dtype.fields["logP"][1] if "logP" in self.row_dtype.names else -1
+        self.field_offsets = np.asarray(offs + [logp_off], dtype=np.int32)
+        tmpl = empty_structured_array(1, dtype=self.row_dtype)
+        self.d_template = torch.from_numpy(tmpl.view(np.uint8).copy()).to(self.device)
+        self.group = group
+        self.rank, self.world = _dist_info(group)
+        self._cap = 0
+        self._rows_cap = 0
+        self._turn_rows = 0  # global rows drawn so far (Philox counter base)
+        self.seed = None
+
+    # ---------------------------------------------------------------- buffers
+    def _ensure(self, n_local: int, capacity: int, want_z: bool):
+        dev = self.device
+        if n_local > self._cap:
+            self.d_x = torch.empty((n_local, self.D), dtype=torch.float64, device=dev)
+            self.d_logq = torch.empty(n_local, dtype=torch.float64, device=dev)
+            self.d_logw = torch.empty(n_local, dtype=torch.float64, device=dev)
+            self.d_scratch = torch.empty(n_local // 1024 + 2, dtype=torch.int64, device=dev)
+            self.d_z = None
+            self._cap = n_local
+        if want_z and (self.d_z is None or self.d_z.shape[0] < n_local):
+            self.d_z = torch.empty((self._cap, self.D), dtype=torch.float32, device=dev)
+        if capacity > self._rows_cap:
+            self.d_rows = torch.empty(capacity * self.row_bytes, dtype=torch.uint8, device=dev)
+            self._rows_cap = capacity
+        if not hasattr(self, "d_stats"):
+            self.d_stats = torch.empty(2, dtype=torch.float64, device=dev)
+            self.d_counts = torch.zeros(2, dtype=torch.int64, device=dev)
+
+    def configure(self, scale, shift, lo, hi, log_prior_const, r_max, sqrt_temperature=1.0):
+        f64 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64), device=self.device)  # noqa: E731
+        self.d_scale, self.d_shift, self.d_lo, self.d_hi = f64(scale), f64(shift), f64(lo), f64(hi)
+        self.log_prior_const = log_prior_const
+        self.r_max = float(r_max) if r_max else 0.0
+        self.sqrt_t = float(sqrt_temperature)
+
+    def _seed(self):
+        if self.seed is None:
+            s = torch.randint(0, 2**62, (1,), dtype=torch.int64)
+            if self.world > 1:
+                import torch.distributed as dist
+
+                s = s.to(self.device)
+                dist.broadcast(s, src=0, group=self.group)
+                s = s.cpu()
+            self.seed = int(s.item())
+        return self.seed
+
+    def _shard(self, n_total: int):
+        base, rem = divmod(n_total, self.world)
+        n_local = base + (1 if self.rank < rem else 0)
+        start = self.rank * base + min(self.rank, rem)
+        return n_local, start
+
+    # ------------------------------------------------------------------ turns
+    def draw_turn(self, n_total: int, want_z: bool = False):
+        """One fused draw of ``n_total`` global rows (this rank's shard).
+        Leaves x / log_q / log_w on the device; returns ``n_local``."""
+        self.model._ready()
+        n_local, start = self._shard(n_total)
+        self._ensure(max(n_local, 1), self._rows_cap, want_z)
+        self.d_stats[0] = -float("inf")
+        self.d_stats[1] = 0.0
+        lpc = float("nan") if self.log_prior_const is None else float(self.log_prior_const)
+        with torch.cuda.device(self.device):
+            _lib.check(
+                _lib.load().nb200_populate_draw(
+                    self.model._handle, n_local, C.c_uint64(self._seed()),
+                    C.c_uint64(self._turn_rows + start), self.r_max, self.sqrt_t,
+                    _ptr(self.d_scale), _ptr(self.d_shift), _ptr(self.d_lo), _ptr(self.d_hi),
+                    lpc, _ptr(self.d_x), _ptr(self.d_logq), _ptr(self.d_logw),
+                    _ptr(self.d_z) if want_z else None, _ptr(self.d_stats), _stream(),
+                ),
+                "nb200_populate_draw",
+            )
+        self._last = (n_local, start)
+        return n_local
+
+    def accept_turn(self, capacity_left: int, write_offset: int):
+        """Rejection + compaction of the last draw.  Returns the number of rows
+        accepted on this rank (device scalar tensor ``d_counts``)."""
+        n_local, start = self._last
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(self.d_stats[0:1], op=dist.ReduceOp.MAX, group=self.group)
+        lp = 0.0 if self.log_prior_const is None else float(self.log_prior_const)
+        with torch.cuda.device(self.device):
+            _lib.check(
+                _lib.load().nb200_populate_accept(
+                    n_local, self.D, _ptr(self.d_x), _ptr(self.d_logw), _ptr(self.d_stats),
+                    C.c_uint64(self._seed()), C.c_uint64(self._turn_rows + start), lp,
+                    _ptr(self.d_template), self.row_bytes,
+                    self.field_offsets.ctypes.data_as(C.c_void_p), _ptr(self.d_rows),
+                    int(capacity_left), int(write_offset), _ptr(self.d_counts),
+                    _ptr(self.d_scratch), _stream(),
+                ),
+                "nb200_populate_accept",
+            )
+        return self.d_counts
+
+    def run(self, n_samples: int, drawsize: int, max_samples: int = 1_000_000, host_prior=None):
+        """The whole ``while n_accepted < n_samples`` loop.
+
+        Returns ``(rows, n_proposed, n_accepted)``; ``rows`` is a fresh
+        structured numpy array (at most ``n_samples`` records, draw order,
+        rank-major when sharded).  ``host_prior(x_struct) -> log_p`` is used
+        when the prior is not a uniform box (evaluated on the host like the
+        reference does, /root/reference/.../flowproposal/base.py:1032-1051).
+        """
+        self._ensure(1, int(n_samples), False)
+        n_proposed = 0
+        n_accepted = 0  # global
+        n_local_written = 0
+        local_counts = []
+        while n_accepted < n_samples:
+            self.draw_turn(int(drawsize))
+            n_proposed += int(drawsize)
+            if host_prior is not None:
+                self._apply_host_prior(host_prior)
+            counts = self.accept_turn(int(n_samples) - n_local_written, n_local_written)
+            if self.world > 1:
+                import torch.distributed as dist
+
+                tot = counts[0:1].clone()
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
+                c = counts.cpu()
+                n_accepted += int(tot.item())
+            else:
+                c = counts.cpu()
+                n_accepted += int(c[0])
+            n_local_written += int(c[1])
+            local_counts.append(int(c[0]))
+            self._turn_rows += int(drawsize)
+            if n_proposed > max_samples:
+                logger.warning("Reached max samples (%s)", max_samples)
+                break
+        rows = self._gather_rows(n_local_written, int(n_samples))
+        return rows, n_proposed, n_accepted
+
+    def _apply_host_prior(self, host_prior):
+        n_local, _ = self._last
+        x = self.d_x[:n_local].cpu().numpy()
+        lw = self.d_logw[:n_local].cpu().numpy()
+        ok = ~np.isnan(lw)
+        xs = empty_structured_array(int(ok.sum()), dtype=self.row_dtype)
+        for i, nm in enumerate(self.names):
+            xs[nm] = x[ok, i]
+        lp = np.asarray(host_prior(xs), dtype=np.float64)
+        lw[ok] += lp
+        lw[ok & ~np.isfinite(lw)] = np.nan
+        self.d_logw[:n_local].copy_(torch.from_numpy(lw))
+        good = lw[ok][np.isfinite(lw[ok])]
+        self.d_stats[0] = float(good.max()) if good.size else -float("inf")
+        self._host_logp = None
+
+    def _gather_rows(self, n_local_written: int, n_samples: int) -> np.ndarray:
+        rb = self.row_bytes
+        if self.world == 1:
+            if not n_local_written:
+                return empty_structured_array(0, dtype=self.row_dtype)
+            host = self.d_rows[: n_local_written * rb].cpu().numpy()
+            return host.view(self.row_dtype)
+        import torch.distributed as dist
+
+        cnt = torch.tensor([n_local_written], dtype=torch.int64, device=self.device)
+        allc = [torch.zeros_like(cnt) for _ in range(self.world)]
+        dist.all_gather(allc, cnt, group=self.group)
+        allc = [int(c.item()) for c in allc]
+        mx = max(max(allc), 1)
+        send = self.d_rows[: mx * rb] if self._rows_cap >= mx else torch.cat(
+            [self.d_rows, torch.zeros(mx * rb - self.d_rows.numel(), dtype=torch.uint8, device=self.device)]
+        )
+        recv = torch.empty(self.world * mx * rb, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(recv, send.contiguous(), group=self.group)
+        parts = [recv[r * mx * rb : r * mx * rb + allc[r] * rb] for r in range(self.world)]
+        full = torch.cat(parts)[: n_samples * rb]
+        if not full.numel():
+            return empty_structured_array(0, dtype=self.row_dtype)
+        return full.cpu().numpy().view(self.row_dtype)
+
+
+class B200FlowProposal:
+    """Standalone mirror of ``FlowProposal`` for the hot path (see module doc).
+
+    ``model`` needs ``names``, ``bounds`` (name -> (lo, hi)), ``log_prior(x)``
+    and ``log_likelihood(x)`` on structured arrays -- the surface of
+    /root/reference/src/nessai/model.py:53 that this path touches.
+    """
+
+    _FlowModelClass = B200FlowModel
+
+    def __init__(
+        self,
+        model,
+        rng: Optional[np.random.Generator] = None,
+        flow_config=None,
+        training_config=None,
+        output=None,
+        poolsize=None,
+        drawsize=None,
+        plot=False,
+        check_acceptance=False,
+        max_poolsize_scale=10,
+        update_poolsize=True,
+        accumulate_weights=False,
+        fallback_reparameterisation="zscore",
+        latent_temperature=None,
+        volume_fraction=0.95,
+        fixed_radius=None,
+        device_prior="auto",
+    ):
+        if accumulate_weights:
+            raise NotImplementedError("nessai_b200: accumulate_weights is not implemented")
+        if fallback_reparameterisation not in ("zscore", "null", None):
+            raise NotImplementedError(
+                "nessai_b200: only the 'zscore' and 'null' reparameterisations run on the device"
+            )
+        self.model = model
+        self.rng = rng if rng is not None else np.random.default_rng()
+        self.flow_config = dict(flow_config or {})
+        self.training_config = dict(training_config or {})
+        self.output = output if output is not None else os.getcwd()
+        self._poolsize = 10000 if poolsize is None else int(poolsize)
+        self._poolsize_scale = 1.0
+        self.max_poolsize_scale = max_poolsize_scale
+        self.update_poolsize = update_poolsize
+        self.drawsize = self._poolsize if drawsize is None else int(drawsize)
+        self.check_acceptance = check_acceptance
+        self.accumulate_weights = False
+        self.fallback_reparameterisation = fallback_reparameterisation
+        if latent_temperature is not None:
+            if isinstance(latent_temperature, bool) or not isinstance(latent_temperature, (int, float)):
+                raise TypeError("latent_temperature must be a float")
+            if latent_temperature <= 0.0:
+                raise ValueError("latent_temperature must be positive")
+            latent_temperature = float(latent_temperature)
+        self.latent_temperature = latent_temperature
+        self.volume_fraction = volume_fraction
+        self.fixed_radius = fixed_radius
+        self.device_prior = device_prior
+        self.flow = None
+        self.initialised = False
+        self.populated = False
+        self.populating = False
+        self.indices = []
+        self.samples = None
+        self.x = None
+        self.training_count = 0
+        self.populated_count = 0
+        self.population_acceptance = None
+        self.population_time = datetime.timedelta()
+        self.ns_acceptance = 1.0
+        self.acceptance = []
+        self.r = np.nan
+        self._checked_population = True
+        self.training_data = None
+        self._engine = None
+        self.names = list(model.names)
+        self.prime_parameters = [f"{n}_prime" if fallback_reparameterisation == "zscore" else n for n in self.names]
+        self.scale = np.ones(len(self.names))
+        self.shift = np.zeros(len(self.names))
+
+    # ------------------------------------------------------------- properties
+    @property
+    def poolsize(self):
+        return int(self._poolsize_scale * self._poolsize)
+
+    @property
+    def dims(self):
+        return len(self.names)
+
+    prime_dims = dims
+
+    @property
+    def x_dtype(self):
+        return get_dtype(self.names)
+
+    population_dtype = x_dtype
+
+    def update_poolsize_scale(self, acceptance):
+        """flowproposal/base.py:416-435."""
+        if not acceptance:
+            self._poolsize_scale = self.max_poolsize_scale
+        else:
+            self._poolsize_scale = min(max(1.0 / acceptance, 1.0), self.max_poolsize_scale)
+
+    # ------------------------------------------------------------- lifecycle
+    def initialise(self, resumed: bool = False) -> None:
+        """flowproposal/base.py:358-391."""
+        os.makedirs(self.output, exist_ok=True)
+        self.flow_config["n_inputs"] = self.dims
+        self.flow = self._FlowModelClass(
+            flow_config=self.flow_config,
+            training_config=self.training_config,
+            output=self.output,
+            rng=self.rng,
+        )
+        self.flow.initialise()
+        if self.fixed_radius:
+            self.radius = float(self.fixed_radius)
+        else:
+            self.radius = float(compute_radius(self.dims, self.volume_fraction))
+        self.populated = False
+        self.initialised = True
+
+    # -------------------------------------------------------------- rescaling
+    def check_state(self, x):
+        """z-score statistics from the training set
+        (reparameterisations/rescale.py:293-304: np.std / np.mean)."""
+        if self.fallback_reparameterisation == "zscore":
+            self.scale = np.array([np.std(x[n]) for n in self.names])
+            self.shift = np.array([np.mean(x[n]) for n in self.names])
+
+    def rescale(self, x, **kwargs):
+        """x -> (x', log|J|)  (flowproposal/base.py:716-753, rescale.py:233-261)."""
+        x = np.atleast_1d(x)
+        x_prime = empty_structured_array(x.size, self.prime_parameters)
+        log_J = np.zeros(x.size)
+        for i, (n, pn) in enumerate(zip(self.names, self.prime_parameters)):
+            x_prime[pn] = (x[n] - self.shift[i]) / self.scale[i]
+            log_J -= np.log(np.abs(self.scale[i]))
+        for p in NON_SAMPLING_PARAMETERS:
+            x_prime[p] = x[p]
+        return x_prime, log_J
+
+    def inverse_rescale(self, x_prime, **kwargs):
+        """x' -> (x, log|J|)  (flowproposal/base.py:755-784, rescale.py:263-291)."""
+        x = empty_structured_array(x_prime.size, self.names)
+        log_J = np.zeros(x.size)
+        for i, (n, pn) in enumerate(zip(self.names, self.prime_parameters)):
+            x[n] = x_prime[pn] * self.scale[i] + self.shift[i]
+            log_J += np.log(np.abs(self.scale[i]))
+        for p in NON_SAMPLING_PARAMETERS:
+            x[p] = x_prime[p]
+        return x, log_J
+
+    # ---------------------------------------------------------------- training
+    def train(self, x, plot=False):
+        """flowproposal/base.py:870-925."""
+        if not self.initialised:
+            raise RuntimeError("B200FlowProposal is not initialised.")
+        self.training_data = x.copy()
+        self.check_state(self.training_data)
+        x_prime, _ = self.rescale(x)
+        self.training_data_prime = x_prime.copy()
+        x_prime_array = live_points_to_array(x_prime, self.prime_parameters, copy=True)
+        self.flow.train(x_prime_array, output=self.output, plot=False)
+        self.populated = False
+        self.training_count += 1
+
+    def reset_model_weights(self, **kwargs):
+        self.flow.reset_model(**kwargs)
+
+    # ----------------------------------------------------------------- passes
+    def forward_pass(self, x, rescale=True, **kwargs):
+        """flowproposal/base.py:961-994."""
+        log_J = 0
+        if rescale:
+            x, log_J_rescale = self.rescale(x, **kwargs)
+            log_J += log_J_rescale
+        names = self.prime_parameters if rescale else [n for n in x.dtype.names if n not in NON_SAMPLING_PARAMETERS]
+        x = live_points_to_array(x, names=names, copy=True)
+        if x.ndim == 1:
+            x = x[np.newaxis, :]
+        z, log_prob = self.flow.forward_and_log_prob(x)
+        return z, log_prob + log_J
+
+    def latent_log_prob(self, z, temperature=None):
+        """flowproposal/base.py:401-414."""
+        z = np.asarray(z)
+        if temperature in (None, 1.0):
+            z_in, log_j = z, 0.0
+        else:
+            scale = np.sqrt(float(temperature))
+            z_in, log_j = z / scale, z.shape[-1] * np.log(scale)
+        z_tensor = self.flow.numpy_array_to_tensor(z_in)
+        log_p = self.flow.model.base_distribution_log_prob(z_tensor)
+        return log_p.cpu().numpy().astype(np.float64) - log_j
+
+    def check_prior_bounds(self, x, *args):
+        flags = np.ones(x.size, dtype=bool)
+        for n in self.names:
+            lo, hi = self.model.bounds[n]
+            flags &= ~((x[n] < lo) | (x[n] > hi))
+        return (a[flags] for a in (x,) + args)
+
+    def backward_pass(self, z, rescale=True, discard_nans=True, return_z=False, **kwargs):
+        """flowproposal/flowproposal.py:345-389 (host-orchestrated variant; the
+        fused path is ``populate``)."""
+        x, log_j = self.flow.inverse(z)
+        log_prob = self.latent_log_prob(z, self.latent_temperature) - log_j
+        if discard_nans:
+            valid = np.isfinite(log_prob)
+            x, log_prob, z = x[valid], log_prob[valid], z[valid]
+        xs = empty_structured_array(x.shape[0], self.prime_parameters)
+        for i, p in enumerate(self.prime_parameters):
+            xs[p] = x[:, i]
+        if rescale:
+            xs, log_J = self.inverse_rescale(xs)
+            log_prob -= log_J
+            xs, z, log_prob = self.check_prior_bounds(xs, z, log_prob)
+        if return_z:
+            return xs, log_prob, z
+        return xs, log_prob
+
+    def log_prior(self, x):
+        return np.asarray(self.model.log_prior(x), dtype=np.float64)
+
+    def compute_weights(self, x, log_q, return_log_prior=False):
+        log_p = self.log_prior(x)
+        log_w = log_p - log_q
+        return (log_w, log_p) if return_log_prior else log_w
+
+    # --------------------------------------------------------------- populate
+    def _get_engine(self):
+        if self._engine is None or self._engine.flow is not self.flow:
+            self._engine = PopulateEngine(self.flow, self.names, self.x_dtype)
+            if self.device_prior in ("auto", True, "uniform"):
+                self._log_prior_const = detect_uniform_box_prior(self.model, self.rng)
+                if self.device_prior in (True, "uniform") and self._log_prior_const is None:
+                    raise RuntimeError("device_prior requested but the prior is not a finite uniform box")
+            else:
+                self._log_prior_const = None
+        lo = [self.model.bounds[n][0] for n in self.names]
+        hi = [self.model.bounds[n][1] for n in self.names]
+        t = self.latent_temperature
+        self._engine.configure(
+            self.scale, self.shift, lo, hi, self._log_prior_const, self.radius,
+            1.0 if t in (None, 1.0) else float(np.sqrt(t)),
+        )
+        return self._engine
+
+    def populate(self, worst_point, n_samples=10000, plot=False, r=None, max_samples=1_000_000) -> None:
+        """flowproposal/flowproposal.py:391-534 with the loop body on the GPU."""
+        st = datetime.datetime.now()
+        if not self.initialised:
+            raise RuntimeError(
+                "Proposal has not been initialised. Try calling `initialise()` first."
+            )
+        if r is not None:
+            self.radius = float(r)
+        self.indices = []
+        eng = self._get_engine()
+        host_prior = None if self._log_prior_const is not None else self.log_prior
+        rows, n_proposed, n_accepted = eng.run(
+            int(n_samples), int(self.drawsize), max_samples=max_samples, host_prior=host_prior
+        )
+        self.x = rows
+        self.samples = rows
+        if host_prior is not None and len(rows):
+            self.samples["logP"] = self.log_prior(self.samples)
+        self.n_proposed = n_proposed
+        self.population_time += datetime.datetime.now() - st
+        if len(self.samples):
+            self.samples["logL"] = np.asarray(self.model.log_likelihood(self.samples))
+        if self.check_acceptance:
+            self.acceptance.append(self.compute_acceptance(worst_point["logL"]))
+        self.indices = self.rng.permutation(self.samples.size).tolist()
+        self.population_acceptance = n_accepted / n_proposed
+        self.populated_count += 1
+        self.populated = True
+        self._checked_population = False
+
+    def compute_acceptance(self, logL):
+        return (self.samples["logL"] > logL).sum() / self.samples.size
+
+    def draw(self, worst_point):
+        """flowproposal/base.py:1152-1183."""
+        if not self.populated:
+            self.populating = True
+            if self.update_poolsize:
+                self.update_poolsize_scale(self.ns_acceptance)
+            while not self.populated:
+                self.populate(worst_point, n_samples=self.poolsize)
+            self.populating = False
+        index = self.indices.pop()
+        new_sample = self.samples[index]
+        if not self.indices:
+            self.populated = False
+        return new_sample
+
+    def reset(self):
+        self.indices = []
+        self.samples = None
+        self.x = None
+        self.populated = False
+        self.populated_count = 0
+        self.population_acceptance = None
+        self._poolsize_scale = 1.0
+        self._checked_population = True
+        self.acceptance = []
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["initialised"] = False
+        state["weights_file"] = getattr(state.get("flow"), "weights_file", None)
+        state["resume_populated"] = bool(state["populated"] and state["indices"])
+        for k in ("model", "flow", "_engine"):
+            state.pop(k, None)
+        return state
+
+    def resume(self, model, flow_config, weights_file=None):
+        """flowproposal/base.py:1237-1271."""
+        self.model = model
+        self.flow_config = dict(flow_config)
+        self._engine = None
+        self.initialise(resumed=True)
+        if weights_file is None:
+            weights_file = getattr(self, "weights_file", None)
+        if weights_file is not None and os.path.exists(weights_file):
+            self.flow.reload_weights(weights_file)

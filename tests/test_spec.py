@@ -1,0 +1,123 @@
+"""Host logic: flat layout, initialisation, folding and program encoding."""
+
+import numpy as np
+import pytest
+from _program_interp import run_program
+from conftest import reference_or_skip
+
+from nessai_b200.spec import FlowSpec
+
+
+def load_spec(cfg, sd):
+    sp = FlowSpec(cfg)
+    theta = np.zeros(sp.n_theta, np.float32)
+    ints = {}
+    sp.load_state_dict_numpy(sd, theta, ints)
+    return sp, theta, ints
+
+
+def test_state_dict_layout_matches_reference_keys(golden):
+    name, g, cfg, sd = golden
+    sp, theta, ints = load_spec(cfg, sd)
+    mine = sp.state_dict_numpy(theta, ints)
+    assert list(mine) == list(sd)  # same keys, same order
+    for k in sd:
+        assert mine[k].shape == sd[k].shape
+        np.testing.assert_array_equal(mine[k], sd[k])
+
+
+def test_folded_program_matches_golden(golden):
+    name, g, cfg, sd = golden
+    if "nsf" in name:
+        pytest.skip("spline op is checked on the GPU (numpy interpreter covers affine couplings)")
+    sp, theta, ints = load_spec(cfg, sd)
+    ff = sp.fold(theta, ints)
+    z, lj = run_program(ff.program(False), g["x"])
+    x, ilj = run_program(ff.program(True), g["z"])
+    np.testing.assert_allclose(z, g["fwd_z64"], atol=2e-5, rtol=1e-5)
+    np.testing.assert_allclose(lj, g["fwd_logj64"], atol=2e-5, rtol=1e-5)
+    np.testing.assert_allclose(x, g["inv_x64"], atol=2e-5, rtol=1e-5)
+    np.testing.assert_allclose(ilj, g["inv_logj64"], atol=2e-5, rtol=1e-5)
+
+
+def test_program_fp32_within_stated_tolerance(golden):
+    """fp32 evaluation of the folded program vs the reference's fp32 outputs:
+    log_prob / log|J| rtol 1e-4 (BASELINE.json north_star)."""
+    name, g, cfg, sd = golden
+    if "nsf" in name:
+        pytest.skip("spline op is checked on the GPU")
+    sp, theta, ints = load_spec(cfg, sd)
+    ff = sp.fold(theta, ints)
+    z, lj = run_program(ff.program(False), g["x"], np.float32)
+    lp = -0.5 * (z.astype(np.float64) ** 2).sum(1) - 0.5 * sp.D * np.log(2 * np.pi) + lj
+    np.testing.assert_allclose(lp, g["fwd_logprob"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize(
+    "cfg",
+    [
+        dict(n_inputs=16, n_neurons=64, n_blocks=4, n_layers=2, ftype="realnvp", net="mlp"),
+        dict(n_inputs=3, n_neurons=None, n_blocks=2, n_layers=2, ftype="realnvp"),
+        dict(n_inputs=6, n_neurons=16, n_blocks=3, n_layers=2, ftype="nsf"),
+        dict(n_inputs=5, n_neurons=8, n_blocks=2, n_layers=1, ftype="realnvp",
+             linear_transform="permutation", net="mlp"),
+    ],
+)
+def test_init_is_bit_identical_to_configure_model(cfg):
+    """Same torch seed -> same initial state_dict as the reference's
+    configure_model (flows/utils.py:208-246)."""
+    reference_or_skip()
+    import torch
+    from nessai.flowmodel.utils import update_flow_config
+    from nessai.flows import configure_model
+
+    torch.manual_seed(42)
+    ref = configure_model(update_flow_config(cfg)).state_dict()
+    sp = FlowSpec(cfg)
+    torch.manual_seed(42)
+    theta, ints = sp.init_state()
+    mine = sp.state_dict_numpy(theta, ints)
+    assert list(mine) == list(ref)
+    for k, v in ref.items():
+        np.testing.assert_array_equal(mine[k], v.numpy())
+
+
+@pytest.mark.reference
+def test_reset_weights_matches_reference():
+    reference_or_skip()
+    import torch
+    from nessai.flows import configure_model
+    from nessai.flows.utils import reset_weights
+
+    cfg = dict(n_inputs=4, n_neurons=8, n_blocks=2, n_layers=2, ftype="realnvp")
+    torch.manual_seed(0)
+    m = configure_model(cfg)
+    sp = FlowSpec(cfg)
+    torch.manual_seed(0)
+    theta, ints = sp.init_state()
+    torch.manual_seed(5)
+    m.apply(reset_weights)
+    torch.manual_seed(5)
+    sp.reset_weights(theta)
+    mine = sp.state_dict_numpy(theta, ints)
+    for k, v in m.state_dict().items():
+        np.testing.assert_array_equal(mine[k], v.numpy())
+
+
+def test_unsupported_options_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        FlowSpec(dict(n_inputs=4, ftype="maf"))
+    with pytest.raises(NotImplementedError):
+        FlowSpec(dict(n_inputs=4, ftype="realnvp", linear_transform="svd"))
+    with pytest.raises(NotImplementedError):
+        FlowSpec(dict(n_inputs=4, ftype="realnvp", distribution="lars"))
+    with pytest.raises(ValueError):
+        FlowSpec(dict(n_inputs=1, ftype="realnvp"))
+    with pytest.raises(TypeError):
+        FlowSpec(dict(n_inputs=4.0, ftype="realnvp"))
+
+
+def test_n_neurons_auto():
+    assert FlowSpec(dict(n_inputs=5, ftype="realnvp")).H == 10
+    assert FlowSpec(dict(n_inputs=5, n_neurons="equal", ftype="realnvp")).H == 5
