@@ -1,0 +1,477 @@
+#!/usr/bin/env python
+"""bench.py -- proposed live-points/sec of FlowProposal.populate (BASELINE.json).
+
+Workload (config C2): 16-D correlated Gaussian, RealNVP with 4 coupling layers and
+a [64, 64] MLP conditioner (weights: the reference-trained golden fixture),
+z-score reparameterisation, constant-volume latent radius (0.95), uniform box
+prior [-10, 10]^16, ``poolsize = drawsize = 1e6`` per GPU.  One "step" is one
+``populate(worst_point, n_samples=pool)`` call = as many 1e6-row turns as the
+reference's own loop makes (2 with the default ``max_samples``).
+
+  value : proposed rows / s, device pipeline only (draw + accept kernels; no D2H)
+  e2e   : n_proposed / population_time through ``B200FlowProposal.populate`` with
+          host structured arrays in and out (the D2H copy of the accepted records
+          and the host bookkeeping are inside the timed region)
+
+``--impl reference`` times the UNMODIFIED reference's FlowProposal.populate
+(baseline/_ref on the restated glasflow.nflows shim) on the host cores.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+D = 16
+POOL = 1_000_000
+FLOPS_PER_ROW = 47.7e3  # SURVEY.md 8(d), C2 RealNVP/MLP
+BYTES_PER_ROW = 68.0  # sample_and_log_prob, in-kernel RNG, z not returned
+SEED = 20251017
+
+
+def load_c2():
+    g = np.load(os.path.join(REPO, "tests", "golden", "c2_realnvp_mlp.npz"))
+    cfg = json.loads(str(g["flow_config"]))
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
+    return g, cfg, sd
+
+
+def live_points(n=2000):
+    rng = np.random.default_rng(SEED)
+    idx = np.arange(D)
+    cov = 0.5 ** np.abs(idx[:, None] - idx[None, :])
+    return rng.multivariate_normal(np.zeros(D), cov, size=n), cov
+
+
+class GaussianModel:
+    """16-D correlated Gaussian likelihood, uniform prior on [-10, 10]^16."""
+
+    def __init__(self):
+        self.names = [f"x{i}" for i in range(D)]
+        self.bounds = {n: [-10.0, 10.0] for n in self.names}
+        _, cov = live_points(2)
+        self._icov = np.linalg.inv(cov)
+        self._norm = -0.5 * (D * np.log(2 * np.pi) + np.linalg.slogdet(cov)[1])
+
+    def _arr(self, x):
+        return np.stack([x[n] for n in self.names], axis=-1)
+
+    def log_prior(self, x):
+        a = self._arr(x)
+        lp = np.full(a.shape[0] if a.ndim > 1 else 1, -D * np.log(20.0))
+        return np.where(np.all((a >= -10) & (a <= 10), axis=-1), lp, -np.inf)
+
+    def log_likelihood(self, x):
+        a = self._arr(x)
+        return self._norm - 0.5 * np.einsum("...i,ij,...j->...", a, self._icov, a)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            p = [v.strip() for v in s.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx = float(p[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": mx,
+            "reasons": sorted(reasons),
+            "samples": len(sm),
+        }
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------ ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from nessai_b200 import _lib
+    from nessai_b200.livepoint import numpy_array_to_live_points
+    from nessai_b200.proposal import B200FlowProposal
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    g, cfg, sd = load_c2()
+    live, _ = live_points()
+    model = GaussianModel()
+    torch.manual_seed(SEED)
+    pool = args.pool * world  # weak scaling: 1e6 rows per GPU per turn
+    prop = B200FlowProposal(
+        model, rng=np.random.default_rng(SEED), flow_config=cfg,
+        training_config=dict(device_tag=f"cuda:{local_rank}"),
+        output=tempfile.mkdtemp(), poolsize=pool, drawsize=pool, device_prior="auto",
+    )
+    prop.initialise()
+    live_s = numpy_array_to_live_points(live, model.names)
+    live_s["logL"] = model.log_likelihood(live_s)
+    prop.check_state(live_s)  # z-score statistics
+    prop.flow.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    prop.flow.model.eval()
+    worst = live_s[np.argmin(live_s["logL"])]
+    eng = prop._get_engine()
+    max_samples = pool
+
+    def device_step():
+        """populate()'s loop, device side only."""
+        n_acc, n_prop, written = 0, 0, 0
+        while n_acc < pool:
+            eng.draw_turn(pool)
+            n_prop += pool
+            c = eng.accept_turn(pool - written, written)
+            if world > 1:
+                tot = c[0:1].clone()
+                dist.all_reduce(tot)
+                n_acc += int(tot.item())
+                c = c.cpu()
+            else:
+                c = c.cpu()
+                n_acc += int(c[0])
+            written += int(c[1])
+            eng._turn_rows += pool
+            if n_prop > max_samples:
+                break
+        return n_prop
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng._ensure(1, pool, False)
+    for _ in range(args.warmup):
+        device_step()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    # ---- device-only timing (value) + dominant-kernel timing for the roofline
+    barrier()
+    _lib.reset_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    n_prop_total = 0
+    for _ in range(args.steps):
+        n_prop_total += device_step()
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    # dominant kernel alone: the fused draw kernel, CUDA events on its stream
+    n_local = eng._shard(pool)[0]
+    kt = []
+    for _ in range(max(args.steps, 3)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.draw_turn(pool)
+        b.record()
+        torch.cuda.synchronize()
+        kt.append(a.elapsed_time(b))
+    k_ms = float(np.mean(kt))
+    # ---- end to end through the plugin-facing call (host arrays in/out)
+    for _ in range(min(args.warmup, 2)):
+        prop.populate(worst, n_samples=pool, max_samples=max_samples)
+    barrier()
+    prop.population_time *= 0
+    t_e2e_prop, d2h = 0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        prop.populate(worst, n_samples=pool, max_samples=max_samples)
+        t_e2e_prop += prop.n_proposed
+        d2h += prop.samples.nbytes
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    pop_s = torch.tensor([prop.population_time.total_seconds()], device=dev)
+    if world > 1:
+        dist.all_reduce(pop_s, op=dist.ReduceOp.MAX)
+    pop_s = float(pop_s.item())
+    clk = clocks.stop() if rank == 0 else None
+
+    if rank == 0:
+        peaks, which = measured_peaks()
+        rows_s = n_prop_total / (ms_total * 1e-3)
+        k_rows_s = n_local / (k_ms * 1e-3)
+        tf = k_rows_s * FLOPS_PER_ROW / 1e12
+        peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        out = {
+            "metric": "proposed live-points/sec (FlowProposal.populate, 16-D, pool 1e6)",
+            "value": rows_s,
+            "unit": "rows/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic (Philox latent draws; reference-trained golden weights)",
+            "config": {
+                "workload": "C2: 16-D RealNVP 4x[64,64] MLP, poolsize=drawsize=1e6 per GPU, "
+                            "zscore, constant-volume radius 0.95, uniform box prior",
+                "rows_per_turn_per_gpu": args.pool,
+                "turns_per_step": int(round(n_prop_total / args.steps / pool)),
+                "l2": "each turn writes 144 MB of fresh outputs (> 126 MB L2); inputs are generated in-kernel",
+                "tc_kernel": bool(os.environ.get("NB200_DISABLE_TC", "0") != "1"),
+            },
+            "clocks": clk,
+            "e2e": {
+                "value": t_e2e_prop / pop_s,
+                "unit": "rows/s",
+                "h2d_bytes_per_step": 4 * D * 8,
+                "d2h_bytes_per_step": d2h / args.steps,
+                "population_time_s": pop_s,
+                "wall_s": wall,
+                "population_acceptance": prop.population_acceptance,
+            },
+            "gpu_launches": int(launches),
+            "roofline": {
+                "kernel": "populate_draw (fused draw + inverse flow + rescale + weights)",
+                "bound": "tensor",
+                "achieved": tf,
+                "peak": peak_tf,
+                "unit": "TFLOP/s",
+                "frac": tf / peak_tf,
+                "peak_source": f"{which} bf16 sustained",
+                "traffic": None,
+                "kernel_ms": k_ms,
+                "rows_per_launch": n_local,
+                "hbm": {
+                    "achieved": k_rows_s * BYTES_PER_ROW / 1e9,
+                    "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s",
+                    "frac": k_rows_s * BYTES_PER_ROW / 1e9 / peaks["hbm_gbs"],
+                    "written_bytes_per_row": 144,
+                },
+            },
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(threads=1, pool=args.cpu_pool)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------- reference
+def reference_populate(threads, pool, steps=1, warmup=0):
+    """Time the UNMODIFIED reference's FlowProposal.populate on the host cores."""
+    import oracle.refenv as refenv
+
+    refenv.activate()
+    import torch
+    from nessai.livepoint import numpy_array_to_live_points
+    from nessai.model import Model
+    from nessai.proposal import FlowProposal
+
+    torch.set_num_threads(threads)
+    g, cfg, sd = load_c2()
+    live, cov = live_points()
+
+    class RefModel(Model):
+        def __init__(self):
+            self.names = [f"x{i}" for i in range(D)]
+            self.bounds = {n: [-10.0, 10.0] for n in self.names}
+            self._icov = np.linalg.inv(cov)
+            self._norm = -0.5 * (D * np.log(2 * np.pi) + np.linalg.slogdet(cov)[1])
+
+        def log_prior(self, x):
+            lp = np.log(self.in_bounds(x), dtype="float")
+            for n in self.names:
+                lp -= np.log(20.0)
+            return lp
+
+        def log_likelihood(self, x):
+            a = self.unstructured_view(x)
+            return self._norm - 0.5 * np.einsum("...i,ij,...j->...", a, self._icov, a)
+
+    model = RefModel()
+    rng = np.random.default_rng(SEED)
+    model.set_rng(rng)
+    torch.manual_seed(SEED)
+    prop = FlowProposal(
+        model, rng=rng, flow_config=dict(cfg),
+        output=tempfile.mkdtemp(), poolsize=pool, drawsize=pool, plot=False,
+        fallback_reparameterisation="zscore",
+    )
+    prop.initialise()
+    live_s = numpy_array_to_live_points(live, model.names)
+    live_s["logL"] = model.log_likelihood(live_s)
+    prop.check_state(live_s)
+    prop.flow.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    prop.flow.model.eval()
+    worst = live_s[np.argmin(live_s["logL"])]
+    # count proposed rows (populate keeps n_proposed in a local variable)
+    counter = {"n": 0}
+    draw = prop.sample_latent_distribution
+
+    def counting_draw(n):
+        z = draw(n)
+        counter["n"] += len(z)
+        return z
+
+    prop.sample_latent_distribution = counting_draw
+    for _ in range(warmup):
+        prop.populate(worst, n_samples=pool, plot=False, max_samples=pool)
+    prop.population_time *= 0
+    counter["n"] = 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        prop.populate(worst, n_samples=pool, plot=False, max_samples=pool)
+    n_prop = counter["n"]
+    wall = time.perf_counter() - t0
+    pop_s = prop.population_time.total_seconds()
+    return n_prop, pop_s, wall, prop.population_acceptance
+
+
+def cpu_baseline(threads, pool):
+    import oracle.refenv as refenv
+
+    if not refenv.reference_available():
+        return {"value": None, "unit": "rows/s", "cores": threads, "kind": "reference",
+                "sample": "baseline/_ref not present"}
+    n_prop, pop_s, wall, acc = reference_populate(threads, pool, steps=1, warmup=0)
+    return {
+        "value": n_prop / pop_s,
+        "unit": "rows/s",
+        "cores": threads,
+        "kind": "reference",
+        "sample": f"one populate(n_samples={pool}, drawsize={pool}) = {n_prop} proposed rows in "
+                  f"{pop_s:.1f} s; unmodified nessai FlowProposal (baseline/_ref) on the restated "
+                  "glasflow.nflows shim (oracle/shims), same weights/live points as the GPU arm",
+        "population_acceptance": acc,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle.refenv as refenv
+
+    if not refenv.reference_available():
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref (pip --target install of /root/reference) not present"}))
+        return
+    threads = os.cpu_count() or 1
+    pool = args.cpu_pool
+    n_prop, pop_s, wall, acc = reference_populate(threads, pool, steps=args.steps, warmup=min(args.warmup, 1))
+    v = n_prop / pop_s
+    out = {
+        "impl": "reference",
+        "metric": "proposed live-points/sec (FlowProposal.populate, 16-D, pool 1e6)",
+        "value": v,
+        "unit": "rows/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * pop_s / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {
+            "workload": "C2: 16-D RealNVP 4x[64,64] MLP, zscore, constant-volume radius 0.95, "
+                        f"bounded sample: poolsize=drawsize={pool} per populate() (linear in rows)",
+        },
+        "cpu_baseline": {
+            "value": v, "unit": "rows/s", "cores": threads, "kind": "reference",
+            "sample": f"{args.steps} x populate(n_samples={pool}); nessai FlowProposal on the "
+                      "restated glasflow.nflows shim, torch threads = all host cores",
+        },
+        "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "population_acceptance": acc,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pool", type=int, default=POOL)
+    ap.add_argument("--cpu-pool", type=int, default=200_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -233,8 +233,6 @@ class B200Flow(torch.nn.Module):
         return z, logj
 
     def _forward(self, x, want_logp=True):
-        if context_given(x):
-            raise NotImplementedError
         self._ready()
         x = self._prep(x)
         n = x.shape[0]
@@ -332,9 +330,6 @@ class B200Flow(torch.nn.Module):
             self._eager = EagerFlow(self.spec, self.ints, self.device)
         return self._eager
 
-
-def context_given(x):
-    return False
 
 
 class B200FlowModel:

@@ -1,0 +1,156 @@
+"""Parity of the CUDA flow (through the C ABI, via B200FlowModel) with the
+reference's outputs (golden fixtures) and the float64 oracle.
+
+Stated tolerance (BASELINE.json north_star): log_prob / log|J| rtol 1e-4 in fp32;
+samples x/z: atol 1e-4 + rtol 1e-4.
+"""
+
+import pickle
+
+import numpy as np
+import pytest
+import torch
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-4, 1e-4
+
+
+def make_model(cfg, sd, tmp_path):
+    from nessai_b200.flowmodel import B200FlowModel
+
+    fm = B200FlowModel(flow_config=cfg, training_config=dict(device_tag="cuda:0"), output=str(tmp_path))
+    fm.initialise()
+    fm.model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    fm.model.eval()
+    return fm
+
+
+def test_inverse_and_forward_match_reference(golden, tmp_path):
+    name, g, cfg, sd = golden
+    fm = make_model(cfg, sd, tmp_path)
+    x, logj = fm.inverse(g["z"])
+    assert x.dtype == np.float64 and logj.dtype == np.float64 and x.flags.writeable
+    np.testing.assert_allclose(x, g["inv_x"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(logj, g["inv_logj"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(x, g["inv_x64"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(logj, g["inv_logj64"], rtol=RTOL, atol=ATOL)
+    x2, logq = fm.sample_and_log_prob(z=g["z"])
+    np.testing.assert_allclose(x2, x, rtol=0, atol=0)
+    np.testing.assert_allclose(logq, g["inv_logq"], rtol=RTOL, atol=ATOL)
+    z, logp = fm.forward_and_log_prob(g["x"])
+    np.testing.assert_allclose(z, g["fwd_z"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(logp, g["fwd_logprob"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(logp, g["fwd_logprob64"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(fm.log_prob(g["x"]), logp, rtol=0, atol=0)
+    zt, lj = fm.model.forward(torch.from_numpy(g["x"]))
+    np.testing.assert_allclose(lj.cpu().numpy(), g["fwd_logj"], rtol=RTOL, atol=ATOL)
+
+
+def test_round_trip_property(golden, tmp_path):
+    """inverse(forward(x)) == x, logJ_fwd == -logJ_inv to 5 decimals
+    (/root/reference/tests/test_flows/test_included_flows.py:144-154)."""
+    name, g, cfg, sd = golden
+    fm = make_model(cfg, sd, tmp_path)
+    zt, lj = fm.model.forward(torch.from_numpy(g["x"]))
+    xt, ilj = fm.model.inverse(zt)
+    np.testing.assert_array_almost_equal(xt.cpu().numpy(), g["x"], decimal=4)
+    np.testing.assert_array_almost_equal(lj.cpu().numpy(), -ilj.cpu().numpy(), decimal=4)
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 127, 129, 1000])
+def test_ragged_sizes(n, tmp_path):
+    g, cfg, sd = load_golden("c2_realnvp_mlp")
+    fm = make_model(cfg, sd, tmp_path)
+    z = np.resize(g["z"], (n, 16)) if n else np.zeros((0, 16))
+    x, lq = fm.sample_and_log_prob(z=z)
+    assert x.shape == (n, 16) and lq.shape == (n,)
+    if n:
+        k = min(n, len(g["z"]))
+        np.testing.assert_allclose(lq[:k], g["inv_logq"][:k], rtol=RTOL, atol=ATOL)
+
+
+def test_large_batch_is_consistent_with_small(tmp_path):
+    """Size-independent property at the bench size: 1e6 rows = tiled copies of the
+    golden rows must give exactly the golden-sized result, row for row."""
+    g, cfg, sd = load_golden("c2_realnvp_mlp")
+    fm = make_model(cfg, sd, tmp_path)
+    reps = 1_000_000 // len(g["z"]) + 1
+    z = np.tile(g["z"], (reps, 1))[:1_000_000]
+    x, lq = fm.sample_and_log_prob(z=z)
+    x0, lq0 = fm.sample_and_log_prob(z=g["z"])
+    np.testing.assert_array_equal(x[: len(x0)], x0)
+    idx = np.arange(1_000_000) % len(g["z"])
+    np.testing.assert_array_equal(lq, lq0[idx])
+    np.testing.assert_array_equal(x, x0[idx])
+
+
+def test_latent_sampling_matches_philox_oracle(tmp_path):
+    from oracle.philox_numpy import latent_normals
+
+    g, cfg, sd = load_golden("c2_realnvp_mlp")
+    fm = make_model(cfg, sd, tmp_path)
+    z = fm.sample_latent_distribution(5000)
+    assert z.shape == (5000, 16) and z.dtype == np.float64
+    seed = fm.model._rng_seed
+    ref = latent_normals(seed, np.arange(5000), 16)
+    np.testing.assert_allclose(z, ref, atol=2e-5, rtol=1e-5)
+    z2 = fm.sample_latent_distribution(5000)  # next rows of the stream
+    ref2 = latent_normals(seed, np.arange(5000, 10000), 16)
+    np.testing.assert_allclose(z2, ref2, atol=2e-5, rtol=1e-5)
+    big = fm.sample_latent_distribution(400_000)
+    assert abs(big.mean()) < 5e-3 and abs(big.var() - 1) < 5e-3
+
+
+def test_sample_and_log_prob_self_consistent(tmp_path):
+    """test_included_flows.py:129-141."""
+    g, cfg, sd = load_golden("c2_realnvp_resnet")
+    fm = make_model(cfg, sd, tmp_path)
+    x, lq = fm.sample_and_log_prob(N=2000)
+    lp = fm.log_prob(x)
+    ok = np.isfinite(lq)
+    np.testing.assert_allclose(lp[ok], lq[ok], rtol=1e-3, atol=1e-3)
+
+
+def test_weights_roundtrip_and_pickle(tmp_path):
+    g, cfg, sd = load_golden("c1_realnvp_2d")
+    fm = make_model(cfg, sd, tmp_path)
+    f = str(tmp_path / "model.pt")
+    fm.save_weights(f)
+    loaded = torch.load(f, weights_only=True)
+    assert list(loaded) == list(sd)
+    for k in sd:
+        np.testing.assert_array_equal(loaded[k].numpy(), sd[k])
+    fm2 = make_model(cfg, {k: np.zeros_like(v) if v.dtype.kind == "f" else v for k, v in sd.items()}, tmp_path)
+    fm2.load_weights(f)
+    np.testing.assert_array_equal(fm2.inverse(g["z"])[0], fm.inverse(g["z"])[0])
+    state = pickle.loads(pickle.dumps(fm))
+    assert state.initialised is False and not hasattr(state, "model")
+
+
+def test_training_tracks_reference_history(tmp_path):
+    """Same seeds, same data, same hyper-parameters as the golden run of the
+    reference FlowModel.train: the first epochs' losses must agree."""
+    from nessai_b200.flowmodel import B200FlowModel
+
+    g, cfg, sd = load_golden("c2_realnvp_mlp")
+    seed = 20251017
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    fm = B200FlowModel(flow_config=cfg, training_config=dict(max_epochs=8, patience=8, batch_size=1000),
+                       output=str(tmp_path), rng=rng)
+    fm.initialise()
+    init = fm.model.state_dict()
+    for k in init:
+        np.testing.assert_array_equal(init[k].numpy(), g[f"init/{k}"])
+    hist = fm.train(g["train_data"], plot=False)
+    assert set(hist) == {"loss", "val_loss"} and len(hist["loss"]) == 8
+    np.testing.assert_allclose(hist["loss"][:4], g["loss"][:4], rtol=2e-3)
+    np.testing.assert_allclose(hist["val_loss"][:4], g["val_loss"][:4], rtol=5e-3)
+    assert hist["loss"][-1] < hist["loss"][0]
+    # trained flow evaluates through the kernels and stays self-consistent
+    x, lq = fm.sample_and_log_prob(N=1000)
+    lp = fm.log_prob(x)
+    ok = np.isfinite(lq)
+    np.testing.assert_allclose(lp[ok], lq[ok], rtol=1e-3, atol=1e-3)

@@ -1,0 +1,163 @@
+"""Parity of the fused populate turn + rejection step with a numpy restatement of
+flowproposal.py:431-510 driven by the SAME latent draws and uniforms (Philox is
+restated in oracle/philox_numpy.py), plus the plugin-level populate() contract."""
+
+import numpy as np
+import pytest
+import torch
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+class BoxGaussian:
+    def __init__(self, d, lo=-10.0, hi=10.0):
+        self.names = [f"x{i}" for i in range(d)]
+        self.bounds = {n: [lo, hi] for n in self.names}
+        self.d, self.lo, self.hi = d, lo, hi
+
+    def _arr(self, x):
+        return np.stack([x[n] for n in self.names], axis=-1)
+
+    def log_prior(self, x):
+        a = self._arr(x)
+        inb = np.all((a >= self.lo) & (a <= self.hi), axis=-1)
+        return np.where(inb, -self.d * np.log(self.hi - self.lo), -np.inf)
+
+    def log_likelihood(self, x):
+        return -0.5 * np.sum(self._arr(x) ** 2, axis=-1)
+
+
+def make_proposal(name, tmp_path, pool, lo=-10.0, hi=10.0, **kw):
+    from nessai_b200.livepoint import numpy_array_to_live_points
+    from nessai_b200.proposal import B200FlowProposal
+
+    g, cfg, sd = load_golden(name)
+    d = cfg["n_inputs"]
+    model = BoxGaussian(d, lo, hi)
+    torch.manual_seed(11)
+    prop = B200FlowProposal(model, rng=np.random.default_rng(3), flow_config=cfg,
+                            training_config=dict(device_tag="cuda:0"), output=str(tmp_path),
+                            poolsize=pool, drawsize=pool, **kw)
+    prop.initialise()
+    rng = np.random.default_rng(5)
+    live = numpy_array_to_live_points(1.5 * rng.standard_normal((500, d)) + 0.3, model.names)
+    prop.check_state(live)
+    prop.flow.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    prop.flow.model.eval()
+    return prop, model, g, cfg, sd, live
+
+
+@pytest.mark.parametrize("name", ["c2_realnvp_mlp", "c1_realnvp_2d", "d5_realnvp_perm_tanh"])
+def test_fused_turn_matches_numpy_restatement(name, tmp_path):
+    from oracle.flow_numpy import NumpyFlow
+    from oracle.philox_numpy import accept_uniform, latent_normals
+
+    n = 20000
+    prop, model, g, cfg, sd, live = make_proposal(name, tmp_path, n, lo=-4.0, hi=4.0)
+    d = cfg["n_inputs"]
+    eng = prop._get_engine()
+    eng._ensure(n, n, True)
+    eng.draw_turn(n, want_z=True)
+    z = eng.d_z[:n].cpu().numpy().astype(np.float64)
+    x = eng.d_x[:n].cpu().numpy()
+    logq = eng.d_logq[:n].cpu().numpy()
+    logw = eng.d_logw[:n].cpu().numpy()
+    stats = eng.d_stats.cpu().numpy()
+    # (1) the latent draw is the Philox stream
+    z_ref = latent_normals(eng.seed, np.arange(n), d)
+    np.testing.assert_allclose(z, z_ref, atol=2e-5, rtol=1e-5)
+    # (2) restate the turn in float64 from the same z
+    nf = NumpyFlow(sd, ftype="realnvp", net=cfg.get("net", "resnet"),
+                   activation_name=cfg.get("activation", "relu"), hidden_features=cfg["n_neurons"])
+    xp, lq = nf.sample_and_log_prob(z)
+    x_ref = xp * prop.scale + prop.shift
+    lq = lq - np.sum(np.log(np.abs(prop.scale)))
+    keep = np.sqrt(np.sum(z**2, axis=1)) <= prop.radius
+    inb = np.all((x_ref >= -4.0) & (x_ref <= 4.0), axis=1)
+    valid = keep & inb & np.isfinite(lq)
+    # rows whose radius / bounds decision is within fp32 rounding of the edge are ambiguous
+    edge = (np.abs(np.sqrt(np.sum(z**2, axis=1)) - prop.radius) < 1e-4) | np.any(
+        (np.abs(np.abs(x_ref) - 4.0) < 1e-3), axis=1)
+    dev_valid = ~np.isnan(logw)
+    assert np.array_equal(dev_valid[~edge], valid[~edge])
+    both = dev_valid & valid
+    assert both.sum() > 0.3 * n * 0  # some survive
+    np.testing.assert_allclose(x[both], x_ref[both], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(logq[both], lq[both], rtol=1e-4, atol=1e-4)
+    lw_ref = -d * np.log(8.0) - lq
+    np.testing.assert_allclose(logw[both], lw_ref[both], rtol=1e-4, atol=1e-4)
+    assert stats[1] == dev_valid.sum()
+    np.testing.assert_allclose(stats[0], logw[dev_valid].max(), rtol=0, atol=0)
+    # (3) rejection step with the same uniforms
+    counts = eng.accept_turn(n, 0).cpu().numpy()
+    u = accept_uniform(eng.seed, np.arange(n))
+    margin = (logw - stats[0]) - np.log(u)
+    acc_ref = dev_valid & (margin > 0)
+    ambiguous = dev_valid & (np.abs(margin) < 1e-9)
+    assert abs(int(counts[0]) - int(acc_ref.sum())) <= int(ambiguous.sum())
+    rows = eng._gather_rows(int(counts[1]), n)
+    assert rows.dtype == prop.x_dtype and len(rows) == counts[1]
+    if not ambiguous.any():
+        got = np.stack([rows[nm] for nm in model.names], axis=-1)
+        np.testing.assert_array_equal(got, x[acc_ref])  # draw order preserved, bit-exact copy
+        assert np.all(rows["logP"] == -d * np.log(8.0)) and np.all(np.isnan(rows["logL"])) and np.all(rows["it"] == 0)
+
+
+def test_populate_contract(tmp_path):
+    """Attributes / dtypes the sampler relies on."""
+    pool = 50000
+    prop, model, g, cfg, sd, live = make_proposal("c2_realnvp_mlp", tmp_path, pool)
+    worst = live[0]
+    prop.populate(worst, n_samples=pool, max_samples=4 * pool)
+    assert prop.populated and prop.samples.dtype == prop.x_dtype
+    assert 0 < prop.samples.size <= pool
+    assert len(prop.indices) == prop.samples.size and sorted(prop.indices) == list(range(prop.samples.size))
+    assert 0 < prop.population_acceptance <= 1
+    assert np.all(np.isfinite(prop.samples["logL"])) and np.all(prop.samples["logP"] == -16 * np.log(20.0))
+    a = np.stack([prop.samples[n] for n in model.names], axis=-1)
+    assert np.all((a >= -10) & (a <= 10))
+    new = prop.draw(worst)
+    assert new.dtype == prop.x_dtype and len(prop.indices) == prop.samples.size - 1
+    # acceptance is consistent with the weights: E[accept] = mean(w) / max(w)
+    eng = prop._engine
+    eng.draw_turn(pool)
+    lw = eng.d_logw[: pool].cpu().numpy()
+    ok = ~np.isnan(lw)
+    expect = np.exp(lw[ok] - lw[ok].max()).sum() / pool
+    c = eng.accept_turn(pool, 0).cpu().numpy()
+    assert abs(c[0] / pool - expect) < 5 * np.sqrt(expect / pool) + 1e-4
+
+
+def test_host_prior_path_matches_device_prior(tmp_path):
+    pool = 20000
+    p1, model, *_ = make_proposal("c1_realnvp_2d", tmp_path, pool, device_prior="auto")
+    p2, *_ = make_proposal("c1_realnvp_2d", tmp_path, pool, device_prior=False)
+    w = None
+    p1.populate(w, n_samples=pool, max_samples=pool)
+    p2.populate(w, n_samples=pool, max_samples=pool)
+    assert p1._log_prior_const is not None and p2._log_prior_const is None
+    # same seeds -> same Philox streams -> identical pools
+    assert p1.samples.size == p2.samples.size
+    for n in model.names + ["logP"]:
+        np.testing.assert_allclose(p1.samples[n], p2.samples[n], rtol=0, atol=1e-12)
+
+
+def test_full_size_turn_properties(tmp_path):
+    """BASELINE size (1e6 rows): size-independent invariants of one turn."""
+    pool = 1_000_000
+    prop, model, *_ = make_proposal("c2_realnvp_mlp", tmp_path, pool)
+    eng = prop._get_engine()
+    eng._ensure(pool, pool, False)
+    eng.draw_turn(pool)
+    lw = eng.d_logw[:pool]
+    ok = ~torch.isnan(lw)
+    stats = eng.d_stats.cpu().numpy()
+    assert int(ok.sum()) == int(stats[1])
+    assert float(lw[ok].max()) == stats[0]
+    # the truncation keeps ~95 % of the latent draws (constant volume 0.95)
+    assert 0.90 < stats[1] / pool <= 0.951 + 0.002
+    x = eng.d_x[:pool][ok]
+    assert bool(((x >= -10) & (x <= 10)).all())
+    c = eng.accept_turn(pool, 0).cpu().numpy()
+    assert 0 < c[0] <= stats[1] and c[1] == min(c[0], pool)
