@@ -30,6 +30,10 @@ const char* nb200_last_error(void);
 /* number of kernel launches issued by this library since load / last reset */
 int64_t nb200_launch_count(void);
 void nb200_reset_launch_count(void);
+/* Enable (1, default) / disable (0) the tcgen05 specialisation for the flow shapes it
+ * covers; disabled, every flow runs the generic fp32 kernel.  Returns the previous
+ * setting.  (Environment: NB200_DISABLE_TC=1 sets the initial value to 0.) */
+int nb200_set_tensor_core_path(int enabled);
 
 /* flows/utils.py:208-246 configure_model -> a device-resident flow object.
  * D = features, H = conditioner width, activation: 0 relu, 1 tanh, 2 silu. */

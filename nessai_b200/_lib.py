@@ -62,6 +62,7 @@ _SIGS = {
     "nb200_last_error": (C.c_char_p, []),
     "nb200_launch_count": (C.c_int64, []),
     "nb200_reset_launch_count": (None, []),
+    "nb200_set_tensor_core_path": (C.c_int, [C.c_int]),
     "nb200_flow_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]),
     "nb200_flow_destroy": (C.c_int, [C.c_void_p]),
     "nb200_flow_set_program": (

@@ -12,6 +12,7 @@
 #include "../../include/nessai_b200.h"
 #include "flow_interp.cuh"
 #include "philox.cuh"
+#include "populate_common.cuh"
 #include "flow_tc.cuh"
 
 using namespace nb200;
@@ -39,6 +40,11 @@ extern "C" int nb200_version(void) { return 100; }
 extern "C" const char* nb200_last_error(void) { return g_err; }
 extern "C" int64_t nb200_launch_count(void) { return g_launches.load(); }
 extern "C" void nb200_reset_launch_count(void) { g_launches.store(0); }
+extern "C" int nb200_set_tensor_core_path(int enabled) {
+  const int prev = tc_enabled() ? 1 : 0;
+  tc_enabled_flag() = enabled ? 1 : 0;
+  return prev;
+}
 
 // ----------------------------------------------------------------------------- flow object
 struct DirProgram {
@@ -130,6 +136,7 @@ extern "C" int nb200_flow_set_program(nb200_flow* f, int direction, const int32_
   // try the tcgen05 specialisation (RealNVP + MLP conditioner shapes it covers)
   if (int rc = tc_build(p.tc, p.h_ops, n_ops, h_blob, f->D, f->H, f->activation, final_buf))
     return fail(rc, "tc_build failed: %s", cudaGetErrorString(cudaGetLastError()));
+  p.tc.const_logdet = (float)const_logdet;
   return 0;
 }
 
@@ -202,92 +209,17 @@ __global__ void sample_latent_kernel(float* __restrict__ z, int64_t n, int D, ui
   }
 }
 
-__device__ __forceinline__ void atomic_max_double(double* addr, double v) {
-  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
-  unsigned long long old = *a, assumed;
-  do {
-    assumed = old;
-    if (!(v > __longlong_as_double(assumed))) break;
-    old = atomicCAS(a, assumed, __double_as_longlong(v));
-  } while (assumed != old);
-}
-
-struct PopulateArgs {
-  int64_t n;
-  uint64_t seed, row_offset;
-  float r_max, sqrt_t;
-  const double *scale, *shift, *lo, *hi;
-  double log_prior_const;  // NaN: prior added by the caller
-  double log_j_rescale;    // sum log|scale|
-  double* x;
-  double* logq;
-  double* logw;
-  float* z;
-  double* stats;
-};
-
-// shared tail of the populate turn: rescale, bounds, weights (all float64 like the
-// reference's numpy side), block max / count.
-__device__ __forceinline__ void populate_tail(const PopulateArgs& A, int D, int BS,
-                                              const float* fin, int64_t row, bool alive,
-                                              float base_lp, float logj, double* red) {
-  double logq = NAN, logw = NAN;
-  bool ok = alive;
-  if (row < A.n) {
-    bool inb = true;
-    for (int d = 0; d < D; ++d) {
-      const double xp = (double)fin[d * BS];
-      const double xv = xp * A.scale[d] + A.shift[d];
-      A.x[row * D + d] = xv;
-      inb = inb && !(xv < A.lo[d]) && !(xv > A.hi[d]);
-    }
-    if (ok) {
-      logq = (double)base_lp - (double)D * log((double)A.sqrt_t) - (double)logj - A.log_j_rescale;
-      ok = isfinite(logq) && inb;
-    }
-    if (ok) logw = (isnan(A.log_prior_const) ? 0.0 : A.log_prior_const) - logq;
-    A.logq[row] = ok ? logq : NAN;
-    A.logw[row] = ok ? logw : NAN;
-  } else {
-    ok = false;
-  }
-  // block reduction: max(log_w), count(valid)
-  double m = ok ? logw : -INFINITY;
-  double c = ok ? 1.0 : 0.0;
-  for (int o = 16; o > 0; o >>= 1) {
-    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    c += __shfl_xor_sync(0xffffffffu, c, o);
-  }
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = BS >> 5;
-  __syncthreads();
-  if (l == 0) {
-    red[w] = m;
-    red[8 + w] = c;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < nw; ++i) {
-      m = fmax(m, red[i]);
-      c += red[8 + i];
-    }
-    if (c > 0) {
-      atomic_max_double(A.stats, m);
-      atomicAdd(A.stats + 1, c);
-    }
-  }
-}
-
 template <int ACT>
 __global__ void __launch_bounds__(128)
 populate_draw_kernel(FlowProgramDev P, PopulateArgs A) {
   extern __shared__ float4 smem4[];
-  __shared__ double red[16];
   float* Ws;
   float* bufs[4];
   const int BS = blockDim.x;
   carve_buffers(reinterpret_cast<float*>(smem4), P, BS, Ws, bufs);
   const int64_t ntiles = (A.n + BS - 1) / BS;
   const int D = P.D;
+  double vmax = -INFINITY, vcount = 0.0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row = tile * BS + threadIdx.x;
     float ss = 0.f;
@@ -308,8 +240,10 @@ populate_draw_kernel(FlowProgramDev P, PopulateArgs A) {
     const bool alive = !(A.r_max > 0.f) || (rad <= A.r_max);
     const float logj = run_program<ACT>(P, Ws, bufs, BS) + P.const_logdet;
     const float base_lp = -0.5f * ss - 0.5f * D * LOG_2PI;
-    populate_tail(A, D, BS, bufs[P.final_buf], row, alive, base_lp, logj, red);
+    const float* fin = bufs[P.final_buf];
+    populate_row(A, D, [&](int d) { return fin[d * BS]; }, row, alive, base_lp, logj, vmax, vcount);
   }
+  populate_publish(A, vmax, vcount);
 }
 
 // ----------------------------------------------------------------------------- accept + compact
@@ -442,20 +376,28 @@ accept_write_kernel(const double* __restrict__ x, const double* __restrict__ log
 // ----------------------------------------------------------------------------- launch helpers
 template <typename K>
 static int prep_kernel(K kernel, size_t smem) {
+  // opt in to > 48 KB dynamic shared memory (static shared memory counts
+  // against the 227 KB limit, so ask for what the launch needs, rounded up)
   static thread_local const void* done[16];
+  static thread_local size_t done_smem[16];
   static thread_local int ndone = 0;
+  int slot = -1;
   for (int i = 0; i < ndone; ++i)
-    if (done[i] == (const void*)kernel) return 0;
-  CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  if (ndone < 16) done[ndone++] = (const void*)kernel;
-  (void)smem;
+    if (done[i] == (const void*)kernel) slot = i;
+  if (slot >= 0 && done_smem[slot] >= smem) return 0;
+  CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (slot < 0 && ndone < 16) slot = ndone++;
+  if (slot >= 0) {
+    done[slot] = (const void*)kernel;
+    done_smem[slot] = smem;
+  }
   return 0;
 }
 
 static int pick_block(const FlowProgramDev& P, int& BS, size_t& smem) {
   for (int bs : {128, 64, 32}) {
     const size_t s = interp_smem_bytes(P, bs);
-    if (s <= 227 * 1024) {
+    if (s <= 226 * 1024) {
       BS = bs;
       smem = s;
       return 0;
@@ -499,20 +441,22 @@ static int launch_apply(nb200_flow* f, int direction, const float* in, float* ou
 
 extern "C" int nb200_flow_inverse(nb200_flow* f, const float* d_z, float* d_x, float* d_logj,
                                   float* d_logq, int64_t n, void* stream) {
+  if (n <= 0) return 0;
   if (!f || !d_z) return fail(1, "nb200_flow_inverse: bad arguments");
   return launch_apply(f, 1, d_z, d_x, d_logj, d_logq, n, (cudaStream_t)stream);
 }
 
 extern "C" int nb200_flow_forward(nb200_flow* f, const float* d_x, float* d_z, float* d_logj,
                                   float* d_logp, int64_t n, void* stream) {
+  if (n <= 0) return 0;
   if (!f || !d_x) return fail(1, "nb200_flow_forward: bad arguments");
   return launch_apply(f, 0, d_x, d_z, d_logj, d_logp, n, (cudaStream_t)stream);
 }
 
 extern "C" int nb200_sample_latent(float* d_z, int64_t n, int D, uint64_t seed,
                                    uint64_t row_offset, void* stream) {
-  if (!d_z || D < 1) return fail(1, "nb200_sample_latent: bad arguments");
   if (n <= 0) return 0;
+  if (!d_z || D < 1) return fail(1, "nb200_sample_latent: bad arguments");
   const int bs = 256;
   sample_latent_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
       d_z, n, D, seed, row_offset);

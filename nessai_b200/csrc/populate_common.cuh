@@ -1,0 +1,88 @@
+// Per-row tail of one populate turn, shared by the generic and the tcgen05 kernels:
+// float64 rescale + prior bounds + log-weights, exactly the numpy-side arithmetic of
+// /root/reference/src/nessai/proposal/flowproposal/flowproposal.py:345-389 and
+// base.py:1069-1098 for a diagonal (z-score / null) reparameterisation and a
+// uniform box prior.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace nb200 {
+
+struct PopulateArgs {
+  int64_t n;
+  uint64_t seed, row_offset;
+  float r_max, sqrt_t;
+  const double *scale, *shift, *lo, *hi;
+  double log_prior_const;  // NaN: prior added by the caller
+  double log_j_rescale;    // sum log|scale|
+  double* x;
+  double* logq;
+  double* logw;
+  float* z;
+  double* stats;  // {max log_w, n_valid}
+};
+
+__device__ __forceinline__ void atomic_max_double(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if (!(v > __longlong_as_double(assumed))) break;
+    old = atomicCAS(a, assumed, __double_as_longlong(v));
+  } while (assumed != old);
+}
+
+// xp(d): the row's x' (fp32) for feature d.  Updates the thread-local running
+// max / count; returns nothing (outputs written to global memory).
+template <int MAXD = 0, typename XP>
+__device__ __forceinline__ void populate_row(const PopulateArgs& A, int D, XP xp, int64_t row,
+                                             bool alive, float base_lp, float logj, double& vmax,
+                                             double& vcount) {
+  if (row >= A.n) return;
+  bool inb = true;
+  if (MAXD > 0) {  // compile-time trip count: xp(d) may index registers
+#pragma unroll
+    for (int d = 0; d < (MAXD > 0 ? MAXD : 1); ++d) {
+      if (d < D) {
+        const double xv = (double)xp(d) * A.scale[d] + A.shift[d];
+        A.x[row * D + d] = xv;
+        inb = inb && !(xv < A.lo[d]) && !(xv > A.hi[d]);
+      }
+    }
+  } else {
+    for (int d = 0; d < D; ++d) {
+      const double xv = (double)xp(d) * A.scale[d] + A.shift[d];
+      A.x[row * D + d] = xv;
+      inb = inb && !(xv < A.lo[d]) && !(xv > A.hi[d]);
+    }
+  }
+  double logq = NAN, logw = NAN;
+  bool ok = alive;
+  if (ok) {
+    logq = (double)base_lp - (double)D * log((double)A.sqrt_t) - (double)logj - A.log_j_rescale;
+    ok = isfinite(logq) && inb;
+  }
+  if (ok) {
+    logw = (isnan(A.log_prior_const) ? 0.0 : A.log_prior_const) - logq;
+    vmax = fmax(vmax, logw);
+    vcount += 1.0;
+  }
+  A.logq[row] = ok ? logq : NAN;
+  A.logw[row] = ok ? logw : NAN;
+}
+
+// warp-reduce the thread-local (max, count) and publish with one atomic per warp
+__device__ __forceinline__ void populate_publish(const PopulateArgs& A, double vmax,
+                                                 double vcount) {
+  for (int o = 16; o > 0; o >>= 1) {
+    vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    vcount += __shfl_xor_sync(0xffffffffu, vcount, o);
+  }
+  if ((threadIdx.x & 31) == 0 && vcount > 0) {
+    atomic_max_double(A.stats, vmax);
+    atomicAdd(A.stats + 1, vcount);
+  }
+}
+
+}  // namespace nb200

@@ -126,7 +126,7 @@ def test_weights_roundtrip_and_pickle(tmp_path):
     fm2.load_weights(f)
     np.testing.assert_array_equal(fm2.inverse(g["z"])[0], fm.inverse(g["z"])[0])
     state = pickle.loads(pickle.dumps(fm))
-    assert state.initialised is False and not hasattr(state, "model")
+    assert state.initialised is False and "model" not in state.__dict__ and "_optimiser" not in state.__dict__
 
 
 def test_training_tracks_reference_history(tmp_path):

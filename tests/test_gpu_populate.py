@@ -134,6 +134,8 @@ def test_host_prior_path_matches_device_prior(tmp_path):
     p1, model, *_ = make_proposal("c1_realnvp_2d", tmp_path, pool, device_prior="auto")
     p2, *_ = make_proposal("c1_realnvp_2d", tmp_path, pool, device_prior=False)
     w = None
+    p1._get_engine().seed = 1234
+    p2._get_engine().seed = 1234
     p1.populate(w, n_samples=pool, max_samples=pool)
     p2.populate(w, n_samples=pool, max_samples=pool)
     assert p1._log_prior_const is not None and p2._log_prior_const is None
