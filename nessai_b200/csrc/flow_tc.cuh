@@ -1,18 +1,19 @@
 // tcgen05 / TMEM kernel for the headline flow shape: RealNVP with an MLP
-// conditioner  d_id -> 64 -> 64 -> 2*d_tr  (ReLU), D <= 16, up to 4 coupling layers.
+// conditioner  d_id -> 64 -> 64 -> 2*d_tr  (ReLU), D <= 16, up to 8 coupling layers.
 //
 // Per 128-row tile one thread owns one row (TMEM lane == row).  The three
 // conditioner GEMMs of every coupling layer run on the 5th-gen tensor cores:
-//   A (activations)  : shared memory, K-major no-swizzle canonical layout, written by
-//                      the row's own thread as bf16 hi/lo halves (split-bf16: the
-//                      products hi*Whi + lo*Whi + hi*Wlo recover ~16 mantissa bits,
-//                      fp32-grade parity with the reference's fp32 CPU flow)
-//   B (weights)      : shared memory, resident for the whole kernel (all layers)
+//   A (activations)  : TENSOR MEMORY (tcgen05.mma with the A operand in TMEM), written
+//                      by the row's own thread with tcgen05.st as bf16 hi/lo halves
+//                      (split-bf16: hi*Whi + lo*Whi + hi*Wlo recovers ~16 mantissa
+//                      bits -> fp32-grade parity with the reference's fp32 CPU flow)
+//   B (weights)      : shared memory (K-major, no-swizzle canonical layout), resident
+//                      for the whole kernel, all layers
 //   D (accumulator)  : TMEM, fp32, read back with tcgen05.ld by the row's thread
-// Biases ride in the GEMM as an extra K column (A holds a constant 1).
-// Two 128-thread epilogue groups work on two tiles at once, each with its own
-// single-thread MMA issuer warp, so one group's tensor-core time hides behind the
-// other group's CUDA-core epilogue (ReLU + split, coupling, 16x16 affine).
+// Activations never touch shared memory, so TC_NG tiles are in flight per SM (one
+// 128-thread epilogue group + one single-thread MMA issuer warp each, 128 TMEM
+// columns per group): one group's tensor-core and barrier latency hides behind the
+// other groups' CUDA-core epilogues (ReLU + split, coupling, 16x16 affine).
 //
 // Replaces, for this shape, the generic interpreter in flow_interp.cuh -- i.e. the
 // reference's NFlow.inverse / forward (flows/base.py:209-221) over nflows'
@@ -35,27 +36,32 @@ namespace nb200 {
 constexpr int TC_H = 64;            // conditioner width
 constexpr int TC_DP = 16;           // padded feature count (registers per row)
 constexpr int TC_N3 = 16;           // padded 2*d_tr
-constexpr int TC_K2 = TC_H + 16;    // hidden K plus the bias k-step
-constexpr int TC_MAXL = 4;
-constexpr int TC_W1_BYTES = TC_H * 16 * 2;            // 2 chunks x (64 rows x 16 B)
-constexpr int TC_W2_BYTES = TC_H * 16 * (TC_K2 / 8);  // 10 chunks x 1 KB
-constexpr int TC_W3_BYTES = TC_N3 * 16 * (TC_K2 / 8); // 10 chunks x 256 B
-constexpr int TC_LAYER_BYTES = 2 * (TC_W1_BYTES + TC_W2_BYTES + TC_W3_BYTES);  // hi + lo
+constexpr int TC_TR0 = 8;           // register slot of the first transformed feature
+constexpr int TC_MAXL = 8;
+constexpr int TC_W1_BYTES = TC_H * 16 * 2;            // 2 K-chunks x (64 rows x 16 B); bias at k = 8
+constexpr int TC_W2_BYTES = TC_H * 16 * (TC_H / 8);   // 8 chunks x 1 KB
+constexpr int TC_W3_BYTES = TC_N3 * 16 * (TC_H / 8);  // 8 chunks x 256 B
+constexpr int TC_BIAS_BYTES = (TC_H + TC_N3) * 4;     // fp32 b2[64], b3[16]
+constexpr int TC_LAYER_BYTES = 2 * (TC_W1_BYTES + TC_W2_BYTES + TC_W3_BYTES) + TC_BIAS_BYTES;
 constexpr int TC_OFF_W1HI = 0;
 constexpr int TC_OFF_W1LO = TC_W1_BYTES;
 constexpr int TC_OFF_W2HI = 2 * TC_W1_BYTES;
 constexpr int TC_OFF_W2LO = TC_OFF_W2HI + TC_W2_BYTES;
 constexpr int TC_OFF_W3HI = TC_OFF_W2LO + TC_W2_BYTES;
 constexpr int TC_OFF_W3LO = TC_OFF_W3HI + TC_W3_BYTES;
+constexpr int TC_OFF_BIAS = TC_OFF_W3LO + TC_W3_BYTES;
 constexpr int TC_AFF_BYTES = (TC_DP * TC_DP + TC_DP) * 4;
-// per epilogue group A-operand buffers (128 rows)
-constexpr int TC_A1_BYTES = 2 * 2048;             // 2 chunks (features 0..7 | constant bias chunk)
-constexpr int TC_TR0 = 8;                         // register slot of the first transformed feature
-constexpr int TC_A2HI_BYTES = (TC_K2 / 8) * 2048; // 10 chunks (8 data, bias chunk, zero chunk)
-constexpr int TC_A2LO_BYTES = (TC_H / 8) * 2048;  // 8 chunks
-constexpr int TC_GROUP_BYTES = 2 * TC_A1_BYTES + TC_A2HI_BYTES + TC_A2LO_BYTES;
-constexpr int TC_NG = 2;
+// TMEM columns of one epilogue group (one 128-row tile in flight)
+constexpr int TC_COLS = 128;
+constexpr int TC_COL_D = 0;     // accumulator, 64 fp32 columns
+constexpr int TC_COL_AH = 64;   // activations hi: 64 bf16 = 32 columns (A1 hi aliases the first 8)
+constexpr int TC_COL_AL = 96;   // activations lo
+#ifndef NB200_TC_NG
+#define NB200_TC_NG 4
+#endif
+constexpr int TC_NG = NB200_TC_NG;
 constexpr int TC_THREADS = TC_NG * 128 + TC_NG * 32;
+constexpr int TC_TMEM_COLS = (TC_NG * TC_COLS <= 128) ? 128 : (TC_NG * TC_COLS <= 256 ? 256 : 512);
 
 struct TcProgram {
   bool valid = false;
@@ -171,13 +177,14 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
     for (int n = 0; n < TC_H; ++n) {
       for (int k = 0; k < TC_H; ++k)
         tc_put(lb + TC_OFF_W2HI, lb + TC_OFF_W2LO, TC_H, n, k, blob[b.w_off + k * b.Npad + n]);
-      tc_put(lb + TC_OFF_W2HI, lb + TC_OFF_W2LO, TC_H, n, TC_H, blob[b.b_off + n]);
     }
     for (int n = 0; n < c.N; ++n) {
       for (int k = 0; k < TC_H; ++k)
         tc_put(lb + TC_OFF_W3HI, lb + TC_OFF_W3LO, TC_N3, n, k, blob[c.w_off + k * c.Npad + n]);
-      tc_put(lb + TC_OFF_W3HI, lb + TC_OFF_W3LO, TC_N3, n, TC_H, blob[c.b_off + n]);
     }
+    float* bias = reinterpret_cast<float*>(lb + TC_OFF_BIAS);
+    for (int n = 0; n < TC_H; ++n) bias[n] = blob[b.b_off + n];
+    for (int n = 0; n < c.N; ++n) bias[TC_H + n] = blob[c.b_off + n];
   }
   // Affines, re-laid-out to the kernel's register slots: inside coupling layer l the
   // identity features live in slots [0, d_id) and the transformed ones in
@@ -248,13 +255,14 @@ __host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
-                                       uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem desc]   (A operand in tensor memory)
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -271,8 +279,23 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// pin the loaded registers behind the preceding tcgen05.wait::ld (no instructions)
+__device__ __forceinline__ void tc_pin16(uint32_t (&r)[16]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]),
+               "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]),
+               "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])::"memory");
 }
 // split two fp32 into packed bf16x2 hi (truncated) and lo (remainder, rounded);
 // element `a` goes to the low half-word.  RELU clamps negatives of both parts.
@@ -290,29 +313,37 @@ __device__ __forceinline__ void tc_split2(float a, float b, uint32_t& hi, uint32
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 
-// hidden-layer epilogue: 64 accumulator columns -> ReLU -> split -> A2 hi/lo (row t)
-__device__ __forceinline__ void tc_hidden_epilogue(uint32_t taddr, uint8_t* a2hi, uint8_t* a2lo,
-                                                   int t) {
+// hidden-layer epilogue: 64 accumulator columns (+ bias) -> ReLU -> split -> the
+// row's A operand in TMEM (hi: 32 columns, lo: 32 columns).  bias == nullptr when
+// the bias rode in the GEMM.
+__device__ __forceinline__ void tc_hidden_epilogue(uint32_t tg, const float* __restrict__ bias) {
+  uint32_t ra[16], rb[16];
+  tc_ld16(tg + TC_COL_D, ra);
+  tc_wait_ld();
+  tc_pin16(ra);
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    uint32_t r0[16], r1[16];
-    tc_ld16(taddr + half * 32, r0);
-    tc_ld16(taddr + half * 32 + 16, r1);
-    tc_wait_ld();
+  for (int q = 0; q < 4; ++q) {
+    uint32_t(&cur)[16] = (q & 1) ? rb : ra;
+    uint32_t(&nxt)[16] = (q & 1) ? ra : rb;
+    if (q < 3) tc_ld16(tg + TC_COL_D + 16 * (q + 1), nxt);  // in flight while `cur` is processed
+    uint32_t hi[8], lo[8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint32_t* r = (c < 2) ? r0 : r1;
-      const int o = (c & 1) * 8;
-      uint4 h, l;
-      tc_split2<true>(__uint_as_float(r[o + 0]), __uint_as_float(r[o + 1]), h.x, l.x);
-      tc_split2<true>(__uint_as_float(r[o + 2]), __uint_as_float(r[o + 3]), h.y, l.y);
-      tc_split2<true>(__uint_as_float(r[o + 4]), __uint_as_float(r[o + 5]), h.z, l.z);
-      tc_split2<true>(__uint_as_float(r[o + 6]), __uint_as_float(r[o + 7]), h.w, l.w);
-      const int chunk = half * 4 + c;
-      *reinterpret_cast<uint4*>(a2hi + chunk * 2048 + t * 16) = h;
-      *reinterpret_cast<uint4*>(a2lo + chunk * 2048 + t * 16) = l;
+    for (int j = 0; j < 8; ++j) {
+      float v0 = __uint_as_float(cur[2 * j]), v1 = __uint_as_float(cur[2 * j + 1]);
+      if (bias) {
+        v0 += bias[16 * q + 2 * j];
+        v1 += bias[16 * q + 2 * j + 1];
+      }
+      tc_split2<true>(v0, v1, hi[j], lo[j]);
+    }
+    tc_st8(tg + TC_COL_AH + 8 * q, hi);
+    tc_st8(tg + TC_COL_AL + 8 * q, lo);
+    if (q < 3) {
+      tc_wait_ld();
+      tc_pin16(nxt);
     }
   }
+  tc_wait_st();
 }
 
 // h <- A h + b  with A k-major [16][16] fp32 in shared memory (warp-wide broadcasts)
@@ -352,46 +383,45 @@ struct TcIO {
 
 // The epilogue-group body shared by the apply and populate kernels: runs the whole
 // program for one row held in h[] and returns the row log|det J| (without const).
-__device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* img, uint8_t* gbuf,
-                                            uint32_t tmem_d, uint32_t bar_in, uint32_t bar_out,
-                                            uint32_t& ph_out, int t, float (&h)[TC_DP]) {
-  uint8_t* a1hi = gbuf;
-  uint8_t* a1lo = gbuf + TC_A1_BYTES;
-  uint8_t* a2hi = gbuf + 2 * TC_A1_BYTES;
-  uint8_t* a2lo = a2hi + TC_A2HI_BYTES;
+// tg: the group's TMEM base with this warp's lane quarter in the upper half-word.
+__device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* img, uint32_t tg,
+                                            uint32_t bar_in, uint32_t bar_out, uint32_t& ph_out,
+                                            float (&h)[TC_DP]) {
   const float* aff = reinterpret_cast<const float*>(img + (size_t)P.L * TC_LAYER_BYTES);
-  const uint32_t taddr = tmem_d + ((uint32_t)((t >> 5) * 32) << 16);
   float ld = 0.f;
   tc_affine(aff, h);
   for (int l = 0; l < P.L; ++l) {
     const int d_tr = P.d_tr[l];
-    // ---- E0: identity features (slots 0..7; unused slots are zero) -> A1 chunk 0
+    const float* bias = reinterpret_cast<const float*>(img + (size_t)l * TC_LAYER_BYTES + TC_OFF_BIAS);
+    // ---- E0: identity features (slots 0..7; unused slots are zero) + the constant 1
+    //      that carries the first-layer bias -> A1 (16 bf16 = 8 columns, hi and lo)
     {
-      uint4 hh, ll;
-      tc_split2<false>(h[0], h[1], hh.x, ll.x);
-      tc_split2<false>(h[2], h[3], hh.y, ll.y);
-      tc_split2<false>(h[4], h[5], hh.z, ll.z);
-      tc_split2<false>(h[6], h[7], hh.w, ll.w);
-      *reinterpret_cast<uint4*>(a1hi + t * 16) = hh;
-      *reinterpret_cast<uint4*>(a1lo + t * 16) = ll;
+      uint32_t hi[8], lo[8];
+      tc_split2<false>(h[0], h[1], hi[0], lo[0]);
+      tc_split2<false>(h[2], h[3], hi[1], lo[1]);
+      tc_split2<false>(h[4], h[5], hi[2], lo[2]);
+      tc_split2<false>(h[6], h[7], hi[3], lo[3]);
+      hi[4] = 0x00003F80u;  // element 8 == 1.0 (bf16)
+      hi[5] = hi[6] = hi[7] = 0u;
+      lo[4] = lo[5] = lo[6] = lo[7] = 0u;
+      tc_st8(tg + TC_COL_AH, hi);
+      tc_st8(tg + TC_COL_AL, lo);
+      tc_wait_st();
     }
-    tc_fence_async_smem();
     tc_fence_before();
     tc_mbar_arrive(bar_in);
-    // ---- E1: hidden layer 1
+    // ---- E1: hidden layer 1 (bias rode in GEMM1)
     tc_mbar_wait(bar_out, ph_out);
     ph_out ^= 1;
     tc_fence_after();
-    tc_hidden_epilogue(taddr, a2hi, a2lo, t);
-    tc_fence_async_smem();
+    tc_hidden_epilogue(tg, nullptr);
     tc_fence_before();
     tc_mbar_arrive(bar_in);
     // ---- E2: hidden layer 2
     tc_mbar_wait(bar_out, ph_out);
     ph_out ^= 1;
     tc_fence_after();
-    tc_hidden_epilogue(taddr, a2hi, a2lo, t);
-    tc_fence_async_smem();
+    tc_hidden_epilogue(tg, bias);
     tc_fence_before();
     tc_mbar_arrive(bar_in);
     // ---- E3: coupling on the transformed half, then the next affine
@@ -399,20 +429,22 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
     ph_out ^= 1;
     tc_fence_after();
     uint32_t r[16];
-    tc_ld16(taddr, r);
+    tc_ld16(tg + TC_COL_D, r);
     tc_wait_ld();
+    tc_pin16(r);
     tc_fence_before();
 #pragma unroll
     for (int f = 0; f < TC_N3 / 2; ++f) {
       if (f < d_tr) {
-        const float tt = __uint_as_float(r[2 * f]);
+        const float tt = __uint_as_float(r[2 * f]) + bias[TC_H + 2 * f];
         float s = 1.f, ls = 0.f;
         if (!P.additive) {
-          s = 1.f / (1.f + __expf(-(__uint_as_float(r[2 * f + 1]) + 2.f))) + 1e-3f;
+          const float u = __uint_as_float(r[2 * f + 1]) + bias[TC_H + 2 * f + 1];
+          s = __fdividef(1.f, 1.f + __expf(-(u + 2.f))) + 1e-3f;
           ls = __logf(s);
         }
         if (P.inverse) {
-          h[TC_TR0 + f] = (h[TC_TR0 + f] - tt) / s;
+          h[TC_TR0 + f] = __fdividef(h[TC_TR0 + f] - tt, s);
         } else {
           h[TC_TR0 + f] = fmaf(h[TC_TR0 + f], s, tt);
         }
@@ -425,12 +457,10 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
 }
 
 // MMA issuer (one elected thread) for one epilogue group
-__device__ __forceinline__ void tc_issuer(const TcParams& P, uint32_t img_s, uint32_t gbuf_s,
-                                          uint32_t tmem_d, uint32_t bar_in, uint32_t bar_out,
-                                          int64_t my_tiles) {
-  const uint32_t a1hi = gbuf_s, a1lo = gbuf_s + TC_A1_BYTES;
-  const uint32_t a2hi = gbuf_s + 2 * TC_A1_BYTES, a2lo = a2hi + TC_A2HI_BYTES;
+__device__ __forceinline__ void tc_issuer(const TcParams& P, uint32_t img_s, uint32_t tg,
+                                          uint32_t bar_in, uint32_t bar_out, int64_t my_tiles) {
   constexpr uint32_t ID64 = tc_idesc(128, TC_H), ID16 = tc_idesc(128, TC_N3);
+  const uint32_t d = tg + TC_COL_D, ah = tg + TC_COL_AH, al = tg + TC_COL_AL;
   uint32_t ph_in = 0;
   for (int64_t it = 0; it < my_tiles; ++it) {
     for (int l = 0; l < P.L; ++l) {
@@ -440,15 +470,14 @@ __device__ __forceinline__ void tc_issuer(const TcParams& P, uint32_t img_s, uin
       ph_in ^= 1;
       tc_fence_after();
       {
-        const uint64_t ah = tc_desc(a1hi, 2048, 128), al = tc_desc(a1lo, 2048, 128);
         const uint64_t bh = tc_desc(lb + TC_OFF_W1HI, TC_H * 16, 128);
         const uint64_t bl = tc_desc(lb + TC_OFF_W1LO, TC_H * 16, 128);
-        tc_mma(tmem_d, ah, bh, ID64, 0);
-        tc_mma(tmem_d, al, bh, ID64, 1);
-        tc_mma(tmem_d, ah, bl, ID64, 1);
+        tc_mma_ts(d, ah, bh, ID64, 0);
+        tc_mma_ts(d, al, bh, ID64, 1);
+        tc_mma_ts(d, ah, bl, ID64, 1);
       }
       tc_commit(bar_out);
-      // GEMM2: [128 x 80] x [80 x 64], GEMM3: [128 x 80] x [80 x 16]
+      // GEMM2: [128 x 64] x [64 x 64], GEMM3: [128 x 64] x [64 x 16]
 #pragma unroll 1
       for (int g3 = 0; g3 < 2; ++g3) {
         tc_mbar_wait(bar_in, ph_in);
@@ -459,16 +488,12 @@ __device__ __forceinline__ void tc_issuer(const TcParams& P, uint32_t img_s, uin
         const uint32_t nrows = g3 ? TC_N3 : TC_H;
         const uint32_t idesc = g3 ? ID16 : ID64;
 #pragma unroll
-        for (int ks = 0; ks < TC_K2 / 16; ++ks) {
-          const uint64_t ah = tc_desc(a2hi + ks * 4096, 2048, 128);
+        for (int ks = 0; ks < TC_H / 16; ++ks) {
           const uint64_t bh = tc_desc(whi + ks * 2 * nrows * 16, nrows * 16, 128);
           const uint64_t bl = tc_desc(wlo + ks * 2 * nrows * 16, nrows * 16, 128);
-          tc_mma(tmem_d, ah, bh, idesc, ks > 0);
-          if (ks < TC_H / 16) {
-            const uint64_t al = tc_desc(a2lo + ks * 4096, 2048, 128);
-            tc_mma(tmem_d, al, bh, idesc, 1);
-          }
-          tc_mma(tmem_d, ah, bl, idesc, 1);
+          tc_mma_ts(d, ah + 8 * ks, bh, idesc, ks > 0);
+          tc_mma_ts(d, al + 8 * ks, bh, idesc, 1);
+          tc_mma_ts(d, ah + 8 * ks, bl, idesc, 1);
         }
         tc_commit(bar_out);
       }
@@ -480,34 +505,22 @@ struct TcShared {
   uint64_t bar_in[TC_NG];
   uint64_t bar_out[TC_NG];
   uint32_t tmem_base;
+  uint32_t pad;
+  double cst[4][TC_DP];  // populate: scale, shift, lo, hi
 };
 
 __device__ __forceinline__ size_t tc_image_pad(int image_bytes) {
   return ((size_t)image_bytes + 1023) & ~(size_t)1023;
 }
 
-// common prologue: weights -> smem, constant chunks, barriers, TMEM
-__device__ __forceinline__ void tc_prologue(const TcParams& P, uint8_t* smem, TcShared*& sh,
-                                            uint8_t*& gbufs) {
-  const size_t ipad = tc_image_pad(P.image_bytes);
-  gbufs = smem + ipad;
-  sh = reinterpret_cast<TcShared*>(gbufs + TC_NG * TC_GROUP_BYTES);
+// common prologue: weights -> smem, barriers, TMEM
+__device__ __forceinline__ void tc_prologue(const TcParams& P, uint8_t* smem, TcShared*& sh) {
+  sh = reinterpret_cast<TcShared*>(smem + tc_image_pad(P.image_bytes));
   const int tid = threadIdx.x;
   {
     const uint4* src = reinterpret_cast<const uint4*>(P.image);
     uint4* dst = reinterpret_cast<uint4*>(smem);
     for (int i = tid; i < P.image_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
-  }
-  // constant operand chunks: A1 chunk 1 and A2hi chunk 8 hold the bias column
-  // (first element == 1.0, bf16 0x3F80); A1lo chunk 1 and A2hi chunk 9 are zeros
-  for (int i = tid; i < TC_NG * 128; i += blockDim.x) {
-    const int g = i >> 7, j = i & 127;
-    uint8_t* gb = gbufs + g * TC_GROUP_BYTES;
-    const uint4 one = make_uint4(0x00003F80u, 0u, 0u, 0u), zero = make_uint4(0u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(gb + 2048 + j * 16) = one;                                   // A1hi chunk 1
-    *reinterpret_cast<uint4*>(gb + TC_A1_BYTES + 2048 + j * 16) = zero;                    // A1lo chunk 1
-    *reinterpret_cast<uint4*>(gb + 2 * TC_A1_BYTES + 8 * 2048 + j * 16) = one;             // A2hi chunk 8
-    *reinterpret_cast<uint4*>(gb + 2 * TC_A1_BYTES + 9 * 2048 + j * 16) = zero;            // A2hi chunk 9
   }
   if (tid == 0) {
     for (int g = 0; g < TC_NG; ++g) {
@@ -519,11 +532,11 @@ __device__ __forceinline__ void tc_prologue(const TcParams& P, uint8_t* smem, Tc
   if ((tid >> 5) == TC_NG * 4) {  // first issuer warp owns the TMEM allocation
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      tc_smem_u32(&sh->tmem_base)),
-                 "r"(128u)
+                 "r"((uint32_t)TC_TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  tc_fence_async_smem();
+  tc_fence_async_smem();  // weights were written with generic stores, the MMA reads them via the async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -535,13 +548,13 @@ __device__ __forceinline__ void tc_epilogue_end(TcShared* sh) {
   if ((threadIdx.x >> 5) == TC_NG * 4) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sh->tmem_base),
-                 "r"(128u)
+                 "r"((uint32_t)TC_TMEM_COLS)
                  : "memory");
   }
 }
 
 inline size_t tc_smem_bytes(int image_bytes) {
-  return (((size_t)image_bytes + 1023) & ~(size_t)1023) + TC_NG * TC_GROUP_BYTES + 64;
+  return (((size_t)image_bytes + 1023) & ~(size_t)1023) + sizeof(TcShared) + 64;
 }
 
 __device__ __forceinline__ int64_t tc_my_tiles(int64_t ntiles, int g) {
@@ -555,14 +568,13 @@ __device__ __forceinline__ int64_t tc_my_tiles(int64_t ntiles, int g) {
 __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P, TcIO io) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   TcShared* sh;
-  uint8_t* gbufs;
-  tc_prologue(P, tc_smem, sh, gbufs);
+  tc_prologue(P, tc_smem, sh);
   const int warp = threadIdx.x >> 5;
   const int64_t ntiles = (io.n + 127) / 128;
   const uint32_t tmem = sh->tmem_base;
   if (warp < TC_NG * 4) {
     const int g = warp >> 2, t = threadIdx.x & 127;
-    uint8_t* gbuf = gbufs + g * TC_GROUP_BYTES;
+    const uint32_t tg = tmem + g * TC_COLS + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t bar_in = tc_smem_u32(&sh->bar_in[g]), bar_out = tc_smem_u32(&sh->bar_out[g]);
     uint32_t ph_out = 0;
     const int64_t stride = (int64_t)gridDim.x * TC_NG;
@@ -576,8 +588,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P
         h[d] = (valid && d < P.D) ? __ldg(io.in + row * P.D + d) : 0.f;
         ss_in = fmaf(h[d], h[d], ss_in);
       }
-      const float ld = tc_run_row(P, tc_smem, gbuf, tmem + g * 64, bar_in, bar_out, ph_out, t, h) +
-                       P.const_logdet;
+      const float ld = tc_run_row(P, tc_smem, tg, bar_in, bar_out, ph_out, h) + P.const_logdet;
       float ss_out = 0.f;
 #pragma unroll
       for (int d = 0; d < TC_DP; ++d) {
@@ -597,8 +608,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P
   } else {
     const int g = warp - TC_NG * 4;
     if ((threadIdx.x & 31) == 0)
-      tc_issuer(P, tc_smem_u32(tc_smem), tc_smem_u32(gbufs + g * TC_GROUP_BYTES), tmem + g * 64,
-                tc_smem_u32(&sh->bar_in[g]), tc_smem_u32(&sh->bar_out[g]), tc_my_tiles(ntiles, g));
+      tc_issuer(P, tc_smem_u32(tc_smem), tmem + g * TC_COLS, tc_smem_u32(&sh->bar_in[g]),
+                tc_smem_u32(&sh->bar_out[g]), tc_my_tiles(ntiles, g));
     __syncwarp();
   }
   tc_epilogue_end(sh);
@@ -607,14 +618,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P
 __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParams P, PopulateArgs A) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   TcShared* sh;
-  uint8_t* gbufs;
-  tc_prologue(P, tc_smem, sh, gbufs);
+  tc_prologue(P, tc_smem, sh);
   const int warp = threadIdx.x >> 5;
   const int64_t ntiles = (A.n + 127) / 128;
   const uint32_t tmem = sh->tmem_base;
   if (warp < TC_NG * 4) {
     const int g = warp >> 2, t = threadIdx.x & 127;
-    uint8_t* gbuf = gbufs + g * TC_GROUP_BYTES;
+    const uint32_t tg = tmem + g * TC_COLS + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t bar_in = tc_smem_u32(&sh->bar_in[g]), bar_out = tc_smem_u32(&sh->bar_out[g]);
     uint32_t ph_out = 0;
     double vmax = -INFINITY, vcount = 0.0;
@@ -641,8 +651,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParam
       }
       const float rad = sqrtf(ss) * A.sqrt_t;
       const bool alive = !(A.r_max > 0.f) || (rad <= A.r_max);
-      const float logj = tc_run_row(P, tc_smem, gbuf, tmem + g * 64, bar_in, bar_out, ph_out, t, h) +
-                         P.const_logdet;
+      const float logj = tc_run_row(P, tc_smem, tg, bar_in, bar_out, ph_out, h) + P.const_logdet;
       const float base_lp = -0.5f * ss - 0.5f * P.D * TC_LOG_2PI;
       populate_row<TC_DP>(A, P.D, [&](int d) { return h[d]; }, row, alive, base_lp, logj, vmax,
                           vcount);
@@ -651,8 +660,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParam
   } else {
     const int g = warp - TC_NG * 4;
     if ((threadIdx.x & 31) == 0)
-      tc_issuer(P, tc_smem_u32(tc_smem), tc_smem_u32(gbufs + g * TC_GROUP_BYTES), tmem + g * 64,
-                tc_smem_u32(&sh->bar_in[g]), tc_smem_u32(&sh->bar_out[g]), tc_my_tiles(ntiles, g));
+      tc_issuer(P, tc_smem_u32(tc_smem), tmem + g * TC_COLS, tc_smem_u32(&sh->bar_in[g]),
+                tc_smem_u32(&sh->bar_out[g]), tc_my_tiles(ntiles, g));
     __syncwarp();
   }
   tc_epilogue_end(sh);
