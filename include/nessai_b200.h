@@ -73,7 +73,10 @@ int nb200_sample_latent(float* d_z, int64_t n, int D, uint64_t seed, uint64_t ro
  * (model.py:497-518) -> log_w = log_prior_const - log_q (base.py:1069-1098,
  * uniform box prior) -> running max of log_w over valid rows.
  *
- * d_scale, d_shift, d_lo, d_hi: float64[D] device.  Outputs: d_x float64[n*D],
+ * d_scale, d_shift, d_lo, d_hi: float64[D] device.  Outputs: d_xp float32[n*D] (the
+ * flow output x' BEFORE the rescale; x = (double)x' * scale + shift is formed in
+ * float64 for the bounds check here and again, identically, for the accepted
+ * rows in nb200_populate_accept, so dropped rows never cost a float64 write),
  * d_logq float64[n], d_logw float64[n] (NaN for dropped rows), d_z float32[n*D]
  * or NULL, d_stats: float64[2] = {max log_w (init -inf by caller), n_valid
  * (accumulated)}.  If log_prior_const is NaN, d_logw holds -log_q and the caller
@@ -81,19 +84,20 @@ int nb200_sample_latent(float* d_z, int64_t n, int D, uint64_t seed, uint64_t ro
 int nb200_populate_draw(nb200_flow* flow, int64_t n, uint64_t seed, uint64_t row_offset,
                         float r_max, float sqrt_temperature, const double* d_scale,
                         const double* d_shift, const double* d_lo, const double* d_hi,
-                        double log_prior_const, double* d_x, double* d_logq, double* d_logw,
+                        double log_prior_const, float* d_xp, double* d_logq, double* d_logw,
                         float* d_z, double* d_stats, void* stream);
 
 /* Rejection step + compaction, flowproposal/flowproposal.py:491-498:
  * accept = (log_w - max) > log(u), u ~ U(0,1) (Philox, `seed`, counter =
  * row_offset + row); accepted rows are written IN DRAW ORDER as structured
- * live-point records: each record starts as a copy of d_row_template
+ * live-point records (x = (double)x' * scale + shift): each record starts as a copy of d_row_template
  * (row_bytes, multiple of 4) and gets the D parameters (float64 at byte offsets
  * h_field_offsets[0..D-1]) and logP (float64 at h_field_offsets[D], skipped if
  * negative) overwritten.  At most `capacity` records are written to d_rows;
  * d_counts: int64[2] = {n_accepted (all), n_written}.  d_max points at the
  * (possibly all-reduced) maximum of log_w.  d_scratch: int64[ceil(n/1024)+1]. */
-int nb200_populate_accept(int64_t n, int D, const double* d_x, const double* d_logw,
+int nb200_populate_accept(int64_t n, int D, const float* d_xp, const double* d_scale,
+                          const double* d_shift, const double* d_logw,
                           const double* d_max, uint64_t seed, uint64_t row_offset,
                           double log_p_value, const uint8_t* d_row_template, int row_bytes,
                           const int32_t* h_field_offsets, uint8_t* d_rows, int64_t capacity,

@@ -89,9 +89,9 @@ _SIGS = {
     ),
     "nb200_populate_accept": (
         C.c_int,
-        [C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
-         C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
-         C.c_void_p, C.c_void_p, C.c_void_p],
+        [C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_uint64, C.c_uint64, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+         C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
 }
 

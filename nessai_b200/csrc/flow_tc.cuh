@@ -224,16 +224,16 @@ __device__ __forceinline__ void tc_mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
+  // try_wait suspends the thread in hardware (up to the tick hint) instead of spinning
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "TC_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra TC_DONE_%=;\n\t"
+      "bra TC_WAIT_%=;\n\t"
+      "TC_DONE_%=:\n\t}"
+      ::"r"(bar), "r"(parity), "r"(0x989680u)
+      : "memory");
 }
 __device__ __forceinline__ void tc_fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -617,7 +617,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P
 
 __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParams P, PopulateArgs A) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
-  TcShared* sh;
+  TcShared* sh = reinterpret_cast<TcShared*>(tc_smem + tc_image_pad(P.image_bytes));
+  if (threadIdx.x < 4 * TC_DP) {
+    const int which = threadIdx.x / TC_DP, d = threadIdx.x % TC_DP;
+    const double* src = which == 0 ? A.scale : which == 1 ? A.shift : which == 2 ? A.lo : A.hi;
+    sh->cst[which][d] = d < P.D ? src[d] : 0.0;
+  }
   tc_prologue(P, tc_smem, sh);
   const int warp = threadIdx.x >> 5;
   const int64_t ntiles = (A.n + 127) / 128;
@@ -628,6 +633,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParam
     const uint32_t bar_in = tc_smem_u32(&sh->bar_in[g]), bar_out = tc_smem_u32(&sh->bar_out[g]);
     uint32_t ph_out = 0;
     double vmax = -INFINITY, vcount = 0.0;
+    const double *c_scale = sh->cst[0], *c_shift = sh->cst[1], *c_lo = sh->cst[2], *c_hi = sh->cst[3];
     const int64_t stride = (int64_t)gridDim.x * TC_NG;
     for (int64_t tile = (int64_t)blockIdx.x * TC_NG + g; tile < ntiles; tile += stride) {
       const int64_t row = tile * 128 + t;
@@ -654,7 +660,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParam
       const float logj = tc_run_row(P, tc_smem, tg, bar_in, bar_out, ph_out, h) + P.const_logdet;
       const float base_lp = -0.5f * ss - 0.5f * P.D * TC_LOG_2PI;
       populate_row<TC_DP>(A, P.D, [&](int d) { return h[d]; }, row, alive, base_lp, logj, vmax,
-                          vcount);
+                          vcount, c_scale, c_shift, c_lo, c_hi);
     }
     populate_publish(A, vmax, vcount);
   } else {

@@ -241,7 +241,8 @@ populate_draw_kernel(FlowProgramDev P, PopulateArgs A) {
     const float logj = run_program<ACT>(P, Ws, bufs, BS) + P.const_logdet;
     const float base_lp = -0.5f * ss - 0.5f * D * LOG_2PI;
     const float* fin = bufs[P.final_buf];
-    populate_row(A, D, [&](int d) { return fin[d * BS]; }, row, alive, base_lp, logj, vmax, vcount);
+    populate_row(A, D, [&](int d) { return fin[d * BS]; }, row, alive, base_lp, logj, vmax, vcount,
+                 A.scale, A.shift, A.lo, A.hi);
   }
   populate_publish(A, vmax, vcount);
 }
@@ -328,7 +329,8 @@ struct RowFormat {
 };
 
 __global__ void __launch_bounds__(ACC_THREADS)
-accept_write_kernel(const double* __restrict__ x, const double* __restrict__ logw,
+accept_write_kernel(const float* __restrict__ xp, const double* __restrict__ scale,
+                    const double* __restrict__ shift, const double* __restrict__ logw,
                     const double* __restrict__ d_max, int64_t n, uint64_t seed,
                     uint64_t row_offset, const int64_t* __restrict__ scratch, double logp,
                     const uint32_t* __restrict__ tmpl, RowFormat F, uint32_t* __restrict__ rows,
@@ -357,9 +359,10 @@ accept_write_kernel(const double* __restrict__ x, const double* __restrict__ log
     if (idx < capacity) {
       uint32_t* dst = rows + (write_offset + idx) * F.row_words;
       for (int w = 0; w < F.row_words; ++w) dst[w] = tmpl[w];
-      const double* xr = x + (base + j) * F.D;
+      const float* xr = xp + (base + j) * F.D;
       for (int d = 0; d < F.D; ++d) {
-        const unsigned long long b = __double_as_longlong(xr[d]);
+        // same float64 arithmetic as the bounds check of the draw kernel
+        const unsigned long long b = __double_as_longlong((double)xr[d] * scale[d] + shift[d]);
         dst[F.off[d] / 4] = (uint32_t)b;
         dst[F.off[d] / 4 + 1] = (uint32_t)(b >> 32);
       }
@@ -468,9 +471,9 @@ extern "C" int nb200_sample_latent(float* d_z, int64_t n, int D, uint64_t seed,
 extern "C" int nb200_populate_draw(nb200_flow* f, int64_t n, uint64_t seed, uint64_t row_offset,
                                    float r_max, float sqrt_temperature, const double* d_scale,
                                    const double* d_shift, const double* d_lo, const double* d_hi,
-                                   double log_prior_const, double* d_x, double* d_logq,
+                                   double log_prior_const, float* d_xp, double* d_logq,
                                    double* d_logw, float* d_z, double* d_stats, void* stream) {
-  if (!f || !d_scale || !d_shift || !d_lo || !d_hi || !d_x || !d_logq || !d_logw || !d_stats)
+  if (!f || !d_scale || !d_shift || !d_lo || !d_hi || !d_xp || !d_logq || !d_logw || !d_stats)
     return fail(1, "nb200_populate_draw: bad arguments");
   DirProgram& p = f->dir[1];
   if (!p.d_ops) return fail(6, "inverse program not set");
@@ -488,7 +491,7 @@ extern "C" int nb200_populate_draw(nb200_flow* f, int64_t n, uint64_t seed, uint
   A.hi = d_hi;
   A.log_prior_const = log_prior_const;
   A.log_j_rescale = 0.0;  // filled on device by the kernels from d_scale (row constant)
-  A.x = d_x;
+  A.xp = d_xp;
   A.logq = d_logq;
   A.logw = d_logw;
   A.z = d_z;
@@ -529,13 +532,14 @@ extern "C" int nb200_populate_draw(nb200_flow* f, int64_t n, uint64_t seed, uint
   return 0;
 }
 
-extern "C" int nb200_populate_accept(int64_t n, int D, const double* d_x, const double* d_logw,
+extern "C" int nb200_populate_accept(int64_t n, int D, const float* d_xp, const double* d_scale,
+                                     const double* d_shift, const double* d_logw,
                                      const double* d_max, uint64_t seed, uint64_t row_offset,
                                      double log_p_value, const uint8_t* d_row_template,
                                      int row_bytes, const int32_t* h_field_offsets,
                                      uint8_t* d_rows, int64_t capacity, int64_t write_offset,
                                      int64_t* d_counts, int64_t* d_scratch, void* stream) {
-  if (!d_x || !d_logw || !d_max || !d_row_template || !h_field_offsets || !d_rows || !d_counts ||
+  if (!d_xp || !d_scale || !d_shift || !d_logw || !d_max || !d_row_template || !h_field_offsets || !d_rows || !d_counts ||
       !d_scratch)
     return fail(1, "nb200_populate_accept: bad arguments");
   if (row_bytes % 4 || row_bytes <= 0) return fail(1, "row_bytes must be a positive multiple of 4");
@@ -558,7 +562,7 @@ extern "C" int nb200_populate_accept(int64_t n, int D, const double* d_x, const 
                                                                  row_offset, d_scratch);
   accept_scan_kernel<<<1, 1024, 0, st>>>(d_scratch, nchunks, capacity, d_counts);
   accept_write_kernel<<<(unsigned)nchunks, ACC_THREADS, 0, st>>>(
-      d_x, d_logw, d_max, n, seed, row_offset, d_scratch, log_p_value,
+      d_xp, d_scale, d_shift, d_logw, d_max, n, seed, row_offset, d_scratch, log_p_value,
       reinterpret_cast<const uint32_t*>(d_row_template), F, reinterpret_cast<uint32_t*>(d_rows),
       capacity, write_offset);
   g_launches += 3;

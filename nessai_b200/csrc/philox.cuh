@@ -49,15 +49,15 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint64_t seed, uint64_
 // (0, 1]-open uniform from 32 random bits, fp32
 __device__ __forceinline__ float u01(uint32_t r) { return ((float)r + 0.5f) * 2.3283064365386963e-10f; }
 
-// two standard normals from two 32-bit words (Box-Muller, accurate logf/sincosf)
+// two standard normals from two 32-bit words: Box-Muller with an accurate log
+// (small radii matter) and the fast sin/cos on an angle in [-pi, pi)
 __device__ __forceinline__ void box_muller(uint32_t r0, uint32_t r1, float& n0, float& n1) {
   const float u1 = fminf(u01(r0), 1.0f);
   const float u2 = u01(r1);
   const float rad = sqrtf(-2.0f * logf(u1));
-  float s, c;
-  sincospif(2.0f * u2, &s, &c);
-  n0 = rad * c;
-  n1 = rad * s;
+  const float th = fmaf(6.283185307179586f, u2, -3.141592653589793f);
+  n0 = rad * __cosf(th);
+  n1 = rad * __sinf(th);
 }
 
 }  // namespace nb200

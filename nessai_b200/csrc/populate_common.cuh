@@ -16,7 +16,7 @@ struct PopulateArgs {
   const double *scale, *shift, *lo, *hi;
   double log_prior_const;  // NaN: prior added by the caller
   double log_j_rescale;    // sum log|scale|
-  double* x;
+  float* xp;      // x' (flow output, before the rescale), fp32 [n, D]
   double* logq;
   double* logw;
   float* z;
@@ -38,23 +38,29 @@ __device__ __forceinline__ void atomic_max_double(double* addr, double v) {
 template <int MAXD = 0, typename XP>
 __device__ __forceinline__ void populate_row(const PopulateArgs& A, int D, XP xp, int64_t row,
                                              bool alive, float base_lp, float logj, double& vmax,
-                                             double& vcount) {
+                                             double& vcount, const double* __restrict__ scale,
+                                             const double* __restrict__ shift,
+                                             const double* __restrict__ lo,
+                                             const double* __restrict__ hi) {
   if (row >= A.n) return;
+  // cst: scale | shift | lo | hi, each TC_DP-strided doubles (shared or global memory)
   bool inb = true;
   if (MAXD > 0) {  // compile-time trip count: xp(d) may index registers
 #pragma unroll
     for (int d = 0; d < (MAXD > 0 ? MAXD : 1); ++d) {
       if (d < D) {
-        const double xv = (double)xp(d) * A.scale[d] + A.shift[d];
-        A.x[row * D + d] = xv;
-        inb = inb && !(xv < A.lo[d]) && !(xv > A.hi[d]);
+        const float v = xp(d);
+        A.xp[row * D + d] = v;
+        const double xv = (double)v * scale[d] + shift[d];
+        inb = inb && !(xv < lo[d]) && !(xv > hi[d]);
       }
     }
   } else {
     for (int d = 0; d < D; ++d) {
-      const double xv = (double)xp(d) * A.scale[d] + A.shift[d];
-      A.x[row * D + d] = xv;
-      inb = inb && !(xv < A.lo[d]) && !(xv > A.hi[d]);
+      const float v = xp(d);
+      A.xp[row * D + d] = v;
+      const double xv = (double)v * scale[d] + shift[d];
+      inb = inb && !(xv < lo[d]) && !(xv > hi[d]);
     }
   }
   double logq = NAN, logw = NAN;

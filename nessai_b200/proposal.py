@@ -120,7 +120,7 @@ class PopulateEngine:
     def _ensure(self, n_local: int, capacity: int, want_z: bool):
         dev = self.device
         if n_local > self._cap:
-            self.d_x = torch.empty((n_local, self.D), dtype=torch.float64, device=dev)
+            self.d_xp = torch.empty((n_local, self.D), dtype=torch.float32, device=dev)
             self.d_logq = torch.empty(n_local, dtype=torch.float64, device=dev)
             self.d_logw = torch.empty(n_local, dtype=torch.float64, device=dev)
             self.d_scratch = torch.empty(n_local // 1024 + 2, dtype=torch.int64, device=dev)
@@ -176,13 +176,17 @@ class PopulateEngine:
                     self.model._handle, n_local, C.c_uint64(self._seed()),
                     C.c_uint64(self._turn_rows + start), self.r_max, self.sqrt_t,
                     _ptr(self.d_scale), _ptr(self.d_shift), _ptr(self.d_lo), _ptr(self.d_hi),
-                    lpc, _ptr(self.d_x), _ptr(self.d_logq), _ptr(self.d_logw),
+                    lpc, _ptr(self.d_xp), _ptr(self.d_logq), _ptr(self.d_logw),
                     _ptr(self.d_z) if want_z else None, _ptr(self.d_stats), _stream(),
                 ),
                 "nb200_populate_draw",
             )
         self._last = (n_local, start)
         return n_local
+
+    def physical_x(self, n: int) -> torch.Tensor:
+        """x = x' * scale + shift (float64) of the last draw, on the device."""
+        return self.d_xp[:n].to(torch.float64) * self.d_scale + self.d_shift
 
     def accept_turn(self, capacity_left: int, write_offset: int):
         """Rejection + compaction of the last draw.  Returns the number of rows
@@ -196,7 +200,8 @@ class PopulateEngine:
         with torch.cuda.device(self.device):
             _lib.check(
                 _lib.load().nb200_populate_accept(
-                    n_local, self.D, _ptr(self.d_x), _ptr(self.d_logw), _ptr(self.d_stats),
+                    n_local, self.D, _ptr(self.d_xp), _ptr(self.d_scale), _ptr(self.d_shift),
+                    _ptr(self.d_logw), _ptr(self.d_stats),
                     C.c_uint64(self._seed()), C.c_uint64(self._turn_rows + start), lp,
                     _ptr(self.d_template), self.row_bytes,
                     self.field_offsets.ctypes.data_as(C.c_void_p), _ptr(self.d_rows),
@@ -248,7 +253,7 @@ class PopulateEngine:
 
     def _apply_host_prior(self, host_prior):
         n_local, _ = self._last
-        x = self.d_x[:n_local].cpu().numpy()
+        x = self.physical_x(n_local).cpu().numpy()
         lw = self.d_logw[:n_local].cpu().numpy()
         ok = ~np.isnan(lw)
         xs = empty_structured_array(int(ok.sum()), dtype=self.row_dtype)

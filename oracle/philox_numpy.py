@@ -52,8 +52,8 @@ def latent_normals(seed, rows, D):
         r = rows_counter(seed, rows, d0 // 4, 0)
         u = [np.minimum(((w.astype(np.float32) + np.float32(0.5)) * np.float32(2.0**-32)), np.float32(1.0)).astype(np.float64) for w in r]
         rad0, rad1 = np.sqrt(-2 * np.log(u[0])), np.sqrt(-2 * np.log(u[2]))
-        v = [rad0 * np.cos(2 * np.pi * u[1]), rad0 * np.sin(2 * np.pi * u[1]),
-             rad1 * np.cos(2 * np.pi * u[3]), rad1 * np.sin(2 * np.pi * u[3])]
+        th0, th1 = 2 * np.pi * u[1] - np.pi, 2 * np.pi * u[3] - np.pi
+        v = [rad0 * np.cos(th0), rad0 * np.sin(th0), rad1 * np.cos(th1), rad1 * np.sin(th1)]
         for j in range(4):
             if d0 + j < D:
                 out[:, d0 + j] = v[j]

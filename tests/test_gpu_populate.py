@@ -60,7 +60,7 @@ def test_fused_turn_matches_numpy_restatement(name, tmp_path):
     eng._ensure(n, n, True)
     eng.draw_turn(n, want_z=True)
     z = eng.d_z[:n].cpu().numpy().astype(np.float64)
-    x = eng.d_x[:n].cpu().numpy()
+    x = eng.physical_x(n).cpu().numpy()
     logq = eng.d_logq[:n].cpu().numpy()
     logw = eng.d_logw[:n].cpu().numpy()
     stats = eng.d_stats.cpu().numpy()
@@ -100,7 +100,7 @@ def test_fused_turn_matches_numpy_restatement(name, tmp_path):
     assert rows.dtype == prop.x_dtype and len(rows) == counts[1]
     if not ambiguous.any():
         got = np.stack([rows[nm] for nm in model.names], axis=-1)
-        np.testing.assert_array_equal(got, x[acc_ref])  # draw order preserved, bit-exact copy
+        np.testing.assert_allclose(got, x[acc_ref], rtol=1e-12, atol=1e-14)  # draw order preserved (fma vs mul+add)
         assert np.all(rows["logP"] == -d * np.log(8.0)) and np.all(np.isnan(rows["logL"])) and np.all(rows["it"] == 0)
 
 
@@ -159,7 +159,7 @@ def test_full_size_turn_properties(tmp_path):
     assert float(lw[ok].max()) == stats[0]
     # the truncation keeps ~95 % of the latent draws (constant volume 0.95)
     assert 0.90 < stats[1] / pool <= 0.951 + 0.002
-    x = eng.d_x[:pool][ok]
+    x = eng.physical_x(pool)[ok]
     assert bool(((x >= -10) & (x <= 10)).all())
     c = eng.accept_turn(pool, 0).cpu().numpy()
     assert 0 < c[0] <= stats[1] and c[1] == min(c[0], pool)
