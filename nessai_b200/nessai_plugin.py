@@ -1,0 +1,160 @@
+"""Bindings into the real ``nessai`` package (plugin points P2 / P3).
+
+Importing this module requires ``nessai`` to be importable.  It defines
+
+* ``B200NessaiFlowProposal(nessai.proposal.FlowProposal)`` with
+  ``_FlowModelClass = B200FlowModel`` -- every flow evaluation of the unmodified
+  reference proposal (train / forward_pass / backward_pass / truncation rules)
+  runs on the CUDA kernels -- and a ``populate`` override that runs the fused
+  device loop whenever the configuration allows it (z-score / null
+  reparameterisation, latent-radius truncation only, no weight accumulation) and
+  otherwise defers to the reference's host loop;
+* the entry point ``nessai.proposals: b200flowproposal``, so
+  ``FlowSampler(model, flow_proposal_class="b200flowproposal")`` picks it up
+  through ``nessai.proposal.utils.get_flow_proposal_class``
+  (/root/reference/src/nessai/proposal/utils.py:110-155).
+"""
+
+from __future__ import annotations
+
+import datetime
+import logging
+
+import numpy as np
+from nessai import config as nessai_config
+from nessai.livepoint import empty_structured_array as nessai_empty_structured_array
+from nessai.proposal.flowproposal import FlowProposal
+from nessai.reparameterisations import NullReparameterisation, ScaleAndShift
+
+from .flowmodel import B200FlowModel
+from .proposal import PopulateEngine, detect_uniform_box_prior
+
+logger = logging.getLogger(__name__)
+
+
+class B200NessaiFlowProposal(FlowProposal):
+    """``FlowProposal`` whose flow and populate loop run on a B200.
+
+    Extra keyword argument ``device_prior``: ``"auto"`` (default) fuses the prior
+    into the device loop when the model's prior is a uniform box (checked
+    numerically, or declared with ``model.uniform_box_prior``); ``False`` always
+    evaluates ``model.batch_evaluate_log_prior`` on the host.
+    """
+
+    _FlowModelClass = B200FlowModel
+
+    def __init__(self, model, device_prior="auto", **kwargs):
+        super().__init__(model, **kwargs)
+        self.device_prior = device_prior
+        self._engine = None
+        self._log_prior_const = None
+
+    # ------------------------------------------------------------ eligibility
+    def _diagonal_rescaling(self):
+        """(scale, shift) in prime-parameter order if the rescaling is a diagonal
+        affine handled on the device, else None."""
+        if self.map_to_unit_hypercube or self.accumulate_weights:
+            return None
+        rep = self._reparameterisation
+        if rep is None:
+            return None
+        if list(self.prime_parameters) != [
+            p for r in rep.values() for p in r.output_parameters
+        ]:
+            return None
+        scale, shift, names = [], [], []
+        for r in rep.values():
+            if isinstance(r, ScaleAndShift):
+                if r.has_pre_rescaling or r.has_post_rescaling or not r.one_to_one:
+                    return None
+                for p in r.parameters:
+                    scale.append(float(r.scale[p]))
+                    shift.append(float(r.shift[p]) if r.shift else 0.0)
+                    names.append(p)
+            elif isinstance(r, NullReparameterisation):
+                for p in r.parameters:
+                    scale.append(1.0)
+                    shift.append(0.0)
+                    names.append(p)
+            else:
+                return None
+        if names != list(self.model.names):
+            return None
+        return np.asarray(scale), np.asarray(shift)
+
+    def _fused_radius(self):
+        rules = self._truncation_scheme.rules
+        if len(rules) != 1 or rules[0].name != "latent_radius":
+            return None
+        return rules[0]
+
+    # ---------------------------------------------------------------- populate
+    def populate(self, worst_point, n_samples=10000, plot=True, r=None, max_samples=1_000_000):
+        """flowproposal.py:391-534; the ``while n_accepted < n_samples`` loop runs
+        on the device when eligible."""
+        diag = self._diagonal_rescaling() if self.initialised else None
+        rule = self._fused_radius() if self.initialised else None
+        if diag is None or rule is None:
+            logger.debug("B200: configuration not eligible for the fused loop; using the host loop")
+            return super().populate(worst_point, n_samples=n_samples, plot=plot, r=r, max_samples=max_samples)
+        st = datetime.datetime.now()
+        if not self.initialised:
+            raise RuntimeError(
+                "Proposal has not been initialised. Try calling `initialise()` first."
+            )
+        self._truncation_scheme.prepare(self, worst_point, radius=r)
+        if self.indices:
+            logger.debug("Existing pool of samples is not empty. Discarding existing samples.")
+        self.indices = []
+        if self._engine is None or self._engine.flow is not self.flow:
+            self._engine = PopulateEngine(
+                self.flow, self.model.names, self.population_dtype,
+                row_template=nessai_empty_structured_array(1, dtype=self.population_dtype),
+            )
+            self._log_prior_const = (
+                detect_uniform_box_prior(self.model, self.rng)
+                if self.device_prior in ("auto", True, "uniform")
+                else None
+            )
+        lo = [self.model.bounds[n][0] for n in self.model.names]
+        hi = [self.model.bounds[n][1] for n in self.model.names]
+        t = self.latent_temperature
+        self._engine.configure(
+            diag[0], diag[1], lo, hi, self._log_prior_const, rule.threshold,
+            1.0 if t in (None, 1.0) else float(np.sqrt(t)),
+        )
+        host_prior = None if self._log_prior_const is not None else self.log_prior
+        rows, n_proposed, n_accepted = self._engine.run(
+            int(n_samples), int(self.drawsize), max_samples=max_samples, host_prior=host_prior
+        )
+        self.x = rows
+        self.samples = self.convert_to_samples(self.x, plot=plot) if host_prior is not None else rows
+        if self._plot_pool and plot:
+            self.plot_pool(self.samples)
+        self.population_time += datetime.datetime.now() - st
+        logger.debug("Evaluating log-likelihoods")
+        self.samples["logL"] = self.model.batch_evaluate_log_likelihood(self.samples)
+        if self.check_acceptance:
+            self.acceptance.append(self.compute_acceptance(worst_point["logL"]))
+        self.indices = self.rng.permutation(self.samples.size).tolist()
+        self.population_acceptance = n_accepted / n_proposed
+        self.populated_count += 1
+        self.populated = True
+        self._checked_population = False
+
+    def __getstate__(self):
+        state = super().__getstate__()
+        state.pop("_engine", None)
+        return state
+
+    def resume(self, model, flow_config, weights_file=None):
+        self._engine = None
+        super().resume(model, flow_config, weights_file=weights_file)
+
+
+def _check_dtype_surface():
+    """The device writes live-point records with nessai's own dtype defaults."""
+    assert nessai_config.livepoints.default_float_dtype == "f8"
+
+
+_check_dtype_surface()

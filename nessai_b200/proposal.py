@@ -86,10 +86,37 @@ def detect_uniform_box_prior(model, rng, n=256, atol=1e-9):
     return const
 
 
+def shard_rows(n_total: int, rank: int, world: int):
+    """Contiguous shard of a ``n_total``-row draw: ``(n_local, first_row)``."""
+    base, rem = divmod(int(n_total), world)
+    return base + (1 if rank < rem else 0), rank * base + min(rank, rem)
+
+
+def gather_records(local_rows: torch.Tensor, n_local: int, n_keep: int, row_bytes: int, group=None):
+    """All-gather the accepted live-point records (uint8, ``row_bytes`` each) of every
+    rank, rank-major, and keep the first ``n_keep``.  Works on any backend (NCCL on
+    GPUs; gloo in the CPU tests).  Returns a uint8 tensor on ``local_rows.device``."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    dev = local_rows.device
+    cnt = torch.tensor([int(n_local)], dtype=torch.int64, device=dev)
+    allc = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(allc, cnt, group=group)
+    allc = [int(c.item()) for c in allc]
+    mx = max(max(allc), 1)
+    send = torch.zeros(mx * row_bytes, dtype=torch.uint8, device=dev)
+    send[: n_local * row_bytes] = local_rows[: n_local * row_bytes]
+    recv = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(recv, send, group=group)
+    parts = [recv[r][: allc[r] * row_bytes] for r in range(world)]
+    return torch.cat(parts)[: n_keep * row_bytes], allc
+
+
 class PopulateEngine:
     """Fused populate turns on one GPU (optionally one rank of many)."""
 
-    def __init__(self, flow: B200FlowModel, names, row_dtype: np.dtype, group=None):
+    def __init__(self, flow: B200FlowModel, names, row_dtype: np.dtype, group=None, row_template=None):
         self.flow = flow
         self.model = flow.model
         self.device = self.model.device
@@ -107,7 +134,8 @@ class PopulateEngine:
                 raise NotImplementedError("live-point parameters must be float64")
         logp_off = self.row_dtype.fields["logP"][1] if "logP" in self.row_dtype.names else -1
         self.field_offsets = np.asarray(offs + [logp_off], dtype=np.int32)
-        tmpl = empty_structured_array(1, dtype=self.row_dtype)
+        tmpl = row_template if row_template is not None else empty_structured_array(1, dtype=self.row_dtype)
+        tmpl = np.ascontiguousarray(tmpl, dtype=self.row_dtype).reshape(1)
         self.d_template = torch.from_numpy(tmpl.view(np.uint8).copy()).to(self.device)
         self.group = group
         self.rank, self.world = _dist_info(group)
@@ -155,10 +183,7 @@ class PopulateEngine:
         return self.seed
 
     def _shard(self, n_total: int):
-        base, rem = divmod(n_total, self.world)
-        n_local = base + (1 if self.rank < rem else 0)
-        start = self.rank * base + min(self.rank, rem)
-        return n_local, start
+        return shard_rows(n_total, self.rank, self.world)
 
     # ------------------------------------------------------------------ turns
     def draw_turn(self, n_total: int, want_z: bool = False):
@@ -274,20 +299,7 @@ class PopulateEngine:
                 return empty_structured_array(0, dtype=self.row_dtype)
             host = self.d_rows[: n_local_written * rb].cpu().numpy()
             return host.view(self.row_dtype)
-        import torch.distributed as dist
-
-        cnt = torch.tensor([n_local_written], dtype=torch.int64, device=self.device)
-        allc = [torch.zeros_like(cnt) for _ in range(self.world)]
-        dist.all_gather(allc, cnt, group=self.group)
-        allc = [int(c.item()) for c in allc]
-        mx = max(max(allc), 1)
-        send = self.d_rows[: mx * rb] if self._rows_cap >= mx else torch.cat(
-            [self.d_rows, torch.zeros(mx * rb - self.d_rows.numel(), dtype=torch.uint8, device=self.device)]
-        )
-        recv = torch.empty(self.world * mx * rb, dtype=torch.uint8, device=self.device)
-        dist.all_gather_into_tensor(recv, send.contiguous(), group=self.group)
-        parts = [recv[r * mx * rb : r * mx * rb + allc[r] * rb] for r in range(self.world)]
-        full = torch.cat(parts)[: n_samples * rb]
+        full, _ = gather_records(self.d_rows, n_local_written, n_samples, rb, self.group)
         if not full.numel():
             return empty_structured_array(0, dtype=self.row_dtype)
         return full.cpu().numpy().view(self.row_dtype)

@@ -1,0 +1,46 @@
+"""Turn gpurun_out/ ncu artefacts into the tracked text summaries under profiles/."""
+import collections, csv, os, subprocess, sys
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(REPO, "profiles")
+G = os.path.join(REPO, "gpurun_out")
+
+def launches(path, dst, title):
+    rows = list(csv.reader(open(path, errors="replace")))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    h = rows[hi]; ki, vi = h.index("Kernel Name"), h.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in rows[hi + 1:]:
+        if len(r) > vi:
+            agg.setdefault(r[ki], []).append(float(r[vi].replace(",", "")))
+    tot = sum(sum(v) for v in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# {title}\n# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
+        f.write("kernel,launches,mean_us,total_us,share\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+            f.write(f"\"{k[:100]}\",{len(v)},{sum(v)/len(v)/1e3:.1f},{sum(v)/1e3:.1f},{sum(v)/tot:.4f}\n")
+
+def full(rep, dst, title, top=30):
+    a = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "ncu_summary.py"), rep], capture_output=True, text=True).stdout
+    b = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "ncu_source.py"), rep, str(top)], capture_output=True, text=True).stdout
+    with open(dst, "w") as f:
+        f.write(f"# {title}\n# ncu --set full --clock-control none --import-source on (one launch)\n\n## raw metrics\n{a}\n## top stalled SASS instructions (warp stall samples)\n{b}")
+
+os.makedirs(OUT, exist_ok=True)
+jobs = [
+    ("launches_r1_generic.csv", "r1_launches_generic_fp32.csv", launches, "bench.py step, generic fp32 kernel (before the tcgen05 kernel)"),
+    ("launches_r1_tc.csv", "r1_launches_tcgen05.csv", launches, "bench.py step, tcgen05 populate kernel"),
+    ("prof_r1_generic.ncu-rep", "r1_ncu_populate_generic_fp32.txt", full, "populate_draw_kernel<relu> (generic fp32 interpreter), 1e6 rows"),
+    ("prof_r1_tc_pop_v1.ncu-rep", "r1_ncu_populate_tcgen05_v1_smemA.txt", full, "flow_tc_populate_kernel v1 (A operand in shared memory, 2 groups), 1e6 rows"),
+    ("prof_r1_tc_pop_v2.ncu-rep", "r1_ncu_populate_tcgen05_v2_tmemA.txt", full, "flow_tc_populate_kernel v2 (A operand in TMEM, 4 groups), 1e6 rows"),
+    ("prof_r1_tc_pop_v3.ncu-rep", "r1_ncu_populate_tcgen05_v3.txt", full, "flow_tc_populate_kernel v3 (fp32 x' output, smem constants, suspended waits), 1e6 rows"),
+    ("prof_r1_tc_v2.ncu-rep", "r1_ncu_apply_tcgen05_v2.txt", full, "flow_tc_apply_kernel v2 (FlowModel.inverse, z supplied), 1e6 rows"),
+]
+for src, dst, fn, title in jobs:
+    p = os.path.join(G, src)
+    if os.path.exists(p):
+        fn(p, os.path.join(OUT, dst), title)
+        print("wrote", dst)
+for j in ("bench_r1_n1.json", "bench_r1_ref.json"):
+    p = os.path.join(G, j)
+    if os.path.exists(p):
+        open(os.path.join(OUT, j), "w").write(open(p).read())
