@@ -41,15 +41,23 @@ constexpr int TC_MAXL = 8;
 constexpr int TC_W1_BYTES = TC_H * 16 * 2;            // 2 K-chunks x (64 rows x 16 B); bias at k = 8
 constexpr int TC_W2_BYTES = TC_H * 16 * (TC_H / 8);   // 8 chunks x 1 KB
 constexpr int TC_W3_BYTES = TC_N3 * 16 * (TC_H / 8);  // 8 chunks x 256 B
-constexpr int TC_BIAS_BYTES = (TC_H + TC_N3) * 4;     // fp32 b2[64], b3[16]
-constexpr int TC_LAYER_BYTES = 2 * (TC_W1_BYTES + TC_W2_BYTES + TC_W3_BYTES) + TC_BIAS_BYTES;
+// biases of GEMM2 / GEMM3 as B operands of one extra K=16 step against a constant
+// "ones" A operand (element k = 0 is 1): D = ones x [b; 0] initialises the accumulator
+constexpr int TC_B2_BYTES = TC_H * 16 * 2;            // 2 chunks x (64 rows x 16 B)
+constexpr int TC_B3_BYTES = TC_N3 * 16 * 2;           // 2 chunks x (16 rows x 16 B)
+constexpr int TC_LAYER_BYTES =
+    2 * (TC_W1_BYTES + TC_W2_BYTES + TC_W3_BYTES + TC_B2_BYTES + TC_B3_BYTES);
+constexpr int TC_ONES_BYTES = 2 * 2048;               // A operand [128 x 16] bf16, shared by all groups
 constexpr int TC_OFF_W1HI = 0;
 constexpr int TC_OFF_W1LO = TC_W1_BYTES;
 constexpr int TC_OFF_W2HI = 2 * TC_W1_BYTES;
 constexpr int TC_OFF_W2LO = TC_OFF_W2HI + TC_W2_BYTES;
 constexpr int TC_OFF_W3HI = TC_OFF_W2LO + TC_W2_BYTES;
 constexpr int TC_OFF_W3LO = TC_OFF_W3HI + TC_W3_BYTES;
-constexpr int TC_OFF_BIAS = TC_OFF_W3LO + TC_W3_BYTES;
+constexpr int TC_OFF_B2HI = TC_OFF_W3LO + TC_W3_BYTES;
+constexpr int TC_OFF_B2LO = TC_OFF_B2HI + TC_B2_BYTES;
+constexpr int TC_OFF_B3HI = TC_OFF_B2LO + TC_B2_BYTES;
+constexpr int TC_OFF_B3LO = TC_OFF_B3HI + TC_B3_BYTES;
 constexpr int TC_AFF_BYTES = (TC_DP * TC_DP + TC_DP) * 4;
 // TMEM columns of one epilogue group (one 128-row tile in flight)
 constexpr int TC_COLS = 128;
@@ -161,8 +169,14 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
     t.d_id[l] = c.d_id;
     t.d_tr[l] = c.d_tr;
   }
-  const int bytes = L * TC_LAYER_BYTES + (L + 1) * TC_AFF_BYTES;
+  const int ones_off = L * TC_LAYER_BYTES + (L + 1) * TC_AFF_BYTES;
+  const int bytes = ones_off + TC_ONES_BYTES;
+  if (((bytes + 1023) & ~1023) + 1024 > 227 * 1024) return 0;  // does not fit: generic kernel
   std::vector<uint8_t> img((size_t)bytes, 0);
+  for (int m = 0; m < 128; ++m) {  // element (m, k = 0) = 1.0 (bf16 0x3F80)
+    const uint16_t one = 0x3F80;
+    memcpy(img.data() + ones_off + (size_t)m * 16, &one, 2);
+  }
   for (int l = 0; l < L; ++l) {
     uint8_t* lb = img.data() + (size_t)l * TC_LAYER_BYTES;
     const FlowOp& a = ops[1 + 4 * l];
@@ -182,9 +196,10 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
       for (int k = 0; k < TC_H; ++k)
         tc_put(lb + TC_OFF_W3HI, lb + TC_OFF_W3LO, TC_N3, n, k, blob[c.w_off + k * c.Npad + n]);
     }
-    float* bias = reinterpret_cast<float*>(lb + TC_OFF_BIAS);
-    for (int n = 0; n < TC_H; ++n) bias[n] = blob[b.b_off + n];
-    for (int n = 0; n < c.N; ++n) bias[TC_H + n] = blob[c.b_off + n];
+    for (int n = 0; n < TC_H; ++n)
+      tc_put(lb + TC_OFF_B2HI, lb + TC_OFF_B2LO, TC_H, n, 0, blob[b.b_off + n]);
+    for (int n = 0; n < c.N; ++n)
+      tc_put(lb + TC_OFF_B3HI, lb + TC_OFF_B3LO, TC_N3, n, 0, blob[c.b_off + n]);
   }
   // Affines, re-laid-out to the kernel's register slots: inside coupling layer l the
   // identity features live in slots [0, d_id) and the transformed ones in
@@ -255,6 +270,16 @@ __host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // D[tmem] (+)= A[tmem] * B[smem desc]   (A operand in tensor memory)
 __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
@@ -297,6 +322,23 @@ __device__ __forceinline__ void tc_pin16(uint32_t (&r)[16]) {
                "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]),
                "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])::"memory");
 }
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 issue two lanes per instruction)
+__device__ __forceinline__ void tc_fma2(float& d0, float& d1, float a0, float a1, float b0,
+                                        float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void tc_sub2(float& d0, float& d1, float a0, float a1, float b0,
+                                        float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "sub.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 // split two fp32 into packed bf16x2 hi (truncated) and lo (remainder, rounded);
 // element `a` goes to the low half-word.  RELU clamps negatives of both parts.
 template <bool RELU>
@@ -305,18 +347,17 @@ __device__ __forceinline__ void tc_split2(float a, float b, uint32_t& hi, uint32
     asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
   else
     asm("cvt.rz.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
-  const float ra = a - __uint_as_float(hi << 16);
-  const float rb = b - __uint_as_float(hi & 0xffff0000u);
+  float ra, rb;
+  tc_sub2(ra, rb, a, b, __uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
   if (RELU)
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
   else
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 
-// hidden-layer epilogue: 64 accumulator columns (+ bias) -> ReLU -> split -> the
-// row's A operand in TMEM (hi: 32 columns, lo: 32 columns).  bias == nullptr when
-// the bias rode in the GEMM.
-__device__ __forceinline__ void tc_hidden_epilogue(uint32_t tg, const float* __restrict__ bias) {
+// hidden-layer epilogue: 64 accumulator columns (bias already accumulated by the
+// GEMM) -> ReLU -> split -> the row's A operand in TMEM (hi: 32 columns, lo: 32).
+__device__ __forceinline__ void tc_hidden_epilogue(uint32_t tg) {
   uint32_t ra[16], rb[16];
   tc_ld16(tg + TC_COL_D, ra);
   tc_wait_ld();
@@ -329,12 +370,7 @@ __device__ __forceinline__ void tc_hidden_epilogue(uint32_t tg, const float* __r
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float v0 = __uint_as_float(cur[2 * j]), v1 = __uint_as_float(cur[2 * j + 1]);
-      if (bias) {
-        v0 += bias[16 * q + 2 * j];
-        v1 += bias[16 * q + 2 * j + 1];
-      }
-      tc_split2<true>(v0, v1, hi[j], lo[j]);
+      tc_split2<true>(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1]), hi[j], lo[j]);
     }
     tc_st8(tg + TC_COL_AH + 8 * q, hi);
     tc_st8(tg + TC_COL_AL + 8 * q, lo);
@@ -361,10 +397,8 @@ __device__ __forceinline__ void tc_affine(const float* __restrict__ A, float (&h
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float4 w = w4[j];
-      o[4 * j + 0] = fmaf(h[k], w.x, o[4 * j + 0]);
-      o[4 * j + 1] = fmaf(h[k], w.y, o[4 * j + 1]);
-      o[4 * j + 2] = fmaf(h[k], w.z, o[4 * j + 2]);
-      o[4 * j + 3] = fmaf(h[k], w.w, o[4 * j + 3]);
+      tc_fma2(o[4 * j + 0], o[4 * j + 1], w.x, w.y, h[k], h[k]);
+      tc_fma2(o[4 * j + 2], o[4 * j + 3], w.z, w.w, h[k], h[k]);
     }
   }
 #pragma unroll
@@ -392,7 +426,6 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
   tc_affine(aff, h);
   for (int l = 0; l < P.L; ++l) {
     const int d_tr = P.d_tr[l];
-    const float* bias = reinterpret_cast<const float*>(img + (size_t)l * TC_LAYER_BYTES + TC_OFF_BIAS);
     // ---- E0: identity features (slots 0..7; unused slots are zero) + the constant 1
     //      that carries the first-layer bias -> A1 (16 bf16 = 8 columns, hi and lo)
     {
@@ -414,14 +447,14 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
     tc_mbar_wait(bar_out, ph_out);
     ph_out ^= 1;
     tc_fence_after();
-    tc_hidden_epilogue(tg, nullptr);
+    tc_hidden_epilogue(tg);
     tc_fence_before();
     tc_mbar_arrive(bar_in);
     // ---- E2: hidden layer 2
     tc_mbar_wait(bar_out, ph_out);
     ph_out ^= 1;
     tc_fence_after();
-    tc_hidden_epilogue(tg, bias);
+    tc_hidden_epilogue(tg);
     tc_fence_before();
     tc_mbar_arrive(bar_in);
     // ---- E3: coupling on the transformed half, then the next affine
@@ -436,10 +469,10 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
 #pragma unroll
     for (int f = 0; f < TC_N3 / 2; ++f) {
       if (f < d_tr) {
-        const float tt = __uint_as_float(r[2 * f]) + bias[TC_H + 2 * f];
+        const float tt = __uint_as_float(r[2 * f]);
         float s = 1.f, ls = 0.f;
         if (!P.additive) {
-          const float u = __uint_as_float(r[2 * f + 1]) + bias[TC_H + 2 * f + 1];
+          const float u = __uint_as_float(r[2 * f + 1]);
           s = __fdividef(1.f, 1.f + __expf(-(u + 2.f))) + 1e-3f;
           ls = __logf(s);
         }
@@ -460,6 +493,7 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
 __device__ __forceinline__ void tc_issuer(const TcParams& P, uint32_t img_s, uint32_t tg,
                                           uint32_t bar_in, uint32_t bar_out, int64_t my_tiles) {
   constexpr uint32_t ID64 = tc_idesc(128, TC_H), ID16 = tc_idesc(128, TC_N3);
+  const uint64_t ones = tc_desc(img_s + P.L * TC_LAYER_BYTES + (P.L + 1) * TC_AFF_BYTES, 2048, 128);
   const uint32_t d = tg + TC_COL_D, ah = tg + TC_COL_AH, al = tg + TC_COL_AL;
   uint32_t ph_in = 0;
   for (int64_t it = 0; it < my_tiles; ++it) {
@@ -487,11 +521,14 @@ __device__ __forceinline__ void tc_issuer(const TcParams& P, uint32_t img_s, uin
         const uint32_t wlo = lb + (g3 ? TC_OFF_W3LO : TC_OFF_W2LO);
         const uint32_t nrows = g3 ? TC_N3 : TC_H;
         const uint32_t idesc = g3 ? ID16 : ID64;
+        // accumulator <- bias (hi + lo) through the constant ones operand
+        tc_mma_ss(d, ones, tc_desc(lb + (g3 ? TC_OFF_B3HI : TC_OFF_B2HI), nrows * 16, 128), idesc, 0);
+        tc_mma_ss(d, ones, tc_desc(lb + (g3 ? TC_OFF_B3LO : TC_OFF_B2LO), nrows * 16, 128), idesc, 1);
 #pragma unroll
         for (int ks = 0; ks < TC_H / 16; ++ks) {
           const uint64_t bh = tc_desc(whi + ks * 2 * nrows * 16, nrows * 16, 128);
           const uint64_t bl = tc_desc(wlo + ks * 2 * nrows * 16, nrows * 16, 128);
-          tc_mma_ts(d, ah + 8 * ks, bh, idesc, ks > 0);
+          tc_mma_ts(d, ah + 8 * ks, bh, idesc, 1);
           tc_mma_ts(d, al + 8 * ks, bh, idesc, 1);
           tc_mma_ts(d, ah + 8 * ks, bl, idesc, 1);
         }
@@ -507,6 +544,7 @@ struct TcShared {
   uint32_t tmem_base;
   uint32_t pad;
   double cst[4][TC_DP];  // populate: scale, shift, lo, hi
+  double log_const;      // populate: D log sqrt(T) + sum log|scale|
 };
 
 __device__ __forceinline__ size_t tc_image_pad(int image_bytes) {
@@ -623,6 +661,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParam
     const double* src = which == 0 ? A.scale : which == 1 ? A.shift : which == 2 ? A.lo : A.hi;
     sh->cst[which][d] = d < P.D ? src[d] : 0.0;
   }
+  if (threadIdx.x == 4 * TC_DP) sh->log_const = populate_log_const(A, P.D);
   tc_prologue(P, tc_smem, sh);
   const int warp = threadIdx.x >> 5;
   const int64_t ntiles = (A.n + 127) / 128;
@@ -634,6 +673,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParam
     uint32_t ph_out = 0;
     double vmax = -INFINITY, vcount = 0.0;
     const double *c_scale = sh->cst[0], *c_shift = sh->cst[1], *c_lo = sh->cst[2], *c_hi = sh->cst[3];
+    const double log_const = sh->log_const;
     const int64_t stride = (int64_t)gridDim.x * TC_NG;
     for (int64_t tile = (int64_t)blockIdx.x * TC_NG + g; tile < ntiles; tile += stride) {
       const int64_t row = tile * 128 + t;
@@ -660,7 +700,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParam
       const float logj = tc_run_row(P, tc_smem, tg, bar_in, bar_out, ph_out, h) + P.const_logdet;
       const float base_lp = -0.5f * ss - 0.5f * P.D * TC_LOG_2PI;
       populate_row<TC_DP>(A, P.D, [&](int d) { return h[d]; }, row, alive, base_lp, logj, vmax,
-                          vcount, c_scale, c_shift, c_lo, c_hi);
+                          vcount, c_scale, c_shift, c_lo, c_hi, log_const);
     }
     populate_publish(A, vmax, vcount);
   } else {

@@ -220,6 +220,10 @@ populate_draw_kernel(FlowProgramDev P, PopulateArgs A) {
   const int64_t ntiles = (A.n + BS - 1) / BS;
   const int D = P.D;
   double vmax = -INFINITY, vcount = 0.0;
+  __shared__ double s_log_const;
+  if (threadIdx.x == 0) s_log_const = populate_log_const(A, D);
+  __syncthreads();
+  const double log_const = s_log_const;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row = tile * BS + threadIdx.x;
     float ss = 0.f;
@@ -242,7 +246,7 @@ populate_draw_kernel(FlowProgramDev P, PopulateArgs A) {
     const float base_lp = -0.5f * ss - 0.5f * D * LOG_2PI;
     const float* fin = bufs[P.final_buf];
     populate_row(A, D, [&](int d) { return fin[d * BS]; }, row, alive, base_lp, logj, vmax, vcount,
-                 A.scale, A.shift, A.lo, A.hi);
+                 A.scale, A.shift, A.lo, A.hi, log_const);
   }
   populate_publish(A, vmax, vcount);
 }
@@ -490,22 +494,11 @@ extern "C" int nb200_populate_draw(nb200_flow* f, int64_t n, uint64_t seed, uint
   A.lo = d_lo;
   A.hi = d_hi;
   A.log_prior_const = log_prior_const;
-  A.log_j_rescale = 0.0;  // filled on device by the kernels from d_scale (row constant)
   A.xp = d_xp;
   A.logq = d_logq;
   A.logw = d_logw;
   A.z = d_z;
   A.stats = d_stats;
-  // sum log|scale| is a row constant: compute once on the host side of the call
-  {
-    double hs[1024];
-    if (f->D > 1024) return fail(1, "D too large");
-    CUDA_OK(cudaMemcpyAsync(hs, d_scale, sizeof(double) * f->D, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
-    double s = 0.0;
-    for (int d = 0; d < f->D; ++d) s += log(fabs(hs[d]));
-    A.log_j_rescale = s;
-  }
   if (p.tc.valid && tc_enabled()) {
     g_launches += 1;
     return tc_launch_populate(p.tc, A, f->num_sms, st)

@@ -15,7 +15,6 @@ struct PopulateArgs {
   float r_max, sqrt_t;
   const double *scale, *shift, *lo, *hi;
   double log_prior_const;  // NaN: prior added by the caller
-  double log_j_rescale;    // sum log|scale|
   float* xp;      // x' (flow output, before the rescale), fp32 [n, D]
   double* logq;
   double* logw;
@@ -41,7 +40,7 @@ __device__ __forceinline__ void populate_row(const PopulateArgs& A, int D, XP xp
                                              double& vcount, const double* __restrict__ scale,
                                              const double* __restrict__ shift,
                                              const double* __restrict__ lo,
-                                             const double* __restrict__ hi) {
+                                             const double* __restrict__ hi, double log_const) {
   if (row >= A.n) return;
   // cst: scale | shift | lo | hi, each TC_DP-strided doubles (shared or global memory)
   bool inb = true;
@@ -66,7 +65,7 @@ __device__ __forceinline__ void populate_row(const PopulateArgs& A, int D, XP xp
   double logq = NAN, logw = NAN;
   bool ok = alive;
   if (ok) {
-    logq = (double)base_lp - (double)D * log((double)A.sqrt_t) - (double)logj - A.log_j_rescale;
+    logq = (double)base_lp - (double)logj - log_const;
     ok = isfinite(logq) && inb;
   }
   if (ok) {
@@ -76,6 +75,14 @@ __device__ __forceinline__ void populate_row(const PopulateArgs& A, int D, XP xp
   }
   A.logq[row] = ok ? logq : NAN;
   A.logw[row] = ok ? logw : NAN;
+}
+
+// row constant of log_q: D log sqrt(T) (latent temperature, base.py:401-414) plus the
+// log-Jacobian of the diagonal rescale, sum log|scale| (rescale.py:263-291)
+__device__ __forceinline__ double populate_log_const(const PopulateArgs& A, int D) {
+  double s = (double)D * log((double)A.sqrt_t);
+  for (int d = 0; d < D; ++d) s += log(fabs(A.scale[d]));
+  return s;
 }
 
 // warp-reduce the thread-local (max, count) and publish with one atomic per warp

@@ -297,8 +297,13 @@ class PopulateEngine:
         if self.world == 1:
             if not n_local_written:
                 return empty_structured_array(0, dtype=self.row_dtype)
-            host = self.d_rows[: n_local_written * rb].cpu().numpy()
-            return host.view(self.row_dtype)
+            # pinned staging (torch's caching host allocator) -> one async D2H copy; the
+            # numpy array aliases the pinned block and keeps it alive
+            nbytes = n_local_written * rb
+            host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            host.copy_(self.d_rows[:nbytes], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            return host.numpy().view(self.row_dtype)
         full, _ = gather_records(self.d_rows, n_local_written, n_samples, rb, self.group)
         if not full.numel():
             return empty_structured_array(0, dtype=self.row_dtype)
