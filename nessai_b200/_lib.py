@@ -13,7 +13,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(_HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libnessai_b200.so")
+LIB_PATH = os.environ.get("NB200_LIB", os.path.join(LIB_DIR, "libnessai_b200.so"))  # NB200_LIB: experiment builds
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 

@@ -171,7 +171,7 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
   }
   const int ones_off = L * TC_LAYER_BYTES + (L + 1) * TC_AFF_BYTES;
   const int bytes = ones_off + TC_ONES_BYTES;
-  if (((bytes + 1023) & ~1023) + 1024 > 227 * 1024) return 0;  // does not fit: generic kernel
+  if (((bytes + 1023) & ~1023) + 4096 > 227 * 1024) return 0;  // does not fit: generic kernel
   std::vector<uint8_t> img((size_t)bytes, 0);
   for (int m = 0; m < 128; ++m) {  // element (m, k = 0) = 1.0 (bf16 0x3F80)
     const uint16_t one = 0x3F80;
@@ -370,7 +370,11 @@ __device__ __forceinline__ void tc_hidden_epilogue(uint32_t tg) {
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+#ifdef NB200_ABL_NO_SPLIT
+      hi[j] = cur[2 * j] & 0xffff0000u; lo[j] = cur[2 * j + 1];
+#else
       tc_split2<true>(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1]), hi[j], lo[j]);
+#endif
     }
     tc_st8(tg + TC_COL_AH + 8 * q, hi);
     tc_st8(tg + TC_COL_AL + 8 * q, lo);
@@ -471,7 +475,11 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
       if (f < d_tr) {
         const float tt = __uint_as_float(r[2 * f]);
         float s = 1.f, ls = 0.f;
+#ifdef NB200_ABL_NO_MUFU
+        if (false) {
+#else
         if (!P.additive) {
+#endif
           const float u = __uint_as_float(r[2 * f + 1]);
           s = __fdividef(1.f, 1.f + __expf(-(u + 2.f))) + 1e-3f;
           ls = __logf(s);
@@ -484,53 +492,95 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
         ld += P.inverse ? -ls : ls;
       }
     }
+#ifndef NB200_ABL_NO_AFFINE
     tc_affine(aff + (size_t)(l + 1) * (TC_AFF_BYTES / 4), h);
+#endif
   }
   return ld;
 }
 
+// B-operand descriptors of one coupling layer, precomputed once per CTA into shared
+// memory so the single issuing thread only loads and fires (building a descriptor is
+// ~8 dependent integer instructions; 31 of them per layer-step dominated the MMA
+// round-trip latency before).
+constexpr int TC_NDESC = 24;  // [0,1] W1 hi/lo; [2,3] b2 hi/lo; [4..7] W2hi; [8..11] W2lo;
+                              // [12,13] b3 hi/lo; [14..17] W3hi; [18..21] W3lo; [22] ones
+__device__ __forceinline__ void tc_build_desc_table(const TcParams& P, uint32_t img_s,
+                                                    uint64_t* table) {
+  for (int i = threadIdx.x; i < P.L * TC_NDESC; i += blockDim.x) {
+    const int l = i / TC_NDESC, j = i % TC_NDESC;
+    const uint32_t lb = img_s + l * TC_LAYER_BYTES;
+    uint64_t d = 0;
+    if (j == 0) d = tc_desc(lb + TC_OFF_W1HI, TC_H * 16, 128);
+    else if (j == 1) d = tc_desc(lb + TC_OFF_W1LO, TC_H * 16, 128);
+    else if (j == 2) d = tc_desc(lb + TC_OFF_B2HI, TC_H * 16, 128);
+    else if (j == 3) d = tc_desc(lb + TC_OFF_B2LO, TC_H * 16, 128);
+    else if (j < 8) d = tc_desc(lb + TC_OFF_W2HI + (j - 4) * 2 * TC_H * 16, TC_H * 16, 128);
+    else if (j < 12) d = tc_desc(lb + TC_OFF_W2LO + (j - 8) * 2 * TC_H * 16, TC_H * 16, 128);
+    else if (j == 12) d = tc_desc(lb + TC_OFF_B3HI, TC_N3 * 16, 128);
+    else if (j == 13) d = tc_desc(lb + TC_OFF_B3LO, TC_N3 * 16, 128);
+    else if (j < 18) d = tc_desc(lb + TC_OFF_W3HI + (j - 14) * 2 * TC_N3 * 16, TC_N3 * 16, 128);
+    else if (j < 22) d = tc_desc(lb + TC_OFF_W3LO + (j - 18) * 2 * TC_N3 * 16, TC_N3 * 16, 128);
+    else if (j == 22)
+      d = tc_desc(img_s + P.L * TC_LAYER_BYTES + (P.L + 1) * TC_AFF_BYTES, 2048, 128);
+    table[i] = d;
+  }
+}
+
 // MMA issuer (one elected thread) for one epilogue group
-__device__ __forceinline__ void tc_issuer(const TcParams& P, uint32_t img_s, uint32_t tg,
+__device__ __forceinline__ void tc_issuer(const TcParams& P, const uint64_t* table, uint32_t tg,
                                           uint32_t bar_in, uint32_t bar_out, int64_t my_tiles) {
   constexpr uint32_t ID64 = tc_idesc(128, TC_H), ID16 = tc_idesc(128, TC_N3);
-  const uint64_t ones = tc_desc(img_s + P.L * TC_LAYER_BYTES + (P.L + 1) * TC_AFF_BYTES, 2048, 128);
   const uint32_t d = tg + TC_COL_D, ah = tg + TC_COL_AH, al = tg + TC_COL_AL;
   uint32_t ph_in = 0;
   for (int64_t it = 0; it < my_tiles; ++it) {
     for (int l = 0; l < P.L; ++l) {
-      const uint32_t lb = img_s + l * TC_LAYER_BYTES;
+      const uint64_t* T = table + l * TC_NDESC;
+      const uint64_t ones = T[22];
       // GEMM1: [128 x 16] x [16 x 64]
-      tc_mbar_wait(bar_in, ph_in);
-      ph_in ^= 1;
-      tc_fence_after();
       {
-        const uint64_t bh = tc_desc(lb + TC_OFF_W1HI, TC_H * 16, 128);
-        const uint64_t bl = tc_desc(lb + TC_OFF_W1LO, TC_H * 16, 128);
-        tc_mma_ts(d, ah, bh, ID64, 0);
-        tc_mma_ts(d, al, bh, ID64, 1);
-        tc_mma_ts(d, ah, bl, ID64, 1);
-      }
-      tc_commit(bar_out);
-      // GEMM2: [128 x 64] x [64 x 64], GEMM3: [128 x 64] x [64 x 16]
-#pragma unroll 1
-      for (int g3 = 0; g3 < 2; ++g3) {
+        const uint64_t bh = T[0], bl = T[1];
         tc_mbar_wait(bar_in, ph_in);
         ph_in ^= 1;
         tc_fence_after();
-        const uint32_t whi = lb + (g3 ? TC_OFF_W3HI : TC_OFF_W2HI);
-        const uint32_t wlo = lb + (g3 ? TC_OFF_W3LO : TC_OFF_W2LO);
-        const uint32_t nrows = g3 ? TC_N3 : TC_H;
-        const uint32_t idesc = g3 ? ID16 : ID64;
-        // accumulator <- bias (hi + lo) through the constant ones operand
-        tc_mma_ss(d, ones, tc_desc(lb + (g3 ? TC_OFF_B3HI : TC_OFF_B2HI), nrows * 16, 128), idesc, 0);
-        tc_mma_ss(d, ones, tc_desc(lb + (g3 ? TC_OFF_B3LO : TC_OFF_B2LO), nrows * 16, 128), idesc, 1);
+        tc_mma_ts(d, ah, bh, ID64, 0);
+        tc_mma_ts(d, al, bh, ID64, 1);
+        tc_mma_ts(d, ah, bl, ID64, 1);
+        tc_commit(bar_out);
+      }
+      // GEMM2: bias + [128 x 64] x [64 x 64]
+      {
+        uint64_t w[10];
 #pragma unroll
-        for (int ks = 0; ks < TC_H / 16; ++ks) {
-          const uint64_t bh = tc_desc(whi + ks * 2 * nrows * 16, nrows * 16, 128);
-          const uint64_t bl = tc_desc(wlo + ks * 2 * nrows * 16, nrows * 16, 128);
-          tc_mma_ts(d, ah + 8 * ks, bh, idesc, 1);
-          tc_mma_ts(d, al + 8 * ks, bh, idesc, 1);
-          tc_mma_ts(d, ah + 8 * ks, bl, idesc, 1);
+        for (int j = 0; j < 10; ++j) w[j] = T[2 + j];
+        tc_mbar_wait(bar_in, ph_in);
+        ph_in ^= 1;
+        tc_fence_after();
+        tc_mma_ss(d, ones, w[0], ID64, 0);
+        tc_mma_ss(d, ones, w[1], ID64, 1);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          tc_mma_ts(d, ah + 8 * ks, w[2 + ks], ID64, 1);
+          tc_mma_ts(d, al + 8 * ks, w[2 + ks], ID64, 1);
+          tc_mma_ts(d, ah + 8 * ks, w[6 + ks], ID64, 1);
+        }
+        tc_commit(bar_out);
+      }
+      // GEMM3: bias + [128 x 64] x [64 x 16]
+      {
+        uint64_t w[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) w[j] = T[12 + j];
+        tc_mbar_wait(bar_in, ph_in);
+        ph_in ^= 1;
+        tc_fence_after();
+        tc_mma_ss(d, ones, w[0], ID16, 0);
+        tc_mma_ss(d, ones, w[1], ID16, 1);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          tc_mma_ts(d, ah + 8 * ks, w[2 + ks], ID16, 1);
+          tc_mma_ts(d, al + 8 * ks, w[2 + ks], ID16, 1);
+          tc_mma_ts(d, ah + 8 * ks, w[6 + ks], ID16, 1);
         }
         tc_commit(bar_out);
       }
@@ -545,6 +595,7 @@ struct TcShared {
   uint32_t pad;
   double cst[4][TC_DP];  // populate: scale, shift, lo, hi
   double log_const;      // populate: D log sqrt(T) + sum log|scale|
+  uint64_t desc[TC_MAXL * TC_NDESC];
 };
 
 __device__ __forceinline__ size_t tc_image_pad(int image_bytes) {
@@ -560,6 +611,7 @@ __device__ __forceinline__ void tc_prologue(const TcParams& P, uint8_t* smem, Tc
     uint4* dst = reinterpret_cast<uint4*>(smem);
     for (int i = tid; i < P.image_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
   }
+  tc_build_desc_table(P, tc_smem_u32(smem), sh->desc);
   if (tid == 0) {
     for (int g = 0; g < TC_NG; ++g) {
       tc_mbar_init(tc_smem_u32(&sh->bar_in[g]), 128);
@@ -646,7 +698,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P
   } else {
     const int g = warp - TC_NG * 4;
     if ((threadIdx.x & 31) == 0)
-      tc_issuer(P, tc_smem_u32(tc_smem), tmem + g * TC_COLS, tc_smem_u32(&sh->bar_in[g]),
+      tc_issuer(P, sh->desc, tmem + g * TC_COLS, tc_smem_u32(&sh->bar_in[g]),
                 tc_smem_u32(&sh->bar_out[g]), tc_my_tiles(ntiles, g));
     __syncwarp();
   }
@@ -706,7 +758,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParam
   } else {
     const int g = warp - TC_NG * 4;
     if ((threadIdx.x & 31) == 0)
-      tc_issuer(P, tc_smem_u32(tc_smem), tmem + g * TC_COLS, tc_smem_u32(&sh->bar_in[g]),
+      tc_issuer(P, sh->desc, tmem + g * TC_COLS, tc_smem_u32(&sh->bar_in[g]),
                 tc_smem_u32(&sh->bar_out[g]), tc_my_tiles(ntiles, g));
     __syncwarp();
   }
