@@ -104,6 +104,44 @@ int nb200_populate_accept(int64_t n, int D, const float* d_xp, const double* d_s
                           int64_t write_offset, int64_t* d_counts, int64_t* d_scratch,
                           void* stream);
 
+/* ------------------------------------------------------------------ training
+ * flowmodel/base.py:365-452 FlowModel._train: one EPOCH of optimisation steps on a
+ * RealNVP flow, fused: train-mode forward (batch-statistics BatchNorm with running-
+ * statistics EMA, uncached LU), loss = -mean(log_prob) (or the weighted loss of
+ * base.py:404-407 when d_w is given), backward, torch.nn.utils.clip_grad_norm_
+ * (base.py:439-443) and the optimiser update (base.py:104-135: adamw / adam / sgd).
+ *
+ * A trainer is built from a packed description of the architecture and of the flat
+ * parameter layout (nessai_b200/train_plan.py; struct TrPlan in csrc/train.cuh):
+ * h_plan int32[n_plan_ints], h_itab int32[n_itab] (permutations, mask index lists),
+ * h_reduce_idx int32[n_reduce] (parameters whose gradient is a plain sum over rows). */
+typedef struct nb200_trainer nb200_trainer;
+int nb200_trainer_create(nb200_trainer** out, const int32_t* h_plan, int n_plan_ints,
+                         const int32_t* h_itab, int n_itab, const int32_t* h_reduce_idx,
+                         int n_reduce);
+int nb200_trainer_destroy(nb200_trainer* trainer);
+/* Copy the gradient of the last step (n_params floats, after clipping) to d_out. */
+int nb200_trainer_copy_grad(nb200_trainer* trainer, float* d_out, void* stream);
+
+/* d_theta_p: trainable parameters (flat fp32, reference state_dict order), d_theta_b: float
+ * buffers (BatchNorm running statistics), d_m / d_v: Adam moments (same size as d_theta_p).
+ * Rows of batch k are d_x[d_perm[k*batch_size + i]] (d_perm NULL: in order), d_x row-major
+ * [n_rows][D].  opt_kind: 0 AdamW, 1 Adam (L2 decay), 2 SGD, -1 gradient only (no update).
+ * clip <= 0 disables clipping.  step0 = optimiser steps taken before this call (bias
+ * correction).  d_loss_sum[0] += loss of every batch (caller zeroes it); d_step_info
+ * (may be NULL): float[2 * n_batches] = {loss, gradient norm} per batch. */
+int nb200_train_epoch(nb200_trainer* trainer, float* d_theta_p, float* d_theta_b, float* d_m,
+                      float* d_v, const float* d_x, const float* d_w, const int64_t* d_perm,
+                      int64_t n_rows, int batch_size, int opt_kind, double lr, double beta1,
+                      double beta2, double eps, double weight_decay, double clip, int64_t step0,
+                      float* d_loss_sum, float* d_step_info, void* stream);
+
+/* flowmodel/base.py:454-523 FlowModel._validate: eval-mode (running statistics) loss of
+ * the UNFOLDED parameters, d_loss[0] = -sum(w log_prob)/sum(w); d_logp (may be NULL):
+ * per-row log_prob. */
+int nb200_eval_loss(nb200_trainer* trainer, float* d_theta_p, float* d_theta_b, const float* d_x,
+                    const float* d_w, int64_t n, float* d_loss, float* d_logp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

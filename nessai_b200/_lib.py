@@ -93,6 +93,23 @@ _SIGS = {
          C.c_uint64, C.c_uint64, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
          C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
+    "nb200_trainer_create": (
+        C.c_int,
+        [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int],
+    ),
+    "nb200_trainer_destroy": (C.c_int, [C.c_void_p]),
+    "nb200_trainer_copy_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nb200_train_epoch": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+         C.c_double, C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "nb200_eval_loss": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+         C.c_void_p, C.c_void_p],
+    ),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

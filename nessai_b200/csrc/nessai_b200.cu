@@ -562,3 +562,228 @@ extern "C" int nb200_populate_accept(int64_t n, int D, const float* d_xp, const 
   CUDA_OK(cudaGetLastError());
   return 0;
 }
+
+// ============================================================================= training
+#include "train.cuh"
+
+struct nb200_trainer {
+  TrPlan h_plan;
+  TrPlan* d_plan = nullptr;
+  int* d_itab = nullptr;
+  int* d_reduce = nullptr;
+  int num_sms = 0;
+  int cap_tiles = 0;
+  float *ws = nullptr, *dout0 = nullptr, *dout1 = nullptr, *ldrow = nullptr, *crow = nullptr;
+  float *stat_part = nullptr, *stats = nullptr, *s_part0 = nullptr, *s_part1 = nullptr;
+  float *wsum_part = nullptr, *loss_part = nullptr, *part = nullptr, *grad = nullptr;
+  float *gn_part = nullptr, *eval_part = nullptr;
+  float* stat_n = nullptr;
+  size_t smem_fwd = 0, smem_bwd = 0;
+};
+
+static void trainer_free_rows(nb200_trainer* t) {
+  cudaFree(t->ws), cudaFree(t->dout0), cudaFree(t->dout1), cudaFree(t->ldrow), cudaFree(t->crow);
+  t->ws = t->dout0 = t->dout1 = t->ldrow = t->crow = nullptr;
+  t->cap_tiles = 0;
+}
+
+extern "C" int nb200_trainer_destroy(nb200_trainer* t) {
+  if (!t) return 0;
+  trainer_free_rows(t);
+  cudaFree(t->d_plan), cudaFree(t->d_itab), cudaFree(t->d_reduce);
+  cudaFree(t->stat_part), cudaFree(t->stats), cudaFree(t->s_part0), cudaFree(t->s_part1);
+  cudaFree(t->wsum_part), cudaFree(t->loss_part), cudaFree(t->part), cudaFree(t->grad);
+  cudaFree(t->gn_part), cudaFree(t->eval_part), cudaFree(t->stat_n);
+  delete t;
+  return 0;
+}
+
+extern "C" int nb200_trainer_create(nb200_trainer** out, const int32_t* h_plan, int n_plan_ints,
+                                    const int32_t* h_itab, int n_itab,
+                                    const int32_t* h_reduce_idx, int n_reduce) {
+  if (!out || !h_plan || !h_itab || !h_reduce_idx)
+    return fail(1, "nb200_trainer_create: bad arguments");
+  if (n_plan_ints != TR_PLAN_INTS)
+    return fail(1, "nb200_trainer_create: plan has %d ints, expected %d", n_plan_ints, TR_PLAN_INTS);
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(3, "nessai_b200 kernels are built for sm_100a only; device %d is sm_%d%d", dev,
+                prop.major, prop.minor);
+  nb200_trainer* t = new (std::nothrow) nb200_trainer();
+  if (!t) return fail(4, "out of host memory");
+  memcpy(&t->h_plan, h_plan, sizeof(TrPlan));
+  const TrPlan& P = t->h_plan;
+  if (P.D < 2 || P.D > TR_MAXD || P.L < 1 || P.L > TR_MAXL || P.n_itab != n_itab ||
+      P.n_reduce != n_reduce || P.max_dim < P.D) {
+    delete t;
+    return fail(1, "nb200_trainer_create: plan out of range (D=%d L=%d)", P.D, P.L);
+  }
+  for (int l = 0; l < P.L; ++l) {
+    const TrLayer& ly = P.layer[l];
+    if (ly.n_lin < 1 || ly.n_lin > TR_MAXLIN || ly.n_buf < 2 || ly.n_buf > TR_MAXBUF) {
+      delete t;
+      return fail(1, "nb200_trainer_create: layer %d has %d linears / %d buffers", l, ly.n_lin, ly.n_buf);
+    }
+  }
+  t->num_sms = prop.multiProcessorCount;
+  t->smem_fwd = 4 * tr_smem_floats(P.D, P.vals_floats, P.max_dim, P.wmax, P.n_itab, false);
+  t->smem_bwd = 4 * tr_smem_floats(P.D, P.vals_floats, P.max_dim, P.wmax, P.n_itab, true);
+  if (t->smem_bwd > 226 * 1024) {
+    delete t;
+    return fail(5, "flow too large for the training kernels (%zu KB shared memory)", t->smem_bwd / 1024);
+  }
+  const int G = TR_MAXG;
+#define TR_ALLOC(ptr, count) CUDA_OK(cudaMalloc(&(ptr), sizeof(*(ptr)) * (size_t)(count)))
+  TR_ALLOC(t->d_plan, 1);
+  TR_ALLOC(t->d_itab, n_itab > 0 ? n_itab : 1);
+  TR_ALLOC(t->d_reduce, n_reduce > 0 ? n_reduce : 1);
+  TR_ALLOC(t->stat_part, (size_t)P.L * G * 2 * P.D);
+  TR_ALLOC(t->stats, (size_t)P.L * 2 * P.D);
+  TR_ALLOC(t->s_part0, (size_t)G * 2 * P.D);
+  TR_ALLOC(t->s_part1, (size_t)G * 2 * P.D);
+  TR_ALLOC(t->wsum_part, G);
+  TR_ALLOC(t->loss_part, G);
+  TR_ALLOC(t->part, (size_t)G * P.n_part);
+  TR_ALLOC(t->grad, P.n_params);
+  TR_ALLOC(t->gn_part, TR_REDUCE_MAXBLOCKS);
+  TR_ALLOC(t->eval_part, 2 * 2 * prop.multiProcessorCount);
+  TR_ALLOC(t->stat_n, G);
+  CUDA_OK(cudaMemcpy(t->d_plan, &t->h_plan, sizeof(TrPlan), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(t->d_itab, h_itab, sizeof(int) * n_itab, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(t->d_reduce, h_reduce_idx, sizeof(int) * n_reduce, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemset(t->grad, 0, sizeof(float) * P.n_params));
+  *out = t;
+  return 0;
+}
+
+static int trainer_reserve(nb200_trainer* t, int n_tiles) {
+  if (n_tiles <= t->cap_tiles) return 0;
+  CUDA_OK(cudaDeviceSynchronize());
+  trainer_free_rows(t);
+  const TrPlan& P = t->h_plan;
+  TR_ALLOC(t->ws, (size_t)n_tiles * P.rec_total * TR_R);
+  TR_ALLOC(t->dout0, (size_t)n_tiles * P.D * TR_R);
+  TR_ALLOC(t->dout1, (size_t)n_tiles * P.D * TR_R);
+  TR_ALLOC(t->ldrow, (size_t)n_tiles * TR_R);
+  TR_ALLOC(t->crow, (size_t)n_tiles * TR_R);
+  t->cap_tiles = n_tiles;
+  return 0;
+}
+
+static TrBuffers trainer_buffers(nb200_trainer* t, float* theta_p, float* theta_b, int G) {
+  TrBuffers B;
+  B.itab = t->d_itab;
+  B.reduce_idx = t->d_reduce;
+  B.theta_p = theta_p;
+  B.theta_b = theta_b;
+  B.ws = t->ws;
+  B.dout[0] = t->dout0;
+  B.dout[1] = t->dout1;
+  B.ldrow = t->ldrow;
+  B.crow = t->crow;
+  B.stat_part = t->stat_part;
+  B.stat_n = t->stat_n;
+  B.stats = t->stats;
+  B.s_part[0] = t->s_part0;
+  B.s_part[1] = t->s_part1;
+  B.wsum_part = t->wsum_part;
+  B.loss_part = t->loss_part;
+  B.part = t->part;
+  B.grad = t->grad;
+  B.gn_part = t->gn_part;
+  B.G = G;
+  B.n_reduce_blocks = std::min(TR_REDUCE_MAXBLOCKS, t->h_plan.L + std::max(1, (t->h_plan.n_reduce * 8 + TR_RED_THREADS - 1) / TR_RED_THREADS));
+  return B;
+}
+
+extern "C" int nb200_trainer_copy_grad(nb200_trainer* t, float* d_out, void* stream) {
+  if (!t || !d_out) return fail(1, "nb200_trainer_copy_grad: bad arguments");
+  CUDA_OK(cudaMemcpyAsync(d_out, t->grad, sizeof(float) * t->h_plan.n_params, cudaMemcpyDeviceToDevice,
+                          (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int nb200_train_epoch(nb200_trainer* t, float* d_theta_p, float* d_theta_b, float* d_m,
+                                 float* d_v, const float* d_x, const float* d_w,
+                                 const int64_t* d_perm, int64_t n_rows, int batch_size,
+                                 int opt_kind, double lr, double beta1, double beta2, double eps,
+                                 double weight_decay, double clip, int64_t step0,
+                                 float* d_loss_sum, float* d_step_info, void* stream) {
+  if (!t || !d_theta_p || !d_x || n_rows < 1 || batch_size < 1)
+    return fail(1, "nb200_train_epoch: bad arguments");
+  if (opt_kind < -1 || opt_kind > 2) return fail(1, "nb200_train_epoch: unknown optimiser %d", opt_kind);
+  if (opt_kind >= 0 && opt_kind <= 1 && (!d_m || !d_v))
+    return fail(1, "nb200_train_epoch: Adam needs its moment buffers");
+  const TrPlan& P = t->h_plan;
+  bool any_bn = false;
+  for (int l = 0; l < P.L; ++l) any_bn |= P.layer[l].bn_uw >= 0;
+  if (any_bn && !d_theta_b) return fail(1, "nb200_train_epoch: BatchNorm buffers missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int max_b = (int)std::min<int64_t>(batch_size, n_rows);
+  if (int rc = trainer_reserve(t, (max_b + TR_R - 1) / TR_R)) return rc;
+  if (int rc = prep_kernel(tr_fwd_kernel, t->smem_fwd)) return rc;
+  if (int rc = prep_kernel(tr_loss_kernel, t->smem_fwd)) return rc;
+  if (int rc = prep_kernel(tr_bwd_kernel, t->smem_bwd)) return rc;
+  int64_t step = step0;
+  int ib = 0;
+  for (int64_t i0 = 0; i0 < n_rows; i0 += batch_size, ++ib) {
+    TrBatch bt;
+    bt.x = d_x;
+    bt.perm = d_perm;
+    bt.w = d_w;
+    bt.i0 = i0;
+    bt.B = (int)std::min<int64_t>(batch_size, n_rows - i0);
+    bt.n_tiles = (bt.B + TR_R - 1) / TR_R;
+    if (bt.B < 2 && any_bn) return fail(1, "nb200_train_epoch: a batch of one row has no batch variance");
+    const int G = std::min(bt.n_tiles, std::min(TR_MAXG, t->num_sms));
+    TrBuffers B = trainer_buffers(t, d_theta_p, d_theta_b, G);
+    for (int l = 0; l < P.L; ++l) tr_fwd_kernel<<<G, TR_THREADS, t->smem_fwd, st>>>(P, B, bt, l);
+    tr_loss_kernel<<<G, TR_THREADS, t->smem_fwd, st>>>(P, B, bt);
+    for (int l = P.L - 1; l >= 0; --l) tr_bwd_kernel<<<G, TR_THREADS, t->smem_bwd, st>>>(P, B, bt, l);
+    tr_reduce_kernel<<<B.n_reduce_blocks, TR_RED_THREADS, 3 * P.D * P.D * sizeof(float), st>>>(P, B);
+    ++step;
+    TrOptim o;
+    o.kind = opt_kind;
+    o.lr = (float)lr;
+    o.beta1 = (float)beta1;
+    o.beta2 = (float)beta2;
+    o.eps = (float)eps;
+    o.weight_decay = (float)weight_decay;
+    o.clip = (float)clip;
+    o.bc1 = (float)(1.0 - std::pow(beta1, (double)step));
+    o.bc2 = (float)(1.0 - std::pow(beta2, (double)step));
+    const int ablocks = std::min((P.n_params + 255) / 256, 2 * t->num_sms);
+    tr_adam_kernel<<<ablocks, 256, 0, st>>>(B, P.n_params, o, d_m, d_v, d_step_info ? d_step_info + 2 * ib : nullptr,
+                                            d_loss_sum);
+    g_launches += 2 * P.L + 3;
+  }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int nb200_eval_loss(nb200_trainer* t, float* d_theta_p, float* d_theta_b, const float* d_x,
+                               const float* d_w, int64_t n, float* d_loss, float* d_logp,
+                               void* stream) {
+  if (!t || !d_theta_p || !d_x || n < 1 || (!d_loss && !d_logp))
+    return fail(1, "nb200_eval_loss: bad arguments");
+  if (n > (int64_t)1 << 30) return fail(1, "nb200_eval_loss: too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = prep_kernel(tr_eval_kernel, t->smem_fwd)) return rc;
+  TrBatch bt;
+  bt.x = d_x;
+  bt.perm = nullptr;
+  bt.w = d_w;
+  bt.i0 = 0;
+  bt.B = (int)n;
+  bt.n_tiles = (int)((n + TR_R - 1) / TR_R);
+  const int G = std::min(bt.n_tiles, 2 * t->num_sms);
+  TrBuffers B = trainer_buffers(t, d_theta_p, d_theta_b, G);
+  tr_eval_kernel<<<G, TR_THREADS, t->smem_fwd, st>>>(t->h_plan, B, bt, t->eval_part, d_logp);
+  if (d_loss) tr_eval_final_kernel<<<1, 32, 0, st>>>(t->eval_part, G, d_loss);
+  g_launches += d_loss ? 2 : 1;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,1195 @@
+// Fused training step of FlowModel._train (/root/reference/src/nessai/flowmodel/base.py:365-452)
+// for RealNVP flows: train-mode forward (batch-statistics BatchNorm, uncached LU), the
+// hand-derived backward pass, a deterministic gradient reduction, global-norm clipping and
+// Adam/AdamW -- the arithmetic the reference leaves to torch autograd + glasflow.nflows.
+// The backward pass is the one restated (and pinned against autograd) in oracle/train_numpy.py.
+//
+// Decomposition.  Rows are independent except through BatchNorm's batch statistics, so a step is a
+// chain of small kernels whose boundaries are exactly those grid-wide reductions:
+//   FWD(0..L-1)  -> LOSS -> BWD(L-1..0) -> REDUCE -> ADAM            (2L + 3 launches)
+// A batch is cut into tiles of 16 rows; a CTA (512 threads) owns tiles blockIdx.x, +gridDim.x, ...
+// and keeps every per-row quantity of a tile in shared memory, FEATURE-MAJOR ([feature][16 rows]),
+// so each thread's 8-row register tile is two 16-byte shared loads per k and weights are read
+// conflict-free.  Saved activations go to an L2-resident workspace in the same layout.
+// Parameter gradients are per-CTA partial sums (no atomics -> bit-reproducible), reduced by REDUCE.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace nb200 {
+
+constexpr int TR_R = 16;         // rows per tile
+constexpr int TR_THREADS = 512;  // threads per CTA of the row kernels (latency-bound: 4 warps / SMSP)
+constexpr int TR_RG = TR_THREADS / 64;   // row groups of the tile GEMM
+constexpr int TR_RT = TR_R / TR_RG;      // rows per thread
+constexpr int TR_RED_THREADS = 128;      // threads per CTA of the REDUCE kernel
+constexpr int TR_MAXL = 16;      // coupling layers
+constexpr int TR_MAXBUF = 12;    // conditioner buffers per layer
+constexpr int TR_MAXLIN = 12;    // linears per conditioner
+constexpr int TR_MAXD = 64;      // features
+constexpr int TR_MAXG = 148;     // CTAs per launch (one per SM)
+constexpr int TR_REDUCE_MAXBLOCKS = 2048;
+
+// ---- plan: ints only; packed by nessai_b200/train_plan.py in exactly this order ----------------
+struct TrLinear {
+  int w_off, b_off, n_in, n_out, in_buf, out_buf, res_buf, pre_act;
+};
+struct TrLayer {
+  int perm_off, lu_bias, lu_lower, lu_upper, lu_diag;  // -1 when absent (perm_off: into itab)
+  int bn_uw, bn_bias, bn_rm, bn_rv;                    // bn_rm / bn_rv: offsets into theta_b
+  int id_off, tr_off, d_id, d_tr;                      // index lists in itab
+  int n_lin, n_buf, rec_floats;                        // saved floats per row: h2 | bufs 1.. | y
+  int ws_off;                                          // feature offset of this layer's record
+  int lu_part_off;                                     // dense LU dW (D*D) inside a partial vector
+  int pad0, pad1;
+  int buf_dim[TR_MAXBUF];
+  int buf_off[TR_MAXBUF];  // feature offset inside the tile value area (buf 0 = identity half)
+  TrLinear lin[TR_MAXLIN];
+};
+struct TrPlan {
+  int D, L, act, additive;
+  int n_params, n_part, rec_total, max_dim;
+  int vals_floats, wmax, n_itab, n_reduce;
+  int pad[4];
+  TrLayer layer[TR_MAXL];
+};
+constexpr int TR_LAYER_INTS = 20 + 2 * TR_MAXBUF + 8 * TR_MAXLIN;
+constexpr int TR_PLAN_INTS = 16 + TR_MAXL * TR_LAYER_INTS;
+static_assert(sizeof(TrLayer) == 4 * TR_LAYER_INTS, "TrLayer layout");
+static_assert(sizeof(TrPlan) == 4 * TR_PLAN_INTS, "TrPlan layout");
+
+struct TrBuffers {
+  const int* itab;
+  const int* reduce_idx;
+  float* theta_p;
+  float* theta_b;
+  float* ws;          // [tile][rec_total][16]
+  float* dout[2];     // [tile][D][16]
+  float* ldrow;       // [tile][16]
+  float* crow;        // [tile][16] loss weight of each row (0 for padding rows)
+  float* stat_part;   // [L][G][2][D] per-CTA (mean, M2)
+  float* stat_n;      // [G] rows per CTA
+  float* stats;       // [L][2][D] batch mean, unbiased variance
+  float* s_part[2];   // [G][2][D] BatchNorm backward sums
+  float* wsum_part;   // [G]
+  float* loss_part;   // [G]
+  float* part;        // [G][n_part] gradient partials
+  float* grad;        // [n_params]
+  float* gn_part;     // [n_reduce_blocks]
+  int n_reduce_blocks;
+  int G;              // CTAs of the row kernels
+};
+
+struct TrBatch {
+  const float* x;       // [n_rows][D] row-major
+  const int64_t* perm;  // row order of the epoch (NULL: identity)
+  const float* w;       // per-row weights (NULL: unweighted)
+  int64_t i0;           // first row of the batch in `perm`
+  int B;                // rows in the batch
+  int n_tiles;
+};
+
+struct TrOptim {
+  int kind;  // 0 AdamW (decoupled decay), 1 Adam (L2 decay), 2 SGD, -1 gradient only
+  float lr, beta1, beta2, eps, weight_decay, clip;
+  float bc1, bc2;  // 1 - beta^t
+};
+
+constexpr float TR_LU_EPS = 1e-3f, TR_BN_EPS = 1e-5f, TR_BN_MOM = 0.1f;
+constexpr float TR_HALF_LOG_2PI = 0.91893853320467274178f;
+
+// ---------------------------------------------------------------------------- elementwise
+__device__ __forceinline__ float tr_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float tr_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float tr_act(int act, float z) {
+  if (act == 0) return fmaxf(z, 0.f);
+  if (act == 1) return tanhf(z);
+  return z * tr_sigmoid(z);
+}
+__device__ __forceinline__ float tr_dact(int act, float z) {
+  if (act == 0) return z > 0.f ? 1.f : 0.f;
+  if (act == 1) {
+    const float t = tanhf(z);
+    return 1.f - t * t;
+  }
+  const float s = tr_sigmoid(z);
+  return s * (1.f + z * (1.f - s));
+}
+
+// ---------------------------------------------------------------------------- tile GEMMs
+// out[c][r] (=|+=) bias[c] + sum_k W[k*ldw + c] * A[k][r] (+ res[c][r]);  c < N, r < 16.
+// Thread (c = tid & 63, rows TR_RT*(tid >> 6) .. +TR_RT); callers synchronise.
+__device__ __forceinline__ void tr_gemm(float* __restrict__ out, const float* __restrict__ A,
+                                        const float* __restrict__ W, int ldw,
+                                        const float* __restrict__ bias,
+                                        const float* __restrict__ res, int N, int K, bool accum) {
+  static_assert(TR_RT == 2, "tile GEMM register tile");
+  const int rg = threadIdx.x >> 6, cl = threadIdx.x & 63;
+  for (int c0 = 0; c0 < N; c0 += 64) {
+    const int c = c0 + cl;
+    if (c < N) {
+      const float b = bias ? bias[c] : 0.f;
+      float acc0 = b, acc1 = b;
+      const float2* A2 = reinterpret_cast<const float2*>(A + rg * TR_RT);
+      const float* w = W + c;
+#pragma unroll 4
+      for (int k = 0; k < K; ++k) {
+        const float wk = w[k * ldw];
+        const float2 a = A2[k * (TR_R / 2)];
+        acc0 = fmaf(wk, a.x, acc0);
+        acc1 = fmaf(wk, a.y, acc1);
+      }
+      float* o = out + c * TR_R + rg * TR_RT;
+      if (res) {
+        const float* rr = res + c * TR_R + rg * TR_RT;
+        acc0 += rr[0], acc1 += rr[1];
+      }
+      if (accum) acc0 += o[0], acc1 += o[1];
+      o[0] = acc0, o[1] = acc1;
+    }
+  }
+}
+
+// Weight gradient of one linear over the tile: g[c*K + k] (=|+=) sum_r delta[c][r] * A[k][r].
+__device__ __forceinline__ void tr_wgrad(float* __restrict__ g, const float* __restrict__ delta,
+                                         const float* __restrict__ A, int N, int K, bool first) {
+  const int tid = threadIdx.x;
+  if (K <= TR_THREADS && (TR_THREADS % K) == 0) {
+    const int k = tid % K, cstep = TR_THREADS / K;
+    float a[TR_R];
+    const float4* A4 = reinterpret_cast<const float4*>(A + k * TR_R);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 v = A4[q];
+      a[4 * q] = v.x, a[4 * q + 1] = v.y, a[4 * q + 2] = v.z, a[4 * q + 3] = v.w;
+    }
+    for (int c = tid / K; c < N; c += cstep) {
+      const float4* d4 = reinterpret_cast<const float4*>(delta + c * TR_R);
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = d4[q];
+        s = fmaf(v.x, a[4 * q], s);
+        s = fmaf(v.y, a[4 * q + 1], s);
+        s = fmaf(v.z, a[4 * q + 2], s);
+        s = fmaf(v.w, a[4 * q + 3], s);
+      }
+      float* p = g + c * K + k;
+      *p = first ? s : *p + s;
+    }
+  } else {
+    for (int e = tid; e < N * K; e += TR_THREADS) {
+      const int c = e / K, k = e - c * K;
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < TR_R; ++r) s = fmaf(delta[c * TR_R + r], A[k * TR_R + r], s);
+      g[e] = first ? s : g[e] + s;
+    }
+  }
+}
+
+// Bias gradient: g[c] (=|+=) sum_r delta[c][r]
+__device__ __forceinline__ void tr_bgrad(float* __restrict__ g, const float* __restrict__ delta,
+                                         int N, bool first) {
+  for (int c = threadIdx.x; c < N; c += TR_THREADS) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < TR_R; ++r) s += delta[c * TR_R + r];
+    g[c] = first ? s : g[c] + s;
+  }
+}
+
+// ---------------------------------------------------------------------------- async copies
+// Global -> shared staging uses cp.async (LDGSTS): a thread queues all its copies without waiting,
+// so a tile / a weight matrix costs ONE memory latency instead of one per loop iteration (with a
+// single warp per SM sub-partition there is no other latency hiding).
+__device__ __forceinline__ uint32_t tr_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tr_cp4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tr_s32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tr_cp16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tr_s32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tr_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tr_cp_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Store a [n][16] shared tile to global memory (both 16-byte aligned).
+__device__ __forceinline__ void tr_copy(float* __restrict__ dst, const float* __restrict__ src,
+                                        int n_feat) {
+  float4* d = reinterpret_cast<float4*>(dst);
+  const float4* s = reinterpret_cast<const float4*>(src);
+  for (int i = threadIdx.x; i < n_feat * 4; i += TR_THREADS) d[i] = s[i];
+}
+// Queue the load of a [n][16] global tile into shared memory (caller commits and waits).
+__device__ __forceinline__ void tr_copy_async(float* dst, const float* src, int n_feat) {
+  for (int i = threadIdx.x; i < n_feat * 4; i += TR_THREADS) tr_cp16(dst + 4 * i, src + 4 * i);
+}
+// Queue n floats (no alignment assumed).
+__device__ __forceinline__ void tr_copy_async4(float* dst, const float* src, int n) {
+  for (int i = threadIdx.x; i < n; i += TR_THREADS) tr_cp4(dst + i, src + i);
+}
+
+// Queue nn.Linear weights (row-major [n_out][n_in]) into shared memory.
+// transposed: W[k * (n_out | 1) + c]  (forward: thread index = output column c)
+// natural:    W[c * n_in + k]          (backward: thread index = input column k)
+__device__ __forceinline__ void tr_load_w_async(float* sW, const float* W, int n_out, int n_in,
+                                                bool transposed) {
+  const int n = n_out * n_in;
+  if (transposed) {
+    const int ld = n_out | 1;
+    int c = threadIdx.x / n_in, k = threadIdx.x - c * n_in;
+    const int dc = TR_THREADS / n_in, dk = TR_THREADS - dc * n_in;
+    for (int i = threadIdx.x; i < n; i += TR_THREADS) {
+      tr_cp4(sW + k * ld + c, W + i);
+      c += dc, k += dk;
+      if (k >= n_in) k -= n_in, ++c;
+    }
+  } else if ((((uintptr_t)W) & 15) == 0 && (n & 3) == 0) {
+    for (int i = threadIdx.x; i < n / 4; i += TR_THREADS) tr_cp16(sW + 4 * i, W + 4 * i);
+  } else {
+    for (int i = threadIdx.x; i < n; i += TR_THREADS) tr_cp4(sW + i, W + i);
+  }
+}
+
+// Dense W = Lo Up of nflows' LULinear (unit lower x upper with softplus diagonal) into shared
+// memory.  The triangles are staged in `stage` (>= D*D floats) first.  transposed as above.
+__device__ __forceinline__ void tr_lu_dense(float* __restrict__ sW, float* __restrict__ stage,
+                                            const float* __restrict__ theta, const TrLayer& ly,
+                                            int D, bool transposed) {
+  const int ntri = D * (D - 1) / 2;
+  float* lower = stage;
+  float* upper = stage + ntri;
+  float* diag = stage + 2 * ntri;
+  tr_copy_async4(lower, theta + ly.lu_lower, ntri);
+  tr_copy_async4(upper, theta + ly.lu_upper, ntri);
+  tr_copy_async4(diag, theta + ly.lu_diag, D);
+  tr_copy_async4(sW + D * (D | 1), theta + ly.lu_bias, D);
+  tr_cp_commit();
+  tr_cp_wait<0>();
+  __syncthreads();
+  for (int m = threadIdx.x; m < D; m += TR_THREADS) diag[m] = tr_softplus(diag[m]) + TR_LU_EPS;
+  __syncthreads();
+  const int ld = transposed ? (D | 1) : D;
+  for (int e = threadIdx.x; e < D * D; e += TR_THREADS) {
+    const int i = e / D, j = e - i * D;
+    const int mmax = i < j ? i : j;
+    float s = 0.f;
+    for (int m = 0; m <= mmax; ++m) {
+      const float lo = (m == i) ? 1.f : lower[i * (i - 1) / 2 + m];
+      const float up = (m == j) ? diag[m] : upper[m * D - m * (m + 1) / 2 + (j - m - 1)];
+      s = fmaf(lo, up, s);
+    }
+    if (transposed) sW[j * ld + i] = s;
+    else sW[i * ld + j] = s;
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------- shared memory map
+struct TrSmem {
+  float* W;     // staged weights of one linear, double buffered: W + (j & 1) * wbuf
+  int wbuf;
+  float* Wlu;   // dense LU matrix [D][D|1]
+  float* H1;    // [D][16] layer input (after the permutation)
+  float* H2;    // [D][16] after the LU linear
+  float* Y;     // [D][16] coupling output (before BatchNorm)
+  float* X;     // [D][16] scratch (x-hat / dy / dh2 ...)
+  float* Pf;    // [D][16] prefetched tile (backward: previous layer's output)
+  float* V;     // [vals][16] conditioner buffers
+  float* Gv;    // [vals][16] their gradients (backward only)
+  float* A;     // [max_dim][16] staged GEMM operand
+  float* bn;    // [4][D]: mean, rstd, w, beta  (+ [2][D] S1,S2 in backward)
+  float* c;     // [16] row weights
+  float* ld;    // [16]
+  float* red;   // [3 * TR_THREADS] block reductions
+  float* stage; // [TR_MAXG][2][D] per-CTA partials staged for the cross-CTA reductions
+  int* itab;    // permutations / mask index lists
+};
+__host__ __device__ inline int tr_align4(int n) { return (n + 3) & ~3; }
+__host__ __device__ inline size_t tr_smem_floats(int D, int vals, int max_dim, int wmax, int n_itab, bool backward) {
+  size_t n = 0;
+  n += 2 * (tr_align4(wmax) + tr_align4(max_dim));
+  n += tr_align4(D * (D | 1) + D);
+  n += 5 * (size_t)D * TR_R;
+  n += (size_t)vals * TR_R * (backward ? 2 : 1);
+  n += (size_t)max_dim * TR_R;
+  n += tr_align4(6 * D);
+  n += 2 * TR_R + 3 * TR_THREADS;
+  n += (size_t)TR_MAXG * (2 * D + 1);
+  n += tr_align4(n_itab);
+  return n;
+}
+__device__ __forceinline__ TrSmem tr_carve(float* s, const TrPlan& P, bool backward) {
+  TrSmem m;
+  const int D = P.D;
+  m.W = s, m.wbuf = tr_align4(P.wmax) + tr_align4(P.max_dim), s += 2 * m.wbuf;
+  m.Wlu = s, s += tr_align4(D * (D | 1) + D);
+  m.H1 = s, s += D * TR_R;
+  m.H2 = s, s += D * TR_R;
+  m.Y = s, s += D * TR_R;
+  m.X = s, s += D * TR_R;
+  m.Pf = s, s += D * TR_R;
+  m.V = s, s += P.vals_floats * TR_R;
+  m.Gv = s;
+  if (backward) s += P.vals_floats * TR_R;
+  m.A = s, s += P.max_dim * TR_R;
+  m.bn = s, s += tr_align4(6 * D);
+  m.c = s, s += TR_R;
+  m.ld = s, s += TR_R;
+  m.red = s, s += 3 * TR_THREADS;
+  m.stage = s, s += TR_MAXG * (2 * D + 1);
+  m.itab = reinterpret_cast<int*>(s);
+  return m;
+}
+
+// Index tables into shared memory (first thing every row kernel does).
+__device__ __forceinline__ void tr_stage_itab(const TrBuffers& Bf, const TrPlan& P, const TrSmem& S) {
+  tr_copy_async4(reinterpret_cast<float*>(S.itab), reinterpret_cast<const float*>(Bf.itab), P.n_itab);
+  tr_cp_commit();
+  tr_cp_wait<0>();
+  __syncthreads();
+}
+
+template <int NT = TR_THREADS>
+__device__ __forceinline__ float tr_block_sum(float v, float* red) {
+  __syncthreads();
+  red[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = NT / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  const float r = red[0];
+  __syncthreads();
+  return r;
+}
+
+// Combine the per-CTA (n, mean, M2) partials of BatchNorm layer `l` (Chan et al.) into
+// bn[0][d] = mean, bn[1][d] = 1/sqrt(var + eps), and return the unbiased variance through var_out.
+// The partials are first staged in shared memory with independent coalesced loads (one L2
+// latency instead of G dependent ones).
+__device__ __forceinline__ void tr_reduce_stats(const TrBuffers& Bf, int l, int D, int B, float* bn,
+                                                float* var_out, float* stage, float* red) {
+  const int G = Bf.G;
+  float* sn = stage + G * 2 * D;
+  tr_copy_async4(stage, Bf.stat_part + (size_t)l * G * 2 * D, G * 2 * D);
+  tr_copy_async4(sn, Bf.stat_n, G);
+  tr_cp_commit();
+  tr_cp_wait<0>();
+  __syncthreads();
+  const int nsl = TR_THREADS / D;
+  const int d = threadIdx.x % D, sl = threadIdx.x / D;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  if (sl < nsl)
+    for (int g = sl; g < G; g += nsl) {
+      const float nb = sn[g];
+      if (nb == 0.f) continue;
+      const float mb = stage[g * 2 * D + d], m2b = stage[g * 2 * D + D + d];
+      const float nn = n + nb, delta = mb - mean;
+      mean += delta * (nb / nn);
+      m2 += m2b + delta * delta * (n * nb / nn);
+      n = nn;
+    }
+  red[threadIdx.x] = n, red[TR_THREADS + threadIdx.x] = mean, red[2 * TR_THREADS + threadIdx.x] = m2;
+  __syncthreads();
+  if ((int)threadIdx.x < D) {
+    n = 0.f, mean = 0.f, m2 = 0.f;
+    for (int q = 0; q < nsl; ++q) {
+      const int t = q * D + threadIdx.x;
+      const float nb = red[t];
+      if (nb == 0.f) continue;
+      const float mb = red[TR_THREADS + t], m2b = red[2 * TR_THREADS + t];
+      const float nn = n + nb, delta = mb - mean;
+      mean += delta * (nb / nn);
+      m2 += m2b + delta * delta * (n * nb / nn);
+      n = nn;
+    }
+    const float var = m2 / (float)(B - 1);
+    bn[threadIdx.x] = mean;
+    bn[D + threadIdx.x] = rsqrtf(var + TR_BN_EPS);
+    if (var_out) var_out[threadIdx.x] = var;
+  }
+  __syncthreads();
+}
+
+// out[c] = sum_g src[g * ncol + c]  (ncol <= TR_THREADS): the G partials are split over
+// TR_THREADS / ncol thread slices so every thread issues independent loads.
+__device__ __forceinline__ void tr_colsum(const float* __restrict__ src, int G, int ncol, float* out,
+                                          float* red) {
+  const int nsl = TR_THREADS / ncol;
+  const int c = threadIdx.x % ncol, sl = threadIdx.x / ncol;
+  float s = 0.f;
+  if (sl < nsl)
+    for (int g = sl; g < G; g += nsl) s += src[(size_t)g * ncol + c];
+  __syncthreads();
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if ((int)threadIdx.x < ncol) {
+    float t = 0.f;
+    for (int q = 0; q < nsl; ++q) t += red[q * ncol + threadIdx.x];
+    out[threadIdx.x] = t;
+  }
+  __syncthreads();
+}
+
+// Load BatchNorm layer l's (mean, rstd, w, beta) into bn[0..3][D] for the training pass.
+// first_use: the statistics are still per-CTA partials (reduce them; block 0 publishes them and
+// EMA-updates the running buffers); otherwise read the published values.
+__device__ __forceinline__ void tr_bn_setup(const TrBuffers& Bf, const TrLayer& ly, int l, int D, int B,
+                                            float* bn, float* scratch, bool first_use, float* stage, float* red) {
+  if (first_use) {
+    tr_reduce_stats(Bf, l, D, B, bn, scratch, stage, red);
+    if (blockIdx.x == 0)
+      for (int d = threadIdx.x; d < D; d += TR_THREADS) {
+        Bf.stats[(l * 2) * D + d] = bn[d];
+        Bf.stats[(l * 2 + 1) * D + d] = scratch[d];
+        float* rm = Bf.theta_b + ly.bn_rm;
+        float* rv = Bf.theta_b + ly.bn_rv;
+        rm[d] = (1.f - TR_BN_MOM) * rm[d] + TR_BN_MOM * bn[d];
+        rv[d] = (1.f - TR_BN_MOM) * rv[d] + TR_BN_MOM * scratch[d];
+      }
+  } else {
+    for (int d = threadIdx.x; d < D; d += TR_THREADS) {
+      bn[d] = Bf.stats[(l * 2) * D + d];
+      bn[D + d] = rsqrtf(Bf.stats[(l * 2 + 1) * D + d] + TR_BN_EPS);
+    }
+  }
+  for (int d = threadIdx.x; d < D; d += TR_THREADS) {
+    bn[2 * D + d] = tr_softplus(__ldg(Bf.theta_p + ly.bn_uw + d)) + TR_BN_EPS;
+    bn[3 * D + d] = __ldg(Bf.theta_p + ly.bn_bias + d);
+  }
+  __syncthreads();
+}
+
+// Eval-mode BatchNorm constants (running statistics).
+__device__ __forceinline__ void tr_bn_setup_eval(const TrBuffers& Bf, const TrLayer& ly, int D, float* bn) {
+  for (int d = threadIdx.x; d < D; d += TR_THREADS) {
+    bn[d] = Bf.theta_b[ly.bn_rm + d];
+    bn[D + d] = rsqrtf(Bf.theta_b[ly.bn_rv + d] + TR_BN_EPS);
+    bn[2 * D + d] = tr_softplus(__ldg(Bf.theta_p + ly.bn_uw + d)) + TR_BN_EPS;
+    bn[3 * D + d] = __ldg(Bf.theta_p + ly.bn_bias + d);
+  }
+  __syncthreads();
+}
+
+// Gather the batch rows of one tile (layer-0 input), applying the layer permutation, and the
+// per-row loss weights.  Padding rows are zero with weight zero.
+__device__ __forceinline__ void tr_load_x(const TrBatch& bt, int tile, int D, const int* lperm,
+                                          float* H1, float* c) {
+  for (int e = threadIdx.x; e < D * TR_R; e += TR_THREADS) {
+    const int r = e / D, j = e - r * D;  // consecutive threads read consecutive features of a row
+    const int row = tile * TR_R + r;
+    float v = 0.f;
+    if (row < bt.B) {
+      const int64_t gi = bt.perm ? bt.perm[bt.i0 + row] : bt.i0 + row;
+      v = __ldg(bt.x + gi * D + (lperm ? lperm[j] : j));
+    }
+    H1[j * TR_R + r] = v;
+  }
+  if (threadIdx.x < TR_R) {
+    const int row = tile * TR_R + threadIdx.x;
+    float w = 0.f;
+    if (row < bt.B) {
+      const int64_t gi = bt.perm ? bt.perm[bt.i0 + row] : bt.i0 + row;
+      w = bt.w ? __ldg(bt.w + gi) : 1.f;
+    }
+    c[threadIdx.x] = w;
+  }
+}
+
+// H1[j][r] = BN(Yprev)[perm[j]][r]; optionally also X[d][r] = x-hat[d][r] (unpermuted).
+__device__ __forceinline__ void tr_bn_apply_perm(const float* Yprev, const float* bn, int D,
+                                                 const int* lperm, float* H1, float* xhat) {
+  for (int e = threadIdx.x; e < D * TR_R; e += TR_THREADS) {
+    const int j = e / TR_R, r = e - j * TR_R;
+    const int d = lperm ? lperm[j] : j;
+    const float xh = (Yprev[d * TR_R + r] - bn[d]) * bn[D + d];
+    H1[j * TR_R + r] = fmaf(bn[2 * D + d], xh, bn[3 * D + d]);
+    if (xhat) xhat[d * TR_R + r] = xh;
+  }
+}
+
+// Queue the weights of linear j of the conditioner into buffer j & 1 (one commit group).
+__device__ __forceinline__ void tr_prefetch_w(const TrBuffers& Bf, const TrLayer& ly, const TrSmem& S, int j,
+                                              bool transposed, int P_max_dim) {
+  const TrLinear& ln = ly.lin[j];
+  float* buf = S.W + (j & 1) * S.wbuf;
+  tr_load_w_async(buf, Bf.theta_p + ln.w_off, ln.n_out, ln.n_in, transposed);
+  if (transposed) tr_copy_async4(buf + S.wbuf - tr_align4(P_max_dim), Bf.theta_p + ln.b_off, ln.n_out);
+  tr_cp_commit();
+}
+
+// Conditioner + coupling of layer `ly` on one tile: H1 -> H2 (LU) -> V (net) -> Y.
+// ld[r] += sum log s.  save != NULL: write the layer record (h2 | bufs 1.. | y) there.
+// The caller has queued the weights of linear 0 (tr_prefetch_w) as the most recent commit group.
+__device__ __forceinline__ void tr_layer_forward(const TrBuffers& Bf, const TrPlan& P, const TrLayer& ly,
+                                                 const TrSmem& S, float* save) {
+  const int D = P.D, act = P.act;
+  const int* itab = S.itab;
+  if (ly.lu_bias >= 0) {
+    tr_gemm(S.H2, S.H1, S.Wlu, D | 1, S.Wlu + D * (D | 1), nullptr, D, D, false);
+  } else {
+    for (int e = threadIdx.x; e < D * TR_R; e += TR_THREADS) S.H2[e] = S.H1[e];
+  }
+  __syncthreads();
+  if (save) tr_copy(save, S.H2, D);
+  for (int e = threadIdx.x; e < ly.d_id * TR_R; e += TR_THREADS) {
+    const int i = e / TR_R, r = e - i * TR_R;
+    S.V[e] = S.H2[itab[ly.id_off + i] * TR_R + r];
+  }
+  __syncthreads();
+  for (int j = 0; j < ly.n_lin; ++j) {
+    const TrLinear& ln = ly.lin[j];
+    const float* src = S.V + ly.buf_off[ln.in_buf] * TR_R;
+    const float* Aop = src;
+    if (ln.pre_act) {
+      for (int e = threadIdx.x; e < ln.n_in * TR_R; e += TR_THREADS) S.A[e] = tr_act(act, src[e]);
+      Aop = S.A;
+    }
+    if (j + 1 < ly.n_lin) {
+      tr_prefetch_w(Bf, ly, S, j + 1, true, P.max_dim);
+      tr_cp_wait<1>();
+    } else {
+      tr_cp_wait<0>();
+    }
+    __syncthreads();
+    tr_gemm(S.V + ly.buf_off[ln.out_buf] * TR_R, Aop, S.W + (j & 1) * S.wbuf, ln.n_out | 1,
+            S.W + (j & 1) * S.wbuf + S.wbuf - tr_align4(P.max_dim), ln.res_buf >= 0 ? S.V + ly.buf_off[ln.res_buf] * TR_R : nullptr,
+            ln.n_out, ln.n_in, false);
+    __syncthreads();
+  }
+  const float* prm = S.V + ly.buf_off[ly.n_buf - 1] * TR_R;
+  for (int e = threadIdx.x; e < ly.d_id * TR_R; e += TR_THREADS) {
+    const int i = e / TR_R, r = e - i * TR_R;
+    const int f = itab[ly.id_off + i];
+    S.Y[f * TR_R + r] = S.H2[f * TR_R + r];
+  }
+  for (int e = threadIdx.x; e < ly.d_tr * TR_R; e += TR_THREADS) {
+    const int i = e / TR_R, r = e - i * TR_R;
+    const int f = itab[ly.tr_off + i];
+    const float t = S.H2[f * TR_R + r];
+    if (P.additive) {
+      S.Y[f * TR_R + r] = t + prm[e];
+      S.A[e] = 0.f;
+    } else {
+      const float s = tr_sigmoid(prm[ly.d_tr * TR_R + e] + 2.f) + 1e-3f;
+      S.Y[f * TR_R + r] = fmaf(t, s, prm[e]);
+      S.A[e] = logf(s);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < TR_R) {
+    float s = 0.f;
+    for (int i = 0; i < ly.d_tr; ++i) s += S.A[i * TR_R + threadIdx.x];
+    S.ld[threadIdx.x] += s;
+  }
+  if (save) {
+    const int nb = ly.rec_floats - 2 * D;
+    tr_copy(save + D * TR_R, S.V + ly.buf_off[1] * TR_R, nb);
+    tr_copy(save + (D + nb) * TR_R, S.Y, D);
+  }
+  __syncthreads();
+}
+
+// Row-constant log|det| of the flow: LU diagonals + BatchNorm scales.  stats == NULL: eval mode
+// (running variance from theta_b); otherwise the published batch variances.
+__device__ __forceinline__ float tr_const_logdet(const TrBuffers& Bf, const TrPlan& P, const float* stats,
+                                                 float* red) {
+  const int D = P.D;
+  float s = 0.f;
+  for (int e = threadIdx.x; e < P.L * D; e += TR_THREADS) {
+    const int l = e / D, d = e - l * D;
+    const TrLayer& ly = P.layer[l];
+    if (ly.lu_bias >= 0) s += logf(tr_softplus(__ldg(Bf.theta_p + ly.lu_diag + d)) + TR_LU_EPS);
+    if (ly.bn_uw >= 0) {
+      const float var = stats ? stats[(l * 2 + 1) * D + d] : Bf.theta_b[ly.bn_rv + d];
+      s += logf(tr_softplus(__ldg(Bf.theta_p + ly.bn_uw + d)) + TR_BN_EPS) - 0.5f * logf(var + TR_BN_EPS);
+    }
+  }
+  return tr_block_sum(s, red);
+}
+
+// ============================================================================ FWD(l)
+extern __shared__ __align__(16) float tr_smem_dyn[];
+
+__global__ void __launch_bounds__(TR_THREADS) tr_fwd_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf, TrBatch bt, int l) {
+  const TrLayer& ly = P.layer[l];
+  const int D = P.D;
+  TrSmem S = tr_carve(tr_smem_dyn, P, false);
+  tr_stage_itab(Bf, P, S);
+  const int* lperm = ly.perm_off >= 0 ? S.itab + ly.perm_off : nullptr;
+  const bool bn_prev = l > 0 && P.layer[l - 1].bn_uw >= 0;
+  if (bn_prev) tr_bn_setup(Bf, P.layer[l - 1], l - 1, D, bt.B, S.bn, S.bn + 4 * D, true, S.stage, S.red);
+  if (ly.lu_bias >= 0) tr_lu_dense(S.Wlu, S.stage, Bf.theta_p, ly, D, true);
+  __syncthreads();
+  float n_run = 0.f, mean_run = 0.f, m2_run = 0.f;  // BatchNorm partials of feature threadIdx.x
+  float wsum = 0.f;
+  int rows_cta = 0;
+  for (int tile = blockIdx.x; tile < bt.n_tiles; tile += gridDim.x) {
+    float* rec = Bf.ws + ((size_t)tile * P.rec_total + ly.ws_off) * TR_R;
+    if (l == 0) {
+      tr_prefetch_w(Bf, ly, S, 0, true, P.max_dim);
+      tr_load_x(bt, tile, D, lperm, S.H1, S.c);
+      if (threadIdx.x < TR_R) S.ld[threadIdx.x] = 0.f;
+      __syncthreads();
+      if (threadIdx.x < TR_R) Bf.crow[tile * TR_R + threadIdx.x] = S.c[threadIdx.x];
+      if (threadIdx.x == 0)
+        for (int r = 0; r < TR_R; ++r) wsum += S.c[r];
+    } else {
+      const TrLayer& lp = P.layer[l - 1];
+      const float* yprev = Bf.ws + ((size_t)tile * P.rec_total + lp.ws_off + lp.rec_floats - D) * TR_R;
+      tr_copy_async(S.Y, yprev, D);
+      tr_cp_commit();
+      tr_prefetch_w(Bf, ly, S, 0, true, P.max_dim);
+      if (threadIdx.x < TR_R) S.ld[threadIdx.x] = Bf.ldrow[tile * TR_R + threadIdx.x];
+      tr_cp_wait<1>();
+      __syncthreads();
+      if (bn_prev) {
+        tr_bn_apply_perm(S.Y, S.bn, D, lperm, S.H1, nullptr);
+      } else {
+        for (int e = threadIdx.x; e < D * TR_R; e += TR_THREADS) {
+          const int j = e / TR_R, r = e - j * TR_R;
+          S.H1[e] = S.Y[(lperm ? lperm[j] : j) * TR_R + r];
+        }
+      }
+      __syncthreads();
+    }
+    tr_layer_forward(Bf, P, ly, S, rec);
+    if (threadIdx.x < TR_R) Bf.ldrow[tile * TR_R + threadIdx.x] = S.ld[threadIdx.x];
+    const int nv = min(TR_R, bt.B - tile * TR_R);
+    rows_cta += nv;
+    if (ly.bn_uw >= 0 && (int)threadIdx.x < D) {
+      const float* y = S.Y + threadIdx.x * TR_R;
+      float m = 0.f;
+      for (int r = 0; r < nv; ++r) m += y[r];
+      m /= (float)nv;
+      float q = 0.f;
+      for (int r = 0; r < nv; ++r) q += (y[r] - m) * (y[r] - m);
+      const float nb = (float)nv, nn = n_run + nb, delta = m - mean_run;
+      mean_run += delta * (nb / nn);
+      m2_run += q + delta * delta * (n_run * nb / nn);
+      n_run = nn;
+    }
+    __syncthreads();
+  }
+  if (ly.bn_uw >= 0 && (int)threadIdx.x < D) {
+    float* p = Bf.stat_part + ((size_t)(l * Bf.G + blockIdx.x) * 2) * D;
+    p[threadIdx.x] = mean_run;
+    p[D + threadIdx.x] = m2_run;
+  }
+  if (threadIdx.x == 0) {
+    if (l == 0) {
+      Bf.stat_n[blockIdx.x] = (float)rows_cta;
+      Bf.wsum_part[blockIdx.x] = wsum;
+    }
+  }
+}
+
+// ============================================================================ LOSS
+// z = BN_{L-1}(y_{L-1}); loss partial; dout_{L-1} = c_r z; BatchNorm backward sums of layer L-1.
+__global__ void __launch_bounds__(TR_THREADS) tr_loss_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf, TrBatch bt) {
+  const int D = P.D, L = P.L;
+  const TrLayer& ly = P.layer[L - 1];
+  TrSmem S = tr_carve(tr_smem_dyn, P, false);
+  tr_stage_itab(Bf, P, S);
+  const bool bn = ly.bn_uw >= 0;
+  if (bn) tr_bn_setup(Bf, ly, L - 1, D, bt.B, S.bn, S.bn + 4 * D, true, S.stage, S.red);
+  // the last layer's statistics are published by block 0 only: use our own copy for the constant
+  float cld = 0.f;
+  {
+    float s = 0.f;
+    for (int e = threadIdx.x; e < L * D; e += TR_THREADS) {
+      const int l = e / D, d = e - l * D;
+      const TrLayer& lq = P.layer[l];
+      if (lq.lu_bias >= 0) s += logf(tr_softplus(__ldg(Bf.theta_p + lq.lu_diag + d)) + TR_LU_EPS);
+      if (lq.bn_uw >= 0) {
+        const float var = (l == L - 1) ? S.bn[4 * D + d] : Bf.stats[(l * 2 + 1) * D + d];
+        s += logf(tr_softplus(__ldg(Bf.theta_p + lq.bn_uw + d)) + TR_BN_EPS) - 0.5f * logf(var + TR_BN_EPS);
+      }
+    }
+    cld = tr_block_sum(s, S.red);
+  }
+  float csum = 0.f;
+  {
+    float s = 0.f;
+    for (int g = threadIdx.x; g < Bf.G; g += TR_THREADS) s += Bf.wsum_part[g];
+    csum = tr_block_sum(s, S.red);
+  }
+  const float inv_csum = 1.f / csum;
+  float s1 = 0.f, s2 = 0.f, loss = 0.f;
+  float* dout = Bf.dout[(L - 1) & 1];
+  for (int tile = blockIdx.x; tile < bt.n_tiles; tile += gridDim.x) {
+    const float* y = Bf.ws + ((size_t)tile * P.rec_total + ly.ws_off + ly.rec_floats - D) * TR_R;
+    tr_copy_async(S.Y, y, D);
+    tr_cp_commit();
+    if (threadIdx.x < TR_R) {
+      S.c[threadIdx.x] = Bf.crow[tile * TR_R + threadIdx.x] * inv_csum;
+      S.ld[threadIdx.x] = Bf.ldrow[tile * TR_R + threadIdx.x];
+    }
+    tr_cp_wait<0>();
+    __syncthreads();
+    if (threadIdx.x < TR_R) Bf.crow[tile * TR_R + threadIdx.x] = S.c[threadIdx.x];
+    // X = x-hat, H1 = z, H2 = dout
+    for (int e = threadIdx.x; e < D * TR_R; e += TR_THREADS) {
+      const int d = e / TR_R, r = e - d * TR_R;
+      float z = S.Y[e], xh = 0.f;
+      if (bn) {
+        xh = (z - S.bn[d]) * S.bn[D + d];
+        z = fmaf(S.bn[2 * D + d], xh, S.bn[3 * D + d]);
+      }
+      S.X[e] = xh;
+      S.H1[e] = z;
+      S.H2[e] = S.c[r] * z;
+    }
+    __syncthreads();
+    tr_copy(dout + (size_t)tile * D * TR_R, S.H2, D);
+    if (threadIdx.x < TR_R) {
+      float q = 0.f;
+      for (int d = 0; d < D; ++d) q += S.H1[d * TR_R + threadIdx.x] * S.H1[d * TR_R + threadIdx.x];
+      const float logp = -0.5f * q - (float)D * TR_HALF_LOG_2PI + S.ld[threadIdx.x] + cld;
+      loss += S.c[threadIdx.x] * logp;  // c == 0 for padding rows
+    }
+    if (bn && (int)threadIdx.x < D) {
+      for (int r = 0; r < TR_R; ++r) {
+        const float g = S.H2[threadIdx.x * TR_R + r];
+        s1 += g;
+        s2 = fmaf(g, S.X[threadIdx.x * TR_R + r], s2);
+      }
+    }
+    __syncthreads();
+  }
+  if (bn && (int)threadIdx.x < D) {
+    float* sp = Bf.s_part[(L - 1) & 1] + (size_t)blockIdx.x * 2 * D;
+    sp[threadIdx.x] = s1;
+    sp[D + threadIdx.x] = s2;
+  }
+  const float lsum = tr_block_sum(threadIdx.x < TR_R ? loss : 0.f, S.red);
+  if (threadIdx.x == 0) Bf.loss_part[blockIdx.x] = -lsum;
+}
+
+// ============================================================================ BWD(l)
+__global__ void __launch_bounds__(TR_THREADS) tr_bwd_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf, TrBatch bt, int l) {
+  const TrLayer& ly = P.layer[l];
+  const int D = P.D, act = P.act;
+  TrSmem S = tr_carve(tr_smem_dyn, P, true);
+  tr_stage_itab(Bf, P, S);
+  const int* itab = S.itab;
+  const int* lperm = ly.perm_off >= 0 ? S.itab + ly.perm_off : nullptr;
+  const bool bn = ly.bn_uw >= 0;
+  const bool bn_prev = l > 0 && P.layer[l - 1].bn_uw >= 0;
+  float* bnp = S.bn;            // this layer: mean, rstd, w, beta
+  float* sS = S.bn + 4 * D;     // S1, S2 of this layer
+  float* part = Bf.part + (size_t)blockIdx.x * P.n_part;
+  if (bn) {
+    tr_bn_setup(Bf, ly, l, D, bt.B, bnp, nullptr, false, nullptr, nullptr);
+    tr_colsum(Bf.s_part[l & 1], Bf.G, 2 * D, sS, S.red);
+    if (blockIdx.x == 0)
+      for (int d = threadIdx.x; d < D; d += TR_THREADS) {
+        Bf.grad[ly.bn_bias + d] = sS[d];
+        const float dw = sS[D + d] - 1.f / bnp[2 * D + d];
+        Bf.grad[ly.bn_uw + d] = dw * tr_sigmoid(__ldg(Bf.theta_p + ly.bn_uw + d));
+      }
+  }
+  if (ly.lu_bias >= 0) tr_lu_dense(S.Wlu, S.stage, Bf.theta_p, ly, D, false);
+  __syncthreads();
+  const float invB = 1.f / (float)bt.B, invBm1 = 1.f / (float)(bt.B - 1);
+  float p1 = 0.f, p2 = 0.f;  // BatchNorm backward sums of layer l-1 (feature threadIdx.x)
+  bool first = true;
+  const float* dout_in = Bf.dout[l & 1];
+  float* dout_out = Bf.dout[(l - 1) & 1];
+  for (int tile = blockIdx.x; tile < bt.n_tiles; tile += gridDim.x) {
+    const float* rec = Bf.ws + ((size_t)tile * P.rec_total + ly.ws_off) * TR_R;
+    const int nb = ly.rec_floats - 2 * D;
+    tr_copy_async(S.H2, rec, D);
+    tr_copy_async(S.V + ly.buf_off[1] * TR_R, rec + D * TR_R, nb);
+    tr_copy_async(S.Y, rec + (D + nb) * TR_R, D);
+    tr_copy_async(S.X, dout_in + (size_t)tile * D * TR_R, D);
+    if (l > 0) {
+      const TrLayer& lp = P.layer[l - 1];
+      tr_copy_async(S.Pf, Bf.ws + ((size_t)tile * P.rec_total + lp.ws_off + lp.rec_floats - D) * TR_R, D);
+    }
+    tr_cp_commit();
+    tr_prefetch_w(Bf, ly, S, ly.n_lin - 1, false, P.max_dim);
+    if (l == 0) tr_load_x(bt, tile, D, lperm, S.H1, S.ld);  // S.ld: scratch for the row weights
+    if (threadIdx.x < TR_R) S.c[threadIdx.x] = Bf.crow[tile * TR_R + threadIdx.x];
+    for (int e = threadIdx.x; e < P.vals_floats * TR_R; e += TR_THREADS) S.Gv[e] = 0.f;
+    tr_cp_wait<1>();
+    __syncthreads();
+    // dy (in place in X): BatchNorm backward
+    if (bn) {
+      for (int e = threadIdx.x; e < D * TR_R; e += TR_THREADS) {
+        const int d = e / TR_R, r = e - d * TR_R;
+        const float w = bnp[2 * D + d];
+        const float xh = (S.Y[e] - bnp[d]) * bnp[D + d];
+        const float v = S.X[e] - xh * (sS[D + d] - 1.f / w) * invBm1 - sS[d] * invB;
+        S.X[e] = (tile * TR_R + r < bt.B) ? w * bnp[D + d] * v : 0.f;
+      }
+    }
+    for (int e = threadIdx.x; e < ly.d_id * TR_R; e += TR_THREADS) {
+      const int i = e / TR_R, r = e - i * TR_R;
+      S.V[e] = S.H2[itab[ly.id_off + i] * TR_R + r];
+    }
+    __syncthreads();
+    // coupling backward: Gv[last] = d params, Y := d h2 (transformed half)
+    {
+      const int last = ly.buf_off[ly.n_buf - 1] * TR_R;
+      const float* prm = S.V + last;
+      float* gprm = S.Gv + last;
+      for (int e = threadIdx.x; e < ly.d_tr * TR_R; e += TR_THREADS) {
+        const int i = e / TR_R, r = e - i * TR_R;
+        const int f = itab[ly.tr_off + i];
+        const float dt2 = S.X[f * TR_R + r];
+        if (P.additive) {
+          gprm[e] = dt2;
+          S.Y[f * TR_R + r] = dt2;
+        } else {
+          const float sg = tr_sigmoid(prm[ly.d_tr * TR_R + e] + 2.f);
+          const float s = sg + 1e-3f;
+          const float ds = dt2 * S.H2[f * TR_R + r] - S.c[r] / s;
+          gprm[e] = dt2;
+          gprm[ly.d_tr * TR_R + e] = ds * sg * (1.f - sg);
+          S.Y[f * TR_R + r] = dt2 * s;
+        }
+      }
+    }
+    __syncthreads();
+    // conditioner backward
+    for (int j = ly.n_lin - 1; j >= 0; --j) {
+      const TrLinear& ln = ly.lin[j];
+      const float* src = S.V + ly.buf_off[ln.in_buf] * TR_R;
+      const float* delta = S.Gv + ly.buf_off[ln.out_buf] * TR_R;
+      const float* Aop = src;
+      if (ln.pre_act) {
+        for (int e = threadIdx.x; e < ln.n_in * TR_R; e += TR_THREADS) S.A[e] = tr_act(act, src[e]);
+        Aop = S.A;
+      }
+      if (j > 0) {
+        tr_prefetch_w(Bf, ly, S, j - 1, false, P.max_dim);
+        tr_cp_wait<1>();
+      } else {
+        tr_cp_wait<0>();
+      }
+      __syncthreads();
+      tr_wgrad(part + ln.w_off, delta, Aop, ln.n_out, ln.n_in, first);
+      tr_bgrad(part + ln.b_off, delta, ln.n_out, first);
+      __syncthreads();
+      // A := W^T delta (input gradient before the activation derivative)
+      tr_gemm(S.A, delta, S.W + (j & 1) * S.wbuf, ln.n_in, nullptr, nullptr, ln.n_in, ln.n_out, false);
+      __syncthreads();
+      float* gin = S.Gv + ly.buf_off[ln.in_buf] * TR_R;
+      for (int e = threadIdx.x; e < ln.n_in * TR_R; e += TR_THREADS)
+        gin[e] += ln.pre_act ? S.A[e] * tr_dact(act, src[e]) : S.A[e];
+      if (ln.res_buf >= 0) {
+        float* gres = S.Gv + ly.buf_off[ln.res_buf] * TR_R;
+        for (int e = threadIdx.x; e < ln.n_out * TR_R; e += TR_THREADS) gres[e] += delta[e];
+      }
+      __syncthreads();
+    }
+    // d h2 (identity half) = dy + d(net input)
+    for (int e = threadIdx.x; e < ly.d_id * TR_R; e += TR_THREADS) {
+      const int i = e / TR_R, r = e - i * TR_R;
+      const int f = itab[ly.id_off + i];
+      S.Y[f * TR_R + r] = S.X[f * TR_R + r] + S.Gv[e];
+    }
+    // layer input h1 (and x-hat of the previous BatchNorm, into X)
+    __syncthreads();
+    if (l > 0) {
+      if (bn_prev) {
+        // previous layer's BatchNorm constants: published by FWD(l) block 0
+        const TrLayer& lp = P.layer[l - 1];
+        for (int e = threadIdx.x; e < D * TR_R; e += TR_THREADS) {
+          const int j = e / TR_R, r = e - j * TR_R;
+          const int d = lperm ? lperm[j] : j;
+          const float mean = Bf.stats[((l - 1) * 2) * D + d];
+          const float rstd = rsqrtf(Bf.stats[((l - 1) * 2 + 1) * D + d] + TR_BN_EPS);
+          const float w = tr_softplus(__ldg(Bf.theta_p + lp.bn_uw + d)) + TR_BN_EPS;
+          const float xh = (S.Pf[d * TR_R + r] - mean) * rstd;
+          S.H1[j * TR_R + r] = fmaf(w, xh, __ldg(Bf.theta_p + lp.bn_bias + d));
+          S.X[d * TR_R + r] = xh;
+        }
+      } else {
+        for (int e = threadIdx.x; e < D * TR_R; e += TR_THREADS) {
+          const int j = e / TR_R, r = e - j * TR_R;
+          S.H1[e] = S.Pf[(lperm ? lperm[j] : j) * TR_R + r];
+        }
+      }
+    }
+    __syncthreads();
+    const float* dh1 = S.Y;
+    if (ly.lu_bias >= 0) {
+      tr_wgrad(part + ly.lu_part_off, S.Y, S.H1, D, D, first);
+      tr_bgrad(part + ly.lu_bias, S.Y, D, first);
+      tr_gemm(S.A, S.Y, S.Wlu, D, nullptr, nullptr, D, D, false);
+      dh1 = S.A;
+      __syncthreads();
+    }
+    if (l > 0) {
+      // un-permute into H2, store, and accumulate the previous BatchNorm's backward sums
+      for (int e = threadIdx.x; e < D * TR_R; e += TR_THREADS) {
+        const int j = e / TR_R, r = e - j * TR_R;
+        S.H2[(lperm ? lperm[j] : j) * TR_R + r] = dh1[e];
+      }
+      __syncthreads();
+      tr_copy(dout_out + (size_t)tile * D * TR_R, S.H2, D);
+      if (bn_prev && (int)threadIdx.x < D) {
+        for (int r = 0; r < TR_R; ++r) {
+          const float g = S.H2[threadIdx.x * TR_R + r];
+          p1 += g;
+          p2 = fmaf(g, S.X[threadIdx.x * TR_R + r], p2);
+        }
+      }
+    }
+    first = false;
+    __syncthreads();
+  }
+  if (first) {
+    // this CTA had no tile: its partial vector must still be defined for REDUCE
+    for (int j = 0; j < ly.n_lin; ++j) {
+      const TrLinear& ln = ly.lin[j];
+      for (int e = threadIdx.x; e < ln.n_in * ln.n_out; e += TR_THREADS) part[ln.w_off + e] = 0.f;
+      for (int e = threadIdx.x; e < ln.n_out; e += TR_THREADS) part[ln.b_off + e] = 0.f;
+    }
+    if (ly.lu_bias >= 0) {
+      for (int e = threadIdx.x; e < D * D; e += TR_THREADS) part[ly.lu_part_off + e] = 0.f;
+      for (int e = threadIdx.x; e < D; e += TR_THREADS) part[ly.lu_bias + e] = 0.f;
+    }
+  }
+  if (bn_prev && (int)threadIdx.x < D) {
+    float* sp = Bf.s_part[(l - 1) & 1] + (size_t)blockIdx.x * 2 * D;
+    sp[threadIdx.x] = p1;
+    sp[D + threadIdx.x] = p2;
+  }
+}
+
+// ============================================================================ REDUCE
+// grad = sum of the per-CTA partials; LU chain rule (dense dW -> lower / upper / diagonal);
+// per-block sums of squares for the global gradient norm.
+__global__ void __launch_bounds__(TR_RED_THREADS) tr_reduce_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf) {
+  const int D = P.D, G = Bf.G, n_part = P.n_part;
+  __shared__ float red[TR_RED_THREADS];
+  float sq = 0.f;
+  const int b = blockIdx.x;
+  // sum over the per-CTA partials with 8 independent loads in flight
+  auto psum = [&](const float* src) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int g = 0;
+    for (; g + 8 <= G; g += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += src[(size_t)(g + u) * n_part];
+    }
+#pragma unroll
+    for (int u = 0; u < 7; ++u)
+      if (g + u < G) acc[u] += src[(size_t)(g + u) * n_part];
+    return ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  };
+  if (b < P.L) {
+    const TrLayer& ly = P.layer[b];
+    if (ly.bn_uw >= 0)
+      for (int d = threadIdx.x; d < D; d += TR_RED_THREADS) {
+        const float g0 = Bf.grad[ly.bn_bias + d], g1 = Bf.grad[ly.bn_uw + d];
+        sq += g0 * g0 + g1 * g1;
+      }
+    if (ly.lu_bias >= 0) {
+      float* sdW = tr_smem_dyn;         // [D][D]
+      float* sLo = sdW + D * D;          // [D][D]
+      float* sUp = sLo + D * D;          // [D][D]
+      for (int e = threadIdx.x; e < D * D; e += TR_RED_THREADS) {
+        sdW[e] = psum(Bf.part + ly.lu_part_off + e);
+        const int i = e / D, j = e - i * D;
+        sLo[e] = i == j ? 1.f : (j < i ? __ldg(Bf.theta_p + ly.lu_lower + i * (i - 1) / 2 + j) : 0.f);
+        sUp[e] = i == j ? tr_softplus(__ldg(Bf.theta_p + ly.lu_diag + i)) + TR_LU_EPS
+                        : (i < j ? __ldg(Bf.theta_p + ly.lu_upper + i * D - i * (i + 1) / 2 + (j - i - 1)) : 0.f);
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < D * D; e += TR_RED_THREADS) {
+        const int i = e / D, j = e - i * D;
+        if (j < i) {  // d lower[i][j] = sum_k dW[i][k] Up[j][k]
+          float s = 0.f;
+          for (int k = j; k < D; ++k) s = fmaf(sdW[i * D + k], sUp[j * D + k], s);
+          Bf.grad[ly.lu_lower + i * (i - 1) / 2 + j] = s;
+          sq += s * s;
+        } else {  // d upper[i][j] = sum_k Lo[k][i] dW[k][j]
+          float s = 0.f;
+          for (int k = i; k < D; ++k) s = fmaf(sLo[k * D + i], sdW[k * D + j], s);
+          if (i == j) {
+            s = (s - 1.f / sUp[e]) * tr_sigmoid(__ldg(Bf.theta_p + ly.lu_diag + i));
+            Bf.grad[ly.lu_diag + i] = s;
+          } else {
+            Bf.grad[ly.lu_upper + i * D - i * (i + 1) / 2 + (j - i - 1)] = s;
+          }
+          sq += s * s;
+        }
+      }
+    }
+  } else {
+    // 8 lanes per parameter (each sums every 8th partial, all loads independent), then a
+    // 3-step shuffle: one memory latency per parameter instead of G/8
+    const int n_reduce = P.n_reduce;
+    const int sub = threadIdx.x & 7;
+    const int per_block = TR_RED_THREADS / 8;
+    for (int i = (b - P.L) * per_block + (threadIdx.x >> 3); i < n_reduce + per_block;
+         i += (gridDim.x - P.L) * per_block) {
+      const bool ok = i < n_reduce;
+      const int p = ok ? Bf.reduce_idx[i] : 0;
+      const float* src = Bf.part + p;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (ok) {
+        int g = sub;
+        for (; g + 24 < G; g += 32) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] += src[(size_t)(g + 8 * u) * n_part];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (g + 8 * u < G) acc[u] += src[(size_t)(g + 8 * u) * n_part];
+      }
+      float sgm = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+      sgm += __shfl_xor_sync(0xffffffffu, sgm, 1);
+      sgm += __shfl_xor_sync(0xffffffffu, sgm, 2);
+      sgm += __shfl_xor_sync(0xffffffffu, sgm, 4);
+      if (ok && sub == 0) {
+        Bf.grad[p] = sgm;
+        sq += sgm * sgm;
+      }
+    }
+  }
+  const float tot = tr_block_sum<TR_RED_THREADS>(sq, red);
+  if (threadIdx.x == 0) Bf.gn_part[b] = tot;
+}
+
+// ============================================================================ ADAM
+// clip_grad_norm_ + torch.optim.AdamW / Adam / SGD on the flat parameter vector.
+// d_loss[0] = this step's loss, d_loss[1] = gradient norm before clipping.
+__global__ void __launch_bounds__(256) tr_adam_kernel(TrBuffers Bf, int n_params, TrOptim o, float* __restrict__ m,
+                                                      float* __restrict__ v, float* d_loss,
+                                                      float* d_loss_accum) {
+  __shared__ float s_coef;
+  __shared__ float red[256];
+  {
+    float gsum = 0.f;
+    for (int i = threadIdx.x; i < Bf.n_reduce_blocks; i += blockDim.x) gsum += Bf.gn_part[i];
+    float lsum = 0.f;
+    if (blockIdx.x == 0)
+      for (int g = threadIdx.x; g < Bf.G; g += blockDim.x) lsum += Bf.loss_part[g];
+    red[threadIdx.x] = gsum;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+      if ((int)threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+      __syncthreads();
+    }
+    const float gn = sqrtf(red[0]);
+    __syncthreads();
+    red[threadIdx.x] = lsum;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+      if ((int)threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      s_coef = o.clip > 0.f ? fminf(1.f, o.clip / (gn + 1e-6f)) : 1.f;
+      if (blockIdx.x == 0) {
+        const float loss = red[0];
+        if (d_loss) d_loss[0] = loss, d_loss[1] = gn;
+        if (d_loss_accum) d_loss_accum[0] += loss;
+      }
+    }
+    __syncthreads();
+  }
+  const float coef = s_coef;
+  const int n = n_params;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float g = Bf.grad[i] * coef;
+    if (o.kind < 0) {
+      Bf.grad[i] = g;
+      continue;
+    }
+    float p = Bf.theta_p[i];
+    if (o.kind == 2) {
+      if (o.weight_decay != 0.f) g = fmaf(o.weight_decay, p, g);
+      Bf.theta_p[i] = p - o.lr * g;
+      continue;
+    }
+    if (o.kind == 0) p *= 1.f - o.lr * o.weight_decay;
+    else if (o.weight_decay != 0.f) g = fmaf(o.weight_decay, p, g);
+    const float mi = o.beta1 * m[i] + (1.f - o.beta1) * g;
+    const float vi = o.beta2 * v[i] + (1.f - o.beta2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(o.bc2) + o.eps;
+    Bf.theta_p[i] = p - (o.lr / o.bc1) * (mi / denom);
+  }
+}
+
+// ============================================================================ EVAL
+// Eval-mode loss (FlowModel._validate, flowmodel/base.py:454-523): running statistics, every layer
+// of a tile in one pass.  out_part[g] = {sum c logp, sum c}; also per-row log_prob when d_logp.
+__global__ void __launch_bounds__(TR_THREADS) tr_eval_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf, TrBatch bt, float* out_part,
+                                                             float* d_logp) {
+  const int D = P.D, L = P.L;
+  TrSmem S = tr_carve(tr_smem_dyn, P, false);
+  tr_stage_itab(Bf, P, S);
+  const float cld = tr_const_logdet(Bf, P, nullptr, S.red);
+  float loss = 0.f, csum = 0.f;
+  for (int tile = blockIdx.x; tile < bt.n_tiles; tile += gridDim.x) {
+    for (int l = 0; l < L; ++l) {
+      const TrLayer& ly = P.layer[l];
+      const int* lperm = ly.perm_off >= 0 ? S.itab + ly.perm_off : nullptr;
+      if (ly.lu_bias >= 0) tr_lu_dense(S.Wlu, S.stage, Bf.theta_p, ly, D, true);
+      tr_prefetch_w(Bf, ly, S, 0, true, P.max_dim);
+      if (l == 0) {
+        tr_load_x(bt, tile, D, lperm, S.H1, S.c);
+        if (threadIdx.x < TR_R) S.ld[threadIdx.x] = 0.f;
+      } else {
+        const TrLayer& lp = P.layer[l - 1];
+        if (lp.bn_uw >= 0) {
+          tr_bn_setup_eval(Bf, lp, D, S.bn);
+          tr_bn_apply_perm(S.Y, S.bn, D, lperm, S.H1, nullptr);
+        } else {
+          for (int e = threadIdx.x; e < D * TR_R; e += TR_THREADS) {
+            const int j = e / TR_R, r = e - j * TR_R;
+            S.H1[e] = S.Y[(lperm ? lperm[j] : j) * TR_R + r];
+          }
+        }
+      }
+      __syncthreads();
+      tr_layer_forward(Bf, P, ly, S, nullptr);
+    }
+    const TrLayer& ll = P.layer[L - 1];
+    if (ll.bn_uw >= 0) {
+      tr_bn_setup_eval(Bf, ll, D, S.bn);
+      tr_bn_apply_perm(S.Y, S.bn, D, nullptr, S.H1, nullptr);
+    } else {
+      for (int e = threadIdx.x; e < D * TR_R; e += TR_THREADS) S.H1[e] = S.Y[e];
+    }
+    __syncthreads();
+    if (threadIdx.x < TR_R) {
+      float q = 0.f;
+      for (int d = 0; d < D; ++d) q += S.H1[d * TR_R + threadIdx.x] * S.H1[d * TR_R + threadIdx.x];
+      const float logp = -0.5f * q - (float)D * TR_HALF_LOG_2PI + S.ld[threadIdx.x] + cld;
+      const int row = tile * TR_R + threadIdx.x;
+      if (row < bt.B) {
+        loss += S.c[threadIdx.x] * logp;
+        csum += S.c[threadIdx.x];
+        if (d_logp) d_logp[row] = logp;
+      }
+    }
+    __syncthreads();
+  }
+  const float a = tr_block_sum(threadIdx.x < TR_R ? loss : 0.f, S.red);
+  const float b = tr_block_sum(threadIdx.x < TR_R ? csum : 0.f, S.red);
+  if (threadIdx.x == 0) out_part[2 * blockIdx.x] = a, out_part[2 * blockIdx.x + 1] = b;
+}
+
+__global__ void tr_eval_final_kernel(const float* part, int G, float* d_loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int g = 0; g < G; ++g) a += part[2 * g], b += part[2 * g + 1];
+    d_loss[0] = -a / b;
+  }
+}
+
+}  // namespace nb200

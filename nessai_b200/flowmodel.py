@@ -125,6 +125,7 @@ class B200Flow(torch.nn.Module):
             raise RuntimeError("nessai_b200 requires a CUDA device (B200, sm_100a)")
         theta, ints = spec.init_state()
         self.ints = ints
+        self.ints_version = 0
         self.theta_p = torch.nn.Parameter(
             torch.from_numpy(theta[: spec.n_params].copy()).to(self.device)
         )
@@ -133,7 +134,6 @@ class B200Flow(torch.nn.Module):
         )
         self._handle = C.c_void_p()
         self._dirty = True
-        self._eager = None
         lib = _lib.load()
         with torch.cuda.device(self.device):
             _lib.check(
@@ -173,9 +173,8 @@ class B200Flow(torch.nn.Module):
             for k, v in state_dict.items()
         }
         self.spec.load_state_dict_numpy(sd, theta, self.ints, strict=strict)
+        self.ints_version += 1
         self.set_theta_numpy(theta)
-        if self._eager is not None:
-            self._eager.update_ints(self.ints)
 
     def to(self, device=None, *args, **kwargs):
         if device is not None and torch.device(device).type != "cuda":
@@ -322,14 +321,6 @@ class B200Flow(torch.nn.Module):
         off = self._rng_rows
         self._rng_rows += int(n_rows)
         return C.c_uint64(self._rng_seed), C.c_uint64(off)
-
-    def eager(self):
-        from .train_eager import EagerFlow
-
-        if self._eager is None:
-            self._eager = EagerFlow(self.spec, self.ints, self.device)
-        return self._eager
-
 
 
 class B200FlowModel:
@@ -484,54 +475,51 @@ class B200FlowModel:
         self.model.end_iteration()
 
     # --------------------------------------------------------------- training
-    def _loss(self, x, w, training):
+    def _trainer(self):
+        """The fused training kernels bound to the current model (rebuilt when the
+        permutations / masks change)."""
         model = self.model
-        lp = model.eager().log_prob((model.theta_p, model.theta_b), x, training=training)
-        if w is not None:
-            return -torch.sum(lp * w) / torch.sum(w)
-        return -lp.mean()
+        key = (id(model), model.ints_version)
+        if getattr(self, "_fused", None) is None or self._fused_key != key:
+            from .trainer import FusedTrainer
+
+            self._fused = FusedTrainer(model)
+            self._fused_key = key
+        return self._fused
 
     def _train(self, train_data, noise_scale=0.0, is_dataloader=False, weighted=False, is_conditional=False):
-        """One epoch (flowmodel/base.py:365-452).  The batch permutation comes
-        from torch's CPU generator like the reference's ``torch.randperm``; the
-        per-batch loss stays on the device (one host sync per epoch, not per
-        batch)."""
+        """One epoch (flowmodel/base.py:365-452) as ONE call into the fused kernels:
+        every batch runs forward + backward + clip + optimiser step on the device.
+        The batch permutation comes from torch's CPU generator like the reference's
+        ``torch.randperm``; the mean batch loss is read back once per epoch."""
         model = self.model
         model.train()
         x_all, w_all = (train_data if weighted else (train_data, None))
-        p = torch.randperm(x_all.shape[0]).to(self.device)
-        x_all = x_all[p, :]
-        if w_all is not None:
-            w_all = w_all[p]
-        total = torch.zeros((), device=self.device)
-        n = 0
-        clip = self.training_config["clip_grad_norm"]
-        for i0 in range(0, x_all.shape[0], self._batch_size):
-            x = x_all[i0 : i0 + self._batch_size]
-            w = None if w_all is None else w_all[i0 : i0 + self._batch_size]
-            if noise_scale:
-                x = x + noise_scale * torch.randn_like(x)
-            model.theta_p.grad = None
-            loss = self._loss(x, w, training=True)
-            total += loss.detach()
-            loss.backward()
-            if clip:
-                torch.nn.utils.clip_grad_norm_(model.parameters(), clip)
-            self._optimiser.step()
-            n += 1
+        perm = torch.randperm(x_all.shape[0]).to(self.device)
+        if noise_scale:
+            x_all = x_all + noise_scale * torch.randn_like(x_all)
+        n_batches = -(-x_all.shape[0] // self._batch_size)
+        total = self._trainer().epoch(
+            x_all, w_all, perm, self._batch_size, self._optimiser, self.training_config["clip_grad_norm"]
+        )
         self.end_iteration()
         if self.training_config["annealing"]:
-            self.scheduler.step()
-        return float(total.item()) / n
+            self._epochs_done += 1
+            from .trainer import cosine_annealing_lr
+
+            for g in self._optimiser.param_groups:
+                g["lr"] = cosine_annealing_lr(self._base_lr, self._epochs_done, self._t_max)
+        self._pending_train_loss = (total, n_batches)
+        return None
 
     def _validate(self, val_data, is_dataloader=False, weighted=False, is_conditional=False):
-        """flowmodel/base.py:454-523: eval mode (running statistics)."""
+        """flowmodel/base.py:454-523: eval mode (running statistics); returns the
+        device scalar (read back together with the training loss)."""
         x, w = (val_data if weighted else (val_data, None))
         if not len(x):
-            return np.nan
+            return None
         self.model.eval()
-        with torch.no_grad():
-            return float(self._loss(x, w, training=False).item())
+        return self._trainer().eval_loss(x, w)
 
     def finalise(self):
         self.model.finalise()
@@ -569,7 +557,10 @@ class B200FlowModel:
         if max_epochs is None:
             max_epochs = self.training_config["max_epochs"]
         if self.training_config["annealing"]:
-            self.scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(self._optimiser, max_epochs)
+            # torch.optim.lr_scheduler.CosineAnnealingLR(optimiser, max_epochs), closed form
+            self._base_lr = float(self._optimiser.param_groups[0]["lr"])
+            self._t_max = max_epochs
+            self._epochs_done = 0
         if patience is None:
             patience = self.training_config["patience"]
         best_epoch = 0
@@ -580,8 +571,13 @@ class B200FlowModel:
         current_weights_file = os.path.join(output, "model.pt")
         epoch = 0
         for epoch in range(1, max_epochs + 1):
-            loss = self._train(train_data, noise_scale=noise_scale, weighted=weighted)
-            val_loss = self._validate(val_data, weighted=weighted)
+            self._train(train_data, noise_scale=noise_scale, weighted=weighted)
+            val_dev = self._validate(val_data, weighted=weighted)
+            # the single host synchronisation of the epoch: both losses in one read
+            total, n_batches = self._pending_train_loss
+            both = self._fused._loss.cpu().numpy()
+            loss = float(both[0]) / n_batches
+            val_loss = float(both[1]) if val_dev is not None else np.nan
             history["loss"].append(loss)
             history["val_loss"].append(val_loss)
             if validate and (val_loss < best_val_loss):
@@ -645,9 +641,8 @@ class B200FlowModel:
                 model.spec.reset_weights(theta)
             else:
                 model.spec.reset_permutations(theta, model.ints)
+        model.ints_version += 1
         model.set_theta_numpy(theta)
-        if model._eager is not None:
-            model._eager.update_ints(model.ints)
         self._optimiser = self.get_optimiser()
 
     # -------------------------------------------------------------- inference
@@ -709,4 +704,6 @@ class B200FlowModel:
         state.pop("model", None)
         state.pop("flow_config", None)
         state.pop("scheduler", None)
+        for k in ("_fused", "_fused_key", "_pending_train_loss"):
+            state.pop(k, None)
         return state

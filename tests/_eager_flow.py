@@ -1,16 +1,9 @@
-"""Differentiable train-mode flow on the flat parameter buffer (torch ops).
-
-Used ONLY by ``B200FlowModel.train`` for the optimisation loop
-(/root/reference/src/nessai/flowmodel/base.py:365-452 ``_train``): train-mode
-BatchNorm (batch statistics + running-stat EMA), uncached LU, affine coupling,
-MLP / ResidualNet conditioner -- the arithmetic the reference delegates to
-glasflow.nflows.  Inference (``populate`` and every
-``forward_and_log_prob`` / ``inverse`` / ``sample_and_log_prob`` call) never comes
-here: it runs the hand-written kernels through the C ABI.
-
-INTERIM: this is the autograd stand-in for the fused forward+backward+AdamW
-training kernels; it runs on the CUDA device the flow lives on
-and is also the on-device gradient oracle for those kernels.
+"""TEST INFRASTRUCTURE: differentiable train-mode flow on the flat parameter buffer
+(torch ops + autograd), the on-device gradient cross-check for the fused training
+kernels (``nessai_b200/csrc/train.cuh``).  Restates the train-mode arithmetic the
+reference delegates to glasflow.nflows: batch-statistics BatchNorm,
+uncached LU, affine coupling, MLP / ResidualNet conditioner.  The product never
+imports this file.
 """
 
 from __future__ import annotations
@@ -20,7 +13,7 @@ import math
 import torch
 import torch.nn.functional as F
 
-from .spec import ACT_RELU, ACT_TANH, FlowSpec
+from nessai_b200.spec import ACT_RELU, ACT_TANH, FlowSpec
 
 
 def _act(kind):

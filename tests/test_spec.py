@@ -121,3 +121,44 @@ def test_unsupported_options_fail_loudly():
 def test_n_neurons_auto():
     assert FlowSpec(dict(n_inputs=5, ftype="realnvp")).H == 10
     assert FlowSpec(dict(n_inputs=5, n_neurons="equal", ftype="realnvp")).H == 5
+
+
+def test_train_plan_packs_every_golden_realnvp():
+    """The packed TrPlan (csrc/train.cuh) covers every parameter exactly once:
+    conditioner weights / biases and LU biases through reduce_idx, LU triangles and
+    BatchNorm parameters through their layer records."""
+    from conftest import GOLDEN_NAMES, load_golden
+
+    from nessai_b200.spec import FlowSpec
+    from nessai_b200.train_plan import TR_LAYER_INTS, TR_PLAN_INTS, TrainPlanUnsupported, build_train_plan
+
+    for name in GOLDEN_NAMES:
+        g, cfg, sd = load_golden(name)
+        spec = FlowSpec(cfg)
+        theta = np.zeros(spec.n_theta, dtype=np.float32)
+        ints = {}
+        spec.load_state_dict_numpy(sd, theta, ints)
+        if spec.ftype != "realnvp":
+            with pytest.raises(TrainPlanUnsupported):
+                build_train_plan(spec, ints)
+            continue
+        plan, itab, red = build_train_plan(spec, ints)
+        assert plan.size == TR_PLAN_INTS and plan[0] == spec.D and plan[1] == spec.L
+        covered = np.zeros(spec.n_params, dtype=int)
+        covered[red] += 1
+        D = spec.D
+        ntri = D * (D - 1) // 2
+        for l in range(spec.L):
+            row = plan[16 + l * TR_LAYER_INTS : 16 + (l + 1) * TR_LAYER_INTS]
+            if row[1] >= 0:
+                covered[row[2] : row[2] + ntri] += 1
+                covered[row[3] : row[3] + ntri] += 1
+                covered[row[4] : row[4] + D] += 1
+            if row[5] >= 0:
+                covered[row[5] : row[5] + D] += 1
+                covered[row[6] : row[6] + D] += 1
+            n_buf = row[14]
+            dims = row[20 : 20 + n_buf]
+            assert row[15] == 2 * D + dims[1:].sum()
+            assert dims[0] == row[11] and dims[-1] == row[12] * spec.coupling_multiplier
+        assert (covered == 1).all()
