@@ -290,6 +290,39 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The issuer warp runs CONVERGED and every tcgen05.mma / commit is predicated by elect.sync
+// inside the asm: with warp-uniform operands ptxas keeps descriptors in uniform registers and
+// issues back to back (measured 32.5 cycles per 128x64x16 MMA = the tensor-pipe floor).  Issued
+// from a divergent single-lane branch instead, every MMA is wrapped in an ELECT /
+// R2UR.BROADCAST waterfall loop (47-122 cycles each, scripts/ubench/mma_rate3.cu).
+__device__ __forceinline__ void tc_mma_ss_e(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts_e(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_e(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
@@ -499,91 +532,55 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
   return ld;
 }
 
-// B-operand descriptors of one coupling layer, precomputed once per CTA into shared
-// memory so the single issuing thread only loads and fires (building a descriptor is
-// ~8 dependent integer instructions; 31 of them per layer-step dominated the MMA
-// round-trip latency before).
-constexpr int TC_NDESC = 24;  // [0,1] W1 hi/lo; [2,3] b2 hi/lo; [4..7] W2hi; [8..11] W2lo;
-                              // [12,13] b3 hi/lo; [14..17] W3hi; [18..21] W3lo; [22] ones
-__device__ __forceinline__ void tc_build_desc_table(const TcParams& P, uint32_t img_s,
-                                                    uint64_t* table) {
-  for (int i = threadIdx.x; i < P.L * TC_NDESC; i += blockDim.x) {
-    const int l = i / TC_NDESC, j = i % TC_NDESC;
-    const uint32_t lb = img_s + l * TC_LAYER_BYTES;
-    uint64_t d = 0;
-    if (j == 0) d = tc_desc(lb + TC_OFF_W1HI, TC_H * 16, 128);
-    else if (j == 1) d = tc_desc(lb + TC_OFF_W1LO, TC_H * 16, 128);
-    else if (j == 2) d = tc_desc(lb + TC_OFF_B2HI, TC_H * 16, 128);
-    else if (j == 3) d = tc_desc(lb + TC_OFF_B2LO, TC_H * 16, 128);
-    else if (j < 8) d = tc_desc(lb + TC_OFF_W2HI + (j - 4) * 2 * TC_H * 16, TC_H * 16, 128);
-    else if (j < 12) d = tc_desc(lb + TC_OFF_W2LO + (j - 8) * 2 * TC_H * 16, TC_H * 16, 128);
-    else if (j == 12) d = tc_desc(lb + TC_OFF_B3HI, TC_N3 * 16, 128);
-    else if (j == 13) d = tc_desc(lb + TC_OFF_B3LO, TC_N3 * 16, 128);
-    else if (j < 18) d = tc_desc(lb + TC_OFF_W3HI + (j - 14) * 2 * TC_N3 * 16, TC_N3 * 16, 128);
-    else if (j < 22) d = tc_desc(lb + TC_OFF_W3LO + (j - 18) * 2 * TC_N3 * 16, TC_N3 * 16, 128);
-    else if (j == 22)
-      d = tc_desc(img_s + P.L * TC_LAYER_BYTES + (P.L + 1) * TC_AFF_BYTES, 2048, 128);
-    table[i] = d;
-  }
-}
-
-// MMA issuer (one elected thread) for one epilogue group
-__device__ __forceinline__ void tc_issuer(const TcParams& P, const uint64_t* table, uint32_t tg,
+// MMA issuer for one epilogue group: the WHOLE warp runs this (converged); descriptors are
+// uniform arithmetic on the shared-memory image base.
+__device__ __forceinline__ void tc_issuer(const TcParams& P, uint32_t img_s, uint32_t tg,
                                           uint32_t bar_in, uint32_t bar_out, int64_t my_tiles) {
   constexpr uint32_t ID64 = tc_idesc(128, TC_H), ID16 = tc_idesc(128, TC_N3);
   const uint32_t d = tg + TC_COL_D, ah = tg + TC_COL_AH, al = tg + TC_COL_AL;
+  const uint64_t ones = tc_desc(img_s + P.L * TC_LAYER_BYTES + (P.L + 1) * TC_AFF_BYTES, 2048, 128);
+  // a descriptor `off` bytes further into the image: the start address field is bits [0, 14) >> 4
+  auto adv = [](uint64_t desc, uint32_t off) { return desc + (uint64_t)(off >> 4); };
   uint32_t ph_in = 0;
   for (int64_t it = 0; it < my_tiles; ++it) {
     for (int l = 0; l < P.L; ++l) {
-      const uint64_t* T = table + l * TC_NDESC;
-      const uint64_t ones = T[22];
+      const uint32_t lb = img_s + l * TC_LAYER_BYTES;
+      const uint64_t d64 = tc_desc(lb, TC_H * 16, 128);    // 64-row operands (W1, W2, b2)
+      const uint64_t d16 = tc_desc(lb, TC_N3 * 16, 128);   // 16-row operands (W3, b3)
       // GEMM1: [128 x 16] x [16 x 64]
-      {
-        const uint64_t bh = T[0], bl = T[1];
-        tc_mbar_wait(bar_in, ph_in);
-        ph_in ^= 1;
-        tc_fence_after();
-        tc_mma_ts(d, ah, bh, ID64, 0);
-        tc_mma_ts(d, al, bh, ID64, 1);
-        tc_mma_ts(d, ah, bl, ID64, 1);
-        tc_commit(bar_out);
-      }
+      tc_mbar_wait(bar_in, ph_in);
+      ph_in ^= 1;
+      tc_fence_after();
+      tc_mma_ts_e(d, ah, adv(d64, TC_OFF_W1HI), ID64, 0);
+      tc_mma_ts_e(d, al, adv(d64, TC_OFF_W1HI), ID64, 1);
+      tc_mma_ts_e(d, ah, adv(d64, TC_OFF_W1LO), ID64, 1);
+      tc_commit_e(bar_out);
       // GEMM2: bias + [128 x 64] x [64 x 64]
-      {
-        uint64_t w[10];
+      tc_mbar_wait(bar_in, ph_in);
+      ph_in ^= 1;
+      tc_fence_after();
+      tc_mma_ss_e(d, ones, adv(d64, TC_OFF_B2HI), ID64, 0);
+      tc_mma_ss_e(d, ones, adv(d64, TC_OFF_B2LO), ID64, 1);
 #pragma unroll
-        for (int j = 0; j < 10; ++j) w[j] = T[2 + j];
-        tc_mbar_wait(bar_in, ph_in);
-        ph_in ^= 1;
-        tc_fence_after();
-        tc_mma_ss(d, ones, w[0], ID64, 0);
-        tc_mma_ss(d, ones, w[1], ID64, 1);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          tc_mma_ts(d, ah + 8 * ks, w[2 + ks], ID64, 1);
-          tc_mma_ts(d, al + 8 * ks, w[2 + ks], ID64, 1);
-          tc_mma_ts(d, ah + 8 * ks, w[6 + ks], ID64, 1);
-        }
-        tc_commit(bar_out);
+      for (int ks = 0; ks < 4; ++ks) {
+        tc_mma_ts_e(d, ah + 8 * ks, adv(d64, TC_OFF_W2HI + ks * 2 * TC_H * 16), ID64, 1);
+        tc_mma_ts_e(d, al + 8 * ks, adv(d64, TC_OFF_W2HI + ks * 2 * TC_H * 16), ID64, 1);
+        tc_mma_ts_e(d, ah + 8 * ks, adv(d64, TC_OFF_W2LO + ks * 2 * TC_H * 16), ID64, 1);
       }
+      tc_commit_e(bar_out);
       // GEMM3: bias + [128 x 64] x [64 x 16]
-      {
-        uint64_t w[10];
+      tc_mbar_wait(bar_in, ph_in);
+      ph_in ^= 1;
+      tc_fence_after();
+      tc_mma_ss_e(d, ones, adv(d16, TC_OFF_B3HI), ID16, 0);
+      tc_mma_ss_e(d, ones, adv(d16, TC_OFF_B3LO), ID16, 1);
 #pragma unroll
-        for (int j = 0; j < 10; ++j) w[j] = T[12 + j];
-        tc_mbar_wait(bar_in, ph_in);
-        ph_in ^= 1;
-        tc_fence_after();
-        tc_mma_ss(d, ones, w[0], ID16, 0);
-        tc_mma_ss(d, ones, w[1], ID16, 1);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          tc_mma_ts(d, ah + 8 * ks, w[2 + ks], ID16, 1);
-          tc_mma_ts(d, al + 8 * ks, w[2 + ks], ID16, 1);
-          tc_mma_ts(d, ah + 8 * ks, w[6 + ks], ID16, 1);
-        }
-        tc_commit(bar_out);
+      for (int ks = 0; ks < 4; ++ks) {
+        tc_mma_ts_e(d, ah + 8 * ks, adv(d16, TC_OFF_W3HI + ks * 2 * TC_N3 * 16), ID16, 1);
+        tc_mma_ts_e(d, al + 8 * ks, adv(d16, TC_OFF_W3HI + ks * 2 * TC_N3 * 16), ID16, 1);
+        tc_mma_ts_e(d, ah + 8 * ks, adv(d16, TC_OFF_W3LO + ks * 2 * TC_N3 * 16), ID16, 1);
       }
+      tc_commit_e(bar_out);
     }
   }
 }
@@ -595,7 +592,6 @@ struct TcShared {
   uint32_t pad;
   double cst[4][TC_DP];  // populate: scale, shift, lo, hi
   double log_const;      // populate: D log sqrt(T) + sum log|scale|
-  uint64_t desc[TC_MAXL * TC_NDESC];
 };
 
 __device__ __forceinline__ size_t tc_image_pad(int image_bytes) {
@@ -611,7 +607,6 @@ __device__ __forceinline__ void tc_prologue(const TcParams& P, uint8_t* smem, Tc
     uint4* dst = reinterpret_cast<uint4*>(smem);
     for (int i = tid; i < P.image_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
   }
-  tc_build_desc_table(P, tc_smem_u32(smem), sh->desc);
   if (tid == 0) {
     for (int g = 0; g < TC_NG; ++g) {
       tc_mbar_init(tc_smem_u32(&sh->bar_in[g]), 128);
@@ -696,10 +691,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P
       }
     }
   } else {
-    const int g = warp - TC_NG * 4;
-    if ((threadIdx.x & 31) == 0)
-      tc_issuer(P, sh->desc, tmem + g * TC_COLS, tc_smem_u32(&sh->bar_in[g]),
-                tc_smem_u32(&sh->bar_out[g]), tc_my_tiles(ntiles, g));
+    // issuer warp g: all 32 lanes converged, one elected lane fires each MMA
+    const int g = __shfl_sync(0xffffffffu, warp - TC_NG * 4, 0);
+    tc_issuer(P, tc_smem_u32(tc_smem), __shfl_sync(0xffffffffu, tmem, 0) + g * TC_COLS,
+              tc_smem_u32(&sh->bar_in[g]), tc_smem_u32(&sh->bar_out[g]), tc_my_tiles(ntiles, g));
     __syncwarp();
   }
   tc_epilogue_end(sh);
@@ -756,10 +751,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParam
     }
     populate_publish(A, vmax, vcount);
   } else {
-    const int g = warp - TC_NG * 4;
-    if ((threadIdx.x & 31) == 0)
-      tc_issuer(P, sh->desc, tmem + g * TC_COLS, tc_smem_u32(&sh->bar_in[g]),
-                tc_smem_u32(&sh->bar_out[g]), tc_my_tiles(ntiles, g));
+    // issuer warp g: all 32 lanes converged, one elected lane fires each MMA
+    const int g = __shfl_sync(0xffffffffu, warp - TC_NG * 4, 0);
+    tc_issuer(P, tc_smem_u32(tc_smem), __shfl_sync(0xffffffffu, tmem, 0) + g * TC_COLS,
+              tc_smem_u32(&sh->bar_in[g]), tc_smem_u32(&sh->bar_out[g]), tc_my_tiles(ntiles, g));
     __syncwarp();
   }
   tc_epilogue_end(sh);
