@@ -38,26 +38,28 @@ constexpr int TC_DP = 16;           // padded feature count (registers per row)
 constexpr int TC_N3 = 16;           // padded 2*d_tr
 constexpr int TC_TR0 = 8;           // register slot of the first transformed feature
 constexpr int TC_MAXL = 8;
-constexpr int TC_W1_BYTES = TC_H * 16 * 2;            // 2 K-chunks x (64 rows x 16 B); bias at k = 8
+constexpr int TC_W1_BYTES = TC_H * 16 * 2;            // 2 K-chunks x (64 rows x 16 B): K = 16 state slots
 constexpr int TC_W2_BYTES = TC_H * 16 * (TC_H / 8);   // 8 chunks x 1 KB
 constexpr int TC_W3_BYTES = TC_N3 * 16 * (TC_H / 8);  // 8 chunks x 256 B
-// biases of GEMM2 / GEMM3 as B operands of one extra K=16 step against a constant
-// "ones" A operand (element k = 0 is 1): D = ones x [b; 0] initialises the accumulator
-constexpr int TC_B2_BYTES = TC_H * 16 * 2;            // 2 chunks x (64 rows x 16 B)
-constexpr int TC_B3_BYTES = TC_N3 * 16 * 2;           // 2 chunks x (16 rows x 16 B)
+// Biases enter as ONE extra K=16 step against a constant "ones" A operand whose elements
+// k = 0, 1 are 1: the B operand carries bias_hi at k = 0 and bias_lo at k = 1 (K-chunk 0 only;
+// its K-chunk 1 is a shared all-zero chunk reached through the descriptor's LBO).
+constexpr int TC_B1_BYTES = TC_H * 16;
+constexpr int TC_B2_BYTES = TC_H * 16;
+constexpr int TC_B3_BYTES = TC_N3 * 16;
 constexpr int TC_LAYER_BYTES =
-    2 * (TC_W1_BYTES + TC_W2_BYTES + TC_W3_BYTES + TC_B2_BYTES + TC_B3_BYTES);
+    2 * (TC_W1_BYTES + TC_W2_BYTES + TC_W3_BYTES) + TC_B1_BYTES + TC_B2_BYTES + TC_B3_BYTES;
 constexpr int TC_ONES_BYTES = 2 * 2048;               // A operand [128 x 16] bf16, shared by all groups
+constexpr int TC_ZERO_BYTES = TC_H * 16;              // all-zero K-chunk 1 of the bias operands
 constexpr int TC_OFF_W1HI = 0;
 constexpr int TC_OFF_W1LO = TC_W1_BYTES;
 constexpr int TC_OFF_W2HI = 2 * TC_W1_BYTES;
 constexpr int TC_OFF_W2LO = TC_OFF_W2HI + TC_W2_BYTES;
 constexpr int TC_OFF_W3HI = TC_OFF_W2LO + TC_W2_BYTES;
 constexpr int TC_OFF_W3LO = TC_OFF_W3HI + TC_W3_BYTES;
-constexpr int TC_OFF_B2HI = TC_OFF_W3LO + TC_W3_BYTES;
-constexpr int TC_OFF_B2LO = TC_OFF_B2HI + TC_B2_BYTES;
-constexpr int TC_OFF_B3HI = TC_OFF_B2LO + TC_B2_BYTES;
-constexpr int TC_OFF_B3LO = TC_OFF_B3HI + TC_B3_BYTES;
+constexpr int TC_OFF_B1 = TC_OFF_W3LO + TC_W3_BYTES;
+constexpr int TC_OFF_B2 = TC_OFF_B1 + TC_B1_BYTES;
+constexpr int TC_OFF_B3 = TC_OFF_B2 + TC_B2_BYTES;
 constexpr int TC_AFF_BYTES = (TC_DP * TC_DP + TC_DP) * 4;
 // TMEM columns of one epilogue group (one 128-row tile in flight)
 constexpr int TC_COLS = 128;
@@ -170,23 +172,43 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
     t.d_tr[l] = c.d_tr;
   }
   const int ones_off = L * TC_LAYER_BYTES + (L + 1) * TC_AFF_BYTES;
-  const int bytes = ones_off + TC_ONES_BYTES;
+  const int bytes = ones_off + TC_ONES_BYTES + TC_ZERO_BYTES;
   if (((bytes + 1023) & ~1023) + 4096 > 227 * 1024) return 0;  // does not fit: generic kernel
   std::vector<uint8_t> img((size_t)bytes, 0);
-  for (int m = 0; m < 128; ++m) {  // element (m, k = 0) = 1.0 (bf16 0x3F80)
-    const uint16_t one = 0x3F80;
-    memcpy(img.data() + ones_off + (size_t)m * 16, &one, 2);
+  for (int m = 0; m < 128; ++m) {  // elements (m, k = 0) and (m, k = 1) are 1.0 (bf16 0x3F80)
+    const uint16_t one[2] = {0x3F80, 0x3F80};
+    memcpy(img.data() + ones_off + (size_t)m * 16, one, 4);
   }
+  auto slot = [&](int layer, int j) {  // register slot of natural feature j; layer < 0 or >= L: natural
+    if (layer < 0 || layer >= L) return j;
+    return j < t.d_id[layer] ? j : TC_TR0 + (j - t.d_id[layer]);
+  };
+  // bias operand: (n, k = 0) = hi, (n, k = 1) = lo
+  auto put_bias = [&](uint8_t* base, int n, float b) {
+    const uint16_t hi = tc_bf16_rn(b);
+    const uint16_t lo = tc_bf16_rn(b - tc_bf16_to_f(hi));
+    memcpy(base + (size_t)n * 16, &hi, 2);
+    memcpy(base + (size_t)n * 16 + 2, &lo, 2);
+  };
   for (int l = 0; l < L; ++l) {
     uint8_t* lb = img.data() + (size_t)l * TC_LAYER_BYTES;
+    const FlowOp& f = ops[4 * l];  // the affine in front of coupling l
     const FlowOp& a = ops[1 + 4 * l];
     const FlowOp& b = ops[2 + 4 * l];
     const FlowOp& c = ops[3 + 4 * l];
-    // W1: (n, k) = blob[w_off + k*Npad + n]; bias rides at k = d_id
+    // GEMM1 consumes the state BEFORE the affine (so the fp32 affine runs on the CUDA cores
+    // while the tensor core works): W1' = W1 A[:, identity], b1' = b1 + W1 b[identity], float64
     for (int n = 0; n < TC_H; ++n) {
-      for (int k = 0; k < a.K; ++k)
-        tc_put(lb + TC_OFF_W1HI, lb + TC_OFF_W1LO, TC_H, n, k, blob[a.w_off + k * a.Npad + n]);
-      tc_put(lb + TC_OFF_W1HI, lb + TC_OFF_W1LO, TC_H, n, TC_TR0, blob[a.b_off + n]);
+      for (int k = 0; k < D; ++k) {
+        double acc = 0.0;
+        for (int j = 0; j < a.K; ++j)
+          acc += (double)blob[a.w_off + j * a.Npad + n] * (double)blob[f.w_off + k * f.Npad + j];
+        tc_put(lb + TC_OFF_W1HI, lb + TC_OFF_W1LO, TC_H, n, slot(l - 1, k), (float)acc);
+      }
+      double bacc = blob[a.b_off + n];
+      for (int j = 0; j < a.K; ++j)
+        bacc += (double)blob[a.w_off + j * a.Npad + n] * (double)blob[f.b_off + j];
+      put_bias(lb + TC_OFF_B1, n, (float)bacc);
     }
     for (int n = 0; n < TC_H; ++n) {
       for (int k = 0; k < TC_H; ++k)
@@ -196,18 +218,12 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
       for (int k = 0; k < TC_H; ++k)
         tc_put(lb + TC_OFF_W3HI, lb + TC_OFF_W3LO, TC_N3, n, k, blob[c.w_off + k * c.Npad + n]);
     }
-    for (int n = 0; n < TC_H; ++n)
-      tc_put(lb + TC_OFF_B2HI, lb + TC_OFF_B2LO, TC_H, n, 0, blob[b.b_off + n]);
-    for (int n = 0; n < c.N; ++n)
-      tc_put(lb + TC_OFF_B3HI, lb + TC_OFF_B3LO, TC_N3, n, 0, blob[c.b_off + n]);
+    for (int n = 0; n < TC_H; ++n) put_bias(lb + TC_OFF_B2, n, blob[b.b_off + n]);
+    for (int n = 0; n < c.N; ++n) put_bias(lb + TC_OFF_B3, n, blob[c.b_off + n]);
   }
   // Affines, re-laid-out to the kernel's register slots: inside coupling layer l the
   // identity features live in slots [0, d_id) and the transformed ones in
   // [TC_TR0, TC_TR0 + d_tr); the flow's input / output use the natural order.
-  auto slot = [&](int layer, int j) {  // layer < 0 or >= L: natural order
-    if (layer < 0 || layer >= L) return j;
-    return j < t.d_id[layer] ? j : TC_TR0 + (j - t.d_id[layer]);
-  };
   for (int i = 0; i <= L; ++i) {
     const FlowOp& f = ops[4 * i];
     float* A = reinterpret_cast<float*>(img.data() + (size_t)L * TC_LAYER_BYTES +
@@ -442,6 +458,27 @@ __device__ __forceinline__ void tc_affine(const float* __restrict__ A, float (&h
   for (int k = 0; k < TC_DP; ++k) h[k] = o[k];
 }
 
+#ifdef NB200_TC_TRACE
+// Debug build only: clock64 stamps of CTA 0 (epilogue group 0 thread 0: even slots; issuer 0:
+// odd slots) to find where a tile-layer's latency goes.  Read back with nb200_debug_trace().
+__device__ long long tc_trace_buf[2][4096];
+__device__ int tc_trace_n[2];
+__device__ __forceinline__ void tc_stamp(int who, int tag) {
+  if (blockIdx.x == 0) {
+    const int i = tc_trace_n[who];
+    if (i < 4096) {
+      tc_trace_buf[who][i] = (clock64() << 8) | tag;
+      tc_trace_n[who] = i + 1;
+    }
+  }
+}
+#define TC_STAMP_E(tag) do { if (threadIdx.x == 0) tc_stamp(0, tag); } while (0)
+#define TC_STAMP_I(tag) do { if (threadIdx.x == TC_NG * 128) tc_stamp(1, tag); } while (0)
+#else
+#define TC_STAMP_E(tag) do { } while (0)
+#define TC_STAMP_I(tag) do { } while (0)
+#endif
+
 struct TcIO {
   // apply mode
   const float* in;
@@ -460,42 +497,46 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
                                             float (&h)[TC_DP]) {
   const float* aff = reinterpret_cast<const float*>(img + (size_t)P.L * TC_LAYER_BYTES);
   float ld = 0.f;
-  tc_affine(aff, h);
   for (int l = 0; l < P.L; ++l) {
     const int d_tr = P.d_tr[l];
-    // ---- E0: identity features (slots 0..7; unused slots are zero) + the constant 1
-    //      that carries the first-layer bias -> A1 (16 bf16 = 8 columns, hi and lo)
+    // ---- E0: the 16 state slots BEFORE this layer's affine -> A1 (16 bf16 = 8 columns,
+    //      hi and lo); GEMM1 carries the affine folded into its weights
     {
       uint32_t hi[8], lo[8];
-      tc_split2<false>(h[0], h[1], hi[0], lo[0]);
-      tc_split2<false>(h[2], h[3], hi[1], lo[1]);
-      tc_split2<false>(h[4], h[5], hi[2], lo[2]);
-      tc_split2<false>(h[6], h[7], hi[3], lo[3]);
-      hi[4] = 0x00003F80u;  // element 8 == 1.0 (bf16)
-      hi[5] = hi[6] = hi[7] = 0u;
-      lo[4] = lo[5] = lo[6] = lo[7] = 0u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) tc_split2<false>(h[2 * j], h[2 * j + 1], hi[j], lo[j]);
       tc_st8(tg + TC_COL_AH, hi);
       tc_st8(tg + TC_COL_AL, lo);
       tc_wait_st();
     }
     tc_fence_before();
+    TC_STAMP_E(1);
     tc_mbar_arrive(bar_in);
-    // ---- E1: hidden layer 1 (bias rode in GEMM1)
+    // the fp32 affine in front of the coupling, in the shadow of GEMM1
+#ifndef NB200_ABL_NO_AFFINE
+    tc_affine(aff + (size_t)l * (TC_AFF_BYTES / 4), h);
+#endif
+    // ---- E1: hidden layer 1
     tc_mbar_wait(bar_out, ph_out);
+    TC_STAMP_E(2);
     ph_out ^= 1;
     tc_fence_after();
     tc_hidden_epilogue(tg);
     tc_fence_before();
+    TC_STAMP_E(3);
     tc_mbar_arrive(bar_in);
     // ---- E2: hidden layer 2
     tc_mbar_wait(bar_out, ph_out);
+    TC_STAMP_E(4);
     ph_out ^= 1;
     tc_fence_after();
     tc_hidden_epilogue(tg);
     tc_fence_before();
+    TC_STAMP_E(5);
     tc_mbar_arrive(bar_in);
     // ---- E3: coupling on the transformed half, then the next affine
     tc_mbar_wait(bar_out, ph_out);
+    TC_STAMP_E(6);
     ph_out ^= 1;
     tc_fence_after();
     uint32_t r[16];
@@ -525,10 +566,8 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
         ld += P.inverse ? -ls : ls;
       }
     }
-#ifndef NB200_ABL_NO_AFFINE
-    tc_affine(aff + (size_t)(l + 1) * (TC_AFF_BYTES / 4), h);
-#endif
   }
+  tc_affine(aff + (size_t)P.L * (TC_AFF_BYTES / 4), h);
   return ld;
 }
 
@@ -538,29 +577,38 @@ __device__ __forceinline__ void tc_issuer(const TcParams& P, uint32_t img_s, uin
                                           uint32_t bar_in, uint32_t bar_out, int64_t my_tiles) {
   constexpr uint32_t ID64 = tc_idesc(128, TC_H), ID16 = tc_idesc(128, TC_N3);
   const uint32_t d = tg + TC_COL_D, ah = tg + TC_COL_AH, al = tg + TC_COL_AL;
-  const uint64_t ones = tc_desc(img_s + P.L * TC_LAYER_BYTES + (P.L + 1) * TC_AFF_BYTES, 2048, 128);
+  const uint32_t ones_s = img_s + P.L * TC_LAYER_BYTES + (P.L + 1) * TC_AFF_BYTES;
+  const uint32_t zero_s = ones_s + TC_ONES_BYTES;
+  const uint64_t ones = tc_desc(ones_s, 2048, 128);
   // a descriptor `off` bytes further into the image: the start address field is bits [0, 14) >> 4
   auto adv = [](uint64_t desc, uint32_t off) { return desc + (uint64_t)(off >> 4); };
   uint32_t ph_in = 0;
   for (int64_t it = 0; it < my_tiles; ++it) {
     for (int l = 0; l < P.L; ++l) {
       const uint32_t lb = img_s + l * TC_LAYER_BYTES;
-      const uint64_t d64 = tc_desc(lb, TC_H * 16, 128);    // 64-row operands (W1, W2, b2)
-      const uint64_t d16 = tc_desc(lb, TC_N3 * 16, 128);   // 16-row operands (W3, b3)
-      // GEMM1: [128 x 16] x [16 x 64]
+      const uint64_t d64 = tc_desc(lb, TC_H * 16, 128);    // 64-row operands (W1, W2)
+      const uint64_t d16 = tc_desc(lb, TC_N3 * 16, 128);   // 16-row operands (W3)
+      // bias operands: K-chunk 1 is the shared zero chunk (LBO = distance to it)
+      const uint64_t b1 = tc_desc(lb + TC_OFF_B1, zero_s - (lb + TC_OFF_B1), 128);
+      const uint64_t b2 = tc_desc(lb + TC_OFF_B2, zero_s - (lb + TC_OFF_B2), 128);
+      const uint64_t b3 = tc_desc(lb + TC_OFF_B3, zero_s - (lb + TC_OFF_B3), 128);
+      // GEMM1: bias + [128 x 16] x [16 x 64]
       tc_mbar_wait(bar_in, ph_in);
+      TC_STAMP_I(11);
       ph_in ^= 1;
       tc_fence_after();
-      tc_mma_ts_e(d, ah, adv(d64, TC_OFF_W1HI), ID64, 0);
+      tc_mma_ss_e(d, ones, b1, ID64, 0);
+      tc_mma_ts_e(d, ah, adv(d64, TC_OFF_W1HI), ID64, 1);
       tc_mma_ts_e(d, al, adv(d64, TC_OFF_W1HI), ID64, 1);
       tc_mma_ts_e(d, ah, adv(d64, TC_OFF_W1LO), ID64, 1);
       tc_commit_e(bar_out);
+      TC_STAMP_I(12);
       // GEMM2: bias + [128 x 64] x [64 x 64]
       tc_mbar_wait(bar_in, ph_in);
+      TC_STAMP_I(13);
       ph_in ^= 1;
       tc_fence_after();
-      tc_mma_ss_e(d, ones, adv(d64, TC_OFF_B2HI), ID64, 0);
-      tc_mma_ss_e(d, ones, adv(d64, TC_OFF_B2LO), ID64, 1);
+      tc_mma_ss_e(d, ones, b2, ID64, 0);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         tc_mma_ts_e(d, ah + 8 * ks, adv(d64, TC_OFF_W2HI + ks * 2 * TC_H * 16), ID64, 1);
@@ -568,12 +616,13 @@ __device__ __forceinline__ void tc_issuer(const TcParams& P, uint32_t img_s, uin
         tc_mma_ts_e(d, ah + 8 * ks, adv(d64, TC_OFF_W2LO + ks * 2 * TC_H * 16), ID64, 1);
       }
       tc_commit_e(bar_out);
+      TC_STAMP_I(14);
       // GEMM3: bias + [128 x 64] x [64 x 16]
       tc_mbar_wait(bar_in, ph_in);
+      TC_STAMP_I(15);
       ph_in ^= 1;
       tc_fence_after();
-      tc_mma_ss_e(d, ones, adv(d16, TC_OFF_B3HI), ID16, 0);
-      tc_mma_ss_e(d, ones, adv(d16, TC_OFF_B3LO), ID16, 1);
+      tc_mma_ss_e(d, ones, b3, ID16, 0);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         tc_mma_ts_e(d, ah + 8 * ks, adv(d16, TC_OFF_W3HI + ks * 2 * TC_N3 * 16), ID16, 1);
@@ -581,6 +630,7 @@ __device__ __forceinline__ void tc_issuer(const TcParams& P, uint32_t img_s, uin
         tc_mma_ts_e(d, ah + 8 * ks, adv(d16, TC_OFF_W3LO + ks * 2 * TC_N3 * 16), ID16, 1);
       }
       tc_commit_e(bar_out);
+      TC_STAMP_I(16);
     }
   }
 }
@@ -668,18 +718,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P
       const bool valid = row < io.n;
       float h[TC_DP];
       float ss_in = 0.f;
+      if (P.D == TC_DP) {  // a row is 64 contiguous, 64-byte aligned bytes
+        const float4* p4 = reinterpret_cast<const float4*>(io.in + row * TC_DP);
 #pragma unroll
-      for (int d = 0; d < TC_DP; ++d) {
-        h[d] = (valid && d < P.D) ? __ldg(io.in + row * P.D + d) : 0.f;
-        ss_in = fmaf(h[d], h[d], ss_in);
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = valid ? __ldg(p4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          h[4 * q] = v.x, h[4 * q + 1] = v.y, h[4 * q + 2] = v.z, h[4 * q + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < TC_DP; ++d) h[d] = (valid && d < P.D) ? __ldg(io.in + row * P.D + d) : 0.f;
       }
+#pragma unroll
+      for (int d = 0; d < TC_DP; ++d) ss_in = fmaf(h[d], h[d], ss_in);
       const float ld = tc_run_row(P, tc_smem, tg, bar_in, bar_out, ph_out, h) + P.const_logdet;
       float ss_out = 0.f;
 #pragma unroll
-      for (int d = 0; d < TC_DP; ++d) {
-        if (d < P.D) {
-          ss_out = fmaf(h[d], h[d], ss_out);
-          if (valid && io.out) io.out[row * P.D + d] = h[d];
+      for (int d = 0; d < TC_DP; ++d) ss_out = d < P.D ? fmaf(h[d], h[d], ss_out) : ss_out;
+      if (valid && io.out) {
+        if (P.D == TC_DP) {
+          float4* o4 = reinterpret_cast<float4*>(io.out + row * TC_DP);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o4[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int d = 0; d < TC_DP; ++d)
+            if (d < P.D) io.out[row * P.D + d] = h[d];
         }
       }
       if (valid) {

@@ -563,6 +563,17 @@ extern "C" int nb200_populate_accept(int64_t n, int D, const float* d_xp, const 
   return 0;
 }
 
+#ifdef NB200_TC_TRACE
+extern "C" int nb200_debug_trace(long long* h_out, int* h_n) {
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpyFromSymbol(h_out, nb200::tc_trace_buf, sizeof(long long) * 2 * 4096));
+  CUDA_OK(cudaMemcpyFromSymbol(h_n, nb200::tc_trace_n, sizeof(int) * 2));
+  int zero[2] = {0, 0};
+  CUDA_OK(cudaMemcpyToSymbol(nb200::tc_trace_n, zero, sizeof(zero)));
+  return 0;
+}
+#endif
+
 // ============================================================================= training
 #include "train.cuh"
 
