@@ -825,14 +825,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParam
 }
 
 inline int tc_prep(const void* kernel, size_t smem) {
-  static thread_local const void* done[4];
+  // opt in to > 48 KB dynamic shared memory; remembers the largest size set per kernel
+  static thread_local const void* done[8];
+  static thread_local size_t done_smem[8];
   static thread_local int nd = 0;
+  int slot = -1;
   for (int i = 0; i < nd; ++i)
-    if (done[i] == kernel) return 0;
+    if (done[i] == kernel) slot = i;
+  if (slot >= 0 && done_smem[slot] >= smem) return 0;
   if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
       cudaSuccess)
     return 1;
-  if (nd < 4) done[nd++] = kernel;
+  if (slot < 0 && nd < 8) slot = nd++;
+  if (slot >= 0) {
+    done[slot] = kernel;
+    done_smem[slot] = smem;
+  }
   return 0;
 }
 

@@ -14,6 +14,7 @@
 #include "philox.cuh"
 #include "populate_common.cuh"
 #include "flow_tc.cuh"
+#include "flow_tc_res.cuh"
 
 using namespace nb200;
 
@@ -57,6 +58,7 @@ struct DirProgram {
   int wmax = 0;
   double const_logdet = 0.0;
   TcProgram tc;  // tensor-core specialisation (valid == false when not applicable)
+  RsProgram rs;  // tensor-core specialisation for the ResidualNet conditioner
 };
 
 struct nb200_flow {
@@ -71,6 +73,7 @@ static void free_dir(DirProgram& p) {
   if (p.d_blob) cudaFree(p.d_blob);
   delete[] p.h_ops;
   tc_free(p.tc);
+  rs_free(p.rs);
   p = DirProgram();
 }
 
@@ -137,6 +140,11 @@ extern "C" int nb200_flow_set_program(nb200_flow* f, int direction, const int32_
   if (int rc = tc_build(p.tc, p.h_ops, n_ops, h_blob, f->D, f->H, f->activation, final_buf))
     return fail(rc, "tc_build failed: %s", cudaGetErrorString(cudaGetLastError()));
   p.tc.const_logdet = (float)const_logdet;
+  if (!p.tc.valid) {
+    if (int rc = rs_build(p.rs, p.h_ops, n_ops, h_blob, f->D, f->H, f->activation))
+      return fail(rc, "rs_build failed: %s", cudaGetErrorString(cudaGetLastError()));
+    p.rs.const_logdet = (float)const_logdet;
+  }
   return 0;
 }
 
@@ -425,6 +433,13 @@ static int launch_apply(nb200_flow* f, int direction, const float* in, float* ou
                ? fail(2, "tc kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()))
                : 0;
   }
+  if (p.rs.valid && tc_enabled()) {
+    TcIO io{in, out, logj, lp, direction == 1 ? 1 : 2, n};
+    const int nl = rs_launch<0>(p.rs, io, PopulateArgs(), n, f->num_sms, st);
+    if (!nl) return fail(2, "tc resnet kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    g_launches += nl;
+    return 0;
+  }
   FlowProgramDev P = make_dev(f, p);
   int BS;
   size_t smem;
@@ -504,6 +519,12 @@ extern "C" int nb200_populate_draw(nb200_flow* f, int64_t n, uint64_t seed, uint
     return tc_launch_populate(p.tc, A, f->num_sms, st)
                ? fail(2, "tc populate launch failed: %s", cudaGetErrorString(cudaGetLastError()))
                : 0;
+  }
+  if (p.rs.valid && tc_enabled()) {
+    const int nl = rs_launch<1>(p.rs, TcIO(), A, n, f->num_sms, st);
+    if (!nl) return fail(2, "tc resnet populate launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    g_launches += nl;
+    return 0;
   }
   FlowProgramDev P = make_dev(f, p);
   int BS;

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nessai_b200 import _lib
 from nessai_b200.flowmodel import B200FlowModel
 
-g = np.load("tests/golden/c2_realnvp_mlp.npz")
+g = np.load(f"tests/golden/{sys.argv[1] if len(sys.argv) > 1 else "c2_realnvp_mlp"}.npz")
 cfg = json.loads(str(g["flow_config"]))
 sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
 fm = B200FlowModel(flow_config=cfg, training_config=dict(device_tag="cuda:0"), output=tempfile.mkdtemp())
