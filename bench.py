@@ -316,11 +316,55 @@ def run_ours(args):
                 },
             },
         }
+        if world == 1:
+            out["variants"] = {"c2_resnet_default_conditioner": resnet_variant(prop, args.pool, dev)}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(threads=1, pool=args.cpu_pool)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def resnet_variant(prop, pool, dev):
+    """BASELINE.json's "4x[64,64] conditioner" is ambiguous between net="mlp" (the headline
+    above) and nessai's DEFAULT net="resnet" (2 residual blocks of width 64): the same fused
+    draw turn timed on the resnet flow (reference-trained golden weights), device only."""
+    import torch
+
+    from nessai_b200.flowmodel import B200FlowModel
+    from nessai_b200.proposal import PopulateEngine
+
+    g = np.load(os.path.join(REPO, "tests", "golden", "c2_realnvp_resnet.npz"))
+    cfg = json.loads(str(g["flow_config"]))
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
+    fm = B200FlowModel(flow_config=cfg, training_config=dict(device_tag=str(dev)), output=tempfile.mkdtemp())
+    fm.initialise()
+    fm.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    fm.model.eval()
+    e0 = prop._get_engine()
+    eng = PopulateEngine(fm, e0.names, e0.row_dtype)
+    eng.d_scale, eng.d_shift, eng.d_lo, eng.d_hi = e0.d_scale, e0.d_shift, e0.d_lo, e0.d_hi
+    eng.log_prior_const, eng.r_max, eng.sqrt_t = e0.log_prior_const, e0.r_max, e0.sqrt_t
+    eng._ensure(pool, pool, False)
+    for _ in range(3):
+        eng.draw_turn(pool)
+    torch.cuda.synchronize()
+    kt = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.draw_turn(pool)
+        b.record()
+        torch.cuda.synchronize()
+        kt.append(a.elapsed_time(b))
+    ms = float(np.mean(kt))
+    return {
+        "kernel": "populate_draw, ResidualNet conditioner (2 tcgen05 passes of 2 layers)",
+        "kernel_ms": ms,
+        "rows_per_s": pool / (ms * 1e-3),
+        "tflops_algorithmic": pool / (ms * 1e-3) * 146e3 / 1e12,
+        "flops_per_row": 146e3,
+    }
 
 
 # ------------------------------------------------------------------------- reference
