@@ -317,12 +317,47 @@ def run_ours(args):
             },
         }
         if world == 1:
+            out["coupling_forward"] = coupling_roofline(dev, peaks, which)
             out["variants"] = {"c2_resnet_default_conditioner": resnet_variant(prop, args.pool, dev)}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(threads=1, pool=args.cpu_pool)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def coupling_roofline(dev, peaks, which, n=8_000_000):
+    """The element-wise coupling stage alone (conditioner output supplied), SURVEY.md 8(d):
+    196 B/row at D = 16 (x in, shift|scale in, y out, log|det| out).  8e6 rows = 1.57 GB per
+    launch, far beyond the 126 MB L2; CUDA events on the launching stream."""
+    import torch
+
+    from nessai_b200.coupling import coupling_transform
+
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.randn(n, D, device=dev, generator=g)
+    p = torch.randn(n, D, device=dev, generator=g)
+    tf = list(range(1, D, 2))
+    for _ in range(3):
+        coupling_transform(x, p, tf)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        coupling_transform(x, p, tf)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = float(np.median(ts))
+    gbs = n * 196.0 / (ms * 1e-3) / 1e9
+    return {
+        "kernel": "coupling_vec_kernel (AffineCouplingTransform forward, conditioner output supplied)",
+        "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "frac": gbs / peaks["hbm_gbs"], "peak_source": f"{which} copy bandwidth",
+        "bytes_per_row": 196, "rows_per_launch": n, "kernel_ms": ms,
+        "note": "includes the two torch.empty output allocations of the Python wrapper",
+    }
 
 
 def resnet_variant(prop, pool, dev):

@@ -104,6 +104,16 @@ int nb200_populate_accept(int64_t n, int D, const float* d_xp, const double* d_s
                           int64_t write_offset, int64_t* d_counts, int64_t* d_scratch,
                           void* stream);
 
+/* glasflow.nflows AffineCouplingTransform._coupling_transform_forward / _inverse (the
+ * element-wise stage of flows/realnvp.py:110-112 with the conditioner output supplied):
+ * d_params[n][2*d_tr] = shift | unconstrained scale (nflows layout; [n][d_tr] when additive),
+ * scale = sigmoid(u + 2) + 1e-3; transformed features y = x*scale + shift (inverse:
+ * (x - shift)/scale), identity features copied, d_logdet[n] = +-sum log scale.
+ * h_transform_features: the d_tr feature indices (host int32), D <= 64. */
+int nb200_coupling_transform(const float* d_x, const float* d_params, float* d_y, float* d_logdet,
+                             int64_t n, int D, const int32_t* h_transform_features, int d_tr,
+                             int additive, int inverse, void* stream);
+
 /* ------------------------------------------------------------------ training
  * flowmodel/base.py:365-452 FlowModel._train: one EPOCH of optimisation steps on a
  * RealNVP flow, fused: train-mode forward (batch-statistics BatchNorm with running-

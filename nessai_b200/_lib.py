@@ -93,6 +93,11 @@ _SIGS = {
          C.c_uint64, C.c_uint64, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
          C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
+    "nb200_coupling_transform": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int,
+         C.c_int, C.c_int, C.c_void_p],
+    ),
     "nb200_trainer_create": (
         C.c_int,
         [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int],

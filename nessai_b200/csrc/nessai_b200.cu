@@ -15,6 +15,7 @@
 #include "populate_common.cuh"
 #include "flow_tc.cuh"
 #include "flow_tc_res.cuh"
+#include "coupling.cuh"
 
 using namespace nb200;
 
@@ -580,6 +581,49 @@ extern "C" int nb200_populate_accept(int64_t n, int D, const float* d_xp, const 
       reinterpret_cast<const uint32_t*>(d_row_template), F, reinterpret_cast<uint32_t*>(d_rows),
       capacity, write_offset);
   g_launches += 3;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int nb200_coupling_transform(const float* d_x, const float* d_params, float* d_y,
+                                        float* d_logdet, int64_t n, int D,
+                                        const int32_t* h_transform_features, int d_tr, int additive,
+                                        int inverse, void* stream) {
+  if (n <= 0) return 0;
+  if (!d_x || !d_params || !d_y || !d_logdet || !h_transform_features)
+    return fail(1, "nb200_coupling_transform: bad arguments");
+  if (D < 1 || D > CP_MAXD || d_tr < 1 || d_tr > D)
+    return fail(1, "nb200_coupling_transform: D=%d d_tr=%d out of range", D, d_tr);
+  CouplingMap map;
+  for (int f = 0; f < CP_MAXD; ++f) map.rank[f] = -1;
+  for (int i = 0; i < d_tr; ++i) {
+    const int f = h_transform_features[i];
+    if (f < 0 || f >= D || map.rank[f] >= 0)
+      return fail(1, "nb200_coupling_transform: bad transform feature list");
+    map.rank[f] = (int8_t)i;
+  }
+  int dev = 0, sms = 148;
+  CUDA_OK(cudaGetDevice(&dev));
+  CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int lpr = D / 4;
+  const bool vec = D % 4 == 0 && (lpr & (lpr - 1)) == 0 && lpr <= 16 &&
+                   ((uintptr_t)d_x % 16 == 0) && ((uintptr_t)d_y % 16 == 0);
+  if (vec) {
+    const int64_t total = n * lpr;
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sms * 32);
+#define CP_LAUNCH(L) coupling_vec_kernel<L><<<grid, 256, 0, st>>>(d_x, d_params, d_y, d_logdet, n, d_tr, additive, inverse, map)
+    if (lpr == 1) CP_LAUNCH(1);
+    else if (lpr == 2) CP_LAUNCH(2);
+    else if (lpr == 4) CP_LAUNCH(4);
+    else if (lpr == 8) CP_LAUNCH(8);
+    else CP_LAUNCH(16);
+#undef CP_LAUNCH
+  } else {
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sms * 32);
+    coupling_row_kernel<<<grid, 256, 0, st>>>(d_x, d_params, d_y, d_logdet, n, D, d_tr, additive, inverse, map);
+  }
+  g_launches += 1;
   CUDA_OK(cudaGetLastError());
   return 0;
 }
