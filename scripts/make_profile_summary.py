@@ -33,6 +33,9 @@ jobs = [
     ("prof_r1_tc_pop_v1.ncu-rep", "r1_ncu_populate_tcgen05_v1_smemA.txt", full, "flow_tc_populate_kernel v1 (A operand in shared memory, 2 groups), 1e6 rows"),
     ("prof_r1_tc_pop_v2.ncu-rep", "r1_ncu_populate_tcgen05_v2_tmemA.txt", full, "flow_tc_populate_kernel v2 (A operand in TMEM, 4 groups), 1e6 rows"),
     ("prof_r1_tc_pop_v3.ncu-rep", "r1_ncu_populate_tcgen05_v3.txt", full, "flow_tc_populate_kernel v3 (fp32 x' output, smem constants, suspended waits), 1e6 rows"),
+    ("prof_r1_tc_pop_v6.ncu-rep", "r1_ncu_populate_tcgen05_v6_converged_issuer.txt", full, "flow_tc_populate_kernel v6 (converged issuer warps, affine folded into GEMM1, single bias MMA), 1e6 rows"),
+    ("prof_r1_tc_res_v1.ncu-rep", "r1_ncu_populate_tcgen05_resnet_v1.txt", full, "flow_tc_res_kernel<1> (ResidualNet conditioner, last of 2 layer passes), 1e6 rows"),
+    ("prof_r1_coupling.ncu-rep", "r1_ncu_coupling_transform.txt", full, "coupling_vec_kernel<4> (affine coupling transform alone, 8e6 rows x 196 B)"),
     ("prof_r1_tc_v2.ncu-rep", "r1_ncu_apply_tcgen05_v2.txt", full, "flow_tc_apply_kernel v2 (FlowModel.inverse, z supplied), 1e6 rows"),
 ]
 for src, dst, fn, title in jobs:
@@ -40,7 +43,7 @@ for src, dst, fn, title in jobs:
     if os.path.exists(p):
         fn(p, os.path.join(OUT, dst), title)
         print("wrote", dst)
-for j in ("bench_r1_n1.json", "bench_r1_ref.json"):
+for j in ("bench_r1_n1.json", "bench_r1_ref.json", "bench_r1_n2.json", "r1_tc_phase_timeline.txt"):
     p = os.path.join(G, j)
     if os.path.exists(p):
         open(os.path.join(OUT, j), "w").write(open(p).read())
