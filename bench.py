@@ -321,7 +321,8 @@ def run_ours(args):
         }
         if world == 1 and not args.no_extras:
             out["coupling_forward"] = coupling_roofline(dev, peaks, which)
-            out["variants"] = {"c2_resnet_default_conditioner": resnet_variant(prop, args.pool, dev)}
+            out["variants"] = {"c2_resnet_default_conditioner": resnet_variant(prop, args.pool, dev),
+                               "c3_nsf_32d": nsf_variant(dev)}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(threads=1, pool=args.cpu_pool)
         print(json.dumps(out), flush=True)
@@ -403,6 +404,37 @@ def resnet_variant(prop, pool, dev):
         "tflops_algorithmic": pool / (ms * 1e-3) * 146e3 / 1e12,
         "flops_per_row": 146e3,
     }
+
+
+def nsf_variant(dev, n=2_000_000):
+    """Config C3 (32-D NSF, 6 layers, ResidualNet 64, 8 bins): sample_and_log_prob of a pool of
+    2e6 rows through the generic fp32 kernel (randomly initialised flow; the spline path has no
+    tensor-core specialisation yet)."""
+    import torch
+
+    from nessai_b200.flowmodel import B200FlowModel
+
+    torch.manual_seed(3)
+    fm = B200FlowModel(flow_config=dict(n_inputs=32, ftype="nsf", n_blocks=6, n_layers=2, n_neurons=64),
+                       training_config=dict(device_tag=str(dev)), output=tempfile.mkdtemp())
+    fm.initialise()
+    fm.model.eval()
+    z = torch.randn(n, 32, device=dev)
+    for _ in range(2):
+        fm.model._inverse(z)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fm.model._inverse(z)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = float(np.mean(ts))
+    return {"kernel": "flow_apply_kernel (generic fp32 interpreter, spline couplings)", "kernel_ms": ms,
+            "rows_per_s": n / (ms * 1e-3), "rows": n, "flops_per_row": 0.50e6,
+            "tflops_algorithmic": n / (ms * 1e-3) * 0.50e6 / 1e12}
 
 
 # ------------------------------------------------------------------------- reference
