@@ -505,6 +505,7 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) tc_split2<false>(h[2 * j], h[2 * j + 1], hi[j], lo[j]);
+      TC_STAMP_E(9);
       tc_st8(tg + TC_COL_AH, hi);
       tc_st8(tg + TC_COL_AL, lo);
       tc_wait_st();
@@ -544,6 +545,7 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
     tc_wait_ld();
     tc_pin16(r);
     tc_fence_before();
+    TC_STAMP_E(7);
 #pragma unroll
     for (int f = 0; f < TC_N3 / 2; ++f) {
       if (f < d_tr) {
@@ -566,6 +568,7 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
         ld += P.inverse ? -ls : ls;
       }
     }
+    TC_STAMP_E(8);
   }
   tc_affine(aff + (size_t)P.L * (TC_AFF_BYTES / 4), h);
   return ld;

@@ -92,25 +92,59 @@ def shard_rows(n_total: int, rank: int, world: int):
     return base + (1 if rank < rem else 0), rank * base + min(rank, rem)
 
 
-def gather_records(local_rows: torch.Tensor, n_local: int, n_keep: int, row_bytes: int, group=None):
+def gather_records(local_rows: torch.Tensor, n_local: int, n_keep: int, row_bytes: int, group=None,
+                   to_host: bool = False):
     """All-gather the accepted live-point records (uint8, ``row_bytes`` each) of every
     rank, rank-major, and keep the first ``n_keep``.  Works on any backend (NCCL on
-    GPUs; gloo in the CPU tests).  Returns a uint8 tensor on ``local_rows.device``."""
+    GPUs; gloo in the CPU tests).  Returns ``(rows, counts)``: a uint8 tensor on
+    ``local_rows.device`` -- or, with ``to_host``, a uint8 tensor in PINNED host memory
+    filled by one asynchronous device-to-host copy per rank segment (no device-side
+    concatenation, no pageable staging)."""
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     dev = local_rows.device
     cnt = torch.tensor([int(n_local)], dtype=torch.int64, device=dev)
-    allc = [torch.zeros_like(cnt) for _ in range(world)]
-    dist.all_gather(allc, cnt, group=group)
-    allc = [int(c.item()) for c in allc]
+    if dev.type == "cuda":
+        allc_t = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc_t, cnt, group=group)
+        allc = [int(c) for c in allc_t.cpu().tolist()]  # one synchronisation
+    else:
+        tmp = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(tmp, cnt, group=group)
+        allc = [int(c.item()) for c in tmp]
     mx = max(max(allc), 1)
-    send = torch.zeros(mx * row_bytes, dtype=torch.uint8, device=dev)
-    send[: n_local * row_bytes] = local_rows[: n_local * row_bytes]
-    recv = [torch.empty_like(send) for _ in range(world)]
-    dist.all_gather(recv, send, group=group)
-    parts = [recv[r][: allc[r] * row_bytes] for r in range(world)]
-    return torch.cat(parts)[: n_keep * row_bytes], allc
+    if local_rows.numel() >= mx * row_bytes and dev.type == "cuda":
+        send = local_rows[: mx * row_bytes]  # the tail past n_local is never read back
+    else:
+        send = torch.zeros(mx * row_bytes, dtype=torch.uint8, device=dev)
+        send[: n_local * row_bytes] = local_rows[: n_local * row_bytes]
+    if dev.type == "cuda":
+        recv_t = torch.empty((world, mx * row_bytes), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(recv_t, send, group=group)
+        recv = [recv_t[r] for r in range(world)]
+    else:
+        recv = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(recv, send, group=group)
+    # rank-major, first n_keep records
+    take, left = [], int(n_keep)
+    for r in range(world):
+        k = min(allc[r], left)
+        take.append(k)
+        left -= k
+    total = sum(take)
+    if to_host and dev.type == "cuda":
+        host = torch.empty(total * row_bytes, dtype=torch.uint8, pin_memory=True)
+        off = 0
+        for r in range(world):
+            nb = take[r] * row_bytes
+            if nb:
+                host[off : off + nb].copy_(recv[r][:nb], non_blocking=True)
+                off += nb
+        torch.cuda.current_stream(dev).synchronize()
+        return host, allc
+    parts = [recv[r][: take[r] * row_bytes] for r in range(world)]
+    return torch.cat(parts), allc
 
 
 class PopulateEngine:
@@ -161,6 +195,7 @@ class PopulateEngine:
             self._rows_cap = capacity
         if not hasattr(self, "d_stats"):
             self.d_stats = torch.empty(2, dtype=torch.float64, device=dev)
+            self._stats_init = torch.tensor([-float("inf"), 0.0], dtype=torch.float64, device=dev)
             self.d_counts = torch.zeros(2, dtype=torch.int64, device=dev)
 
     def configure(self, scale, shift, lo, hi, log_prior_const, r_max, sqrt_temperature=1.0):
@@ -192,8 +227,7 @@ class PopulateEngine:
         self.model._ready()
         n_local, start = self._shard(n_total)
         self._ensure(max(n_local, 1), self._rows_cap, want_z)
-        self.d_stats[0] = -float("inf")
-        self.d_stats[1] = 0.0
+        self.d_stats.copy_(self._stats_init, non_blocking=True)  # {max log_w = -inf, n_valid = 0}
         lpc = float("nan") if self.log_prior_const is None else float(self.log_prior_const)
         with torch.cuda.device(self.device):
             _lib.check(
@@ -262,8 +296,9 @@ class PopulateEngine:
 
                 tot = counts[0:1].clone()
                 dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
-                c = counts.cpu()
-                n_accepted += int(tot.item())
+                both = torch.cat([counts, tot]).cpu()  # one synchronisation per turn
+                c = both[:2]
+                n_accepted += int(both[2])
             else:
                 c = counts.cpu()
                 n_accepted += int(c[0])
@@ -304,10 +339,10 @@ class PopulateEngine:
             host.copy_(self.d_rows[:nbytes], non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
             return host.numpy().view(self.row_dtype)
-        full, _ = gather_records(self.d_rows, n_local_written, n_samples, rb, self.group)
+        full, _ = gather_records(self.d_rows, n_local_written, n_samples, rb, self.group, to_host=True)
         if not full.numel():
             return empty_structured_array(0, dtype=self.row_dtype)
-        return full.cpu().numpy().view(self.row_dtype)
+        return full.numpy().view(self.row_dtype)
 
 
 class B200FlowProposal:

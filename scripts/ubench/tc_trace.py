@@ -22,7 +22,7 @@ for who in (0, 1):
         ev.append((int(v) >> 8, who, int(v) & 255))
 ev.sort()
 t0 = ev[0][0]
-names = {1: "E0 done->arrive", 2: "E1 wake", 3: "E1 done->arrive", 4: "E2 wake", 5: "E2 done->arrive", 6: "E3 wake",
+names = {7: "E3 TMEM loaded", 8: "E3 coupling done", 9: "E0 split done", 1: "E0 done->arrive", 2: "E1 wake", 3: "E1 done->arrive", 4: "E2 wake", 5: "E2 done->arrive", 6: "E3 wake",
          11: "  I: wake G1", 12: "  I: G1 issued+commit", 13: "  I: wake G2", 14: "  I: G2 issued+commit", 15: "  I: wake G3", 16: "  I: G3 issued+commit"}
 prev = t0
 for t, who, tag in ev[60:110]:
