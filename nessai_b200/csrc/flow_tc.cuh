@@ -404,6 +404,65 @@ __device__ __forceinline__ void tc_split2(float a, float b, uint32_t& hi, uint32
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 
+// raw SFU ops (no denormal / range fix-up code around them: operands here are O(1))
+__device__ __forceinline__ float tc_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tc_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tc_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// The affine coupling on the 8 transformed slots h[TC_TR0 ..], branch-free so that the eight
+// SFU chains (ex2 -> rcp -> lg2 / rcp) interleave instead of running one after the other:
+// r[2f] = shift, r[2f+1] = unconstrained scale, scale = sigmoid(u + 2) + 1e-3.  Slots >= d_tr
+// carry zero weights (their h stays 0); only their log-scale has to be masked.
+template <bool INVERSE>
+__device__ __forceinline__ float tc_coupling8(const uint32_t (&r)[16], float (&h)[TC_DP], int d_tr) {
+  float s[8];
+#pragma unroll
+  for (int f = 0; f < 8; ++f)
+    s[f] = tc_ex2((__uint_as_float(r[2 * f + 1]) + 2.f) * -1.4426950408889634f);
+#pragma unroll
+  for (int f = 0; f < 8; ++f) s[f] = tc_rcp(1.f + s[f]) + 1e-3f;
+  float ld = 0.f;
+#pragma unroll
+  for (int f = 0; f < 8; ++f) {
+    const float tt = __uint_as_float(r[2 * f]);
+    const float ls = tc_lg2(s[f]) * 0.6931471805599453f;
+    if (INVERSE) h[TC_TR0 + f] = (h[TC_TR0 + f] - tt) * tc_rcp(s[f]);
+    else h[TC_TR0 + f] = fmaf(h[TC_TR0 + f], s[f], tt);
+    ld += f < d_tr ? ls : 0.f;
+  }
+  return INVERSE ? -ld : ld;
+}
+// volume-preserving (additive) coupling: scale == 1
+template <bool INVERSE>
+__device__ __forceinline__ void tc_coupling8_additive(const uint32_t (&r)[16], float (&h)[TC_DP]) {
+#pragma unroll
+  for (int f = 0; f < 8; ++f) {
+    const float tt = __uint_as_float(r[2 * f]);
+    h[TC_TR0 + f] = INVERSE ? h[TC_TR0 + f] - tt : h[TC_TR0 + f] + tt;
+  }
+}
+__device__ __forceinline__ float tc_coupling(const uint32_t (&r)[16], float (&h)[TC_DP], int d_tr,
+                                             int additive, int inverse) {
+  if (additive) {
+    if (inverse) tc_coupling8_additive<true>(r, h);
+    else tc_coupling8_additive<false>(r, h);
+    return 0.f;
+  }
+  return inverse ? tc_coupling8<true>(r, h, d_tr) : tc_coupling8<false>(r, h, d_tr);
+}
+
 // hidden-layer epilogue: 64 accumulator columns (bias already accumulated by the
 // GEMM) -> ReLU -> split -> the row's A operand in TMEM (hi: 32 columns, lo: 32).
 __device__ __forceinline__ void tc_hidden_epilogue(uint32_t tg) {
@@ -546,28 +605,7 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
     tc_pin16(r);
     tc_fence_before();
     TC_STAMP_E(7);
-#pragma unroll
-    for (int f = 0; f < TC_N3 / 2; ++f) {
-      if (f < d_tr) {
-        const float tt = __uint_as_float(r[2 * f]);
-        float s = 1.f, ls = 0.f;
-#ifdef NB200_ABL_NO_MUFU
-        if (false) {
-#else
-        if (!P.additive) {
-#endif
-          const float u = __uint_as_float(r[2 * f + 1]);
-          s = __fdividef(1.f, 1.f + __expf(-(u + 2.f))) + 1e-3f;
-          ls = __logf(s);
-        }
-        if (P.inverse) {
-          h[TC_TR0 + f] = __fdividef(h[TC_TR0 + f] - tt, s);
-        } else {
-          h[TC_TR0 + f] = fmaf(h[TC_TR0 + f], s, tt);
-        }
-        ld += P.inverse ? -ls : ls;
-      }
-    }
+    ld += tc_coupling(r, h, d_tr, P.additive, P.inverse);
     TC_STAMP_E(8);
   }
   tc_affine(aff + (size_t)P.L * (TC_AFF_BYTES / 4), h);

@@ -310,21 +310,7 @@ __device__ __forceinline__ float rs_run_row(const RsParams& P, const uint8_t* im
       tc_ld16(tg + RS_COL_D2, r);
       tc_wait_ld();
       tc_pin16(r);
-#pragma unroll
-      for (int f = 0; f < TC_N3 / 2; ++f) {
-        if (f < d_tr) {
-          const float tt = __uint_as_float(r[2 * f]);
-          float s = 1.f, ls = 0.f;
-          if (!P.additive) {
-            const float u = __uint_as_float(r[2 * f + 1]);
-            s = __fdividef(1.f, 1.f + __expf(-(u + 2.f))) + 1e-3f;
-            ls = __logf(s);
-          }
-          if (P.inverse) h[TC_TR0 + f] = __fdividef(h[TC_TR0 + f] - tt, s);
-          else h[TC_TR0 + f] = fmaf(h[TC_TR0 + f], s, tt);
-          ld += P.inverse ? -ls : ls;
-        }
-      }
+      ld += tc_coupling(r, h, d_tr, P.additive, P.inverse);
     }
   }
   if (c == 0 && P.last) tc_affine(aff + (size_t)P.nl * (TC_AFF_BYTES / 4), h);
