@@ -833,8 +833,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParam
       float ss = 0.f;
 #pragma unroll
       for (int d0 = 0; d0 < TC_DP; d0 += 4) {
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (d0 < P.D) {
+        // unconditional: the four Philox chains interleave (unused features are masked below)
+        float v[4];
+        {
           const Philox4 r = philox4x32_10(A.seed, A.row_offset + row, d0 / 4, 0);
           box_muller(r.x, r.y, v[0], v[1]);
           box_muller(r.z, r.w, v[2], v[3]);

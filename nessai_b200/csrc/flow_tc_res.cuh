@@ -473,8 +473,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_res_kernel(RsParams P, 
         } else {
 #pragma unroll
           for (int d0 = 0; d0 < TC_DP; d0 += 4) {
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            if (d0 < P.D) {
+            float v[4];
+            {
               const Philox4 r = philox4x32_10(A.seed, A.row_offset + row, d0 / 4, 0);
               box_muller(r.x, r.y, v[0], v[1]);
               box_muller(r.z, r.w, v[2], v[3]);

@@ -44,17 +44,28 @@ __device__ __forceinline__ void populate_row(const PopulateArgs& A, int D, XP xp
   if (row >= A.n) return;
   // cst: scale | shift | lo | hi, each TC_DP-strided doubles (shared or global memory)
   bool inb = true;
-  if (MAXD > 0) {  // compile-time trip count: xp(d) may index registers
-    if (MAXD == 16 && D == 16) {  // the row is 64 contiguous, 64-byte aligned bytes
-      float4* o4 = reinterpret_cast<float4*>(A.xp + row * 16);
+  if (MAXD == 16 && D == 16) {
+    // full rows: 64 contiguous, 64-byte aligned bytes out; no per-feature predicates, so the
+    // sixteen float64 rescale / bounds chains interleave
+    float v[16];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) o4[q] = make_float4(xp(4 * q), xp(4 * q + 1), xp(4 * q + 2), xp(4 * q + 3));
+    for (int d = 0; d < 16; ++d) v[d] = xp(d);
+    float4* o4 = reinterpret_cast<float4*>(A.xp + row * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    int bad = 0;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
+      const double xv = (double)v[d] * scale[d] + shift[d];
+      bad |= (xv < lo[d]) | (xv > hi[d]);
     }
+    inb = !bad;
+  } else if (MAXD > 0) {  // compile-time trip count: xp(d) may index registers
 #pragma unroll
     for (int d = 0; d < (MAXD > 0 ? MAXD : 1); ++d) {
       if (d < D) {
         const float v = xp(d);
-        if (!(MAXD == 16 && D == 16)) A.xp[row * D + d] = v;
+        A.xp[row * D + d] = v;
         const double xv = (double)v * scale[d] + shift[d];
         inb = inb && !(xv < lo[d]) && !(xv > hi[d]);
       }
