@@ -78,12 +78,112 @@ def net_ops(spec, ls):
     return ops, nb + 1
 
 
+MIN_BIN_WIDTH = MIN_BIN_HEIGHT = MIN_DERIVATIVE = 1e-3
+
+
+def _spline_knots(u, B):
+    """softmax -> min size -> cumulative knots with both ends forced to -B / +B
+    (nflows rational_quadratic_spline).  Returns (p, knots[..., K+1])."""
+    K = u.shape[-1]
+    e = np.exp(u - u.max(-1, keepdims=True))
+    p = e / e.sum(-1, keepdims=True)
+    w = MIN_BIN_WIDTH + (1 - MIN_BIN_WIDTH * K) * p
+    s = np.concatenate([np.zeros(w.shape[:-1] + (1,)), np.cumsum(w, -1)], -1) * 2 * B - B
+    s[..., 0] = -B
+    s[..., -1] = B
+    return p, s
+
+
+def spline_forward(x, params, B, hidden):
+    """Rational-quadratic spline coupling, forward direction, linear tails.
+    x (N, F); params (N, F, 3K-1).  Returns (y, logdet (N, F), cache)."""
+    K = (params.shape[-1] + 1) // 3
+    uw = params[..., :K] / np.sqrt(hidden)
+    uh = params[..., K : 2 * K] / np.sqrt(hidden)
+    ud = params[..., 2 * K :]
+    pw, sw = _spline_knots(uw, B)
+    ph, sh = _spline_knots(uh, B)
+    const = np.log(np.exp(1 - MIN_DERIVATIVE) - 1)
+    udp = np.concatenate([np.full(ud.shape[:-1] + (1,), const), ud, np.full(ud.shape[:-1] + (1,), const)], -1)
+    d = MIN_DERIVATIVE + _softplus(udp)
+    inside = (x >= -B) & (x <= B)
+    loc = sw.copy()
+    loc[..., -1] += 1e-6
+    k = np.clip(np.sum(np.clip(x, -B, B)[..., None] >= loc, -1) - 1, 0, K - 1)
+
+    def g(a, idx):
+        return np.take_along_axis(a, idx[..., None], -1)[..., 0]
+
+    a, W = g(sw, k), g(sw, k + 1) - g(sw, k)
+    c, Hh = g(sh, k), g(sh, k + 1) - g(sh, k)
+    d0, d1 = g(d, k), g(d, k + 1)
+    th = (x - a) / W
+    dl = Hh / W
+    t = th * (1 - th)
+    Nn = Hh * (dl * th**2 + d0 * t)
+    Dn = dl + (d0 + d1 - 2 * dl) * t
+    Q = d1 * th**2 + 2 * dl * t + d0 * (1 - th) ** 2
+    y = np.where(inside, c + Nn / Dn, x)
+    ld = np.where(inside, 2 * np.log(dl) + np.log(Q) - 2 * np.log(Dn), 0.0)
+    cache = dict(K=K, B=B, hidden=hidden, pw=pw, ph=ph, udp=udp, k=k, inside=inside, W=W, Hh=Hh, d0=d0, d1=d1,
+                 th=th, dl=dl, t=t, Nn=Nn, Dn=Dn, Q=Q)
+    return y, ld, cache
+
+
+def spline_backward(gy, gl, cache):
+    """Gradients of sum(gy * y + gl * logdet) w.r.t. x and the raw conditioner outputs."""
+    C = cache
+    K, B = C["K"], C["B"]
+    W, Hh, d0, d1, th, dl, t, Nn, Dn, Q = (C[n] for n in ("W", "Hh", "d0", "d1", "th", "dl", "t", "Nn", "Dn", "Q"))
+    inside = C["inside"]
+    gN = gy / Dn
+    gD = -gy * Nn / Dn**2
+    dDn_dth = (d0 + d1 - 2 * dl) * (1 - 2 * th)
+    dQ_dth = 2 * d1 * th + 2 * dl * (1 - 2 * th) - 2 * d0 * (1 - th)
+    gth = gN * Hh * (2 * dl * th + d0 * (1 - 2 * th)) + gD * dDn_dth + gl * (dQ_dth / Q - 2 * dDn_dth / Dn)
+    gdl = gN * Hh * th**2 + gD * (1 - 2 * t) + gl * (2 / dl + 2 * t / Q - 2 * (1 - 2 * t) / Dn)
+    gH = gN * (dl * th**2 + d0 * t) + gdl / W
+    gd0 = gN * Hh * t + gD * t + gl * ((1 - th) ** 2 / Q - 2 * t / Dn)
+    gd1 = gD * t + gl * (th**2 / Q - 2 * t / Dn)
+    gx_in = gth / W
+    ga = -gth / W
+    gW = -gth * th / W - gdl * dl / W
+    gc = gy
+    z = lambda v: np.where(inside, v, 0.0)  # noqa: E731
+    ga, gW, gc, gH, gd0, gd1 = z(ga), z(gW), z(gc), z(gH), z(gd0), z(gd1)
+    gx = np.where(inside, gx_in, gy)
+    k = C["k"]
+    shape = k.shape + (K + 1,)
+
+    def knot_grads(g_left, g_size):
+        """d/d knots s_j from the left-knot position and the bin size s_{k+1} - s_k; the two
+        end knots are constants."""
+        gs = np.zeros(shape)
+        np.put_along_axis(gs, k[..., None], np.take_along_axis(gs, k[..., None], -1) + (g_left - g_size)[..., None], -1)
+        np.put_along_axis(gs, (k + 1)[..., None], np.take_along_axis(gs, (k + 1)[..., None], -1) + g_size[..., None], -1)
+        gs[..., 0] = 0.0
+        gs[..., -1] = 0.0
+        # s_j = -B + 2B sum_{i<j} w_i  ->  d/dw_i = 2B sum_{j>i} gs_j (j <= K-1)
+        rev = np.cumsum(gs[..., ::-1], -1)[..., ::-1]
+        return 2 * B * rev[..., 1:]
+
+    def softmax_back(p, gwt, minsize):
+        gp = (1 - minsize * K) * gwt
+        return p * (gp - np.sum(p * gp, -1, keepdims=True))
+
+    guw = softmax_back(C["pw"], knot_grads(ga, gW), MIN_BIN_WIDTH) / np.sqrt(C["hidden"])
+    guh = softmax_back(C["ph"], knot_grads(gc, gH), MIN_BIN_HEIGHT) / np.sqrt(C["hidden"])
+    gd = np.zeros(shape)
+    np.put_along_axis(gd, k[..., None], gd0[..., None], -1)
+    np.put_along_axis(gd, (k + 1)[..., None], np.take_along_axis(gd, (k + 1)[..., None], -1) + gd1[..., None], -1)
+    gud = (gd * _sigmoid(C["udp"]))[..., 1:-1]
+    return gx, np.concatenate([guw, guh, gud], -1)
+
+
 class TrainStepOracle:
     """Forward + backward + optimiser step on a flat float64 ``theta``."""
 
     def __init__(self, spec, ints):
-        if spec.ftype != "realnvp":
-            raise NotImplementedError("training oracle: RealNVP only")
         self.spec = spec
         self.ints = ints
 
@@ -148,7 +248,11 @@ class TrainStepOracle:
                 bufs[op["out"]] = o
             p = bufs[-1]
             d_tr = tr.shape[1]
-            if sp.volume_preserving:
+            if sp.ftype == "nsf":
+                s = None
+                tr2, ldf, S["spline"] = spline_forward(tr, p.reshape(B, d_tr, -1), sp.tail_bound, sp.H)
+                ld_rows = ld_rows + ldf.sum(1)
+            elif sp.volume_preserving:
                 s = np.ones_like(tr)
                 tr2 = tr + p
             else:
@@ -209,7 +313,10 @@ class TrainStepOracle:
             did = dy[:, ls.identity].copy()
             s, tr = S["s"], S["tr"]
             d_tr = tr.shape[1]
-            if sp.volume_preserving:
+            if sp.ftype == "nsf":
+                dtr, dpp = spline_backward(dtr2, np.broadcast_to((-c)[:, None], dtr2.shape), S["spline"])
+                dp = dpp.reshape(B, -1)
+            elif sp.volume_preserving:
                 dp = dtr2
                 dtr = dtr2
             else:
