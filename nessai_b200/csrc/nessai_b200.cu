@@ -693,7 +693,7 @@ extern "C" int nb200_trainer_create(nb200_trainer** out, const int32_t* h_plan, 
   memcpy(&t->h_plan, h_plan, sizeof(TrPlan));
   const TrPlan& P = t->h_plan;
   if (P.D < 2 || P.D > TR_MAXD || P.L < 1 || P.L > TR_MAXL || P.n_itab != n_itab ||
-      P.n_reduce != n_reduce || P.max_dim < P.D) {
+      P.n_reduce != n_reduce || P.max_dim < P.D || P.max_in < P.D) {
     delete t;
     return fail(1, "nb200_trainer_create: plan out of range (D=%d L=%d)", P.D, P.L);
   }
@@ -705,8 +705,8 @@ extern "C" int nb200_trainer_create(nb200_trainer** out, const int32_t* h_plan, 
     }
   }
   t->num_sms = prop.multiProcessorCount;
-  t->smem_fwd = 4 * tr_smem_floats(P.D, P.vals_floats, P.max_dim, P.wmax, P.n_itab, false);
-  t->smem_bwd = 4 * tr_smem_floats(P.D, P.vals_floats, P.max_dim, P.wmax, P.n_itab, true);
+  t->smem_fwd = 4 * tr_smem_floats(P.D, P.vals_floats, P.max_in, P.wmax, P.n_itab, false);
+  t->smem_bwd = 4 * tr_smem_floats(P.D, P.vals_floats, P.max_in, P.wmax, P.n_itab, true);
   if (t->smem_bwd > 226 * 1024) {
     delete t;
     return fail(5, "flow too large for the training kernels (%zu KB shared memory)", t->smem_bwd / 1024);
@@ -816,10 +816,26 @@ extern "C" int nb200_train_epoch(nb200_trainer* t, float* d_theta_p, float* d_th
     if (bt.B < 2 && any_bn) return fail(1, "nb200_train_epoch: a batch of one row has no batch variance");
     const int G = std::min(bt.n_tiles, std::min(TR_MAXG, t->num_sms));
     TrBuffers B = trainer_buffers(t, d_theta_p, d_theta_b, G);
-    for (int l = 0; l < P.L; ++l) tr_fwd_kernel<<<G, TR_THREADS, t->smem_fwd, st>>>(P, B, bt, l);
+    // NB200_TR_SYNC=1: synchronise and report after every launch (debugging aid)
+    static const bool dbg = getenv("NB200_TR_SYNC") != nullptr;
+#define TR_DBG(what, idx)                                                                       \
+  if (dbg) {                                                                                    \
+    fprintf(stderr, "[nb200 train] %s %d ...", what, idx);                                      \
+    cudaError_t e_ = cudaStreamSynchronize(st);                                                 \
+    fprintf(stderr, " %s\n", cudaGetErrorString(e_));                                           \
+  }
+    for (int l = 0; l < P.L; ++l) {
+      tr_fwd_kernel<<<G, TR_THREADS, t->smem_fwd, st>>>(P, B, bt, l);
+      TR_DBG("fwd", l)
+    }
     tr_loss_kernel<<<G, TR_THREADS, t->smem_fwd, st>>>(P, B, bt);
-    for (int l = P.L - 1; l >= 0; --l) tr_bwd_kernel<<<G, TR_THREADS, t->smem_bwd, st>>>(P, B, bt, l);
+    TR_DBG("loss", 0)
+    for (int l = P.L - 1; l >= 0; --l) {
+      tr_bwd_kernel<<<G, TR_THREADS, t->smem_bwd, st>>>(P, B, bt, l);
+      TR_DBG("bwd", l)
+    }
     tr_reduce_kernel<<<B.n_reduce_blocks, TR_RED_THREADS, 3 * P.D * P.D * sizeof(float), st>>>(P, B);
+    TR_DBG("reduce", 0)
     ++step;
     TrOptim o;
     o.kind = opt_kind;

@@ -24,6 +24,7 @@ constexpr int TR_THREADS = 512;  // threads per CTA of the row kernels (latency-
 constexpr int TR_RG = TR_THREADS / 64;   // row groups of the tile GEMM
 constexpr int TR_RT = TR_R / TR_RG;      // rows per thread
 constexpr int TR_RED_THREADS = 128;      // threads per CTA of the REDUCE kernel
+constexpr int TR_CHUNK = 64;             // output columns per staged weight unit
 constexpr int TR_MAXL = 16;      // coupling layers
 constexpr int TR_MAXBUF = 12;    // conditioner buffers per layer
 constexpr int TR_MAXLIN = 12;    // linears per conditioner
@@ -51,7 +52,10 @@ struct TrPlan {
   int D, L, act, additive;
   int n_params, n_part, rec_total, max_dim;
   int vals_floats, wmax, n_itab, n_reduce;
-  int pad[4];
+  int num_bins;      // > 0: rational-quadratic spline coupling (NSF) with this many bins
+  int tail_bound;    // float bits of the spline's linear-tail bound
+  int hidden;        // conditioner width (nflows divides the unnormalised widths / heights by sqrt of it)
+  int max_in;        // max(D, widest linear INPUT): rows of the staged-operand tiles
   TrLayer layer[TR_MAXL];
 };
 constexpr int TR_LAYER_INTS = 20 + 2 * TR_MAXBUF + 8 * TR_MAXLIN;
@@ -301,7 +305,8 @@ struct TrSmem {
   float* Pf;    // [D][16] prefetched tile (backward: previous layer's output)
   float* V;     // [vals][16] conditioner buffers
   float* Gv;    // [vals][16] their gradients (backward only)
-  float* A;     // [max_dim][16] staged GEMM operand
+  float* A;     // [max_in][16] staged GEMM operand
+  float* A2;    // [max_in][16] input-gradient accumulator over output chunks (backward only)
   float* bn;    // [4][D]: mean, rstd, w, beta  (+ [2][D] S1,S2 in backward)
   float* c;     // [16] row weights
   float* ld;    // [16]
@@ -310,13 +315,13 @@ struct TrSmem {
   int* itab;    // permutations / mask index lists
 };
 __host__ __device__ inline int tr_align4(int n) { return (n + 3) & ~3; }
-__host__ __device__ inline size_t tr_smem_floats(int D, int vals, int max_dim, int wmax, int n_itab, bool backward) {
+__host__ __device__ inline size_t tr_smem_floats(int D, int vals, int max_in, int wmax, int n_itab, bool backward) {
   size_t n = 0;
-  n += 2 * (tr_align4(wmax) + tr_align4(max_dim));
+  n += 2 * (tr_align4(wmax) + TR_CHUNK);
   n += tr_align4(D * (D | 1) + D);
   n += 5 * (size_t)D * TR_R;
   n += (size_t)vals * TR_R * (backward ? 2 : 1);
-  n += (size_t)max_dim * TR_R;
+  n += (size_t)max_in * TR_R * (backward ? 2 : 1);
   n += tr_align4(6 * D);
   n += 2 * TR_R + 3 * TR_THREADS;
   n += (size_t)TR_MAXG * (2 * D + 1);
@@ -326,7 +331,7 @@ __host__ __device__ inline size_t tr_smem_floats(int D, int vals, int max_dim, i
 __device__ __forceinline__ TrSmem tr_carve(float* s, const TrPlan& P, bool backward) {
   TrSmem m;
   const int D = P.D;
-  m.W = s, m.wbuf = tr_align4(P.wmax) + tr_align4(P.max_dim), s += 2 * m.wbuf;
+  m.W = s, m.wbuf = tr_align4(P.wmax) + TR_CHUNK, s += 2 * m.wbuf;
   m.Wlu = s, s += tr_align4(D * (D | 1) + D);
   m.H1 = s, s += D * TR_R;
   m.H2 = s, s += D * TR_R;
@@ -336,7 +341,9 @@ __device__ __forceinline__ TrSmem tr_carve(float* s, const TrPlan& P, bool backw
   m.V = s, s += P.vals_floats * TR_R;
   m.Gv = s;
   if (backward) s += P.vals_floats * TR_R;
-  m.A = s, s += P.max_dim * TR_R;
+  m.A = s, s += P.max_in * TR_R;
+  m.A2 = s;
+  if (backward) s += P.max_in * TR_R;
   m.bn = s, s += tr_align4(6 * D);
   m.c = s, s += TR_R;
   m.ld = s, s += TR_R;
@@ -513,19 +520,156 @@ __device__ __forceinline__ void tr_bn_apply_perm(const float* Yprev, const float
   }
 }
 
-// Queue the weights of linear j of the conditioner into buffer j & 1 (one commit group).
-__device__ __forceinline__ void tr_prefetch_w(const TrBuffers& Bf, const TrLayer& ly, const TrSmem& S, int j,
-                                              bool transposed, int P_max_dim) {
+// ---------------------------------------------------------------------------- RQ spline
+// nflows' unconstrained_rational_quadratic_spline, linear tails, for one
+// (row, transformed feature): p points at the feature's 3K-1 raw conditioner outputs in the
+// feature-major tile (stride TR_R floats).  The backward pass is oracle/train_numpy.py::spline_backward.
+constexpr int TR_MAXBINS = 16;
+constexpr float TR_SPL_MIN = 1e-3f;  // min bin width / height / derivative
+
+struct TrSpline {
+  float pw[TR_MAXBINS], ph[TR_MAXBINS];  // softmax probabilities of widths / heights
+  int k;                                  // bin
+  bool inside;
+  float W, Hh, d0, d1, th, dl, t, Nn, Dn, Q, c;
+};
+
+__device__ __forceinline__ void tr_spline_softmax(const float* p, int K, float isq, float* out) {
+  float mx = -INFINITY;
+  for (int j = 0; j < K; ++j) mx = fmaxf(mx, p[j * TR_R] * isq);
+  float sum = 0.f;
+  for (int j = 0; j < K; ++j) {
+    out[j] = expf(p[j * TR_R] * isq - mx);
+    sum += out[j];
+  }
+  const float inv = 1.f / sum;
+  for (int j = 0; j < K; ++j) out[j] *= inv;
+}
+// knot j of a cumulative-size vector: s_0 = -B, s_K = +B (forced), else -B + 2B * cumsum
+__device__ __forceinline__ float tr_spline_size(float prob, int K) {
+  return TR_SPL_MIN + (1.f - TR_SPL_MIN * K) * prob;
+}
+
+__device__ __forceinline__ void tr_spline_eval(float x, const float* p, int K, float B, float isq,
+                                               TrSpline& S, float& y, float& ld) {
+  S.inside = (x >= -B) && (x <= B);
+  tr_spline_softmax(p, K, isq, S.pw);
+  tr_spline_softmax(p + K * TR_R, K, isq, S.ph);
+  // bin = last knot <= x among s_0 .. s_{K-1} (nflows searchsorted with the last knot at B + 1e-6)
+  const float xc = fminf(fmaxf(x, -B), B);
+  float cum = 0.f, right = -B;
+  int k = 0;
+  float a = -B, a1 = B;
+  for (int j = 0; j < K; ++j) {
+    const float left = right;
+    cum += tr_spline_size(S.pw[j], K);
+    right = (j == K - 1) ? B : fmaf(2.f * B, cum, -B);
+    if (j == 0 || xc >= left) k = j, a = left, a1 = right;
+  }
+  S.k = k;
+  // height knots of bin k
+  float c0 = -B, c1 = B;
+  cum = 0.f;
+  for (int j = 0; j < K; ++j) {
+    const float lo = (j == 0) ? -B : fmaf(2.f * B, cum, -B);
+    cum += tr_spline_size(S.ph[j], K);
+    const float hi = (j == K - 1) ? B : fmaf(2.f * B, cum, -B);
+    if (j == k) c0 = lo, c1 = hi;
+  }
+  const float* ud = p + 2 * K * TR_R;
+  S.d0 = (k == 0) ? 1.f : TR_SPL_MIN + tr_softplus(ud[(k - 1) * TR_R]);
+  S.d1 = (k == K - 1) ? 1.f : TR_SPL_MIN + tr_softplus(ud[k * TR_R]);
+  S.W = a1 - a;
+  S.Hh = c1 - c0;
+  S.c = c0;
+  S.th = (xc - a) / S.W;
+  S.dl = S.Hh / S.W;
+  S.t = S.th * (1.f - S.th);
+  S.Nn = S.Hh * (S.dl * S.th * S.th + S.d0 * S.t);
+  S.Dn = S.dl + (S.d0 + S.d1 - 2.f * S.dl) * S.t;
+  S.Q = S.d1 * S.th * S.th + 2.f * S.dl * S.t + S.d0 * (1.f - S.th) * (1.f - S.th);
+  if (S.inside) {
+    y = S.c + S.Nn / S.Dn;
+    ld = 2.f * logf(S.dl) + logf(S.Q) - 2.f * logf(S.Dn);
+  } else {
+    y = x;
+    ld = 0.f;
+  }
+}
+
+// Gradients of gy * y + gl * logdet w.r.t. x (returned) and the raw conditioner outputs
+// (written to g, same layout as p).
+__device__ __forceinline__ float tr_spline_backward(float x, const float* p, float* g, int K, float B,
+                                                    float isq, float gy, float gl) {
+  TrSpline S;
+  float y, ld;
+  tr_spline_eval(x, p, K, B, isq, S, y, ld);
+  const int M = 3 * K - 1;
+  if (!S.inside) {
+    for (int j = 0; j < M; ++j) g[j * TR_R] = 0.f;
+    return gy;
+  }
+  const float th = S.th, dl = S.dl, t = S.t, d0 = S.d0, d1 = S.d1;
+  const float gN = gy / S.Dn, gD = -gy * S.Nn / (S.Dn * S.Dn);
+  const float dDn = (d0 + d1 - 2.f * dl) * (1.f - 2.f * th);
+  const float dQ = 2.f * d1 * th + 2.f * dl * (1.f - 2.f * th) - 2.f * d0 * (1.f - th);
+  const float gth = gN * S.Hh * (2.f * dl * th + d0 * (1.f - 2.f * th)) + gD * dDn + gl * (dQ / S.Q - 2.f * dDn / S.Dn);
+  const float gdl = gN * S.Hh * th * th + gD * (1.f - 2.f * t) +
+                    gl * (2.f / dl + 2.f * t / S.Q - 2.f * (1.f - 2.f * t) / S.Dn);
+  const float gH = gN * (dl * th * th + d0 * t) + gdl / S.W;
+  const float gd0 = gN * S.Hh * t + gD * t + gl * ((1.f - th) * (1.f - th) / S.Q - 2.f * t / S.Dn);
+  const float gd1 = gD * t + gl * (th * th / S.Q - 2.f * t / S.Dn);
+  const float ga = -gth / S.W;
+  const float gW = -gth * th / S.W - gdl * dl / S.W;
+  const float gc = gy;
+  const int k = S.k;
+  // knots s_1 .. s_{K-1} are free (s_0, s_K constants): gs_k += g_left - g_size, gs_{k+1} += g_size;
+  // d/d size_i = 2B * sum_{j > i, j <= K-1} gs_j; then the softmax backward
+  const float scale = (1.f - TR_SPL_MIN * K) * 2.f * B;
+  for (int which = 0; which < 2; ++which) {
+    const float gl_ = which == 0 ? ga : gc, gs_ = which == 0 ? gW : gH;
+    const float* pr = which == 0 ? S.pw : S.ph;
+    const float gsk = (k >= 1) ? gl_ - gs_ : 0.f;       // knot k (constant when k == 0)
+    const float gsk1 = (k + 1 <= K - 1) ? gs_ : 0.f;    // knot k + 1 (constant when k == K-1)
+    // g size_i = scale * (gsk [i < k] + gsk1 [i < k + 1])
+    float dot = 0.f;
+    for (int i = 0; i < K; ++i) {
+      const float gi = scale * ((i < k ? gsk : 0.f) + (i < k + 1 ? gsk1 : 0.f));
+      dot += pr[i] * gi;
+    }
+    for (int i = 0; i < K; ++i) {
+      const float gi = scale * ((i < k ? gsk : 0.f) + (i < k + 1 ? gsk1 : 0.f));
+      g[(which * K + i) * TR_R] = pr[i] * (gi - dot) * isq;
+    }
+  }
+  const float* ud = p + 2 * K * TR_R;
+  for (int j = 0; j < K - 1; ++j) {
+    // unnormalised derivative j is knot j + 1
+    float gd = 0.f;
+    if (j + 1 == k) gd = gd0;
+    else if (j + 1 == k + 1) gd = gd1;
+    g[(2 * K + j) * TR_R] = gd != 0.f ? gd * tr_sigmoid(ud[j * TR_R]) : 0.f;
+  }
+  return gth / S.W;
+}
+
+// Weights are staged in UNITS of one linear x one chunk of <= 64 output columns (so that a wide
+// final layer -- 368 columns for the 32-D spline flow -- needs no more shared memory than a
+// 64 x 64 one), double buffered: unit u lives in buffer u & 1.
+__device__ __forceinline__ int tr_n_chunks(int n_out) { return (n_out + TR_CHUNK - 1) / TR_CHUNK; }
+__device__ __forceinline__ void tr_prefetch_unit(const TrBuffers& Bf, const TrLayer& ly, const TrSmem& S,
+                                                 int j, int q, int u, bool transposed, int max_dim) {
   const TrLinear& ln = ly.lin[j];
-  float* buf = S.W + (j & 1) * S.wbuf;
-  tr_load_w_async(buf, Bf.theta_p + ln.w_off, ln.n_out, ln.n_in, transposed);
-  if (transposed) tr_copy_async4(buf + S.wbuf - tr_align4(P_max_dim), Bf.theta_p + ln.b_off, ln.n_out);
+  const int c0 = q * TR_CHUNK, nc = min(TR_CHUNK, ln.n_out - c0);
+  float* buf = S.W + (u & 1) * S.wbuf;
+  tr_load_w_async(buf, Bf.theta_p + ln.w_off + (size_t)c0 * ln.n_in, nc, ln.n_in, transposed);
+  if (transposed) tr_copy_async4(buf + S.wbuf - TR_CHUNK, Bf.theta_p + ln.b_off + c0, nc);
   tr_cp_commit();
 }
 
 // Conditioner + coupling of layer `ly` on one tile: H1 -> H2 (LU) -> V (net) -> Y.
 // ld[r] += sum log s.  save != NULL: write the layer record (h2 | bufs 1.. | y) there.
-// The caller has queued the weights of linear 0 (tr_prefetch_w) as the most recent commit group.
+// The caller has queued unit (linear 0, chunk 0) into buffer 0 as the most recent commit group.
 __device__ __forceinline__ void tr_layer_forward(const TrBuffers& Bf, const TrPlan& P, const TrLayer& ly,
                                                  const TrSmem& S, float* save) {
   const int D = P.D, act = P.act;
@@ -542,6 +686,7 @@ __device__ __forceinline__ void tr_layer_forward(const TrBuffers& Bf, const TrPl
     S.V[e] = S.H2[itab[ly.id_off + i] * TR_R + r];
   }
   __syncthreads();
+  int u = 0;
   for (int j = 0; j < ly.n_lin; ++j) {
     const TrLinear& ln = ly.lin[j];
     const float* src = S.V + ly.buf_off[ln.in_buf] * TR_R;
@@ -550,17 +695,22 @@ __device__ __forceinline__ void tr_layer_forward(const TrBuffers& Bf, const TrPl
       for (int e = threadIdx.x; e < ln.n_in * TR_R; e += TR_THREADS) S.A[e] = tr_act(act, src[e]);
       Aop = S.A;
     }
-    if (j + 1 < ly.n_lin) {
-      tr_prefetch_w(Bf, ly, S, j + 1, true, P.max_dim);
-      tr_cp_wait<1>();
-    } else {
-      tr_cp_wait<0>();
+    const int nq = tr_n_chunks(ln.n_out);
+    for (int q = 0; q < nq; ++q, ++u) {
+      const bool more = q + 1 < nq || j + 1 < ly.n_lin;
+      if (more) {
+        tr_prefetch_unit(Bf, ly, S, q + 1 < nq ? j : j + 1, q + 1 < nq ? q + 1 : 0, u + 1, true, P.max_dim);
+        tr_cp_wait<1>();
+      } else {
+        tr_cp_wait<0>();
+      }
+      __syncthreads();
+      const int c0 = q * TR_CHUNK, nc = min(TR_CHUNK, ln.n_out - c0);
+      const float* buf = S.W + (u & 1) * S.wbuf;
+      tr_gemm(S.V + (ly.buf_off[ln.out_buf] + c0) * TR_R, Aop, buf, nc | 1, buf + S.wbuf - TR_CHUNK,
+              ln.res_buf >= 0 ? S.V + (ly.buf_off[ln.res_buf] + c0) * TR_R : nullptr, nc, ln.n_in, false);
+      __syncthreads();
     }
-    __syncthreads();
-    tr_gemm(S.V + ly.buf_off[ln.out_buf] * TR_R, Aop, S.W + (j & 1) * S.wbuf, ln.n_out | 1,
-            S.W + (j & 1) * S.wbuf + S.wbuf - tr_align4(P.max_dim), ln.res_buf >= 0 ? S.V + ly.buf_off[ln.res_buf] * TR_R : nullptr,
-            ln.n_out, ln.n_in, false);
-    __syncthreads();
   }
   const float* prm = S.V + ly.buf_off[ly.n_buf - 1] * TR_R;
   for (int e = threadIdx.x; e < ly.d_id * TR_R; e += TR_THREADS) {
@@ -572,7 +722,14 @@ __device__ __forceinline__ void tr_layer_forward(const TrBuffers& Bf, const TrPl
     const int i = e / TR_R, r = e - i * TR_R;
     const int f = itab[ly.tr_off + i];
     const float t = S.H2[f * TR_R + r];
-    if (P.additive) {
+    if (P.num_bins > 0) {
+      TrSpline sp;
+      float y, ld;
+      tr_spline_eval(t, prm + (size_t)i * (3 * P.num_bins - 1) * TR_R + r, P.num_bins, __int_as_float(P.tail_bound),
+                     rsqrtf((float)P.hidden), sp, y, ld);
+      S.Y[f * TR_R + r] = y;
+      S.A[e] = ld;
+    } else if (P.additive) {
       S.Y[f * TR_R + r] = t + prm[e];
       S.A[e] = 0.f;
     } else {
@@ -632,7 +789,7 @@ __global__ void __launch_bounds__(TR_THREADS) tr_fwd_kernel(const __grid_constan
   for (int tile = blockIdx.x; tile < bt.n_tiles; tile += gridDim.x) {
     float* rec = Bf.ws + ((size_t)tile * P.rec_total + ly.ws_off) * TR_R;
     if (l == 0) {
-      tr_prefetch_w(Bf, ly, S, 0, true, P.max_dim);
+      tr_prefetch_unit(Bf, ly, S, 0, 0, 0, true, P.max_dim);
       tr_load_x(bt, tile, D, lperm, S.H1, S.c);
       if (threadIdx.x < TR_R) S.ld[threadIdx.x] = 0.f;
       __syncthreads();
@@ -644,7 +801,7 @@ __global__ void __launch_bounds__(TR_THREADS) tr_fwd_kernel(const __grid_constan
       const float* yprev = Bf.ws + ((size_t)tile * P.rec_total + lp.ws_off + lp.rec_floats - D) * TR_R;
       tr_copy_async(S.Y, yprev, D);
       tr_cp_commit();
-      tr_prefetch_w(Bf, ly, S, 0, true, P.max_dim);
+      tr_prefetch_unit(Bf, ly, S, 0, 0, 0, true, P.max_dim);
       if (threadIdx.x < TR_R) S.ld[threadIdx.x] = Bf.ldrow[tile * TR_R + threadIdx.x];
       tr_cp_wait<1>();
       __syncthreads();
@@ -813,7 +970,7 @@ __global__ void __launch_bounds__(TR_THREADS) tr_bwd_kernel(const __grid_constan
       tr_copy_async(S.Pf, Bf.ws + ((size_t)tile * P.rec_total + lp.ws_off + lp.rec_floats - D) * TR_R, D);
     }
     tr_cp_commit();
-    tr_prefetch_w(Bf, ly, S, ly.n_lin - 1, false, P.max_dim);
+    tr_prefetch_unit(Bf, ly, S, ly.n_lin - 1, 0, 0, false, P.max_dim);
     if (l == 0) tr_load_x(bt, tile, D, lperm, S.H1, S.ld);  // S.ld: scratch for the row weights
     if (threadIdx.x < TR_R) S.c[threadIdx.x] = Bf.crow[tile * TR_R + threadIdx.x];
     for (int e = threadIdx.x; e < P.vals_floats * TR_R; e += TR_THREADS) S.Gv[e] = 0.f;
@@ -843,7 +1000,12 @@ __global__ void __launch_bounds__(TR_THREADS) tr_bwd_kernel(const __grid_constan
         const int i = e / TR_R, r = e - i * TR_R;
         const int f = itab[ly.tr_off + i];
         const float dt2 = S.X[f * TR_R + r];
-        if (P.additive) {
+        if (P.num_bins > 0) {
+          const size_t o = (size_t)i * (3 * P.num_bins - 1) * TR_R + r;
+          S.Y[f * TR_R + r] = tr_spline_backward(S.H2[f * TR_R + r], prm + o, gprm + o, P.num_bins,
+                                                 __int_as_float(P.tail_bound), rsqrtf((float)P.hidden), dt2,
+                                                 -S.c[r]);
+        } else if (P.additive) {
           gprm[e] = dt2;
           S.Y[f * TR_R + r] = dt2;
         } else {
@@ -858,6 +1020,7 @@ __global__ void __launch_bounds__(TR_THREADS) tr_bwd_kernel(const __grid_constan
     }
     __syncthreads();
     // conditioner backward
+    int u = 0;
     for (int j = ly.n_lin - 1; j >= 0; --j) {
       const TrLinear& ln = ly.lin[j];
       const float* src = S.V + ly.buf_off[ln.in_buf] * TR_R;
@@ -867,22 +1030,26 @@ __global__ void __launch_bounds__(TR_THREADS) tr_bwd_kernel(const __grid_constan
         for (int e = threadIdx.x; e < ln.n_in * TR_R; e += TR_THREADS) S.A[e] = tr_act(act, src[e]);
         Aop = S.A;
       }
-      if (j > 0) {
-        tr_prefetch_w(Bf, ly, S, j - 1, false, P.max_dim);
-        tr_cp_wait<1>();
-      } else {
-        tr_cp_wait<0>();
+      const int nq = tr_n_chunks(ln.n_out);
+      for (int q = 0; q < nq; ++q, ++u) {
+        const bool more = q + 1 < nq || j > 0;
+        if (more) {
+          tr_prefetch_unit(Bf, ly, S, q + 1 < nq ? j : j - 1, q + 1 < nq ? q + 1 : 0, u + 1, false, P.max_dim);
+          tr_cp_wait<1>();
+        } else {
+          tr_cp_wait<0>();
+        }
+        __syncthreads();
+        const int c0 = q * TR_CHUNK, nc = min(TR_CHUNK, ln.n_out - c0);
+        tr_wgrad(part + ln.w_off + (size_t)c0 * ln.n_in, delta + c0 * TR_R, Aop, nc, ln.n_in, first);
+        tr_bgrad(part + ln.b_off + c0, delta + c0 * TR_R, nc, first);
+        // A2 (+)= W[c0 : c0 + nc]^T delta[c0 : c0 + nc] (input gradient before the activation derivative)
+        tr_gemm(S.A2, delta + c0 * TR_R, S.W + (u & 1) * S.wbuf, ln.n_in, nullptr, nullptr, ln.n_in, nc, q > 0);
+        __syncthreads();
       }
-      __syncthreads();
-      tr_wgrad(part + ln.w_off, delta, Aop, ln.n_out, ln.n_in, first);
-      tr_bgrad(part + ln.b_off, delta, ln.n_out, first);
-      __syncthreads();
-      // A := W^T delta (input gradient before the activation derivative)
-      tr_gemm(S.A, delta, S.W + (j & 1) * S.wbuf, ln.n_in, nullptr, nullptr, ln.n_in, ln.n_out, false);
-      __syncthreads();
       float* gin = S.Gv + ly.buf_off[ln.in_buf] * TR_R;
       for (int e = threadIdx.x; e < ln.n_in * TR_R; e += TR_THREADS)
-        gin[e] += ln.pre_act ? S.A[e] * tr_dact(act, src[e]) : S.A[e];
+        gin[e] += ln.pre_act ? S.A2[e] * tr_dact(act, src[e]) : S.A2[e];
       if (ln.res_buf >= 0) {
         float* gres = S.Gv + ly.buf_off[ln.res_buf] * TR_R;
         for (int e = threadIdx.x; e < ln.n_out * TR_R; e += TR_THREADS) gres[e] += delta[e];
@@ -1031,8 +1198,10 @@ __global__ void __launch_bounds__(TR_RED_THREADS) tr_reduce_kernel(const __grid_
     const int n_reduce = P.n_reduce;
     const int sub = threadIdx.x & 7;
     const int per_block = TR_RED_THREADS / 8;
-    for (int i = (b - P.L) * per_block + (threadIdx.x >> 3); i < n_reduce + per_block;
-         i += (gridDim.x - P.L) * per_block) {
+    // warp-uniform trip count (the shuffles below need all 32 lanes): 4 parameters per warp
+    for (int base = (b - P.L) * per_block + 4 * (threadIdx.x >> 5); base < n_reduce;
+         base += (gridDim.x - P.L) * per_block) {
+      const int i = base + ((threadIdx.x & 31) >> 3);
       const bool ok = i < n_reduce;
       const int p = ok ? Bf.reduce_idx[i] : 0;
       const float* src = Bf.part + p;
@@ -1139,7 +1308,7 @@ __global__ void __launch_bounds__(TR_THREADS) tr_eval_kernel(const __grid_consta
       const TrLayer& ly = P.layer[l];
       const int* lperm = ly.perm_off >= 0 ? S.itab + ly.perm_off : nullptr;
       if (ly.lu_bias >= 0) tr_lu_dense(S.Wlu, S.stage, Bf.theta_p, ly, D, true);
-      tr_prefetch_w(Bf, ly, S, 0, true, P.max_dim);
+      tr_prefetch_unit(Bf, ly, S, 0, 0, 0, true, P.max_dim);
       if (l == 0) {
         tr_load_x(bt, tile, D, lperm, S.H1, S.c);
         if (threadIdx.x < TR_R) S.ld[threadIdx.x] = 0.f;

@@ -51,8 +51,8 @@ def conditioner_ops(spec: FlowSpec, ls):
 
 def build_train_plan(spec: FlowSpec, ints: dict) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Returns ``(plan int32[TR_PLAN_INTS], itab int32[...], reduce_idx int32[...])``."""
-    if spec.ftype != "realnvp":
-        raise TrainPlanUnsupported("fused training kernels cover RealNVP flows")
+    if spec.ftype == "nsf" and not (2 <= spec.num_bins <= 16):
+        raise TrainPlanUnsupported("fused training kernels cover spline flows with 2..16 bins")
     D, L = spec.D, spec.L
     if D > TR_MAXD or L > TR_MAXL:
         raise TrainPlanUnsupported(f"fused training kernels cover D <= {TR_MAXD}, n_blocks <= {TR_MAXL}")
@@ -63,7 +63,7 @@ def build_train_plan(spec: FlowSpec, ints: dict) -> Tuple[np.ndarray, np.ndarray
     layers = np.zeros((TR_MAXL, TR_LAYER_INTS), dtype=np.int64)
     ws_off = 0
     n_part = spec.n_params
-    max_dim, vals_floats, wmax = D, 0, 0
+    max_dim, vals_floats, wmax, max_in = D, 0, 0, D
     for l, ls in enumerate(spec.layers):
         row = layers[l]
         row[:] = 0
@@ -113,15 +113,19 @@ def build_train_plan(spec: FlowSpec, ints: dict) -> Tuple[np.ndarray, np.ndarray
             row[base + 8 * j : base + 8 * j + 8] = [w, b, lr.n_in, lr.n_out, i_in, i_out, i_res, pre]
             reduce_idx.extend(range(w, w + lr.n_in * lr.n_out))
             reduce_idx.extend(range(b, b + lr.n_out))
-            wmax = max(wmax, lr.n_in * (lr.n_out | 1), lr.n_in * lr.n_out)
+            wmax = max(wmax, lr.n_in * (min(lr.n_out, 64) | 1))  # one unit = <= 64 output columns
+            max_in = max(max_in, lr.n_in)
         ws_off += rec
         max_dim = max(max_dim, max(buf_dim))
         vals_floats = max(vals_floats, sum(buf_dim))
     head = np.zeros(16, dtype=np.int64)
-    head[:12] = [
+    head[:16] = [
         D, L, spec.activation, int(spec.volume_preserving),
         spec.n_params, n_part, ws_off, max_dim,
         vals_floats, wmax, len(itab), len(reduce_idx),
+        spec.num_bins if spec.ftype == "nsf" else 0,
+        int(np.float32(spec.tail_bound).view(np.int32)) if spec.ftype == "nsf" else 0,
+        spec.H, max_in,
     ]
     plan = np.concatenate([head, layers.ravel()]).astype(np.int32)
     assert plan.size == TR_PLAN_INTS

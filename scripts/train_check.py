@@ -1,4 +1,5 @@
 """GPU check of the fused training kernels against the float64 oracle (one case, verbose)."""
+import faulthandler; faulthandler.dump_traceback_later(40, exit=True)
 import json, os, sys, tempfile, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -138,10 +138,6 @@ def test_train_plan_packs_every_golden_realnvp():
         theta = np.zeros(spec.n_theta, dtype=np.float32)
         ints = {}
         spec.load_state_dict_numpy(sd, theta, ints)
-        if spec.ftype != "realnvp":
-            with pytest.raises(TrainPlanUnsupported):
-                build_train_plan(spec, ints)
-            continue
         plan, itab, red = build_train_plan(spec, ints)
         assert plan.size == TR_PLAN_INTS and plan[0] == spec.D and plan[1] == spec.L
         covered = np.zeros(spec.n_params, dtype=int)
