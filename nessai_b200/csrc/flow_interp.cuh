@@ -90,9 +90,12 @@ __device__ __forceinline__ void op_coupling_affine(const FlowOp& op, const float
                                                    float* const* bufs, int BS, float& ld) {
   const float* bs = Ws + op.K * op.Npad;
   const float* src = bufs[op.src];
-  float* x = bufs[op.x_buf] + op.d_id * BS;
+  const float* x = bufs[op.x_buf] + op.d_id * BS;  // values the affine acts on
+  float* xo = bufs[op.dst] + op.d_id * BS;         // == x except for the MAF inverse passes
   const bool inverse = op.flags & FLAG_INVERSE;
   const bool additive = op.flags & FLAG_ADDITIVE;
+  const bool softplus_scale = op.flags & FLAG_SOFTPLUS_SCALE;
+  const bool count_ld = !(op.flags & FLAG_NO_LOGDET);
   for (int n0 = 0; n0 < op.Npad; n0 += 8) {
     float acc[8];
 #pragma unroll
@@ -117,15 +120,17 @@ __device__ __forceinline__ void op_coupling_affine(const FlowOp& op, const float
         const float t = acc[2 * i];
         float s = 1.f, ls = 0.f;
         if (!additive) {
-          s = 1.f / (1.f + expf(-(acc[2 * i + 1] + 2.f))) + 1e-3f;
-          ls = logf(s);
+          const float u = acc[2 * i + 1];
+          s = softplus_scale ? (u > 20.f ? u : log1pf(expf(u))) + 1e-3f
+                             : 1.f / (1.f + expf(-(u + 2.f))) + 1e-3f;
+          ls = count_ld ? logf(s) : 0.f;
         }
         const float xi = x[f * BS];
         if (inverse) {
-          x[f * BS] = (xi - t) / s;
+          xo[f * BS] = (xi - t) / s;
           ld -= ls;
         } else {
-          x[f * BS] = fmaf(xi, s, t);
+          xo[f * BS] = fmaf(xi, s, t);
           ld += ls;
         }
       }

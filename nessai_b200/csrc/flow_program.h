@@ -15,7 +15,9 @@ enum : int {
   FLAG_OUT_ACT = 2,   // activation applied to the op's output
   FLAG_ACCUM = 4,     // dst += (residual connection)
   FLAG_INVERSE = 8,   // coupling applied in the inverse direction
-  FLAG_ADDITIVE = 16  // volume preserving coupling (scale == 1)
+  FLAG_ADDITIVE = 16,       // volume preserving coupling (scale == 1)
+  FLAG_SOFTPLUS_SCALE = 32, // scale = softplus(u) + 1e-3 (nflows MaskedAffineAutoregressiveTransform)
+  FLAG_NO_LOGDET = 64       // do not accumulate log|det| (intermediate passes of the MAF inverse)
 };
 enum : int { BUF_X0 = 0, BUF_X1 = 1, BUF_A0 = 2, BUF_A1 = 3 };
 enum : int { ACT_RELU = 0, ACT_TANH = 1, ACT_SILU = 2 };

@@ -164,6 +164,7 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
         2 * c.d_tr > TC_N3 || c.d_id + c.d_tr != D || c.N != 2 * c.d_tr)
       return 0;
     const int inv = (c.flags & FLAG_INVERSE) ? 1 : 0, add = (c.flags & FLAG_ADDITIVE) ? 1 : 0;
+    if ((c.flags & ~(FLAG_INVERSE | FLAG_ADDITIVE)) != 0 || c.x_buf != c.dst) return 0;
     if ((inverse >= 0 && inverse != inv) || (additive >= 0 && additive != add)) return 0;
     inverse = inv;
     additive = add;

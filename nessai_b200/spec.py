@@ -40,6 +40,8 @@ FLAG_OUT_ACT = 2
 FLAG_ACCUM = 4
 FLAG_INVERSE = 8
 FLAG_ADDITIVE = 16
+FLAG_SOFTPLUS_SCALE = 32  # scale = softplus(u) + 1e-3 (masked affine autoregressive transform)
+FLAG_NO_LOGDET = 64  # do not accumulate log|det| (intermediate passes of the MAF inverse)
 
 BUF_X0, BUF_X1, BUF_A0, BUF_A1 = 0, 1, 2, 3
 
@@ -97,6 +99,7 @@ class LinearRef:
     bias: str
     n_in: int
     n_out: int
+    mask: Optional[str] = None  # MADE: float buffer multiplied into the weight
 
 
 @dataclass
@@ -155,9 +158,11 @@ class FlowSpec:
             self.ftype = "realnvp"
         elif ftype in ("nsf", "spline"):
             self.ftype = "nsf"
+        elif ftype == "maf":
+            self.ftype = "maf"
         else:
             raise NotImplementedError(
-                f"nessai_b200: flow type {ftype!r} is not implemented (realnvp, nsf)"
+                f"nessai_b200: flow type {ftype!r} is not implemented (realnvp, nsf, maf)"
             )
         act = cfg.pop("activation", "relu")
         if callable(act):
@@ -193,6 +198,18 @@ class FlowSpec:
             mask = cfg.pop("mask", None)
             self.num_bins = 0
             self.tail_bound = 0.0
+        elif self.ftype == "maf":
+            # /root/reference/src/nessai/flows/maf.py:62-104
+            self.net = "resnet" if cfg.pop("use_residual_blocks", True) else "mlp"
+            if cfg.pop("use_random_masks", False):
+                raise NotImplementedError("nessai_b200: MAF with random masks is not implemented")
+            self.random_permutations = bool(cfg.pop("use_random_permutations", False))
+            self.volume_preserving = False
+            self.bn_between = bool(cfg.pop("batch_norm_between_layers", False))
+            self.linear_transform = "permutation"
+            self.num_bins = 0
+            self.tail_bound = 0.0
+            mask = None
         else:
             self.net = "resnet"
             self.volume_preserving = False
@@ -228,6 +245,8 @@ class FlowSpec:
     # ------------------------------------------------------------------ masks
     def _make_masks(self, mask) -> np.ndarray:
         D, L = self.D, self.L
+        if self.ftype == "maf":
+            return np.ones((L, D))  # every feature is transformed (autoregressively)
         if self.ftype == "nsf":
             # create_alternating_binary_mask(features, even=(i % 2 == 0)):
             # ones (= transformed) at start::2, start = 0 if even else 1
@@ -259,7 +278,7 @@ class FlowSpec:
     def coupling_multiplier(self) -> int:
         if self.ftype == "nsf":
             return 3 * self.num_bins - 1
-        return 1 if self.volume_preserving else 2
+        return 1 if (self.volume_preserving and self.ftype == "realnvp") else 2
 
     def _build_layout(self) -> None:
         D, H = self.D, self.H
@@ -284,6 +303,40 @@ class FlowSpec:
                 ls.perm_key = f"{root}.{t}._permutation"
                 entries.append(Entry(ls.perm_key, (D,), "ibuf"))
                 t += 1
+            if self.ftype == "maf":
+                cp = f"{root}.{t}"
+                ls.coupling_prefix = cp
+                ls.identity = np.zeros(0, dtype=np.int64)
+                ls.transform = np.arange(D, dtype=np.int64)
+                net = f"{cp}.autoregressive_net"
+
+                def mlin(name, n_in, n_o):
+                    entries.append(Entry(f"{net}.{name}.weight", (n_o, n_in), "param"))
+                    entries.append(Entry(f"{net}.{name}.bias", (n_o,), "param"))
+                    entries.append(Entry(f"{net}.{name}.mask", (n_o, n_in), "fbuf"))
+                    entries.append(Entry(f"{net}.{name}.degrees", (n_o,), "ibuf"))
+                    ls.linears.append(LinearRef(f"{net}.{name}.weight", f"{net}.{name}.bias", n_in, n_o,
+                                                f"{net}.{name}.mask"))
+
+                mlin("initial_layer", D, H)
+                for b in range(self.n_layers):
+                    if self.net == "resnet":
+                        mlin(f"blocks.{b}.linear_layers.0", H, H)
+                        mlin(f"blocks.{b}.linear_layers.1", H, H)
+                    else:
+                        mlin(f"blocks.{b}.linear", H, H)
+                mlin("final_layer", H, 2 * D)
+                t += 1
+                if self.bn_between:
+                    bp = f"{root}.{t}"
+                    ls.bn_prefix = bp
+                    entries.append(Entry(f"{bp}.unconstrained_weight", (D,), "param"))
+                    entries.append(Entry(f"{bp}.bias", (D,), "param"))
+                    entries.append(Entry(f"{bp}.running_mean", (D,), "fbuf"))
+                    entries.append(Entry(f"{bp}.running_var", (D,), "fbuf"))
+                    t += 1
+                layers.append(ls)
+                continue
             cp = f"{root}.{t}"
             ls.coupling_prefix = cp
             m = self.masks[i]
@@ -361,12 +414,18 @@ class FlowSpec:
 
         for ls in self.layers:
             if ls.perm_key is not None:
-                ints[ls.perm_key] = torch.randperm(self.D).numpy().astype(np.int64)
+                if self.ftype == "maf" and not self.random_permutations:
+                    ints[ls.perm_key] = np.arange(self.D - 1, -1, -1, dtype=np.int64)  # ReversePermutation
+                else:
+                    ints[ls.perm_key] = torch.randperm(self.D).numpy().astype(np.int64)
             if ls.lu_prefix is not None:
                 const = np.log(np.exp(1 - self.LU_EPS) - 1)
                 put(f"{ls.lu_prefix}.unconstrained_upper_diag", np.full(self.D, const))
-            ints[f"{ls.coupling_prefix}.identity_features"] = ls.identity.copy()
-            ints[f"{ls.coupling_prefix}.transform_features"] = ls.transform.copy()
+            if self.ftype == "maf":
+                self._made_masks(ls, theta, ints)
+            else:
+                ints[f"{ls.coupling_prefix}.identity_features"] = ls.identity.copy()
+                ints[f"{ls.coupling_prefix}.transform_features"] = ls.transform.copy()
             for lr in ls.linears:
                 # torch.nn.Linear.reset_parameters (stock torch)
                 w = torch.empty(lr.n_out, lr.n_in)
@@ -385,6 +444,28 @@ class FlowSpec:
                 put(f"{ls.bn_prefix}.unconstrained_weight", np.full(self.D, const))
                 put(f"{ls.bn_prefix}.running_var", np.full(self.D, reset_bn_running_var_to))
         return theta, ints
+
+    def _made_masks(self, ls: "LayerSpec", theta: np.ndarray, ints: Dict[str, np.ndarray]) -> None:
+        """Degrees and masks of nflows' MADE with sequential (non-random) degrees
+        (glasflow.nflows.transforms.made.MaskedLinear._get_mask_and_degrees): hidden
+        units get degrees ``arange(H) % max(1, D-1) + min(1, D-1)`` and see inputs of
+        degree <= their own; output (2 per feature, feature-major) ``i`` sees hidden
+        units of degree < i."""
+        D = self.D
+        in_deg = np.arange(1, D + 1)
+        for k, lr in enumerate(ls.linears):
+            is_output = k == len(ls.linears) - 1
+            if is_output:
+                out_deg = np.repeat(np.arange(1, D + 1), lr.n_out // D)
+                mask = out_deg[:, None] > in_deg[None, :]
+            else:
+                mx, mn = max(1, D - 1), min(1, D - 1)
+                out_deg = np.arange(lr.n_out) % mx + mn
+                mask = out_deg[:, None] >= in_deg[None, :]
+            e = self.by_key[lr.mask]
+            theta[e.offset : e.offset + e.size] = mask.astype(np.float32).ravel()
+            ints[lr.mask[: -len("mask")] + "degrees"] = out_deg.astype(np.int64)
+            in_deg = out_deg
 
     def reset_weights(self, theta: np.ndarray) -> None:
         """In-place mirror of ``model.apply(reset_weights)``
@@ -420,7 +501,7 @@ class FlowSpec:
         import torch
 
         for ls in self.layers:
-            if ls.perm_key is not None:
+            if ls.perm_key is not None and not (self.ftype == "maf" and not self.random_permutations):
                 ints[ls.perm_key] = torch.randperm(self.D).numpy().astype(np.int64)
             if ls.lu_prefix is not None:
                 for name, val in (
@@ -540,10 +621,13 @@ class FoldedFlow:
     # -- conditioner weights as (W (out,in), b (out,)) float64 ----------------
     def net_weights(self, ls: LayerSpec):
         sp = self.spec
-        return [
-            (sp.get(self.theta64, lr.weight), sp.get(self.theta64, lr.bias))
-            for lr in ls.linears
-        ]
+        out = []
+        for lr in ls.linears:
+            W = sp.get(self.theta64, lr.weight)
+            if lr.mask is not None:
+                W = W * sp.get(self.theta64, lr.mask)
+            out.append((W, sp.get(self.theta64, lr.bias)))
+        return out
 
     def program(self, inverse: bool) -> "Program":
         """Encode one direction as the op list + float blob the kernels run."""
@@ -587,7 +671,60 @@ class FoldedFlow:
             emit_linear(cur_x, dst, A, b, 0)
             cur_x = dst
 
+        def emit_made(ls: LayerSpec, src_x, dst_x, z_x, flags):
+            """One MADE pass reading its input from ``src_x``; the affine acts on ``z_x`` and
+            writes ``dst_x`` (nflows MaskedAffineAutoregressiveTransform: params viewed
+            (N, D, 2) = (unconstrained scale, shift); scale = softplus(u) + 1e-3)."""
+            ws = self.net_weights(ls)
+            W, b = ws[0]
+            if sp.net == "resnet":
+                emit_linear(src_x, BUF_A0, W, b, 0)
+                for blk in range(sp.n_layers):
+                    W0, b0 = ws[1 + 2 * blk]
+                    W1, b1 = ws[2 + 2 * blk]
+                    emit_linear(BUF_A0, BUF_A1, W0, b0, FLAG_IN_ACT | FLAG_OUT_ACT)
+                    emit_linear(BUF_A1, BUF_A0, W1, b1, FLAG_ACCUM)
+                last_src = BUF_A0
+            else:
+                bufs = [BUF_A0, BUF_A1]
+                emit_linear(src_x, bufs[0], W, b, FLAG_OUT_ACT)
+                src = bufs[0]
+                for j, (Wj, bj) in enumerate(ws[1:-1]):
+                    dst = bufs[(j + 1) % 2]
+                    emit_linear(src, dst, Wj, bj, FLAG_OUT_ACT)
+                    src = dst
+                last_src = src
+            Wf, bf = ws[-1]
+            K = Wf.shape[1]
+            # kernel layout: interleaved (shift_i, unconstrained_scale_i)
+            Wi = np.zeros((2 * D, K))
+            bi = np.zeros(2 * D)
+            Wi[0::2], bi[0::2] = Wf[1::2], bf[1::2]
+            Wi[1::2], bi[1::2] = Wf[0::2], bf[0::2]
+            Np = _pad8(2 * D)
+            Wk = np.zeros((K, Np))
+            Wk[:, : 2 * D] = Wi.T
+            bp = np.zeros(Np)
+            bp[: 2 * D] = bi
+            w_off = push(Wk)
+            b_off = push(bp)
+            ops.append([OP_COUPLING_AFFINE, last_src, dst_x, 0, K, 2 * D, Np, w_off, b_off,
+                        flags | FLAG_SOFTPLUS_SCALE, z_x, 0, D, 0, 0, 0])
+
         def emit_coupling(ls: LayerSpec):
+            nonlocal cur_x
+            if sp.ftype == "maf":
+                if not inverse:
+                    emit_made(ls, cur_x, cur_x, cur_x, 0)
+                    return
+                # inverse: D sequential passes from x = 0 (AutoregressiveTransform.inverse)
+                other = BUF_X1 if cur_x == BUF_X0 else BUF_X0
+                emit_linear(cur_x, other, np.zeros((D, D)), np.zeros(D), 0)
+                for i in range(D):
+                    last = i == D - 1
+                    emit_made(ls, other, other, cur_x, FLAG_INVERSE | (0 if last else FLAG_NO_LOGDET))
+                cur_x = other
+                return
             d_id, d_tr = len(ls.identity), len(ls.transform)
             ws = self.net_weights(ls)
             if sp.net == "mlp":

@@ -51,6 +51,8 @@ def conditioner_ops(spec: FlowSpec, ls):
 
 def build_train_plan(spec: FlowSpec, ints: dict) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Returns ``(plan int32[TR_PLAN_INTS], itab int32[...], reduce_idx int32[...])``."""
+    if spec.ftype == "maf":
+        raise TrainPlanUnsupported("fused training kernels do not cover masked autoregressive flows yet")
     if spec.ftype == "nsf" and not (2 <= spec.num_bins <= 16):
         raise TrainPlanUnsupported("fused training kernels cover spline flows with 2..16 bins")
     D, L = spec.D, spec.L

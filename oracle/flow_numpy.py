@@ -90,6 +90,8 @@ class NumpyFlow:
                 out.append(("perm", p))
             elif f"{p}.identity_features" in self.sd:
                 out.append(("coupling", p))
+            elif f"{p}.autoregressive_net.initial_layer.weight" in self.sd:
+                out.append(("maf", p))
             elif f"{p}.unconstrained_weight" in self.sd:
                 out.append(("bn", p))
             else:
@@ -243,6 +245,50 @@ class NumpyFlow:
         ld = np.where(inside, ld, 0.0)
         return out, ld
 
+    # ------------------------------------------- masked affine autoregressive
+    def _made(self, p, h):
+        """nflows MADE (/root/reference/src/nessai/flows/maf.py:84-98 ->
+        MaskedAffineAutoregressiveTransform): masked linears, residual blocks
+        ``h += lin1(act(lin0(act(h))))`` or feed-forward blocks ``act(lin(h))``."""
+        sd, act = self.sd, self.act
+        n = f"{p}.autoregressive_net"
+
+        def lin(name, v):
+            return v @ (sd[f"{n}.{name}.weight"] * sd[f"{n}.{name}.mask"]).T + sd[f"{n}.{name}.bias"]
+
+        h = lin("initial_layer", h)
+        if f"{n}.blocks.0.linear_layers.0.weight" in sd:
+            b = 0
+            while f"{n}.blocks.{b}.linear_layers.0.weight" in sd:
+                t = lin(f"blocks.{b}.linear_layers.0", act(h))
+                h = h + lin(f"blocks.{b}.linear_layers.1", act(t))
+                b += 1
+        else:
+            h = act(h)
+            b = 0
+            while f"{n}.blocks.{b}.linear.weight" in sd:
+                h = act(lin(f"blocks.{b}.linear", h))
+                b += 1
+        return lin("final_layer", h)
+
+    def _maf(self, p, x, inverse):
+        """params viewed (N, D, 2) = (unconstrained scale, shift); scale = softplus(u) + 1e-3;
+        inverse = D sequential passes from zeros (AutoregressiveTransform.inverse)."""
+        D = x.shape[1]
+
+        def scale_shift(inp):
+            prm = self._made(p, inp).reshape(len(inp), D, 2)
+            return softplus(prm[..., 0]) + 1e-3, prm[..., 1]
+
+        if not inverse:
+            s, t = scale_shift(x)
+            return s * x + t, np.sum(np.log(s), axis=1)
+        out = np.zeros_like(x)
+        for _ in range(D):
+            s, t = scale_shift(out)
+            out = (x - t) / s
+        return out, -np.sum(np.log(s), axis=1)
+
     # ---------------------------------------------------------------- public
     def _apply(self, kind, p, x, inverse):
         return {
@@ -250,6 +296,7 @@ class NumpyFlow:
             "lu": self._lu,
             "bn": self._bn,
             "coupling": self._coupling,
+            "maf": self._maf,
         }[kind](p, x, inverse)
 
     def forward(self, x):

@@ -44,15 +44,18 @@ def run_program(prog, rows, dtype=np.float64):
             u = out[:, 1 : 2 * d_tr : 2]
             if flags & S.FLAG_ADDITIVE:
                 s = np.ones_like(t)
+            elif flags & S.FLAG_SOFTPLUS_SCALE:
+                s = np.logaddexp(0, u) + dtype(1e-3)
             else:
                 s = 1 / (1 + np.exp(-(u + 2))) + dtype(1e-3)
             x = bufs[xb][:, d_id : d_id + d_tr]
+            ls = 0.0 if flags & S.FLAG_NO_LOGDET else np.log(s).sum(1)
             if flags & S.FLAG_INVERSE:
-                bufs[xb][:, d_id : d_id + d_tr] = (x - t) / s
-                ld -= np.log(s).sum(1)
+                bufs[dst][:, d_id : d_id + d_tr] = (x - t) / s
+                ld -= ls
             else:
-                bufs[xb][:, d_id : d_id + d_tr] = x * s + t
-                ld += np.log(s).sum(1)
+                bufs[dst][:, d_id : d_id + d_tr] = x * s + t
+                ld += ls
         else:
             raise NotImplementedError(typ)
     return bufs[prog.final_buf][:, : prog.D].copy(), ld + dtype(prog.const_logdet)

@@ -16,6 +16,7 @@ GOLDEN_NAMES = [
     "d4_realnvp_additive_silu",
     "c1_realnvp_2d",
     "d6_nsf",
+    "d8_maf",
 ]
 
 

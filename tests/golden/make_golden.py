@@ -80,7 +80,7 @@ def make(name, flow_config, data, n_eval, epochs, tmp):
         inv_x, inv_lj = model.inverse(z)
         inv_lq = model.base_distribution_log_prob(z) - inv_lj
     kw = dict(
-        ftype="nsf" if str(flow_config.get("ftype")).lower() == "nsf" else "realnvp",
+        ftype={"nsf": "nsf", "maf": "maf"}.get(str(flow_config.get("ftype")).lower(), "realnvp"),
         net=flow_config.get("net", "resnet"),
         activation_name=flow_config.get("activation", "relu"),
         volume_preserving=flow_config.get("use_volume_preserving", False),
@@ -127,6 +127,14 @@ def main():
     import tempfile
 
     tmp = tempfile.mkdtemp()
+    only = set(sys.argv[1:])  # e.g. `make_golden.py d8_maf`: regenerate just that fixture
+    global make
+    _make = make
+
+    def make(name, *a, **k):  # noqa: F811
+        if not only or name in only:
+            _make(name, *a, **k)
+
     rng = np.random.default_rng(SEED)
     live16 = gaussian_live_points(2000, 16, rng)
     # C2: 16-D RealNVP, 4 coupling layers, [64, 64] MLP conditioner
@@ -167,6 +175,12 @@ def main():
         "d6_nsf",
         dict(n_inputs=6, n_neurons=16, n_blocks=3, n_layers=2, ftype="nsf"),
         rosenbrock_like(2000, 6, rng), 512, 60, tmp,
+    )
+    # masked autoregressive flow: MADE with residual blocks, reverse permutations
+    make(
+        "d8_maf",
+        dict(n_inputs=8, n_neurons=32, n_blocks=3, n_layers=2, ftype="maf"),
+        rosenbrock_like(2000, 8, np.random.default_rng(SEED + 8)), 512, 60, tmp,
     )
 
 

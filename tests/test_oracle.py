@@ -17,7 +17,7 @@ from oracle.philox_numpy import philox4x32_10
 def numpy_flow(cfg, sd):
     return NumpyFlow(
         sd,
-        ftype="nsf" if str(cfg.get("ftype")).lower() == "nsf" else "realnvp",
+        ftype={"nsf": "nsf", "maf": "maf"}.get(str(cfg.get("ftype")).lower(), "realnvp"),
         net=cfg.get("net", "resnet"),
         activation_name=cfg.get("activation", "relu"),
         volume_preserving=cfg.get("use_volume_preserving", False),

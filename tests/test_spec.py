@@ -107,7 +107,9 @@ def test_reset_weights_matches_reference():
 
 def test_unsupported_options_fail_loudly():
     with pytest.raises(NotImplementedError):
-        FlowSpec(dict(n_inputs=4, ftype="maf"))
+        FlowSpec(dict(n_inputs=4, ftype="maf", use_random_masks=True))
+    with pytest.raises(NotImplementedError):
+        FlowSpec(dict(n_inputs=4, ftype="glow"))
     with pytest.raises(NotImplementedError):
         FlowSpec(dict(n_inputs=4, ftype="realnvp", linear_transform="svd"))
     with pytest.raises(NotImplementedError):
@@ -138,6 +140,10 @@ def test_train_plan_packs_every_golden_realnvp():
         theta = np.zeros(spec.n_theta, dtype=np.float32)
         ints = {}
         spec.load_state_dict_numpy(sd, theta, ints)
+        if spec.ftype == "maf":
+            with pytest.raises(TrainPlanUnsupported):
+                build_train_plan(spec, ints)
+            continue
         plan, itab, red = build_train_plan(spec, ints)
         assert plan.size == TR_PLAN_INTS and plan[0] == spec.D and plan[1] == spec.L
         covered = np.zeros(spec.n_params, dtype=int)
