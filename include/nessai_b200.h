@@ -130,6 +130,10 @@ int nb200_trainer_create(nb200_trainer** out, const int32_t* h_plan, int n_plan_
                          const int32_t* h_itab, int n_itab, const int32_t* h_reduce_idx,
                          int n_reduce);
 int nb200_trainer_destroy(nb200_trainer* trainer);
+/* MADE masks (flows/maf.py -> nflows MaskedLinear): h_mask float[n_params], the mask value for
+ * masked-linear weights and 1 elsewhere (NULL: none).  Masked weights are held at exactly zero
+ * (theta_p *= mask at the start of every epoch) and their gradients are masked. */
+int nb200_trainer_set_param_mask(nb200_trainer* trainer, const float* h_mask);
 /* Copy the gradient of the last step (n_params floats, after clipping) to d_out. */
 int nb200_trainer_copy_grad(nb200_trainer* trainer, float* d_out, void* stream);
 

@@ -103,6 +103,7 @@ _SIGS = {
         [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int],
     ),
     "nb200_trainer_destroy": (C.c_int, [C.c_void_p]),
+    "nb200_trainer_set_param_mask": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nb200_trainer_copy_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nb200_train_epoch": (
         C.c_int,

@@ -652,7 +652,7 @@ struct nb200_trainer {
   float *ws = nullptr, *dout0 = nullptr, *dout1 = nullptr, *ldrow = nullptr, *crow = nullptr;
   float *stat_part = nullptr, *stats = nullptr, *s_part0 = nullptr, *s_part1 = nullptr;
   float *wsum_part = nullptr, *loss_part = nullptr, *part = nullptr, *grad = nullptr;
-  float *gn_part = nullptr, *eval_part = nullptr;
+  float *gn_part = nullptr, *eval_part = nullptr, *pmask = nullptr;
   float* stat_n = nullptr;
   size_t smem_fwd = 0, smem_bwd = 0;
 };
@@ -669,7 +669,7 @@ extern "C" int nb200_trainer_destroy(nb200_trainer* t) {
   cudaFree(t->d_plan), cudaFree(t->d_itab), cudaFree(t->d_reduce);
   cudaFree(t->stat_part), cudaFree(t->stats), cudaFree(t->s_part0), cudaFree(t->s_part1);
   cudaFree(t->wsum_part), cudaFree(t->loss_part), cudaFree(t->part), cudaFree(t->grad);
-  cudaFree(t->gn_part), cudaFree(t->eval_part), cudaFree(t->stat_n);
+  cudaFree(t->gn_part), cudaFree(t->eval_part), cudaFree(t->stat_n), cudaFree(t->pmask);
   delete t;
   return 0;
 }
@@ -771,8 +771,21 @@ static TrBuffers trainer_buffers(nb200_trainer* t, float* theta_p, float* theta_
   B.grad = t->grad;
   B.gn_part = t->gn_part;
   B.G = G;
+  B.pmask = t->pmask;
   B.n_reduce_blocks = std::min(TR_REDUCE_MAXBLOCKS, t->h_plan.L + std::max(1, (t->h_plan.n_reduce * 8 + TR_RED_THREADS - 1) / TR_RED_THREADS));
   return B;
+}
+
+extern "C" int nb200_trainer_set_param_mask(nb200_trainer* t, const float* h_mask) {
+  if (!t) return fail(1, "nb200_trainer_set_param_mask: bad arguments");
+  if (!h_mask) {
+    cudaFree(t->pmask);
+    t->pmask = nullptr;
+    return 0;
+  }
+  if (!t->pmask) TR_ALLOC(t->pmask, t->h_plan.n_params);
+  CUDA_OK(cudaMemcpy(t->pmask, h_mask, sizeof(float) * t->h_plan.n_params, cudaMemcpyHostToDevice));
+  return 0;
 }
 
 extern "C" int nb200_trainer_copy_grad(nb200_trainer* t, float* d_out, void* stream) {
@@ -803,6 +816,11 @@ extern "C" int nb200_train_epoch(nb200_trainer* t, float* d_theta_p, float* d_th
   if (int rc = prep_kernel(tr_fwd_kernel, t->smem_fwd)) return rc;
   if (int rc = prep_kernel(tr_loss_kernel, t->smem_fwd)) return rc;
   if (int rc = prep_kernel(tr_bwd_kernel, t->smem_bwd)) return rc;
+  if (t->pmask) {
+    tr_mask_params_kernel<<<std::min((P.n_params + 255) / 256, 2 * t->num_sms), 256, 0, st>>>(d_theta_p, t->pmask,
+                                                                                                 P.n_params);
+    g_launches += 1;
+  }
   int64_t step = step0;
   int ib = 0;
   for (int64_t i0 = 0; i0 < n_rows; i0 += batch_size, ++ib) {
@@ -873,6 +891,11 @@ extern "C" int nb200_eval_loss(nb200_trainer* t, float* d_theta_p, float* d_thet
   bt.n_tiles = (int)((n + TR_R - 1) / TR_R);
   const int G = std::min(bt.n_tiles, 2 * t->num_sms);
   TrBuffers B = trainer_buffers(t, d_theta_p, d_theta_b, G);
+  if (t->pmask) {
+    tr_mask_params_kernel<<<std::min((t->h_plan.n_params + 255) / 256, 2 * t->num_sms), 256, 0, st>>>(
+        d_theta_p, t->pmask, t->h_plan.n_params);
+    g_launches += 1;
+  }
   tr_eval_kernel<<<G, TR_THREADS, t->smem_fwd, st>>>(t->h_plan, B, bt, t->eval_part, d_logp);
   if (d_loss) tr_eval_final_kernel<<<1, 32, 0, st>>>(t->eval_part, G, d_loss);
   g_launches += d_loss ? 2 : 1;

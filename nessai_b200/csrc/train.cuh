@@ -49,7 +49,7 @@ struct TrLayer {
   TrLinear lin[TR_MAXLIN];
 };
 struct TrPlan {
-  int D, L, act, additive;
+  int D, L, act, additive;  // additive: 0 affine coupling, 1 additive coupling, 2 masked affine autoregressive (MAF)
   int n_params, n_part, rec_total, max_dim;
   int vals_floats, wmax, n_itab, n_reduce;
   int num_bins;      // > 0: rational-quadratic spline coupling (NSF) with this many bins
@@ -82,6 +82,7 @@ struct TrBuffers {
   float* grad;        // [n_params]
   float* gn_part;     // [n_reduce_blocks]
   int n_reduce_blocks;
+  const float* pmask; // [n_params] or NULL: MADE masks (1 elsewhere); masked weights stay exactly 0
   int G;              // CTAs of the row kernels
 };
 
@@ -729,7 +730,12 @@ __device__ __forceinline__ void tr_layer_forward(const TrBuffers& Bf, const TrPl
                      rsqrtf((float)P.hidden), sp, y, ld);
       S.Y[f * TR_R + r] = y;
       S.A[e] = ld;
-    } else if (P.additive) {
+    } else if (P.additive == 2) {
+      // MaskedAffineAutoregressiveTransform: params (D, 2) = (unconstrained scale, shift)
+      const float s = tr_softplus(prm[(2 * i) * TR_R + r]) + 1e-3f;
+      S.Y[f * TR_R + r] = fmaf(t, s, prm[(2 * i + 1) * TR_R + r]);
+      S.A[e] = logf(s);
+    } else if (P.additive == 1) {
       S.Y[f * TR_R + r] = t + prm[e];
       S.A[e] = 0.f;
     } else {
@@ -1005,7 +1011,14 @@ __global__ void __launch_bounds__(TR_THREADS) tr_bwd_kernel(const __grid_constan
           S.Y[f * TR_R + r] = tr_spline_backward(S.H2[f * TR_R + r], prm + o, gprm + o, P.num_bins,
                                                  __int_as_float(P.tail_bound), rsqrtf((float)P.hidden), dt2,
                                                  -S.c[r]);
-        } else if (P.additive) {
+        } else if (P.additive == 2) {
+          const float u = prm[(2 * i) * TR_R + r];
+          const float s = tr_softplus(u) + 1e-3f;
+          const float ds = dt2 * S.H2[f * TR_R + r] - S.c[r] / s;
+          gprm[(2 * i) * TR_R + r] = ds * tr_sigmoid(u);
+          gprm[(2 * i + 1) * TR_R + r] = dt2;
+          S.Y[f * TR_R + r] = dt2 * s;
+        } else if (P.additive == 1) {
           gprm[e] = dt2;
           S.Y[f * TR_R + r] = dt2;
         } else {
@@ -1060,7 +1073,8 @@ __global__ void __launch_bounds__(TR_THREADS) tr_bwd_kernel(const __grid_constan
     for (int e = threadIdx.x; e < ly.d_id * TR_R; e += TR_THREADS) {
       const int i = e / TR_R, r = e - i * TR_R;
       const int f = itab[ly.id_off + i];
-      S.Y[f * TR_R + r] = S.X[f * TR_R + r] + S.Gv[e];
+      // MAF: every feature is both conditioner input and transformed -> add the two paths
+      S.Y[f * TR_R + r] = (P.additive == 2 ? S.Y[f * TR_R + r] : S.X[f * TR_R + r]) + S.Gv[e];
     }
     // layer input h1 (and x-hat of the previous BatchNorm, into X)
     __syncthreads();
@@ -1221,6 +1235,7 @@ __global__ void __launch_bounds__(TR_RED_THREADS) tr_reduce_kernel(const __grid_
       sgm += __shfl_xor_sync(0xffffffffu, sgm, 2);
       sgm += __shfl_xor_sync(0xffffffffu, sgm, 4);
       if (ok && sub == 0) {
+        if (Bf.pmask) sgm *= Bf.pmask[p];
         Bf.grad[p] = sgm;
         sq += sgm * sgm;
       }
@@ -1291,6 +1306,12 @@ __global__ void __launch_bounds__(256) tr_adam_kernel(TrBuffers Bf, int n_params
     const float denom = sqrtf(vi) / sqrtf(o.bc2) + o.eps;
     Bf.theta_p[i] = p - (o.lr / o.bc1) * (mi / denom);
   }
+}
+
+// theta_p *= mask: masked MADE weights are kept at exactly zero (they never influence the
+// reference's outputs either: nflows multiplies by the mask in every forward pass)
+__global__ void tr_mask_params_kernel(float* __restrict__ theta_p, const float* __restrict__ mask, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) theta_p[i] *= mask[i];
 }
 
 // ============================================================================ EVAL

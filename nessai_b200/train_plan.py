@@ -49,10 +49,17 @@ def conditioner_ops(spec: FlowSpec, ls):
     return ops, nb + 1
 
 
+def param_mask(spec: FlowSpec):
+    """``(n_params,)`` float32 multiplier for MADE flows: the position of every masked-linear
+    weight, to be filled with its mask (see :func:`fill_param_mask`); None for other flows."""
+    if spec.ftype != "maf":
+        return None
+    return [(spec.by_key[lr.weight].offset, spec.by_key[lr.mask].offset - spec.n_params, lr.n_in * lr.n_out)
+            for ls in spec.layers for lr in ls.linears]
+
+
 def build_train_plan(spec: FlowSpec, ints: dict) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Returns ``(plan int32[TR_PLAN_INTS], itab int32[...], reduce_idx int32[...])``."""
-    if spec.ftype == "maf":
-        raise TrainPlanUnsupported("fused training kernels do not cover masked autoregressive flows yet")
     if spec.ftype == "nsf" and not (2 <= spec.num_bins <= 16):
         raise TrainPlanUnsupported("fused training kernels cover spline flows with 2..16 bins")
     D, L = spec.D, spec.L
@@ -84,11 +91,13 @@ def build_train_plan(spec: FlowSpec, ints: dict) -> Tuple[np.ndarray, np.ndarray
         if ls.bn_prefix is not None:
             bn = [off(f"{ls.bn_prefix}.unconstrained_weight"), off(f"{ls.bn_prefix}.bias"),
                   boff(f"{ls.bn_prefix}.running_mean"), boff(f"{ls.bn_prefix}.running_var")]
+        # MAF: every feature is conditioner input AND transformed
+        identity = ls.transform if spec.ftype == "maf" else ls.identity
         id_off = len(itab)
-        itab.extend(int(v) for v in ls.identity)
+        itab.extend(int(v) for v in identity)
         tr_off = len(itab)
         itab.extend(int(v) for v in ls.transform)
-        d_id, d_tr = len(ls.identity), len(ls.transform)
+        d_id, d_tr = len(identity), len(ls.transform)
         ops, n_buf = conditioner_ops(spec, ls)
         if len(ops) > TR_MAXLIN or n_buf > TR_MAXBUF:
             raise TrainPlanUnsupported("conditioner too deep for the fused training kernels")
@@ -122,7 +131,7 @@ def build_train_plan(spec: FlowSpec, ints: dict) -> Tuple[np.ndarray, np.ndarray
         vals_floats = max(vals_floats, sum(buf_dim))
     head = np.zeros(16, dtype=np.int64)
     head[:16] = [
-        D, L, spec.activation, int(spec.volume_preserving),
+        D, L, spec.activation, 2 if spec.ftype == "maf" else int(spec.volume_preserving),
         spec.n_params, n_part, ws_off, max_dim,
         vals_floats, wmax, len(itab), len(reduce_idx),
         spec.num_bins if spec.ftype == "nsf" else 0,

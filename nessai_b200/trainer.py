@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .train_plan import build_train_plan
+from .train_plan import build_train_plan, param_mask
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -44,6 +44,16 @@ class FusedTrainer:
                 "nb200_trainer_create",
             )
         n = model.spec.n_params
+        segs = param_mask(model.spec)
+        if segs:
+            # MADE: masks are float buffers of the flow (theta_b)
+            tb = model.theta_b.detach().cpu().numpy()
+            pm = np.ones(n, dtype=np.float32)
+            for w_off, m_off, size in segs:
+                pm[w_off : w_off + size] = tb[m_off : m_off + size]
+            with torch.cuda.device(self.device):
+                _lib.check(lib.nb200_trainer_set_param_mask(self._handle, pm.ctypes.data_as(C.c_void_p)),
+                           "nb200_trainer_set_param_mask")
         self.m = torch.zeros(n, device=self.device, dtype=torch.float32)
         self.v = torch.zeros(n, device=self.device, dtype=torch.float32)
         self.step = 0

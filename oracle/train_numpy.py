@@ -234,21 +234,31 @@ class TrainStepOracle:
                 ld_const += np.sum(np.log(diag))
                 S.update(lo=lo, up=up, diag=diag, ud=ud, W=W)
             S["h2"] = h
-            ident, tr = h[:, ls.identity], h[:, ls.transform]
+            maf = sp.ftype == "maf"
+            ident, tr = (h, h) if maf else (h[:, ls.identity], h[:, ls.transform])
             ops, nbuf = net_ops(sp, ls)
             bufs = [None] * nbuf
             bufs[0] = ident
+            def weight(lr):
+                W = self._get(theta, lr.weight)
+                return W * self._get(theta, lr.mask) if getattr(lr, "mask", None) else W
+
             for op in ops:
                 a = bufs[op["inp"]]
                 if op["pre_act"]:
                     a = _act(act, a)
-                o = a @ self._get(theta, op["lin"].weight).T + self._get(theta, op["lin"].bias)
+                o = a @ weight(op["lin"]).T + self._get(theta, op["lin"].bias)
                 if op["res"] >= 0:
                     o = o + bufs[op["res"]]
                 bufs[op["out"]] = o
             p = bufs[-1]
             d_tr = tr.shape[1]
-            if sp.ftype == "nsf":
+            if maf:
+                # MaskedAffineAutoregressiveTransform: params (B, D, 2) = (unconstrained scale, shift)
+                s = _softplus(p[:, 0::2]) + 1e-3
+                tr2 = tr * s + p[:, 1::2]
+                ld_rows = ld_rows + np.sum(np.log(s), axis=1)
+            elif sp.ftype == "nsf":
                 s = None
                 tr2, ldf, S["spline"] = spline_forward(tr, p.reshape(B, d_tr, -1), sp.tail_bound, sp.H)
                 ld_rows = ld_rows + ldf.sum(1)
@@ -260,7 +270,8 @@ class TrainStepOracle:
                 tr2 = tr * s + p[:, :d_tr]
                 ld_rows = ld_rows + np.sum(np.log(s), axis=1)
             y = np.empty_like(h)
-            y[:, ls.identity] = ident
+            if not maf:
+                y[:, ls.identity] = ident
             y[:, ls.transform] = tr2
             S.update(ops=ops, bufs=bufs, s=s, tr=tr, y=y)
             h = y
@@ -309,11 +320,18 @@ class TrainStepOracle:
             else:
                 dy = dh
             # coupling
+            maf = sp.ftype == "maf"
             dtr2 = dy[:, ls.transform]
-            did = dy[:, ls.identity].copy()
+            did = np.zeros_like(dy) if maf else dy[:, ls.identity].copy()
             s, tr = S["s"], S["tr"]
             d_tr = tr.shape[1]
-            if sp.ftype == "nsf":
+            if maf:
+                ds = dtr2 * tr + (-c)[:, None] / s
+                dp = np.empty((B, 2 * d_tr))
+                dp[:, 0::2] = ds * _sigmoid(S["bufs"][-1][:, 0::2])
+                dp[:, 1::2] = dtr2
+                dtr = dtr2 * s
+            elif sp.ftype == "nsf":
                 dtr, dpp = spline_backward(dtr2, np.broadcast_to((-c)[:, None], dtr2.shape), S["spline"])
                 dp = dpp.reshape(B, -1)
             elif sp.volume_preserving:
@@ -333,18 +351,24 @@ class TrainStepOracle:
                 delta = gb[op["out"]]
                 a_pre = bufs[op["inp"]]
                 a = _act(act, a_pre) if op["pre_act"] else a_pre
-                gput(op["lin"].weight, delta.T @ a)
+                gW = delta.T @ a
+                if getattr(op["lin"], "mask", None):
+                    gW = gW * self._get(theta, op["lin"].mask)
+                gput(op["lin"].weight, gW)
                 gput(op["lin"].bias, delta.sum(0))
-                da = delta @ self._get(theta, op["lin"].weight)
+                da = delta @ weight(op["lin"])
                 if op["pre_act"]:
                     da = da * _dact(act, a_pre)
                 gb[op["inp"]] = gb[op["inp"]] + da
                 if op["res"] >= 0:
                     gb[op["res"]] = gb[op["res"]] + delta
             did += gb[0]
-            dh2 = np.empty_like(dy)
-            dh2[:, ls.identity] = did
-            dh2[:, ls.transform] = dtr
+            if maf:
+                dh2 = dtr + did
+            else:
+                dh2 = np.empty_like(dy)
+                dh2[:, ls.identity] = did
+                dh2[:, ls.transform] = dtr
             if ls.lu_prefix is not None:
                 lo, up, diag, ud, W = S["lo"], S["up"], S["diag"], S["ud"], S["W"]
                 gput(f"{ls.lu_prefix}.bias", dh2.sum(0))

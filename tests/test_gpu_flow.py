@@ -129,12 +129,15 @@ def test_weights_roundtrip_and_pickle(tmp_path):
     assert state.initialised is False and "model" not in state.__dict__ and "_optimiser" not in state.__dict__
 
 
-def test_training_tracks_reference_history(tmp_path):
+@pytest.mark.parametrize("name", ["c2_realnvp_mlp", "c2_realnvp_resnet", "d6_nsf", "d8_maf"])
+def test_training_tracks_reference_history(name, tmp_path):
     """Same seeds, same data, same hyper-parameters as the golden run of the
-    reference FlowModel.train: the first epochs' losses must agree."""
+    reference FlowModel.train (RealNVP with both conditioners, the spline flow and the
+    masked autoregressive flow): bit-identical initial weights, and the first epochs'
+    losses must agree."""
     from nessai_b200.flowmodel import B200FlowModel
 
-    g, cfg, sd = load_golden("c2_realnvp_mlp")
+    g, cfg, sd = load_golden(name)
     seed = 20251017
     rng = np.random.default_rng(seed)
     torch.manual_seed(seed)

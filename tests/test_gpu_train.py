@@ -13,7 +13,7 @@ from conftest import load_golden
 pytestmark = pytest.mark.gpu
 
 CASES = ["c2_realnvp_mlp", "c2_realnvp_resnet", "d5_realnvp_perm_tanh", "d4_realnvp_additive_silu", "c1_realnvp_2d",
-         "d6_nsf"]
+         "d6_nsf", "d8_maf"]
 
 
 def make_model(cfg, sd, tmp_path, **training):

@@ -140,10 +140,6 @@ def test_train_plan_packs_every_golden_realnvp():
         theta = np.zeros(spec.n_theta, dtype=np.float32)
         ints = {}
         spec.load_state_dict_numpy(sd, theta, ints)
-        if spec.ftype == "maf":
-            with pytest.raises(TrainPlanUnsupported):
-                build_train_plan(spec, ints)
-            continue
         plan, itab, red = build_train_plan(spec, ints)
         assert plan.size == TR_PLAN_INTS and plan[0] == spec.D and plan[1] == spec.L
         covered = np.zeros(spec.n_params, dtype=int)
@@ -163,4 +159,5 @@ def test_train_plan_packs_every_golden_realnvp():
             dims = row[20 : 20 + n_buf]
             assert row[15] == 2 * D + dims[1:].sum()
             assert dims[0] == row[11] and dims[-1] == row[12] * spec.coupling_multiplier
+            assert row[11] == (D if spec.ftype == "maf" else len(spec.layers[l].identity))
         assert (covered == 1).all()
