@@ -158,3 +158,13 @@ def _check_dtype_surface():
 
 
 _check_dtype_surface()
+
+
+# ------------------------------------------------------------------ importance nested sampler
+def __getattr__(name):
+    # lazily re-exported: importing the importance sampler pulls in more of nessai
+    if name in ("B200ImportanceFlowProposal", "B200ImportanceNestedSampler"):
+        from . import nessai_ins_plugin
+
+        return getattr(nessai_ins_plugin, name)
+    raise AttributeError(name)
