@@ -252,6 +252,10 @@ def run_ours(args):
         d2h += prop.samples.nbytes
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    if os.environ.get("NB200_TIMING") and rank == 0:
+        print(f"[nb200 timing] last gather (all-gather + D2H) {1e3 * getattr(eng, 'last_gather_s', float('nan')):.2f} ms; "
+              f"population_time per populate {1e3 * prop.population_time.total_seconds() / args.steps:.2f} ms; "
+              f"phases of the last populate (ms): { {k: round(1e3 * v, 3) for k, v in getattr(eng, 'last_phase_s', {}).items()} }", file=sys.stderr)
     pop_s = torch.tensor([prop.population_time.total_seconds()], device=dev)
     if world > 1:
         dist.all_reduce(pop_s, op=dist.ReduceOp.MAX)

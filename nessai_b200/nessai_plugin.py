@@ -27,7 +27,7 @@ from nessai.proposal.flowproposal import FlowProposal
 from nessai.reparameterisations import NullReparameterisation, ScaleAndShift
 
 from .flowmodel import B200FlowModel
-from .proposal import PopulateEngine, detect_uniform_box_prior
+from .proposal import IndexPool, PopulateEngine, detect_uniform_box_prior
 
 logger = logging.getLogger(__name__)
 
@@ -136,7 +136,7 @@ class B200NessaiFlowProposal(FlowProposal):
         self.samples["logL"] = self.model.batch_evaluate_log_likelihood(self.samples)
         if self.check_acceptance:
             self.acceptance.append(self.compute_acceptance(worst_point["logL"]))
-        self.indices = self.rng.permutation(self.samples.size).tolist()
+        self.indices = IndexPool(self.rng.permutation(self.samples.size))
         self.population_acceptance = n_accepted / n_proposed
         self.populated_count += 1
         self.populated = True

@@ -134,6 +134,16 @@ def gather_records(local_rows: torch.Tensor, n_local: int, n_keep: int, row_byte
         left -= k
     total = sum(take)
     if to_host and dev.type == "cuda":
+        if os.environ.get("NB200_TIMING"):
+            import sys
+            import time
+
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            host = torch.empty(total * row_bytes, dtype=torch.uint8, pin_memory=True)
+            t1 = time.perf_counter()
+            if dist.get_rank(group) == 0:
+                print(f"[nb200 timing] pinned alloc {1e3 * (t1 - t0):.2f} ms for {total * row_bytes / 1e6:.1f} MB", file=sys.stderr)
         host = torch.empty(total * row_bytes, dtype=torch.uint8, pin_memory=True)
         off = 0
         for r in range(world):
@@ -145,6 +155,39 @@ def gather_records(local_rows: torch.Tensor, n_local: int, n_keep: int, row_byte
         return host, allc
     parts = [recv[r][: take[r] * row_bytes] for r in range(world)]
     return torch.cat(parts), allc
+
+
+class IndexPool:
+    """List-like pool of sample indices (``pop`` / ``len`` / truthiness / iteration) over a
+    numpy permutation.  The reference keeps ``rng.permutation(n).tolist()``
+    (/root/reference/src/nessai/proposal/flowproposal/flowproposal.py:530) and pops from
+    its end; for a 1e6-row pool building and freeing that list of Python ints costs
+    milliseconds per populate -- more than the fused draw itself -- so the same order is
+    served from the array."""
+
+    __slots__ = ("_a", "_n")
+
+    def __init__(self, permutation):
+        self._a = np.asarray(permutation)
+        self._n = int(self._a.size)
+
+    def pop(self):
+        if self._n == 0:
+            raise IndexError("pop from empty pool")
+        self._n -= 1
+        return int(self._a[self._n])
+
+    def __len__(self):
+        return self._n
+
+    def __bool__(self):
+        return self._n > 0
+
+    def __iter__(self):
+        return iter(self._a[: self._n].tolist())
+
+    def tolist(self):
+        return self._a[: self._n].tolist()
 
 
 class PopulateEngine:
@@ -199,8 +242,13 @@ class PopulateEngine:
             self.d_counts = torch.zeros(2, dtype=torch.int64, device=dev)
 
     def configure(self, scale, shift, lo, hi, log_prior_const, r_max, sqrt_temperature=1.0):
-        f64 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64), device=self.device)  # noqa: E731
-        self.d_scale, self.d_shift, self.d_lo, self.d_hi = f64(scale), f64(shift), f64(lo), f64(hi)
+        # one H2D copy of the four float64 vectors, and only when they change (populate() calls
+        # this every time; the z-score statistics only change when the flow is retrained)
+        host = np.stack([np.asarray(a, dtype=np.float64) for a in (scale, shift, lo, hi)])
+        if getattr(self, "_cfg_host", None) is None or self._cfg_host.shape != host.shape or not np.array_equal(self._cfg_host, host):
+            dev = torch.from_numpy(host).to(self.device)
+            self.d_scale, self.d_shift, self.d_lo, self.d_hi = dev[0], dev[1], dev[2], dev[3]
+            self._cfg_host = host
         self.log_prior_const = log_prior_const
         self.r_max = float(r_max) if r_max else 0.0
         self.sqrt_t = float(sqrt_temperature)
@@ -285,12 +333,30 @@ class PopulateEngine:
         n_accepted = 0  # global
         n_local_written = 0
         local_counts = []
+        timing = bool(os.environ.get("NB200_TIMING"))
+        if timing:
+            import time
+
+            self.last_phase_s = {"draw": 0.0, "accept": 0.0, "counts": 0.0}
+
+            def tick(name, t0):
+                torch.cuda.synchronize(self.device)
+                self.last_phase_s[name] += time.perf_counter() - t0
+                return time.perf_counter()
+
         while n_accepted < n_samples:
+            if timing:
+                torch.cuda.synchronize(self.device)
+                tt = time.perf_counter()
             self.draw_turn(int(drawsize))
+            if timing:
+                tt = tick("draw", tt)
             n_proposed += int(drawsize)
             if host_prior is not None:
                 self._apply_host_prior(host_prior)
             counts = self.accept_turn(int(n_samples) - n_local_written, n_local_written)
+            if timing:
+                tt = tick("accept", tt)
             if self.world > 1:
                 import torch.distributed as dist
 
@@ -302,13 +368,23 @@ class PopulateEngine:
             else:
                 c = counts.cpu()
                 n_accepted += int(c[0])
+            if timing:
+                tt = tick("counts", tt)
             n_local_written += int(c[1])
             local_counts.append(int(c[0]))
             self._turn_rows += int(drawsize)
             if n_proposed > max_samples:
                 logger.warning("Reached max samples (%s)", max_samples)
                 break
-        rows = self._gather_rows(n_local_written, int(n_samples))
+        if os.environ.get("NB200_TIMING"):
+            import time
+
+            torch.cuda.synchronize(self.device)
+            t0 = time.perf_counter()
+            rows = self._gather_rows(n_local_written, int(n_samples))
+            self.last_gather_s = time.perf_counter() - t0
+        else:
+            rows = self._gather_rows(n_local_written, int(n_samples))
         return rows, n_proposed, n_accepted
 
     def _apply_host_prior(self, host_prior):
@@ -621,7 +697,7 @@ class B200FlowProposal:
             self.samples["logL"] = np.asarray(self.model.log_likelihood(self.samples))
         if self.check_acceptance:
             self.acceptance.append(self.compute_acceptance(worst_point["logL"]))
-        self.indices = self.rng.permutation(self.samples.size).tolist()
+        self.indices = IndexPool(self.rng.permutation(self.samples.size))
         self.population_acceptance = n_accepted / n_proposed
         self.populated_count += 1
         self.populated = True
