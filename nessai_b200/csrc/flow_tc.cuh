@@ -21,6 +21,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -110,24 +111,74 @@ inline bool tc_enabled() {
   return v == 1;
 }
 
-// ---- host: float -> bf16 (round to nearest even), split into hi + lo
-inline uint16_t tc_bf16_rn(float f) {
+// ---- 16-bit operand format of the split.  fp16 (default): hi + lo carry 11 + 11 significand
+// bits, so hi*Whi + lo*Whi + hi*Wlo is accurate to ~2^-21 -- fp32 class -- at the cost of
+// fp16's range: |value| >= 65504 cannot be represented (weights: the flow falls back to the
+// generic kernel; activations: the row comes out NaN and is dropped like any other numerical
+// failure).  -DNB200_TC_BF16 selects bf16 (8 + 8 bits, ~1e-5, fp32 range).
+#ifdef NB200_TC_BF16
+constexpr uint16_t TC_ONE16 = 0x3F80;
+constexpr uint32_t TC_IDESC_FMT = (1u << 7) | (1u << 10);  // a_format = b_format = BF16
+inline uint16_t tc_h16_rn(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
   if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;  // NaN
   u += 0x7fffu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
 }
-inline float tc_bf16_to_f(uint16_t h) {
+inline float tc_h16_to_f(uint16_t h) {
   uint32_t u = (uint32_t)h << 16;
   float f;
   memcpy(&f, &u, 4);
   return f;
 }
+inline bool tc_h16_representable(float f) { return std::isfinite(f); }
+#else
+constexpr uint16_t TC_ONE16 = 0x3C00;
+constexpr uint32_t TC_IDESC_FMT = 0u;  // a_format = b_format = F16
+inline uint16_t tc_h16_rn(float f) {  // float -> IEEE half, round to nearest even
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint16_t sign = (uint16_t)((x >> 16) & 0x8000u);
+  x &= 0x7fffffffu;
+  if (x > 0x7f800000u) return sign | 0x7e00;
+  if (x >= 0x477ff000u) return sign | 0x7c00;  // >= 65520 rounds to infinity
+  if (x < 0x38800000u) {                       // below 2^-14: subnormal half = round(f * 2^24)
+    float a;
+    memcpy(&a, &x, 4);
+    return sign | (uint16_t)lrintf(a * 16777216.0f);
+  }
+  uint32_t h = (((x >> 23) - 112u) << 10) | ((x & 0x7fffffu) >> 13);
+  const uint32_t rem = x & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
+  return sign | (uint16_t)h;
+}
+inline float tc_h16_to_f(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+  float f;
+  if (e == 0) {
+    f = (float)m * 5.9604644775390625e-8f;  // 2^-24
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u |= sign;
+    memcpy(&f, &u, 4);
+    return f;
+  }
+  const uint32_t u = sign | (e == 31 ? 0x7f800000u | (m << 13) : ((e + 112u) << 23) | (m << 13));
+  memcpy(&f, &u, 4);
+  return f;
+}
+inline bool tc_h16_representable(float f) { return std::fabs(f) < 65504.f; }
+#endif
+inline bool& tc_put_overflow() {  // set when a weight does not fit the operand format
+  static thread_local bool v = false;
+  return v;
+}
 // write element (n, k) of a K-major canonical operand with `rows` rows per chunk
 inline void tc_put(uint8_t* base_hi, uint8_t* base_lo, int rows, int n, int k, float w) {
-  const uint16_t hi = tc_bf16_rn(w);
-  const uint16_t lo = tc_bf16_rn(w - tc_bf16_to_f(hi));
+  if (!tc_h16_representable(w)) tc_put_overflow() = true;
+  const uint16_t hi = tc_h16_rn(w);
+  const uint16_t lo = tc_h16_rn(w - tc_h16_to_f(hi));
   const size_t off = (size_t)(k / 8) * rows * 16 + (size_t)n * 16 + (k % 8) * 2;
   memcpy(base_hi + off, &hi, 2);
   memcpy(base_lo + off, &lo, 2);
@@ -172,12 +223,13 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
     t.d_id[l] = c.d_id;
     t.d_tr[l] = c.d_tr;
   }
+  tc_put_overflow() = false;
   const int ones_off = L * TC_LAYER_BYTES + (L + 1) * TC_AFF_BYTES;
   const int bytes = ones_off + TC_ONES_BYTES + TC_ZERO_BYTES;
   if (((bytes + 1023) & ~1023) + 4096 > 227 * 1024) return 0;  // does not fit: generic kernel
   std::vector<uint8_t> img((size_t)bytes, 0);
   for (int m = 0; m < 128; ++m) {  // elements (m, k = 0) and (m, k = 1) are 1.0 (bf16 0x3F80)
-    const uint16_t one[2] = {0x3F80, 0x3F80};
+    const uint16_t one[2] = {TC_ONE16, TC_ONE16};
     memcpy(img.data() + ones_off + (size_t)m * 16, one, 4);
   }
   auto slot = [&](int layer, int j) {  // register slot of natural feature j; layer < 0 or >= L: natural
@@ -186,8 +238,9 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
   };
   // bias operand: (n, k = 0) = hi, (n, k = 1) = lo
   auto put_bias = [&](uint8_t* base, int n, float b) {
-    const uint16_t hi = tc_bf16_rn(b);
-    const uint16_t lo = tc_bf16_rn(b - tc_bf16_to_f(hi));
+    if (!tc_h16_representable(b)) tc_put_overflow() = true;
+    const uint16_t hi = tc_h16_rn(b);
+    const uint16_t lo = tc_h16_rn(b - tc_h16_to_f(hi));
     memcpy(base + (size_t)n * 16, &hi, 2);
     memcpy(base + (size_t)n * 16 + 2, &lo, 2);
   };
@@ -234,6 +287,7 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
         A[slot(i - 1, k) * TC_DP + slot(i, n)] = blob[f.w_off + k * f.Npad + n];
     for (int n = 0; n < D; ++n) A[TC_DP * TC_DP + slot(i, n)] = blob[f.b_off + n];
   }
+  if (tc_put_overflow()) return 0;  // a weight outside the operand format's range: generic kernel
   if (cudaMalloc(&t.d_image, bytes) != cudaSuccess) return 2;
   if (cudaMemcpy(t.d_image, img.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) return 2;
   t.image_bytes = bytes;
@@ -284,7 +338,7 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32
 }
 // kind::f16 instruction descriptor: bf16 x bf16 -> f32, both operands K-major
 __host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
+  return (1u << 4) | TC_IDESC_FMT | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc]
@@ -393,6 +447,7 @@ __device__ __forceinline__ void tc_sub2(float& d0, float& d1, float a0, float a1
 // element `a` goes to the low half-word.  RELU clamps negatives of both parts.
 template <bool RELU>
 __device__ __forceinline__ void tc_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+#ifdef NB200_TC_BF16
   if (RELU)
     asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
   else
@@ -403,6 +458,24 @@ __device__ __forceinline__ void tc_split2(float a, float b, uint32_t& hi, uint32
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
   else
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+#else
+  // hi truncated toward zero, so the remainder has the sign of the value and ReLU on both
+  // parts is ReLU on the sum
+  if (RELU)
+    asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  else
+    asm("cvt.rz.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  float ha, hb;
+  asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}"
+      : "=f"(ha), "=f"(hb)
+      : "r"(hi));
+  float ra, rb;
+  tc_sub2(ra, rb, a, b, ha, hb);
+  if (RELU)
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+  else
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+#endif
 }
 
 // raw SFU ops (no denormal / range fix-up code around them: operands here are O(1))

@@ -135,6 +135,7 @@ inline int rs_build(RsProgram& t, const FlowOp* ops, int n_ops, const float* blo
     t.d_id[l] = c.d_id;
     t.d_tr[l] = c.d_tr;
   }
+  tc_put_overflow() = false;
   const RsLayout lay = rs_layout(NB);
   const int fixed = 2 * TC_AFF_BYTES + TC_ONES_BYTES + TC_ZERO_BYTES + 4096;
   int per_pass = (227 * 1024 - fixed) / (lay.layer_bytes + TC_AFF_BYTES);
@@ -148,8 +149,9 @@ inline int rs_build(RsProgram& t, const FlowOp* ops, int n_ops, const float* blo
     return j < t.d_id[layer] ? j : TC_TR0 + (j - t.d_id[layer]);
   };
   auto put_bias = [&](uint8_t* base, int n, float b) {
-    const uint16_t hi = tc_bf16_rn(b);
-    const uint16_t lo = tc_bf16_rn(b - tc_bf16_to_f(hi));
+    if (!tc_h16_representable(b)) tc_put_overflow() = true;
+    const uint16_t hi = tc_h16_rn(b);
+    const uint16_t lo = tc_h16_rn(b - tc_h16_to_f(hi));
     memcpy(base + (size_t)n * 16, &hi, 2);
     memcpy(base + (size_t)n * 16 + 2, &lo, 2);
   };
@@ -168,7 +170,7 @@ inline int rs_build(RsProgram& t, const FlowOp* ops, int n_ops, const float* blo
     const int bytes = ones_off + TC_ONES_BYTES + TC_ZERO_BYTES;
     std::vector<uint8_t> img((size_t)bytes, 0);
     for (int m = 0; m < 128; ++m) {
-      const uint16_t one[2] = {0x3F80, 0x3F80};
+      const uint16_t one[2] = {TC_ONE16, TC_ONE16};
       memcpy(img.data() + ones_off + (size_t)m * 16, one, 4);
     }
     for (int li = 0; li < nl; ++li) {
@@ -213,6 +215,7 @@ inline int rs_build(RsProgram& t, const FlowOp* ops, int n_ops, const float* blo
     }
     float* aff = reinterpret_cast<float*>(img.data() + (size_t)nl * lay.layer_bytes);
     for (int li = 0; li < n_aff; ++li) put_affine(aff + (size_t)li * (TC_AFF_BYTES / 4), l0 + li);
+    if (tc_put_overflow()) return 0;
     RsPass& P = t.pass[p];
     if (cudaMalloc(&P.d_image, bytes) != cudaSuccess) return 2;
     if (cudaMemcpy(P.d_image, img.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) return 2;

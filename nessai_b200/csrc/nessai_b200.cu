@@ -15,6 +15,7 @@
 #include "populate_common.cuh"
 #include "flow_tc.cuh"
 #include "flow_tc_res.cuh"
+#include "flow_tc_nsf.cuh"
 #include "coupling.cuh"
 
 using namespace nb200;
@@ -60,6 +61,7 @@ struct DirProgram {
   double const_logdet = 0.0;
   TcProgram tc;  // tensor-core specialisation (valid == false when not applicable)
   RsProgram rs;  // tensor-core specialisation for the ResidualNet conditioner
+  NsProgram ns;  // tensor-core specialisation for the neural spline flow
 };
 
 struct nb200_flow {
@@ -75,6 +77,7 @@ static void free_dir(DirProgram& p) {
   delete[] p.h_ops;
   tc_free(p.tc);
   rs_free(p.rs);
+  ns_free(p.ns);
   p = DirProgram();
 }
 
@@ -145,6 +148,11 @@ extern "C" int nb200_flow_set_program(nb200_flow* f, int direction, const int32_
     if (int rc = rs_build(p.rs, p.h_ops, n_ops, h_blob, f->D, f->H, f->activation))
       return fail(rc, "rs_build failed: %s", cudaGetErrorString(cudaGetLastError()));
     p.rs.const_logdet = (float)const_logdet;
+    if (!p.rs.valid) {
+      if (int rc = ns_build(p.ns, p.h_ops, n_ops, h_blob, f->D, f->H, f->activation))
+        return fail(rc, "ns_build failed: %s", cudaGetErrorString(cudaGetLastError()));
+      p.ns.const_logdet = (float)const_logdet;
+    }
   }
   return 0;
 }
@@ -441,6 +449,13 @@ static int launch_apply(nb200_flow* f, int direction, const float* in, float* ou
     g_launches += nl;
     return 0;
   }
+  if (p.ns.valid && tc_enabled()) {
+    TcIO io{in, out, logj, lp, direction == 1 ? 1 : 2, n};
+    const int nl = ns_launch<0>(p.ns, io, PopulateArgs(), n, f->num_sms, st);
+    if (!nl) return fail(2, "tc nsf kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    g_launches += nl;
+    return 0;
+  }
   FlowProgramDev P = make_dev(f, p);
   int BS;
   size_t smem;
@@ -524,6 +539,12 @@ extern "C" int nb200_populate_draw(nb200_flow* f, int64_t n, uint64_t seed, uint
   if (p.rs.valid && tc_enabled()) {
     const int nl = rs_launch<1>(p.rs, TcIO(), A, n, f->num_sms, st);
     if (!nl) return fail(2, "tc resnet populate launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    g_launches += nl;
+    return 0;
+  }
+  if (p.ns.valid && tc_enabled()) {
+    const int nl = ns_launch<1>(p.ns, TcIO(), A, n, f->num_sms, st);
+    if (!nl) return fail(2, "tc nsf populate launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     g_launches += nl;
     return 0;
   }
