@@ -330,6 +330,8 @@ __device__ __forceinline__ float ns_spline(const float (&p)[NS_G], float x, floa
 struct NsShared {
   uint64_t bar_in[RS_NG];
   uint64_t bar_out[RS_NG];
+  uint64_t bar_cr[RS_NG][2];  // final-layer chunk ready in D2 / D (tcgen05.commit -> epilogue)
+  uint64_t bar_cf[RS_NG][2];  // ... and read out again (epilogue arrivals -> issuer)
   uint32_t tmem_base;
   uint32_t pad;
   double cst[4][NS_DP];
@@ -345,8 +347,46 @@ __device__ __forceinline__ void ns_tile_sync(int g) {
 
 // One layer pass for one row; the state is in TMEM columns NS_COL_ST.., the log|det| partial of
 // this thread is returned (c == 0 and c == 1 threads of a row each sum their own features).
+// Barriers of one tile group (shared-memory addresses) and the phase bits of this thread.
+struct NsBars {
+  uint32_t in, out, cr0, cr1, cf0, cf1;
+  uint32_t ph, pc0, pc1;
+};
+
+// Spline of feature i = 2 j + c from the chunk parameters in TMEM columns `col`; the chunk buffer
+// is handed back to the issuer as soon as the parameters are in registers.
+__device__ __forceinline__ void ns_chunk(const NsParams& P, uint32_t tg, int c, int j, uint32_t col, uint32_t bar_cr,
+                                         uint32_t& pc, uint32_t bar_cf, float& ld) {
+  rs_wait(bar_cr, pc);
+  const int i = 2 * j + c;
+  const bool mine = i < P.ly.d_tr;
+  uint32_t ra[16], rb[8], xv = 0u;
+  const uint32_t st = tg + NS_COL_ST + (mine ? P.ly.trslot[i] : 0);
+  if (mine) {
+    tc_ld16(tg + col + NS_G * c, ra);
+    ns_ld8(tg + col + NS_G * c + 16, rb);
+    xv = ns_ld1(st);
+    tc_wait_ld();
+    tc_pin16(ra);
+  }
+  if (j + 2 < P.nch) rs_arrive(bar_cf);
+  if (mine) {
+    float p[NS_G];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) p[k] = __uint_as_float(ra[k]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) p[16 + k] = __uint_as_float(rb[k]);
+    const float y = P.inverse ? ns_spline<true>(p, __uint_as_float(xv), P.tail_bound, ld)
+                              : ns_spline<false>(p, __uint_as_float(xv), P.tail_bound, ld);
+    ns_st1(st, __float_as_uint(y));
+    tc_wait_st();
+  }
+}
+
+// One layer pass for one row; the state is in TMEM columns NS_COL_ST.., the log|det| partial of
+// this thread is returned (c == 0 and c == 1 threads of a row each sum their own features).
 __device__ __forceinline__ float ns_run_layer(const NsParams& P, const NsLayout& lay, uint32_t tg, int g, int c,
-                                              uint32_t bar_in, uint32_t bar_out, uint32_t& ph) {
+                                              NsBars& B) {
   float ld = 0.f;
   {  // state slots 16c .. 16c+15 -> K chunk c of the A operand
     uint32_t r[16], hi[8], lo[8];
@@ -360,46 +400,32 @@ __device__ __forceinline__ float ns_run_layer(const NsParams& P, const NsLayout&
     tc_st8(tg + NS_COL_AL + 8 * c, lo);
     tc_wait_st();
   }
-  rs_arrive(bar_in);  // -> G0
+  rs_arrive(B.in);  // -> G0
   for (int b = 0; b < P.NB; ++b) {
-    rs_wait(bar_out, ph);
+    rs_wait(B.out, B.ph);
     rs_hidden_half<true>(tg, NS_COL_D, c);
-    rs_arrive(bar_in);
-    rs_wait(bar_out, ph);
+    rs_arrive(B.in);
+    rs_wait(B.out, B.ph);
     rs_hidden_half<true>(tg, NS_COL_D2, c);
-    rs_arrive(bar_in);
+    rs_arrive(B.in);
   }
-  rs_wait(bar_out, ph);
+  rs_wait(B.out, B.ph);
   rs_hidden_half<false>(tg, NS_COL_D, c);
-  for (int j = 0; j < P.nch; ++j) {
-    rs_arrive(bar_in);  // -> Gf chunk j: D2[0:48] = Wf_j D + bf_j
-    rs_wait(bar_out, ph);
-    const int i = 2 * j + c;
-    if (i < P.ly.d_tr) {
-      uint32_t ra[16], rb[8];
-      tc_ld16(tg + NS_COL_D2 + NS_G * c, ra);
-      ns_ld8(tg + NS_COL_D2 + NS_G * c + 16, rb);
-      const uint32_t st = tg + NS_COL_ST + P.ly.trslot[i];
-      const uint32_t xv = ns_ld1(st);
-      tc_wait_ld();
-      tc_pin16(ra);
-      float p[NS_G];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) p[k] = __uint_as_float(ra[k]);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) p[16 + k] = __uint_as_float(rb[k]);
-      const float y = P.inverse ? ns_spline<true>(p, __uint_as_float(xv), P.tail_bound, ld)
-                                : ns_spline<false>(p, __uint_as_float(xv), P.tail_bound, ld);
-      ns_st1(st, __float_as_uint(y));
-      tc_wait_st();
-    }
+  // The final layer's chunks alternate between the two accumulators (the residual stream in D is
+  // dead once its activation is the A operand), so chunk j + 1 is computed while chunk j's
+  // splines run: Gf chunk j: (D2 | D)[0:48] = Wf_j a + bf_j
+  rs_arrive(B.in);
+  for (int j = 0; j < P.nch; j += 2) {
+    ns_chunk(P, tg, c, j, NS_COL_D2, B.cr0, B.pc0, B.cf0, ld);
+    if (j + 1 < P.nch) ns_chunk(P, tg, c, j + 1, NS_COL_D, B.cr1, B.pc1, B.cf1, ld);
   }
   ns_tile_sync(g);  // the state written by the twin warp is visible before the next split
   return ld;
 }
 
 __device__ __forceinline__ void ns_issuer(const NsParams& P, const NsLayout& lay, uint32_t img_s, uint32_t tg,
-                                          uint32_t bar_in, uint32_t bar_out, int64_t my_tiles) {
+                                          const NsBars& B, int64_t my_tiles) {
+  const uint32_t bar_in = B.in, bar_out = B.out;
   constexpr uint32_t ID64 = tc_idesc(128, TC_H), ID48 = tc_idesc(128, NS_CN);
   const uint32_t d = tg + NS_COL_D, d2 = tg + NS_COL_D2, ah = tg + NS_COL_AH, al = tg + NS_COL_AL;
   const uint32_t ones_s = img_s + lay.layer_bytes;
@@ -420,7 +446,7 @@ __device__ __forceinline__ void ns_issuer(const NsParams& P, const NsLayout& lay
   const uint32_t lb = img_s;
   const uint64_t d64 = tc_desc(lb, TC_H * 16, 128);
   const uint64_t d48 = tc_desc(lb, NS_CN * 16, 128);
-  uint32_t ph = 0;
+  uint32_t ph = 0, pf0 = 0, pf1 = 0;
   for (int64_t it = 0; it < my_tiles; ++it) {
     // G0: K = 32 state slots (2 k-steps)
     tc_mbar_wait(bar_in, ph);
@@ -448,13 +474,24 @@ __device__ __forceinline__ void ns_issuer(const NsParams& P, const NsLayout& lay
              adv(d64, wb + 3 * RS_W_BIG), TC_H, ID64, 1);
       tc_commit_e(bar_out);
     }
+    tc_mbar_wait(bar_in, ph);
+    ph ^= 1;
+    tc_fence_after();
     for (int j = 0; j < P.nch; ++j) {
-      tc_mbar_wait(bar_in, ph);
-      ph ^= 1;
-      tc_fence_after();
-      gemm64(d2, bias(lb + lay.bf + j * NS_BF), adv(d48, lay.wf + j * 2 * NS_WF),
+      const bool odd = j & 1;
+      if (j >= 2) {  // the buffer's previous chunk has been read out
+        if (odd) {
+          tc_mbar_wait(B.cf1, pf1);
+          pf1 ^= 1;
+        } else {
+          tc_mbar_wait(B.cf0, pf0);
+          pf0 ^= 1;
+        }
+        tc_fence_after();
+      }
+      gemm64(odd ? d : d2, bias(lb + lay.bf + j * NS_BF), adv(d48, lay.wf + j * 2 * NS_WF),
              adv(d48, lay.wf + j * 2 * NS_WF + NS_WF), NS_CN, ID48, 0);
-      tc_commit_e(bar_out);
+      tc_commit_e(odd ? B.cr1 : B.cr0);
     }
   }
 }
@@ -483,6 +520,10 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_nsf_kernel(NsParams P, 
     for (int g = 0; g < RS_NG; ++g) {
       tc_mbar_init(tc_smem_u32(&sh->bar_in[g]), RS_EW * 32);
       tc_mbar_init(tc_smem_u32(&sh->bar_out[g]), 1);
+      for (int b = 0; b < 2; ++b) {
+        tc_mbar_init(tc_smem_u32(&sh->bar_cr[g][b]), 1);
+        tc_mbar_init(tc_smem_u32(&sh->bar_cf[g][b]), RS_EW * 32);
+      }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -504,8 +545,9 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_nsf_kernel(NsParams P, 
   if (warp < RS_NG * RS_EW) {
     const int g = warp / RS_EW, w8 = warp % RS_EW, q = w8 & 3, c = w8 >> 2;
     const uint32_t tg = tmem + g * NS_COLS + ((uint32_t)(q * 32) << 16);
-    const uint32_t bar_in = tc_smem_u32(&sh->bar_in[g]), bar_out = tc_smem_u32(&sh->bar_out[g]);
-    uint32_t ph = 0;
+    NsBars B{tc_smem_u32(&sh->bar_in[g]),    tc_smem_u32(&sh->bar_out[g]),   tc_smem_u32(&sh->bar_cr[g][0]),
+             tc_smem_u32(&sh->bar_cr[g][1]), tc_smem_u32(&sh->bar_cf[g][0]), tc_smem_u32(&sh->bar_cf[g][1]),
+             0u, 0u, 0u};
     double vmax = -INFINITY, vcount = 0.0;
     const int64_t stride = (int64_t)gridDim.x * RS_NG;
     for (int64_t tile = (int64_t)blockIdx.x * RS_NG + g; tile < ntiles; tile += stride) {
@@ -578,7 +620,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_nsf_kernel(NsParams P, 
           ns_tile_sync(g);  // LD columns are reused below
         }
       }
-      float ld = ns_run_layer(P, lay, tg, g, c, bar_in, bar_out, ph);
+      float ld = ns_run_layer(P, lay, tg, g, c, B);
       // ---- combine the two halves' log|det| and hand the row on
       ns_st1(tg + NS_COL_LD + c, __float_as_uint(ld));
       tc_wait_st();
@@ -649,8 +691,11 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_nsf_kernel(NsParams P, 
     if (MODE == 1 && P.last && c == 0) populate_publish(A, vmax, vcount);
   } else {
     const int g = __shfl_sync(0xffffffffu, warp - RS_NG * RS_EW, 0);
-    ns_issuer(P, lay, tc_smem_u32(ns_smem), __shfl_sync(0xffffffffu, tmem, 0) + g * NS_COLS,
-              tc_smem_u32(&sh->bar_in[g]), tc_smem_u32(&sh->bar_out[g]), rs_my_tiles(ntiles, g));
+    const NsBars B{tc_smem_u32(&sh->bar_in[g]),    tc_smem_u32(&sh->bar_out[g]),   tc_smem_u32(&sh->bar_cr[g][0]),
+                   tc_smem_u32(&sh->bar_cr[g][1]), tc_smem_u32(&sh->bar_cf[g][0]), tc_smem_u32(&sh->bar_cf[g][1]),
+                   0u, 0u, 0u};
+    ns_issuer(P, lay, tc_smem_u32(ns_smem), __shfl_sync(0xffffffffu, tmem, 0) + g * NS_COLS, B,
+              rs_my_tiles(ntiles, g));
     __syncwarp();
   }
   tc_fence_before();

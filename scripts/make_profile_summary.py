@@ -34,6 +34,8 @@ jobs = [
     ("prof_r1_tc_pop_v2.ncu-rep", "r1_ncu_populate_tcgen05_v2_tmemA.txt", full, "flow_tc_populate_kernel v2 (A operand in TMEM, 4 groups), 1e6 rows"),
     ("prof_r1_tc_pop_v3.ncu-rep", "r1_ncu_populate_tcgen05_v3.txt", full, "flow_tc_populate_kernel v3 (fp32 x' output, smem constants, suspended waits), 1e6 rows"),
     ("prof_r1_tc_pop_v6.ncu-rep", "r1_ncu_populate_tcgen05_v6_converged_issuer.txt", full, "flow_tc_populate_kernel v6 (converged issuer warps, affine folded into GEMM1, single bias MMA), 1e6 rows"),
+    ("prof_r1_tc_pop_v7.ncu-rep", "r1_ncu_populate_tcgen05_v7_fp16_split.txt", full, "flow_tc_populate_kernel v7 (fp16 hi/lo split operands, FFMA2 affine, bias MMA), 1e6 rows"),
+    ("prof_r1_tc_nsf_v1.ncu-rep", "r1_ncu_nsf_tcgen05_v1.txt", full, "flow_tc_nsf_kernel<0> (C3: 32-D spline flow, one layer of 6, 2e6 rows)"),
     ("prof_r1_tc_res_v1.ncu-rep", "r1_ncu_populate_tcgen05_resnet_v1.txt", full, "flow_tc_res_kernel<1> (ResidualNet conditioner, last of 2 layer passes), 1e6 rows"),
     ("prof_r1_coupling.ncu-rep", "r1_ncu_coupling_transform.txt", full, "coupling_vec_kernel<4> (affine coupling transform alone, 8e6 rows x 196 B)"),
     ("prof_r1_tc_v2.ncu-rep", "r1_ncu_apply_tcgen05_v2.txt", full, "flow_tc_apply_kernel v2 (FlowModel.inverse, z supplied), 1e6 rows"),
