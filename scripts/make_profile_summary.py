@@ -45,7 +45,7 @@ for src, dst, fn, title in jobs:
     if os.path.exists(p):
         fn(p, os.path.join(OUT, dst), title)
         print("wrote", dst)
-for j in ("bench_r1_n1.json", "bench_r1_ref.json", "bench_r1_n2.json", "r1_tc_phase_timeline.txt"):
+for j in ("bench_r1_n1.json", "bench_r1_ref.json", "bench_r1_n2.json", "bench_r1_n8.json", "r1_tc_phase_timeline.txt"):
     p = os.path.join(G, j)
     if os.path.exists(p):
         open(os.path.join(OUT, j), "w").write(open(p).read())
