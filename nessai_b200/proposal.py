@@ -218,6 +218,7 @@ class PopulateEngine:
         self.rank, self.world = _dist_info(group)
         self._cap = 0
         self._rows_cap = 0
+        self._gen = 0  # bumped whenever a device buffer is (re)allocated
         self._turn_rows = 0  # global rows drawn so far (Philox counter base)
         self.seed = None
 
@@ -231,24 +232,33 @@ class PopulateEngine:
             self.d_scratch = torch.empty(n_local // 1024 + 2, dtype=torch.int64, device=dev)
             self.d_z = None
             self._cap = n_local
+            self._gen += 1
         if want_z and (self.d_z is None or self.d_z.shape[0] < n_local):
             self.d_z = torch.empty((self._cap, self.D), dtype=torch.float32, device=dev)
+            self._gen += 1
         if capacity > self._rows_cap:
             self.d_rows = torch.empty(capacity * self.row_bytes, dtype=torch.uint8, device=dev)
             self._rows_cap = capacity
+            self._gen += 1
         if not hasattr(self, "d_stats"):
             self.d_stats = torch.empty(2, dtype=torch.float64, device=dev)
             self._stats_init = torch.tensor([-float("inf"), 0.0], dtype=torch.float64, device=dev)
             self.d_counts = torch.zeros(2, dtype=torch.int64, device=dev)
+            self._gen += 1
 
     def configure(self, scale, shift, lo, hi, log_prior_const, r_max, sqrt_temperature=1.0):
         # one H2D copy of the four float64 vectors, and only when they change (populate() calls
         # this every time; the z-score statistics only change when the flow is retrained)
-        host = np.stack([np.asarray(a, dtype=np.float64) for a in (scale, shift, lo, hi)])
-        if getattr(self, "_cfg_host", None) is None or self._cfg_host.shape != host.shape or not np.array_equal(self._cfg_host, host):
-            dev = torch.from_numpy(host).to(self.device)
+        c = getattr(self, "_cfg_host", None)
+        same = c is not None and all(
+            a is b or (np.shape(a) == b.shape and np.array_equal(a, b)) for a, b in zip((scale, shift, lo, hi), c)
+        )
+        if not same:
+            host = [np.array(a, dtype=np.float64) for a in (scale, shift, lo, hi)]
+            dev = torch.from_numpy(np.stack(host)).to(self.device)
             self.d_scale, self.d_shift, self.d_lo, self.d_hi = dev[0], dev[1], dev[2], dev[3]
             self._cfg_host = host
+            self._gen += 1
         self.log_prior_const = log_prior_const
         self.r_max = float(r_max) if r_max else 0.0
         self.sqrt_t = float(sqrt_temperature)
@@ -269,26 +279,43 @@ class PopulateEngine:
         return shard_rows(n_total, self.rank, self.world)
 
     # ------------------------------------------------------------------ turns
+    def _call(self, fn, args, what):
+        idx = self.device.index
+        if idx is None or torch.cuda.current_device() == idx:
+            rc = fn(*args)
+        else:
+            with torch.cuda.device(self.device):
+                rc = fn(*args)
+        if rc:
+            _lib.check(rc, what)
+
     def draw_turn(self, n_total: int, want_z: bool = False):
         """One fused draw of ``n_total`` global rows (this rank's shard).
         Leaves x / log_q / log_w on the device; returns ``n_local``."""
         self.model._ready()
-        n_local, start = self._shard(n_total)
-        self._ensure(max(n_local, 1), self._rows_cap, want_z)
+        key = (n_total, want_z, self._gen, self.model._handle.value, self.log_prior_const, self.r_max, self.sqrt_t)
+        if getattr(self, "_draw_key", None) != key:
+            # the argument list only changes with the buffers / configuration: build it once
+            n_local, start = self._shard(n_total)
+            self._ensure(max(n_local, 1), self._rows_cap, want_z)
+            key = key[:2] + (self._gen,) + key[3:]
+            lpc = float("nan") if self.log_prior_const is None else float(self.log_prior_const)
+            self._draw_args = [
+                self.model._handle, n_local, self._seed(), 0, self.r_max, self.sqrt_t,
+                self.d_scale.data_ptr(), self.d_shift.data_ptr(), self.d_lo.data_ptr(), self.d_hi.data_ptr(),
+                lpc, self.d_xp.data_ptr(), self.d_logq.data_ptr(), self.d_logw.data_ptr(),
+                self.d_z.data_ptr() if want_z else None, self.d_stats.data_ptr(), None,
+            ]
+            self._draw_shard = (n_local, start)
+            self._draw_key = key
+            self._draw_fn = _lib.load().nb200_populate_draw
+        n_local, start = self._draw_shard
         self.d_stats.copy_(self._stats_init, non_blocking=True)  # {max log_w = -inf, n_valid = 0}
-        lpc = float("nan") if self.log_prior_const is None else float(self.log_prior_const)
-        with torch.cuda.device(self.device):
-            _lib.check(
-                _lib.load().nb200_populate_draw(
-                    self.model._handle, n_local, C.c_uint64(self._seed()),
-                    C.c_uint64(self._turn_rows + start), self.r_max, self.sqrt_t,
-                    _ptr(self.d_scale), _ptr(self.d_shift), _ptr(self.d_lo), _ptr(self.d_hi),
-                    lpc, _ptr(self.d_xp), _ptr(self.d_logq), _ptr(self.d_logw),
-                    _ptr(self.d_z) if want_z else None, _ptr(self.d_stats), _stream(),
-                ),
-                "nb200_populate_draw",
-            )
-        self._last = (n_local, start)
+        args = self._draw_args
+        args[3] = self._turn_rows + start
+        args[16] = torch.cuda.current_stream(self.device).cuda_stream
+        self._call(self._draw_fn, args, "nb200_populate_draw")
+        self._last = self._draw_shard
         return n_local
 
     def physical_x(self, n: int) -> torch.Tensor:
@@ -303,20 +330,23 @@ class PopulateEngine:
             import torch.distributed as dist
 
             dist.all_reduce(self.d_stats[0:1], op=dist.ReduceOp.MAX, group=self.group)
-        lp = 0.0 if self.log_prior_const is None else float(self.log_prior_const)
-        with torch.cuda.device(self.device):
-            _lib.check(
-                _lib.load().nb200_populate_accept(
-                    n_local, self.D, _ptr(self.d_xp), _ptr(self.d_scale), _ptr(self.d_shift),
-                    _ptr(self.d_logw), _ptr(self.d_stats),
-                    C.c_uint64(self._seed()), C.c_uint64(self._turn_rows + start), lp,
-                    _ptr(self.d_template), self.row_bytes,
-                    self.field_offsets.ctypes.data_as(C.c_void_p), _ptr(self.d_rows),
-                    int(capacity_left), int(write_offset), _ptr(self.d_counts),
-                    _ptr(self.d_scratch), _stream(),
-                ),
-                "nb200_populate_accept",
-            )
+        key = (n_local, self._gen, self.log_prior_const)
+        if getattr(self, "_accept_key", None) != key:
+            lp = 0.0 if self.log_prior_const is None else float(self.log_prior_const)
+            self._accept_args = [
+                n_local, self.D, self.d_xp.data_ptr(), self.d_scale.data_ptr(), self.d_shift.data_ptr(),
+                self.d_logw.data_ptr(), self.d_stats.data_ptr(), self._seed(), 0, lp,
+                self.d_template.data_ptr(), self.row_bytes, self.field_offsets.ctypes.data,
+                self.d_rows.data_ptr(), 0, 0, self.d_counts.data_ptr(), self.d_scratch.data_ptr(), None,
+            ]
+            self._accept_key = key
+            self._accept_fn = _lib.load().nb200_populate_accept
+        args = self._accept_args
+        args[8] = self._turn_rows + start
+        args[14] = int(capacity_left)
+        args[15] = int(write_offset)
+        args[18] = torch.cuda.current_stream(self.device).cuda_stream
+        self._call(self._accept_fn, args, "nb200_populate_accept")
         return self.d_counts
 
     def run(self, n_samples: int, drawsize: int, max_samples: int = 1_000_000, host_prior=None):
@@ -327,13 +357,132 @@ class PopulateEngine:
         rank-major when sharded).  ``host_prior(x_struct) -> log_p`` is used
         when the prior is not a uniform box (evaluated on the host like the
         reference does, /root/reference/.../flowproposal/base.py:1032-1051).
+
+        With the prior on the device the loop is software-pipelined: the counts of
+        turn t are read through a pinned buffer and an event, and while the host waits
+        for them the draw of turn t + 1 is already running when the loop is expected
+        to go on (it goes on exactly as the reference's does -- a draw that turns out
+        not to be needed is discarded and the Philox counter is not advanced for it, so
+        the pool does not depend on the speculation).  On one GPU the accepted records
+        of turn t also cross to the host on a copy stream under the next draw.
         """
-        self._ensure(1, int(n_samples), False)
+        n_samples, drawsize = int(n_samples), int(drawsize)
+        self._ensure(1, n_samples, False)
+        timing = bool(os.environ.get("NB200_TIMING"))
+        if host_prior is not None or timing or n_samples <= 0:
+            return self._run_serial(n_samples, drawsize, max_samples, host_prior, timing)
+        dev = self.device
+        if not hasattr(self, "_h_counts"):
+            self._h_counts = torch.zeros(3, dtype=torch.int64, pin_memory=True)
+            self._h_counts_np = self._h_counts.numpy()
+            self._ev_counts = torch.cuda.Event()
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        tr = [] if os.environ.get("NB200_TRACE") else None  # host timeline of this call
+        if tr is not None:
+            import time
+
+            self.last_trace = tr
+            tr.append(("start", time.perf_counter()))
+        n_proposed = n_accepted = n_local_written = 0
+        hint = getattr(self, "_accept_hint", None)  # accepted rows per turn, last seen
+        drawn_ahead = False
+        rb = self.row_bytes
+        max_turns = int(max_samples) // drawsize + 1
+        single = self.world == 1
+        cs = self._copy_stream
+        # pinned destination of the accepted records (one GPU): sized for what the turns are
+        # expected to add; if that turns out too small the records are copied once at the end
+        host, host_cap, overflow, copied = None, 0, False, 0
+        if single and hint:
+            host_cap = min(n_samples, int(1.3 * hint * max_turns) + 4096)
+            host = torch.empty(host_cap * rb, dtype=torch.uint8, pin_memory=True)
+
+        def copy_rows(lo, hi):
+            with torch.cuda.stream(cs):
+                host[lo * rb : hi * rb].copy_(self.d_rows[lo * rb : hi * rb], non_blocking=True)
+
+        turn = 0
+        while True:
+            if not drawn_ahead:
+                self.draw_turn(drawsize)
+            drawn_ahead = False
+            n_proposed += drawsize
+            turn += 1
+            counts = self.accept_turn(n_samples - n_local_written, n_local_written)
+            self._turn_rows += drawsize
+            if single:
+                self._h_counts[:2].copy_(counts, non_blocking=True)
+            else:
+                import torch.distributed as dist
+
+                tot = counts[0:1].clone()
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
+                self._h_counts.copy_(torch.cat([counts, tot]), non_blocking=True)
+            self._ev_counts.record(main)
+            if tr is not None:
+                tr.append(("enqueued", time.perf_counter()))
+            # the records this turn is expected to add start crossing before their count is known
+            ahead_rows = 0
+            if host is not None and not overflow:
+                ahead_rows = min(hint + 4 * int(hint ** 0.5) + 64, n_samples - n_local_written,
+                                 host_cap - n_local_written)
+                if ahead_rows > 0:
+                    cs.wait_event(self._ev_counts)
+                    copy_rows(n_local_written, n_local_written + ahead_rows)
+                else:
+                    ahead_rows = 0
+            if (hint is not None and n_proposed <= max_samples
+                    and n_accepted + 2 * hint + 64 < n_samples):
+                self.draw_turn(drawsize)  # speculative: overlaps the round trip below
+                drawn_ahead = True
+            if tr is not None:
+                tr.append(("ahead", time.perf_counter()))
+            self._ev_counts.synchronize()
+            if tr is not None:
+                tr.append(("counts", time.perf_counter()))
+            c_acc, c_written = int(self._h_counts_np[0]), int(self._h_counts_np[1])
+            glob = c_acc if single else int(self._h_counts_np[2])
+            n_accepted += glob
+            hint = glob
+            if single and c_written:
+                if host is None:
+                    host_cap = max(min(n_samples, int(1.3 * c_written * (max_turns - turn + 1)) + 4096), c_written)
+                    host = torch.empty(host_cap * rb, dtype=torch.uint8, pin_memory=True)
+                if not overflow and n_local_written + c_written <= host_cap:
+                    if c_written > ahead_rows:
+                        cs.wait_event(self._ev_counts)
+                        copy_rows(n_local_written + ahead_rows, n_local_written + c_written)
+                    copied = n_local_written + c_written
+                else:
+                    overflow = True
+            n_local_written += c_written
+            if tr is not None:
+                tr.append(("copy_enqueued", time.perf_counter()))
+            if n_proposed > max_samples:
+                logger.warning("Reached max samples (%s)", max_samples)
+                break
+            if n_accepted >= n_samples:
+                break
+        self._accept_hint = hint
+        if drawn_ahead:
+            self._last = None  # a draw that was not needed: nothing of it is read
+        if host is not None:
+            self._copy_stream.synchronize()  # d_rows is free for the next populate
+        if host is not None and not overflow and copied == n_local_written:
+            rows = host[: n_local_written * self.row_bytes].numpy().view(self.row_dtype)
+        else:
+            rows = self._gather_rows(n_local_written, n_samples)
+        if tr is not None:
+            tr.append(("rows", time.perf_counter()))
+        return rows, n_proposed, n_accepted
+
+    def _run_serial(self, n_samples, drawsize, max_samples, host_prior, timing):
+        """The same loop, one synchronisation per turn and no overlap (host-side prior, or
+        NB200_TIMING phase timing)."""
         n_proposed = 0
         n_accepted = 0  # global
         n_local_written = 0
-        local_counts = []
-        timing = bool(os.environ.get("NB200_TIMING"))
         if timing:
             import time
 
@@ -371,14 +520,11 @@ class PopulateEngine:
             if timing:
                 tt = tick("counts", tt)
             n_local_written += int(c[1])
-            local_counts.append(int(c[0]))
             self._turn_rows += int(drawsize)
             if n_proposed > max_samples:
                 logger.warning("Reached max samples (%s)", max_samples)
                 break
-        if os.environ.get("NB200_TIMING"):
-            import time
-
+        if timing:
             torch.cuda.synchronize(self.device)
             t0 = time.perf_counter()
             rows = self._gather_rows(n_local_written, int(n_samples))
@@ -665,6 +811,9 @@ class B200FlowProposal:
                 self._log_prior_const = None
         lo = [self.model.bounds[n][0] for n in self.names]
         hi = [self.model.bounds[n][1] for n in self.names]
+        if getattr(self, "_bounds_cache", None) is None or self._bounds_cache[0] != (lo, hi):
+            self._bounds_cache = ((lo, hi), np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64))
+        lo, hi = self._bounds_cache[1], self._bounds_cache[2]
         t = self.latent_temperature
         self._engine.configure(
             self.scale, self.shift, lo, hi, self._log_prior_const, self.radius,
