@@ -480,6 +480,7 @@ class PopulateEngine:
     def _run_serial(self, n_samples, drawsize, max_samples, host_prior, timing):
         """The same loop, one synchronisation per turn and no overlap (host-side prior, or
         NB200_TIMING phase timing)."""
+        self._ensure(1, int(n_samples), False)
         n_proposed = 0
         n_accepted = 0  # global
         n_local_written = 0

@@ -145,6 +145,26 @@ def test_host_prior_path_matches_device_prior(tmp_path):
         np.testing.assert_allclose(p1.samples[n], p2.samples[n], rtol=0, atol=1e-12)
 
 
+def test_pipelined_loop_matches_serial_loop(tmp_path):
+    """The software-pipelined turn loop (speculative next draw, records copied ahead of their
+    count) returns exactly what the one-synchronisation-per-turn loop returns, including when the
+    speculation is wrong (a discarded draw) and when the pinned destination was sized too small."""
+    pool = 30000
+    pa, model, *_ = make_proposal("c2_realnvp_mlp", tmp_path, pool)
+    pb, *_ = make_proposal("c2_realnvp_mlp", tmp_path, pool)
+    ea, eb = pa._get_engine(), pb._get_engine()
+    ea.seed = eb.seed = 99
+    for n_samples, max_samples, hint in ((4000, 20 * pool, None), (2500, 20 * pool, 1), (10**6, 3 * pool, None),
+                                         (1800, 20 * pool, 10**5)):
+        if hint is not None:
+            ea._accept_hint = hint
+        ra, pra, aa = ea.run(n_samples, pool, max_samples=max_samples)
+        rb, prb, ab = eb._run_serial(n_samples, pool, max_samples, None, False)
+        assert (pra, aa) == (prb, ab) and ea._turn_rows == eb._turn_rows
+        assert ra.dtype == rb.dtype and len(ra) == len(rb) > 0
+        assert ra.tobytes() == rb.tobytes()
+
+
 def test_full_size_turn_properties(tmp_path):
     """BASELINE size (1e6 rows): size-independent invariants of one turn."""
     pool = 1_000_000
