@@ -282,66 +282,6 @@ __device__ __forceinline__ bool accept_row(const double* __restrict__ logw, doub
   return (lw - mx) > log(u);
 }
 
-__global__ void __launch_bounds__(ACC_THREADS)
-accept_count_kernel(const double* __restrict__ logw, const double* __restrict__ d_max, int64_t n,
-                    uint64_t seed, uint64_t row_offset, int64_t* __restrict__ scratch) {
-  __shared__ int wsum[ACC_THREADS / 32];
-  const double mx = *d_max;
-  const int64_t base = (int64_t)blockIdx.x * ACC_CHUNK + threadIdx.x * 4;
-  int c = 0;
-  for (int j = 0; j < 4; ++j) c += accept_row(logw, mx, seed, row_offset + base + j, base + j, n);
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int i = 0; i < ACC_THREADS / 32; ++i) t += wsum[i];
-    scratch[blockIdx.x] = t;
-  }
-}
-
-// exclusive scan of the chunk counts (single block)
-__global__ void __launch_bounds__(1024)
-accept_scan_kernel(int64_t* __restrict__ scratch, int64_t nchunks, int64_t capacity,
-                   int64_t* __restrict__ counts) {
-  __shared__ int64_t wsum[32];
-  __shared__ int64_t carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (int64_t base = 0; base < nchunks; base += 1024) {
-    const int64_t i = base + threadIdx.x;
-    const int64_t v = i < nchunks ? scratch[i] : 0;
-    int64_t incl = v;
-    for (int o = 1; o < 32; o <<= 1) {
-      const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
-      if ((threadIdx.x & 31) >= o) incl += t;
-    }
-    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      int64_t w = wsum[threadIdx.x];
-      int64_t wi = w;
-      for (int o = 1; o < 32; o <<= 1) {
-        const int64_t t = __shfl_up_sync(0xffffffffu, wi, o);
-        if (threadIdx.x >= o) wi += t;
-      }
-      wsum[threadIdx.x] = wi - w;  // exclusive warp offsets
-    }
-    __syncthreads();
-    const int64_t carry = carry_s;
-    const int64_t excl = carry + wsum[threadIdx.x >> 5] + incl - v;
-    if (i < nchunks) scratch[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = excl + v;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    const int64_t total = carry_s;
-    counts[0] = total;
-    counts[1] = total < capacity ? total : capacity;
-  }
-}
-
 struct RowFormat {
   int row_words;
   int D;
@@ -349,51 +289,137 @@ struct RowFormat {
   int off[256];  // byte offsets of the D parameters
 };
 
+// Chunk status word of the single-pass scan: flag (2 bits) | count (62 bits).
+constexpr unsigned long long ACC_FLAG_AGG = 1ull << 62, ACC_FLAG_INCL = 2ull << 62,
+                             ACC_VALUE_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long acc_ld(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void acc_st(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Rejection step + in-order compaction in ONE pass (flowproposal.py:492-506): a chunk of
+// ACC_CHUNK rows per block; the exclusive offset of a chunk comes from a decoupled look-back over
+// the status words of its predecessors (chunks are taken in ticket order, so a predecessor is
+// always running or done); accepted rows are written as live-point records by the whole warp
+// (one coalesced 4-byte word per lane) in draw order.  status[0 .. nchunks-1] and the ticket
+// status[nchunks] are zeroed by the launcher.
 __global__ void __launch_bounds__(ACC_THREADS)
-accept_write_kernel(const float* __restrict__ xp, const double* __restrict__ scale,
+accept_fused_kernel(const float* __restrict__ xp, const double* __restrict__ scale,
                     const double* __restrict__ shift, const double* __restrict__ logw,
-                    const double* __restrict__ d_max, int64_t n, uint64_t seed,
-                    uint64_t row_offset, const int64_t* __restrict__ scratch, double logp,
+                    const double* __restrict__ d_max, int64_t n, uint64_t seed, uint64_t row_offset,
+                    unsigned long long* __restrict__ status, int64_t nchunks, double logp,
                     const uint32_t* __restrict__ tmpl, RowFormat F, uint32_t* __restrict__ rows,
-                    int64_t capacity, int64_t write_offset) {
+                    int64_t capacity, int64_t write_offset, int64_t* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char acc_smem[];
+  double* scale_s = reinterpret_cast<double*>(acc_smem);          // [D]
+  double* shift_s = scale_s + F.D;                                 // [D]
+  uint32_t* tmpl_s = reinterpret_cast<uint32_t*>(shift_s + F.D);   // [row_words]
+  short* src_s = reinterpret_cast<short*>(tmpl_s + F.row_words);   // [row_words]: 2 d + half, or -1
   __shared__ int wsum[ACC_THREADS / 32];
+  __shared__ int64_t chunk_s, prefix_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) chunk_s = (int64_t)atomicAdd(reinterpret_cast<unsigned int*>(status + nchunks), 1u);
+  for (int w = tid; w < F.row_words; w += ACC_THREADS) {
+    tmpl_s[w] = tmpl[w];
+    src_s[w] = -1;
+  }
+  for (int d = tid; d < F.D; d += ACC_THREADS) scale_s[d] = scale[d], shift_s[d] = shift[d];
+  __syncthreads();
+  for (int d = tid; d < F.D; d += ACC_THREADS) {
+    src_s[F.off[d] / 4] = (short)(2 * d);
+    src_s[F.off[d] / 4 + 1] = (short)(2 * d + 1);
+  }
+  if (tid == 0 && F.logp_off >= 0) {
+    const unsigned long long b = __double_as_longlong(logp);
+    tmpl_s[F.logp_off / 4] = (uint32_t)b;
+    tmpl_s[F.logp_off / 4 + 1] = (uint32_t)(b >> 32);
+  }
+  const int64_t chunk = chunk_s;
   const double mx = *d_max;
-  const int64_t base = (int64_t)blockIdx.x * ACC_CHUNK + threadIdx.x * 4;
-  bool acc[4];
+  const int64_t base = chunk * ACC_CHUNK + tid * 4;
+  unsigned accbits = 0;
   int c = 0;
+#pragma unroll
   for (int j = 0; j < 4; ++j) {
-    acc[j] = accept_row(logw, mx, seed, row_offset + base + j, base + j, n);
-    c += acc[j];
+    const bool a = accept_row(logw, mx, seed, row_offset + base + j, base + j, n);
+    accbits |= (unsigned)a << j;
+    c += a;
   }
   int incl = c;
   for (int o = 1; o < 32; o <<= 1) {
     const int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if ((threadIdx.x & 31) >= o) incl += t;
+    if (lane >= o) incl += t;
   }
-  if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+  if (lane == 31) wsum[warp] = incl;
   __syncthreads();
-  int woff = 0;
-  for (int i = 0; i < (threadIdx.x >> 5); ++i) woff += wsum[i];
-  int64_t idx = scratch[blockIdx.x] + woff + incl - c;
-  for (int j = 0; j < 4; ++j) {
-    if (!acc[j]) continue;
-    if (idx < capacity) {
-      uint32_t* dst = rows + (write_offset + idx) * F.row_words;
-      for (int w = 0; w < F.row_words; ++w) dst[w] = tmpl[w];
-      const float* xr = xp + (base + j) * F.D;
-      for (int d = 0; d < F.D; ++d) {
-        // same float64 arithmetic as the bounds check of the draw kernel
-        const unsigned long long b = __double_as_longlong((double)xr[d] * scale[d] + shift[d]);
-        dst[F.off[d] / 4] = (uint32_t)b;
-        dst[F.off[d] / 4 + 1] = (uint32_t)(b >> 32);
-      }
-      if (F.logp_off >= 0) {
-        const unsigned long long b = __double_as_longlong(logp);
-        dst[F.logp_off / 4] = (uint32_t)b;
-        dst[F.logp_off / 4 + 1] = (uint32_t)(b >> 32);
+  if (warp == 0) {
+    int tot = 0;
+    for (int i = 0; i < ACC_THREADS / 32; ++i) tot += wsum[i];
+    if (lane == 0) acc_st(status + chunk, (chunk == 0 ? ACC_FLAG_INCL : ACC_FLAG_AGG) | (unsigned long long)tot);
+    // look back: lanes read the 32 predecessors below i, nearest first
+    int64_t excl = 0;
+    int64_t i = chunk - 1;
+    while (i >= 0) {
+      const int64_t idx = i - lane;
+      const unsigned long long sw = idx >= 0 ? acc_ld(status + idx) : ACC_FLAG_INCL;
+      const unsigned flag = (unsigned)(sw >> 62);
+      const unsigned m_incl = __ballot_sync(0xffffffffu, flag == 2);
+      const unsigned m_none = __ballot_sync(0xffffffffu, flag == 0);
+      const int first = m_incl ? __ffs(m_incl) - 1 : 32;          // nearest inclusive prefix
+      const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
+      if (m_none & need) continue;                                // a predecessor has not published yet
+      long long v = (lane <= first) ? (long long)(sw & ACC_VALUE_MASK) : 0ll;
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      excl += v;
+      if (m_incl) break;
+      i -= 32;
+    }
+    if (lane == 0) {
+      if (chunk > 0) acc_st(status + chunk, ACC_FLAG_INCL | (unsigned long long)(excl + tot));
+      prefix_s = excl;
+      if (chunk == nchunks - 1) {
+        const int64_t total = excl + tot;
+        counts[0] = total;
+        counts[1] = total < capacity ? total : capacity;
       }
     }
-    ++idx;
+  }
+  __syncthreads();
+  int woff = 0;
+  for (int i = 0; i < warp; ++i) woff += wsum[i];
+  const int64_t idx0 = prefix_s + woff + incl - c;  // first record of this thread
+  unsigned todo = __ballot_sync(0xffffffffu, c > 0);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const unsigned bits = __shfl_sync(0xffffffffu, accbits, src);
+    int64_t idx = __shfl_sync(0xffffffffu, idx0, src);
+    const int64_t row0 = chunk * ACC_CHUNK + (warp * 32 + src) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!((bits >> j) & 1u)) continue;
+      if (idx < capacity) {
+        uint32_t* dst = rows + (write_offset + idx) * F.row_words;
+        const float* xr = xp + (row0 + j) * F.D;
+        for (int w = lane; w < F.row_words; w += 32) {
+          const int sc = src_s[w];
+          uint32_t word = tmpl_s[w];
+          if (sc >= 0) {
+            // same float64 arithmetic as the bounds check of the draw kernel
+            const int d = sc >> 1;
+            const unsigned long long b = __double_as_longlong((double)xr[d] * scale_s[d] + shift_s[d]);
+            word = (sc & 1) ? (uint32_t)(b >> 32) : (uint32_t)b;
+          }
+          dst[w] = word;
+        }
+      }
+      ++idx;
+    }
   }
 }
 
@@ -594,14 +620,15 @@ extern "C" int nb200_populate_accept(int64_t n, int D, const float* d_xp, const 
   if (F.logp_off >= 0 && (F.logp_off % 4 || F.logp_off + 8 > row_bytes))
     return fail(1, "bad logP offset");
   const int64_t nchunks = (n + ACC_CHUNK - 1) / ACC_CHUNK;
-  accept_count_kernel<<<(unsigned)nchunks, ACC_THREADS, 0, st>>>(d_logw, d_max, n, seed,
-                                                                 row_offset, d_scratch);
-  accept_scan_kernel<<<1, 1024, 0, st>>>(d_scratch, nchunks, capacity, d_counts);
-  accept_write_kernel<<<(unsigned)nchunks, ACC_THREADS, 0, st>>>(
-      d_xp, d_scale, d_shift, d_logw, d_max, n, seed, row_offset, d_scratch, log_p_value,
-      reinterpret_cast<const uint32_t*>(d_row_template), F, reinterpret_cast<uint32_t*>(d_rows),
-      capacity, write_offset);
-  g_launches += 3;
+  const size_t smem = (size_t)D * 16 + (size_t)F.row_words * 6 + 16;
+  if (smem > 40 * 1024) return fail(1, "nb200_populate_accept: record too large (%d bytes)", row_bytes);
+  CUDA_OK(cudaMemsetAsync(d_scratch, 0, (size_t)(nchunks + 1) * sizeof(int64_t), st));
+  accept_fused_kernel<<<(unsigned)nchunks, ACC_THREADS, smem, st>>>(
+      d_xp, d_scale, d_shift, d_logw, d_max, n, seed, row_offset,
+      reinterpret_cast<unsigned long long*>(d_scratch), nchunks, log_p_value,
+      reinterpret_cast<const uint32_t*>(d_row_template), F, reinterpret_cast<uint32_t*>(d_rows), capacity,
+      write_offset, d_counts);
+  g_launches += 1;
   CUDA_OK(cudaGetLastError());
   return 0;
 }
