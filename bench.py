@@ -182,24 +182,9 @@ def run_ours(args):
     max_samples = pool
 
     def device_step():
-        """populate()'s loop, device side only."""
-        n_acc, n_prop, written = 0, 0, 0
-        while n_acc < pool:
-            eng.draw_turn(pool)
-            n_prop += pool
-            c = eng.accept_turn(pool - written, written)
-            if world > 1:
-                tot = c[0:1].clone()
-                dist.all_reduce(tot)
-                n_acc += int(tot.item())
-                c = c.cpu()
-            else:
-                c = c.cpu()
-                n_acc += int(c[0])
-            written += int(c[1])
-            eng._turn_rows += pool
-            if n_prop > max_samples:
-                break
+        """populate()'s loop, device side only: the same turn loop as the e2e call
+        (PopulateEngine.run) with the accepted records left in HBM."""
+        _, n_prop, _ = eng.run(pool, pool, max_samples=max_samples, to_host=False)
         return n_prop
 
     def barrier():

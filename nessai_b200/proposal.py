@@ -349,7 +349,8 @@ class PopulateEngine:
         self._call(self._accept_fn, args, "nb200_populate_accept")
         return self.d_counts
 
-    def run(self, n_samples: int, drawsize: int, max_samples: int = 1_000_000, host_prior=None):
+    def run(self, n_samples: int, drawsize: int, max_samples: int = 1_000_000, host_prior=None,
+            to_host: bool = True):
         """The whole ``while n_accepted < n_samples`` loop.
 
         Returns ``(rows, n_proposed, n_accepted)``; ``rows`` is a fresh
@@ -365,11 +366,13 @@ class PopulateEngine:
         not to be needed is discarded and the Philox counter is not advanced for it, so
         the pool does not depend on the speculation).  On one GPU the accepted records
         of turn t also cross to the host on a copy stream under the next draw.
+        ``to_host=False`` leaves the records in ``d_rows`` (``rows`` is then the number of
+        records written on this rank): the device side of the loop alone.
         """
         n_samples, drawsize = int(n_samples), int(drawsize)
         self._ensure(1, n_samples, False)
         timing = bool(os.environ.get("NB200_TIMING"))
-        if host_prior is not None or timing or n_samples <= 0:
+        if host_prior is not None or (timing and to_host) or n_samples <= 0:
             return self._run_serial(n_samples, drawsize, max_samples, host_prior, timing)
         dev = self.device
         if not hasattr(self, "_h_counts"):
@@ -389,7 +392,7 @@ class PopulateEngine:
         drawn_ahead = False
         rb = self.row_bytes
         max_turns = int(max_samples) // drawsize + 1
-        single = self.world == 1
+        single = self.world == 1 and to_host
         cs = self._copy_stream
         # pinned destination of the accepted records (one GPU): sized for what the turns are
         # expected to add; if that turns out too small the records are copied once at the end
@@ -411,7 +414,7 @@ class PopulateEngine:
             turn += 1
             counts = self.accept_turn(n_samples - n_local_written, n_local_written)
             self._turn_rows += drawsize
-            if single:
+            if self.world == 1:
                 self._h_counts[:2].copy_(counts, non_blocking=True)
             else:
                 import torch.distributed as dist
@@ -442,7 +445,7 @@ class PopulateEngine:
             if tr is not None:
                 tr.append(("counts", time.perf_counter()))
             c_acc, c_written = int(self._h_counts_np[0]), int(self._h_counts_np[1])
-            glob = c_acc if single else int(self._h_counts_np[2])
+            glob = c_acc if self.world == 1 else int(self._h_counts_np[2])
             n_accepted += glob
             hint = glob
             if single and c_written:
@@ -469,7 +472,9 @@ class PopulateEngine:
             self._last = None  # a draw that was not needed: nothing of it is read
         if host is not None:
             self._copy_stream.synchronize()  # d_rows is free for the next populate
-        if host is not None and not overflow and copied == n_local_written:
+        if not to_host:
+            rows = n_local_written
+        elif host is not None and not overflow and copied == n_local_written:
             rows = host[: n_local_written * self.row_bytes].numpy().view(self.row_dtype)
         else:
             rows = self._gather_rows(n_local_written, n_samples)
