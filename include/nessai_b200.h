@@ -80,12 +80,14 @@ int nb200_sample_latent(float* d_z, int64_t n, int D, uint64_t seed, uint64_t ro
  * d_logq float64[n], d_logw float64[n] (NaN for dropped rows), d_z float32[n*D]
  * or NULL, d_stats: float64[2] = {max log_w (init -inf by caller), n_valid
  * (accumulated)}.  If log_prior_const is NaN, d_logw holds -log_q and the caller
- * adds its own prior. */
+ * adds its own prior.  min_log_q: rows with log_q <= min_log_q are dropped
+ * (MinLogQTruncation.apply_after_backward, proposal/flowproposal/truncation.py:388-394);
+ * -inf or NaN keeps every row. */
 int nb200_populate_draw(nb200_flow* flow, int64_t n, uint64_t seed, uint64_t row_offset,
                         float r_max, float sqrt_temperature, const double* d_scale,
                         const double* d_shift, const double* d_lo, const double* d_hi,
-                        double log_prior_const, float* d_xp, double* d_logq, double* d_logw,
-                        float* d_z, double* d_stats, void* stream);
+                        double log_prior_const, double min_log_q, float* d_xp, double* d_logq,
+                        double* d_logw, float* d_z, double* d_stats, void* stream);
 
 /* Rejection step + compaction, flowproposal/flowproposal.py:491-498:
  * accept = (log_w - max) > log(u), u ~ U(0,1) (Philox, `seed`, counter =
@@ -95,14 +97,18 @@ int nb200_populate_draw(nb200_flow* flow, int64_t n, uint64_t seed, uint64_t row
  * h_field_offsets[0..D-1]) and logP (float64 at h_field_offsets[D], skipped if
  * negative) overwritten.  At most `capacity` records are written to d_rows;
  * d_counts: int64[2] = {n_accepted (all), n_written}.  d_max points at the
- * (possibly all-reduced) maximum of log_w.  d_scratch: int64[ceil(n/1024)+1]. */
+ * (possibly all-reduced) maximum of log_w.  d_scratch: int64[ceil(n/1024)+1].
+ * d_logl (float64[n] or NULL): per-row log-likelihood evaluated inside the loop
+ * (LikelihoodThresholdTruncation, flowproposal.py:456-460), written to the
+ * record's logL field at byte offset logl_offset (skipped if NULL / negative).
+ * One single-pass kernel: decoupled look-back scan over 1024-row chunks. */
 int nb200_populate_accept(int64_t n, int D, const float* d_xp, const double* d_scale,
-                          const double* d_shift, const double* d_logw,
+                          const double* d_shift, const double* d_logw, const double* d_logl,
                           const double* d_max, uint64_t seed, uint64_t row_offset,
                           double log_p_value, const uint8_t* d_row_template, int row_bytes,
-                          const int32_t* h_field_offsets, uint8_t* d_rows, int64_t capacity,
-                          int64_t write_offset, int64_t* d_counts, int64_t* d_scratch,
-                          void* stream);
+                          const int32_t* h_field_offsets, int logl_offset, uint8_t* d_rows,
+                          int64_t capacity, int64_t write_offset, int64_t* d_counts,
+                          int64_t* d_scratch, void* stream);
 
 /* glasflow.nflows AffineCouplingTransform._coupling_transform_forward / _inverse (the
  * element-wise stage of flows/realnvp.py:110-112 with the conditioner output supplied):

@@ -84,13 +84,13 @@ _SIGS = {
     "nb200_populate_draw": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_float, C.c_float,
-         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
     "nb200_populate_accept": (
         C.c_int,
-        [C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-         C.c_uint64, C.c_uint64, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+        [C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_uint64, C.c_uint64, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
          C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
     "nb200_coupling_transform": (

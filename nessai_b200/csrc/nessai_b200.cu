@@ -311,6 +311,7 @@ __device__ __forceinline__ void acc_st(unsigned long long* p, unsigned long long
 __global__ void __launch_bounds__(ACC_THREADS)
 accept_fused_kernel(const float* __restrict__ xp, const double* __restrict__ scale,
                     const double* __restrict__ shift, const double* __restrict__ logw,
+                    const double* __restrict__ logl, int logl_off,
                     const double* __restrict__ d_max, int64_t n, uint64_t seed, uint64_t row_offset,
                     unsigned long long* __restrict__ status, int64_t nchunks, double logp,
                     const uint32_t* __restrict__ tmpl, RowFormat F, uint32_t* __restrict__ rows,
@@ -319,7 +320,8 @@ accept_fused_kernel(const float* __restrict__ xp, const double* __restrict__ sca
   double* scale_s = reinterpret_cast<double*>(acc_smem);          // [D]
   double* shift_s = scale_s + F.D;                                 // [D]
   uint32_t* tmpl_s = reinterpret_cast<uint32_t*>(shift_s + F.D);   // [row_words]
-  short* src_s = reinterpret_cast<short*>(tmpl_s + F.row_words);   // [row_words]: 2 d + half, or -1
+  short* src_s = reinterpret_cast<short*>(tmpl_s + F.row_words);   // [row_words]: 2 d + half, -1: template,
+                                                                   // -2 / -3: low / high word of logL
   __shared__ int wsum[ACC_THREADS / 32];
   __shared__ int64_t chunk_s, prefix_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -338,6 +340,10 @@ accept_fused_kernel(const float* __restrict__ xp, const double* __restrict__ sca
     const unsigned long long b = __double_as_longlong(logp);
     tmpl_s[F.logp_off / 4] = (uint32_t)b;
     tmpl_s[F.logp_off / 4 + 1] = (uint32_t)(b >> 32);
+  }
+  if (tid == 0 && logl && logl_off >= 0) {
+    src_s[logl_off / 4] = -2;
+    src_s[logl_off / 4 + 1] = -3;
   }
   const int64_t chunk = chunk_s;
   const double mx = *d_max;
@@ -414,6 +420,9 @@ accept_fused_kernel(const float* __restrict__ xp, const double* __restrict__ sca
             const int d = sc >> 1;
             const unsigned long long b = __double_as_longlong((double)xr[d] * scale_s[d] + shift_s[d]);
             word = (sc & 1) ? (uint32_t)(b >> 32) : (uint32_t)b;
+          } else if (sc < -1) {
+            const unsigned long long b = __double_as_longlong(logl[row0 + j]);
+            word = sc == -3 ? (uint32_t)(b >> 32) : (uint32_t)b;
           }
           dst[w] = word;
         }
@@ -532,8 +541,9 @@ extern "C" int nb200_sample_latent(float* d_z, int64_t n, int D, uint64_t seed,
 extern "C" int nb200_populate_draw(nb200_flow* f, int64_t n, uint64_t seed, uint64_t row_offset,
                                    float r_max, float sqrt_temperature, const double* d_scale,
                                    const double* d_shift, const double* d_lo, const double* d_hi,
-                                   double log_prior_const, float* d_xp, double* d_logq,
-                                   double* d_logw, float* d_z, double* d_stats, void* stream) {
+                                   double log_prior_const, double min_log_q, float* d_xp,
+                                   double* d_logq, double* d_logw, float* d_z, double* d_stats,
+                                   void* stream) {
   if (!f || !d_scale || !d_shift || !d_lo || !d_hi || !d_xp || !d_logq || !d_logw || !d_stats)
     return fail(1, "nb200_populate_draw: bad arguments");
   DirProgram& p = f->dir[1];
@@ -551,6 +561,7 @@ extern "C" int nb200_populate_draw(nb200_flow* f, int64_t n, uint64_t seed, uint
   A.lo = d_lo;
   A.hi = d_hi;
   A.log_prior_const = log_prior_const;
+  A.min_log_q = isnan(min_log_q) ? -INFINITY : min_log_q;
   A.xp = d_xp;
   A.logq = d_logq;
   A.logw = d_logw;
@@ -596,11 +607,12 @@ extern "C" int nb200_populate_draw(nb200_flow* f, int64_t n, uint64_t seed, uint
 
 extern "C" int nb200_populate_accept(int64_t n, int D, const float* d_xp, const double* d_scale,
                                      const double* d_shift, const double* d_logw,
-                                     const double* d_max, uint64_t seed, uint64_t row_offset,
-                                     double log_p_value, const uint8_t* d_row_template,
-                                     int row_bytes, const int32_t* h_field_offsets,
-                                     uint8_t* d_rows, int64_t capacity, int64_t write_offset,
-                                     int64_t* d_counts, int64_t* d_scratch, void* stream) {
+                                     const double* d_logl, const double* d_max, uint64_t seed,
+                                     uint64_t row_offset, double log_p_value,
+                                     const uint8_t* d_row_template, int row_bytes,
+                                     const int32_t* h_field_offsets, int logl_offset, uint8_t* d_rows,
+                                     int64_t capacity, int64_t write_offset, int64_t* d_counts,
+                                     int64_t* d_scratch, void* stream) {
   if (!d_xp || !d_scale || !d_shift || !d_logw || !d_max || !d_row_template || !h_field_offsets || !d_rows || !d_counts ||
       !d_scratch)
     return fail(1, "nb200_populate_accept: bad arguments");
@@ -619,12 +631,14 @@ extern "C" int nb200_populate_accept(int64_t n, int D, const float* d_xp, const 
   F.logp_off = h_field_offsets[D];
   if (F.logp_off >= 0 && (F.logp_off % 4 || F.logp_off + 8 > row_bytes))
     return fail(1, "bad logP offset");
+  if (d_logl && logl_offset >= 0 && (logl_offset % 4 || logl_offset + 8 > row_bytes))
+    return fail(1, "bad logL offset");
   const int64_t nchunks = (n + ACC_CHUNK - 1) / ACC_CHUNK;
   const size_t smem = (size_t)D * 16 + (size_t)F.row_words * 6 + 16;
   if (smem > 40 * 1024) return fail(1, "nb200_populate_accept: record too large (%d bytes)", row_bytes);
   CUDA_OK(cudaMemsetAsync(d_scratch, 0, (size_t)(nchunks + 1) * sizeof(int64_t), st));
   accept_fused_kernel<<<(unsigned)nchunks, ACC_THREADS, smem, st>>>(
-      d_xp, d_scale, d_shift, d_logw, d_max, n, seed, row_offset,
+      d_xp, d_scale, d_shift, d_logw, d_logl, d_logl ? logl_offset : -1, d_max, n, seed, row_offset,
       reinterpret_cast<unsigned long long*>(d_scratch), nchunks, log_p_value,
       reinterpret_cast<const uint32_t*>(d_row_template), F, reinterpret_cast<uint32_t*>(d_rows), capacity,
       write_offset, d_counts);

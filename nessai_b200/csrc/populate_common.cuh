@@ -15,6 +15,7 @@ struct PopulateArgs {
   float r_max, sqrt_t;
   const double *scale, *shift, *lo, *hi;
   double log_prior_const;  // NaN: prior added by the caller
+  double min_log_q;        // rows with log_q <= min_log_q are dropped (-inf: keep all)
   float* xp;      // x' (flow output, before the rescale), fp32 [n, D]
   double* logq;
   double* logw;
@@ -82,7 +83,7 @@ __device__ __forceinline__ void populate_row(const PopulateArgs& A, int D, XP xp
   bool ok = alive;
   if (ok) {
     logq = (double)base_lp - (double)logj - log_const;
-    ok = isfinite(logq) && inb;
+    ok = isfinite(logq) && inb && (logq > A.min_log_q);
   }
   if (ok) {
     logw = (isnan(A.log_prior_const) ? 0.0 : A.log_prior_const) - logq;

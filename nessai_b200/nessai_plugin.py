@@ -82,19 +82,26 @@ class B200NessaiFlowProposal(FlowProposal):
             return None
         return np.asarray(scale), np.asarray(shift)
 
-    def _fused_radius(self):
-        rules = self._truncation_scheme.rules
-        if len(rules) != 1 or rules[0].name != "latent_radius":
+    def _fused_rules(self):
+        """The truncation rules as a name -> rule dict if the device loop implements all of
+        them (latent radius, minimum log q, likelihood threshold with a device likelihood),
+        else None."""
+        rules = {}
+        for rule in self._truncation_scheme.rules:
+            if rule.name in rules or rule.name not in ("latent_radius", "min_log_q", "likelihood_threshold"):
+                return None
+            rules[rule.name] = rule
+        if "likelihood_threshold" in rules and not hasattr(self.model, "log_likelihood_torch"):
             return None
-        return rules[0]
+        return rules
 
     # ---------------------------------------------------------------- populate
     def populate(self, worst_point, n_samples=10000, plot=True, r=None, max_samples=1_000_000):
         """flowproposal.py:391-534; the ``while n_accepted < n_samples`` loop runs
         on the device when eligible."""
         diag = self._diagonal_rescaling() if self.initialised else None
-        rule = self._fused_radius() if self.initialised else None
-        if diag is None or rule is None:
+        rules = self._fused_rules() if self.initialised else None
+        if diag is None or rules is None:
             logger.debug("B200: configuration not eligible for the fused loop; using the host loop")
             return super().populate(worst_point, n_samples=n_samples, plot=plot, r=r, max_samples=max_samples)
         st = datetime.datetime.now()
@@ -119,11 +126,17 @@ class B200NessaiFlowProposal(FlowProposal):
         lo = [self.model.bounds[n][0] for n in self.model.names]
         hi = [self.model.bounds[n][1] for n in self.model.names]
         t = self.latent_temperature
+        in_loop = "likelihood_threshold" in rules
         self._engine.configure(
-            diag[0], diag[1], lo, hi, self._log_prior_const, rule.threshold,
+            diag[0], diag[1], lo, hi, self._log_prior_const,
+            rules["latent_radius"].threshold if "latent_radius" in rules else 0.0,
             1.0 if t in (None, 1.0) else float(np.sqrt(t)),
+            min_log_q=rules["min_log_q"].min_log_q if "min_log_q" in rules else None,
+            likelihood=self.model.log_likelihood_torch if in_loop else None,
+            log_l_threshold=rules["likelihood_threshold"].threshold if in_loop else None,
         )
         host_prior = None if self._log_prior_const is not None else self.log_prior
+        evals0 = getattr(self._engine, "likelihood_evaluations", 0)
         rows, n_proposed, n_accepted = self._engine.run(
             int(n_samples), int(self.drawsize), max_samples=max_samples, host_prior=host_prior
         )
@@ -132,8 +145,17 @@ class B200NessaiFlowProposal(FlowProposal):
         if self._plot_pool and plot:
             self.plot_pool(self.samples)
         self.population_time += datetime.datetime.now() - st
-        logger.debug("Evaluating log-likelihoods")
-        self.samples["logL"] = self.model.batch_evaluate_log_likelihood(self.samples)
+        if in_loop:
+            self.model.likelihood_evaluations += self._engine.likelihood_evaluations - evals0
+        else:
+            logger.debug("Evaluating log-likelihoods")
+            fn = getattr(self.model, "log_likelihood_torch", None)
+            if fn is not None and self._engine.world == 1 and host_prior is None and len(rows):
+                # the accepted records are still on the device: 8 bytes per row come back
+                self.samples["logL"] = self._engine.device_log_likelihood(len(rows), fn).cpu().numpy()
+                self.model.likelihood_evaluations += len(rows)
+            else:
+                self.samples["logL"] = self.model.batch_evaluate_log_likelihood(self.samples)
         if self.check_acceptance:
             self.acceptance.append(self.compute_acceptance(worst_point["logL"]))
         self.indices = IndexPool(self.rng.permutation(self.samples.size))

@@ -211,6 +211,11 @@ class PopulateEngine:
                 raise NotImplementedError("live-point parameters must be float64")
         logp_off = self.row_dtype.fields["logP"][1] if "logP" in self.row_dtype.names else -1
         self.field_offsets = np.asarray(offs + [logp_off], dtype=np.int32)
+        self.logl_offset = (
+            int(self.row_dtype.fields["logL"][1])
+            if "logL" in self.row_dtype.names and self.row_dtype.fields["logL"][0] == np.dtype("f8")
+            else -1
+        )
         tmpl = row_template if row_template is not None else empty_structured_array(1, dtype=self.row_dtype)
         tmpl = np.ascontiguousarray(tmpl, dtype=self.row_dtype).reshape(1)
         self.d_template = torch.from_numpy(tmpl.view(np.uint8).copy()).to(self.device)
@@ -246,7 +251,13 @@ class PopulateEngine:
             self.d_counts = torch.zeros(2, dtype=torch.int64, device=dev)
             self._gen += 1
 
-    def configure(self, scale, shift, lo, hi, log_prior_const, r_max, sqrt_temperature=1.0):
+    def configure(self, scale, shift, lo, hi, log_prior_const, r_max, sqrt_temperature=1.0, min_log_q=None,
+                  likelihood=None, log_l_threshold=None):
+        """``min_log_q``: MinLogQTruncation (truncation.py:368-394).  ``likelihood``: a callable
+        ``x (n, D) float64 device tensor -> (n,) log-likelihood`` evaluated on every proposed
+        row inside the loop; with ``log_l_threshold`` rows at or below it are dropped before the
+        rejection step (LikelihoodThresholdTruncation, truncation.py:397-429) and the accepted
+        records carry their logL."""
         # one H2D copy of the four float64 vectors, and only when they change (populate() calls
         # this every time; the z-score statistics only change when the flow is retrained)
         c = getattr(self, "_cfg_host", None)
@@ -262,6 +273,9 @@ class PopulateEngine:
         self.log_prior_const = log_prior_const
         self.r_max = float(r_max) if r_max else 0.0
         self.sqrt_t = float(sqrt_temperature)
+        self.min_log_q = -float("inf") if min_log_q is None or np.isnan(min_log_q) else float(min_log_q)
+        self.likelihood = likelihood
+        self.log_l_threshold = -float("inf") if log_l_threshold is None else float(log_l_threshold)
 
     def _seed(self):
         if self.seed is None:
@@ -293,7 +307,8 @@ class PopulateEngine:
         """One fused draw of ``n_total`` global rows (this rank's shard).
         Leaves x / log_q / log_w on the device; returns ``n_local``."""
         self.model._ready()
-        key = (n_total, want_z, self._gen, self.model._handle.value, self.log_prior_const, self.r_max, self.sqrt_t)
+        key = (n_total, want_z, self._gen, self.model._handle.value, self.log_prior_const, self.r_max, self.sqrt_t,
+               self.min_log_q)
         if getattr(self, "_draw_key", None) != key:
             # the argument list only changes with the buffers / configuration: build it once
             n_local, start = self._shard(n_total)
@@ -303,7 +318,7 @@ class PopulateEngine:
             self._draw_args = [
                 self.model._handle, n_local, self._seed(), 0, self.r_max, self.sqrt_t,
                 self.d_scale.data_ptr(), self.d_shift.data_ptr(), self.d_lo.data_ptr(), self.d_hi.data_ptr(),
-                lpc, self.d_xp.data_ptr(), self.d_logq.data_ptr(), self.d_logw.data_ptr(),
+                lpc, self.min_log_q, self.d_xp.data_ptr(), self.d_logq.data_ptr(), self.d_logw.data_ptr(),
                 self.d_z.data_ptr() if want_z else None, self.d_stats.data_ptr(), None,
             ]
             self._draw_shard = (n_local, start)
@@ -313,10 +328,42 @@ class PopulateEngine:
         self.d_stats.copy_(self._stats_init, non_blocking=True)  # {max log_w = -inf, n_valid = 0}
         args = self._draw_args
         args[3] = self._turn_rows + start
-        args[16] = torch.cuda.current_stream(self.device).cuda_stream
+        args[17] = torch.cuda.current_stream(self.device).cuda_stream
         self._call(self._draw_fn, args, "nb200_populate_draw")
         self._last = self._draw_shard
+        if self.likelihood is not None:
+            self._apply_device_likelihood(n_local)
         return n_local
+
+    def device_log_likelihood(self, n_written: int, fn) -> torch.Tensor:
+        """``fn(x)`` on the accepted records still resident in ``d_rows`` (``x``: ``(n, D)``
+        float64, gathered from the records' parameter fields)."""
+        words = self.row_bytes // 4
+        rows32 = self.d_rows[: n_written * self.row_bytes].view(torch.int32).view(n_written, words)
+        if getattr(self, "_param_cols", None) is None:
+            cols = np.stack([self.field_offsets[: self.D] // 4, self.field_offsets[: self.D] // 4 + 1], axis=1)
+            self._param_cols = torch.from_numpy(cols.reshape(-1).astype(np.int64)).to(self.device)
+        x = rows32.index_select(1, self._param_cols).contiguous().view(torch.float64)
+        return torch.as_tensor(fn(x), device=self.device).to(torch.float64).reshape(n_written)
+
+    def _apply_device_likelihood(self, n: int):
+        """logL of every proposed row on the device (flowproposal.py:456-467 without the host
+        round trip); rows at or below the threshold leave the turn, and the statistics of the
+        rejection step (max log_w, valid count) are recomputed over what is left."""
+        if n <= 0:
+            return
+        self.likelihood_evaluations = getattr(self, "likelihood_evaluations", 0) + n
+        if getattr(self, "d_logl", None) is None or self.d_logl.shape[0] < self._cap:
+            self.d_logl = torch.empty(self._cap, dtype=torch.float64, device=self.device)
+            self._gen += 1
+        ll = self.likelihood(self.physical_x(n))
+        ll = torch.as_tensor(ll, device=self.device).to(torch.float64).reshape(n)
+        self.d_logl[:n] = ll
+        lw = self.d_logw[:n]
+        lw.masked_fill_(~(ll > self.log_l_threshold), float("nan"))
+        valid = ~torch.isnan(lw)
+        self.d_stats[0] = torch.where(valid, lw, torch.full_like(lw, -float("inf"))).max()
+        self.d_stats[1] = valid.sum().to(torch.float64)
 
     def physical_x(self, n: int) -> torch.Tensor:
         """x = x' * scale + shift (float64) of the last draw, on the device."""
@@ -330,22 +377,24 @@ class PopulateEngine:
             import torch.distributed as dist
 
             dist.all_reduce(self.d_stats[0:1], op=dist.ReduceOp.MAX, group=self.group)
-        key = (n_local, self._gen, self.log_prior_const)
+        with_logl = self.likelihood is not None and getattr(self, "d_logl", None) is not None and self.logl_offset >= 0
+        key = (n_local, self._gen, self.log_prior_const, with_logl)
         if getattr(self, "_accept_key", None) != key:
             lp = 0.0 if self.log_prior_const is None else float(self.log_prior_const)
             self._accept_args = [
                 n_local, self.D, self.d_xp.data_ptr(), self.d_scale.data_ptr(), self.d_shift.data_ptr(),
-                self.d_logw.data_ptr(), self.d_stats.data_ptr(), self._seed(), 0, lp,
-                self.d_template.data_ptr(), self.row_bytes, self.field_offsets.ctypes.data,
+                self.d_logw.data_ptr(), self.d_logl.data_ptr() if with_logl else None,
+                self.d_stats.data_ptr(), self._seed(), 0, lp,
+                self.d_template.data_ptr(), self.row_bytes, self.field_offsets.ctypes.data, self.logl_offset,
                 self.d_rows.data_ptr(), 0, 0, self.d_counts.data_ptr(), self.d_scratch.data_ptr(), None,
             ]
             self._accept_key = key
             self._accept_fn = _lib.load().nb200_populate_accept
         args = self._accept_args
-        args[8] = self._turn_rows + start
-        args[14] = int(capacity_left)
-        args[15] = int(write_offset)
-        args[18] = torch.cuda.current_stream(self.device).cuda_stream
+        args[9] = self._turn_rows + start
+        args[16] = int(capacity_left)
+        args[17] = int(write_offset)
+        args[20] = torch.cuda.current_stream(self.device).cuda_stream
         self._call(self._accept_fn, args, "nb200_populate_accept")
         return self.d_counts
 
@@ -602,7 +651,14 @@ class B200FlowProposal:
         volume_fraction=0.95,
         fixed_radius=None,
         device_prior="auto",
+        truncation_methods=None,
     ):
+        methods = ["latent_radius"] if truncation_methods is None else list(dict.fromkeys(truncation_methods))
+        unknown = set(methods) - {"latent_radius", "min_log_q", "likelihood_threshold"}
+        if unknown:
+            # truncation.py:431-435 (TRUNCATION_REGISTRY)
+            raise ValueError(f"Unknown truncation method(s): {sorted(unknown)}")
+        self.truncation_methods = methods
         if accumulate_weights:
             raise NotImplementedError("nessai_b200: accumulate_weights is not implemented")
         if fallback_reparameterisation not in ("zscore", "null", None):
@@ -649,6 +705,7 @@ class B200FlowProposal:
         self._checked_population = True
         self.training_data = None
         self._engine = None
+        self._min_log_q, self._loop_likelihood, self._log_l_threshold = None, None, None
         self.names = list(model.names)
         self.prime_parameters = [f"{n}_prime" if fallback_reparameterisation == "zscore" else n for n in self.names]
         self.scale = np.ones(len(self.names))
@@ -822,10 +879,30 @@ class B200FlowProposal:
         lo, hi = self._bounds_cache[1], self._bounds_cache[2]
         t = self.latent_temperature
         self._engine.configure(
-            self.scale, self.shift, lo, hi, self._log_prior_const, self.radius,
+            self.scale, self.shift, lo, hi, self._log_prior_const,
+            self.radius if "latent_radius" in self.truncation_methods else 0.0,
             1.0 if t in (None, 1.0) else float(np.sqrt(t)),
+            min_log_q=self._min_log_q, likelihood=self._loop_likelihood, log_l_threshold=self._log_l_threshold,
         )
         return self._engine
+
+    def _prepare_truncation(self, worst_point):
+        """``TruncationScheme.prepare`` for the optional rules (truncation.py:378-386,410-420)."""
+        self._min_log_q, self._loop_likelihood, self._log_l_threshold = None, None, None
+        if "min_log_q" in self.truncation_methods:
+            if self.training_data is None or not len(self.training_data):
+                raise RuntimeError("min_log_q truncation requires training_data to be set")
+            self._min_log_q = float(self.forward_pass(self.training_data)[1].min())
+        if "likelihood_threshold" in self.truncation_methods:
+            fn = getattr(self.model, "log_likelihood_torch", None)
+            if fn is None:
+                raise NotImplementedError(
+                    "nessai_b200: likelihood_threshold truncation runs inside the device loop and needs "
+                    "model.log_likelihood_torch(x: (n, D) float64 device tensor) -> (n,) tensor"
+                )
+            thr = np.asarray(worst_point["logL"], dtype=float).reshape(-1)[0] if worst_point is not None else np.nan
+            self._loop_likelihood = fn
+            self._log_l_threshold = float(thr) if np.isfinite(thr) else -np.inf
 
     def populate(self, worst_point, n_samples=10000, plot=False, r=None, max_samples=1_000_000) -> None:
         """flowproposal/flowproposal.py:391-534 with the loop body on the GPU."""
@@ -837,6 +914,7 @@ class B200FlowProposal:
         if r is not None:
             self.radius = float(r)
         self.indices = []
+        self._prepare_truncation(worst_point)
         eng = self._get_engine()
         host_prior = None if self._log_prior_const is not None else self.log_prior
         rows, n_proposed, n_accepted = eng.run(
@@ -848,8 +926,14 @@ class B200FlowProposal:
             self.samples["logP"] = self.log_prior(self.samples)
         self.n_proposed = n_proposed
         self.population_time += datetime.datetime.now() - st
-        if len(self.samples):
-            self.samples["logL"] = np.asarray(self.model.log_likelihood(self.samples))
+        if len(self.samples) and self._loop_likelihood is None:
+            # flowproposal.py:519-523; on the device when the model offers it (the accepted
+            # records are still resident, so only 8 bytes per row come back)
+            fn = getattr(self.model, "log_likelihood_torch", None)
+            if fn is not None and eng.world == 1:
+                self.samples["logL"] = eng.device_log_likelihood(len(rows), fn).cpu().numpy()
+            else:
+                self.samples["logL"] = np.asarray(self.model.log_likelihood(self.samples))
         if self.check_acceptance:
             self.acceptance.append(self.compute_acceptance(worst_point["logL"]))
         self.indices = IndexPool(self.rng.permutation(self.samples.size))
@@ -892,7 +976,7 @@ class B200FlowProposal:
         state["initialised"] = False
         state["weights_file"] = getattr(state.get("flow"), "weights_file", None)
         state["resume_populated"] = bool(state["populated"] and state["indices"])
-        for k in ("model", "flow", "_engine"):
+        for k in ("model", "flow", "_engine", "_loop_likelihood"):
             state.pop(k, None)
         return state
 

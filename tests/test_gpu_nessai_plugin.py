@@ -56,6 +56,45 @@ def test_flowsampler_runs_with_b200_proposal(tmp_path):
     assert -9.0 < fs.ns.log_evidence < -4.0
 
 
+def test_flowsampler_with_truncation_rules_on_device(tmp_path):
+    """The optional truncation rules (truncation.py:368-429) and the pool likelihood run inside
+    the fused device loop when the model offers ``log_likelihood_torch``: the reference's
+    sampler, unmodified, never evaluates the likelihood of a pool on the host."""
+    reference_or_skip()
+    import torch
+    from nessai.flowsampler import FlowSampler
+
+    from nessai_b200.nessai_plugin import B200NessaiFlowProposal
+
+    model = make_model()
+    calls = {"device_rows": 0}
+
+    def log_likelihood_torch(x):
+        calls["device_rows"] += x.shape[0]
+        return (-0.5 * x * x - 0.5 * float(np.log(2 * np.pi))).sum(dim=1)
+
+    type(model).log_likelihood_torch = staticmethod(log_likelihood_torch)
+    fs = FlowSampler(
+        model, output=str(tmp_path), resume=False, seed=4321, nlive=200, plot=False,
+        flow_proposal_class=B200NessaiFlowProposal, flow_config=dict(n_blocks=2),
+        training_config=dict(max_epochs=50, patience=10), maximum_uninformed=200,
+        max_iteration=1000, poolsize=2000, checkpointing=False,
+        truncation_methods=["latent_radius", "min_log_q", "likelihood_threshold"],
+    )
+    fs.run(plot=False, save=False)
+    prop = fs.ns._flow_proposal
+    assert [r.name for r in prop._truncation_scheme.rules] == ["latent_radius", "min_log_q", "likelihood_threshold"]
+    assert prop._engine is not None and prop.populated_count >= 1
+    assert calls["device_rows"] > 0 and prop._engine.likelihood is not None
+    assert np.isfinite(prop._engine.min_log_q)
+    # every pooled sample is above the contour it was drawn for and carries the model's logL
+    s = prop.samples
+    np.testing.assert_allclose(s["logL"], model.log_likelihood(s), rtol=1e-10)
+    assert np.all(s["logL"] > prop._truncation_scheme.rules[2].threshold)
+    # truncated at max_iteration: a loose sanity bound around the analytic -5.99
+    assert np.isfinite(fs.ns.log_evidence) and -8.0 < fs.ns.log_evidence < -4.5
+
+
 def test_plugin_matches_reference_flow_numerics(tmp_path):
     """Same weights in the reference FlowModel (CPU, shim) and B200FlowModel."""
     reference_or_skip()

@@ -165,6 +165,120 @@ def test_pipelined_loop_matches_serial_loop(tmp_path):
         assert ra.tobytes() == rb.tobytes()
 
 
+def _engine_config(prop, **kw):
+    lo = [prop.model.bounds[n][0] for n in prop.names]
+    hi = [prop.model.bounds[n][1] for n in prop.names]
+    prop._engine.configure(prop.scale, prop.shift, lo, hi, prop._log_prior_const, prop.radius, 1.0, **kw)
+
+
+def test_min_log_q_truncation(tmp_path):
+    """MinLogQTruncation (truncation.py:368-394) inside the fused turn: the same draw with
+    and without the rule differs exactly by the rows with log_q <= min_log_q."""
+    n = 20000
+    prop, model, g, cfg, sd, live = make_proposal("c2_realnvp_mlp", tmp_path, n, lo=-6.0, hi=6.0)
+    eng = prop._get_engine()
+    eng.seed = 7
+    eng.draw_turn(n)
+    lq0, lw0 = eng.d_logq[:n].cpu().numpy(), eng.d_logw[:n].cpu().numpy()
+    thr = float(np.nanmedian(lq0))
+    _engine_config(prop, min_log_q=thr)
+    eng.draw_turn(n)  # same Philox counter: _turn_rows has not advanced
+    lq1, lw1 = eng.d_logq[:n].cpu().numpy(), eng.d_logw[:n].cpu().numpy()
+    keep = ~np.isnan(lw0) & (lq0 > thr)
+    assert np.array_equal(~np.isnan(lw1), keep) and 0.3 * n < keep.sum() < 0.7 * n
+    assert np.array_equal(lw1[keep], lw0[keep]) and np.array_equal(lq1[keep], lq0[keep])
+    stats = eng.d_stats.cpu().numpy()
+    assert stats[1] == keep.sum() and stats[0] == lw0[keep].max()
+    # through the proposal: the threshold is the minimum log q of the training data
+    prop2, *_ = make_proposal("c2_realnvp_mlp", tmp_path, n, lo=-6.0, hi=6.0,
+                              truncation_methods=["latent_radius", "min_log_q"])
+    prop2.training_data = live
+    prop2.populate(live[0], n_samples=1500, max_samples=40 * n)
+    assert prop2._min_log_q == prop2.forward_pass(live)[1].min()
+    assert len(prop2.samples) == 1500
+    assert np.all(prop2.forward_pass(prop2.samples)[1] > prop2._min_log_q - 1e-4)
+    with pytest.raises(ValueError):
+        make_proposal("c2_realnvp_mlp", tmp_path, n, truncation_methods=["no_such_rule"])
+
+
+class TorchBoxGaussian(BoxGaussian):
+    """A model that also offers its likelihood on device tensors."""
+
+    def log_likelihood_torch(self, x):
+        self.device_calls = getattr(self, "device_calls", 0) + 1
+        return -0.5 * (x * x).sum(dim=1)
+
+
+def _torch_model_proposal(tmp_path, pool, **kw):
+    prop, model, g, cfg, sd, live = make_proposal("c2_realnvp_mlp", tmp_path, pool, lo=-6.0, hi=6.0, **kw)
+    tm = TorchBoxGaussian(16, -6.0, 6.0)
+    prop.model = tm
+    live["logL"] = tm.log_likelihood(live)
+    return prop, tm, live
+
+
+def test_likelihood_threshold_truncation_on_device(tmp_path):
+    """LikelihoodThresholdTruncation (truncation.py:397-429, flowproposal.py:456-467) with the
+    likelihood evaluated on the device inside the loop."""
+    from oracle.philox_numpy import accept_uniform
+
+    n = 20000
+    prop, tm, live = _torch_model_proposal(tmp_path, n, truncation_methods=["latent_radius", "likelihood_threshold"])
+    worst = live[np.argsort(live["logL"])[len(live) // 2]]  # a contour that cuts the pool
+    thr = float(worst["logL"])
+    prop._prepare_truncation(worst)
+    eng = prop._get_engine()
+    eng._ensure(n, n, False)
+    eng.seed = 21
+    eng.draw_turn(n)
+    x = eng.physical_x(n).cpu().numpy()
+    lw, ll = eng.d_logw[:n].cpu().numpy(), eng.d_logl[:n].cpu().numpy()
+    stats = eng.d_stats.cpu().numpy()
+    np.testing.assert_allclose(ll, -0.5 * (x**2).sum(1), rtol=1e-12)
+    valid = ~np.isnan(lw)
+    assert np.all(ll[valid] > thr) and 0 < valid.sum() < 0.9 * n
+    assert stats[1] == valid.sum() and stats[0] == lw[valid].max()
+    # the rule removes exactly the rows at or below the contour
+    _engine_config(prop)
+    eng.draw_turn(n)
+    lw_all = eng.d_logw[:n].cpu().numpy()
+    assert np.array_equal(valid, ~np.isnan(lw_all) & (ll > thr))
+    # rejection step over what is left, same uniforms; records carry x and logL
+    prop._get_engine()
+    eng.draw_turn(n)
+    counts = eng.accept_turn(n, 0).cpu().numpy()
+    u = accept_uniform(eng.seed, np.arange(n))
+    margin = (lw - stats[0]) - np.log(u)
+    acc = valid & (margin > 0)
+    assert not (valid & (np.abs(margin) < 1e-9)).any()
+    assert counts[0] == acc.sum()
+    rows = eng._gather_rows(int(counts[1]), n)
+    np.testing.assert_array_equal(rows["logL"], ll[acc])
+    got = np.stack([rows[nm] for nm in tm.names], axis=-1)
+    np.testing.assert_allclose(got, x[acc], rtol=1e-12, atol=1e-14)
+    # through populate(): every sample is above the contour and no host likelihood call is made
+    tm.log_likelihood = None
+    prop.populate(worst, n_samples=800, max_samples=100 * n)
+    assert len(prop.samples) == 800 and np.all(prop.samples["logL"] > thr)
+    a = np.stack([prop.samples[nm] for nm in tm.names], axis=-1)
+    np.testing.assert_allclose(prop.samples["logL"], -0.5 * (a**2).sum(1), rtol=1e-12)
+    # without a device likelihood the rule cannot run inside the device loop: say so
+    prop.model = BoxGaussian(16, -6.0, 6.0)
+    with pytest.raises(NotImplementedError):
+        prop.populate(worst, n_samples=10)
+
+
+def test_pool_likelihood_on_device(tmp_path):
+    """flowproposal.py:519-523 on the accepted records while they are still in HBM."""
+    n = 20000
+    prop, tm, live = _torch_model_proposal(tmp_path, n)
+    host_ll = tm.log_likelihood
+    tm.log_likelihood = None  # the host path must not be taken
+    prop.populate(live[0], n_samples=3000, max_samples=40 * n)
+    assert tm.device_calls == 1 and len(prop.samples) == 3000
+    np.testing.assert_allclose(prop.samples["logL"], host_ll(prop.samples), rtol=1e-12)
+
+
 def test_full_size_turn_properties(tmp_path):
     """BASELINE size (1e6 rows): size-independent invariants of one turn."""
     pool = 1_000_000
