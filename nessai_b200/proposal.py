@@ -425,7 +425,7 @@ class PopulateEngine:
             return self._run_serial(n_samples, drawsize, max_samples, host_prior, timing)
         dev = self.device
         if not hasattr(self, "_h_counts"):
-            self._h_counts = torch.zeros(3, dtype=torch.int64, pin_memory=True)
+            self._h_counts = torch.zeros(2 * max(self.world, 2), dtype=torch.int64, pin_memory=True)
             self._h_counts_np = self._h_counts.numpy()
             self._ev_counts = torch.cuda.Event()
             self._copy_stream = torch.cuda.Stream(device=dev)
@@ -443,6 +443,13 @@ class PopulateEngine:
         max_turns = int(max_samples) // drawsize + 1
         single = self.world == 1 and to_host
         cs = self._copy_stream
+        # several GPUs on one node: the pool is assembled in host memory shared by the ranks,
+        # each rank copying only its own records (hostpool.py); else all-gather at the end
+        shared = self._shared_pool(n_samples * rb) if (self.world > 1 and to_host) else None
+        if shared is not None:
+            pool_host = shared.tensors[self._pool_turn % shared.n_buffers]
+            self._pool_turn += 1
+        placed = 0  # records of all ranks placed in the shared pool so far
         # pinned destination of the accepted records (one GPU): sized for what the turns are
         # expected to add; if that turns out too small the records are copied once at the end
         host, host_cap, overflow, copied = None, 0, False, 0
@@ -468,9 +475,11 @@ class PopulateEngine:
             else:
                 import torch.distributed as dist
 
-                tot = counts[0:1].clone()
-                dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
-                self._h_counts.copy_(torch.cat([counts, tot]), non_blocking=True)
+                # every rank's {accepted, written}: the global count and this rank's offset
+                if getattr(self, "_d_allc", None) is None:
+                    self._d_allc = torch.empty(2 * self.world, dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(self._d_allc, counts, group=self.group)
+                self._h_counts[: 2 * self.world].copy_(self._d_allc, non_blocking=True)
             self._ev_counts.record(main)
             if tr is not None:
                 tr.append(("enqueued", time.perf_counter()))
@@ -493,8 +502,24 @@ class PopulateEngine:
             self._ev_counts.synchronize()
             if tr is not None:
                 tr.append(("counts", time.perf_counter()))
-            c_acc, c_written = int(self._h_counts_np[0]), int(self._h_counts_np[1])
-            glob = c_acc if self.world == 1 else int(self._h_counts_np[2])
+            if self.world == 1:
+                c_acc, c_written = int(self._h_counts_np[0]), int(self._h_counts_np[1])
+                glob = c_acc
+            else:
+                allc = self._h_counts_np[: 2 * self.world].reshape(self.world, 2)
+                c_acc, c_written = int(allc[self.rank, 0]), int(allc[self.rank, 1])
+                glob = int(allc[:, 0].sum())
+                if shared is not None:
+                    # turn-major, rank-major order; the pool keeps the first n_samples records
+                    lo = placed + int(allc[: self.rank, 1].sum())
+                    hi = min(lo + c_written, n_samples)
+                    if hi > lo:
+                        cs.wait_event(self._ev_counts)
+                        with torch.cuda.stream(cs):
+                            pool_host[lo * rb : hi * rb].copy_(
+                                self.d_rows[n_local_written * rb : (n_local_written + hi - lo) * rb],
+                                non_blocking=True)
+                    placed = min(placed + int(allc[:, 1].sum()), n_samples)
             n_accepted += glob
             hint = glob
             if single and c_written:
@@ -519,10 +544,13 @@ class PopulateEngine:
         self._accept_hint = hint
         if drawn_ahead:
             self._last = None  # a draw that was not needed: nothing of it is read
-        if host is not None:
+        if host is not None or shared is not None:
             self._copy_stream.synchronize()  # d_rows is free for the next populate
         if not to_host:
             rows = n_local_written
+        elif shared is not None:
+            shared.barrier()  # every rank's records have landed
+            rows = pool_host[: placed * rb].numpy().view(self.row_dtype)
         elif host is not None and not overflow and copied == n_local_written:
             rows = host[: n_local_written * self.row_bytes].numpy().view(self.row_dtype)
         else:
@@ -530,6 +558,28 @@ class PopulateEngine:
         if tr is not None:
             tr.append(("rows", time.perf_counter()))
         return rows, n_proposed, n_accepted
+
+    def _shared_pool(self, nbytes: int):
+        """The node-local shared host pool (hostpool.py), created collectively on first use and
+        whenever a larger one is needed; None when the ranks span several nodes, when it is
+        disabled (NB200_NO_SHM=1) or when any rank fails to map it."""
+        from .hostpool import SharedHostPool, same_node
+
+        if getattr(self, "_pool_ok", None) is None:
+            self._pool_ok = os.environ.get("NB200_NO_SHM", "0") != "1" and same_node(self.group)
+            self._pool, self._pool_turn = None, 0
+        if not self._pool_ok:
+            return None
+        if self._pool is None or self._pool.nbytes < nbytes:
+            try:  # the constructor fails on every rank or on none
+                if self._pool is not None:
+                    self._pool.close()
+                self._pool = SharedHostPool(nbytes, group=self.group)
+            except RuntimeError as e:  # pragma: no cover - depends on the host
+                logger.warning("nessai_b200: shared host pool unavailable (%s); using all-gather", e)
+                self._pool_ok, self._pool = False, None
+                return None
+        return self._pool
 
     def _run_serial(self, n_samples, drawsize, max_samples, host_prior, timing):
         """The same loop, one synchronisation per turn and no overlap (host-side prior, or

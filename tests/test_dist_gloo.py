@@ -61,6 +61,38 @@ def test_shard_and_gather_world2(tmp_path):
     assert set(res["it"].tolist()) <= {0, 1}
 
 
+def _pool_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nessai_b200.hostpool import SharedHostPool, same_node
+
+    assert same_node()
+    pool = SharedHostPool(10_000, n_buffers=2, register=False)
+    assert pool.nbytes == 12288 and len(pool.tensors) == 2
+    seen = []
+    for turn in range(3):  # buffers are used round-robin
+        buf = pool.tensors[turn % 2]
+        lo, hi = (0, 3000) if rank == 0 else (3000, 7000)
+        buf[lo:hi] = torch.full((hi - lo,), 10 * turn + rank + 1, dtype=torch.uint8)
+        pool.barrier()
+        seen.append(buf[:7000].clone())  # every rank reads the bytes of both
+        pool.barrier()  # nobody overwrites before everybody has read
+    torch.save(seen, f"{out}.{rank}")
+    dist.destroy_process_group()
+
+
+def test_shared_host_pool_world2(tmp_path):
+    """hostpool.py: one block of node-local shared memory, each rank writes its own
+    records, a host barrier, every rank sees the whole pool."""
+    out = str(tmp_path / "pool")
+    mp.spawn(_pool_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    a, b = (torch.load(f"{out}.{r}", weights_only=False) for r in range(2))
+    for turn in range(3):
+        assert torch.equal(a[turn], b[turn])
+        assert set(a[turn][:3000].tolist()) == {10 * turn + 1} and set(a[turn][3000:].tolist()) == {10 * turn + 2}
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith(f"nb200-")]  # unlinked once mapped
+
+
 def test_shard_rows_properties():
     from nessai_b200.proposal import shard_rows
 
