@@ -232,6 +232,11 @@ def run_ours(args):
     t_e2e_prop, d2h = 0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        if world > 1:
+            # align the ranks: between two populates every rank evaluates the pool's likelihood on
+            # its host, and the first collective of a populate would otherwise charge the skew of
+            # that phase to population_time (the reference's own timer, flowproposal.py:400,518)
+            dist.barrier()
         prop.populate(worst, n_samples=pool, max_samples=max_samples)
         t_e2e_prop += prop.n_proposed
         d2h += prop.samples.nbytes
@@ -273,6 +278,9 @@ def run_ours(args):
                 "turns_per_step": int(round(n_prop_total / args.steps / pool)),
                 "l2": "each turn writes 80 MB of fresh outputs; L2 (126 MB) is flushed between steps by the accept kernels and the next turn; inputs are generated in-kernel",
                 "tc_kernel": bool(os.environ.get("NB200_DISABLE_TC", "0") != "1"),
+                "e2e_note": "n_proposed / population_time of B200FlowProposal.populate (max over ranks); N>1: ranks "
+                            "aligned by a barrier before each populate, pool assembled in node-local shared pinned "
+                            "host memory, d2h_bytes_per_step = bytes of the whole pool (each rank copies its own share)",
             },
             "clocks": clk,
             "e2e": {

@@ -546,6 +546,8 @@ class PopulateEngine:
             self._last = None  # a draw that was not needed: nothing of it is read
         if host is not None or shared is not None:
             self._copy_stream.synchronize()  # d_rows is free for the next populate
+        if tr is not None:
+            tr.append(("copies_done", time.perf_counter()))
         if not to_host:
             rows = n_local_written
         elif shared is not None:

@@ -52,6 +52,10 @@ for name in ("shared", "allgather"):
     for _ in range(reps):
         p.populate(worst, n_samples=pool, max_samples=pool)
     t = p.population_time.total_seconds() / reps
+    tr = getattr(eng, "last_trace", None)
+    if tr and os.environ.get("NB200_TRACE"):
+        line = " ".join(f"{b}+{1e3 * (tb - ta):.3f}" for (a, ta), (b, tb) in zip(tr[:-1], tr[1:]))
+        print(f"[trace {name} rank {rank}] {line}", flush=True)
     eng._turn_rows = 10 * pool
     p.populate(worst, n_samples=pool, max_samples=pool)
     rows = np.stack([p.samples[n] for n in model.names] + [p.samples["logP"]], axis=1)  # plain (n, D + 1) float64
