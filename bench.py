@@ -302,9 +302,9 @@ def run_ours(args):
                 "frac": tf / peak_tf,
                 "peak_source": f"{which} bf16 sustained",
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full,
-                # profiles/r1_ncu_populate_tcgen05_v6_converged_issuer.txt): below the 80 MB the
+                # profiles/r1_ncu_populate_tcgen05_v7_fp16_split.txt): below the 80 MB the
                 # kernel writes because the tail of the output is still in the 126 MB L2 at kernel end
-                "traffic": 37.26e6,
+                "traffic": 36.85e6,
                 "kernel_ms": k_ms,
                 "rows_per_launch": n_local,
                 "hbm": {
@@ -379,8 +379,7 @@ def resnet_variant(prop, pool, dev):
     fm.model.eval()
     e0 = prop._get_engine()
     eng = PopulateEngine(fm, e0.names, e0.row_dtype)
-    eng.d_scale, eng.d_shift, eng.d_lo, eng.d_hi = e0.d_scale, e0.d_shift, e0.d_lo, e0.d_hi
-    eng.log_prior_const, eng.r_max, eng.sqrt_t = e0.log_prior_const, e0.r_max, e0.sqrt_t
+    eng.configure(*e0._cfg_host, e0.log_prior_const, e0.r_max, e0.sqrt_t)
     eng._ensure(pool, pool, False)
     for _ in range(3):
         eng.draw_turn(pool)

@@ -226,6 +226,7 @@ class PopulateEngine:
         self._gen = 0  # bumped whenever a device buffer is (re)allocated
         self._turn_rows = 0  # global rows drawn so far (Philox counter base)
         self.seed = None
+        self.min_log_q, self.likelihood, self.log_l_threshold = -float("inf"), None, -float("inf")
 
     # ---------------------------------------------------------------- buffers
     def _ensure(self, n_local: int, capacity: int, want_z: bool):
