@@ -36,6 +36,8 @@ jobs = [
     ("prof_r1_tc_pop_v6.ncu-rep", "r1_ncu_populate_tcgen05_v6_converged_issuer.txt", full, "flow_tc_populate_kernel v6 (converged issuer warps, affine folded into GEMM1, single bias MMA), 1e6 rows"),
     ("prof_r1_tc_pop_v7.ncu-rep", "r1_ncu_populate_tcgen05_v7_fp16_split.txt", full, "flow_tc_populate_kernel v7 (fp16 hi/lo split operands, FFMA2 affine, bias MMA), 1e6 rows"),
     ("prof_r1_tc_nsf_v1.ncu-rep", "r1_ncu_nsf_tcgen05_v1.txt", full, "flow_tc_nsf_kernel<0> (C3: 32-D spline flow, one layer of 6, 2e6 rows)"),
+    ("prof_r1_tc_nsf_v2.ncu-rep", "r1_ncu_nsf_tcgen05_v2_double_buffered_chunks.txt", full, "flow_tc_nsf_kernel<0> v2 (final-layer chunks double-buffered across D2 / D), one layer of 6, 2e6 rows"),
+    ("prof_r1_accept_fused.ncu-rep", "r1_ncu_accept_fused.txt", full, "accept_fused_kernel (rejection step + in-order compaction, single pass), 1e6 rows"),
     ("prof_r1_tc_res_v1.ncu-rep", "r1_ncu_populate_tcgen05_resnet_v1.txt", full, "flow_tc_res_kernel<1> (ResidualNet conditioner, last of 2 layer passes), 1e6 rows"),
     ("prof_r1_coupling.ncu-rep", "r1_ncu_coupling_transform.txt", full, "coupling_vec_kernel<4> (affine coupling transform alone, 8e6 rows x 196 B)"),
     ("prof_r1_tc_v2.ncu-rep", "r1_ncu_apply_tcgen05_v2.txt", full, "flow_tc_apply_kernel v2 (FlowModel.inverse, z supplied), 1e6 rows"),
@@ -45,7 +47,8 @@ for src, dst, fn, title in jobs:
     if os.path.exists(p):
         fn(p, os.path.join(OUT, dst), title)
         print("wrote", dst)
-for j in ("bench_r1_n1.json", "bench_r1_ref.json", "bench_r1_n2.json", "bench_r1_n8.json", "r1_tc_phase_timeline.txt"):
+for j in ("bench_r1_n1.json", "bench_r1_ref.json", "bench_r1_n2.json", "bench_r1_n4.json", "bench_r1_n8.json",
+          "r1_tc_phase_timeline.txt"):
     p = os.path.join(G, j)
     if os.path.exists(p):
         open(os.path.join(OUT, j), "w").write(open(p).read())
