@@ -24,12 +24,68 @@ import numpy as np
 from nessai import config as nessai_config
 from nessai.livepoint import empty_structured_array as nessai_empty_structured_array
 from nessai.proposal.flowproposal import FlowProposal
-from nessai.reparameterisations import NullReparameterisation, ScaleAndShift
+from nessai.reparameterisations import NullReparameterisation, RescaleToBounds, ScaleAndShift
 
 from .flowmodel import B200FlowModel
 from .proposal import IndexPool, PopulateEngine, detect_uniform_box_prior
 
 logger = logging.getLogger(__name__)
+
+
+
+def diagonal_rescaling(rep, prime_parameters, model_names):
+    """``(scale, shift)`` with ``x = x' * scale + shift`` per parameter (model order) when the
+    combined reparameterisation ``rep`` (reparameterisations/combined.py:154-192) is a diagonal
+    affine map, else ``None``.  A diagonal affine is what the fused populate tail evaluates
+    (float64): ``log|J| = sum log|scale|``.  Recognised:
+
+    * ``NullReparameterisation`` (reparameterisations/null.py): identity;
+    * ``ScaleAndShift`` / ``Rescale`` (rescale.py:233-291) without pre-/post-rescaling:
+      ``x = x' * scale + shift``;
+    * ``RescaleToBounds`` (rescale.py:321-731) without boundary inversion and without pre-/post-
+      rescaling functions: ``x = (hi - lo) * (x' - r0) / (r1 - r0) + lo + offset`` with
+      ``[lo, hi]`` the current (possibly data-updated) bounds, ``[r0, r1]`` the rescale bounds
+      (rescale.py:533-543,669-680), i.e. ``scale = (hi - lo) / (r1 - r0)``,
+      ``shift = lo + offset - scale * r0``.
+
+    Anything else (logit / log post-rescaling, boundary inversion, angles, user classes) is not
+    a diagonal affine and keeps the reference's host loop."""
+    if rep is None:
+        return None
+    if list(prime_parameters) != [p for r in rep.values() for p in r.output_parameters]:
+        return None
+    scale, shift, names = [], [], []
+    for r in rep.values():
+        if isinstance(r, ScaleAndShift):
+            if r.has_pre_rescaling or r.has_post_rescaling or not r.one_to_one:
+                return None
+            for p in r.parameters:
+                scale.append(float(r.scale[p]))
+                shift.append(float(r.shift[p]) if r.shift else 0.0)
+                names.append(p)
+        elif isinstance(r, NullReparameterisation):
+            for p in r.parameters:
+                scale.append(1.0)
+                shift.append(0.0)
+                names.append(p)
+        elif type(r) is RescaleToBounds:
+            # subclasses may override the rescaling hooks: only the stock class is recognised
+            if r.boundary_inversion or r.has_pre_rescaling or r.has_post_rescaling or not r.one_to_one:
+                return None
+            for p in r.parameters:
+                lo, hi = (float(b) for b in r.bounds[p])
+                s = (hi - lo) / float(r._rescale_factor[p])
+                scale.append(s)
+                shift.append(lo + float(r.offsets[p]) - s * float(r._rescale_shift[p]))
+                names.append(p)
+        else:
+            return None
+    if names != list(model_names):
+        return None
+    scale, shift = np.asarray(scale, dtype=np.float64), np.asarray(shift, dtype=np.float64)
+    if not (np.all(np.isfinite(scale)) and np.all(np.isfinite(shift)) and np.all(scale != 0.0)):
+        return None
+    return scale, shift
 
 
 class B200NessaiFlowProposal(FlowProposal):
@@ -55,32 +111,7 @@ class B200NessaiFlowProposal(FlowProposal):
         affine handled on the device, else None."""
         if self.map_to_unit_hypercube or self.accumulate_weights:
             return None
-        rep = self._reparameterisation
-        if rep is None:
-            return None
-        if list(self.prime_parameters) != [
-            p for r in rep.values() for p in r.output_parameters
-        ]:
-            return None
-        scale, shift, names = [], [], []
-        for r in rep.values():
-            if isinstance(r, ScaleAndShift):
-                if r.has_pre_rescaling or r.has_post_rescaling or not r.one_to_one:
-                    return None
-                for p in r.parameters:
-                    scale.append(float(r.scale[p]))
-                    shift.append(float(r.shift[p]) if r.shift else 0.0)
-                    names.append(p)
-            elif isinstance(r, NullReparameterisation):
-                for p in r.parameters:
-                    scale.append(1.0)
-                    shift.append(0.0)
-                    names.append(p)
-            else:
-                return None
-        if names != list(self.model.names):
-            return None
-        return np.asarray(scale), np.asarray(shift)
+        return diagonal_rescaling(self._reparameterisation, self.prime_parameters, self.model.names)
 
     def _fused_rules(self):
         """The truncation rules as a name -> rule dict if the device loop implements all of

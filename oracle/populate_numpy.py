@@ -15,7 +15,12 @@ What is restated (reference file:line):
   (truncation.py:422-429) -> ``log_w = log_prior - log_q`` (base.py:1069-1098);
 * the rejection step, flowproposal.py:491-502: ``log_w -= max``, ``accept = log_w > log u``
   (``u`` supplied), the first ``n_samples - n_accepted`` accepted rows kept in draw order;
-* the loop and its stop conditions, flowproposal.py:431,436-439,496-502.
+* the loop and its stop conditions, flowproposal.py:431,436-439,496-502;
+* the ``accumulate_weights`` variant of the loop and of the rejection step,
+  flowproposal.py:414-417,471-490,504-512: every turn's surviving rows and weights are kept,
+  ``log_constant`` is the running maximum, the expected pool size is
+  ``exp(logsumexp(log_weights - log_constant))`` and the rejection step runs over ALL rows so
+  far (fresh uniforms each time) only once that reaches ``n_samples``.
 
 Pinned by ``tests/test_populate_oracle.py`` against the reference's own ``populate`` run on
 the CPU with its latent draws and uniforms recorded.
@@ -89,3 +94,44 @@ def populate_loop(flow, draw_z, draw_u, n_samples, drawsize, max_samples=1_000_0
             break
     x = np.concatenate(out) if out else np.empty((0, 0))
     return x, n_proposed, n_accepted
+
+
+def populate_loop_accumulate(flow, draw_z, draw_u, n_samples, drawsize, max_samples=1_000_000, **turn_kwargs):
+    """flowproposal.py:414-417,431-490,504-512 (``accumulate_weights=True``).  ``draw_u(m)`` is
+    called exactly where the reference calls ``rng.random(len(log_weights))``: with ``m`` = the
+    number of valid rows accumulated so far, every time the expected pool size reaches
+    ``n_samples``, and once more after the loop if the last rejection step is stale.  Returns
+    ``(x_accepted[: n_samples], n_proposed, n_accepted, log_n_expected)``."""
+    xs, lws = [], []
+    log_constant, log_n_expected = -np.inf, -np.inf
+    n_proposed, n_accepted, accept = 0, 0, None
+    log_n = np.log(n_samples)
+    total = 0
+    while n_accepted < n_samples:
+        t = populate_turn(flow, draw_z(drawsize), **turn_kwargs)
+        n_proposed += drawsize
+        v = t["valid"]
+        if not v.any():  # flowproposal.py:436-439,449-453: nothing survived the truncations
+            if n_proposed > max_samples:
+                break
+            continue
+        xs.append(t["x"][v])
+        lws.append(t["log_w"][v])
+        total += int(v.sum())
+        log_constant = max(float(np.max(t["log_w"][v])), log_constant)
+        lw = np.concatenate(lws)
+        d = lw - log_constant
+        log_n_expected = float(np.log(np.sum(np.exp(d))))  # scipy logsumexp of values <= 0
+        if log_n_expected >= log_n:
+            accept = (lw - log_constant) > np.log(draw_u(total))
+            n_accepted = int(accept.sum())
+        if n_proposed > max_samples:
+            break
+    if not xs:
+        return np.empty((0, 0)), n_proposed, 0, log_n_expected
+    lw = np.concatenate(lws)
+    if accept is None or len(accept) != total:
+        accept = (lw - log_constant) > np.log(draw_u(total))
+    n_accepted = int(accept.sum())
+    x = np.concatenate(xs)[accept][:n_samples]
+    return x, n_proposed, n_accepted, log_n_expected

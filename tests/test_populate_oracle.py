@@ -148,3 +148,44 @@ def test_oracle_turn_and_loop_match_reference_populate(tmp_path, rules):
         assert next(zi, None) is None  # the oracle loop stopped exactly where the reference did
     if "likelihood_threshold" in scheme:
         assert np.all(prop.samples["logL"] > scheme["likelihood_threshold"].threshold)
+
+
+def test_oracle_accumulate_loop_matches_reference_populate(tmp_path):
+    """``accumulate_weights=True`` (flowproposal.py:471-490,504-512): the oracle loop, fed the
+    reference's recorded latent draws and uniform blocks, consumes them at the same points,
+    stops on the same turn and keeps the same pool."""
+    reference_or_skip()
+    from oracle.flow_numpy import NumpyFlow
+    from oracle.populate_numpy import populate_loop_accumulate
+
+    drawsize, n_samples = 4000, 300
+    prop, model, live, sd, cfg, zs, rng = reference_proposal(tmp_path, drawsize, accumulate_weights=True)
+    D = cfg["n_inputs"]
+    worst = live[np.argsort(live["logL"])[len(live) // 3]]
+    prop.training_data = live
+    n_blocks0 = len(rng.blocks)
+    prop.populate(worst, n_samples=n_samples, plot=False, max_samples=40 * drawsize)
+    us = rng.blocks[n_blocks0:]
+    assert len(zs) >= 2 and 1 <= len(us) <= len(zs)
+    scale, shift = diagonal_rescale(prop, D)
+    nf = NumpyFlow(sd, ftype="realnvp", net="mlp", hidden_features=cfg["n_neurons"])
+    scheme = {r.name: r for r in prop._truncation_scheme.rules}
+    zi, ui = iter(zs), iter(us)
+
+    def draw_u(m):
+        u = next(ui)
+        assert len(u) == m  # one uniform per accumulated surviving row, as the reference drew
+        return u
+
+    x, n_proposed, n_accepted, log_n_expected = populate_loop_accumulate(
+        nf, lambda n: next(zi), draw_u, n_samples, drawsize, max_samples=40 * drawsize,
+        scale=scale, shift=shift, lo=-4.0, hi=4.0, log_prior_const=-D * np.log(8.0),
+        r_max=scheme["latent_radius"].threshold)
+    assert next(zi, None) is None and next(ui, None) is None  # same number of turns and of rejection steps
+    assert n_proposed == len(zs) * drawsize
+    ref = np.stack([prop.samples[n] for n in model.names], axis=-1)
+    # the reference's flow is fp32: a row whose margin is at rounding level may flip
+    assert abs(len(x) - len(ref)) <= 1 and abs(n_accepted / n_proposed - prop.population_acceptance) <= 1 / n_proposed
+    if len(x) == len(ref):
+        np.testing.assert_allclose(x, ref, rtol=1e-4, atol=1e-4)
+    assert log_n_expected >= np.log(n_samples)
