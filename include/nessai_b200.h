@@ -110,6 +110,43 @@ int nb200_populate_accept(int64_t n, int D, const float* d_xp, const double* d_s
                           int64_t capacity, int64_t write_offset, int64_t* d_counts,
                           int64_t* d_scratch, void* stream);
 
+/* The same rejection step + compaction for a reparameterisation that is not a diagonal
+ * affine: the physical rows x (float64[n*D]) were formed by nb200_reparam_tail and are copied
+ * into the records as they are.  Everything else as nb200_populate_accept. */
+int nb200_populate_accept_x64(int64_t n, int D, const double* d_x64, const double* d_logw,
+                              const double* d_logl, const double* d_max, uint64_t seed,
+                              uint64_t row_offset, double log_p_value,
+                              const uint8_t* d_row_template, int row_bytes,
+                              const int32_t* h_field_offsets, int logl_offset, uint8_t* d_rows,
+                              int64_t capacity, int64_t write_offset, int64_t* d_counts,
+                              int64_t* d_scratch, void* stream);
+
+/* Populate tail for per-parameter maps x = h(x') * scale + shift, h = identity (kind 0),
+ * sigmoid (1), |.| (2) or exp (3): the inverse direction of
+ * reparameterisations/rescale.py:635-660 RescaleToBounds.inverse_reparameterise with
+ * post_rescaling "logit" (utils/rescaling.py:310-330 sigmoid, log|J| = log h + log1p(-h)),
+ * "log" (utils/rescaling.py:385-402 exp, log|J| = x') or boundary inversion
+ * (rescale.py:570-590: |x'|, an "upper" edge folded into a negative scale), then the affine
+ * map to the prior bounds (rescale.py:544-553, log|J| = log|scale|).  Runs AFTER
+ * nb200_populate_draw called with scale = 1, shift = 0, lo = -inf, hi = +inf,
+ * min_log_q = -inf: d_xp float32[n*D] is the flow output, d_logq float64[n] the flow's own
+ * log q (NaN: dropped).  Rewrites d_logq (-= log|J|), d_logw (= log_prior_const - log_q; NaN
+ * for rows outside d_lo/d_hi, with non-finite log_q or log_q <= min_log_q), writes
+ * d_x64 float64[n*D], and accumulates d_stats = {max log_w, n_valid} (reset by the caller).
+ * d_kind int32[D], d_scale/d_shift/d_lo/d_hi float64[D] on the device; D <= 64. */
+int nb200_reparam_tail(int64_t n, int D, const float* d_xp, const int32_t* d_kind,
+                       const double* d_scale, const double* d_shift, const double* d_lo,
+                       const double* d_hi, double log_prior_const, double min_log_q,
+                       double* d_logq, double* d_logw, double* d_x64, double* d_stats,
+                       void* stream);
+
+/* accumulate_weights variant, flowproposal/flowproposal.py:471-490: the expected pool size is
+ * exp(logsumexp(log_weights - log_constant)).  d_partials[b] (float64[n_partials]) receives
+ * block b's share of sum_i exp(d_logw[i] - *d_max) over the non-NaN rows; the caller adds them
+ * in index order (no atomics: the sum is reproducible). */
+int nb200_sum_exp(const double* d_logw, int64_t n, const double* d_max, double* d_partials,
+                  int n_partials, void* stream);
+
 /* glasflow.nflows AffineCouplingTransform._coupling_transform_forward / _inverse (the
  * element-wise stage of flows/realnvp.py:110-112 with the conditioner output supplied):
  * d_params[n][2*d_tr] = shift | unconstrained scale (nflows layout; [n][d_tr] when additive),

@@ -93,6 +93,18 @@ _SIGS = {
          C.c_uint64, C.c_uint64, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
          C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
+    "nb200_populate_accept_x64": (
+        C.c_int,
+        [C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_uint64, C.c_uint64, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+         C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "nb200_reparam_tail": (
+        C.c_int,
+        [C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "nb200_sum_exp": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "nb200_coupling_transform": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int,

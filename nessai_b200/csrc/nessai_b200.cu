@@ -13,6 +13,7 @@
 #include "flow_interp.cuh"
 #include "philox.cuh"
 #include "populate_common.cuh"
+#include "reparam_tail.cuh"
 #include "flow_tc.cuh"
 #include "flow_tc_res.cuh"
 #include "flow_tc_nsf.cuh"
@@ -309,7 +310,8 @@ __device__ __forceinline__ void acc_st(unsigned long long* p, unsigned long long
 // (one coalesced 4-byte word per lane) in draw order.  status[0 .. nchunks-1] and the ticket
 // status[nchunks] are zeroed by the launcher.
 __global__ void __launch_bounds__(ACC_THREADS)
-accept_fused_kernel(const float* __restrict__ xp, const double* __restrict__ scale,
+accept_fused_kernel(const float* __restrict__ xp, const double* __restrict__ x64,
+                    const double* __restrict__ scale,
                     const double* __restrict__ shift, const double* __restrict__ logw,
                     const double* __restrict__ logl, int logl_off,
                     const double* __restrict__ d_max, int64_t n, uint64_t seed, uint64_t row_offset,
@@ -418,7 +420,9 @@ accept_fused_kernel(const float* __restrict__ xp, const double* __restrict__ sca
           if (sc >= 0) {
             // same float64 arithmetic as the bounds check of the draw kernel
             const int d = sc >> 1;
-            const unsigned long long b = __double_as_longlong((double)xr[d] * scale_s[d] + shift_s[d]);
+            // (x64: physical x already formed by reparam_tail_kernel for a non-affine rescaling)
+            const unsigned long long b = __double_as_longlong(
+                x64 ? x64[(row0 + j) * F.D + d] : (double)xr[d] * scale_s[d] + shift_s[d]);
             word = (sc & 1) ? (uint32_t)(b >> 32) : (uint32_t)b;
           } else if (sc < -1) {
             const unsigned long long b = __double_as_longlong(logl[row0 + j]);
@@ -605,15 +609,15 @@ extern "C" int nb200_populate_draw(nb200_flow* f, int64_t n, uint64_t seed, uint
   return 0;
 }
 
-extern "C" int nb200_populate_accept(int64_t n, int D, const float* d_xp, const double* d_scale,
-                                     const double* d_shift, const double* d_logw,
-                                     const double* d_logl, const double* d_max, uint64_t seed,
-                                     uint64_t row_offset, double log_p_value,
-                                     const uint8_t* d_row_template, int row_bytes,
-                                     const int32_t* h_field_offsets, int logl_offset, uint8_t* d_rows,
-                                     int64_t capacity, int64_t write_offset, int64_t* d_counts,
-                                     int64_t* d_scratch, void* stream) {
-  if (!d_xp || !d_scale || !d_shift || !d_logw || !d_max || !d_row_template || !h_field_offsets || !d_rows || !d_counts ||
+static int populate_accept_impl(int64_t n, int D, const float* d_xp, const double* d_x64,
+                                const double* d_scale, const double* d_shift, const double* d_logw,
+                                const double* d_logl, const double* d_max, uint64_t seed,
+                                uint64_t row_offset, double log_p_value,
+                                const uint8_t* d_row_template, int row_bytes,
+                                const int32_t* h_field_offsets, int logl_offset, uint8_t* d_rows,
+                                int64_t capacity, int64_t write_offset, int64_t* d_counts,
+                                int64_t* d_scratch, void* stream) {
+  if ((!d_xp && !d_x64) || !d_scale || !d_shift || !d_logw || !d_max || !d_row_template || !h_field_offsets || !d_rows || !d_counts ||
       !d_scratch)
     return fail(1, "nb200_populate_accept: bad arguments");
   if (row_bytes % 4 || row_bytes <= 0) return fail(1, "row_bytes must be a positive multiple of 4");
@@ -638,10 +642,71 @@ extern "C" int nb200_populate_accept(int64_t n, int D, const float* d_xp, const 
   if (smem > 40 * 1024) return fail(1, "nb200_populate_accept: record too large (%d bytes)", row_bytes);
   CUDA_OK(cudaMemsetAsync(d_scratch, 0, (size_t)(nchunks + 1) * sizeof(int64_t), st));
   accept_fused_kernel<<<(unsigned)nchunks, ACC_THREADS, smem, st>>>(
-      d_xp, d_scale, d_shift, d_logw, d_logl, d_logl ? logl_offset : -1, d_max, n, seed, row_offset,
+      d_xp, d_x64, d_scale, d_shift, d_logw, d_logl, d_logl ? logl_offset : -1, d_max, n, seed, row_offset,
       reinterpret_cast<unsigned long long*>(d_scratch), nchunks, log_p_value,
       reinterpret_cast<const uint32_t*>(d_row_template), F, reinterpret_cast<uint32_t*>(d_rows), capacity,
       write_offset, d_counts);
+  g_launches += 1;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int nb200_populate_accept(int64_t n, int D, const float* d_xp, const double* d_scale,
+                                     const double* d_shift, const double* d_logw,
+                                     const double* d_logl, const double* d_max, uint64_t seed,
+                                     uint64_t row_offset, double log_p_value,
+                                     const uint8_t* d_row_template, int row_bytes,
+                                     const int32_t* h_field_offsets, int logl_offset, uint8_t* d_rows,
+                                     int64_t capacity, int64_t write_offset, int64_t* d_counts,
+                                     int64_t* d_scratch, void* stream) {
+  if (!d_xp) return fail(1, "nb200_populate_accept: bad arguments");
+  return populate_accept_impl(n, D, d_xp, nullptr, d_scale, d_shift, d_logw, d_logl, d_max, seed,
+                              row_offset, log_p_value, d_row_template, row_bytes, h_field_offsets,
+                              logl_offset, d_rows, capacity, write_offset, d_counts, d_scratch, stream);
+}
+
+extern "C" int nb200_populate_accept_x64(int64_t n, int D, const double* d_x64, const double* d_logw,
+                                         const double* d_logl, const double* d_max, uint64_t seed,
+                                         uint64_t row_offset, double log_p_value,
+                                         const uint8_t* d_row_template, int row_bytes,
+                                         const int32_t* h_field_offsets, int logl_offset,
+                                         uint8_t* d_rows, int64_t capacity, int64_t write_offset,
+                                         int64_t* d_counts, int64_t* d_scratch, void* stream) {
+  if (!d_x64) return fail(1, "nb200_populate_accept_x64: bad arguments");
+  // scale / shift are unused when x64 is given; any valid device pointer of >= D doubles serves
+  return populate_accept_impl(n, D, nullptr, d_x64, d_x64, d_x64, d_logw, d_logl, d_max, seed,
+                              row_offset, log_p_value, d_row_template, row_bytes, h_field_offsets,
+                              logl_offset, d_rows, capacity, write_offset, d_counts, d_scratch, stream);
+}
+
+extern "C" int nb200_reparam_tail(int64_t n, int D, const float* d_xp, const int32_t* d_kind,
+                                  const double* d_scale, const double* d_shift, const double* d_lo,
+                                  const double* d_hi, double log_prior_const, double min_log_q,
+                                  double* d_logq, double* d_logw, double* d_x64, double* d_stats,
+                                  void* stream) {
+  if (!d_xp || !d_kind || !d_scale || !d_shift || !d_lo || !d_hi || !d_logq || !d_logw || !d_x64 || !d_stats)
+    return fail(1, "nb200_reparam_tail: bad arguments");
+  if (D < 1 || D > TAIL_MAXD) return fail(1, "nb200_reparam_tail: D=%d out of range (1..%d)", D, TAIL_MAXD);
+  if (n <= 0) return 0;
+  int dev = 0, sms = 148;
+  CUDA_OK(cudaGetDevice(&dev));
+  CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = (int)std::min<int64_t>((n + TAIL_THREADS - 1) / TAIL_THREADS, (int64_t)sms * 8);
+  reparam_tail_kernel<<<grid, TAIL_THREADS, 0, (cudaStream_t)stream>>>(
+      n, D, d_xp, d_kind, d_scale, d_shift, d_lo, d_hi,
+      isnan(log_prior_const) ? 0.0 : log_prior_const, isnan(min_log_q) ? -INFINITY : min_log_q,
+      d_logq, d_logw, d_x64, d_stats);
+  g_launches += 1;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int nb200_sum_exp(const double* d_logw, int64_t n, const double* d_max,
+                             double* d_partials, int n_partials, void* stream) {
+  if (!d_logw || !d_max || !d_partials || n_partials < 1 || n_partials > 65535)
+    return fail(1, "nb200_sum_exp: bad arguments");
+  if (n < 0) n = 0;  // every partial is still written (zeros)
+  sum_exp_kernel<<<n_partials, SUMEXP_THREADS, 0, (cudaStream_t)stream>>>(d_logw, n, d_max, d_partials);
   g_launches += 1;
   CUDA_OK(cudaGetLastError());
   return 0;

@@ -1,0 +1,148 @@
+// Populate tail for reparameterisations that are NOT a diagonal affine:
+// per feature  x = h(x') * scale + shift  with  h in {identity, sigmoid, |.|, exp}, float64, the
+// inverse direction of /root/reference/src/nessai/reparameterisations/rescale.py:635-660
+// (RescaleToBounds.inverse_reparameterise):
+//   * post_rescaling "logit"  -> h = sigmoid, log|J| += log h + log1p(-h)   (utils/rescaling.py:310-330)
+//   * post_rescaling "log"    -> h = exp,     log|J| += x'                  (utils/rescaling.py:385-402)
+//   * boundary inversion      -> h = |.|      (rescale.py:570-590: value[value < 0] *= -1; "upper"
+//                                edge: 1 - value, folded into a negative scale)
+// followed by the affine map back to the prior bounds (rescale.py:544-553), whose log|J| is
+// log|scale|, then the prior-bounds check (model.py:497-518) and log_w = log_prior - log_q
+// (flowproposal/base.py:1069-1098).
+//
+// The per-row arithmetic is a __host__ __device__ function so that the very same source is
+// compiled by g++ into a host harness in tests/ (tests/_hostcheck) and checked against the numpy
+// oracle without a GPU; the library only ever calls it from the kernel below.
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#ifdef __CUDACC__
+#define NB200_HD __host__ __device__ __forceinline__
+#else
+#define NB200_HD inline
+#endif
+
+namespace nb200 {
+
+enum TailKind : int32_t { TAIL_IDENTITY = 0, TAIL_SIGMOID = 1, TAIL_ABS = 2, TAIL_EXP = 3 };
+
+// One feature: returns x, adds the log-Jacobian of h (NOT of the affine part) to logj.
+NB200_HD double tail_feature(int32_t kind, double scale, double shift, double v, double& logj) {
+  double h = v;
+  if (kind == TAIL_SIGMOID) {
+    h = 1.0 / (1.0 + exp(-v));
+    logj += log(h) + log1p(-h);
+  } else if (kind == TAIL_ABS) {
+    h = fabs(v);
+  } else if (kind == TAIL_EXP) {
+    h = exp(v);
+    logj += v;
+  }
+  return h * scale + shift;
+}
+
+// One row.  logq_flow: log q of the flow alone (NaN: the row was already dropped by the draw
+// kernel).  log_scale_sum = sum_d log|scale_d|.  Writes x[D]; returns true when the row
+// survives and then logq_out / logw_out are its log q / log weight.
+NB200_HD bool tail_row(int D, const float* xp, const int32_t* kind, const double* scale,
+                       const double* shift, const double* lo, const double* hi,
+                       double log_scale_sum, double log_prior_const, double min_log_q,
+                       double logq_flow, double* x, double& logq_out, double& logw_out) {
+  double logj = log_scale_sum;
+  bool inb = true;
+  for (int d = 0; d < D; ++d) {
+    const double xv = tail_feature(kind[d], scale[d], shift[d], (double)xp[d], logj);
+    x[d] = xv;
+    inb = inb && !(xv < lo[d]) && !(xv > hi[d]);
+  }
+  const double logq = logq_flow - logj;
+  // isfinite() also rejects the NaN of an already-dropped row
+  const bool ok = inb && (logq - logq == 0.0) && (logq > min_log_q);
+  logq_out = ok ? logq : NAN;
+  logw_out = ok ? (log_prior_const - logq) : NAN;
+  return ok;
+}
+
+#ifdef __CUDACC__
+#define TAIL_THREADS 256
+#define TAIL_MAXD 64
+
+// One thread per row: 4 D + 8 bytes in, 8 D + 16 bytes out per row (HBM-bound, a fraction of
+// the draw kernel's time).  The per-feature constants sit in shared memory.
+__global__ void __launch_bounds__(TAIL_THREADS)
+reparam_tail_kernel(int64_t n, int D, const float* __restrict__ xp, const int32_t* __restrict__ kind,
+                    const double* __restrict__ scale, const double* __restrict__ shift,
+                    const double* __restrict__ lo, const double* __restrict__ hi,
+                    double log_prior_const, double min_log_q, double* __restrict__ logq,
+                    double* __restrict__ logw, double* __restrict__ x64, double* __restrict__ stats) {
+  __shared__ double c_s[4 * TAIL_MAXD];
+  __shared__ int32_t k_s[TAIL_MAXD];
+  __shared__ double lss_s;
+  for (int d = threadIdx.x; d < D; d += TAIL_THREADS) {
+    c_s[d] = scale[d];
+    c_s[TAIL_MAXD + d] = shift[d];
+    c_s[2 * TAIL_MAXD + d] = lo[d];
+    c_s[3 * TAIL_MAXD + d] = hi[d];
+    k_s[d] = kind[d];
+  }
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int d = 0; d < D; ++d) s += log(fabs(scale[d]));
+    lss_s = s;
+  }
+  __syncthreads();
+  double vmax = -INFINITY, vcount = 0.0;
+  for (int64_t row = (int64_t)blockIdx.x * TAIL_THREADS + threadIdx.x; row < n;
+       row += (int64_t)gridDim.x * TAIL_THREADS) {
+    // x is written straight to global memory (every row: the accept kernel only reads the
+    // rows it keeps, and a device likelihood may read them all)
+    double lq, lw;
+    const bool ok = tail_row(D, xp + row * D, k_s, c_s, c_s + TAIL_MAXD, c_s + 2 * TAIL_MAXD,
+                             c_s + 3 * TAIL_MAXD, lss_s, log_prior_const, min_log_q, logq[row],
+                             x64 + row * D, lq, lw);
+    logq[row] = lq;
+    logw[row] = lw;
+    if (ok) {
+      vmax = fmax(vmax, lw);
+      vcount += 1.0;
+    }
+  }
+  // same publication as the draw kernels (populate_common.cuh: populate_publish)
+  for (int o = 16; o > 0; o >>= 1) {
+    vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    vcount += __shfl_xor_sync(0xffffffffu, vcount, o);
+  }
+  if ((threadIdx.x & 31) == 0 && vcount > 0) {
+    atomic_max_double(stats, vmax);
+    atomicAdd(stats + 1, vcount);
+  }
+}
+
+// sum_i exp(log_w_i - max) over the non-NaN rows: the expected pool size of the
+// accumulate_weights variant (flowproposal.py:474-475: logsumexp(log_weights - log_constant)).
+// One partial per block, written unconditionally, so the total does not depend on atomics.
+#define SUMEXP_THREADS 256
+__global__ void __launch_bounds__(SUMEXP_THREADS)
+sum_exp_kernel(const double* __restrict__ logw, int64_t n, const double* __restrict__ d_max,
+               double* __restrict__ partials) {
+  const double mx = *d_max;
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * SUMEXP_THREADS + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * SUMEXP_THREADS) {
+    const double lw = logw[i];
+    if (!isnan(lw) && lw > -INFINITY) s += exp(lw - mx);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ double ws[SUMEXP_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < SUMEXP_THREADS / 32; ++i) t += ws[i];
+    partials[blockIdx.x] = t;
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace nb200

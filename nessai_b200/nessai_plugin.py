@@ -6,9 +6,10 @@ Importing this module requires ``nessai`` to be importable.  It defines
   ``_FlowModelClass = B200FlowModel`` -- every flow evaluation of the unmodified
   reference proposal (train / forward_pass / backward_pass / truncation rules)
   runs on the CUDA kernels -- and a ``populate`` override that runs the fused
-  device loop whenever the configuration allows it (z-score / null
-  reparameterisation, latent-radius truncation only, no weight accumulation) and
-  otherwise defers to the reference's host loop;
+  device loop whenever the configuration allows it (``parameter_maps``: z-score /
+  null / scale / rescale-to-bounds reparameterisations incl. logit / log
+  post-rescaling and boundary inversion; the three truncation rules; weight
+  accumulation for affine maps) and otherwise defers to the reference's host loop;
 * the entry point ``nessai.proposals: b200flowproposal``, so
   ``FlowSampler(model, flow_proposal_class="b200flowproposal")`` picks it up
   through ``nessai.proposal.utils.get_flow_proposal_class``
@@ -25,58 +26,92 @@ from nessai import config as nessai_config
 from nessai.livepoint import empty_structured_array as nessai_empty_structured_array
 from nessai.proposal.flowproposal import FlowProposal
 from nessai.reparameterisations import NullReparameterisation, RescaleToBounds, ScaleAndShift
+from nessai.utils.rescaling import exp_with_log_jacobian as _ref_exp
+from nessai.utils.rescaling import sigmoid as _ref_sigmoid
 
 from .flowmodel import B200FlowModel
-from .proposal import IndexPool, PopulateEngine, detect_uniform_box_prior
+from .proposal import GeneralPopulateEngine, IndexPool, PopulateEngine, detect_uniform_box_prior
 
 logger = logging.getLogger(__name__)
 
 
+# per-parameter map kinds of the device tail (csrc/reparam_tail.cuh: TailKind)
+KIND_IDENTITY, KIND_SIGMOID, KIND_ABS, KIND_EXP = 0, 1, 2, 3
 
-def diagonal_rescaling(rep, prime_parameters, model_names):
-    """``(scale, shift)`` with ``x = x' * scale + shift`` per parameter (model order) when the
-    combined reparameterisation ``rep`` (reparameterisations/combined.py:154-192) is a diagonal
-    affine map, else ``None``.  A diagonal affine is what the fused populate tail evaluates
-    (float64): ``log|J| = sum log|scale|``.  Recognised:
+
+def parameter_maps(rep, prime_parameters, model_names):
+    """``(kind, scale, shift)`` with ``x = h(x') * scale + shift`` per parameter (model order),
+    ``h`` = identity / sigmoid / ``|.|`` / exp, when the combined reparameterisation ``rep``
+    (reparameterisations/combined.py:154-192) is made of such one-to-one per-parameter maps, else
+    ``None``.  ``log|J| = sum log|scale| + sum log|h'(x')|``.  Recognised:
 
     * ``NullReparameterisation`` (reparameterisations/null.py): identity;
     * ``ScaleAndShift`` / ``Rescale`` (rescale.py:233-291) without pre-/post-rescaling:
       ``x = x' * scale + shift``;
-    * ``RescaleToBounds`` (rescale.py:321-731) without boundary inversion and without pre-/post-
-      rescaling functions: ``x = (hi - lo) * (x' - r0) / (r1 - r0) + lo + offset`` with
-      ``[lo, hi]`` the current (possibly data-updated) bounds, ``[r0, r1]`` the rescale bounds
-      (rescale.py:533-543,669-680), i.e. ``scale = (hi - lo) / (r1 - r0)``,
-      ``shift = lo + offset - scale * r0``.
+    * the stock ``RescaleToBounds`` (rescale.py:321-731) without a pre-rescaling function:
+      ``x = (hi - lo) * (h(x') - r0) / (r1 - r0) + lo + offset`` with ``[lo, hi]`` the current
+      (possibly data-updated) bounds and ``[r0, r1]`` the rescale bounds (rescale.py:533-553,
+      669-680), i.e. ``scale = (hi - lo) / (r1 - r0)``, ``shift = lo + offset - scale * r0``;
+      ``h`` = sigmoid for ``post_rescaling="logit"``, exp for ``"log"`` (utils/rescaling.py:
+      310-330,385-402); with boundary inversion (rescale.py:570-590) ``h = |.|`` and the detected
+      edge picks the map: "lower" ``[0, 1] -> [lo, hi]``, "upper" ``1 - |x'|`` first (negative
+      scale), no edge ``[-1, 1] -> [lo, hi]`` with ``h`` = identity.
 
-    Anything else (logit / log post-rescaling, boundary inversion, angles, user classes) is not
-    a diagonal affine and keeps the reference's host loop."""
+    Anything else (user rescaling functions, inversion combined with a post-rescaling, an edge
+    not detected yet, angles, user classes) keeps the reference's host loop."""
     if rep is None:
         return None
     if list(prime_parameters) != [p for r in rep.values() for p in r.output_parameters]:
         return None
-    scale, shift, names = [], [], []
+    kind, scale, shift, names = [], [], [], []
     for r in rep.values():
         if isinstance(r, ScaleAndShift):
             if r.has_pre_rescaling or r.has_post_rescaling or not r.one_to_one:
                 return None
             for p in r.parameters:
+                kind.append(KIND_IDENTITY)
                 scale.append(float(r.scale[p]))
                 shift.append(float(r.shift[p]) if r.shift else 0.0)
                 names.append(p)
         elif isinstance(r, NullReparameterisation):
             for p in r.parameters:
+                kind.append(KIND_IDENTITY)
                 scale.append(1.0)
                 shift.append(0.0)
                 names.append(p)
         elif type(r) is RescaleToBounds:
             # subclasses may override the rescaling hooks: only the stock class is recognised
-            if r.boundary_inversion or r.has_pre_rescaling or r.has_post_rescaling or not r.one_to_one:
+            if r.has_pre_rescaling or not r.one_to_one:
                 return None
+            post = KIND_IDENTITY
+            if r.has_post_rescaling:
+                if r.post_rescaling_inv is _ref_sigmoid:
+                    post = KIND_SIGMOID
+                elif r.post_rescaling_inv is _ref_exp:
+                    post = KIND_EXP
+                else:
+                    return None
             for p in r.parameters:
                 lo, hi = (float(b) for b in r.bounds[p])
-                s = (hi - lo) / float(r._rescale_factor[p])
+                off = float(r.offsets[p])
+                if r.boundary_inversion and p in r.boundary_inversion:
+                    edge = (r._edges or {}).get(p)
+                    if post != KIND_IDENTITY or edge is None:
+                        return None
+                    if edge == "lower":
+                        k, s, t = KIND_ABS, hi - lo, lo + off
+                    elif edge == "upper":
+                        k, s, t = KIND_ABS, -(hi - lo), hi + off
+                    elif not edge:
+                        k, s, t = KIND_IDENTITY, (hi - lo) / 2.0, lo + off + (hi - lo) / 2.0
+                    else:
+                        return None
+                else:
+                    s = (hi - lo) / float(r._rescale_factor[p])
+                    k, t = post, lo + off - s * float(r._rescale_shift[p])
+                kind.append(k)
                 scale.append(s)
-                shift.append(lo + float(r.offsets[p]) - s * float(r._rescale_shift[p]))
+                shift.append(t)
                 names.append(p)
         else:
             return None
@@ -85,7 +120,16 @@ def diagonal_rescaling(rep, prime_parameters, model_names):
     scale, shift = np.asarray(scale, dtype=np.float64), np.asarray(shift, dtype=np.float64)
     if not (np.all(np.isfinite(scale)) and np.all(np.isfinite(shift)) and np.all(scale != 0.0)):
         return None
-    return scale, shift
+    return np.asarray(kind, dtype=np.int32), scale, shift
+
+
+def diagonal_rescaling(rep, prime_parameters, model_names):
+    """``(scale, shift)`` when ``parameter_maps`` finds a diagonal affine (every ``h`` the
+    identity): what the fused populate tail of the draw kernels evaluates itself."""
+    maps = parameter_maps(rep, prime_parameters, model_names)
+    if maps is None or np.any(maps[0] != KIND_IDENTITY):
+        return None
+    return maps[1], maps[2]
 
 
 class B200NessaiFlowProposal(FlowProposal):
@@ -106,12 +150,12 @@ class B200NessaiFlowProposal(FlowProposal):
         self._log_prior_const = None
 
     # ------------------------------------------------------------ eligibility
-    def _diagonal_rescaling(self):
-        """(scale, shift) in prime-parameter order if the rescaling is a diagonal
-        affine handled on the device, else None."""
-        if self.map_to_unit_hypercube or self.accumulate_weights:
+    def _parameter_maps(self):
+        """(kind, scale, shift) in prime-parameter order if the rescaling is made of
+        per-parameter maps the device evaluates, else None."""
+        if self.map_to_unit_hypercube:
             return None
-        return diagonal_rescaling(self._reparameterisation, self.prime_parameters, self.model.names)
+        return parameter_maps(self._reparameterisation, self.prime_parameters, self.model.names)
 
     def _fused_rules(self):
         """The truncation rules as a name -> rule dict if the device loop implements all of
@@ -130,36 +174,45 @@ class B200NessaiFlowProposal(FlowProposal):
     def populate(self, worst_point, n_samples=10000, plot=True, r=None, max_samples=1_000_000):
         """flowproposal.py:391-534; the ``while n_accepted < n_samples`` loop runs
         on the device when eligible."""
-        diag = self._diagonal_rescaling() if self.initialised else None
+        st = datetime.datetime.now()
+        maps = self._parameter_maps() if self.initialised else None
         rules = self._fused_rules() if self.initialised else None
-        if diag is None or rules is None:
+        eligible = maps is not None and rules is not None
+        if eligible and np.any(maps[0] != KIND_IDENTITY) and len(maps[0]) > GeneralPopulateEngine.MAX_D:
+            eligible = False
+        if eligible:
+            affine = not np.any(maps[0] != KIND_IDENTITY)
+            engine_cls = PopulateEngine if affine else GeneralPopulateEngine
+            if (self._engine is None or self._engine.flow is not self.flow
+                    or type(self._engine) is not engine_cls):
+                # (the class can change between populates: boundary inversion re-detects its
+                # edges whenever the flow is retrained, rescale.py:662-665)
+                self._engine = engine_cls(
+                    self.flow, self.model.names, self.population_dtype,
+                    row_template=nessai_empty_structured_array(1, dtype=self.population_dtype),
+                )
+                self._log_prior_const = (
+                    detect_uniform_box_prior(self.model, self.rng)
+                    if self.device_prior in ("auto", True, "uniform")
+                    else None
+                )
+            if self.accumulate_weights and (
+                not affine or "likelihood_threshold" in rules or self._log_prior_const is None
+            ):
+                eligible = False  # the accumulating device loop: affine maps, device prior
+        if not eligible:
             logger.debug("B200: configuration not eligible for the fused loop; using the host loop")
             return super().populate(worst_point, n_samples=n_samples, plot=plot, r=r, max_samples=max_samples)
-        st = datetime.datetime.now()
-        if not self.initialised:
-            raise RuntimeError(
-                "Proposal has not been initialised. Try calling `initialise()` first."
-            )
         self._truncation_scheme.prepare(self, worst_point, radius=r)
         if self.indices:
             logger.debug("Existing pool of samples is not empty. Discarding existing samples.")
         self.indices = []
-        if self._engine is None or self._engine.flow is not self.flow:
-            self._engine = PopulateEngine(
-                self.flow, self.model.names, self.population_dtype,
-                row_template=nessai_empty_structured_array(1, dtype=self.population_dtype),
-            )
-            self._log_prior_const = (
-                detect_uniform_box_prior(self.model, self.rng)
-                if self.device_prior in ("auto", True, "uniform")
-                else None
-            )
         lo = [self.model.bounds[n][0] for n in self.model.names]
         hi = [self.model.bounds[n][1] for n in self.model.names]
         t = self.latent_temperature
         in_loop = "likelihood_threshold" in rules
         self._engine.configure(
-            diag[0], diag[1], lo, hi, self._log_prior_const,
+            *(maps[1:] if affine else maps), lo, hi, self._log_prior_const,
             rules["latent_radius"].threshold if "latent_radius" in rules else 0.0,
             1.0 if t in (None, 1.0) else float(np.sqrt(t)),
             min_log_q=rules["min_log_q"].min_log_q if "min_log_q" in rules else None,
@@ -168,9 +221,14 @@ class B200NessaiFlowProposal(FlowProposal):
         )
         host_prior = None if self._log_prior_const is not None else self.log_prior
         evals0 = getattr(self._engine, "likelihood_evaluations", 0)
-        rows, n_proposed, n_accepted = self._engine.run(
-            int(n_samples), int(self.drawsize), max_samples=max_samples, host_prior=host_prior
-        )
+        if self.accumulate_weights:
+            rows, n_proposed, n_accepted = self._engine.run_accumulate(
+                int(n_samples), int(self.drawsize), max_samples=max_samples
+            )
+        else:
+            rows, n_proposed, n_accepted = self._engine.run(
+                int(n_samples), int(self.drawsize), max_samples=max_samples, host_prior=host_prior
+            )
         self.x = rows
         self.samples = self.convert_to_samples(self.x, plot=plot) if host_prior is not None else rows
         if self._plot_pool and plot:

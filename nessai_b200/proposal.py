@@ -190,6 +190,45 @@ class IndexPool:
         return self._a[: self._n].tolist()
 
 
+class AccumulateControl:
+    """Loop control of ``populate`` with ``accumulate_weights=True``, host side, exactly the
+    reference's (/root/reference/src/nessai/proposal/flowproposal/flowproposal.py:431-490,
+    504-512): a turn that added no surviving row only checks ``max_samples`` (``continue``,
+    :436-439,449-453); otherwise the rejection step runs when the expected pool size has reached
+    ``n_samples`` (:477-485); ``max_samples`` ends the loop after the turn (:486-488); after the
+    loop the rejection step is repeated if rows were added since the last one (:505-507)."""
+
+    def __init__(self, n_samples: int, max_samples: int):
+        import math
+
+        self.n_samples, self.max_samples = int(n_samples), int(max_samples)
+        self.log_n = math.log(self.n_samples) if self.n_samples > 0 else -math.inf
+        self.n_proposed = self.n_accepted = 0
+        self.stale = False  # rows were added since the last rejection step
+        self.stopped_on_max_samples = False
+
+    def go_on(self) -> bool:
+        return not self.stopped_on_max_samples and self.n_accepted < self.n_samples
+
+    def turn_drawn(self, n_drawn: int, added_rows: bool, n_expected: float) -> bool:
+        """Account for a turn; True when the rejection step must run now."""
+        import math
+
+        self.n_proposed += int(n_drawn)
+        if not added_rows:
+            return False
+        self.stale = True
+        return n_expected > 0.0 and math.log(n_expected) >= self.log_n
+
+    def rejected(self, n_accepted: int):
+        self.n_accepted = int(n_accepted)
+        self.stale = False
+
+    def end_turn(self):
+        if self.n_proposed > self.max_samples:
+            self.stopped_on_max_samples = True
+
+
 class PopulateEngine:
     """Fused populate turns on one GPU (optionally one rank of many)."""
 
@@ -332,9 +371,13 @@ class PopulateEngine:
         args[17] = torch.cuda.current_stream(self.device).cuda_stream
         self._call(self._draw_fn, args, "nb200_populate_draw")
         self._last = self._draw_shard
+        self._after_draw(n_local)
+        return n_local
+
+    def _after_draw(self, n_local: int):
+        """What follows the fused draw kernel within a turn (overridden by GeneralPopulateEngine)."""
         if self.likelihood is not None:
             self._apply_device_likelihood(n_local)
-        return n_local
 
     def device_log_likelihood(self, n_written: int, fn) -> torch.Tensor:
         """``fn(x)`` on the accepted records still resident in ``d_rows`` (``x``: ``(n, D)``
@@ -562,6 +605,111 @@ class PopulateEngine:
             tr.append(("rows", time.perf_counter()))
         return rows, n_proposed, n_accepted
 
+    # ------------------------------------------------------- accumulate_weights
+    def run_accumulate(self, n_samples: int, drawsize: int, max_samples: int = 1_000_000):
+        """The ``accumulate_weights=True`` variant of the loop
+        (/root/reference/src/nessai/proposal/flowproposal/flowproposal.py:414-417,471-490,504-512):
+        the rows and weights of EVERY turn are kept (turn ``t`` is drawn into slot ``t`` of the
+        device buffers by the same fused kernel, the running maximum ``log_constant`` and the
+        valid count accumulate in ``d_stats``), the expected pool size
+        ``exp(logsumexp(log_weights - log_constant))`` is one reduction kernel per turn, and the
+        rejection step runs over all rows so far -- fresh uniforms each time -- only once that
+        reaches ``n_samples``; ``samples[accept][:n_samples]`` is what the accept kernel's
+        capacity implements.  One host synchronisation per turn (this variant is not pipelined).
+        Returns ``(rows, n_proposed, n_accepted)`` like ``run``."""
+        import math
+
+        if self.likelihood is not None:
+            raise NotImplementedError("nessai_b200: accumulate_weights with likelihood_threshold truncation")
+        if self.log_prior_const is None:
+            raise NotImplementedError("nessai_b200: accumulate_weights needs the prior on the device")
+        n_samples, drawsize = int(n_samples), int(drawsize)
+        ctl = AccumulateControl(n_samples, max_samples)
+        n_local, start = self._shard(drawsize)
+        # rows per turn slot: the same on every rank, a multiple of 32 rows (vector stores)
+        stride = -(-(-(-drawsize // self.world)) // 32) * 32
+        max_turns = int(max_samples) // max(drawsize, 1) + 1
+        cap = stride * max_turns
+        limit = int(os.environ.get("NB200_ACCUMULATE_MAX_BYTES", 64 << 30))
+        if cap * (4 * self.D + 16) > limit:
+            raise MemoryError(
+                f"nessai_b200: accumulate_weights would keep {cap} rows on the device "
+                f"({cap * (4 * self.D + 16) / 2**30:.1f} GiB); lower max_samples"
+            )
+        self._ensure(cap, max(n_samples, 1), False)
+        self.model._ready()
+        lib = _lib.load()
+        dev = self.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        if getattr(self, "d_partials", None) is None:
+            self.d_partials = torch.empty(self._N_PARTIALS, dtype=torch.float64, device=dev)
+        self.d_logw[:cap].fill_(float("nan"))  # slot padding and undrawn slots never count
+        self.d_stats.copy_(self._stats_init, non_blocking=True)
+        lpc = float(self.log_prior_const)
+        info = dict(stride=stride, n_local=n_local, start=start, draw_offsets=[], rejects=[], n_expected=[])
+        self.last_accumulate = info
+        turn, n_valid = 0, 0
+        while ctl.go_on():
+            off = turn * stride
+            info["draw_offsets"].append(self._turn_rows + start)
+            self._call(lib.nb200_populate_draw, [
+                self.model._handle, n_local, self._seed(), self._turn_rows + start, self.r_max, self.sqrt_t,
+                self.d_scale.data_ptr(), self.d_shift.data_ptr(), self.d_lo.data_ptr(), self.d_hi.data_ptr(),
+                lpc, self.min_log_q, self.d_xp.data_ptr() + off * self.D * 4, self.d_logq.data_ptr() + off * 8,
+                self.d_logw.data_ptr() + off * 8, None, self.d_stats.data_ptr(), st,
+            ], "nb200_populate_draw")
+            self._turn_rows += drawsize
+            turn += 1
+            rows = turn * stride
+            if self.world > 1:
+                import torch.distributed as dist
+
+                dist.all_reduce(self.d_stats[0:1], op=dist.ReduceOp.MAX, group=self.group)
+            self._call(lib.nb200_sum_exp, [
+                self.d_logw.data_ptr(), rows, self.d_stats.data_ptr(), self.d_partials.data_ptr(),
+                self._N_PARTIALS, st,
+            ], "nb200_sum_exp")
+            # {sum exp(log_w - log_constant), valid rows}: the partials are added in index order
+            both = torch.stack([self.d_partials.sum(), self.d_stats[1]])
+            if self.world > 1:
+                dist.all_reduce(both, op=dist.ReduceOp.SUM, group=self.group)
+            n_expected, nv = (float(v) for v in both.cpu())  # the synchronisation of this turn
+            info["n_expected"].append(n_expected)
+            added = int(nv) > n_valid
+            n_valid = int(nv)
+            if ctl.turn_drawn(drawsize, added, n_expected):
+                ctl.rejected(self._accumulate_reject(rows, n_samples, info))
+            ctl.end_turn()
+        if ctl.stopped_on_max_samples:
+            logger.warning("Reached max samples (%s)", max_samples)
+        if turn and ctl.stale:
+            ctl.rejected(self._accumulate_reject(turn * stride, n_samples, info))
+        n_written = int(self.d_counts.cpu()[1]) if info["rejects"] else 0
+        return self._gather_rows(n_written, n_samples), ctl.n_proposed, ctl.n_accepted
+
+    _N_PARTIALS = 296  # blocks of the sum-exp reduction: two per SM
+
+    def _accumulate_reject(self, rows: int, n_samples: int, info: dict) -> int:
+        """Rejection step over the first ``rows`` slot rows with the running maximum
+        (flowproposal.py:483-485,505-508); returns the global number of accepted rows.  Every call
+        reserves its own block of Philox counters, so the uniforms are fresh."""
+        base = self._turn_rows + self.rank * rows
+        self._turn_rows += self.world * rows
+        info["rejects"].append((base, rows))
+        self._call(_lib.load().nb200_populate_accept, [
+            rows, self.D, self.d_xp.data_ptr(), self.d_scale.data_ptr(), self.d_shift.data_ptr(),
+            self.d_logw.data_ptr(), None, self.d_stats.data_ptr(), self._seed(), base,
+            float(self.log_prior_const), self.d_template.data_ptr(), self.row_bytes,
+            self.field_offsets.ctypes.data, self.logl_offset, self.d_rows.data_ptr(), int(n_samples), 0,
+            self.d_counts.data_ptr(), self.d_scratch.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream,
+        ], "nb200_populate_accept")
+        tot = self.d_counts[0:1].clone()
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
+        return int(tot.cpu())
+
     def _shared_pool(self, nbytes: int):
         """The node-local shared host pool (hostpool.py), created collectively on first use and
         whenever a larger one is needed; None when the ranks span several nodes, when it is
@@ -675,6 +823,89 @@ class PopulateEngine:
         return full.numpy().view(self.row_dtype)
 
 
+class GeneralPopulateEngine(PopulateEngine):
+    """``PopulateEngine`` for per-parameter maps ``x = h(x') * scale + shift`` that are not all
+    affine: ``h`` = sigmoid (``RescaleToBounds`` with ``post_rescaling="logit"``), exp (``"log"``)
+    or ``|.|`` (boundary inversion) --
+    /root/reference/src/nessai/reparameterisations/rescale.py:570-590,635-660.
+
+    The fused draw kernel is left exactly as it is: it is given the identity map and no bounds,
+    so it leaves the flow output ``x'`` and the flow's own ``log q``; ``nb200_reparam_tail``
+    (csrc/reparam_tail.cuh) then forms ``x`` and ``log|J|`` in float64, checks the prior bounds
+    and ``min_log_q``, rewrites ``log q`` / ``log w`` and the turn's statistics, and the
+    rejection step copies the float64 rows into the records (``nb200_populate_accept_x64``).
+    The loop, its pipelining and the multi-GPU exchange are the base class's."""
+
+    MAX_D = 64  # TAIL_MAXD
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if self.D > self.MAX_D:
+            raise NotImplementedError(f"nessai_b200: the non-affine tail supports at most {self.MAX_D} parameters")
+        self.d_x64 = None
+        self._tail_min_log_q = -float("inf")
+
+    def configure(self, kind, scale, shift, lo, hi, log_prior_const, r_max, sqrt_temperature=1.0, min_log_q=None,
+                  likelihood=None, log_l_threshold=None):
+        """As ``PopulateEngine.configure`` with the per-parameter ``kind`` (0 identity, 1 sigmoid,
+        2 abs, 3 exp) in front."""
+        D = self.D
+        if getattr(self, "_identity", None) is None:
+            self._identity = (np.ones(D), np.zeros(D), np.full(D, -np.inf), np.full(D, np.inf))
+        super().configure(*self._identity, log_prior_const, r_max, sqrt_temperature, min_log_q=None,
+                          likelihood=likelihood, log_l_threshold=log_l_threshold)
+        self._tail_min_log_q = -float("inf") if min_log_q is None or np.isnan(min_log_q) else float(min_log_q)
+        new = [np.array(kind, dtype=np.int32)] + [np.array(a, dtype=np.float64) for a in (scale, shift, lo, hi)]
+        if any(a.shape != (D,) for a in new):
+            raise ValueError("kind / scale / shift / lo / hi must have one entry per parameter")
+        if np.any((new[0] < 0) | (new[0] > 3)):
+            raise ValueError("unknown per-parameter map kind")
+        old = getattr(self, "_tail_host", None)
+        if old is None or not all(np.array_equal(a, b) for a, b in zip(new, old)):
+            self.t_kind = torch.from_numpy(new[0]).to(self.device)
+            dev = torch.from_numpy(np.stack(new[1:])).to(self.device)
+            self.t_scale, self.t_shift, self.t_lo, self.t_hi = dev[0], dev[1], dev[2], dev[3]
+            self._tail_host = new
+
+    def _after_draw(self, n_local: int):
+        if self.d_x64 is None or self.d_x64.shape[0] < self._cap:
+            self.d_x64 = torch.empty((self._cap, self.D), dtype=torch.float64, device=self.device)
+        if n_local > 0:
+            self.d_stats.copy_(self._stats_init, non_blocking=True)  # the draw kernel's were pre-tail
+            lpc = float("nan") if self.log_prior_const is None else float(self.log_prior_const)
+            self._call(_lib.load().nb200_reparam_tail, [
+                n_local, self.D, self.d_xp.data_ptr(), self.t_kind.data_ptr(), self.t_scale.data_ptr(),
+                self.t_shift.data_ptr(), self.t_lo.data_ptr(), self.t_hi.data_ptr(), lpc, self._tail_min_log_q,
+                self.d_logq.data_ptr(), self.d_logw.data_ptr(), self.d_x64.data_ptr(), self.d_stats.data_ptr(),
+                torch.cuda.current_stream(self.device).cuda_stream,
+            ], "nb200_reparam_tail")
+        super()._after_draw(n_local)
+
+    def physical_x(self, n: int) -> torch.Tensor:
+        return self.d_x64[:n]
+
+    def accept_turn(self, capacity_left: int, write_offset: int):
+        n_local, start = self._last
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(self.d_stats[0:1], op=dist.ReduceOp.MAX, group=self.group)
+        with_logl = self.likelihood is not None and getattr(self, "d_logl", None) is not None and self.logl_offset >= 0
+        lp = 0.0 if self.log_prior_const is None else float(self.log_prior_const)
+        self._call(_lib.load().nb200_populate_accept_x64, [
+            n_local, self.D, self.d_x64.data_ptr(), self.d_logw.data_ptr(),
+            self.d_logl.data_ptr() if with_logl else None, self.d_stats.data_ptr(), self._seed(),
+            self._turn_rows + start, lp, self.d_template.data_ptr(), self.row_bytes,
+            self.field_offsets.ctypes.data, self.logl_offset, self.d_rows.data_ptr(), int(capacity_left),
+            int(write_offset), self.d_counts.data_ptr(), self.d_scratch.data_ptr(),
+            torch.cuda.current_stream(self.device).cuda_stream,
+        ], "nb200_populate_accept_x64")
+        return self.d_counts
+
+    def run_accumulate(self, *args, **kwargs):
+        raise NotImplementedError("nessai_b200: accumulate_weights with a non-affine reparameterisation")
+
+
 class B200FlowProposal:
     """Standalone mirror of ``FlowProposal`` for the hot path (see module doc).
 
@@ -712,8 +943,10 @@ class B200FlowProposal:
             # truncation.py:431-435 (TRUNCATION_REGISTRY)
             raise ValueError(f"Unknown truncation method(s): {sorted(unknown)}")
         self.truncation_methods = methods
-        if accumulate_weights:
-            raise NotImplementedError("nessai_b200: accumulate_weights is not implemented")
+        if accumulate_weights and "likelihood_threshold" in methods:
+            raise NotImplementedError(
+                "nessai_b200: accumulate_weights with likelihood_threshold truncation is not implemented"
+            )
         if fallback_reparameterisation not in ("zscore", "null", None):
             raise NotImplementedError(
                 "nessai_b200: only the 'zscore' and 'null' reparameterisations run on the device"
@@ -729,7 +962,7 @@ class B200FlowProposal:
         self.update_poolsize = update_poolsize
         self.drawsize = self._poolsize if drawsize is None else int(drawsize)
         self.check_acceptance = check_acceptance
-        self.accumulate_weights = False
+        self.accumulate_weights = bool(accumulate_weights)
         self.fallback_reparameterisation = fallback_reparameterisation
         if latent_temperature is not None:
             if isinstance(latent_temperature, bool) or not isinstance(latent_temperature, (int, float)):
@@ -970,9 +1203,15 @@ class B200FlowProposal:
         self._prepare_truncation(worst_point)
         eng = self._get_engine()
         host_prior = None if self._log_prior_const is not None else self.log_prior
-        rows, n_proposed, n_accepted = eng.run(
-            int(n_samples), int(self.drawsize), max_samples=max_samples, host_prior=host_prior
-        )
+        if self.accumulate_weights:
+            # flowproposal.py:471-490,504-512 (raises if the prior is not on the device)
+            rows, n_proposed, n_accepted = eng.run_accumulate(
+                int(n_samples), int(self.drawsize), max_samples=max_samples
+            )
+        else:
+            rows, n_proposed, n_accepted = eng.run(
+                int(n_samples), int(self.drawsize), max_samples=max_samples, host_prior=host_prior
+            )
         self.x = rows
         self.samples = rows
         if host_prior is not None and len(rows):

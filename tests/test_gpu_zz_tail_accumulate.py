@@ -1,0 +1,387 @@
+"""GPU parity of the two populate variants added after the round's last GPU session -- written
+and CPU-checked (oracle pins, host-compiled row function, loop control) without access to a
+GPU, so this file sorts last:
+
+* the non-affine populate tail (``nb200_reparam_tail`` + ``nb200_populate_accept_x64``,
+  ``GeneralPopulateEngine``): logit / log post-rescaling and boundary inversion,
+  reparameterisations/rescale.py:570-590,635-660;
+* ``accumulate_weights`` (``nb200_sum_exp``, ``PopulateEngine.run_accumulate``),
+  flowproposal.py:414-417,471-490,504-512.
+"""
+
+import numpy as np
+import pytest
+import torch
+from conftest import load_golden, reference_or_skip
+
+pytestmark = pytest.mark.gpu
+
+KIND = np.array([0, 1, 2, 3, 1, 2, 0], dtype=np.int32)
+SCALE = np.array([1.5, 8.0, -3.0, 2.0, 0.5, 4.0, -0.7])
+SHIFT = np.array([0.2, -4.0, 5.0, -1.0, 0.0, -2.0, 0.3])
+LO = np.array([-3.0, -4.0, 2.0, -1.0, 0.0, -2.0, -2.0])
+HI = np.array([3.0, 4.0, 5.0, 9.0, 0.5, 1.5, 2.0])
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _tail_inputs(n, d=7, seed=5):
+    rng = np.random.default_rng(seed)
+    xp = rng.normal(0.0, 1.0, size=(n, d)).astype(np.float32)
+    if n >= 100:
+        xp[:50, 1] = rng.choice([-60.0, 45.0, 800.0, -800.0], size=50)  # saturated sigmoid
+        xp[50:80, 3] = 900.0  # exp overflow
+    logq_flow = rng.normal(-8.0, 2.0, size=n)
+    logq_flow[rng.random(n) < 0.1] = np.nan  # rows the draw kernel already dropped
+    return xp, logq_flow
+
+
+@pytest.mark.parametrize("n,min_log_q", [(5000, None), (100_003, -12.0), (1, None)])
+def test_reparam_tail_kernel_matches_oracle(n, min_log_q):
+    from nessai_b200 import _lib
+    from oracle.reparam_numpy import tail_rows
+
+    lib = _lib.load()
+    xp, logq_flow = _tail_inputs(n)
+    x_ref, lq_ref, lw_ref, valid = tail_rows(xp, logq_flow, kind=KIND, scale=SCALE, shift=SHIFT, lo=LO, hi=HI,
+                                             log_prior_const=-2.5, min_log_q=min_log_q)
+    d_xp, d_kind = _dev(xp), _dev(KIND)
+    d_c = [_dev(a) for a in (SCALE, SHIFT, LO, HI)]
+    d_logq, d_logw = _dev(logq_flow.copy()), torch.empty(n, dtype=torch.float64, device="cuda")
+    d_x64 = torch.empty((n, 7), dtype=torch.float64, device="cuda")
+    d_stats = _dev(np.array([-np.inf, 0.0]))
+    _lib.check(lib.nb200_reparam_tail(
+        n, 7, d_xp.data_ptr(), d_kind.data_ptr(), *(a.data_ptr() for a in d_c), -2.5,
+        float("nan") if min_log_q is None else min_log_q, d_logq.data_ptr(), d_logw.data_ptr(),
+        d_x64.data_ptr(), d_stats.data_ptr(), _stream()), "nb200_reparam_tail")
+    torch.cuda.synchronize()
+    logq, logw, x64, stats = (t.cpu().numpy() for t in (d_logq, d_logw, d_x64, d_stats))
+    np.testing.assert_array_equal(~np.isnan(logw), valid)
+    np.testing.assert_array_equal(~np.isnan(logq), valid)
+    with np.errstate(all="ignore"):
+        # device libm vs numpy: a few ulp in exp / log1p
+        np.testing.assert_allclose(x64, x_ref, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(logq[valid], lq_ref[valid], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(logw[valid], lw_ref[valid], rtol=1e-12, atol=1e-12)
+    assert stats[1] == valid.sum()
+    if valid.any():
+        assert stats[0] == logw[valid].max()
+
+
+def test_sum_exp_and_x64_accept_match_numpy():
+    from nessai_b200 import _lib
+    from nessai_b200.livepoint import get_dtype
+    from oracle.philox_numpy import accept_uniform
+
+    lib = _lib.load()
+    n, d, seed, offset = 70_001, 7, 987654321, 12345
+    rng = np.random.default_rng(1)
+    logw = rng.normal(-3.0, 0.5, size=n)
+    logw[rng.random(n) < 0.3] = np.nan
+    x64 = rng.normal(size=(n, d))
+    valid = ~np.isnan(logw)
+    mx = logw[valid].max()
+    d_logw, d_x64, d_max = _dev(logw), _dev(x64), _dev(np.array([mx, 0.0]))
+    parts = torch.full((296,), float("nan"), dtype=torch.float64, device="cuda")
+    _lib.check(lib.nb200_sum_exp(d_logw.data_ptr(), n, d_max.data_ptr(), parts.data_ptr(), 296, _stream()), "sum_exp")
+    got = float(parts.sum().cpu())
+    np.testing.assert_allclose(got, np.exp(logw[valid] - mx).sum(), rtol=1e-12)
+    # bit-reproducible: no atomics
+    parts2 = torch.empty_like(parts)
+    _lib.check(lib.nb200_sum_exp(d_logw.data_ptr(), n, d_max.data_ptr(), parts2.data_ptr(), 296, _stream()), "sum_exp")
+    assert torch.equal(parts, parts2)
+    # rejection step + compaction from float64 rows
+    names = [f"x{i}" for i in range(d)]
+    dtype = get_dtype(names)
+    from nessai_b200.livepoint import empty_structured_array
+
+    tmpl = _dev(empty_structured_array(1, dtype=dtype).view(np.uint8).copy())
+    offs = np.asarray([dtype.fields[nm][1] for nm in names] + [dtype.fields["logP"][1]], dtype=np.int32)
+    rows = torch.zeros(n * dtype.itemsize, dtype=torch.uint8, device="cuda")
+    counts = torch.zeros(2, dtype=torch.int64, device="cuda")
+    scratch = torch.empty(n // 1024 + 2, dtype=torch.int64, device="cuda")
+    cap = 3000  # 6134 rows pass the rejection step (computed with the numpy Philox)
+    _lib.check(lib.nb200_populate_accept_x64(
+        n, d, d_x64.data_ptr(), d_logw.data_ptr(), None, d_max.data_ptr(), seed, offset, -1.25,
+        tmpl.data_ptr(), dtype.itemsize, offs.ctypes.data, int(dtype.fields["logL"][1]), rows.data_ptr(), cap, 0,
+        counts.data_ptr(), scratch.data_ptr(), _stream()), "accept_x64")
+    c = counts.cpu().numpy()
+    u = accept_uniform(seed, offset + np.arange(n))
+    margin = (logw - mx) - np.log(u)
+    acc = valid & (margin > 0)
+    assert not (valid & (np.abs(margin) < 1e-9)).any()
+    assert c[0] == acc.sum() == 6134 and c[1] == cap
+    rec = rows[: cap * dtype.itemsize].cpu().numpy().view(dtype)
+    got = np.stack([rec[nm] for nm in names], axis=-1)
+    np.testing.assert_array_equal(got, x64[acc][:cap])  # copied bit for bit, draw order
+    assert np.all(rec["logP"] == -1.25) and np.all(np.isnan(rec["logL"])) and np.all(rec["it"] == 0)
+
+
+def _general_engine(tmp_path, name="c2_realnvp_mlp", seed=77):
+    from nessai_b200.flowmodel import B200FlowModel
+    from nessai_b200.livepoint import get_dtype
+    from nessai_b200.proposal import GeneralPopulateEngine
+
+    g, cfg, sd = load_golden(name)
+    D = cfg["n_inputs"]
+    fm = B200FlowModel(flow_config=cfg, training_config=dict(device_tag="cuda:0"), output=str(tmp_path))
+    fm.initialise()
+    fm.model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    fm.model.eval()
+    names = [f"x{i}" for i in range(D)]
+    eng = GeneralPopulateEngine(fm, names, get_dtype(names))
+    eng.seed = seed
+    kind = np.arange(D) % 4  # identity, sigmoid, abs, exp in turn
+    scale = np.where(kind == 1, 8.0, np.where(kind == 3, 0.5, np.where(kind == 2, -2.0, 1.4)))
+    shift = np.where(kind == 1, -4.0, np.where(kind == 2, 3.0, 0.1))
+    lo = np.where(kind == 1, -4.0, np.where(kind == 2, -3.0, np.where(kind == 3, 0.0, -5.0)))
+    hi = np.where(kind == 1, 4.0, np.where(kind == 2, 3.0, np.where(kind == 3, 6.0, 5.0)))
+    return eng, cfg, sd, (kind.astype(np.int32), scale, shift, lo, hi)
+
+
+def test_general_engine_turn_and_loop_match_oracle(tmp_path):
+    """draw kernel (identity map) + tail kernel + x64 rejection step against the float64 flow
+    oracle followed by the tail oracle, on the same Philox rows."""
+    from oracle.flow_numpy import NumpyFlow
+    from oracle.philox_numpy import accept_uniform, latent_normals
+    from oracle.reparam_numpy import tail_rows
+
+    n = 20000
+    eng, cfg, sd, (kind, scale, shift, lo, hi) = _general_engine(tmp_path)
+    D = cfg["n_inputs"]
+    lpc, r_max = -3.0, 4.9
+    eng.configure(kind, scale, shift, lo, hi, lpc, r_max, 1.0, min_log_q=-27.0)  # cuts ~7 % of the rows
+    eng._ensure(n, n, True)
+    eng.draw_turn(n, want_z=True)
+    z = eng.d_z[:n].cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(z, latent_normals(eng.seed, np.arange(n), D), atol=2e-5, rtol=1e-5)
+    x = eng.physical_x(n).cpu().numpy()
+    logq, logw = eng.d_logq[:n].cpu().numpy(), eng.d_logw[:n].cpu().numpy()
+    stats = eng.d_stats.cpu().numpy()
+    nf = NumpyFlow(sd, ftype="realnvp", net="mlp", hidden_features=cfg["n_neurons"])
+    xp64, lq_flow = nf.sample_and_log_prob(z)
+    keep = np.sqrt(np.sum(z**2, axis=1)) <= r_max
+    x_ref, lq_ref, lw_ref, valid = tail_rows(xp64, np.where(keep, lq_flow, np.nan), kind=kind, scale=scale,
+                                             shift=shift, lo=lo, hi=hi, log_prior_const=lpc, min_log_q=-27.0)
+    # rows within fp32 rounding of the radius, of a bound or of min_log_q may flip
+    edge = (np.abs(np.sqrt(np.sum(z**2, axis=1)) - r_max) < 1e-4) | np.any(
+        (np.abs(x_ref - lo) < 2e-3) | (np.abs(x_ref - hi) < 2e-3), axis=1) | (np.abs(lq_ref + 27.0) < 1e-3)
+    dev_valid = ~np.isnan(logw)
+    assert np.array_equal(dev_valid[~edge], valid[~edge]) and 0.02 * n < valid.sum() < 0.98 * n
+    both = dev_valid & valid
+    np.testing.assert_allclose(x[both], x_ref[both], rtol=2e-4, atol=2e-4)  # x' is fp32
+    np.testing.assert_allclose(logq[both], lq_ref[both], rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose(logw[both], lw_ref[both], rtol=1e-4, atol=2e-4)
+    assert stats[1] == dev_valid.sum() and stats[0] == logw[dev_valid].max()
+    # rejection step: float64 rows copied into the records in draw order
+    counts = eng.accept_turn(n, 0).cpu().numpy()
+    u = accept_uniform(eng.seed, np.arange(n))
+    margin = (logw - stats[0]) - np.log(u)
+    acc = dev_valid & (margin > 0)
+    if not (dev_valid & (np.abs(margin) < 1e-9)).any():
+        assert counts[0] == acc.sum()
+        rows = eng._gather_rows(int(counts[1]), n)
+        got = np.stack([rows[nm] for nm in eng.names], axis=-1)
+        np.testing.assert_array_equal(got, x[acc])
+        assert np.all(rows["logP"] == lpc)
+    # the whole (pipelined) loop of the base class over the overridden turn
+    eng._turn_rows = 0
+    # (~6 % of the draws are accepted: about five turns, the later ones drawn speculatively)
+    rows, n_proposed, n_accepted = eng.run(5000, n, max_samples=400 * n)
+    assert len(rows) == 5000 and n_accepted >= 5000 and n_proposed % n == 0 and n_proposed >= 3 * n
+    a = np.stack([rows[nm] for nm in eng.names], axis=-1)
+    assert np.all((a >= lo) & (a <= hi))
+    # a serial run from the same counter returns the same bytes
+    eng._turn_rows = 0
+    rows2, p2, a2 = eng._run_serial(5000, n, 400 * n, None, False)
+    assert (p2, a2) == (n_proposed, n_accepted) and rows2.tobytes() == rows.tobytes()
+
+
+def test_identity_kinds_reproduce_the_fused_affine_path(tmp_path):
+    """With every map affine the general engine (draw + tail + x64 accept) must agree with
+    the fused affine tail of the draw kernel: same dropped rows, same weights, same pool."""
+    from nessai_b200.proposal import PopulateEngine
+
+    n = 30000
+    eng, cfg, sd, _ = _general_engine(tmp_path, seed=5)
+    D = cfg["n_inputs"]
+    scale, shift = np.full(D, 1.3), np.linspace(-0.5, 0.5, D)
+    lo, hi = np.full(D, -4.0), np.full(D, 4.0)
+    lpc = -D * np.log(8.0)
+    eng.configure(np.zeros(D, dtype=np.int32), scale, shift, lo, hi, lpc, 4.9)
+    ref = PopulateEngine(eng.flow, eng.names, eng.row_dtype)
+    ref.seed = eng.seed
+    ref.configure(scale, shift, lo, hi, lpc, 4.9)
+    eng.draw_turn(n)
+    ref.draw_turn(n)
+    lw_a, lw_b = eng.d_logw[:n].cpu().numpy(), ref.d_logw[:n].cpu().numpy()
+    np.testing.assert_array_equal(np.isnan(lw_a), np.isnan(lw_b))
+    ok = ~np.isnan(lw_a)
+    np.testing.assert_allclose(lw_a[ok], lw_b[ok], rtol=1e-12, atol=1e-10)
+    np.testing.assert_allclose(eng.physical_x(n).cpu().numpy(), ref.physical_x(n).cpu().numpy(), rtol=1e-14, atol=1e-14)
+    np.testing.assert_array_equal(eng.d_stats.cpu().numpy()[1], ref.d_stats.cpu().numpy()[1])
+
+
+def _affine_proposal(tmp_path, pool, **kw):
+    from nessai_b200.livepoint import numpy_array_to_live_points
+    from nessai_b200.proposal import B200FlowProposal
+
+    g, cfg, sd = load_golden("c2_realnvp_mlp")
+    d = cfg["n_inputs"]
+
+    class Box:
+        names = [f"x{i}" for i in range(d)]
+        bounds = {n: [-4.0, 4.0] for n in names}
+
+        def log_prior(self, x):
+            a = np.stack([x[n] for n in self.names], axis=-1)
+            return np.where(np.all((a >= -4) & (a <= 4), axis=-1), -d * np.log(8.0), -np.inf)
+
+        def log_likelihood(self, x):
+            return -0.5 * np.sum(np.stack([x[n] for n in self.names], axis=-1) ** 2, axis=-1)
+
+    model = Box()
+    torch.manual_seed(11)
+    prop = B200FlowProposal(model, rng=np.random.default_rng(3), flow_config=cfg,
+                            training_config=dict(device_tag="cuda:0"), output=str(tmp_path),
+                            poolsize=pool, drawsize=pool, **kw)
+    prop.initialise()
+    live = numpy_array_to_live_points(1.5 * np.random.default_rng(5).standard_normal((500, d)) + 0.3, model.names)
+    prop.check_state(live)
+    prop.flow.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    prop.flow.model.eval()
+    return prop, model, cfg, sd, live
+
+
+@pytest.mark.parametrize("n_samples,max_turns", [(1200, 400), (10**6, 2)])
+def test_accumulate_device_loop_matches_oracle(tmp_path, n_samples, max_turns):
+    """run_accumulate: every turn lands in its slot with the draws of its own Philox rows, the
+    expected pool size is the sum over all slots, the loop takes the reference's decisions and
+    the final rejection step keeps samples[accept][:n_samples] in draw order."""
+    from nessai_b200.proposal import AccumulateControl
+    from oracle.flow_numpy import NumpyFlow
+    from oracle.philox_numpy import accept_uniform, latent_normals
+    from oracle.populate_numpy import populate_turn
+
+    drawsize = 10_000
+    max_samples = max_turns * drawsize - 1  # the loop ends after max_turns turns at the latest
+    prop, model, cfg, sd, live = _affine_proposal(tmp_path, drawsize, accumulate_weights=True)
+    D = cfg["n_inputs"]
+    eng = prop._get_engine()
+    eng.seed = 4242
+    t0 = eng._turn_rows
+    rows, n_proposed, n_accepted = eng.run_accumulate(n_samples, drawsize, max_samples=max_samples)
+    info = eng.last_accumulate
+    turns, stride = len(info["draw_offsets"]), info["stride"]
+    assert stride == 10_016 and info["n_local"] == drawsize and n_proposed == turns * drawsize
+    assert info["draw_offsets"][0] == t0 and 1 <= turns <= max_turns
+    lw = eng.d_logw[: turns * stride].cpu().numpy()
+    xs = (eng.d_xp[: turns * stride].to(torch.float64) * eng.d_scale + eng.d_shift).cpu().numpy()
+    stats = eng.d_stats.cpu().numpy()
+    valid = ~np.isnan(lw)
+    assert stats[1] == valid.sum() and stats[0] == lw[valid].max()
+    nf = NumpyFlow(sd, ftype="realnvp", net="mlp", hidden_features=cfg["n_neurons"])
+    ctl = AccumulateControl(n_samples, max_samples)
+    n_rej = 0
+    for t in range(turns):
+        slot = slice(t * stride, t * stride + drawsize)
+        assert np.all(np.isnan(lw[t * stride + drawsize : (t + 1) * stride]))  # slot padding never counts
+        z = latent_normals(eng.seed, info["draw_offsets"][t] + np.arange(drawsize), D)
+        o = populate_turn(nf, z, scale=prop.scale, shift=prop.shift, lo=-4.0, hi=4.0,
+                          log_prior_const=-D * np.log(8.0), r_max=prop.radius)
+        edge = (np.abs(np.sqrt(np.sum(z**2, axis=1)) - prop.radius) < 1e-4) | np.any(
+            np.abs(np.abs(o["x"]) - 4.0) < 1e-3, axis=1)
+        assert np.array_equal(valid[slot][~edge], o["valid"][~edge])
+        both = valid[slot] & o["valid"]
+        np.testing.assert_allclose(lw[slot][both], o["log_w"][both], rtol=1e-4, atol=1e-4)
+        # the loop control, replayed on the device's own weights
+        upto = lw[: (t + 1) * stride]
+        v = ~np.isnan(upto)
+        mx = upto[v].max()
+        n_expected = np.exp(upto[v] - mx).sum()
+        np.testing.assert_allclose(info["n_expected"][t], n_expected, rtol=1e-10)
+        assert ctl.go_on()
+        if ctl.turn_drawn(drawsize, bool(valid[slot].any()), info["n_expected"][t]):
+            base, nrows = info["rejects"][n_rej]
+            n_rej += 1
+            assert nrows == (t + 1) * stride
+            ctl.rejected(int((v & ((upto - mx) > np.log(accept_uniform(eng.seed, base + np.arange(nrows))))).sum()))
+        ctl.end_turn()
+    assert not ctl.go_on()
+    if ctl.stale:
+        n_rej += 1
+    assert n_rej == len(info["rejects"])
+    # the last rejection step is the pool
+    base, nrows = info["rejects"][-1]
+    assert nrows == turns * stride
+    margin = (lw - stats[0]) - np.log(accept_uniform(eng.seed, base + np.arange(nrows)))
+    acc = valid & (margin > 0)
+    if not (valid & (np.abs(margin) < 1e-9)).any():
+        assert n_accepted == acc.sum() and len(rows) == min(n_accepted, n_samples)
+        got = np.stack([rows[nm] for nm in model.names], axis=-1)
+        np.testing.assert_allclose(got, xs[acc][:n_samples], rtol=1e-12, atol=1e-14)
+    if n_samples == 1200:
+        assert n_accepted >= n_samples and turns >= 2  # acceptance of this flow is ~3 %: several turns
+    else:
+        assert turns == max_turns and len(rows) < n_samples  # ended by max_samples
+    # fresh uniforms for every rejection step: the counter blocks do not overlap
+    spans = sorted((b, b + r) for b, r in info["rejects"])
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_accumulate_through_the_standalone_proposal(tmp_path):
+    drawsize = 20_000
+    prop, model, cfg, sd, live = _affine_proposal(tmp_path, drawsize, accumulate_weights=True)
+    prop.populate(live[0], n_samples=2000, max_samples=200 * drawsize)
+    assert prop.populated and len(prop.samples) == 2000 and len(prop.indices) == 2000
+    a = np.stack([prop.samples[n] for n in model.names], axis=-1)
+    assert np.all((a >= -4) & (a <= 4)) and np.all(np.isfinite(prop.samples["logL"]))
+    assert 0 < prop.population_acceptance < 1
+    # the pool follows the weights: the importance-weighted mean of the draws predicts the pool mean
+    eng = prop._engine
+    turns, stride = len(eng.last_accumulate["draw_offsets"]), eng.last_accumulate["stride"]
+    lw = eng.d_logw[: turns * stride].cpu().numpy()
+    xs = (eng.d_xp[: turns * stride].to(torch.float64) * eng.d_scale + eng.d_shift).cpu().numpy()
+    ok = ~np.isnan(lw)
+    w = np.exp(lw[ok] - lw[ok].max())
+    mean_w = (xs[ok] * w[:, None]).sum(0) / w.sum()
+    ess = w.sum() ** 2 / (w**2).sum()
+    sd_w = np.sqrt(((xs[ok] - mean_w) ** 2 * w[:, None]).sum(0) / w.sum())
+    assert np.all(np.abs(a.mean(0) - mean_w) < 6 * sd_w * np.sqrt(1 / 2000 + 1 / ess))
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("variant", ["logit_and_default", "accumulate"])
+def test_flowsampler_variants_run_on_the_device_loop(tmp_path, variant):
+    """The reference's FlowSampler, unmodified, with a logit + rescale-to-bounds
+    reparameterisation (GeneralPopulateEngine) and with accumulate_weights=True
+    (run_accumulate): the device loop is the one that runs."""
+    reference_or_skip()
+    from nessai.flowsampler import FlowSampler
+    from test_gpu_nessai_plugin import make_model
+
+    from nessai_b200.nessai_plugin import B200NessaiFlowProposal
+    from nessai_b200.proposal import GeneralPopulateEngine, PopulateEngine
+
+    kw = (dict(reparameterisations={"x": "logit", "y": "default"}) if variant == "logit_and_default"
+          else dict(accumulate_weights=True))
+    fs = FlowSampler(
+        make_model(), output=str(tmp_path), resume=False, seed=1234, nlive=200, plot=False,
+        flow_proposal_class=B200NessaiFlowProposal, flow_config=dict(n_blocks=2),
+        training_config=dict(max_epochs=50, patience=10), maximum_uninformed=200,
+        max_iteration=600, poolsize=2000, checkpointing=False, **kw,
+    )
+    fs.run(plot=False, save=False)
+    prop = fs.ns._flow_proposal
+    assert prop.training_count >= 1 and prop.populated_count >= 1
+    if variant == "logit_and_default":
+        assert type(prop._engine) is GeneralPopulateEngine
+    else:
+        assert type(prop._engine) is PopulateEngine and getattr(prop._engine, "last_accumulate", None)
+    assert np.isfinite(fs.ns.log_evidence) and -9.0 < fs.ns.log_evidence < -4.0

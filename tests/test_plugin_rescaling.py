@@ -46,6 +46,9 @@ CASES = {
     "rescaletobounds_fixed_offset": dict(
         reparameterisations={"rescaletobounds": dict(parameters=[f"x{i}" for i in range(D)], update_bounds=False,
                                                      offset=True, rescale_bounds=[0.0, 1.0])}),
+    # boundary inversion whose edge detection found no edge (the data sit away from the bounds):
+    # the reference then rescales to [-1, 1] (rescale.py:609-617), a diagonal affine
+    "inversion_no_edge": dict(reparameterisations={"inversion": dict(parameters=[f"x{i}" for i in range(D)])}),
     "mixed": dict(reparameterisations={"x0": "default", "x1": "z-score", "x2": "null",
                                        "x3": {"reparameterisation": "scale", "scale": 2.5}}),
 }
@@ -81,7 +84,6 @@ def test_diagonal_rescaling_is_the_reference_map(tmp_path, case):
 
 REFUSED = {
     "logit": dict(reparameterisations={"logit": dict(parameters=[f"x{i}" for i in range(D)])}),
-    "inversion": dict(reparameterisations={"inversion": dict(parameters=[f"x{i}" for i in range(D)])}),
     "one_logit": dict(reparameterisations={"x0": "logit", "x1": "default", "x2": "default", "x3": "default"}),
 }
 

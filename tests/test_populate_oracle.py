@@ -189,3 +189,74 @@ def test_oracle_accumulate_loop_matches_reference_populate(tmp_path):
     if len(x) == len(ref):
         np.testing.assert_allclose(x, ref, rtol=1e-4, atol=1e-4)
     assert log_n_expected >= np.log(n_samples)
+
+
+def test_accumulate_control_replays_reference_loop(tmp_path):
+    """``nessai_b200.proposal.AccumulateControl`` (the host-side loop control of the device
+    accumulate path) takes the reference's decisions: fed the recorded draws it runs the
+    rejection step on the same turns, stops on the same turn and repeats the last rejection
+    step exactly when the reference does."""
+    reference_or_skip()
+    from nessai_b200.proposal import AccumulateControl
+    from oracle.flow_numpy import NumpyFlow
+    from oracle.populate_numpy import populate_turn
+
+    for drawsize, n_samples, max_samples in [(4000, 300, 160000), (3000, 5000, 7000)]:
+        prop, model, live, sd, cfg, zs, rng = reference_proposal(tmp_path, drawsize, accumulate_weights=True)
+        D = cfg["n_inputs"]
+        prop.training_data = live
+        n_blocks0 = len(rng.blocks)
+        prop.populate(live[0], n_samples=n_samples, plot=False, max_samples=max_samples)
+        us = rng.blocks[n_blocks0:]
+        scale, shift = diagonal_rescale(prop, D)
+        nf = NumpyFlow(sd, ftype="realnvp", net="mlp", hidden_features=cfg["n_neurons"])
+        radius = {r.name: r for r in prop._truncation_scheme.rules}["latent_radius"].threshold
+        zi, ui = iter(zs), iter(us)
+        ctl = AccumulateControl(n_samples, max_samples)
+        lws, const = [], -np.inf
+
+        def reject():
+            lw = np.concatenate(lws)
+            u = next(ui)
+            assert len(u) == len(lw)
+            ctl.rejected(int(((lw - const) > np.log(u)).sum()))
+
+        while ctl.go_on():
+            t = populate_turn(nf, next(zi), scale=scale, shift=shift, lo=-4.0, hi=4.0,
+                              log_prior_const=-D * np.log(8.0), r_max=radius)
+            v = t["valid"]
+            if v.any():
+                lws.append(t["log_w"][v])
+                const = max(const, float(t["log_w"][v].max()))
+            n_expected = float(np.sum(np.exp(np.concatenate(lws) - const))) if lws else 0.0
+            if ctl.turn_drawn(drawsize, bool(v.any()), n_expected):
+                reject()
+            ctl.end_turn()
+        if ctl.stale:
+            reject()
+        assert next(zi, None) is None and next(ui, None) is None
+        assert ctl.n_proposed == len(zs) * drawsize
+        assert abs(ctl.n_accepted - round(prop.population_acceptance * ctl.n_proposed)) <= 1
+        if max_samples == 7000:  # ended by max_samples (3 turns of 3000), pool short of n_samples
+            assert ctl.stopped_on_max_samples and len(zs) == 3 and prop.samples.size < n_samples
+
+
+def test_accumulate_control_edge_cases():
+    from nessai_b200.proposal import AccumulateControl
+
+    c = AccumulateControl(100, 1000)
+    assert c.go_on()
+    assert not c.turn_drawn(400, False, 0.0) and not c.stale  # nothing survived: only max_samples is checked
+    c.end_turn()
+    assert c.go_on() and c.n_proposed == 400
+    assert not c.turn_drawn(400, True, 99.9) and c.stale  # expected pool still short
+    c.end_turn()
+    assert c.turn_drawn(400, True, 100.0)  # log(100) >= log(100)
+    c.rejected(97)
+    c.end_turn()
+    assert not c.stale and c.stopped_on_max_samples and not c.go_on()  # 1200 > 1000
+    c = AccumulateControl(10, 10**6)
+    assert c.turn_drawn(50, True, 20.0)
+    c.rejected(12)
+    c.end_turn()
+    assert not c.go_on() and not c.stale and c.n_accepted == 12
