@@ -96,11 +96,13 @@ def populate_loop(flow, draw_z, draw_u, n_samples, drawsize, max_samples=1_000_0
     return x, n_proposed, n_accepted
 
 
-def populate_loop_accumulate(flow, draw_z, draw_u, n_samples, drawsize, max_samples=1_000_000, **turn_kwargs):
+def populate_loop_accumulate(flow, draw_z, draw_u, n_samples, drawsize, max_samples=1_000_000, on_valid=None,
+                             **turn_kwargs):
     """flowproposal.py:414-417,431-490,504-512 (``accumulate_weights=True``).  ``draw_u(m)`` is
     called exactly where the reference calls ``rng.random(len(log_weights))``: with ``m`` = the
     number of valid rows accumulated so far, every time the expected pool size reaches
-    ``n_samples``, and once more after the loop if the last rejection step is stale.  Returns
+    ``n_samples``, and once more after the loop if the last rejection step is stale.
+    ``on_valid(mask)`` (optional) is told every turn's surviving-row mask.  Returns
     ``(x_accepted[: n_samples], n_proposed, n_accepted, log_n_expected)``."""
     xs, lws = [], []
     log_constant, log_n_expected = -np.inf, -np.inf
@@ -111,6 +113,8 @@ def populate_loop_accumulate(flow, draw_z, draw_u, n_samples, drawsize, max_samp
         t = populate_turn(flow, draw_z(drawsize), **turn_kwargs)
         n_proposed += drawsize
         v = t["valid"]
+        if on_valid is not None:
+            on_valid(v)
         if not v.any():  # flowproposal.py:436-439,449-453: nothing survived the truncations
             if n_proposed > max_samples:
                 break

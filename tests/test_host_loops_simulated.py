@@ -1,0 +1,305 @@
+"""Host logic of the populate loops on a SIMULATED device (tests/_simdevice.py: the C-ABI entry
+points answered by the float64 oracle through the same raw pointers).  Covers what a GPU is not
+needed for: slot offsets and Philox counter bookkeeping of ``run_accumulate``, the turn sequence
+of ``GeneralPopulateEngine`` (draw -> tail -> float64-row rejection step), argument order of
+every call, record layout, and the engine selection / configuration of the nessai plugin."""
+
+import numpy as np
+import pytest
+from conftest import load_golden, reference_or_skip
+
+import _simdevice
+
+
+def _flow():
+    from oracle.flow_numpy import NumpyFlow
+
+    g, cfg, sd = load_golden("c2_realnvp_mlp")
+    return NumpyFlow(sd, ftype="realnvp", net="mlp", hidden_features=cfg["n_neurons"]), cfg["n_inputs"]
+
+
+def _zscore(D):
+    live = 1.5 * np.random.default_rng(5).standard_normal((500, D)) + 0.3
+    return live.std(0), live.mean(0)
+
+
+@pytest.mark.parametrize("n_samples,max_samples", [(150, 10**6), (10**5, 2999)])
+def test_run_accumulate_matches_oracle_loop(monkeypatch, n_samples, max_samples):
+    from nessai_b200.livepoint import get_dtype
+    from nessai_b200.proposal import PopulateEngine
+    from oracle.philox_numpy import accept_uniform, latent_normals
+    from oracle.populate_numpy import populate_loop_accumulate
+
+    sim = _simdevice.install(monkeypatch)
+    nf, D = _flow()
+    names = [f"x{i}" for i in range(D)]
+    eng = PopulateEngine(_simdevice.SimFlowModel(nf, D), names, get_dtype(names))
+    scale, shift = _zscore(D)
+    lpc, radius, drawsize = -D * np.log(8.0), 4.9, 1000
+    eng.configure(scale, shift, np.full(D, -4.0), np.full(D, 4.0), lpc, radius)
+    eng.seed = 4242
+    eng._turn_rows = 12345  # an engine that has populated before
+    rows, n_proposed, n_accepted = eng.run_accumulate(n_samples, drawsize, max_samples=max_samples)
+    info = eng.last_accumulate
+    assert info["stride"] == 1024 and info["draw_offsets"][0] == 12345
+    # ---- the oracle loop on the same Philox rows; its uniforms are the slot rows' own counters
+    state = dict(turn=0, masks=[], reject=0)
+
+    def draw_z(n):
+        z = latent_normals(eng.seed, info["draw_offsets"][state["turn"]] + np.arange(n), D)
+        state["turn"] += 1
+        return z
+
+    def on_valid(valid):
+        state["masks"].append(valid)
+
+    def draw_u(m):
+        base, nrows = info["rejects"][state["reject"]]
+        state["reject"] += 1
+        assert nrows == len(state["masks"]) * info["stride"]
+        slot_rows = np.concatenate([t * info["stride"] + np.flatnonzero(v) for t, v in enumerate(state["masks"])])
+        assert len(slot_rows) == m
+        return accept_uniform(eng.seed, base + slot_rows)
+
+    x, p, a, log_n_exp = populate_loop_accumulate(
+        nf, draw_z, draw_u, n_samples, drawsize, max_samples=max_samples, on_valid=on_valid,
+        scale=scale, shift=shift, lo=-4.0, hi=4.0, log_prior_const=lpc, r_max=radius)
+    assert (n_proposed, n_accepted) == (p, a)
+    assert state["turn"] == len(info["draw_offsets"]) and state["reject"] == len(info["rejects"])
+    got = np.stack([rows[nm] for nm in names], axis=-1)
+    assert got.shape == x.shape and len(rows) == min(a, n_samples)
+    np.testing.assert_allclose(got, x, rtol=1e-6, atol=1e-6)  # x' crosses the C ABI as fp32
+    assert np.all(rows["logP"] == lpc)
+    np.testing.assert_allclose(np.log(info["n_expected"][-1]), log_n_exp, rtol=1e-12)
+    # ---- counters: every draw and every rejection step has its own block, in order
+    spans = [(o, o + drawsize) for o in info["draw_offsets"]] + [(b, b + r) for b, r in info["rejects"]]
+    spans.sort()
+    assert all(s[1] <= t[0] for s, t in zip(spans, spans[1:])) and eng._turn_rows == spans[-1][1]
+    if max_samples == 2999:
+        assert len(info["draw_offsets"]) == 3 and len(rows) < n_samples  # ended by max_samples
+    else:
+        assert len(info["draw_offsets"]) >= 2 and len(rows) == n_samples
+    # the engine is still usable for the ordinary loop afterwards (buffers, counters)
+    rows2, p2, a2 = eng.run(50, drawsize, max_samples=10**6)
+    assert len(rows2) == 50 and a2 >= 50
+    assert [c[0] for c in sim.calls].count("sum_exp") == len(info["draw_offsets"])
+
+
+def test_general_engine_loop_matches_oracle(monkeypatch):
+    from nessai_b200.livepoint import get_dtype
+    from nessai_b200.proposal import GeneralPopulateEngine
+    from oracle.philox_numpy import accept_uniform, latent_normals
+    from oracle.reparam_numpy import tail_rows
+
+    sim = _simdevice.install(monkeypatch)
+    nf, D = _flow()
+    names = [f"x{i}" for i in range(D)]
+    eng = GeneralPopulateEngine(_simdevice.SimFlowModel(nf, D), names, get_dtype(names))
+    kind = (np.arange(D) % 4).astype(np.int32)
+    scale = np.where(kind == 1, 8.0, np.where(kind == 3, 0.5, np.where(kind == 2, -2.0, 1.4)))
+    shift = np.where(kind == 1, -4.0, np.where(kind == 2, 3.0, 0.1))
+    lo = np.where(kind == 1, -4.0, np.where(kind == 2, -3.0, np.where(kind == 3, 0.0, -5.0)))
+    hi = np.where(kind == 1, 4.0, np.where(kind == 2, 3.0, np.where(kind == 3, 6.0, 5.0)))
+    lpc, r_max, mlq, n = -3.0, 4.9, -27.0, 2000
+    eng.configure(kind, scale, shift, lo, hi, lpc, r_max, 1.0, min_log_q=mlq)
+    eng.seed = 77
+    rows, n_proposed, n_accepted = eng.run(300, n, max_samples=10**6)
+    turns = n_proposed // n
+    assert [c[0] for c in sim.calls] == ["draw", "tail", "accept_x64"] * turns and turns >= 2
+    # oracle: same rows of the Philox stream, turn by turn
+    kept, total = [], 0
+    for t in range(turns):
+        z = latent_normals(77, t * n + np.arange(n), D)
+        with np.errstate(all="ignore"):
+            xp, lq_flow = nf.sample_and_log_prob(z)
+        keep = np.sqrt(np.sum(z**2, axis=1)) <= r_max
+        x, lq, lw, valid = tail_rows(xp.astype(np.float32), np.where(keep, lq_flow, np.nan), kind=kind, scale=scale,
+                                     shift=shift, lo=lo, hi=hi, log_prior_const=lpc, min_log_q=mlq)
+        u = accept_uniform(77, t * n + np.arange(n))
+        acc = valid & ((lw - lw[valid].max()) > np.log(u))
+        kept.append(x[acc][: max(300 - total, 0)])
+        total += int(acc.sum())
+    assert total == n_accepted and len(rows) == 300
+    got = np.stack([rows[nm] for nm in names], axis=-1)
+    np.testing.assert_allclose(got, np.concatenate(kept), rtol=1e-12, atol=1e-12)
+    assert np.all((got >= lo) & (got <= hi)) and np.all(rows["logP"] == lpc)
+    with pytest.raises(NotImplementedError):
+        eng.run_accumulate(10, n)
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("variant", ["zscore", "rescaletobounds", "logit_mixed", "inversion_edges", "accumulate",
+                                     "accumulate_min_log_q"])
+def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
+    """``B200NessaiFlowProposal.populate`` end to end with the reference's own proposal object
+    (reparameterisations, truncation scheme, live-point dtype): engine selection, configuration
+    and the pool it hands to the sampler, against the reference's host ``populate`` of the same
+    trained flow (distributional: the random streams differ)."""
+    reference_or_skip()
+    import torch
+    from nessai.flowmodel import FlowModel
+    from nessai.livepoint import numpy_array_to_live_points
+    from nessai.model import Model
+
+    from nessai_b200.nessai_plugin import B200NessaiFlowProposal
+    from nessai_b200.proposal import GeneralPopulateEngine, PopulateEngine
+    from oracle.flow_numpy import NumpyFlow
+
+    D = 4
+    names = [f"x{i}" for i in range(D)]
+
+    class Box(Model):
+        def __init__(self):
+            self.names = list(names)
+            self.bounds = {n: [-5.0, 5.0] for n in names}
+
+        def log_prior(self, x):
+            return np.log(self.in_bounds(x), dtype="float") - D * np.log(10.0)
+
+        def log_likelihood(self, x):
+            return -0.5 * np.sum(self.unstructured_view(x) ** 2, axis=-1)
+
+    class CpuFlowB200Proposal(B200NessaiFlowProposal):
+        _FlowModelClass = FlowModel  # the reference's CPU flow; the simulated device evaluates its weights
+
+    kw = dict(
+        zscore={}, rescaletobounds=dict(fallback_reparameterisation="rescaletobounds"),
+        logit_mixed=dict(reparameterisations={"x0": "logit", "x1": "default", "x2": "z-score", "x3": "log-rescale"}),
+        inversion_edges=dict(reparameterisations={"inversion": dict(parameters=names)}),
+        accumulate=dict(accumulate_weights=True),
+        accumulate_min_log_q=dict(accumulate_weights=True, truncation_methods=["latent_radius", "min_log_q"]),
+    )[variant]
+    model = Box()
+    rng = np.random.default_rng(9)
+    model.set_rng(rng)
+    torch.manual_seed(9)
+    flow_config = dict(n_blocks=2, n_neurons=8, n_layers=1, net="mlp", batch_norm_between_layers=False)
+    common = dict(rng=rng, flow_config=flow_config, training_config=dict(max_epochs=30, patience=30),
+                  output=str(tmp_path), poolsize=400, drawsize=2000, plot=False)
+    prop = CpuFlowB200Proposal(model, **common, **kw)
+    prop.initialise()
+    live = numpy_array_to_live_points(np.clip(1.2 * rng.standard_normal((600, D)) + 0.5, -4.9, 4.9), names)
+    live["logL"] = model.log_likelihood(live)
+    prop.train(live, plot=False)
+    if variant == "inversion_edges":
+        (r,) = prop._reparameterisation.values()
+        r._edges.update(x0="lower", x1="upper", x2=False, x3="lower")
+    # the reference's own host populate of the same flow, for comparison
+    worst = live[np.argsort(live["logL"])[0]]
+    from nessai.proposal.flowproposal import FlowProposal
+
+    FlowProposal.populate(prop, worst, n_samples=400, plot=False)
+    ref = np.stack([prop.samples[n] for n in names], axis=-1).copy()
+    ref_acceptance = prop.population_acceptance
+    # the simulated device evaluates the trained weights with the float64 oracle
+    sim = _simdevice.install(monkeypatch)
+    sd = {k: v.detach().cpu().numpy() for k, v in prop.flow.model.state_dict().items()}
+    nf = NumpyFlow(sd, ftype="realnvp", net="mlp", hidden_features=8)
+    prop.flow.model._ready = lambda: None
+    prop.flow.model._handle = _simdevice.SimHandle(nf, D)
+    prop.populate(worst, n_samples=400, plot=False)
+    assert prop._engine is not None and len(sim.calls) > 0  # not the host loop
+    general = variant in ("logit_mixed", "inversion_edges")
+    assert type(prop._engine) is (GeneralPopulateEngine if general else PopulateEngine)
+    kinds = {c[0] for c in sim.calls}
+    assert ("tail" in kinds) == general and ("sum_exp" in kinds) == variant.startswith("accumulate")
+    got = np.stack([prop.samples[n] for n in names], axis=-1)
+    assert prop.populated and len(prop.indices) == prop.samples.size
+    if variant.startswith("accumulate"):
+        assert 0 < len(got) <= 400  # samples[accept][:n_samples]
+    else:
+        assert len(got) == 400
+    assert prop.samples.dtype == prop.population_dtype
+    assert np.all((got >= -5) & (got <= 5)) and np.all(np.isfinite(prop.samples["logL"]))
+    np.testing.assert_allclose(prop.samples["logP"], -D * np.log(10.0))
+    np.testing.assert_allclose(prop.samples["logL"], model.log_likelihood(prop.samples))
+    # same target: pool moments and acceptance agree with the reference's host loop
+    se = ref.std(0) * np.sqrt(1 / len(ref) + 1 / len(got))
+    assert np.all(np.abs(got.mean(0) - ref.mean(0)) < 6 * se), (got.mean(0), ref.mean(0))
+    assert np.all(np.abs(np.log(got.std(0) / ref.std(0))) < 0.35)
+    assert 0.5 < prop.population_acceptance / ref_acceptance < 2.0
+    # and the proposal still serves the sampler
+    new = prop.draw(worst)
+    assert new.dtype == prop.population_dtype and len(prop.indices) == prop.samples.size - 1
+
+
+# ------------------------------------------------------------------ two ranks over gloo
+def _rank_worker(rank, world, port, out):
+    import os
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), here):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    import _simdevice
+    from nessai_b200.livepoint import get_dtype
+    from nessai_b200.proposal import GeneralPopulateEngine, PopulateEngine
+
+    _simdevice.install()
+    nf, D = _flow()
+    names = [f"x{i}" for i in range(D)]
+    scale, shift = _zscore(D)
+    lpc, radius, drawsize = -D * np.log(8.0), 4.9, 1001  # ragged shards: 501 + 500
+    res = {}
+    eng = PopulateEngine(_simdevice.SimFlowModel(nf, D), names, get_dtype(names))
+    eng.configure(scale, shift, np.full(D, -4.0), np.full(D, 4.0), lpc, radius)
+    eng.seed = 4242
+    # (1) the ordinary loop, ended by max_samples so that every accepted row is in the pool
+    rows, p, a = eng.run(10**5, drawsize, max_samples=3 * drawsize - 1)
+    res["loop"] = (np.stack([rows[nm] for nm in names], axis=-1), p, a)
+    # (2) accumulate_weights
+    rows, p, a = eng.run_accumulate(120, drawsize, max_samples=10**6)
+    res["acc"] = (np.stack([rows[nm] for nm in names], axis=-1), p, a, list(eng.last_accumulate["n_expected"]),
+                  eng.last_accumulate["stride"], list(eng.last_accumulate["rejects"]))
+    # (3) the non-affine tail
+    gen = GeneralPopulateEngine(_simdevice.SimFlowModel(nf, D), names, get_dtype(names))
+    kind = (np.arange(D) % 2).astype(np.int32)  # identity / sigmoid
+    gen.configure(kind, np.where(kind == 1, 8.0, 1.4), np.where(kind == 1, -4.0, 0.1), np.full(D, -4.5),
+                  np.full(D, 4.5), lpc, radius, 1.0, min_log_q=-40.0)
+    gen.seed = 99
+    rows, p, a = gen.run(10**5, drawsize, max_samples=3 * drawsize - 1)
+    res["tail"] = (np.stack([rows[nm] for nm in names], axis=-1), p, a)
+    torch.save(res, f"{out}.{world}.{rank}")
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_reproduce_one_rank(tmp_path):
+    """Sharded over two ranks (gloo, simulated device) the loops propose and accept exactly the
+    rows one rank does -- the Philox counter is the global row index and the normaliser is
+    all-reduced -- and every rank ends up with the same pool."""
+    import torch
+    import torch.multiprocessing as mp
+    from test_dist_gloo import _free_port
+
+    out = str(tmp_path / "res")
+    mp.spawn(_rank_worker, args=(1, _free_port(), out), nprocs=1, join=True)
+    mp.spawn(_rank_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    one = torch.load(f"{out}.1.0", weights_only=False)
+    r0, r1 = (torch.load(f"{out}.2.{r}", weights_only=False) for r in range(2))
+
+    def same_rows(a, b):
+        assert a.shape == b.shape and len(a) > 0
+        np.testing.assert_array_equal(a[np.lexsort(a.T)], b[np.lexsort(b.T)])
+
+    for key in ("loop", "tail"):
+        assert one[key][1:] == r0[key][1:] == r1[key][1:] and one[key][1] == 3 * 1001
+        np.testing.assert_array_equal(r0[key][0], r1[key][0])  # the same pool on every rank
+        same_rows(one[key][0], r0[key][0])  # rank-major instead of draw order, same rows
+    # accumulate: the weights (hence the expected pool size each turn) do not depend on the
+    # sharding; the uniforms of the rejection step do
+    np.testing.assert_allclose(one["acc"][3], r0["acc"][3], rtol=1e-12)
+    assert one["acc"][1] == r0["acc"][1] == r1["acc"][1]  # same number of turns
+    np.testing.assert_array_equal(r0["acc"][0], r1["acc"][0])
+    assert r0["acc"][2] == r1["acc"][2] >= 120 and len(r0["acc"][0]) == 120 == len(one["acc"][0])
+    assert r0["acc"][4] == 512 and one["acc"][4] == 1024
+    # the two ranks' counter blocks of a rejection step are adjacent and disjoint
+    (b0, n0), (b1, n1) = r0["acc"][5][-1], r1["acc"][5][-1]
+    assert n0 == n1 and b1 == b0 + n0
