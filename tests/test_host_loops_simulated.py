@@ -303,3 +303,26 @@ def test_two_ranks_reproduce_one_rank(tmp_path):
     # the two ranks' counter blocks of a rejection step are adjacent and disjoint
     (b0, n0), (b1, n1) = r0["acc"][5][-1], r1["acc"][5][-1]
     assert n0 == n1 and b1 == b0 + n0
+
+
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_nothing_survives_the_truncation(monkeypatch, accumulate):
+    """flowproposal.py:436-439: turns whose rows are all truncated only count towards
+    ``max_samples``; the loop ends there with an empty pool of the right dtype."""
+    from nessai_b200.livepoint import get_dtype
+    from nessai_b200.proposal import GeneralPopulateEngine, PopulateEngine
+
+    sim = _simdevice.install(monkeypatch)
+    nf, D = _flow()
+    names = [f"x{i}" for i in range(D)]
+    scale, shift = _zscore(D)
+    for cls in (PopulateEngine,) if accumulate else (PopulateEngine, GeneralPopulateEngine):
+        eng = cls(_simdevice.SimFlowModel(nf, D), names, get_dtype(names))
+        pre = (np.zeros(D, dtype=np.int32),) if cls is GeneralPopulateEngine else ()
+        eng.configure(*pre, scale, shift, np.full(D, -4.0), np.full(D, 4.0), -1.0, 1e-3)  # |z| <= 0.001: nobody
+        eng.seed = 3
+        run = eng.run_accumulate if accumulate else eng.run
+        rows, n_proposed, n_accepted = run(100, 500, max_samples=1600)
+        assert (len(rows), n_proposed, n_accepted) == (0, 2000, 0) and rows.dtype == get_dtype(names)
+    if accumulate:
+        assert eng.last_accumulate["rejects"] == [] and eng.last_accumulate["n_expected"] == [0.0] * 4
