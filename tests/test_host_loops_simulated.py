@@ -129,7 +129,7 @@ def test_general_engine_loop_matches_oracle(monkeypatch):
 
 @pytest.mark.reference
 @pytest.mark.parametrize("variant", ["zscore", "rescaletobounds", "logit_mixed", "inversion_edges", "accumulate",
-                                     "accumulate_min_log_q"])
+                                     "accumulate_min_log_q", "likelihood_threshold", "logit_likelihood_threshold"])
 def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     """``B200NessaiFlowProposal.populate`` end to end with the reference's own proposal object
     (reparameterisations, truncation scheme, live-point dtype): engine selection, configuration
@@ -159,6 +159,10 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
         def log_likelihood(self, x):
             return -0.5 * np.sum(self.unstructured_view(x) ** 2, axis=-1)
 
+        def log_likelihood_torch(self, x):  # INTEGRATION.md 3a (host tensors on the simulated device)
+            self.device_rows = getattr(self, "device_rows", 0) + x.shape[0]
+            return -0.5 * (x * x).sum(dim=1)
+
     class CpuFlowB200Proposal(B200NessaiFlowProposal):
         _FlowModelClass = FlowModel  # the reference's CPU flow; the simulated device evaluates its weights
 
@@ -168,7 +172,12 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
         inversion_edges=dict(reparameterisations={"inversion": dict(parameters=names)}),
         accumulate=dict(accumulate_weights=True),
         accumulate_min_log_q=dict(accumulate_weights=True, truncation_methods=["latent_radius", "min_log_q"]),
+        likelihood_threshold=dict(truncation_methods=["latent_radius", "likelihood_threshold"]),
+        logit_likelihood_threshold=dict(truncation_methods=["latent_radius", "likelihood_threshold"],
+                                        reparameterisations={"x0": "logit", "x1": "logit", "x2": "default",
+                                                             "x3": "default"}),
     )[variant]
+    contour = variant.endswith("likelihood_threshold")
     model = Box()
     rng = np.random.default_rng(9)
     model.set_rng(rng)
@@ -185,7 +194,7 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
         (r,) = prop._reparameterisation.values()
         r._edges.update(x0="lower", x1="upper", x2=False, x3="lower")
     # the reference's own host populate of the same flow, for comparison
-    worst = live[np.argsort(live["logL"])[0]]
+    worst = live[np.argsort(live["logL"])[len(live) // 2 if contour else 0]]  # a contour that cuts the pool
     from nessai.proposal.flowproposal import FlowProposal
 
     FlowProposal.populate(prop, worst, n_samples=400, plot=False)
@@ -199,7 +208,10 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     prop.flow.model._handle = _simdevice.SimHandle(nf, D)
     prop.populate(worst, n_samples=400, plot=False)
     assert prop._engine is not None and len(sim.calls) > 0  # not the host loop
-    general = variant in ("logit_mixed", "inversion_edges")
+    general = variant in ("logit_mixed", "inversion_edges", "logit_likelihood_threshold")
+    if contour:  # the likelihood ran on the "device", inside the loop, never on the host
+        assert model.device_rows > 0 and np.all(prop.samples["logL"] > worst["logL"])
+        assert np.all(prop.samples["logL"] > worst["logL"])
     assert type(prop._engine) is (GeneralPopulateEngine if general else PopulateEngine)
     kinds = {c[0] for c in sim.calls}
     assert ("tail" in kinds) == general and ("sum_exp" in kinds) == variant.startswith("accumulate")
