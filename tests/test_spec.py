@@ -161,3 +161,58 @@ def test_train_plan_packs_every_golden_realnvp():
             assert dims[0] == row[11] and dims[-1] == row[12] * spec.coupling_multiplier
             assert row[11] == (D if spec.ftype == "maf" else len(spec.layers[l].identity))
         assert (covered == 1).all()
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("mask", [[1, 1, -1], [1, 1, 1, -1, -1], [[1, -1, 1], [-1, 1, 1]]])
+def test_custom_mask_of_the_augmented_proposal(mask):
+    """``AugmentedFlowProposal.update_flow_config`` (proposal/augmented.py:91-96) passes
+    ``mask = ones(D); mask[-augment_dims:] = -1`` (realnvp.py:114-131 alternates its sign per
+    layer; a 2-D mask gives every layer its own): same initial state_dict as the reference,
+    the folded program reproduces the reference module in both directions, and the training
+    plan packs it."""
+    reference_or_skip()
+    import torch
+    from nessai.flowmodel.utils import update_flow_config
+    from nessai.flows import configure_model
+
+    from nessai_b200.train_plan import build_train_plan
+
+    D = np.shape(mask)[-1]
+    cfg = dict(n_inputs=D, n_neurons=8, n_blocks=2, n_layers=2, ftype="realnvp", mask=np.array(mask))
+    torch.manual_seed(7)
+    ref = configure_model(update_flow_config(dict(cfg)))
+    ref.eval()
+    sp = FlowSpec(cfg)
+    torch.manual_seed(7)
+    theta, ints = sp.init_state()
+    mine = sp.state_dict_numpy(theta, ints)
+    sd = ref.state_dict()
+    assert list(mine) == list(sd)
+    for k, v in sd.items():
+        np.testing.assert_array_equal(mine[k], v.numpy())
+    # perturb every parameter so that the couplings, LU and BatchNorm all act
+    rng = np.random.default_rng(1)
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.add_(torch.from_numpy(0.2 * rng.standard_normal(tuple(p.shape))).to(p.dtype))
+        for name, b in ref.named_buffers():
+            if name.endswith("running_var"):
+                b.mul_(1.7)
+            elif name.endswith("running_mean"):
+                b.add_(0.3)
+    sd = {k: v.numpy() for k, v in ref.state_dict().items()}
+    sp.load_state_dict_numpy(sd, theta, ints)
+    ff = sp.fold(theta, ints)
+    x = rng.standard_normal((64, D))
+    with torch.no_grad():
+        z_ref, lj_ref = ref.forward(torch.from_numpy(x).float())
+        x_ref, ilj_ref = ref.inverse(torch.from_numpy(x).float())
+    z, lj = run_program(ff.program(False), x)
+    xi, ilj = run_program(ff.program(True), x)
+    np.testing.assert_allclose(z, z_ref.numpy(), rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(lj, lj_ref.numpy(), rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(xi, x_ref.numpy(), rtol=2e-4, atol=5e-5)
+    np.testing.assert_allclose(ilj, ilj_ref.numpy(), rtol=2e-4, atol=2e-5)
+    plan, itab, red = build_train_plan(sp, ints)
+    assert plan[0] == D and plan[1] == 2
