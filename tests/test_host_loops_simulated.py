@@ -338,3 +338,70 @@ def test_nothing_survives_the_truncation(monkeypatch, accumulate):
         assert (len(rows), n_proposed, n_accepted) == (0, 2000, 0) and rows.dtype == get_dtype(names)
     if accumulate:
         assert eng.last_accumulate["rejects"] == [] and eng.last_accumulate["n_expected"] == [0.0] * 4
+
+
+def test_standalone_proposal_contract_on_simulated_device(tmp_path, monkeypatch):
+    """``B200FlowProposal`` (the standalone mirror): the attributes the sampler relies on
+     -- pool, indices, acceptance, draw()/repopulate, pool-size scaling,
+    min_log_q preparation, pickling -- with the flow on the simulated device."""
+    import pickle
+
+    from nessai_b200.livepoint import numpy_array_to_live_points
+    from nessai_b200.proposal import B200FlowProposal
+
+    _simdevice.install(monkeypatch)
+    nf, D = _flow()
+
+    class SimModel(_simdevice.SimFlowModel):
+        weights_file = None
+
+        def __init__(self, flow_config=None, training_config=None, output=None, rng=None):
+            super().__init__(nf, D)
+            self.flow_config = flow_config
+
+        def initialise(self):
+            pass
+
+        def forward_and_log_prob(self, x):
+            z, lj = nf.forward(np.asarray(x, dtype=np.float64))
+            return z, -0.5 * np.sum(z * z, axis=1) - 0.5 * D * np.log(2 * np.pi) + lj
+
+    class Box:
+        names = [f"x{i}" for i in range(D)]
+        bounds = {n: [-4.0, 4.0] for n in names}
+
+        def log_prior(self, x):
+            a = np.stack([x[n] for n in self.names], axis=-1)
+            return np.where(np.all((a >= -4) & (a <= 4), axis=-1), -D * np.log(8.0), -np.inf)
+
+        def log_likelihood(self, x):
+            return -0.5 * np.sum(np.stack([x[n] for n in self.names], axis=-1) ** 2, axis=-1)
+
+    monkeypatch.setattr(B200FlowProposal, "_FlowModelClass", SimModel)
+    prop = B200FlowProposal(Box(), rng=np.random.default_rng(3), flow_config=dict(n_blocks=4), output=str(tmp_path),
+                            poolsize=300, drawsize=2000, truncation_methods=["latent_radius", "min_log_q"])
+    with pytest.raises(RuntimeError):
+        prop.populate(None, n_samples=10)  # flowproposal.py:401-405
+    prop.initialise()
+    live = numpy_array_to_live_points(1.5 * np.random.default_rng(5).standard_normal((500, D)) + 0.3, Box.names)
+    prop.check_state(live)
+    prop.training_data = live
+    prop.populate(live[0], n_samples=300, max_samples=10**6)
+    assert prop.populated and prop.samples.dtype == prop.x_dtype and prop.samples.size == 300
+    assert sorted(prop.indices) == list(range(300)) and 0 < prop.population_acceptance <= 1
+    assert prop._min_log_q == prop.forward_pass(live)[1].min()
+    assert np.all(prop.forward_pass(prop.samples)[1] > prop._min_log_q - 1e-6)
+    assert np.all(prop.samples["logP"] == -D * np.log(8.0)) and np.all(np.isfinite(prop.samples["logL"]))
+    np.testing.assert_allclose(prop.samples["logL"], Box().log_likelihood(prop.samples))
+    # draw() serves the pool in the permuted order and repopulates when it runs dry
+    first = prop.samples[prop.indices.tolist()[-1]].copy()
+    assert prop.draw(live[0]) == first and len(prop.indices) == 299
+    for _ in range(299):
+        prop.draw(live[0])
+    assert not prop.populated and prop.populated_count == 1
+    prop.ns_acceptance = 0.25
+    prop.draw(live[0])  # pool-size scaling (flowproposal/base.py:416-435): 1 / acceptance
+    assert prop.populated_count == 2 and prop.poolsize == 1200 and prop.samples.size == 1200
+    # pickling drops the device objects (flowproposal/base.py:1286-1309)
+    state = pickle.loads(pickle.dumps(prop.__getstate__()))
+    assert "flow" not in state and "_engine" not in state and "model" not in state and state["resume_populated"]
