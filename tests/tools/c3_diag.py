@@ -1,3 +1,5 @@
+"""Verbose error breakdown of the 32-D spline-flow kernels against the float64 oracle (checker script;
+run from the repo root: python tests/tools/c3_diag.py)."""
 import os, sys, tempfile
 import numpy as np, torch
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, "tests")

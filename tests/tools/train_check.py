@@ -2,7 +2,7 @@
 import faulthandler; faulthandler.dump_traceback_later(40, exit=True)
 import json, os, sys, tempfile, time
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))  # repo root
 from nessai_b200.flowmodel import B200FlowModel
 from oracle.train_numpy import TrainStepOracle
 
