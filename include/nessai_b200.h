@@ -121,11 +121,14 @@ int nb200_populate_accept_x64(int64_t n, int D, const double* d_x64, const doubl
                               int64_t capacity, int64_t write_offset, int64_t* d_counts,
                               int64_t* d_scratch, void* stream);
 
-/* Populate tail for per-parameter maps x = h(x') * scale + shift, h = identity (kind 0),
- * sigmoid (1), |.| (2) or exp (3): the inverse direction of
- * reparameterisations/rescale.py:635-660 RescaleToBounds.inverse_reparameterise with
- * post_rescaling "logit" (utils/rescaling.py:310-330 sigmoid, log|J| = log h + log1p(-h)),
- * "log" (utils/rescaling.py:385-402 exp, log|J| = x') or boundary inversion
+/* Populate tail for per-parameter maps x = h(a x' + b) * scale + shift with h = identity
+ * (kind 0), sigmoid (1), |.| (2), exp (3), log (4), the standard normal CDF (5) or its
+ * quantile function (6): the inverse direction of reparameterisations/rescale.py:263-291
+ * (ScaleAndShift) and :635-660 (RescaleToBounds.inverse_reparameterise) with the rescaling
+ * functions of utils/rescaling.py:290-417 as post-rescaling ("logit" -> sigmoid, log|J| =
+ * log h + log1p(-h); "log" -> exp, log|J| = u; "exp" -> log; "gaussian_cdf" -> quantile;
+ * "inv_gaussian_cdf" -> CDF), as pre-rescaling (then the affine map comes first: d_pre_scale /
+ * d_pre_shift = a / b, log|J| += log|a|, scale = 1, shift = 0) or boundary inversion
  * (rescale.py:570-590: |x'|, an "upper" edge folded into a negative scale), then the affine
  * map to the prior bounds (rescale.py:544-553, log|J| = log|scale|).  Runs AFTER
  * nb200_populate_draw called with scale = 1, shift = 0, lo = -inf, hi = +inf,
@@ -133,8 +136,10 @@ int nb200_populate_accept_x64(int64_t n, int D, const double* d_x64, const doubl
  * log q (NaN: dropped).  Rewrites d_logq (-= log|J|), d_logw (= log_prior_const - log_q; NaN
  * for rows outside d_lo/d_hi, with non-finite log_q or log_q <= min_log_q), writes
  * d_x64 float64[n*D], and accumulates d_stats = {max log_w, n_valid} (reset by the caller).
- * d_kind int32[D], d_scale/d_shift/d_lo/d_hi float64[D] on the device; D <= 64. */
+ * d_kind int32[D], d_scale/d_shift/d_lo/d_hi float64[D] on the device; d_pre_scale /
+ * d_pre_shift float64[D] or both NULL (a = 1, b = 0); D <= 64. */
 int nb200_reparam_tail(int64_t n, int D, const float* d_xp, const int32_t* d_kind,
+                       const double* d_pre_scale, const double* d_pre_shift,
                        const double* d_scale, const double* d_shift, const double* d_lo,
                        const double* d_hi, double log_prior_const, double min_log_q,
                        double* d_logq, double* d_logw, double* d_x64, double* d_stats,

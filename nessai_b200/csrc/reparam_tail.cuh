@@ -1,11 +1,17 @@
 // Populate tail for reparameterisations that are NOT a diagonal affine:
-// per feature  x = h(x') * scale + shift  with  h in {identity, sigmoid, |.|, exp}, float64, the
-// inverse direction of /root/reference/src/nessai/reparameterisations/rescale.py:635-660
-// (RescaleToBounds.inverse_reparameterise):
-//   * post_rescaling "logit"  -> h = sigmoid, log|J| += log h + log1p(-h)   (utils/rescaling.py:310-330)
-//   * post_rescaling "log"    -> h = exp,     log|J| += x'                  (utils/rescaling.py:385-402)
-//   * boundary inversion      -> h = |.|      (rescale.py:570-590: value[value < 0] *= -1; "upper"
-//                                edge: 1 - value, folded into a negative scale)
+// per feature  x = h(a x' + b) * scale + shift,  float64, the inverse direction of
+// /root/reference/src/nessai/reparameterisations/rescale.py:263-291 (ScaleAndShift) and :635-660
+// (RescaleToBounds.inverse_reparameterise) with the rescaling functions of
+// utils/rescaling.py:290-417:
+//   * post_rescaling "logit"        -> h = sigmoid,  log|J| += log h + log1p(-h)      (:310-330)
+//   * post_rescaling "log"          -> h = exp,      log|J| += u                       (:385-393)
+//   * post_rescaling "exp"          -> h = log,      log|J| -= log u                   (:369-383)
+//   * post_rescaling "gaussian_cdf" -> h = -sqrt2 erfcinv(2u), log|J| += log sqrt(2 pi) + h^2/2  (:403-407)
+//   * post_rescaling "inv_gaussian_cdf" -> h = erfc(-u/sqrt2)/2, log|J| -= log sqrt(2 pi) + u^2/2 (:396-400)
+//   * boundary inversion            -> h = |.|  (rescale.py:570-590: value[value < 0] *= -1; an
+//                                      "upper" edge, 1 - value, is folded into a negative scale)
+//   * the same functions as PRE-rescaling ("z-score-logit", "log-z-score", ...): the affine
+//     map comes first, u = a x' + b with log|J| += log|a|, then h, then scale = 1, shift = 0
 // followed by the affine map back to the prior bounds (rescale.py:544-553), whose log|J| is
 // log|scale|, then the prior-bounds check (model.py:497-518) and log_w = log_prior - log_q
 // (flowproposal/base.py:1069-1098).
@@ -25,39 +31,66 @@
 
 namespace nb200 {
 
-enum TailKind : int32_t { TAIL_IDENTITY = 0, TAIL_SIGMOID = 1, TAIL_ABS = 2, TAIL_EXP = 3 };
+enum TailKind : int32_t {
+  TAIL_IDENTITY = 0, TAIL_SIGMOID = 1, TAIL_ABS = 2, TAIL_EXP = 3, TAIL_LOG = 4,
+  TAIL_NORMAL_CDF = 5, TAIL_NORMAL_QUANTILE = 6, TAIL_N_KINDS = 7
+};
 
-// One feature: returns x, adds the log-Jacobian of h (NOT of the affine part) to logj.
-NB200_HD double tail_feature(int32_t kind, double scale, double shift, double v, double& logj) {
-  double h = v;
+#ifdef __CUDACC__
+#define NB200_ERFCINV erfcinv
+#else
+// <cmath> has no erfcinv: the host harness supplies one (tests/_hostcheck/reparam_host.cpp)
+extern "C" double nb200_host_erfcinv(double);
+#define NB200_ERFCINV nb200_host_erfcinv
+#endif
+
+// One feature: u = a v + b, returns h(u) * scale + shift and adds the log-Jacobian of h (NOT of
+// the two affine parts, which are row constants) to logj.
+NB200_HD double tail_feature(int32_t kind, double a, double b, double scale, double shift, double v,
+                             double& logj) {
+  const double u = a * v + b;
+  double h = u;
   if (kind == TAIL_SIGMOID) {
-    h = 1.0 / (1.0 + exp(-v));
+    h = 1.0 / (1.0 + exp(-u));
     logj += log(h) + log1p(-h);
   } else if (kind == TAIL_ABS) {
-    h = fabs(v);
+    h = fabs(u);
   } else if (kind == TAIL_EXP) {
-    h = exp(v);
-    logj += v;
+    h = exp(u);
+    logj += u;
+  } else if (kind == TAIL_LOG) {
+    h = log(u);
+    logj -= h;
+  } else if (kind == TAIL_NORMAL_CDF) {
+    h = 0.5 * erfc(-u / 1.4142135623730951);
+    logj += -0.9189385332046727 - 0.5 * u * u;
+  } else if (kind == TAIL_NORMAL_QUANTILE) {
+    h = -1.4142135623730951 * NB200_ERFCINV(2.0 * u);
+    logj += 0.9189385332046727 + 0.5 * h * h;
   }
   return h * scale + shift;
 }
 
 // One row.  logq_flow: log q of the flow alone (NaN: the row was already dropped by the draw
-// kernel).  log_scale_sum = sum_d log|scale_d|.  Writes x[D]; returns true when the row
-// survives and then logq_out / logw_out are its log q / log weight.
-NB200_HD bool tail_row(int D, const float* xp, const int32_t* kind, const double* scale,
-                       const double* shift, const double* lo, const double* hi,
-                       double log_scale_sum, double log_prior_const, double min_log_q,
-                       double logq_flow, double* x, double& logq_out, double& logw_out) {
-  double logj = log_scale_sum;
+// kernel).  log_affine_sum = sum_d (log|scale_d| + log|a_d|).  pre_a / pre_b may be NULL
+// (a = 1, b = 0).  Writes x[D]; returns true when the row survives and then logq_out / logw_out
+// are its log q / log weight.
+NB200_HD bool tail_row(int D, const float* xp, const int32_t* kind, const double* pre_a,
+                       const double* pre_b, const double* scale, const double* shift,
+                       const double* lo, const double* hi, double log_affine_sum,
+                       double log_prior_const, double min_log_q, double logq_flow, double* x,
+                       double& logq_out, double& logw_out) {
+  double logj = log_affine_sum;
   bool inb = true;
   for (int d = 0; d < D; ++d) {
-    const double xv = tail_feature(kind[d], scale[d], shift[d], (double)xp[d], logj);
+    const double xv = tail_feature(kind[d], pre_a ? pre_a[d] : 1.0, pre_b ? pre_b[d] : 0.0, scale[d],
+                                   shift[d], (double)xp[d], logj);
     x[d] = xv;
     inb = inb && !(xv < lo[d]) && !(xv > hi[d]);
   }
   const double logq = logq_flow - logj;
-  // isfinite() also rejects the NaN of an already-dropped row
+  // (logq - logq == 0) is isfinite(): it also rejects the NaN of an already-dropped row and of
+  // a log / quantile evaluated outside its domain
   const bool ok = inb && (logq - logq == 0.0) && (logq > min_log_q);
   logq_out = ok ? logq : NAN;
   logw_out = ok ? (log_prior_const - logq) : NAN;
@@ -72,11 +105,12 @@ NB200_HD bool tail_row(int D, const float* xp, const int32_t* kind, const double
 // the draw kernel's time).  The per-feature constants sit in shared memory.
 __global__ void __launch_bounds__(TAIL_THREADS)
 reparam_tail_kernel(int64_t n, int D, const float* __restrict__ xp, const int32_t* __restrict__ kind,
+                    const double* __restrict__ pre_a, const double* __restrict__ pre_b,
                     const double* __restrict__ scale, const double* __restrict__ shift,
                     const double* __restrict__ lo, const double* __restrict__ hi,
                     double log_prior_const, double min_log_q, double* __restrict__ logq,
                     double* __restrict__ logw, double* __restrict__ x64, double* __restrict__ stats) {
-  __shared__ double c_s[4 * TAIL_MAXD];
+  __shared__ double c_s[6 * TAIL_MAXD];  // scale | shift | lo | hi | a | b
   __shared__ int32_t k_s[TAIL_MAXD];
   __shared__ double lss_s;
   for (int d = threadIdx.x; d < D; d += TAIL_THREADS) {
@@ -84,11 +118,13 @@ reparam_tail_kernel(int64_t n, int D, const float* __restrict__ xp, const int32_
     c_s[TAIL_MAXD + d] = shift[d];
     c_s[2 * TAIL_MAXD + d] = lo[d];
     c_s[3 * TAIL_MAXD + d] = hi[d];
+    c_s[4 * TAIL_MAXD + d] = pre_a ? pre_a[d] : 1.0;
+    c_s[5 * TAIL_MAXD + d] = pre_b ? pre_b[d] : 0.0;
     k_s[d] = kind[d];
   }
   if (threadIdx.x == 0) {
     double s = 0.0;
-    for (int d = 0; d < D; ++d) s += log(fabs(scale[d]));
+    for (int d = 0; d < D; ++d) s += log(fabs(scale[d])) + (pre_a ? log(fabs(pre_a[d])) : 0.0);
     lss_s = s;
   }
   __syncthreads();
@@ -98,9 +134,9 @@ reparam_tail_kernel(int64_t n, int D, const float* __restrict__ xp, const int32_
     // x is written straight to global memory (every row: the accept kernel only reads the
     // rows it keeps, and a device likelihood may read them all)
     double lq, lw;
-    const bool ok = tail_row(D, xp + row * D, k_s, c_s, c_s + TAIL_MAXD, c_s + 2 * TAIL_MAXD,
-                             c_s + 3 * TAIL_MAXD, lss_s, log_prior_const, min_log_q, logq[row],
-                             x64 + row * D, lq, lw);
+    const bool ok = tail_row(D, xp + row * D, k_s, c_s + 4 * TAIL_MAXD, c_s + 5 * TAIL_MAXD, c_s,
+                             c_s + TAIL_MAXD, c_s + 2 * TAIL_MAXD, c_s + 3 * TAIL_MAXD, lss_s,
+                             log_prior_const, min_log_q, logq[row], x64 + row * D, lq, lw);
     logq[row] = lq;
     logw[row] = lw;
     if (ok) {

@@ -20,14 +20,14 @@ from __future__ import annotations
 
 import datetime
 import logging
+from typing import NamedTuple
 
 import numpy as np
 from nessai import config as nessai_config
 from nessai.livepoint import empty_structured_array as nessai_empty_structured_array
 from nessai.proposal.flowproposal import FlowProposal
 from nessai.reparameterisations import NullReparameterisation, RescaleToBounds, ScaleAndShift
-from nessai.utils.rescaling import exp_with_log_jacobian as _ref_exp
-from nessai.utils.rescaling import sigmoid as _ref_sigmoid
+from nessai.utils import rescaling as _ref_rescaling
 
 from .flowmodel import B200FlowModel
 from .proposal import GeneralPopulateEngine, IndexPool, PopulateEngine, detect_uniform_box_prior
@@ -36,100 +36,132 @@ logger = logging.getLogger(__name__)
 
 
 # per-parameter map kinds of the device tail (csrc/reparam_tail.cuh: TailKind)
-KIND_IDENTITY, KIND_SIGMOID, KIND_ABS, KIND_EXP = 0, 1, 2, 3
+(KIND_IDENTITY, KIND_SIGMOID, KIND_ABS, KIND_EXP, KIND_LOG, KIND_NORMAL_CDF,
+ KIND_NORMAL_QUANTILE) = range(7)
+
+# the INVERSE function of a named rescaling (utils/rescaling.py:410-417) -> the kind of h
+_INVERSE_KINDS = (
+    (_ref_rescaling.sigmoid, KIND_SIGMOID),
+    (_ref_rescaling.exp_with_log_jacobian, KIND_EXP),
+    (_ref_rescaling.log_with_log_jacobian, KIND_LOG),
+    (_ref_rescaling.gaussian_cdf, KIND_NORMAL_CDF),
+    (_ref_rescaling.inverse_gaussian_cdf, KIND_NORMAL_QUANTILE),
+)
+
+
+def _kind_of(fn):
+    for ref_fn, kind in _INVERSE_KINDS:
+        if fn is ref_fn:
+            return kind
+    return None
+
+
+class ParameterMaps(NamedTuple):
+    """``x = h(pre_scale * x' + pre_shift) * scale + shift`` per parameter (model order)."""
+
+    kind: np.ndarray
+    scale: np.ndarray
+    shift: np.ndarray
+    pre_scale: np.ndarray
+    pre_shift: np.ndarray
+
+    @property
+    def affine(self) -> bool:
+        return not np.any(self.kind != KIND_IDENTITY)
+
+    @property
+    def has_pre_affine(self) -> bool:
+        return bool(np.any(self.pre_scale != 1.0) or np.any(self.pre_shift != 0.0))
 
 
 def parameter_maps(rep, prime_parameters, model_names):
-    """``(kind, scale, shift)`` with ``x = h(x') * scale + shift`` per parameter (model order),
-    ``h`` = identity / sigmoid / ``|.|`` / exp, when the combined reparameterisation ``rep``
-    (reparameterisations/combined.py:154-192) is made of such one-to-one per-parameter maps, else
-    ``None``.  ``log|J| = sum log|scale| + sum log|h'(x')|``.  Recognised:
+    """The combined reparameterisation ``rep`` (reparameterisations/combined.py:154-192) as
+    one-to-one per-parameter maps ``x = h(a x' + b) * scale + shift`` with ``h`` = identity /
+    sigmoid / ``|.|`` / exp / log / normal CDF / normal quantile (a ``ParameterMaps``), or ``None``
+    when it is not made of such maps.  ``log|J| = sum log|scale| + sum log|a| + sum log|h'|``.
+    Recognised:
 
     * ``NullReparameterisation`` (reparameterisations/null.py): identity;
-    * ``ScaleAndShift`` / ``Rescale`` (rescale.py:233-291) without pre-/post-rescaling:
-      ``x = x' * scale + shift``;
-    * the stock ``RescaleToBounds`` (rescale.py:321-731) without a pre-rescaling function:
+    * ``ScaleAndShift`` / ``Rescale`` (rescale.py:233-291): ``x = x' * scale + shift``; with a
+      named post-rescaling ``x = Q^-1(x') * scale + shift`` ("zscore-gaussian-cdf"); with a
+      named pre-rescaling ``x = P^-1(x' * scale + shift)`` ("z-score-logit", "log-z-score",
+      "z-score-inv-gaussian-cdf": ``a = scale``, ``b = shift``);
+    * the stock ``RescaleToBounds`` (rescale.py:321-731):
       ``x = (hi - lo) * (h(x') - r0) / (r1 - r0) + lo + offset`` with ``[lo, hi]`` the current
       (possibly data-updated) bounds and ``[r0, r1]`` the rescale bounds (rescale.py:533-553,
       669-680), i.e. ``scale = (hi - lo) / (r1 - r0)``, ``shift = lo + offset - scale * r0``;
-      ``h`` = sigmoid for ``post_rescaling="logit"``, exp for ``"log"`` (utils/rescaling.py:
-      310-330,385-402); with boundary inversion (rescale.py:570-590) ``h = |.|`` and the detected
-      edge picks the map: "lower" ``[0, 1] -> [lo, hi]``, "upper" ``1 - |x'|`` first (negative
-      scale), no edge ``[-1, 1] -> [lo, hi]`` with ``h`` = identity.
+      ``h`` from a named post-rescaling ("logit" -> sigmoid, "log" -> exp, ...;
+      utils/rescaling.py:290-417); with boundary inversion (rescale.py:570-590) ``h = |.|`` and
+      the detected edge picks the map: "lower" ``[0, 1] -> [lo, hi]``, "upper" ``1 - |x'|`` first
+      (negative scale), no edge ``[-1, 1] -> [lo, hi]`` with ``h`` = identity; with a named
+      pre-rescaling that affine map becomes ``a, b`` and ``h = P^-1`` comes last.
 
-    Anything else (user rescaling functions, inversion combined with a post-rescaling, an edge
+    Anything else (user rescaling callables, two non-linear stages on one parameter, an edge
     not detected yet, angles, user classes) keeps the reference's host loop."""
     if rep is None:
         return None
     if list(prime_parameters) != [p for r in rep.values() for p in r.output_parameters]:
         return None
-    kind, scale, shift, names = [], [], [], []
+    rows, names = [], []  # rows: (kind, scale, shift, a, b)
     for r in rep.values():
-        if isinstance(r, ScaleAndShift):
-            if r.has_pre_rescaling or r.has_post_rescaling or not r.one_to_one:
-                return None
+        if isinstance(r, NullReparameterisation):
             for p in r.parameters:
-                kind.append(KIND_IDENTITY)
-                scale.append(float(r.scale[p]))
-                shift.append(float(r.shift[p]) if r.shift else 0.0)
+                rows.append((KIND_IDENTITY, 1.0, 0.0, 1.0, 0.0))
                 names.append(p)
-        elif isinstance(r, NullReparameterisation):
-            for p in r.parameters:
-                kind.append(KIND_IDENTITY)
-                scale.append(1.0)
-                shift.append(0.0)
-                names.append(p)
-        elif type(r) is RescaleToBounds:
-            # subclasses may override the rescaling hooks: only the stock class is recognised
-            if r.has_pre_rescaling or not r.one_to_one:
-                return None
-            post = KIND_IDENTITY
-            if r.has_post_rescaling:
-                if r.post_rescaling_inv is _ref_sigmoid:
-                    post = KIND_SIGMOID
-                elif r.post_rescaling_inv is _ref_exp:
-                    post = KIND_EXP
-                else:
-                    return None
-            for p in r.parameters:
+            continue
+        if not (isinstance(r, ScaleAndShift) or type(r) is RescaleToBounds) or not r.one_to_one:
+            # (RescaleToBounds subclasses may override the rescaling hooks: stock class only)
+            return None
+        pre = _kind_of(r.pre_rescaling_inv) if r.has_pre_rescaling else KIND_IDENTITY
+        post = _kind_of(r.post_rescaling_inv) if r.has_post_rescaling else KIND_IDENTITY
+        if pre is None or post is None or (pre != KIND_IDENTITY and post != KIND_IDENTITY):
+            return None
+        for p in r.parameters:
+            k = post
+            if isinstance(r, ScaleAndShift):
+                s, t = float(r.scale[p]), (float(r.shift[p]) if r.shift else 0.0)
+            else:
                 lo, hi = (float(b) for b in r.bounds[p])
                 off = float(r.offsets[p])
                 if r.boundary_inversion and p in r.boundary_inversion:
                     edge = (r._edges or {}).get(p)
-                    if post != KIND_IDENTITY or edge is None:
+                    if post != KIND_IDENTITY or pre != KIND_IDENTITY or edge is None:
                         return None
                     if edge == "lower":
                         k, s, t = KIND_ABS, hi - lo, lo + off
                     elif edge == "upper":
                         k, s, t = KIND_ABS, -(hi - lo), hi + off
                     elif not edge:
-                        k, s, t = KIND_IDENTITY, (hi - lo) / 2.0, lo + off + (hi - lo) / 2.0
+                        s, t = (hi - lo) / 2.0, lo + off + (hi - lo) / 2.0
                     else:
                         return None
                 else:
                     s = (hi - lo) / float(r._rescale_factor[p])
-                    k, t = post, lo + off - s * float(r._rescale_shift[p])
-                kind.append(k)
-                scale.append(s)
-                shift.append(t)
-                names.append(p)
-        else:
-            return None
+                    t = lo + off - s * float(r._rescale_shift[p])
+            if pre != KIND_IDENTITY:
+                rows.append((pre, 1.0, 0.0, s, t))  # the affine map first, then P^-1
+            else:
+                rows.append((k, s, t, 1.0, 0.0))
+            names.append(p)
     if names != list(model_names):
         return None
-    scale, shift = np.asarray(scale, dtype=np.float64), np.asarray(shift, dtype=np.float64)
-    if not (np.all(np.isfinite(scale)) and np.all(np.isfinite(shift)) and np.all(scale != 0.0)):
+    cols = list(zip(*rows))
+    maps = ParameterMaps(np.asarray(cols[0], dtype=np.int32), *(np.asarray(c, dtype=np.float64) for c in cols[1:]))
+    for v in maps[1:]:
+        if not np.all(np.isfinite(v)):
+            return None
+    if np.any(maps.scale == 0.0) or np.any(maps.pre_scale == 0.0):
         return None
-    return np.asarray(kind, dtype=np.int32), scale, shift
+    return maps
 
 
 def diagonal_rescaling(rep, prime_parameters, model_names):
     """``(scale, shift)`` when ``parameter_maps`` finds a diagonal affine (every ``h`` the
     identity): what the fused populate tail of the draw kernels evaluates itself."""
     maps = parameter_maps(rep, prime_parameters, model_names)
-    if maps is None or np.any(maps[0] != KIND_IDENTITY):
+    if maps is None or not maps.affine:
         return None
-    return maps[1], maps[2]
+    return maps.scale, maps.shift
 
 
 class B200NessaiFlowProposal(FlowProposal):
@@ -178,10 +210,10 @@ class B200NessaiFlowProposal(FlowProposal):
         maps = self._parameter_maps() if self.initialised else None
         rules = self._fused_rules() if self.initialised else None
         eligible = maps is not None and rules is not None
-        if eligible and np.any(maps[0] != KIND_IDENTITY) and len(maps[0]) > GeneralPopulateEngine.MAX_D:
+        if eligible and not maps.affine and len(maps.kind) > GeneralPopulateEngine.MAX_D:
             eligible = False
         if eligible:
-            affine = not np.any(maps[0] != KIND_IDENTITY)
+            affine = maps.affine
             engine_cls = PopulateEngine if affine else GeneralPopulateEngine
             if (self._engine is None or self._engine.flow is not self.flow
                     or type(self._engine) is not engine_cls):
@@ -211,13 +243,16 @@ class B200NessaiFlowProposal(FlowProposal):
         hi = [self.model.bounds[n][1] for n in self.model.names]
         t = self.latent_temperature
         in_loop = "likelihood_threshold" in rules
+        extra = {} if affine else dict(pre_scale=maps.pre_scale, pre_shift=maps.pre_shift)
         self._engine.configure(
-            *(maps[1:] if affine else maps), lo, hi, self._log_prior_const,
+            *((maps.scale, maps.shift) if affine else (maps.kind, maps.scale, maps.shift)),
+            lo, hi, self._log_prior_const,
             rules["latent_radius"].threshold if "latent_radius" in rules else 0.0,
             1.0 if t in (None, 1.0) else float(np.sqrt(t)),
             min_log_q=rules["min_log_q"].min_log_q if "min_log_q" in rules else None,
             likelihood=self.model.log_likelihood_torch if in_loop else None,
             log_l_threshold=rules["likelihood_threshold"].threshold if in_loop else None,
+            **extra,
         )
         host_prior = None if self._log_prior_const is not None else self.log_prior
         evals0 = getattr(self._engine, "likelihood_evaluations", 0)

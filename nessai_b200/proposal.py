@@ -824,10 +824,13 @@ class PopulateEngine:
 
 
 class GeneralPopulateEngine(PopulateEngine):
-    """``PopulateEngine`` for per-parameter maps ``x = h(x') * scale + shift`` that are not all
-    affine: ``h`` = sigmoid (``RescaleToBounds`` with ``post_rescaling="logit"``), exp (``"log"``)
-    or ``|.|`` (boundary inversion) --
-    /root/reference/src/nessai/reparameterisations/rescale.py:570-590,635-660.
+    """``PopulateEngine`` for per-parameter maps ``x = h(a x' + b) * scale + shift`` that are not
+    all affine: ``h`` = sigmoid (``RescaleToBounds`` with ``post_rescaling="logit"``), exp
+    (``"log"``), log, the normal CDF / quantile function (``"inv_gaussian_cdf"`` /
+    ``"gaussian_cdf"``) or ``|.|`` (boundary inversion); as a PRE-rescaling the same functions
+    come after the affine map ``a, b`` (``"z-score-logit"``, ``"log-z-score"``, ...) --
+    /root/reference/src/nessai/reparameterisations/rescale.py:263-291,570-590,635-660,
+    utils/rescaling.py:290-417.
 
     The fused draw kernel is left exactly as it is: it is given the identity map and no bounds,
     so it leaves the flow output ``x'`` and the flow's own ``log q``; ``nb200_reparam_tail``
@@ -837,6 +840,7 @@ class GeneralPopulateEngine(PopulateEngine):
     The loop, its pipelining and the multi-GPU exchange are the base class's."""
 
     MAX_D = 64  # TAIL_MAXD
+    N_KINDS = 7  # TAIL_N_KINDS
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
@@ -846,25 +850,29 @@ class GeneralPopulateEngine(PopulateEngine):
         self._tail_min_log_q = -float("inf")
 
     def configure(self, kind, scale, shift, lo, hi, log_prior_const, r_max, sqrt_temperature=1.0, min_log_q=None,
-                  likelihood=None, log_l_threshold=None):
-        """As ``PopulateEngine.configure`` with the per-parameter ``kind`` (0 identity, 1 sigmoid,
-        2 abs, 3 exp) in front."""
+                  likelihood=None, log_l_threshold=None, pre_scale=None, pre_shift=None):
+        """As ``PopulateEngine.configure`` with the per-parameter ``kind`` of ``h`` in front
+        (0 identity, 1 sigmoid, 2 abs, 3 exp, 4 log, 5 normal CDF, 6 normal quantile) and the
+        optional affine map applied BEFORE ``h``: ``x = h(pre_scale x' + pre_shift) scale + shift``."""
         D = self.D
+        pre_scale = np.ones(D) if pre_scale is None else pre_scale
+        pre_shift = np.zeros(D) if pre_shift is None else pre_shift
         if getattr(self, "_identity", None) is None:
             self._identity = (np.ones(D), np.zeros(D), np.full(D, -np.inf), np.full(D, np.inf))
         super().configure(*self._identity, log_prior_const, r_max, sqrt_temperature, min_log_q=None,
                           likelihood=likelihood, log_l_threshold=log_l_threshold)
         self._tail_min_log_q = -float("inf") if min_log_q is None or np.isnan(min_log_q) else float(min_log_q)
-        new = [np.array(kind, dtype=np.int32)] + [np.array(a, dtype=np.float64) for a in (scale, shift, lo, hi)]
+        new = [np.array(kind, dtype=np.int32)] + [
+            np.array(a, dtype=np.float64) for a in (scale, shift, lo, hi, pre_scale, pre_shift)]
         if any(a.shape != (D,) for a in new):
-            raise ValueError("kind / scale / shift / lo / hi must have one entry per parameter")
-        if np.any((new[0] < 0) | (new[0] > 3)):
+            raise ValueError("kind / scale / shift / lo / hi / pre_scale / pre_shift: one entry per parameter")
+        if np.any((new[0] < 0) | (new[0] >= self.N_KINDS)):
             raise ValueError("unknown per-parameter map kind")
         old = getattr(self, "_tail_host", None)
         if old is None or not all(np.array_equal(a, b) for a, b in zip(new, old)):
             self.t_kind = torch.from_numpy(new[0]).to(self.device)
             dev = torch.from_numpy(np.stack(new[1:])).to(self.device)
-            self.t_scale, self.t_shift, self.t_lo, self.t_hi = dev[0], dev[1], dev[2], dev[3]
+            self.t_scale, self.t_shift, self.t_lo, self.t_hi, self.t_pre_scale, self.t_pre_shift = dev.unbind(0)
             self._tail_host = new
 
     def _after_draw(self, n_local: int):
@@ -874,8 +882,9 @@ class GeneralPopulateEngine(PopulateEngine):
             self.d_stats.copy_(self._stats_init, non_blocking=True)  # the draw kernel's were pre-tail
             lpc = float("nan") if self.log_prior_const is None else float(self.log_prior_const)
             self._call(_lib.load().nb200_reparam_tail, [
-                n_local, self.D, self.d_xp.data_ptr(), self.t_kind.data_ptr(), self.t_scale.data_ptr(),
-                self.t_shift.data_ptr(), self.t_lo.data_ptr(), self.t_hi.data_ptr(), lpc, self._tail_min_log_q,
+                n_local, self.D, self.d_xp.data_ptr(), self.t_kind.data_ptr(), self.t_pre_scale.data_ptr(),
+                self.t_pre_shift.data_ptr(), self.t_scale.data_ptr(), self.t_shift.data_ptr(),
+                self.t_lo.data_ptr(), self.t_hi.data_ptr(), lpc, self._tail_min_log_q,
                 self.d_logq.data_ptr(), self.d_logw.data_ptr(), self.d_x64.data_ptr(), self.d_stats.data_ptr(),
                 torch.cuda.current_stream(self.device).cuda_stream,
             ], "nb200_reparam_tail")

@@ -3,13 +3,18 @@ diagonal affine -- TEST INFRASTRUCTURE ONLY: nothing under ``nessai_b200/`` may 
 
 Restates the inverse direction of the reference's ``RescaleToBounds``
 (/root/reference/src/nessai/reparameterisations/rescale.py:635-660) for the configurations the
-device tail covers, as ``x = h(x') * scale + shift`` per parameter:
+device tail covers, and of ``ScaleAndShift`` (rescale.py:263-291) with a pre- or post-rescaling
+function, as ``x = h(a x' + b) * scale + shift`` per parameter:
 
 * ``post_rescaling="logit"``: ``h = sigmoid``, ``log|J| += log h + log1p(-h)``
   (utils/rescaling.py:310-330), then ``[0, 1] -> [lo, hi]`` (rescale.py:544-553);
 * ``post_rescaling="log"``: ``h = exp``, ``log|J| += x'`` (utils/rescaling.py:385-402);
 * boundary inversion (rescale.py:570-590): ``h = |x'|``; a "lower" edge maps ``[0, 1] -> [lo, hi]``,
   an "upper" edge ``1 - |x'|`` first (a negative scale); no detected edge: ``[-1, 1] -> [lo, hi]``;
+* ``post_rescaling`` "exp" / "gaussian_cdf" / "inv_gaussian_cdf": ``h`` = log / the normal quantile
+  function / the normal CDF (utils/rescaling.py:369-407);
+* the same functions as ``pre_rescaling`` ("z-score-logit", "log-z-score",
+  "z-score-inv-gaussian-cdf"): ``x = P^-1(scale * x' + shift)``, i.e. ``a = scale``, ``b = shift``;
 * ``h = identity``: the diagonal affine of ``oracle/populate_numpy.py``;
 
 followed by ``log_q -= log|J|`` (flowproposal.py:378-383), the prior-bounds check
@@ -23,38 +28,54 @@ from __future__ import annotations
 
 import numpy as np
 
-IDENTITY, SIGMOID, ABS, EXP = 0, 1, 2, 3
+IDENTITY, SIGMOID, ABS, EXP, LOG, NORMAL_CDF, NORMAL_QUANTILE = range(7)
 
 
-def inverse_maps(xp, kind, scale, shift):
-    """``x' (n, D) -> (x (n, D), log|J| (n,))`` for the per-parameter ``kind / scale / shift``."""
+def inverse_maps(xp, kind, scale, shift, pre_scale=None, pre_shift=None):
+    """``x' (n, D) -> (x (n, D), log|J| (n,))`` for ``x = h(a x' + b) * scale + shift`` with the
+    per-parameter ``kind`` of ``h``, ``a = pre_scale`` (default 1) and ``b = pre_shift`` (0)."""
+    from scipy.special import erfc, erfcinv
+
     xp = np.asarray(xp, dtype=np.float64)
     kind = np.asarray(kind)
+    D = xp.shape[1]
+    a = np.ones(D) if pre_scale is None else np.asarray(pre_scale, dtype=np.float64)
+    b = np.zeros(D) if pre_shift is None else np.asarray(pre_shift, dtype=np.float64)
     x = np.empty_like(xp)
-    log_j = np.full(xp.shape[0], float(np.sum(np.log(np.abs(scale)))))
+    log_j = np.full(xp.shape[0], float(np.sum(np.log(np.abs(scale))) + np.sum(np.log(np.abs(a)))))
     with np.errstate(all="ignore"):
-        for d in range(xp.shape[1]):
-            v = xp[:, d]
-            if kind[d] == SIGMOID:
-                h = 1.0 / (1.0 + np.exp(-v))
+        for d in range(D):
+            u = a[d] * xp[:, d] + b[d]
+            if kind[d] == SIGMOID:  # utils/rescaling.py:310-330
+                h = 1.0 / (1.0 + np.exp(-u))
                 log_j = log_j + np.log(h) + np.log1p(-h)
-            elif kind[d] == ABS:
-                h = np.abs(v)
-            elif kind[d] == EXP:
-                h = np.exp(v)
-                log_j = log_j + v
+            elif kind[d] == ABS:  # rescale.py:570-590
+                h = np.abs(u)
+            elif kind[d] == EXP:  # utils/rescaling.py:385-393
+                h = np.exp(u)
+                log_j = log_j + u
+            elif kind[d] == LOG:  # utils/rescaling.py:369-383
+                h = np.log(u)
+                log_j = log_j - h
+            elif kind[d] == NORMAL_CDF:  # utils/rescaling.py:396-400
+                h = 0.5 * erfc(-u / np.sqrt(2.0))
+                log_j = log_j - 0.5 * np.log(2 * np.pi) - 0.5 * u**2
+            elif kind[d] == NORMAL_QUANTILE:  # utils/rescaling.py:403-407
+                h = -np.sqrt(2.0) * erfcinv(2.0 * u)
+                log_j = log_j + 0.5 * np.log(2 * np.pi) + 0.5 * h**2
             elif kind[d] == IDENTITY:
-                h = v
+                h = u
             else:
                 raise ValueError(f"unknown kind {kind[d]}")
             x[:, d] = h * scale[d] + shift[d]
     return x, log_j
 
 
-def tail_rows(xp, logq_flow, *, kind, scale, shift, lo, hi, log_prior_const, min_log_q=None):
+def tail_rows(xp, logq_flow, *, kind, scale, shift, lo, hi, log_prior_const, min_log_q=None, pre_scale=None,
+              pre_shift=None):
     """The tail of one turn: ``(x, log_q, log_w, valid)``; ``logq_flow`` is the flow's own
     ``log q`` (NaN where the row was dropped before: radius truncation, non-finite)."""
-    x, log_j = inverse_maps(xp, kind, scale, shift)
+    x, log_j = inverse_maps(xp, kind, scale, shift, pre_scale, pre_shift)
     with np.errstate(all="ignore"):
         log_q = np.asarray(logq_flow, dtype=np.float64) - log_j
         valid = np.isfinite(log_q) & ~np.any((x < lo) | (x > hi), axis=1)

@@ -18,7 +18,7 @@ D = 4
 NAMES = [f"x{i}" for i in range(D)]
 
 
-def make_proposal(tmp_path, **kw):
+def make_proposal(tmp_path, box=None, **kw):
     from nessai.livepoint import numpy_array_to_live_points
     from nessai.model import Model
     from nessai.proposal import FlowProposal
@@ -26,7 +26,8 @@ def make_proposal(tmp_path, **kw):
     class Box(Model):
         def __init__(self):
             self.names = list(NAMES)
-            self.bounds = {n: [-4.0 - i, 6.0 + 2 * i] for i, n in enumerate(self.names)}
+            self.bounds = ({n: list(box) for n in self.names} if box
+                           else {n: [-4.0 - i, 6.0 + 2 * i] for i, n in enumerate(self.names)})
 
         def log_prior(self, x):
             return np.log(self.in_bounds(x), dtype="float")
@@ -40,7 +41,9 @@ def make_proposal(tmp_path, **kw):
     prop = FlowProposal(model, rng=rng, flow_config=dict(n_blocks=2, n_neurons=8), output=str(tmp_path),
                         poolsize=100, plot=False, **kw)
     prop.initialise()
-    live = numpy_array_to_live_points(1.3 * rng.standard_normal((300, D)) + 0.4, model.names)
+    pts = (rng.uniform(box[0] + 0.05 * (box[1] - box[0]), box[1] - 0.05 * (box[1] - box[0]), (300, D)) if box
+           else 1.3 * rng.standard_normal((300, D)) + 0.4)
+    live = numpy_array_to_live_points(pts, model.names)
     prop.check_state(live)
     prop.rescale(live.copy())  # what train() does: boundary inversion detects its edges here
     return prop, model, live
@@ -56,7 +59,24 @@ CASES = {
                               ["lower", "upper", False, "lower"], {0, 2}),
     "inversion_offset": (dict(reparameterisations={"inversion": dict(parameters=NAMES, offset=True)}),
                          ["upper", "upper", "lower", False], {0, 2}),
+    # ScaleAndShift with a post-rescaling: x = Q^-1(x') * scale + shift
+    "zscore_gaussian_cdf": (dict(reparameterisations={"zscore-gaussian-cdf": dict(parameters=NAMES)}), None, {6}),
+    # ... and with a pre-rescaling: x = P^-1(scale * x' + shift) (needs x in P's domain: see BOX)
+    "zscore_logit": (dict(reparameterisations={"z-score-logit": dict(parameters=NAMES)}), None, {1}),
+    "zscore_inv_gaussian_cdf": (dict(reparameterisations={"z-score-inv-gaussian-cdf": dict(parameters=NAMES)}),
+                                None, {5}),
+    "log_zscore": (dict(reparameterisations={"log-z-score": dict(parameters=NAMES)}), None, {3}),
+    "rescale_pre_log_post_none": (dict(reparameterisations={"rescaletobounds": dict(
+        parameters=NAMES, pre_rescaling="log", update_bounds=False)}), None, {3}),
+    "rescale_post_exp": (dict(reparameterisations={"rescaletobounds": dict(
+        parameters=NAMES, post_rescaling="exp", update_bounds=False, rescale_bounds=[1.0, 2.0])}), None, {4}),
+    "rescale_post_inv_gaussian_cdf": (dict(reparameterisations={"rescaletobounds": dict(
+        parameters=NAMES, post_rescaling="inv_gaussian_cdf", update_bounds=False, rescale_bounds=[0.0, 1.0])}),
+        None, {5}),
 }
+# configurations whose forward map needs the physical parameters inside the function's domain
+BOX = {"zscore_logit": (0.0, 1.0), "zscore_inv_gaussian_cdf": (0.0, 1.0), "log_zscore": (0.0, 1.0),
+       "rescale_pre_log_post_none": (0.5, 3.0)}
 
 
 @pytest.mark.reference
@@ -69,29 +89,40 @@ def test_parameter_maps_and_oracle_match_reference_inverse_rescale(tmp_path, cas
     from oracle.reparam_numpy import inverse_maps
 
     kw, edges, kinds = CASES[case]
-    prop, model, live = make_proposal(tmp_path, **kw)
+    prop, model, live = make_proposal(tmp_path, box=BOX.get(case), **kw)
     if edges is not None:
         (r,) = [r for r in prop._reparameterisation.values()]
         for p, e in zip(NAMES, edges):
             r._edges[p] = e  # every branch of rescale.py:570-590, whatever the data suggested
     maps = parameter_maps(prop._reparameterisation, prop.prime_parameters, model.names)
     assert maps is not None
-    kind, scale, shift = maps
-    assert set(kind.tolist()) == kinds
+    kind, scale, shift, pre_scale, pre_shift = maps
+    assert set(kind.tolist()) == kinds and maps.has_pre_affine == (case in BOX)
     assert diagonal_rescaling(prop._reparameterisation, prop.prime_parameters, model.names) is None
     rng = np.random.default_rng(0)
     n = 200
     a = rng.normal(0.0, 1.2, size=(n, D))
     if case == "log":
         a = -np.abs(a)  # log of a value in [0, 1]
+    elif case == "rescale_post_exp":
+        a = np.exp(rng.uniform(0.0, 0.7, size=(n, D)))  # exp of a value in [1, 2]
+    elif case in ("zscore_gaussian_cdf", "rescale_post_inv_gaussian_cdf"):
+        a = rng.uniform(0.01, 0.99, size=(n, D)) if case == "zscore_gaussian_cdf" else a
     xp = empty_structured_array(n, names=prop.prime_parameters)
     for i, p in enumerate(prop.prime_parameters):
         xp[p] = a[:, i]
     x_ref, log_j_ref = prop.inverse_rescale(xp.copy())
-    x, log_j = inverse_maps(a, kind, scale, shift)
+    x, log_j = inverse_maps(a, kind, scale, shift, pre_scale, pre_shift)
     ref = np.stack([x_ref[nm] for nm in model.names], axis=-1)
     np.testing.assert_allclose(x, ref, rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(log_j, log_j_ref, rtol=1e-12, atol=1e-12)
+    # and the forward direction (what the training data take) is its inverse
+    x_prime, log_j_fwd = prop.rescale(live.copy())
+    back, lj_back = inverse_maps(np.stack([x_prime[p] for p in prop.prime_parameters], axis=-1), kind, scale, shift,
+                                 pre_scale, pre_shift)
+    if edges is None:  # (forced edges are not the ones rescale() used)
+        np.testing.assert_allclose(back, np.stack([live[nm] for nm in model.names], axis=-1), rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(lj_back, -log_j_fwd, rtol=1e-9, atol=1e-9)
 
 
 def test_undetected_edge_and_user_functions_are_refused(tmp_path):
@@ -122,39 +153,76 @@ def host_tail(tmp_path_factory):
     subprocess.run([gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(out), src], check=True)
     lib = C.CDLL(str(out))
     lib.tail_rows_host.restype = None
-    lib.tail_rows_host.argtypes = [C.c_int64, C.c_int] + [C.c_void_p] * 6 + [C.c_double, C.c_double] + [C.c_void_p] * 4
+    lib.tail_rows_host.argtypes = [C.c_int64, C.c_int] + [C.c_void_p] * 8 + [C.c_double, C.c_double] + [C.c_void_p] * 4
+    lib.nb200_host_erfcinv.restype = C.c_double
+    lib.nb200_host_erfcinv.argtypes = [C.c_double]
     return lib
 
 
-@pytest.mark.parametrize("min_log_q", [None, -12.0])
-def test_kernel_row_function_matches_oracle(host_tail, min_log_q):
-    from oracle.reparam_numpy import tail_rows
+def test_host_erfcinv_helper(host_tail):
+    """The harness's stand-in for CUDA's erfcinv is accurate to double precision."""
+    from scipy.special import erfcinv
 
-    rng = np.random.default_rng(5)
-    n, d = 5000, 7
-    kind = np.array([0, 1, 2, 3, 1, 2, 0], dtype=np.int32)
-    scale = np.array([1.5, 8.0, -3.0, 2.0, 0.5, 4.0, -0.7])
-    shift = np.array([0.2, -4.0, 5.0, -1.0, 0.0, -2.0, 0.3])
-    lo = np.array([-3.0, -4.0, 2.0, -1.0, 0.0, -2.0, -2.0])
-    hi = np.array([3.0, 4.0, 5.0, 9.0, 0.5, 1.5, 2.0])
+    y = np.concatenate([np.logspace(-300, -1, 400), np.linspace(0.1, 1.9, 400), 2.0 - np.logspace(-15, -1, 100)])
+    got = np.array([host_tail.nb200_host_erfcinv(float(v)) for v in y])
+    np.testing.assert_allclose(got, erfcinv(y), rtol=2e-14, atol=2e-15)
+    assert host_tail.nb200_host_erfcinv(0.0) == np.inf and host_tail.nb200_host_erfcinv(2.0) == -np.inf
+    assert np.isnan(host_tail.nb200_host_erfcinv(-0.5)) and np.isnan(host_tail.nb200_host_erfcinv(2.5))
+
+
+TAIL_CASE = dict(
+    kind=np.array([0, 1, 2, 3, 1, 2, 0, 4, 5, 6, 1, 3], dtype=np.int32),
+    scale=np.array([1.5, 8.0, -3.0, 2.0, 0.5, 4.0, -0.7, 1.2, 6.0, 0.9, 1.0, 1.0]),
+    shift=np.array([0.2, -4.0, 5.0, -1.0, 0.0, -2.0, 0.3, 0.1, -3.0, 0.4, 0.0, 0.0]),
+    lo=np.array([-3.0, -4.0, 2.0, -1.0, 0.0, -2.0, -2.0, -3.0, -3.0, -2.0, 0.0, 0.0]),
+    hi=np.array([3.0, 4.0, 5.0, 9.0, 0.5, 1.5, 2.0, 2.0, 3.0, 2.5, 1.0, 9.0]),
+    pre_scale=np.array([1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.3, 1.0, 0.2, 1.7, 0.6]),
+    pre_shift=np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.5, 0.0, 0.5, -0.3, 0.2]),
+)
+
+
+def tail_case_inputs(n, seed=5):
+    """Rows for TAIL_CASE: every kind, saturated / overflowing / out-of-domain arguments and
+    rows the draw kernel has already dropped."""
+    rng = np.random.default_rng(seed)
+    d = len(TAIL_CASE["kind"])
     xp = rng.normal(0.0, 1.0, size=(n, d)).astype(np.float32)
-    xp[:50, 1] = rng.choice([-60.0, 45.0, 800.0, -800.0], size=50)  # saturated sigmoid: log|J| = -inf
-    xp[50:80, 3] = 900.0  # exp overflow
+    if n >= 200:
+        xp[:50, 1] = rng.choice([-60.0, 45.0, 800.0, -800.0], size=50)  # saturated sigmoid: log|J| = -inf
+        xp[50:80, 3] = 900.0  # exp overflow
+        xp[80:110, 7] = -6.0  # log of a negative number: NaN
+        xp[110:140, 9] = rng.choice([-4.0, 4.0], size=30)  # quantile outside (0, 1): NaN
+        xp[140:170, 8] = rng.choice([-40.0, 40.0], size=30)  # normal CDF saturates at 0 / 1
     logq_flow = rng.normal(-8.0, 2.0, size=n)
     logq_flow[rng.random(n) < 0.1] = np.nan  # rows the draw kernel already dropped
-    x_ref, lq_ref, lw_ref, valid = tail_rows(xp, logq_flow, kind=kind, scale=scale, shift=shift, lo=lo, hi=hi,
-                                             log_prior_const=-2.5, min_log_q=min_log_q)
+    return xp, logq_flow
+
+
+@pytest.mark.parametrize("min_log_q,pre", [(None, True), (-14.0, True), (None, False)])
+def test_kernel_row_function_matches_oracle(host_tail, min_log_q, pre):
+    from oracle.reparam_numpy import tail_rows
+
+    n = 5000
+    c = {k: v.copy() for k, v in TAIL_CASE.items()}
+    if not pre:
+        c["pre_scale"], c["pre_shift"] = None, None
+        c["kind"][[7, 9]] = 0  # their arguments rely on the pre-affine map to be in the domain
+    d = len(c["kind"])
+    xp, logq_flow = tail_case_inputs(n)
+    x_ref, lq_ref, lw_ref, valid = tail_rows(xp, logq_flow, log_prior_const=-2.5, min_log_q=min_log_q, **c)
     logq, logw = logq_flow.copy(), np.empty(n)
     x64 = np.empty((n, d))
     stats = np.array([-np.inf, 0.0])
-    host_tail.tail_rows_host(n, d, xp.ctypes.data, kind.ctypes.data, scale.ctypes.data, shift.ctypes.data,
-                             lo.ctypes.data, hi.ctypes.data, -2.5, -np.inf if min_log_q is None else min_log_q,
+    ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+    host_tail.tail_rows_host(n, d, xp.ctypes.data, c["kind"].ctypes.data, ptr(c["pre_scale"]), ptr(c["pre_shift"]),
+                             c["scale"].ctypes.data, c["shift"].ctypes.data, c["lo"].ctypes.data, c["hi"].ctypes.data,
+                             -2.5, -np.inf if min_log_q is None else min_log_q,
                              logq.ctypes.data, logw.ctypes.data, x64.ctypes.data, stats.ctypes.data)
     assert 0.05 * n < valid.sum() < 0.9 * n
     np.testing.assert_array_equal(~np.isnan(logw), valid)
     np.testing.assert_array_equal(~np.isnan(logq), valid)
     with np.errstate(all="ignore"):
-        np.testing.assert_allclose(x64, x_ref, rtol=1e-14, atol=1e-14)
-    np.testing.assert_allclose(logq[valid], lq_ref[valid], rtol=1e-13, atol=1e-13)
-    np.testing.assert_allclose(logw[valid], lw_ref[valid], rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(x64, x_ref, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(logq[valid], lq_ref[valid], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(logw[valid], lw_ref[valid], rtol=1e-12, atol=1e-12)
     assert stats[1] == valid.sum() and stats[0] == logw[valid].max()
