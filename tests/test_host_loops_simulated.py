@@ -414,3 +414,20 @@ def test_standalone_proposal_contract_on_simulated_device(tmp_path, monkeypatch)
     # pickling drops the device objects (flowproposal/base.py:1286-1309)
     state = pickle.loads(pickle.dumps(prop.__getstate__()))
     assert "flow" not in state and "_engine" not in state and "model" not in state and state["resume_populated"]
+
+
+def test_gpu_test_bodies_pass_on_the_simulated_device():
+    """tests/test_gpu_zz_tail_accumulate.py was written without access to a GPU: its test bodies
+    (index arithmetic, loop replay, tolerances) are executed here against the simulated device,
+    in a subprocess because the dry run patches torch globally."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    from conftest import REPO
+
+    res = subprocess.run([sys.executable, os.path.join(REPO, "tests", "tools", "dryrun_gpu_tests_on_sim.py")],
+                         capture_output=True, text=True, cwd=REPO, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert json.loads(res.stdout.strip().splitlines()[-1]) == {"dryrun_failed": 0, "of": 7}
