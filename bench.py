@@ -319,7 +319,8 @@ def run_ours(args):
         if world == 1 and not args.no_extras:
             out["coupling_forward"] = coupling_roofline(dev, peaks, which)
             out["variants"] = {"c2_resnet_default_conditioner": resnet_variant(prop, args.pool, dev),
-                               "c3_nsf_32d": nsf_variant(dev)}
+                               "c3_nsf_32d": nsf_variant(dev),
+                               "nonaffine_tail_and_accumulate": isolated_variants(args.pool)}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(threads=1, pool=args.cpu_pool)
         print(json.dumps(out), flush=True)
@@ -400,6 +401,21 @@ def resnet_variant(prop, pool, dev):
         "tflops_algorithmic": pool / (ms * 1e-3) * 146e3 / 1e12,
         "flops_per_row": 146e3,
     }
+
+
+def isolated_variants(pool):
+    """The non-affine populate tail and accumulate_weights (scripts/tail_accumulate_variants.py),
+    written after the round's GPU budget was spent: measured in a SUBPROCESS with its own CUDA
+    context, after everything above, so a fault there cannot touch the headline numbers."""
+    try:
+        res = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "tail_accumulate_variants.py"), str(pool)],
+                             capture_output=True, text=True, timeout=240, cwd=REPO)
+        lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+        if res.returncode == 0 and lines:
+            return json.loads(lines[-1])
+        return {"error": f"exit {res.returncode}: {(res.stderr or res.stdout)[-400:]}"}
+    except Exception as e:  # noqa: BLE001 - a variant must never break the bench line
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def nsf_variant(dev, n=2_000_000):
