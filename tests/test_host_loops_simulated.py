@@ -431,3 +431,69 @@ def test_gpu_test_bodies_pass_on_the_simulated_device():
                          capture_output=True, text=True, cwd=REPO, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert json.loads(res.stdout.strip().splitlines()[-1]) == {"dryrun_failed": 0, "of": 7}
+
+
+def test_pipelined_loop_logic_equals_serial_loop(monkeypatch):
+    """The software-pipelined ``PopulateEngine.run`` (speculative next draw, counts through a
+    pinned buffer + event, records copied ahead of their count, pinned destination sized from a
+    hint) against the one-synchronisation-per-turn loop over many sizes / hints / stop conditions.
+    On the simulated device every "asynchronous" operation completes at once, so this checks the
+    bookkeeping (what tests/test_gpu_populate.py::test_pipelined_loop_matches_serial_loop checks on
+    the GPU for four cases), not the stream ordering."""
+    import contextlib
+
+    import torch
+
+    from nessai_b200 import proposal
+    from nessai_b200.livepoint import get_dtype
+
+    pipelined = proposal.PopulateEngine.run  # before install() replaces it by the serial loop
+    _simdevice.install(monkeypatch)
+
+    class Event:
+        def record(self, stream=None):
+            pass
+
+        def synchronize(self):
+            pass
+
+    class Stream:
+        def __init__(self, device=None):
+            pass
+
+        def wait_event(self, ev):
+            pass
+
+        def synchronize(self):
+            pass
+
+    monkeypatch.setattr(torch.cuda, "Event", Event)
+    monkeypatch.setattr(torch.cuda, "Stream", Stream)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    for name in ("empty", "zeros"):
+        orig = getattr(torch, name)
+        monkeypatch.setattr(torch, name, lambda *a, _o=orig, **k: _o(*a, **{**k, "pin_memory": False}))
+    nf, D = _flow()
+    names = [f"x{i}" for i in range(D)]
+    scale, shift = _zscore(D)
+
+    def engine():
+        e = proposal.PopulateEngine(_simdevice.SimFlowModel(nf, D), names, get_dtype(names))
+        e.configure(scale, shift, np.full(D, -4.0), np.full(D, 4.0), -D * np.log(8.0), 4.9)
+        e.seed = 99
+        return e
+
+    ea, eb = engine(), engine()
+    rng = np.random.default_rng(0)
+    drawsize = 600  # ~20 rows accepted per turn
+    cases = [(50, 10**6, None), (1, 10**6, 1), (10**5, 4 * drawsize - 1, None), (45, 10**6, 10**4), (200, 10**6, 3)]
+    cases += [(int(rng.integers(1, 300)), int(rng.choice([10**6, drawsize * int(rng.integers(1, 8))])),
+               [None, 1, int(rng.integers(1, 400))][int(rng.integers(0, 3))]) for _ in range(25)]
+    for n_samples, max_samples, hint in cases:
+        if hint is not None:
+            ea._accept_hint = hint
+        ra, pa, aa = pipelined(ea, n_samples, drawsize, max_samples=max_samples)
+        rb, pb, ab = eb._run_serial(n_samples, drawsize, max_samples, None, False)
+        assert (pa, aa) == (pb, ab) and ea._turn_rows == eb._turn_rows, (n_samples, max_samples, hint)
+        assert ra.dtype == rb.dtype and len(ra) == len(rb) == min(aa, n_samples)
+        assert ra.tobytes() == rb.tobytes(), (n_samples, max_samples, hint)
