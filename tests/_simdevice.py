@@ -185,6 +185,41 @@ def install(monkeypatch=None):
     return sim
 
 
+def install_fake_cuda_async(monkeypatch=None):
+    """Stand-ins for CUDA events / streams / pinned allocations so that the software-pipelined
+    loop can run on the host: every "asynchronous" operation completes at once, which checks the
+    loop's bookkeeping, not its stream ordering."""
+    import contextlib
+
+    import torch
+
+    patch = monkeypatch.setattr if monkeypatch is not None else setattr
+
+    class Event:
+        def record(self, stream=None):
+            pass
+
+        def synchronize(self):
+            pass
+
+    class Stream:
+        def __init__(self, device=None):
+            pass
+
+        def wait_event(self, ev):
+            pass
+
+        def synchronize(self):
+            pass
+
+    patch(torch.cuda, "Event", Event)
+    patch(torch.cuda, "Stream", Stream)
+    patch(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    for name in ("empty", "zeros"):
+        orig = getattr(torch, name)
+        patch(torch, name, lambda *a, _o=orig, **k: _o(*a, **{**k, "pin_memory": False}))
+
+
 class SimFlowModel:
     """The two attributes ``PopulateEngine`` reads from a ``B200FlowModel``."""
 

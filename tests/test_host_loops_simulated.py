@@ -263,12 +263,25 @@ def _rank_worker(rank, world, port, out):
     from nessai_b200.livepoint import get_dtype
     from nessai_b200.proposal import GeneralPopulateEngine, PopulateEngine
 
+    pipelined = PopulateEngine.run  # before install() replaces it by the serial loop
     _simdevice.install()
+    _simdevice.install_fake_cuda_async()
     nf, D = _flow()
     names = [f"x{i}" for i in range(D)]
     scale, shift = _zscore(D)
     lpc, radius, drawsize = -D * np.log(8.0), 4.9, 1001  # ragged shards: 501 + 500
     res = {}
+    # (0) the pipelined loop; with two ranks the pool is assembled in node-local shared host
+    # memory (hostpool.py), every rank copying only its own records, turn-major
+    eng = PopulateEngine(_simdevice.SimFlowModel(nf, D), names, get_dtype(names))
+    eng.configure(scale, shift, np.full(D, -4.0), np.full(D, 4.0), lpc, radius)
+    eng.seed = 4242
+    pools = []
+    for n_samples, max_samples in ((10**5, 3 * drawsize - 1), (40, 10**6), (75, 10**6)):
+        rows, p, a = pipelined(eng, n_samples, drawsize, max_samples=max_samples)
+        pools.append((np.stack([rows[nm] for nm in names], axis=-1).copy(), p, a))
+    res["pipelined"] = pools
+    res["shared_pool"] = getattr(eng, "_pool", None) is not None
     eng = PopulateEngine(_simdevice.SimFlowModel(nf, D), names, get_dtype(names))
     eng.configure(scale, shift, np.full(D, -4.0), np.full(D, 4.0), lpc, radius)
     eng.seed = 4242
@@ -310,6 +323,14 @@ def test_two_ranks_reproduce_one_rank(tmp_path):
         assert a.shape == b.shape and len(a) > 0
         np.testing.assert_array_equal(a[np.lexsort(a.T)], b[np.lexsort(b.T)])
 
+    # pipelined loop + shared host pool: same turns, same counts, same pool on both ranks
+    assert r0["shared_pool"] and r1["shared_pool"] and not one["shared_pool"]
+    for k, (a0, a1, a_one) in enumerate(zip(r0["pipelined"], r1["pipelined"], one["pipelined"])):
+        assert a0[1:] == a1[1:] == a_one[1:]
+        np.testing.assert_array_equal(a0[0], a1[0])
+        # turn-major, and rank-major within a turn = draw order (the shards are contiguous): the
+        # shared-pool path returns the very pool one rank returns, row for row
+        np.testing.assert_array_equal(a0[0], a_one[0])
     for key in ("loop", "tail"):
         assert one[key][1:] == r0[key][1:] == r1[key][1:] and one[key][1] == 3 * 1001
         np.testing.assert_array_equal(r0[key][0], r1[key][0])  # the same pool on every rank
@@ -440,39 +461,12 @@ def test_pipelined_loop_logic_equals_serial_loop(monkeypatch):
     On the simulated device every "asynchronous" operation completes at once, so this checks the
     bookkeeping (what tests/test_gpu_populate.py::test_pipelined_loop_matches_serial_loop checks on
     the GPU for four cases), not the stream ordering."""
-    import contextlib
-
-    import torch
-
     from nessai_b200 import proposal
     from nessai_b200.livepoint import get_dtype
 
     pipelined = proposal.PopulateEngine.run  # before install() replaces it by the serial loop
     _simdevice.install(monkeypatch)
-
-    class Event:
-        def record(self, stream=None):
-            pass
-
-        def synchronize(self):
-            pass
-
-    class Stream:
-        def __init__(self, device=None):
-            pass
-
-        def wait_event(self, ev):
-            pass
-
-        def synchronize(self):
-            pass
-
-    monkeypatch.setattr(torch.cuda, "Event", Event)
-    monkeypatch.setattr(torch.cuda, "Stream", Stream)
-    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
-    for name in ("empty", "zeros"):
-        orig = getattr(torch, name)
-        monkeypatch.setattr(torch, name, lambda *a, _o=orig, **k: _o(*a, **{**k, "pin_memory": False}))
+    _simdevice.install_fake_cuda_async(monkeypatch)
     nf, D = _flow()
     names = [f"x{i}" for i in range(D)]
     scale, shift = _zscore(D)
