@@ -134,17 +134,17 @@ def gather_records(local_rows: torch.Tensor, n_local: int, n_keep: int, row_byte
         left -= k
     total = sum(take)
     if to_host and dev.type == "cuda":
-        if os.environ.get("NB200_TIMING"):
+        timing = bool(os.environ.get("NB200_TIMING"))
+        if timing:
             import sys
             import time
 
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
-            host = torch.empty(total * row_bytes, dtype=torch.uint8, pin_memory=True)
-            t1 = time.perf_counter()
-            if dist.get_rank(group) == 0:
-                print(f"[nb200 timing] pinned alloc {1e3 * (t1 - t0):.2f} ms for {total * row_bytes / 1e6:.1f} MB", file=sys.stderr)
         host = torch.empty(total * row_bytes, dtype=torch.uint8, pin_memory=True)
+        if timing and dist.get_rank(group) == 0:
+            print(f"[nb200 timing] pinned alloc {1e3 * (time.perf_counter() - t0):.2f} ms for "
+                  f"{total * row_bytes / 1e6:.1f} MB", file=sys.stderr)
         off = 0
         for r in range(world):
             nb = take[r] * row_bytes

@@ -3,10 +3,14 @@ and CPU-checked (oracle pins, host-compiled row function, loop control) without 
 GPU, so this file sorts last:
 
 * the non-affine populate tail (``nb200_reparam_tail`` + ``nb200_populate_accept_x64``,
-  ``GeneralPopulateEngine``): logit / log post-rescaling and boundary inversion,
-  reparameterisations/rescale.py:570-590,635-660;
+  ``GeneralPopulateEngine``): named pre- / post-rescalings (logit, log, exp, Gaussian CDF and
+  its inverse) and boundary inversion, reparameterisations/rescale.py:263-291,570-590,635-660;
 * ``accumulate_weights`` (``nb200_sum_exp``, ``PopulateEngine.run_accumulate``),
-  flowproposal.py:414-417,471-490,504-512.
+  flowproposal.py:414-417,471-490,504-512;
+* ``B200AugmentedFlowProposal`` (plugin point P2 of proposal/augmented.py).
+
+The bodies of the first two groups also run on the CPU against the simulated device
+(tests/tools/dryrun_gpu_tests_on_sim.py, tests/test_host_loops_simulated.py).
 """
 
 import numpy as np
