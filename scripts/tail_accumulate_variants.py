@@ -126,6 +126,13 @@ def main():
         "n_expected_last": info["n_expected"][-1],
         "n_expected_check": float(torch.exp(lw[okw] - lw[okw].max()).sum()),
     }
+    # the sum-exp reduction alone, over 8e6 rows of weights (HBM-bound: 8 B/row)
+    m = min(8 * n, aff.d_logw.shape[0])
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    se_ms = timed(lambda: aff._call(lib.nb200_sum_exp, [aff.d_logw.data_ptr(), m, aff.d_stats.data_ptr(),
+                                                         aff.d_partials.data_ptr(), aff._N_PARTIALS, st], "nb200_sum_exp"))
+    out["sum_exp"] = {"rows": m, "kernel_ms": se_ms, "gbs": 8 * m / (se_ms * 1e-3) / 1e9}
     out["kernel_launches"] = _lib.launch_count()
     print(json.dumps(out), flush=True)
 
