@@ -427,3 +427,44 @@ def test_augmented_flow_proposal_on_b200_flows(tmp_path, marginalise):
         prop.rng = np.random.default_rng(1)
         b = prop._marginalise_augment(x.copy())
         assert np.all(np.isfinite(a)) and np.max(np.abs(a - b)) < 0.3
+
+
+@pytest.mark.parametrize("name", ["c2_realnvp_mlp", "c2_realnvp_resnet", "d6_nsf", "d8_maf", "c1_realnvp_2d"])
+def test_reference_self_consistency_pins(name, tmp_path):
+    """The self-consistency properties the reference's own tests pin at this boundary
+    (SURVEY.md 8c), on the kernels:
+    forward_and_log_prob(x) == (forward(x)[0], log_prob(x)) bit for bit
+    (tests/test_flows/test_included_flows.py:114-126); float64 outputs
+    (tests/test_flowmodel/test_flowmodel_base.py:543-549); sample_and_log_prob(z=z) ==
+    base_log_prob(z) - inverse(z)[1] (:552-570); outputs identical before and after the
+    train() -> eval() cache reset (:751-788, bit-exact)."""
+    from test_gpu_flow import make_model
+
+    g, cfg, sd = load_golden(name)
+    fm = make_model(cfg, sd, tmp_path)
+    x, zz = np.asarray(g["x"], dtype=np.float64), np.asarray(g["z"], dtype=np.float64)
+    z, lp = fm.forward_and_log_prob(x)
+    assert z.dtype == np.float64 and lp.dtype == np.float64 and z.shape == x.shape and lp.shape == (len(x),)
+    xt = fm.numpy_array_to_tensor(x)
+    z2, _ = fm.model.forward(xt)
+    lp2 = fm.model.log_prob(xt)
+    np.testing.assert_array_equal(z, z2.cpu().numpy().astype(np.float64))
+    np.testing.assert_array_equal(lp, lp2.cpu().numpy().astype(np.float64))
+    np.testing.assert_array_equal(fm.log_prob(x), lp)
+    x3, lq = fm.sample_and_log_prob(z=zz)
+    x4, lj = fm.inverse(zz)
+    assert x3.dtype == lq.dtype == x4.dtype == lj.dtype == np.float64
+    base = fm.model.base_distribution_log_prob(fm.numpy_array_to_tensor(zz)).cpu().numpy().astype(np.float64)
+    np.testing.assert_array_equal(x3, x4)
+    ok = np.isfinite(lq)
+    assert ok.mean() > 0.9
+    np.testing.assert_allclose(lq[ok], (base - lj)[ok], rtol=1e-5, atol=1e-4)
+    fm.model.train()
+    fm.model.eval()  # flowmodel/base.py:680-682
+    z5, lp5 = fm.forward_and_log_prob(x)
+    np.testing.assert_array_equal(z5, z)
+    np.testing.assert_array_equal(lp5, lp)
+    # inputs are caller-owned and never mutated; outputs are fresh and writable (SURVEY 8b P2)
+    assert np.array_equal(x, np.asarray(g["x"], dtype=np.float64))
+    lp -= 1.0
+    assert not np.shares_memory(lp, z)
