@@ -136,10 +136,17 @@ int nb200_populate_accept_x64(int64_t n, int D, const double* d_x64, const doubl
  * log q (NaN: dropped).  Rewrites d_logq (-= log|J|), d_logw (= log_prior_const - log_q; NaN
  * for rows outside d_lo/d_hi, with non-finite log_q or log_q <= min_log_q), writes
  * d_x64 float64[n*D], and accumulates d_stats = {max log_w, n_valid} (reset by the caller).
+ * Pair kinds, reparameterisations/angle.py:17-186 (Angle.inverse_reparameterise): output slot d
+ * reads TWO flow features (u0, u1) = (x'[d_src[2d]], x'[d_src[2d+1]]): kind 7 the angle
+ * atan2(u1, u0) * scale + shift (scale = 1 / Angle.scale; no log|J| for that constant, as in the
+ * reference), 8 the same modulo 2 pi (prior starting at zero, angle.py:158-166), 9 the radius
+ * sqrt(u0^2 + u1^2) with log|J| -= log r (:172), 10 the same for an AUXILIARY radius whose chi(2)
+ * prior log r - r^2/2 (:183-185) is added to log_w.  d_src int32[2*D] or NULL (slot d reads
+ * feature d); for the other kinds only d_src[2d] is used.
  * d_kind int32[D], d_scale/d_shift/d_lo/d_hi float64[D] on the device; d_pre_scale /
  * d_pre_shift float64[D] or both NULL (a = 1, b = 0); D <= 64. */
 int nb200_reparam_tail(int64_t n, int D, const float* d_xp, const int32_t* d_kind,
-                       const double* d_pre_scale, const double* d_pre_shift,
+                       const int32_t* d_src, const double* d_pre_scale, const double* d_pre_shift,
                        const double* d_scale, const double* d_shift, const double* d_lo,
                        const double* d_hi, double log_prior_const, double min_log_q,
                        double* d_logq, double* d_logw, double* d_x64, double* d_stats,

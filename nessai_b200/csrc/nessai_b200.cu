@@ -680,7 +680,8 @@ extern "C" int nb200_populate_accept_x64(int64_t n, int D, const double* d_x64, 
 }
 
 extern "C" int nb200_reparam_tail(int64_t n, int D, const float* d_xp, const int32_t* d_kind,
-                                  const double* d_pre_scale, const double* d_pre_shift,
+                                  const int32_t* d_src, const double* d_pre_scale,
+                                  const double* d_pre_shift,
                                   const double* d_scale, const double* d_shift, const double* d_lo,
                                   const double* d_hi, double log_prior_const, double min_log_q,
                                   double* d_logq, double* d_logw, double* d_x64, double* d_stats,
@@ -695,7 +696,7 @@ extern "C" int nb200_reparam_tail(int64_t n, int D, const float* d_xp, const int
   CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = (int)std::min<int64_t>((n + TAIL_THREADS - 1) / TAIL_THREADS, (int64_t)sms * 8);
   reparam_tail_kernel<<<grid, TAIL_THREADS, 0, (cudaStream_t)stream>>>(
-      n, D, d_xp, d_kind, d_pre_scale, d_pre_shift, d_scale, d_shift, d_lo, d_hi,
+      n, D, d_xp, d_kind, d_src, d_pre_scale, d_pre_shift, d_scale, d_shift, d_lo, d_hi,
       isnan(log_prior_const) ? 0.0 : log_prior_const, isnan(min_log_q) ? -INFINITY : min_log_q,
       d_logq, d_logw, d_x64, d_stats);
   g_launches += 1;

@@ -33,7 +33,16 @@ namespace nb200 {
 
 enum TailKind : int32_t {
   TAIL_IDENTITY = 0, TAIL_SIGMOID = 1, TAIL_ABS = 2, TAIL_EXP = 3, TAIL_LOG = 4,
-  TAIL_NORMAL_CDF = 5, TAIL_NORMAL_QUANTILE = 6, TAIL_N_KINDS = 7
+  TAIL_NORMAL_CDF = 5, TAIL_NORMAL_QUANTILE = 6,
+  // pair kinds: the output is a function of TWO flow features (u0, u1) = (x'[src0], x'[src1]),
+  // the Cartesian pair of reparameterisations/angle.py:17-186 (Angle.inverse_reparameterise)
+  TAIL_PAIR_FIRST = 7,
+  TAIL_ANGLE = 7,       // atan2(u1, u0) * scale + shift           (scale = 1 / Angle.scale)
+  TAIL_ANGLE_MOD = 8,   // (atan2(u1, u0) mod 2 pi) * scale + shift (prior starting at zero)
+  TAIL_RADIUS = 9,      // sqrt(u0^2 + u1^2), log|J| -= log r
+  TAIL_RADIUS_CHI = 10, // the same for an AUXILIARY radius: its chi(2) prior log r - r^2 / 2 is
+                        // added to the log prior (angle.py:183-185)
+  TAIL_N_KINDS = 11
 };
 
 #ifdef __CUDACC__
@@ -71,30 +80,65 @@ NB200_HD double tail_feature(int32_t kind, double a, double b, double scale, dou
   return h * scale + shift;
 }
 
+// A pair kind: x from (u0, u1); the constant factor of the angle has NO log-Jacobian in the
+// reference (angle.py:120-128,157-170), so scale / shift of pair kinds stay out of the row constant.
+NB200_HD double tail_pair(int32_t kind, double scale, double shift, double u0, double u1, double& logj,
+                          double& logp_extra) {
+  if (kind == TAIL_ANGLE || kind == TAIL_ANGLE_MOD) {
+    double th = atan2(u1, u0);
+    // numpy's `% (2 pi)` of a value in [-pi, pi]: fmod, then + 2 pi when negative (a tiny
+    // negative angle therefore gives exactly 2 pi, as it does in the reference)
+    if (kind == TAIL_ANGLE_MOD && th < 0.0) th += 6.283185307179586;
+    return th * scale + shift;
+  }
+  const double r = sqrt(u0 * u0 + u1 * u1);
+  const double lr = log(r);
+  logj -= lr;
+  if (kind == TAIL_RADIUS_CHI) logp_extra += lr - 0.5 * r * r;
+  return r * scale + shift;
+}
+
 // One row.  logq_flow: log q of the flow alone (NaN: the row was already dropped by the draw
-// kernel).  log_affine_sum = sum_d (log|scale_d| + log|a_d|).  pre_a / pre_b may be NULL
-// (a = 1, b = 0).  Writes x[D]; returns true when the row survives and then logq_out / logw_out
-// are its log q / log weight.
-NB200_HD bool tail_row(int D, const float* xp, const int32_t* kind, const double* pre_a,
-                       const double* pre_b, const double* scale, const double* shift,
-                       const double* lo, const double* hi, double log_affine_sum,
-                       double log_prior_const, double min_log_q, double logq_flow, double* x,
-                       double& logq_out, double& logw_out) {
-  double logj = log_affine_sum;
+// kernel).  log_affine_sum = sum over the non-pair slots of (log|scale_d| + log|a_d|).  pre_a /
+// pre_b may be NULL (a = 1, b = 0); src (int32[2 D]: the one or two flow features output slot d
+// reads) may be NULL (slot d reads feature d).  Writes x[D]; returns true when the row survives
+// and then logq_out / logw_out are its log q / log weight.
+NB200_HD bool tail_row(int D, const float* xp, const int32_t* kind, const int32_t* src,
+                       const double* pre_a, const double* pre_b, const double* scale,
+                       const double* shift, const double* lo, const double* hi,
+                       double log_affine_sum, double log_prior_const, double min_log_q,
+                       double logq_flow, double* x, double& logq_out, double& logw_out) {
+  double logj = log_affine_sum, logp_extra = 0.0;
   bool inb = true;
   for (int d = 0; d < D; ++d) {
-    const double xv = tail_feature(kind[d], pre_a ? pre_a[d] : 1.0, pre_b ? pre_b[d] : 0.0, scale[d],
-                                   shift[d], (double)xp[d], logj);
+    const int i0 = src ? src[2 * d] : d;
+    double xv;
+    if (kind[d] >= TAIL_PAIR_FIRST) {
+      xv = tail_pair(kind[d], scale[d], shift[d], (double)xp[i0], (double)xp[src ? src[2 * d + 1] : d],
+                     logj, logp_extra);
+    } else {
+      xv = tail_feature(kind[d], pre_a ? pre_a[d] : 1.0, pre_b ? pre_b[d] : 0.0, scale[d], shift[d],
+                        (double)xp[i0], logj);
+    }
     x[d] = xv;
     inb = inb && !(xv < lo[d]) && !(xv > hi[d]);
   }
   const double logq = logq_flow - logj;
-  // (logq - logq == 0) is isfinite(): it also rejects the NaN of an already-dropped row and of
-  // a log / quantile evaluated outside its domain
-  const bool ok = inb && (logq - logq == 0.0) && (logq > min_log_q);
+  const double logw = log_prior_const + logp_extra - logq;
+  // (v - v == 0) is isfinite(): it also rejects the NaN of an already-dropped row and of a
+  // log / quantile evaluated outside its domain
+  const bool ok = inb && (logq - logq == 0.0) && (logw - logw == 0.0) && (logq > min_log_q);
   logq_out = ok ? logq : NAN;
-  logw_out = ok ? (log_prior_const - logq) : NAN;
+  logw_out = ok ? logw : NAN;
   return ok;
+}
+
+// The row constant of log|J|: the affine parts of the non-pair slots.
+NB200_HD double tail_log_affine_sum(int D, const int32_t* kind, const double* pre_a, const double* scale) {
+  double s = 0.0;
+  for (int d = 0; d < D; ++d)
+    if (kind[d] < TAIL_PAIR_FIRST) s += log(fabs(scale[d])) + (pre_a ? log(fabs(pre_a[d])) : 0.0);
+  return s;
 }
 
 #ifdef __CUDACC__
@@ -105,13 +149,14 @@ NB200_HD bool tail_row(int D, const float* xp, const int32_t* kind, const double
 // the draw kernel's time).  The per-feature constants sit in shared memory.
 __global__ void __launch_bounds__(TAIL_THREADS)
 reparam_tail_kernel(int64_t n, int D, const float* __restrict__ xp, const int32_t* __restrict__ kind,
-                    const double* __restrict__ pre_a, const double* __restrict__ pre_b,
+                    const int32_t* __restrict__ src, const double* __restrict__ pre_a, const double* __restrict__ pre_b,
                     const double* __restrict__ scale, const double* __restrict__ shift,
                     const double* __restrict__ lo, const double* __restrict__ hi,
                     double log_prior_const, double min_log_q, double* __restrict__ logq,
                     double* __restrict__ logw, double* __restrict__ x64, double* __restrict__ stats) {
   __shared__ double c_s[6 * TAIL_MAXD];  // scale | shift | lo | hi | a | b
   __shared__ int32_t k_s[TAIL_MAXD];
+  __shared__ int32_t src_s[2 * TAIL_MAXD];
   __shared__ double lss_s;
   for (int d = threadIdx.x; d < D; d += TAIL_THREADS) {
     c_s[d] = scale[d];
@@ -121,12 +166,10 @@ reparam_tail_kernel(int64_t n, int D, const float* __restrict__ xp, const int32_
     c_s[4 * TAIL_MAXD + d] = pre_a ? pre_a[d] : 1.0;
     c_s[5 * TAIL_MAXD + d] = pre_b ? pre_b[d] : 0.0;
     k_s[d] = kind[d];
+    src_s[2 * d] = src ? src[2 * d] : d;
+    src_s[2 * d + 1] = src ? src[2 * d + 1] : d;
   }
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int d = 0; d < D; ++d) s += log(fabs(scale[d])) + (pre_a ? log(fabs(pre_a[d])) : 0.0);
-    lss_s = s;
-  }
+  if (threadIdx.x == 0) lss_s = tail_log_affine_sum(D, kind, pre_a, scale);
   __syncthreads();
   double vmax = -INFINITY, vcount = 0.0;
   for (int64_t row = (int64_t)blockIdx.x * TAIL_THREADS + threadIdx.x; row < n;
@@ -134,7 +177,7 @@ reparam_tail_kernel(int64_t n, int D, const float* __restrict__ xp, const int32_
     // x is written straight to global memory (every row: the accept kernel only reads the
     // rows it keeps, and a device likelihood may read them all)
     double lq, lw;
-    const bool ok = tail_row(D, xp + row * D, k_s, c_s + 4 * TAIL_MAXD, c_s + 5 * TAIL_MAXD, c_s,
+    const bool ok = tail_row(D, xp + row * D, k_s, src_s, c_s + 4 * TAIL_MAXD, c_s + 5 * TAIL_MAXD, c_s,
                              c_s + TAIL_MAXD, c_s + 2 * TAIL_MAXD, c_s + 3 * TAIL_MAXD, lss_s,
                              log_prior_const, min_log_q, logq[row], x64 + row * D, lq, lw);
     logq[row] = lq;

@@ -26,7 +26,7 @@ import numpy as np
 from nessai import config as nessai_config
 from nessai.livepoint import empty_structured_array as nessai_empty_structured_array
 from nessai.proposal.flowproposal import FlowProposal
-from nessai.reparameterisations import NullReparameterisation, RescaleToBounds, ScaleAndShift
+from nessai.reparameterisations import Angle, NullReparameterisation, RescaleToBounds, ScaleAndShift
 from nessai.utils import rescaling as _ref_rescaling
 
 from .flowmodel import B200FlowModel
@@ -37,7 +37,7 @@ logger = logging.getLogger(__name__)
 
 # per-parameter map kinds of the device tail (csrc/reparam_tail.cuh: TailKind)
 (KIND_IDENTITY, KIND_SIGMOID, KIND_ABS, KIND_EXP, KIND_LOG, KIND_NORMAL_CDF,
- KIND_NORMAL_QUANTILE) = range(7)
+ KIND_NORMAL_QUANTILE, KIND_ANGLE, KIND_ANGLE_MOD, KIND_RADIUS, KIND_RADIUS_CHI) = range(11)
 
 # the INVERSE function of a named rescaling (utils/rescaling.py:410-417) -> the kind of h
 _INVERSE_KINDS = (
@@ -57,29 +57,34 @@ def _kind_of(fn):
 
 
 class ParameterMaps(NamedTuple):
-    """``x = h(pre_scale * x' + pre_shift) * scale + shift`` per parameter (model order)."""
+    """``x = h(pre_scale * x'[src] + pre_shift) * scale + shift`` per x-space parameter ``names[d]``
+    (``src[d]``: the one or, for the pair kinds of ``Angle``, two prime parameters it reads)."""
 
     kind: np.ndarray
     scale: np.ndarray
     shift: np.ndarray
     pre_scale: np.ndarray
     pre_shift: np.ndarray
+    src: np.ndarray  # (D, 2) indices into the prime parameters
+    names: list  # x-space parameters: the model's, then auxiliary ones (flowproposal/base.py:539-546)
 
     @property
     def affine(self) -> bool:
-        return not np.any(self.kind != KIND_IDENTITY)
+        d = np.arange(len(self.kind))
+        return not np.any(self.kind != KIND_IDENTITY) and bool(np.all(self.src[:, 0] == d))
 
     @property
     def has_pre_affine(self) -> bool:
         return bool(np.any(self.pre_scale != 1.0) or np.any(self.pre_shift != 0.0))
 
 
-def parameter_maps(rep, prime_parameters, model_names):
+def parameter_maps(rep, prime_parameters, model_names, x_parameters=None):
     """The combined reparameterisation ``rep`` (reparameterisations/combined.py:154-192) as
-    one-to-one per-parameter maps ``x = h(a x' + b) * scale + shift`` with ``h`` = identity /
-    sigmoid / ``|.|`` / exp / log / normal CDF / normal quantile (a ``ParameterMaps``), or ``None``
-    when it is not made of such maps.  ``log|J| = sum log|scale| + sum log|a| + sum log|h'|``.
-    Recognised:
+    per-parameter maps ``x = h(a x' + b) * scale + shift`` with ``h`` = identity / sigmoid /
+    ``|.|`` / exp / log / normal CDF / normal quantile, plus the Cartesian pairs of ``Angle`` (a
+    ``ParameterMaps``), or ``None`` when it is not made of such maps.  ``x_parameters``: the
+    proposal's x-space parameters (model names, then auxiliary ones; default the model's).
+    ``log|J| = sum log|scale| + sum log|a| + sum log|h'|``.  Recognised:
 
     * ``NullReparameterisation`` (reparameterisations/null.py): identity;
     * ``ScaleAndShift`` / ``Rescale`` (rescale.py:233-291): ``x = x' * scale + shift``; with a
@@ -94,20 +99,33 @@ def parameter_maps(rep, prime_parameters, model_names):
       utils/rescaling.py:290-417); with boundary inversion (rescale.py:570-590) ``h = |.|`` and
       the detected edge picks the map: "lower" ``[0, 1] -> [lo, hi]``, "upper" ``1 - |x'|`` first
       (negative scale), no edge ``[-1, 1] -> [lo, hi]`` with ``h`` = identity; with a named
-      pre-rescaling that affine map becomes ``a, b`` and ``h = P^-1`` comes last.
+      pre-rescaling that affine map becomes ``a, b`` and ``h = P^-1`` comes last;
+    * the stock ``Angle`` (angle.py:17-186; "angle", "angle-pi", "angle-2pi", "periodic"): the two
+      prime parameters are Cartesian coordinates, ``angle = atan2(y', x') [% 2 pi] / scale`` and
+      ``r = sqrt(x'^2 + y'^2)`` with ``log|J| -= log r``; ``r`` is the model's radial parameter or an
+      auxiliary one with a ``chi(2)`` prior.
 
     Anything else (user rescaling callables, two non-linear stages on one parameter, an edge
-    not detected yet, angles, user classes) keeps the reference's host loop."""
+    not detected yet, ``AnglePair`` / ``ToCartesian`` / ``Dequantise``, user classes) keeps the
+    reference's host loop."""
     if rep is None:
         return None
-    if list(prime_parameters) != [p for r in rep.values() for p in r.output_parameters]:
+    prime_parameters = list(prime_parameters)
+    x_parameters = list(model_names) if x_parameters is None else list(x_parameters)
+    if prime_parameters != [p for r in rep.values() for p in r.output_parameters]:
         return None
-    rows, names = [], []  # rows: (kind, scale, shift, a, b)
+    specs = {}  # x-space name -> (kind, scale, shift, a, b, source prime names)
     for r in rep.values():
         if isinstance(r, NullReparameterisation):
-            for p in r.parameters:
-                rows.append((KIND_IDENTITY, 1.0, 0.0, 1.0, 0.0))
-                names.append(p)
+            for p, pp in zip(r.parameters, r.output_parameters):
+                specs[p] = (KIND_IDENTITY, 1.0, 0.0, 1.0, 0.0, (pp, pp))
+            continue
+        if type(r) is Angle:
+            if len(r.output_parameters) != 2 or not np.isfinite(r.scale) or r.scale == 0:
+                return None
+            pair = (r.x, r.y)
+            specs[r.angle] = (KIND_ANGLE_MOD if r._zero_bound else KIND_ANGLE, 1.0 / float(r.scale), 0.0, 1.0, 0.0, pair)
+            specs[r.radial] = (KIND_RADIUS_CHI if r.chi else KIND_RADIUS, 1.0, 0.0, 1.0, 0.0, pair)
             continue
         if not (isinstance(r, ScaleAndShift) or type(r) is RescaleToBounds) or not r.one_to_one:
             # (RescaleToBounds subclasses may override the rescaling hooks: stock class only)
@@ -116,7 +134,7 @@ def parameter_maps(rep, prime_parameters, model_names):
         post = _kind_of(r.post_rescaling_inv) if r.has_post_rescaling else KIND_IDENTITY
         if pre is None or post is None or (pre != KIND_IDENTITY and post != KIND_IDENTITY):
             return None
-        for p in r.parameters:
+        for p, pp in zip(r.parameters, r.output_parameters):
             k = post
             if isinstance(r, ScaleAndShift):
                 s, t = float(r.scale[p]), (float(r.shift[p]) if r.shift else 0.0)
@@ -139,15 +157,23 @@ def parameter_maps(rep, prime_parameters, model_names):
                     s = (hi - lo) / float(r._rescale_factor[p])
                     t = lo + off - s * float(r._rescale_shift[p])
             if pre != KIND_IDENTITY:
-                rows.append((pre, 1.0, 0.0, s, t))  # the affine map first, then P^-1
+                specs[p] = (pre, 1.0, 0.0, s, t, (pp, pp))  # the affine map first, then P^-1
             else:
-                rows.append((k, s, t, 1.0, 0.0))
-            names.append(p)
-    if names != list(model_names):
+                specs[p] = (k, s, t, 1.0, 0.0, (pp, pp))
+    if set(specs) != set(x_parameters) or len(x_parameters) != len(prime_parameters):
         return None
-    cols = list(zip(*rows))
-    maps = ParameterMaps(np.asarray(cols[0], dtype=np.int32), *(np.asarray(c, dtype=np.float64) for c in cols[1:]))
-    for v in maps[1:]:
+    if list(x_parameters[: len(model_names)]) != list(model_names):
+        return None
+    try:
+        src = np.asarray([[prime_parameters.index(q) for q in specs[n][5]] for n in x_parameters], dtype=np.int32)
+    except ValueError:
+        return None
+    if set(src.ravel().tolist()) != set(range(len(prime_parameters))):
+        return None  # a prime parameter nobody reads: not a bijection
+    cols = list(zip(*(specs[n][:5] for n in x_parameters)))
+    maps = ParameterMaps(np.asarray(cols[0], dtype=np.int32), *(np.asarray(c, dtype=np.float64) for c in cols[1:]),
+                         src, x_parameters)
+    for v in maps[1:5]:
         if not np.all(np.isfinite(v)):
             return None
     if np.any(maps.scale == 0.0) or np.any(maps.pre_scale == 0.0):
@@ -187,7 +213,7 @@ class B200NessaiFlowProposal(FlowProposal):
         per-parameter maps the device evaluates, else None."""
         if self.map_to_unit_hypercube:
             return None
-        return parameter_maps(self._reparameterisation, self.prime_parameters, self.model.names)
+        return parameter_maps(self._reparameterisation, self.prime_parameters, self.model.names, self.parameters)
 
     def _fused_rules(self):
         """The truncation rules as a name -> rule dict if the device loop implements all of
@@ -214,13 +240,16 @@ class B200NessaiFlowProposal(FlowProposal):
             eligible = False
         if eligible:
             affine = maps.affine
+            # auxiliary x-space parameters (the radius of a lone Angle): fields of the population
+            # records that the sampler never sees (flowproposal/base.py:1100-1128)
+            aux = len(maps.names) > len(self.model.names)
             engine_cls = PopulateEngine if affine else GeneralPopulateEngine
             if (self._engine is None or self._engine.flow is not self.flow
-                    or type(self._engine) is not engine_cls):
+                    or type(self._engine) is not engine_cls or self._engine.names != list(maps.names)):
                 # (the class can change between populates: boundary inversion re-detects its
                 # edges whenever the flow is retrained, rescale.py:662-665)
                 self._engine = engine_cls(
-                    self.flow, self.model.names, self.population_dtype,
+                    self.flow, maps.names, self.population_dtype,
                     row_template=nessai_empty_structured_array(1, dtype=self.population_dtype),
                 )
                 self._log_prior_const = (
@@ -232,6 +261,8 @@ class B200NessaiFlowProposal(FlowProposal):
                 not affine or "likelihood_threshold" in rules or self._log_prior_const is None
             ):
                 eligible = False  # the accumulating device loop: affine maps, device prior
+            if aux and ("likelihood_threshold" in rules or self._log_prior_const is None):
+                eligible = False  # their prior is added by the tail kernel; the hooks see model parameters only
         if not eligible:
             logger.debug("B200: configuration not eligible for the fused loop; using the host loop")
             return super().populate(worst_point, n_samples=n_samples, plot=plot, r=r, max_samples=max_samples)
@@ -239,11 +270,12 @@ class B200NessaiFlowProposal(FlowProposal):
         if self.indices:
             logger.debug("Existing pool of samples is not empty. Discarding existing samples.")
         self.indices = []
-        lo = [self.model.bounds[n][0] for n in self.model.names]
-        hi = [self.model.bounds[n][1] for n in self.model.names]
+        unbounded = (-np.inf, np.inf)
+        lo = [self.model.bounds.get(n, unbounded)[0] for n in maps.names]
+        hi = [self.model.bounds.get(n, unbounded)[1] for n in maps.names]
         t = self.latent_temperature
         in_loop = "likelihood_threshold" in rules
-        extra = {} if affine else dict(pre_scale=maps.pre_scale, pre_shift=maps.pre_shift)
+        extra = {} if affine else dict(pre_scale=maps.pre_scale, pre_shift=maps.pre_shift, src=maps.src)
         self._engine.configure(
             *((maps.scale, maps.shift) if affine else (maps.kind, maps.scale, maps.shift)),
             lo, hi, self._log_prior_const,
@@ -265,7 +297,8 @@ class B200NessaiFlowProposal(FlowProposal):
                 int(n_samples), int(self.drawsize), max_samples=max_samples, host_prior=host_prior
             )
         self.x = rows
-        self.samples = self.convert_to_samples(self.x, plot=plot) if host_prior is not None else rows
+        # (with auxiliary parameters the reference's own repacking drops them and sets logP)
+        self.samples = self.convert_to_samples(self.x, plot=plot) if (host_prior is not None or aux) else rows
         if self._plot_pool and plot:
             self.plot_pool(self.samples)
         self.population_time += datetime.datetime.now() - st
@@ -274,7 +307,7 @@ class B200NessaiFlowProposal(FlowProposal):
         else:
             logger.debug("Evaluating log-likelihoods")
             fn = getattr(self.model, "log_likelihood_torch", None)
-            if fn is not None and self._engine.world == 1 and host_prior is None and len(rows):
+            if fn is not None and self._engine.world == 1 and host_prior is None and not aux and len(rows):
                 # the accepted records are still on the device: 8 bytes per row come back
                 self.samples["logL"] = self._engine.device_log_likelihood(len(rows), fn).cpu().numpy()
                 self.model.likelihood_evaluations += len(rows)

@@ -840,7 +840,7 @@ class GeneralPopulateEngine(PopulateEngine):
     The loop, its pipelining and the multi-GPU exchange are the base class's."""
 
     MAX_D = 64  # TAIL_MAXD
-    N_KINDS = 7  # TAIL_N_KINDS
+    N_KINDS = 11  # TAIL_N_KINDS
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
@@ -850,11 +850,15 @@ class GeneralPopulateEngine(PopulateEngine):
         self._tail_min_log_q = -float("inf")
 
     def configure(self, kind, scale, shift, lo, hi, log_prior_const, r_max, sqrt_temperature=1.0, min_log_q=None,
-                  likelihood=None, log_l_threshold=None, pre_scale=None, pre_shift=None):
+                  likelihood=None, log_l_threshold=None, pre_scale=None, pre_shift=None, src=None):
         """As ``PopulateEngine.configure`` with the per-parameter ``kind`` of ``h`` in front
         (0 identity, 1 sigmoid, 2 abs, 3 exp, 4 log, 5 normal CDF, 6 normal quantile) and the
-        optional affine map applied BEFORE ``h``: ``x = h(pre_scale x' + pre_shift) scale + shift``."""
+        optional affine map applied BEFORE ``h``: ``x = h(pre_scale x' + pre_shift) scale + shift``.
+        ``src`` (``(D, 2)`` ints): the flow feature(s) output slot ``d`` reads (default ``d``); the
+        pair kinds of ``Angle`` read two (7 angle, 8 angle mod 2 pi, 9 radius, 10 auxiliary radius
+        with its chi(2) prior)."""
         D = self.D
+        src = np.stack([np.arange(D)] * 2, axis=1) if src is None else np.asarray(src).reshape(-1, 2)
         pre_scale = np.ones(D) if pre_scale is None else pre_scale
         pre_shift = np.zeros(D) if pre_shift is None else pre_shift
         if getattr(self, "_identity", None) is None:
@@ -868,11 +872,15 @@ class GeneralPopulateEngine(PopulateEngine):
             raise ValueError("kind / scale / shift / lo / hi / pre_scale / pre_shift: one entry per parameter")
         if np.any((new[0] < 0) | (new[0] >= self.N_KINDS)):
             raise ValueError("unknown per-parameter map kind")
+        new.append(np.ascontiguousarray(src, dtype=np.int32))
+        if new[-1].shape != (D, 2) or np.any((new[-1] < 0) | (new[-1] >= D)):
+            raise ValueError("src must hold two flow-feature indices per parameter")
         old = getattr(self, "_tail_host", None)
         if old is None or not all(np.array_equal(a, b) for a, b in zip(new, old)):
             self.t_kind = torch.from_numpy(new[0]).to(self.device)
-            dev = torch.from_numpy(np.stack(new[1:])).to(self.device)
+            dev = torch.from_numpy(np.stack(new[1:7])).to(self.device)
             self.t_scale, self.t_shift, self.t_lo, self.t_hi, self.t_pre_scale, self.t_pre_shift = dev.unbind(0)
+            self.t_src = torch.from_numpy(new[7].reshape(-1)).to(self.device)
             self._tail_host = new
 
     def _after_draw(self, n_local: int):
@@ -882,7 +890,8 @@ class GeneralPopulateEngine(PopulateEngine):
             self.d_stats.copy_(self._stats_init, non_blocking=True)  # the draw kernel's were pre-tail
             lpc = float("nan") if self.log_prior_const is None else float(self.log_prior_const)
             self._call(_lib.load().nb200_reparam_tail, [
-                n_local, self.D, self.d_xp.data_ptr(), self.t_kind.data_ptr(), self.t_pre_scale.data_ptr(),
+                n_local, self.D, self.d_xp.data_ptr(), self.t_kind.data_ptr(), self.t_src.data_ptr(),
+                self.t_pre_scale.data_ptr(),
                 self.t_pre_shift.data_ptr(), self.t_scale.data_ptr(), self.t_shift.data_ptr(),
                 self.t_lo.data_ptr(), self.t_hi.data_ptr(), lpc, self._tail_min_log_q,
                 self.d_logq.data_ptr(), self.d_logw.data_ptr(), self.d_x64.data_ptr(), self.d_stats.data_ptr(),

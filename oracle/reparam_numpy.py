@@ -15,6 +15,10 @@ function, as ``x = h(a x' + b) * scale + shift`` per parameter:
   function / the normal CDF (utils/rescaling.py:369-407);
 * the same functions as ``pre_rescaling`` ("z-score-logit", "log-z-score",
   "z-score-inv-gaussian-cdf"): ``x = P^-1(scale * x' + shift)``, i.e. ``a = scale``, ``b = shift``;
+* ``Angle`` (reparameterisations/angle.py:17-186): the flow sees the Cartesian pair
+  ``(r cos(scale * angle), r sin(scale * angle))``; inverse ``r = sqrt(x'^2 + y'^2)``,
+  ``angle = atan2(y', x') [% 2 pi] / scale``, ``log|J| -= log r``; ``r`` is either a model parameter or
+  an auxiliary one with a ``chi(2)`` prior;
 * ``h = identity``: the diagonal affine of ``oracle/populate_numpy.py``;
 
 followed by ``log_q -= log|J|`` (flowproposal.py:378-383), the prior-bounds check
@@ -29,11 +33,19 @@ from __future__ import annotations
 import numpy as np
 
 IDENTITY, SIGMOID, ABS, EXP, LOG, NORMAL_CDF, NORMAL_QUANTILE = range(7)
+# pair kinds: functions of two flow features, reparameterisations/angle.py:149-181
+ANGLE, ANGLE_MOD, RADIUS, RADIUS_CHI = 7, 8, 9, 10
 
 
-def inverse_maps(xp, kind, scale, shift, pre_scale=None, pre_shift=None):
+def inverse_maps(xp, kind, scale, shift, pre_scale=None, pre_shift=None, src=None, return_log_prior=False):
     """``x' (n, D) -> (x (n, D), log|J| (n,))`` for ``x = h(a x' + b) * scale + shift`` with the
-    per-parameter ``kind`` of ``h``, ``a = pre_scale`` (default 1) and ``b = pre_shift`` (0)."""
+    per-parameter ``kind`` of ``h``, ``a = pre_scale`` (default 1) and ``b = pre_shift`` (0).
+    ``src`` (``(D, 2)`` ints, default ``[d, d]``): the flow feature(s) output slot ``d`` reads; the
+    pair kinds read two -- ``ANGLE``: ``atan2(u1, u0) * scale + shift`` (``ANGLE_MOD``: modulo
+    ``2 pi`` first), no log-Jacobian for the constant factor (angle.py:120-128,157-170);
+    ``RADIUS``: ``sqrt(u0^2 + u1^2)``, ``log|J| -= log r`` (angle.py:172); ``RADIUS_CHI``: the same for
+    an auxiliary radius, whose ``chi(2)`` prior ``log r - r^2 / 2`` (angle.py:183-185) is returned
+    as a third array with ``return_log_prior``."""
     from scipy.special import erfc, erfcinv
 
     xp = np.asarray(xp, dtype=np.float64)
@@ -41,11 +53,30 @@ def inverse_maps(xp, kind, scale, shift, pre_scale=None, pre_shift=None):
     D = xp.shape[1]
     a = np.ones(D) if pre_scale is None else np.asarray(pre_scale, dtype=np.float64)
     b = np.zeros(D) if pre_shift is None else np.asarray(pre_shift, dtype=np.float64)
+    src = np.stack([np.arange(D)] * 2, axis=1) if src is None else np.asarray(src).reshape(D, 2)
     x = np.empty_like(xp)
-    log_j = np.full(xp.shape[0], float(np.sum(np.log(np.abs(scale))) + np.sum(np.log(np.abs(a)))))
+    single = kind < ANGLE
+    log_j = np.full(xp.shape[0], float(np.sum(np.log(np.abs(np.asarray(scale)[single])))
+                                       + np.sum(np.log(np.abs(a[single])))))
+    log_p = np.zeros(xp.shape[0])
     with np.errstate(all="ignore"):
         for d in range(D):
-            u = a[d] * xp[:, d] + b[d]
+            if kind[d] >= ANGLE:
+                u0, u1 = xp[:, src[d, 0]], xp[:, src[d, 1]]
+                if kind[d] in (ANGLE, ANGLE_MOD):
+                    h = np.arctan2(u1, u0)
+                    if kind[d] == ANGLE_MOD:
+                        h = h % (2.0 * np.pi)
+                elif kind[d] in (RADIUS, RADIUS_CHI):
+                    h = np.sqrt(u0**2 + u1**2)
+                    log_j = log_j - np.log(h)
+                    if kind[d] == RADIUS_CHI:
+                        log_p = log_p + np.log(h) - 0.5 * h**2
+                else:
+                    raise ValueError(f"unknown kind {kind[d]}")
+                x[:, d] = h * scale[d] + shift[d]
+                continue
+            u = a[d] * xp[:, src[d, 0]] + b[d]
             if kind[d] == SIGMOID:  # utils/rescaling.py:310-330
                 h = 1.0 / (1.0 + np.exp(-u))
                 log_j = log_j + np.log(h) + np.log1p(-h)
@@ -68,18 +99,20 @@ def inverse_maps(xp, kind, scale, shift, pre_scale=None, pre_shift=None):
             else:
                 raise ValueError(f"unknown kind {kind[d]}")
             x[:, d] = h * scale[d] + shift[d]
+    if return_log_prior:
+        return x, log_j, log_p
     return x, log_j
 
 
 def tail_rows(xp, logq_flow, *, kind, scale, shift, lo, hi, log_prior_const, min_log_q=None, pre_scale=None,
-              pre_shift=None):
+              pre_shift=None, src=None):
     """The tail of one turn: ``(x, log_q, log_w, valid)``; ``logq_flow`` is the flow's own
     ``log q`` (NaN where the row was dropped before: radius truncation, non-finite)."""
-    x, log_j = inverse_maps(xp, kind, scale, shift, pre_scale, pre_shift)
+    x, log_j, log_p = inverse_maps(xp, kind, scale, shift, pre_scale, pre_shift, src, return_log_prior=True)
     with np.errstate(all="ignore"):
         log_q = np.asarray(logq_flow, dtype=np.float64) - log_j
-        valid = np.isfinite(log_q) & ~np.any((x < lo) | (x > hi), axis=1)
+        log_w = log_prior_const + log_p - log_q
+        valid = np.isfinite(log_q) & np.isfinite(log_w) & ~np.any((x < lo) | (x > hi), axis=1)
         if min_log_q is not None:
             valid &= log_q > min_log_q
-    log_w = np.where(valid, log_prior_const - log_q, np.nan)
-    return x, np.where(valid, log_q, np.nan), log_w, valid
+    return x, np.where(valid, log_q, np.nan), np.where(valid, log_w, np.nan), valid

@@ -23,15 +23,14 @@ extern "C" double nb200_host_erfcinv(double y) {
 }
 
 extern "C" void tail_rows_host(int64_t n, int D, const float* xp, const int32_t* kind,
-                               const double* pre_a, const double* pre_b,
+                               const int32_t* src, const double* pre_a, const double* pre_b,
                                const double* scale, const double* shift, const double* lo,
                                const double* hi, double log_prior_const, double min_log_q,
                                double* logq, double* logw, double* x64, double* stats) {
-  double lss = 0.0;
-  for (int d = 0; d < D; ++d) lss += log(fabs(scale[d])) + (pre_a ? log(fabs(pre_a[d])) : 0.0);
+  const double lss = nb200::tail_log_affine_sum(D, kind, pre_a, scale);
   for (int64_t row = 0; row < n; ++row) {
     double lq, lw;
-    const bool ok = nb200::tail_row(D, xp + row * D, kind, pre_a, pre_b, scale, shift, lo, hi, lss,
+    const bool ok = nb200::tail_row(D, xp + row * D, kind, src, pre_a, pre_b, scale, shift, lo, hi, lss,
                                     log_prior_const, min_log_q, logq[row], x64 + row * D, lq, lw);
     logq[row] = lq;
     logw[row] = lw;

@@ -82,8 +82,8 @@ class SimLib:
             st[1] += float(t["valid"].sum())
         return 0
 
-    def nb200_reparam_tail(self, n, D, xp, kind, pa, pb, sc, sh, lo, hi, lpc, min_log_q, logq, logw, x64, stats,
-                           stream):
+    def nb200_reparam_tail(self, n, D, xp, kind, src, pa, pb, sc, sh, lo, hi, lpc, min_log_q, logq, logw, x64,
+                           stats, stream):
         self.calls.append(("tail", int(n)))
         if n <= 0:
             return 0
@@ -92,7 +92,8 @@ class SimLib:
         x, q, w, valid = tail_rows(_view(xp, n * D, "f4").reshape(n, D), lq.copy(), kind=_view(kind, D, "i4"),
                                    scale=_view(sc, D, "f8"), shift=_view(sh, D, "f8"), lo=_view(lo, D, "f8"),
                                    hi=_view(hi, D, "f8"), log_prior_const=0.0 if np.isnan(lpc) else float(lpc),
-                                   min_log_q=mlq, pre_scale=_view(pa, D, "f8"), pre_shift=_view(pb, D, "f8"))
+                                   min_log_q=mlq, pre_scale=_view(pa, D, "f8"), pre_shift=_view(pb, D, "f8"),
+                                   src=_view(src, 2 * D, "i4"))
         _view(x64, n * D, "f8")[:] = x.ravel()
         lq[:] = q
         _view(logw, n, "f8")[:] = w

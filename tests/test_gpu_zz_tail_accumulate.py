@@ -31,9 +31,11 @@ def _stream():
 @pytest.mark.parametrize("n,min_log_q,pre", [(5000, None, True), (100_003, -14.0, True), (5000, None, False),
                                              (1, None, True)])
 def test_reparam_tail_kernel_matches_oracle(n, min_log_q, pre):
-    """Every kind of h (identity, sigmoid, abs, exp, log, normal CDF, normal quantile), with and
-    without the pre-affine map, saturated / overflowing / out-of-domain arguments and rows already
-    dropped: the inputs of the host-compiled check (tests/test_reparam_oracle.py), on the GPU."""
+    """Every kind of h (identity, sigmoid, abs, exp, log, normal CDF, normal quantile) and the pair
+    kinds of Angle (angle, angle mod 2 pi, radius, auxiliary radius with its chi prior), with and
+    without the pre-affine map and the source permutation, saturated / overflowing / out-of-domain
+    arguments and rows already dropped: the inputs of the host-compiled check
+    (tests/test_reparam_oracle.py), on the GPU."""
     from test_reparam_oracle import TAIL_CASE, tail_case_inputs
 
     from nessai_b200 import _lib
@@ -42,13 +44,13 @@ def test_reparam_tail_kernel_matches_oracle(n, min_log_q, pre):
     lib = _lib.load()
     c = {k: v.copy() for k, v in TAIL_CASE.items()}
     if not pre:
-        c["pre_scale"], c["pre_shift"] = None, None
+        c["pre_scale"], c["pre_shift"], c["src"] = None, None, None
         c["kind"][[7, 9]] = 0
     d = len(c["kind"])
     xp, logq_flow = tail_case_inputs(n)
     x_ref, lq_ref, lw_ref, valid = tail_rows(xp, logq_flow, log_prior_const=-2.5, min_log_q=min_log_q, **c)
     d_xp, d_kind = _dev(xp), _dev(c["kind"])
-    d_pre = [_dev(c[k]) if pre else None for k in ("pre_scale", "pre_shift")]
+    d_pre = [_dev(c[k]) if pre else None for k in ("src", "pre_scale", "pre_shift")]
     d_c = [_dev(c[k]) for k in ("scale", "shift", "lo", "hi")]
     d_logq, d_logw = _dev(logq_flow.copy()), torch.empty(n, dtype=torch.float64, device="cuda")
     d_x64 = torch.empty((n, d), dtype=torch.float64, device="cuda")
@@ -361,11 +363,12 @@ def test_accumulate_through_the_standalone_proposal(tmp_path):
 
 
 @pytest.mark.reference
-@pytest.mark.parametrize("variant", ["logit_and_default", "accumulate"])
+@pytest.mark.parametrize("variant", ["logit_and_default", "accumulate", "periodic_angle"])
 def test_flowsampler_variants_run_on_the_device_loop(tmp_path, variant):
     """The reference's FlowSampler, unmodified, with a logit + rescale-to-bounds
-    reparameterisation (GeneralPopulateEngine) and with accumulate_weights=True
-    (run_accumulate): the device loop is the one that runs."""
+    reparameterisation (GeneralPopulateEngine), with accumulate_weights=True (run_accumulate)
+    and with an Angle reparameterisation (Cartesian pair + auxiliary radius with its chi prior,
+    GeneralPopulateEngine over three flow features): the device loop is the one that runs."""
     reference_or_skip()
     from nessai.flowsampler import FlowSampler
     from test_gpu_nessai_plugin import make_model
@@ -373,8 +376,9 @@ def test_flowsampler_variants_run_on_the_device_loop(tmp_path, variant):
     from nessai_b200.nessai_plugin import B200NessaiFlowProposal
     from nessai_b200.proposal import GeneralPopulateEngine, PopulateEngine
 
-    kw = (dict(reparameterisations={"x": "logit", "y": "default"}) if variant == "logit_and_default"
-          else dict(accumulate_weights=True))
+    kw = dict(logit_and_default=dict(reparameterisations={"x": "logit", "y": "default"}),
+              accumulate=dict(accumulate_weights=True),
+              periodic_angle=dict(reparameterisations={"x": "periodic", "y": "default"}))[variant]
     fs = FlowSampler(
         make_model(), output=str(tmp_path), resume=False, seed=1234, nlive=200, plot=False,
         flow_proposal_class=B200NessaiFlowProposal, flow_config=dict(n_blocks=2),
@@ -386,6 +390,10 @@ def test_flowsampler_variants_run_on_the_device_loop(tmp_path, variant):
     assert prop.training_count >= 1 and prop.populated_count >= 1
     if variant == "logit_and_default":
         assert type(prop._engine) is GeneralPopulateEngine
+    elif variant == "periodic_angle":
+        assert type(prop._engine) is GeneralPopulateEngine and prop._engine.names == ["x", "y", "x_radial"]
+        assert prop.flow.model.spec.D == 3 and prop.samples.dtype.names[:2] == ("x", "y")
+        assert "x_radial" in prop.x.dtype.names and "x_radial" not in prop.samples.dtype.names
     else:
         assert type(prop._engine) is PopulateEngine and getattr(prop._engine, "last_accumulate", None)
     # truncated at max_iteration (the reference's own CPU proposal gives -7.3 here; analytic -5.99)

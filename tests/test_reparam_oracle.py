@@ -96,8 +96,9 @@ def test_parameter_maps_and_oracle_match_reference_inverse_rescale(tmp_path, cas
             r._edges[p] = e  # every branch of rescale.py:570-590, whatever the data suggested
     maps = parameter_maps(prop._reparameterisation, prop.prime_parameters, model.names)
     assert maps is not None
-    kind, scale, shift, pre_scale, pre_shift = maps
+    kind, scale, shift, pre_scale, pre_shift = maps[:5]
     assert set(kind.tolist()) == kinds and maps.has_pre_affine == (case in BOX)
+    assert maps.names == list(model.names) and np.array_equal(maps.src, np.stack([np.arange(D)] * 2, axis=1))
     assert diagonal_rescaling(prop._reparameterisation, prop.prime_parameters, model.names) is None
     rng = np.random.default_rng(0)
     n = 200
@@ -153,7 +154,7 @@ def host_tail(tmp_path_factory):
     subprocess.run([gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(out), src], check=True)
     lib = C.CDLL(str(out))
     lib.tail_rows_host.restype = None
-    lib.tail_rows_host.argtypes = [C.c_int64, C.c_int] + [C.c_void_p] * 8 + [C.c_double, C.c_double] + [C.c_void_p] * 4
+    lib.tail_rows_host.argtypes = [C.c_int64, C.c_int] + [C.c_void_p] * 9 + [C.c_double, C.c_double] + [C.c_void_p] * 4
     lib.nb200_host_erfcinv.restype = C.c_double
     lib.nb200_host_erfcinv.argtypes = [C.c_double]
     return lib
@@ -171,13 +172,18 @@ def test_host_erfcinv_helper(host_tail):
 
 
 TAIL_CASE = dict(
-    kind=np.array([0, 1, 2, 3, 1, 2, 0, 4, 5, 6, 1, 3], dtype=np.int32),
-    scale=np.array([1.5, 8.0, -3.0, 2.0, 0.5, 4.0, -0.7, 1.2, 6.0, 0.9, 1.0, 1.0]),
-    shift=np.array([0.2, -4.0, 5.0, -1.0, 0.0, -2.0, 0.3, 0.1, -3.0, 0.4, 0.0, 0.0]),
-    lo=np.array([-3.0, -4.0, 2.0, -1.0, 0.0, -2.0, -2.0, -3.0, -3.0, -2.0, 0.0, 0.0]),
-    hi=np.array([3.0, 4.0, 5.0, 9.0, 0.5, 1.5, 2.0, 2.0, 3.0, 2.5, 1.0, 9.0]),
-    pre_scale=np.array([1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.3, 1.0, 0.2, 1.7, 0.6]),
-    pre_shift=np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.5, 0.0, 0.5, -0.3, 0.2]),
+    #              0  1  2  3  4  5  6  7  8  9 10 11 | angle, aux radius, radius, angle mod 2 pi
+    kind=np.array([0, 1, 2, 3, 1, 2, 0, 4, 5, 6, 1, 3, 7, 10, 9, 8], dtype=np.int32),
+    scale=np.array([1.5, 8.0, -3.0, 2.0, 0.5, 4.0, -0.7, 1.2, 6.0, 0.9, 1.0, 1.0, 0.5, 1.0, 1.0, 1.0]),
+    shift=np.array([0.2, -4.0, 5.0, -1.0, 0.0, -2.0, 0.3, 0.1, -3.0, 0.4, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]),
+    lo=np.array([-3.0, -4.0, 2.0, -1.0, 0.0, -2.0, -2.0, -3.0, -3.0, -2.0, 0.0, 0.0, -1.5, -np.inf, 0.0, 0.0]),
+    hi=np.array([3.0, 4.0, 5.0, 9.0, 0.5, 1.5, 2.0, 2.0, 3.0, 2.5, 1.0, 9.0, 1.5, np.inf, 3.5, 2 * np.pi]),
+    pre_scale=np.array([1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.3, 1.0, 0.2, 1.7, 0.6, 1.0, 1.0, 1.0, 1.0]),
+    pre_shift=np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.5, 0.0, 0.5, -0.3, 0.2, 0.0, 0.0, 0.0, 0.0]),
+    # slots 12 / 13 read the flow features (13, 12) as (x', y'), slots 14 / 15 the features (14, 15);
+    # slots 2 and 5 are swapped to exercise the permutation of single-feature kinds
+    src=np.array([[0, 0], [1, 1], [5, 5], [3, 3], [4, 4], [2, 2], [6, 6], [7, 7], [8, 8], [9, 9], [10, 10], [11, 11],
+                  [13, 12], [13, 12], [14, 15], [14, 15]], dtype=np.int32),
 )
 
 
@@ -204,8 +210,8 @@ def test_kernel_row_function_matches_oracle(host_tail, min_log_q, pre):
 
     n = 5000
     c = {k: v.copy() for k, v in TAIL_CASE.items()}
-    if not pre:
-        c["pre_scale"], c["pre_shift"] = None, None
+    if not pre:  # ... and without the optional arrays: slot d reads feature d
+        c["pre_scale"], c["pre_shift"], c["src"] = None, None, None
         c["kind"][[7, 9]] = 0  # their arguments rely on the pre-affine map to be in the domain
     d = len(c["kind"])
     xp, logq_flow = tail_case_inputs(n)
@@ -214,7 +220,8 @@ def test_kernel_row_function_matches_oracle(host_tail, min_log_q, pre):
     x64 = np.empty((n, d))
     stats = np.array([-np.inf, 0.0])
     ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
-    host_tail.tail_rows_host(n, d, xp.ctypes.data, c["kind"].ctypes.data, ptr(c["pre_scale"]), ptr(c["pre_shift"]),
+    host_tail.tail_rows_host(n, d, xp.ctypes.data, c["kind"].ctypes.data, ptr(c["src"]), ptr(c["pre_scale"]),
+                             ptr(c["pre_shift"]),
                              c["scale"].ctypes.data, c["shift"].ctypes.data, c["lo"].ctypes.data, c["hi"].ctypes.data,
                              -2.5, -np.inf if min_log_q is None else min_log_q,
                              logq.ctypes.data, logw.ctypes.data, x64.ctypes.data, stats.ctypes.data)
@@ -226,3 +233,108 @@ def test_kernel_row_function_matches_oracle(host_tail, min_log_q, pre):
     np.testing.assert_allclose(logq[valid], lq_ref[valid], rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(logw[valid], lw_ref[valid], rtol=1e-12, atol=1e-12)
     assert stats[1] == valid.sum() and stats[0] == logw[valid].max()
+
+
+# ------------------------------------------------------------------ Angle (pair maps)
+ANGLE_CASES = {
+    # name: (model bounds of the angle, reparameterisations, expected kinds in x-space order)
+    "angle_aux_radius": ((-np.pi, np.pi), {"a": "angle", "x": "default"}, [7, 0, 10]),
+    "angle_zero_bound": ((0.0, 2 * np.pi), {"a": "angle", "x": "z-score"}, [8, 0, 10]),
+    "angle_pi": ((0.0, np.pi), {"x": "logit", "a": "angle-pi"}, [8, 1, 10]),
+    "periodic": ((0.0, 3.0), {"a": "periodic", "x": "default"}, [8, 0, 10]),  # scale = 2 pi / 3
+    "angle_with_radial_parameter": ((0.0, 2 * np.pi), {"angle": {"parameters": ["a", "x"]}}, [8, 9]),
+}
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("case", list(ANGLE_CASES))
+def test_angle_maps_and_oracle_match_reference(tmp_path, case):
+    """``Angle`` (reparameterisations/angle.py:17-186): the prime space holds Cartesian pairs; the
+    x-space gains an auxiliary radius with a chi(2) prior unless the model has a radial parameter.
+    ``parameter_maps`` + the oracle against the reference's ``inverse_rescale`` and the
+    reparameterisation's own ``log_prior``."""
+    reference_or_skip()
+    from nessai.livepoint import empty_structured_array, numpy_array_to_live_points
+    from nessai.model import Model
+    from nessai.proposal import FlowProposal
+
+    from nessai_b200.nessai_plugin import diagonal_rescaling, parameter_maps
+    from oracle.reparam_numpy import inverse_maps
+
+    bounds, reparams, kinds = ANGLE_CASES[case]
+
+    class M(Model):
+        def __init__(self):
+            self.names = ["a", "x"]
+            self.bounds = {"a": list(bounds), "x": [0.5, 4.0]}
+
+        def log_prior(self, x):
+            return np.log(self.in_bounds(x), dtype="float")
+
+        def log_likelihood(self, x):
+            return np.zeros(x.size)
+
+    model = M()
+    rng = np.random.default_rng(4)
+    model.set_rng(rng)
+    prop = FlowProposal(model, rng=rng, flow_config=dict(n_blocks=2, n_neurons=8), output=str(tmp_path), poolsize=100,
+                        plot=False, reparameterisations=reparams)
+    prop.initialise()
+    live = numpy_array_to_live_points(np.stack([rng.uniform(*bounds, 300), rng.uniform(0.6, 3.9, 300)], axis=1),
+                                      model.names)
+    prop.check_state(live)
+    maps = parameter_maps(prop._reparameterisation, prop.prime_parameters, model.names, prop.parameters)
+    assert maps is not None and maps.names == list(prop.parameters) and not maps.affine
+    assert maps.kind.tolist() == kinds
+    assert diagonal_rescaling(prop._reparameterisation, prop.prime_parameters, model.names) is None
+    n, Dp = 400, len(prop.prime_parameters)
+    assert Dp == len(prop.parameters)
+    a = rng.normal(0.0, 1.0, size=(n, Dp))
+    xp = empty_structured_array(n, names=prop.prime_parameters)
+    for i, p in enumerate(prop.prime_parameters):
+        xp[p] = a[:, i]
+    x_ref, log_j_ref = prop.inverse_rescale(xp.copy())
+    x, log_j, log_p = inverse_maps(a, maps.kind, maps.scale, maps.shift, maps.pre_scale, maps.pre_shift, maps.src,
+                                   return_log_prior=True)
+    ref = np.stack([x_ref[nm] for nm in prop.parameters], axis=-1)
+    np.testing.assert_allclose(x, ref, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(log_j, log_j_ref, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(log_p, prop._reparameterisation.log_prior(x_ref), rtol=1e-12, atol=1e-12)
+    # forward (training data) then inverse gives the angle back
+    x_prime, _ = prop.rescale(live.copy())
+    back = inverse_maps(np.stack([x_prime[p] for p in prop.prime_parameters], axis=-1), maps.kind, maps.scale,
+                        maps.shift, maps.pre_scale, maps.pre_shift, maps.src)[0]
+    np.testing.assert_allclose(back[:, 0], live["a"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(back[:, 1], live["x"], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.reference
+def test_other_angle_classes_are_refused(tmp_path):
+    reference_or_skip()
+    from nessai.livepoint import numpy_array_to_live_points
+    from nessai.model import Model
+    from nessai.proposal import FlowProposal
+
+    from nessai_b200.nessai_plugin import parameter_maps
+
+    class M(Model):
+        def __init__(self):
+            self.names = ["a", "b"]
+            self.bounds = {"a": [0.0, 2 * np.pi], "b": [-np.pi / 2, np.pi / 2]}
+
+        def log_prior(self, x):
+            return np.log(self.in_bounds(x), dtype="float")
+
+        def log_likelihood(self, x):
+            return np.zeros(x.size)
+
+    for reparams in ({"a": "to-cartesian", "b": "default"}, {"angle-pair": {"parameters": ["a", "b"]}}):
+        model = M()
+        rng = np.random.default_rng(4)
+        model.set_rng(rng)
+        prop = FlowProposal(model, rng=rng, flow_config=dict(n_blocks=2, n_neurons=8), output=str(tmp_path),
+                            poolsize=100, plot=False, reparameterisations=reparams)
+        prop.initialise()
+        live = numpy_array_to_live_points(np.stack([rng.uniform(0, 6, 50), rng.uniform(-1, 1, 50)], axis=1), model.names)
+        prop.check_state(live)
+        assert parameter_maps(prop._reparameterisation, prop.prime_parameters, model.names, prop.parameters) is None
