@@ -109,6 +109,66 @@ def main():
     rows, p, a = gen.run(50_000, n, max_samples=50 * n)
     out["general_populate"] = {"rows": int(len(rows)), "n_proposed": int(p), "n_accepted": int(a)}
 
+    # (2b) every kind once, against the same maps written with torch float64 ops on the device
+    # (an independent evaluation: torch.sigmoid / atan2 / hypot / special.ndtr / ndtri ...)
+    kind = np.array([0, 1, 2, 3, 4, 5, 6, 7, 10, 9, 8, 0, 1, 2, 3, 0][:D], dtype=np.int32)
+    sc = np.array([1.5, 20.0, -4.0, 2.0, 1.2, 20.0, 0.9, 0.5, 1.0, 1.0, 1.0, 1.0, 20.0, 3.0, 1.0, 1.0][:D])
+    sh = np.array([0.2, -10.0, 9.0, -1.0, 0.1, -10.0, 0.4, 0.0, 0.0, 0.0, 0.0, 0.0, -10.0, -9.0, 0.0, 0.0][:D])
+    pa = np.array([1.0, 1.0, 1.0, 1.0, 0.3, 1.0, 0.2, 1.0, 1.0, 1.0, 1.0, 1.0, 1.7, 1.0, 0.6, 1.0][:D])
+    pb = np.array([0.0, 0.0, 0.0, 0.0, 1.5, 0.0, 0.5, 0.0, 0.0, 0.0, 0.0, 0.0, -0.3, 0.0, 0.2, 0.0][:D])
+    src = np.stack([np.arange(D)] * 2, axis=1).astype(np.int32)
+    if D >= 11:
+        src[7] = src[8] = (8, 7)
+        src[9] = src[10] = (9, 10)
+        gen.configure(kind, sc, sh, np.full(D, -np.inf), np.full(D, np.inf), lpc, radius, pre_scale=pa, pre_shift=pb,
+                      src=src)
+        gen.draw_turn(n)
+        xp = gen.d_xp[:n].to(torch.float64)
+        t = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float64)).cuda()  # noqa: E731
+        u = xp[:, torch.from_numpy(src[:, 0].astype(np.int64)).cuda()] * t(pa) + t(pb)
+        u1 = xp[:, torch.from_numpy(src[:, 1].astype(np.int64)).cuda()]
+        cols, logj = [], torch.zeros(n, dtype=torch.float64, device="cuda")
+        for d in range(D):
+            k, v = int(kind[d]), u[:, d]
+            if k == 1:
+                h = torch.sigmoid(v)
+                logj += torch.log(h) + torch.log1p(-h)
+            elif k == 2:
+                h = v.abs()
+            elif k == 3:
+                h, logj = torch.exp(v), logj + v
+            elif k == 4:
+                h = torch.log(v)
+                logj -= h
+            elif k == 5:
+                h, logj = torch.special.ndtr(v), logj - 0.9189385332046727 - 0.5 * v * v
+            elif k == 6:
+                h = torch.special.ndtri(v)
+                logj += 0.9189385332046727 + 0.5 * h * h
+            elif k in (7, 8):
+                h = torch.atan2(u1[:, d], xp[:, int(src[d, 0])])
+                h = torch.where((h < 0) & (k == 8), h + 2 * np.pi, h)
+            elif k in (9, 10):
+                h = torch.hypot(xp[:, int(src[d, 0])], u1[:, d])
+                logj -= torch.log(h)
+            else:
+                h = v
+            if k < 7:
+                logj += float(np.log(abs(sc[d])) + np.log(abs(pa[d])))
+            cols.append(h * sc[d] + sh[d])
+        x_t = torch.stack(cols, dim=1)
+        x_k = gen.physical_x(n)
+        fin = torch.isfinite(x_t) & torch.isfinite(x_k)
+        rel = ((x_k - x_t).abs() / (1.0 + x_t.abs()))[fin]
+        okk = ~torch.isnan(gen.d_logw[:n])
+        # log q of the flow alone is not kept after the tail: compare the weights' dependence on
+        # log|J| through differences between the kernel's log w and lpc + chi prior - (flow log q - logj)
+        out["tail_vs_torch_float64"] = {
+            "kinds": kind.tolist(), "max_rel_dx": float(rel.max()), "finite_fraction": float(fin.float().mean()),
+            "same_nonfinite_pattern": bool(torch.equal(torch.isfinite(x_t), torch.isfinite(x_k))),
+            "valid_fraction": float(okk.float().mean()),
+        }
+
     # (3) accumulate_weights
     import time
 
