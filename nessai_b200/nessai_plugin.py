@@ -257,10 +257,8 @@ class B200NessaiFlowProposal(FlowProposal):
                     if self.device_prior in ("auto", True, "uniform")
                     else None
                 )
-            if self.accumulate_weights and (
-                not affine or "likelihood_threshold" in rules or self._log_prior_const is None
-            ):
-                eligible = False  # the accumulating device loop: affine maps, device prior
+            if self.accumulate_weights and ("likelihood_threshold" in rules or self._log_prior_const is None):
+                eligible = False  # the accumulating device loop needs the prior on the device
             if aux and ("likelihood_threshold" in rules or self._log_prior_const is None):
                 eligible = False  # their prior is added by the tail kernel; the hooks see model parameters only
         if not eligible:

@@ -656,8 +656,9 @@ class PopulateEngine:
                 self.model._handle, n_local, self._seed(), self._turn_rows + start, self.r_max, self.sqrt_t,
                 self.d_scale.data_ptr(), self.d_shift.data_ptr(), self.d_lo.data_ptr(), self.d_hi.data_ptr(),
                 lpc, self.min_log_q, self.d_xp.data_ptr() + off * self.D * 4, self.d_logq.data_ptr() + off * 8,
-                self.d_logw.data_ptr() + off * 8, None, self.d_stats.data_ptr(), st,
+                self.d_logw.data_ptr() + off * 8, None, self._accumulate_draw_stats().data_ptr(), st,
             ], "nb200_populate_draw")
+            self._accumulate_after_draw(off, n_local, st)
             self._turn_rows += drawsize
             turn += 1
             rows = turn * stride
@@ -689,6 +690,13 @@ class PopulateEngine:
 
     _N_PARTIALS = 296  # blocks of the sum-exp reduction: two per SM
 
+    def _accumulate_draw_stats(self) -> torch.Tensor:
+        """Where the draw kernel accumulates {max log_w, n_valid} in the accumulating loop."""
+        return self.d_stats
+
+    def _accumulate_after_draw(self, off: int, n_local: int, stream) -> None:
+        """Hook after the draw of a turn into slot offset ``off`` (GeneralPopulateEngine: the tail)."""
+
     def _accumulate_reject(self, rows: int, n_samples: int, info: dict) -> int:
         """Rejection step over the first ``rows`` slot rows with the running maximum
         (flowproposal.py:483-485,505-508); returns the global number of accepted rows.  Every call
@@ -696,19 +704,22 @@ class PopulateEngine:
         base = self._turn_rows + self.rank * rows
         self._turn_rows += self.world * rows
         info["rejects"].append((base, rows))
-        self._call(_lib.load().nb200_populate_accept, [
-            rows, self.D, self.d_xp.data_ptr(), self.d_scale.data_ptr(), self.d_shift.data_ptr(),
-            self.d_logw.data_ptr(), None, self.d_stats.data_ptr(), self._seed(), base,
-            float(self.log_prior_const), self.d_template.data_ptr(), self.row_bytes,
-            self.field_offsets.ctypes.data, self.logl_offset, self.d_rows.data_ptr(), int(n_samples), 0,
-            self.d_counts.data_ptr(), self.d_scratch.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream,
-        ], "nb200_populate_accept")
+        self._accumulate_accept(rows, base, int(n_samples))
         tot = self.d_counts[0:1].clone()
         if self.world > 1:
             import torch.distributed as dist
 
             dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
         return int(tot.cpu())
+
+    def _accumulate_accept(self, rows: int, base: int, n_samples: int) -> None:
+        self._call(_lib.load().nb200_populate_accept, [
+            rows, self.D, self.d_xp.data_ptr(), self.d_scale.data_ptr(), self.d_shift.data_ptr(),
+            self.d_logw.data_ptr(), None, self.d_stats.data_ptr(), self._seed(), base,
+            float(self.log_prior_const), self.d_template.data_ptr(), self.row_bytes,
+            self.field_offsets.ctypes.data, self.logl_offset, self.d_rows.data_ptr(), n_samples, 0,
+            self.d_counts.data_ptr(), self.d_scratch.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream,
+        ], "nb200_populate_accept")
 
     def _shared_pool(self, nbytes: int):
         """The node-local shared host pool (hostpool.py), created collectively on first use and
@@ -920,8 +931,34 @@ class GeneralPopulateEngine(PopulateEngine):
         ], "nb200_populate_accept_x64")
         return self.d_counts
 
-    def run_accumulate(self, *args, **kwargs):
-        raise NotImplementedError("nessai_b200: accumulate_weights with a non-affine reparameterisation")
+    # accumulate_weights: the base loop with the tail applied to each turn's slot; the draw kernel's
+    # own (pre-tail) statistics go to a scratch pair, the tail's accumulate in d_stats
+    def _accumulate_draw_stats(self) -> torch.Tensor:
+        if getattr(self, "d_stats_scratch", None) is None:
+            self.d_stats_scratch = torch.empty(2, dtype=torch.float64, device=self.device)
+        self.d_stats_scratch.copy_(self._stats_init, non_blocking=True)
+        return self.d_stats_scratch
+
+    def _accumulate_after_draw(self, off: int, n_local: int, stream) -> None:
+        if self.d_x64 is None or self.d_x64.shape[0] < self._cap:
+            self.d_x64 = torch.empty((self._cap, self.D), dtype=torch.float64, device=self.device)
+        if n_local <= 0:
+            return
+        self._call(_lib.load().nb200_reparam_tail, [
+            n_local, self.D, self.d_xp.data_ptr() + off * self.D * 4, self.t_kind.data_ptr(), self.t_src.data_ptr(),
+            self.t_pre_scale.data_ptr(), self.t_pre_shift.data_ptr(), self.t_scale.data_ptr(), self.t_shift.data_ptr(),
+            self.t_lo.data_ptr(), self.t_hi.data_ptr(), float(self.log_prior_const), self._tail_min_log_q,
+            self.d_logq.data_ptr() + off * 8, self.d_logw.data_ptr() + off * 8,
+            self.d_x64.data_ptr() + off * self.D * 8, self.d_stats.data_ptr(), stream,
+        ], "nb200_reparam_tail")
+
+    def _accumulate_accept(self, rows: int, base: int, n_samples: int) -> None:
+        self._call(_lib.load().nb200_populate_accept_x64, [
+            rows, self.D, self.d_x64.data_ptr(), self.d_logw.data_ptr(), None, self.d_stats.data_ptr(), self._seed(),
+            base, float(self.log_prior_const), self.d_template.data_ptr(), self.row_bytes,
+            self.field_offsets.ctypes.data, self.logl_offset, self.d_rows.data_ptr(), n_samples, 0,
+            self.d_counts.data_ptr(), self.d_scratch.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream,
+        ], "nb200_populate_accept_x64")
 
 
 class B200FlowProposal:

@@ -123,14 +123,61 @@ def test_general_engine_loop_matches_oracle(monkeypatch):
     got = np.stack([rows[nm] for nm in names], axis=-1)
     np.testing.assert_allclose(got, np.concatenate(kept), rtol=1e-12, atol=1e-12)
     assert np.all((got >= lo) & (got <= hi)) and np.all(rows["logP"] == lpc)
-    with pytest.raises(NotImplementedError):
-        eng.run_accumulate(10, n)
+
+
+def test_general_engine_accumulate(monkeypatch):
+    """accumulate_weights over the non-affine tail: with identity maps it is the affine engine's
+    accumulating loop row for row; with real maps the pool follows the accumulated weights."""
+    from nessai_b200.livepoint import get_dtype
+    from nessai_b200.proposal import GeneralPopulateEngine, PopulateEngine
+    from oracle.philox_numpy import accept_uniform
+
+    sim = _simdevice.install(monkeypatch)
+    nf, D = _flow()
+    names = [f"x{i}" for i in range(D)]
+    scale, shift = _zscore(D)
+    lo, hi, lpc, radius, drawsize = np.full(D, -4.0), np.full(D, 4.0), -D * np.log(8.0), 4.9, 1000
+    aff = PopulateEngine(_simdevice.SimFlowModel(nf, D), names, get_dtype(names))
+    aff.configure(scale, shift, lo, hi, lpc, radius, min_log_q=-40.0)
+    gen = GeneralPopulateEngine(_simdevice.SimFlowModel(nf, D), names, get_dtype(names))
+    gen.configure(np.zeros(D, dtype=np.int32), scale, shift, lo, hi, lpc, radius, min_log_q=-40.0)
+    aff.seed = gen.seed = 31
+    ra, pa, aa = aff.run_accumulate(150, drawsize, max_samples=10**6)
+    rg, pg, ag = gen.run_accumulate(150, drawsize, max_samples=10**6)
+    assert (pa, aa) == (pg, ag) and aff._turn_rows == gen._turn_rows
+    assert aff.last_accumulate["rejects"] == gen.last_accumulate["rejects"]
+    np.testing.assert_allclose(aff.last_accumulate["n_expected"], gen.last_accumulate["n_expected"], rtol=1e-12)
+    for nm in names:  # (the affine path forms x from fp32 x' at the rejection step, the tail before it)
+        np.testing.assert_allclose(rg[nm], ra[nm], rtol=1e-12, atol=1e-12)
+    # sigmoid / abs / exp maps: the final rejection step over all slots, replayed from the buffers
+    kind = (np.arange(D) % 4).astype(np.int32)
+    sc = np.where(kind == 1, 8.0, np.where(kind == 3, 0.5, np.where(kind == 2, -2.0, 1.4)))
+    sh = np.where(kind == 1, -4.0, np.where(kind == 2, 3.0, 0.1))
+    lo2 = np.where(kind == 1, -4.0, np.where(kind == 2, -3.0, np.where(kind == 3, 0.0, -5.0)))
+    hi2 = np.where(kind == 1, 4.0, np.where(kind == 2, 3.0, np.where(kind == 3, 6.0, 5.0)))
+    gen.configure(kind, sc, sh, lo2, hi2, -3.0, radius, min_log_q=-27.0)
+    rows, p, a = gen.run_accumulate(200, drawsize, max_samples=10**6)
+    info = gen.last_accumulate
+    turns, stride = len(info["draw_offsets"]), info["stride"]
+    lw = gen.d_logw[: turns * stride].numpy()
+    x64 = gen.d_x64[: turns * stride].numpy()
+    stats = gen.d_stats.numpy()
+    ok = ~np.isnan(lw)
+    assert stats[1] == ok.sum() and stats[0] == lw[ok].max() and len(rows) == 200 and a >= 200
+    base, nrows = info["rejects"][-1]
+    acc = ok & ((lw - stats[0]) > np.log(accept_uniform(gen.seed, base + np.arange(nrows))))
+    assert a == acc.sum()
+    got = np.stack([rows[nm] for nm in names], axis=-1)
+    np.testing.assert_array_equal(got, x64[acc][:200])
+    assert np.all((got >= lo2) & (got <= hi2))
+    assert [c[0] for c in sim.calls if c[0] in ("draw", "tail")][-2 * turns:] == ["draw", "tail"] * turns
 
 
 @pytest.mark.reference
 @pytest.mark.parametrize("variant", ["zscore", "rescaletobounds", "logit_mixed", "inversion_edges", "accumulate",
                                      "accumulate_min_log_q", "likelihood_threshold", "logit_likelihood_threshold",
-                                     "zscore_gaussian_cdf", "angle_aux", "angle_and_radial_parameter"])
+                                     "zscore_gaussian_cdf", "angle_aux", "angle_and_radial_parameter",
+                                     "accumulate_logit"])
 def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     """``B200NessaiFlowProposal.populate`` end to end with the reference's own proposal object
     (reparameterisations, truncation scheme, live-point dtype): engine selection, configuration
@@ -181,6 +228,8 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
         inversion_edges=dict(reparameterisations={"inversion": dict(parameters=names)}),
         accumulate=dict(accumulate_weights=True),
         accumulate_min_log_q=dict(accumulate_weights=True, truncation_methods=["latent_radius", "min_log_q"]),
+        accumulate_logit=dict(accumulate_weights=True,
+                              reparameterisations={"x0": "logit", "x1": "default", "x2": "default", "x3": "logit"}),
         zscore_gaussian_cdf=dict(reparameterisations={"zscore-gaussian-cdf": dict(parameters=names)}),
         angle_aux=dict(reparameterisations={"x0": "angle", "x1": "default", "x2": "z-score", "x3": "logit"}),
         angle_and_radial_parameter=dict(reparameterisations={"angle": {"parameters": ["x0", "x1"]},
@@ -227,7 +276,7 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     prop.populate(worst, n_samples=400, plot=False)
     assert prop._engine is not None and len(sim.calls) > 0  # not the host loop
     general = variant in ("logit_mixed", "inversion_edges", "logit_likelihood_threshold", "zscore_gaussian_cdf",
-                          "angle_aux", "angle_and_radial_parameter")
+                          "angle_aux", "angle_and_radial_parameter", "accumulate_logit")
     if variant == "angle_aux":  # the auxiliary radius never reaches the sampler (flowproposal/base.py:1100-1128)
         assert prop._engine.names == names + ["x0_radial"] and prop.samples.dtype.names[:D] == tuple(names)
         assert "x0_radial" in prop.x.dtype.names and "x0_radial" not in prop.samples.dtype.names
@@ -472,7 +521,7 @@ def test_gpu_test_bodies_pass_on_the_simulated_device():
     res = subprocess.run([sys.executable, os.path.join(REPO, "tests", "tools", "dryrun_gpu_tests_on_sim.py")],
                          capture_output=True, text=True, cwd=REPO, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert json.loads(res.stdout.strip().splitlines()[-1]) == {"dryrun_failed": 0, "of": 7}
+    assert json.loads(res.stdout.strip().splitlines()[-1]) == {"dryrun_failed": 0, "of": 8}
 
 
 def test_pipelined_loop_logic_equals_serial_loop(monkeypatch):

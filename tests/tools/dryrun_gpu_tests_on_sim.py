@@ -88,6 +88,7 @@ def main():
         ("accumulate 1200", lambda: t.test_accumulate_device_loop_matches_oracle(tmp(), 1200, 400)),
         ("accumulate max_samples", lambda: t.test_accumulate_device_loop_matches_oracle(tmp(), 10**6, 2)),
         ("accumulate standalone", lambda: t.test_accumulate_through_the_standalone_proposal(tmp())),
+        ("general accumulate", lambda: t.test_general_accumulate_reproduces_affine_accumulate(tmp())),
     ]
     failed = 0
     for name, fn in runs:
