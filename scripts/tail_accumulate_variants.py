@@ -186,6 +186,20 @@ def main():
         "n_expected_last": info["n_expected"][-1],
         "n_expected_check": float(torch.exp(lw[okw] - lw[okw].max()).sum()),
     }
+    # accumulate over the non-affine tail with identity maps == the affine accumulating loop
+    gen.configure(np.zeros(D, dtype=np.int32), scale, shift, lo, hi, lpc, radius)
+    aff.seed = gen.seed = 777
+    aff._turn_rows = gen._turn_rows = 0
+    ra, pa, aa = aff.run_accumulate(20_000, n, max_samples=4 * n)
+    rg, pg, ag = gen.run_accumulate(20_000, n, max_samples=4 * n)
+    same = len(ra) == len(rg) and aa == ag
+    out["accumulate_identity_tail_vs_affine"] = {
+        "same_turns": pa == pg, "n_accepted": [int(aa), int(ag)],
+        "n_expected_rel_diff": float(abs(aff.last_accumulate["n_expected"][-1] - gen.last_accumulate["n_expected"][-1])
+                                     / aff.last_accumulate["n_expected"][-1]),
+        "records_max_abs_diff": float(max(np.abs(ra[nm] - rg[nm]).max() for nm in names)) if same and len(ra) else None,
+    }
+
     # the sum-exp reduction alone, over 8e6 rows of weights (HBM-bound: 8 B/row)
     m = min(8 * n, aff.d_logw.shape[0])
     lib = _lib.load()
