@@ -257,10 +257,11 @@ class B200NessaiFlowProposal(FlowProposal):
                     if self.device_prior in ("auto", True, "uniform")
                     else None
                 )
-            if self.accumulate_weights and ("likelihood_threshold" in rules or self._log_prior_const is None):
-                eligible = False  # the accumulating device loop needs the prior on the device
-            if aux and ("likelihood_threshold" in rules or self._log_prior_const is None):
-                eligible = False  # their prior is added by the tail kernel; the hooks see model parameters only
+            self._engine.n_model = len(self.model.names)
+            if (self.accumulate_weights or aux) and self._log_prior_const is None:
+                # the accumulating loop keeps everything on the device; the prior of an auxiliary
+                # parameter is added by the tail kernel, a host-side prior would count it twice
+                eligible = False
         if not eligible:
             logger.debug("B200: configuration not eligible for the fused loop; using the host loop")
             return super().populate(worst_point, n_samples=n_samples, plot=plot, r=r, max_samples=max_samples)

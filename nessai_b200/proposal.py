@@ -264,6 +264,9 @@ class PopulateEngine:
         self._rows_cap = 0
         self._gen = 0  # bumped whenever a device buffer is (re)allocated
         self._turn_rows = 0  # global rows drawn so far (Philox counter base)
+        # the first n_model parameters are the model's (what a device likelihood is given); the rest
+        # are auxiliary x-space parameters of the reparameterisation (flowproposal/base.py:539-546)
+        self.n_model = self.D
         self.seed = None
         self.min_log_q, self.likelihood, self.log_l_threshold = -float("inf"), None, -float("inf")
 
@@ -384,8 +387,9 @@ class PopulateEngine:
         float64, gathered from the records' parameter fields)."""
         words = self.row_bytes // 4
         rows32 = self.d_rows[: n_written * self.row_bytes].view(torch.int32).view(n_written, words)
-        if getattr(self, "_param_cols", None) is None:
-            cols = np.stack([self.field_offsets[: self.D] // 4, self.field_offsets[: self.D] // 4 + 1], axis=1)
+        if getattr(self, "_param_cols", None) is None or self._param_cols.numel() != 2 * self.n_model:
+            offs = self.field_offsets[: self.n_model] // 4
+            cols = np.stack([offs, offs + 1], axis=1)
             self._param_cols = torch.from_numpy(cols.reshape(-1).astype(np.int64)).to(self.device)
         x = rows32.index_select(1, self._param_cols).contiguous().view(torch.float64)
         return torch.as_tensor(fn(x), device=self.device).to(torch.float64).reshape(n_written)
@@ -400,11 +404,17 @@ class PopulateEngine:
         if getattr(self, "d_logl", None) is None or self.d_logl.shape[0] < self._cap:
             self.d_logl = torch.empty(self._cap, dtype=torch.float64, device=self.device)
             self._gen += 1
-        ll = self.likelihood(self.physical_x(n))
-        ll = torch.as_tensor(ll, device=self.device).to(torch.float64).reshape(n)
-        self.d_logl[:n] = ll
-        lw = self.d_logw[:n]
-        lw.masked_fill_(~(ll > self.log_l_threshold), float("nan"))
+        self._likelihood_cut(self.physical_x(n), 0, n, n)
+
+    def _likelihood_cut(self, x: torch.Tensor, off: int, n: int, n_stats: int):
+        """logL of the ``n`` rows at row offset ``off`` (physical ``x``), the contour cut on their
+        weights, and the statistics recomputed over the first ``n_stats`` rows of the weights."""
+        if self.n_model < self.D:
+            x = x[:, : self.n_model].contiguous()
+        ll = torch.as_tensor(self.likelihood(x), device=self.device).to(torch.float64).reshape(n)
+        self.d_logl[off : off + n] = ll
+        self.d_logw[off : off + n].masked_fill_(~(ll > self.log_l_threshold), float("nan"))
+        lw = self.d_logw[:n_stats]
         valid = ~torch.isnan(lw)
         self.d_stats[0] = torch.where(valid, lw, torch.full_like(lw, -float("inf"))).max()
         self.d_stats[1] = valid.sum().to(torch.float64)
@@ -619,8 +629,6 @@ class PopulateEngine:
         Returns ``(rows, n_proposed, n_accepted)`` like ``run``."""
         import math
 
-        if self.likelihood is not None:
-            raise NotImplementedError("nessai_b200: accumulate_weights with likelihood_threshold truncation")
         if self.log_prior_const is None:
             raise NotImplementedError("nessai_b200: accumulate_weights needs the prior on the device")
         n_samples, drawsize = int(n_samples), int(drawsize)
@@ -662,6 +670,14 @@ class PopulateEngine:
             self._turn_rows += drawsize
             turn += 1
             rows = turn * stride
+            if self.likelihood is not None and n_local > 0:
+                # LikelihoodThresholdTruncation inside the accumulating loop (flowproposal.py:456-467):
+                # the slot's rows at or below the contour leave, the running statistics are redone
+                self.likelihood_evaluations = getattr(self, "likelihood_evaluations", 0) + n_local
+                if getattr(self, "d_logl", None) is None or self.d_logl.shape[0] < self._cap:
+                    self.d_logl = torch.empty(self._cap, dtype=torch.float64, device=dev)
+                    self._gen += 1
+                self._likelihood_cut(self._slot_x(off, n_local), off, n_local, rows)
             if self.world > 1:
                 import torch.distributed as dist
 
@@ -712,10 +728,18 @@ class PopulateEngine:
             dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
         return int(tot.cpu())
 
+    def _slot_x(self, off: int, n: int) -> torch.Tensor:
+        """Physical x (float64) of ``n`` rows at row offset ``off`` of the accumulating buffers."""
+        return self.d_xp[off : off + n].to(torch.float64) * self.d_scale + self.d_shift
+
+    def _accumulate_logl_ptr(self):
+        with_logl = self.likelihood is not None and getattr(self, "d_logl", None) is not None and self.logl_offset >= 0
+        return self.d_logl.data_ptr() if with_logl else None
+
     def _accumulate_accept(self, rows: int, base: int, n_samples: int) -> None:
         self._call(_lib.load().nb200_populate_accept, [
             rows, self.D, self.d_xp.data_ptr(), self.d_scale.data_ptr(), self.d_shift.data_ptr(),
-            self.d_logw.data_ptr(), None, self.d_stats.data_ptr(), self._seed(), base,
+            self.d_logw.data_ptr(), self._accumulate_logl_ptr(), self.d_stats.data_ptr(), self._seed(), base,
             float(self.log_prior_const), self.d_template.data_ptr(), self.row_bytes,
             self.field_offsets.ctypes.data, self.logl_offset, self.d_rows.data_ptr(), n_samples, 0,
             self.d_counts.data_ptr(), self.d_scratch.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream,
@@ -952,10 +976,13 @@ class GeneralPopulateEngine(PopulateEngine):
             self.d_x64.data_ptr() + off * self.D * 8, self.d_stats.data_ptr(), stream,
         ], "nb200_reparam_tail")
 
+    def _slot_x(self, off: int, n: int) -> torch.Tensor:
+        return self.d_x64[off : off + n]
+
     def _accumulate_accept(self, rows: int, base: int, n_samples: int) -> None:
         self._call(_lib.load().nb200_populate_accept_x64, [
-            rows, self.D, self.d_x64.data_ptr(), self.d_logw.data_ptr(), None, self.d_stats.data_ptr(), self._seed(),
-            base, float(self.log_prior_const), self.d_template.data_ptr(), self.row_bytes,
+            rows, self.D, self.d_x64.data_ptr(), self.d_logw.data_ptr(), self._accumulate_logl_ptr(),
+            self.d_stats.data_ptr(), self._seed(), base, float(self.log_prior_const), self.d_template.data_ptr(), self.row_bytes,
             self.field_offsets.ctypes.data, self.logl_offset, self.d_rows.data_ptr(), n_samples, 0,
             self.d_counts.data_ptr(), self.d_scratch.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream,
         ], "nb200_populate_accept_x64")
@@ -998,10 +1025,6 @@ class B200FlowProposal:
             # truncation.py:431-435 (TRUNCATION_REGISTRY)
             raise ValueError(f"Unknown truncation method(s): {sorted(unknown)}")
         self.truncation_methods = methods
-        if accumulate_weights and "likelihood_threshold" in methods:
-            raise NotImplementedError(
-                "nessai_b200: accumulate_weights with likelihood_threshold truncation is not implemented"
-            )
         if fallback_reparameterisation not in ("zscore", "null", None):
             raise NotImplementedError(
                 "nessai_b200: only the 'zscore' and 'null' reparameterisations run on the device"

@@ -177,7 +177,8 @@ def test_general_engine_accumulate(monkeypatch):
 @pytest.mark.parametrize("variant", ["zscore", "rescaletobounds", "logit_mixed", "inversion_edges", "accumulate",
                                      "accumulate_min_log_q", "likelihood_threshold", "logit_likelihood_threshold",
                                      "zscore_gaussian_cdf", "angle_aux", "angle_and_radial_parameter",
-                                     "accumulate_logit"])
+                                     "accumulate_logit", "accumulate_likelihood_threshold",
+                                     "angle_aux_likelihood_threshold", "accumulate_angle_likelihood_threshold"])
 def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     """``B200NessaiFlowProposal.populate`` end to end with the reference's own proposal object
     (reparameterisations, truncation scheme, live-point dtype): engine selection, configuration
@@ -200,7 +201,7 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
         def __init__(self):
             self.names = list(names)
             self.bounds = {n: [-5.0, 5.0] for n in names}
-            if variant.startswith("angle"):  # x0: an angle in [0, 2 pi]; x1: a radius-like parameter
+            if "angle" in variant:  # x0: an angle in [0, 2 pi]; x1: a radius-like parameter
                 self.bounds["x0"] = [0.0, 2 * np.pi]
                 self.bounds["x1"] = [0.0, 5.0]
 
@@ -209,13 +210,13 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
 
         def log_likelihood(self, x):
             a = self.unstructured_view(x)
-            if variant.startswith("angle"):  # periodic in the angle
+            if "angle" in variant:  # periodic in the angle
                 return np.cos(a[..., 0] - 1.0) - 0.5 * np.sum((a[..., 1:] - 1.0) ** 2, axis=-1)
             return -0.5 * np.sum(a**2, axis=-1)
 
         def log_likelihood_torch(self, x):  # INTEGRATION.md 3a (host tensors on the simulated device)
             self.device_rows = getattr(self, "device_rows", 0) + x.shape[0]
-            if variant.startswith("angle"):
+            if "angle" in variant:
                 return torch.cos(x[:, 0] - 1.0) - 0.5 * ((x[:, 1:] - 1.0) ** 2).sum(dim=1)
             return -0.5 * (x * x).sum(dim=1)
 
@@ -228,6 +229,14 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
         inversion_edges=dict(reparameterisations={"inversion": dict(parameters=names)}),
         accumulate=dict(accumulate_weights=True),
         accumulate_min_log_q=dict(accumulate_weights=True, truncation_methods=["latent_radius", "min_log_q"]),
+        accumulate_likelihood_threshold=dict(accumulate_weights=True,
+                                             truncation_methods=["latent_radius", "likelihood_threshold"]),
+        angle_aux_likelihood_threshold=dict(
+            truncation_methods=["latent_radius", "likelihood_threshold"],
+            reparameterisations={"x0": "angle", "x1": "default", "x2": "z-score", "x3": "logit"}),
+        accumulate_angle_likelihood_threshold=dict(
+            accumulate_weights=True, truncation_methods=["latent_radius", "likelihood_threshold"],
+            reparameterisations={"x0": "angle", "x1": "default", "x2": "z-score", "x3": "logit"}),
         accumulate_logit=dict(accumulate_weights=True,
                               reparameterisations={"x0": "logit", "x1": "default", "x2": "default", "x3": "logit"}),
         zscore_gaussian_cdf=dict(reparameterisations={"zscore-gaussian-cdf": dict(parameters=names)}),
@@ -240,7 +249,7 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
                                                              "x3": "default"}),
     )[variant]
     contour = variant.endswith("likelihood_threshold")
-    LOG_P = -D * np.log(10.0) if not variant.startswith("angle") else -np.log(2 * np.pi * 5.0 * 100.0)
+    LOG_P = -D * np.log(10.0) if "angle" not in variant else -np.log(2 * np.pi * 5.0 * 100.0)
     model = Box()
     rng = np.random.default_rng(9)
     model.set_rng(rng)
@@ -251,7 +260,7 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     prop = CpuFlowB200Proposal(model, **common, **kw)
     prop.initialise()
     pts = np.clip(1.2 * rng.standard_normal((600, D)) + 0.5, -4.9, 4.9)
-    if variant.startswith("angle"):
+    if "angle" in variant:
         pts[:, 0] = (1.0 + 0.8 * rng.standard_normal(600)) % (2 * np.pi)
         pts[:, 1] = np.clip(np.abs(1.0 + 0.7 * rng.standard_normal(600)), 0.05, 4.9)
     live = numpy_array_to_live_points(pts, names)
@@ -276,8 +285,9 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     prop.populate(worst, n_samples=400, plot=False)
     assert prop._engine is not None and len(sim.calls) > 0  # not the host loop
     general = variant in ("logit_mixed", "inversion_edges", "logit_likelihood_threshold", "zscore_gaussian_cdf",
-                          "angle_aux", "angle_and_radial_parameter", "accumulate_logit")
-    if variant == "angle_aux":  # the auxiliary radius never reaches the sampler (flowproposal/base.py:1100-1128)
+                          "angle_aux", "angle_and_radial_parameter", "accumulate_logit",
+                          "angle_aux_likelihood_threshold", "accumulate_angle_likelihood_threshold")
+    if "angle_aux" in variant or variant == "accumulate_angle_likelihood_threshold":  # the auxiliary radius never reaches the sampler (flowproposal/base.py:1100-1128)
         assert prop._engine.names == names + ["x0_radial"] and prop.samples.dtype.names[:D] == tuple(names)
         assert "x0_radial" in prop.x.dtype.names and "x0_radial" not in prop.samples.dtype.names
     if contour:  # the likelihood ran on the "device", inside the loop, never on the host
