@@ -520,7 +520,9 @@ def test_standalone_proposal_contract_on_simulated_device(tmp_path, monkeypatch)
 def test_gpu_test_bodies_pass_on_the_simulated_device():
     """tests/test_gpu_zz_tail_accumulate.py was written without access to a GPU: its test bodies
     (index arithmetic, loop replay, tolerances) are executed here against the simulated device,
-    in a subprocess because the dry run patches torch globally."""
+    in a subprocess because the dry run patches torch globally.  The bodies of the existing
+    populate tests (tests/test_gpu_populate.py, GPU-verified earlier) run too: a regression guard
+    for the shared host code the new paths hook into."""
     import json
     import os
     import subprocess
@@ -531,7 +533,7 @@ def test_gpu_test_bodies_pass_on_the_simulated_device():
     res = subprocess.run([sys.executable, os.path.join(REPO, "tests", "tools", "dryrun_gpu_tests_on_sim.py")],
                          capture_output=True, text=True, cwd=REPO, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert json.loads(res.stdout.strip().splitlines()[-1]) == {"dryrun_failed": 0, "of": 8}
+    assert json.loads(res.stdout.strip().splitlines()[-1]) == {"dryrun_failed": 0, "of": 14}
 
 
 def test_pipelined_loop_logic_equals_serial_loop(monkeypatch):

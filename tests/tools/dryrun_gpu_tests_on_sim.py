@@ -57,6 +57,11 @@ class SimB200FlowModel:
     def initialise(self):
         self.model = SimB200Flow(self.flow_config)
 
+    def forward_and_log_prob(self, x):
+        nf, D = self.model._handle.flow, self.model._handle.D
+        z, lj = nf.forward(np.asarray(x, dtype=np.float64))
+        return z, -0.5 * np.sum(z * z, axis=1) - 0.5 * D * np.log(2 * np.pi) + lj
+
 
 def main():
     sim = _simdevice.install()
@@ -89,6 +94,20 @@ def main():
         ("accumulate max_samples", lambda: t.test_accumulate_device_loop_matches_oracle(tmp(), 10**6, 2)),
         ("accumulate standalone", lambda: t.test_accumulate_through_the_standalone_proposal(tmp())),
         ("general accumulate", lambda: t.test_general_accumulate_reproduces_affine_accumulate(tmp())),
+    ]
+    # the EXISTING populate tests (GPU-verified earlier in the round): a regression guard for the
+    # shared host code that the new paths hook into (draw_turn / _after_draw / likelihood cut)
+    _simdevice.install_fake_cuda_async()
+    import test_gpu_populate as tp
+
+    runs += [
+        ("existing: fused turn", lambda: [tp.test_fused_turn_matches_numpy_restatement(nm, tmp()) for nm in
+                                          ("c2_realnvp_mlp", "c1_realnvp_2d", "d5_realnvp_perm_tanh")]),
+        ("existing: populate contract", lambda: tp.test_populate_contract(tmp())),
+        ("existing: host prior", lambda: tp.test_host_prior_path_matches_device_prior(tmp())),
+        ("existing: min_log_q", lambda: tp.test_min_log_q_truncation(tmp())),
+        ("existing: likelihood threshold", lambda: tp.test_likelihood_threshold_truncation_on_device(tmp())),
+        ("existing: pool likelihood", lambda: tp.test_pool_likelihood_on_device(tmp())),
     ]
     failed = 0
     for name, fn in runs:
