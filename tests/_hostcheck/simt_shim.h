@@ -1,0 +1,93 @@
+// TEST HARNESS ONLY: a minimal SIMT shim that lets g++ compile and RUN the CUDA kernels of
+// nessai_b200/csrc/reparam_tail.cuh unchanged on the CPU.  One OS thread per CUDA thread; the
+// blocks of a grid run one after the other, so a function-local `__shared__` variable becomes a
+// `static` shared by the threads of the running block.  __syncthreads() is a 256-thread barrier,
+// __shfl_xor_sync() an exchange through a per-warp slot array with two 32-thread barriers (every
+// lane of a warp must call it, as in the kernels), atomics are a mutex.  Faithful for kernels
+// whose warp-level primitives sit outside divergent code -- which is what is being checked.
+#pragma once
+#define __CUDACC__ 1
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __host__
+#define __device__
+#define __forceinline__ inline
+#define __global__
+#define __shared__ static
+#define __launch_bounds__(...)
+
+using std::isnan;
+
+struct simt_dim3 {
+  unsigned x = 1, y = 1, z = 1;
+};
+static thread_local simt_dim3 threadIdx, blockIdx;
+static simt_dim3 blockDim, gridDim;
+
+namespace simt {
+constexpr int kWarp = 32;
+inline std::unique_ptr<std::barrier<>> block_barrier;
+inline std::vector<std::unique_ptr<std::barrier<>>> warp_barrier;
+inline std::vector<double> shfl_slot;
+inline std::mutex atomic_mutex;
+}  // namespace simt
+
+inline void __syncthreads() { simt::block_barrier->arrive_and_wait(); }
+
+inline double __shfl_xor_sync(unsigned, double v, int lane_mask) {
+  const unsigned tid = threadIdx.x, warp = tid / simt::kWarp;
+  simt::shfl_slot[tid] = v;
+  simt::warp_barrier[warp]->arrive_and_wait();
+  const double r = simt::shfl_slot[tid ^ (unsigned)lane_mask];
+  simt::warp_barrier[warp]->arrive_and_wait();
+  return r;
+}
+
+inline double atomicAdd(double* p, double v) {
+  std::lock_guard<std::mutex> g(simt::atomic_mutex);
+  const double old = *p;
+  *p = old + v;
+  return old;
+}
+
+// CUDA's erfcinv for the device build of the header (supplied by the harness)
+extern "C" double nb200_host_erfcinv(double);
+inline double erfcinv(double y) { return nb200_host_erfcinv(y); }
+
+namespace nb200 {
+// populate_common.cuh's atomic maximum (that header needs the CUDA runtime; this is its contract)
+inline void atomic_max_double(double* addr, double v) {
+  std::lock_guard<std::mutex> g(simt::atomic_mutex);
+  if (v > *addr) *addr = v;
+}
+}  // namespace nb200
+
+// Run `kernel(args...)` over a 1-D grid of 1-D blocks.
+template <typename K, typename... A>
+void simt_launch(K kernel, unsigned grid, unsigned block, A... args) {
+  blockDim.x = block;
+  gridDim.x = grid;
+  simt::shfl_slot.assign(block, 0.0);
+  for (unsigned b = 0; b < grid; ++b) {
+    simt::block_barrier = std::make_unique<std::barrier<>>(block);
+    simt::warp_barrier.clear();
+    for (unsigned w = 0; w < (block + simt::kWarp - 1) / simt::kWarp; ++w)
+      simt::warp_barrier.push_back(std::make_unique<std::barrier<>>(simt::kWarp));
+    std::vector<std::thread> threads;
+    threads.reserve(block);
+    for (unsigned t = 0; t < block; ++t)
+      threads.emplace_back([=]() {
+        threadIdx.x = t;
+        blockIdx.x = b;
+        kernel(args...);
+      });
+    for (auto& th : threads) th.join();
+  }
+}

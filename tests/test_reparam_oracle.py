@@ -338,3 +338,84 @@ def test_other_angle_classes_are_refused(tmp_path):
         live = numpy_array_to_live_points(np.stack([rng.uniform(0, 6, 50), rng.uniform(-1, 1, 50)], axis=1), model.names)
         prop.check_state(live)
         assert parameter_maps(prop._reparameterisation, prop.prime_parameters, model.names, prop.parameters) is None
+
+
+# ------------------------------------------------------------------ the CUDA kernels under a CPU SIMT shim
+@pytest.fixture(scope="module")
+def simt_kernels(tmp_path_factory):
+    """reparam_tail_kernel / sum_exp_kernel -- the CUDA source, unchanged -- compiled by g++ against
+    tests/_hostcheck/simt_shim.h (one OS thread per CUDA thread, barriers for __syncthreads and the
+    warp shuffles)."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    out = tmp_path_factory.mktemp("simt") / "libreparam_simt.so"
+    d = os.path.join(REPO, "tests", "_hostcheck")
+    res = subprocess.run([gxx, "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-o", str(out),
+                          os.path.join(d, "reparam_kernels_simt.cpp"), os.path.join(d, "reparam_host.cpp")],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        if "barrier" in res.stderr:
+            pytest.skip("this g++ has no <barrier>")
+        raise RuntimeError(res.stderr)
+    lib = C.CDLL(str(out))
+    lib.simt_reparam_tail.restype = None
+    lib.simt_reparam_tail.argtypes = ([C.c_int, C.c_int64, C.c_int] + [C.c_void_p] * 9 + [C.c_double, C.c_double]
+                                      + [C.c_void_p] * 4)
+    lib.simt_sum_exp.restype = None
+    lib.simt_sum_exp.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    return lib
+
+
+@pytest.mark.parametrize("n,grid,pre", [(1500, 3, True), (700, 4, False), (5, 1, True), (256, 1, True)])
+def test_tail_kernel_source_runs_under_simt_shim(simt_kernels, n, grid, pre):
+    """The whole kernel, not only its row function: constants staged in shared memory, the
+    grid-stride loop (n > grid * 256 and n < grid * 256), the warp reduction and the published
+    statistics, against the oracle."""
+    from oracle.reparam_numpy import tail_rows
+
+    c = {k: v.copy() for k, v in TAIL_CASE.items()}
+    if not pre:
+        c["pre_scale"], c["pre_shift"], c["src"] = None, None, None
+        c["kind"][[7, 9]] = 0
+    d = len(c["kind"])
+    xp, logq_flow = tail_case_inputs(n)
+    x_ref, lq_ref, lw_ref, valid = tail_rows(xp, logq_flow, log_prior_const=-2.5, min_log_q=-14.0, **c)
+    logq, logw = logq_flow.copy(), np.full(n, 123.0)
+    x64 = np.full((n, d), 123.0)
+    stats = np.array([-np.inf, 0.0])
+    ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+    simt_kernels.simt_reparam_tail(grid, n, d, xp.ctypes.data, c["kind"].ctypes.data, ptr(c["src"]),
+                                   ptr(c["pre_scale"]), ptr(c["pre_shift"]), c["scale"].ctypes.data,
+                                   c["shift"].ctypes.data, c["lo"].ctypes.data, c["hi"].ctypes.data, -2.5, -14.0,
+                                   logq.ctypes.data, logw.ctypes.data, x64.ctypes.data, stats.ctypes.data)
+    np.testing.assert_array_equal(~np.isnan(logw), valid)
+    np.testing.assert_array_equal(~np.isnan(logq), valid)
+    with np.errstate(all="ignore"):
+        np.testing.assert_allclose(x64, x_ref, rtol=1e-13, atol=1e-13)  # every row written, none twice
+    np.testing.assert_allclose(logq[valid], lq_ref[valid], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(logw[valid], lw_ref[valid], rtol=1e-12, atol=1e-12)
+    assert stats[1] == valid.sum()
+    if valid.any():
+        assert stats[0] == logw[valid].max()
+    else:
+        assert stats[0] == -np.inf
+
+
+@pytest.mark.parametrize("n,grid", [(3000, 5), (100, 2), (0, 3)])
+def test_sum_exp_kernel_source_runs_under_simt_shim(simt_kernels, n, grid):
+    rng = np.random.default_rng(8)
+    logw = rng.normal(-3.0, 1.0, size=max(n, 1))
+    logw[rng.random(len(logw)) < 0.3] = np.nan
+    if n > 10:
+        logw[3] = -np.inf
+    valid = ~np.isnan(logw[:n]) & (logw[:n] > -np.inf)
+    mx = np.array([logw[:n][valid].max() if valid.any() else -np.inf, 0.0])
+    partials = np.full(grid, np.nan)
+    simt_kernels.simt_sum_exp(grid, logw.ctypes.data, n, mx.ctypes.data, partials.ctypes.data)
+    assert not np.isnan(partials).any()  # every block writes its partial, zeros included
+    np.testing.assert_allclose(partials.sum(), np.exp(logw[:n][valid] - mx[0]).sum() if valid.any() else 0.0,
+                               rtol=1e-13)
+    again = np.full(grid, np.nan)
+    simt_kernels.simt_sum_exp(grid, logw.ctypes.data, n, mx.ctypes.data, again.ctypes.data)
+    np.testing.assert_array_equal(partials, again)  # no atomics: reproducible
