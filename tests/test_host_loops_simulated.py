@@ -319,6 +319,10 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
         assert np.all(np.abs(np.log(got.std(0) / ref.std(0))) < 0.35)
         # (the acceptance is set by the largest weight of each turn: heavy-tailed, hence the wide band)
         assert 0.2 < prop.population_acceptance / ref_acceptance < 5.0
+    # the engine (device buffers, cached argument lists) is reused by the next populate
+    engine = prop._engine
+    prop.populate(worst, n_samples=100, plot=False)
+    assert prop._engine is engine
     # and the proposal still serves the sampler
     new = prop.draw(worst)
     assert new.dtype == ref_dtype and len(prop.indices) == prop.samples.size - 1
