@@ -6,6 +6,8 @@ has no known-answer vectors of its own for the flow; what its tes
 do pin are the self-consistency properties re-checked here.
 """
 
+import os
+
 import numpy as np
 import pytest
 from conftest import reference_or_skip
@@ -93,3 +95,65 @@ def test_shim_runs_reference_flow_properties():
             z2, _ = m.forward(x)
             lp2 = m.log_prob(x)
         assert torch.equal(z, z2) and torch.equal(lp, lp2)
+
+
+# ------------------------------------------------------------------ the CUDA Philox source on the host
+@pytest.fixture(scope="module")
+def philox_source():
+    """nessai_b200/csrc/philox.cuh -- the header the draw kernels include, its generator being
+    ``__host__ __device__`` -- compiled for the host by g++ (tests/_hostcheck/philox_host.cpp)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    import tempfile
+
+    from conftest import REPO
+
+    gxx = shutil.which("g++")
+    cuda_inc = "/usr/local/cuda/include"
+    if gxx is None or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("g++ or the CUDA headers are not available")
+    out = os.path.join(tempfile.mkdtemp(), "libphilox_host.so")
+    subprocess.run([gxx, "-O2", "-std=c++17", "-shared", "-fPIC", f"-I{cuda_inc}", "-o", out,
+                    os.path.join(REPO, "tests", "_hostcheck", "philox_host.cpp"), "-lm"], check=True)
+    lib = C.CDLL(out)
+    lib.philox_host.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.latent_row_host.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+    lib.accept_uniform_host.argtypes = [C.c_uint64, C.c_uint64]
+    lib.accept_uniform_host.restype = C.c_double
+    return lib
+
+
+def test_cuda_philox_source_known_answers(philox_source):
+    """Random123 known-answer vectors through the CUDA header itself: counter = (row_lo, row_hi,
+    block, stream), key = (seed_lo, seed_hi)."""
+    kat = [
+        ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+         (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+    ]
+    out = np.zeros(4, dtype=np.uint32)
+    for ctr, key, expect in kat:
+        philox_source.philox_host(key[0] | (key[1] << 32), ctr[0] | (ctr[1] << 32), ctr[2], ctr[3], out.ctypes.data)
+        assert tuple(int(v) for v in out) == expect
+
+
+def test_cuda_draw_source_matches_numpy_restatement(philox_source):
+    """The latent draw (Box-Muller on the Philox words, fp32) and the rejection step's uniform as
+    the kernels form them, against oracle/philox_numpy.py -- the restatement every GPU parity
+    test is driven by."""
+    from oracle.philox_numpy import accept_uniform, latent_normals
+
+    seed = 0x1234_5678_9ABC_DEF1
+    rows = np.array([0, 1, 2, 1000, 2**32 - 1, 2**32, 2**40 + 12345], dtype=np.uint64)
+    for D in (2, 5, 16, 32):
+        z = np.zeros(D, dtype=np.float32)
+        ref = latent_normals(seed, rows, D)
+        for i, r in enumerate(rows):
+            philox_source.latent_row_host(seed, int(r), D, z.ctypes.data)
+            np.testing.assert_allclose(z, ref[i], rtol=2e-6, atol=2e-6)  # fp32 evaluation vs float64
+    u = accept_uniform(seed, rows)
+    got = [philox_source.accept_uniform_host(seed, int(r)) for r in rows]
+    np.testing.assert_array_equal(got, u)
+    assert np.all((u > 0) & (u < 1))
