@@ -49,6 +49,20 @@ inline double __shfl_xor_sync(unsigned, double v, int lane_mask) {
   simt::warp_barrier[warp]->arrive_and_wait();
   return r;
 }
+inline float __shfl_xor_sync(unsigned m, float v, int lane_mask) {
+  return (float)__shfl_xor_sync(m, (double)v, lane_mask);  // a float survives the round trip exactly
+}
+
+// cache-hinted loads / stores and the fast-math intrinsics of the device build
+template <typename T>
+inline T __ldg(const T* p) { return *p; }
+template <typename T>
+inline T __ldcs(const T* p) { return *p; }
+template <typename T>
+inline void __stcs(T* p, T v) { *p = v; }
+inline float __fdividef(float a, float b) { return a / b; }
+inline float __expf(float x) { return expf(x); }
+inline float __logf(float x) { return logf(x); }
 
 inline double atomicAdd(double* p, double v) {
   std::lock_guard<std::mutex> g(simt::atomic_mutex);
