@@ -7,6 +7,7 @@
 // whose warp-level primitives sit outside divergent code -- which is what is being checked.
 #pragma once
 #define __CUDACC__ 1
+#include <algorithm>
 #include <barrier>
 #include <cmath>
 #include <cstdint>
@@ -24,6 +25,8 @@
 #define __launch_bounds__(...)
 
 using std::isnan;
+using std::max;  // CUDA's global integer min / max
+using std::min;
 
 struct simt_dim3 {
   unsigned x = 1, y = 1, z = 1;
