@@ -78,13 +78,36 @@ inline double atomicAdd(double* p, double v) {
 extern "C" double nb200_host_erfcinv(double);
 inline double erfcinv(double y) { return nb200_host_erfcinv(y); }
 
+inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long expected, unsigned long long v) {
+  std::lock_guard<std::mutex> g(simt::atomic_mutex);
+  const unsigned long long old = *p;
+  if (old == expected) *p = v;
+  return old;
+}
+inline long long __double_as_longlong(double v) {
+  long long r;
+  std::memcpy(&r, &v, sizeof r);
+  return r;
+}
+inline double __longlong_as_double(long long v) {
+  double r;
+  std::memcpy(&r, &v, sizeof r);
+  return r;
+}
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+#define __cosf(x) cosf(x)  // (glibc's <math.h> declares these two names itself)
+#define __sinf(x) sinf(x)
+using std::isfinite;
+
+#ifndef SIMT_HAVE_POPULATE_COMMON
 namespace nb200 {
-// populate_common.cuh's atomic maximum (that header needs the CUDA runtime; this is its contract)
+// populate_common.cuh's atomic maximum, for kernels compiled without that header
 inline void atomic_max_double(double* addr, double v) {
   std::lock_guard<std::mutex> g(simt::atomic_mutex);
   if (v > *addr) *addr = v;
 }
 }  // namespace nb200
+#endif
 
 // Run `kernel(args...)` over a 1-D grid of 1-D blocks.
 template <typename K, typename... A>

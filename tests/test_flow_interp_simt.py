@@ -79,3 +79,87 @@ def test_cuda_interpreter_matches_reference_golden_vectors(simt_interp, golden):
     back, blj, _ = run(simt_interp, sp, ff.program(True), z, lp_mode=1, grid=3)
     np.testing.assert_allclose(back, g["x"][:n], rtol=10 * rtol, atol=10 * atol)
     np.testing.assert_allclose(blj, -lj, rtol=10 * rtol, atol=10 * atol)
+
+
+# ------------------------------------------------------------------ the fused populate turn (generic kernel)
+@pytest.fixture(scope="module")
+def simt_populate(tmp_path_factory):
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    d = os.path.join(REPO, "tests", "_hostcheck")
+    out = tmp_path_factory.mktemp("simt") / "libpopulate_simt.so"
+    res = subprocess.run([gxx, "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", f"-I{d}/fake_cuda", "-o", str(out),
+                          os.path.join(d, "populate_draw_simt.cpp")], capture_output=True, text=True)
+    if res.returncode != 0:
+        if "barrier" in res.stderr:
+            pytest.skip("this g++ has no <barrier>")
+        raise RuntimeError(res.stderr)
+    lib = C.CDLL(str(out))
+    lib.simt_populate_draw.restype = C.c_int
+    lib.simt_populate_draw.argtypes = ([C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_double, C.c_int64,
+                                       C.c_uint64, C.c_uint64, C.c_float, C.c_float] + [C.c_void_p] * 4
+                                       + [C.c_double, C.c_double] + [C.c_void_p] * 5)
+    return lib
+
+
+@pytest.mark.parametrize("name,sqrt_t,min_log_q", [("c2_realnvp_mlp", 1.0, None), ("c1_realnvp_2d", 1.0, None),
+                                                   ("d5_realnvp_perm_tanh", 1.3, None), ("c2_realnvp_resnet", 1.0, -24.0),
+                                                   ("d6_nsf", 1.0, None), ("d8_maf", 1.0, None)])
+def test_cuda_fused_populate_turn_matches_oracle(simt_populate, name, sqrt_t, min_log_q):
+    """One fused turn of the generic kernel -- the CUDA sources of the Philox draw, the flow
+    interpreter and the float64 tail, on the CPU -- against the float64 oracle driven by the
+    restated Philox stream: same latent draws, same surviving rows, same x', log q, log w, same
+    turn statistics (what tests/test_gpu_populate.py checks on the GPU)."""
+    from oracle.flow_numpy import NumpyFlow
+    from oracle.philox_numpy import latent_normals
+    from oracle.populate_numpy import populate_turn
+
+    g, cfg, sd = load_golden(name)
+    sp = FlowSpec(cfg)
+    theta = np.zeros(sp.n_theta, np.float32)
+    ints = {}
+    sp.load_state_dict_numpy(sd, theta, ints)
+    prog = sp.fold(theta, ints).program(True)
+    D, n, seed, offset = sp.D, 700, 0xABCDEF1234, 10**10 + 7
+    rng = np.random.default_rng(3)
+    scale, shift = rng.uniform(0.8, 1.6, D), rng.uniform(-0.3, 0.3, D)
+    lo, hi = np.full(D, -3.5), np.full(D, 3.5)
+    lpc, r_max = -D * np.log(7.0), 1.15 * np.sqrt(D) * sqrt_t
+    ops = np.ascontiguousarray(prog.ops, dtype=np.int32)
+    blob = np.ascontiguousarray(prog.blob, dtype=np.float32)
+    xp = np.full((n, D), np.nan, dtype=np.float32)
+    z = np.full((n, D), np.nan, dtype=np.float32)
+    logq, logw = np.full(n, 7.0), np.full(n, 7.0)
+    stats = np.array([-np.inf, 0.0])
+    rc = simt_populate.simt_populate_draw(
+        3, ops.ctypes.data, int(ops.shape[0]), blob.ctypes.data, D, sp.H, sp.activation, int(prog.final_buf),
+        float(prog.const_logdet), n, seed, offset, r_max, sqrt_t, scale.ctypes.data, shift.ctypes.data, lo.ctypes.data,
+        hi.ctypes.data, lpc, float("nan") if min_log_q is None else min_log_q, xp.ctypes.data, logq.ctypes.data,
+        logw.ctypes.data, z.ctypes.data, stats.ctypes.data)
+    assert rc == 0
+    z_ref = latent_normals(seed, offset + np.arange(n), D)
+    np.testing.assert_allclose(z, z_ref * sqrt_t, rtol=1e-5, atol=2e-5)  # the draw is the Philox stream
+    kw = {k: v for k, v in dict(ftype=sp.ftype, net=sp.net, activation_name=cfg.get("activation", "relu"),
+                                hidden_features=sp.H).items()}
+    if sp.ftype == "nsf":
+        kw.update(num_bins=sp.num_bins, tail_bound=sp.tail_bound)
+    nf = NumpyFlow(sd, **kw)
+    t = populate_turn(nf, z_ref, scale=scale, shift=shift, lo=lo, hi=hi, log_prior_const=lpc, r_max=r_max,
+                      sqrt_t=sqrt_t, min_log_q=min_log_q)
+    # rows within fp32 rounding of the radius, a bound or min_log_q may flip
+    zz = z_ref * sqrt_t
+    edge = (np.abs(np.sqrt(np.sum(zz**2, axis=1)) - r_max) < 1e-4) | np.any(np.abs(np.abs(t["x"]) - 3.5) < 2e-3, axis=1)
+    if min_log_q is not None:
+        with np.errstate(invalid="ignore"):
+            edge |= np.abs(np.nan_to_num(t["log_q"], nan=1e9) - min_log_q) < 1e-3
+    dev_valid = ~np.isnan(logw)
+    np.testing.assert_array_equal(dev_valid[~edge], t["valid"][~edge])
+    assert 0.05 * n < t["valid"].sum() < 0.98 * n
+    both = dev_valid & t["valid"]
+    tol = dict(rtol=5e-4, atol=5e-4) if sp.ftype == "nsf" else dict(rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(xp[both].astype(np.float64) * scale + shift, t["x"][both], **tol)
+    np.testing.assert_allclose(logq[both], t["log_q"][both], **tol)
+    np.testing.assert_allclose(logw[both], t["log_w"][both], **tol)
+    np.testing.assert_array_equal(np.isnan(logq), np.isnan(logw))
+    assert stats[1] == dev_valid.sum() and stats[0] == logw[dev_valid].max()
