@@ -20,6 +20,7 @@ from conftest import load_golden, reference_or_skip
 
 pytestmark = pytest.mark.gpu
 
+
 def _dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
@@ -362,6 +363,72 @@ def test_accumulate_through_the_standalone_proposal(tmp_path):
     assert np.all(np.abs(a.mean(0) - mean_w) < 6 * sd_w * np.sqrt(1 / 2000 + 1 / ess))
 
 
+def test_general_accumulate_reproduces_affine_accumulate(tmp_path):
+    """accumulate_weights over the non-affine tail (slot-offset tail launches, scratch statistics
+    for the draw kernel, float64-row rejection step): with identity maps it must be the affine
+    engine's accumulating loop -- same turns, same expected pool sizes, same pool."""
+    from nessai_b200.proposal import PopulateEngine
+
+    drawsize = 20_000
+    gen, cfg, sd, _ = _general_engine(tmp_path, seed=31)
+    D = cfg["n_inputs"]
+    scale, shift = np.full(D, 1.3), np.linspace(-0.5, 0.5, D)
+    lo, hi, lpc = np.full(D, -4.0), np.full(D, 4.0), -D * np.log(8.0)
+    gen.configure(np.zeros(D, dtype=np.int32), scale, shift, lo, hi, lpc, 4.9, min_log_q=-40.0)
+    aff = PopulateEngine(gen.flow, gen.names, gen.row_dtype)
+    aff.seed = gen.seed
+    aff.configure(scale, shift, lo, hi, lpc, 4.9, min_log_q=-40.0)
+    ra, pa, aa = aff.run_accumulate(3000, drawsize, max_samples=10**7)
+    rg, pg, ag = gen.run_accumulate(3000, drawsize, max_samples=10**7)
+    assert pa == pg and aff.last_accumulate["rejects"] == gen.last_accumulate["rejects"]
+    np.testing.assert_allclose(aff.last_accumulate["n_expected"], gen.last_accumulate["n_expected"], rtol=1e-9)
+    assert abs(aa - ag) <= 2 and len(ra) == len(rg) == 3000  # (a weight within an ulp of log u may flip)
+    if aa == ag:
+        for nm in gen.names:
+            np.testing.assert_allclose(rg[nm], ra[nm], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["c2_realnvp_mlp", "c2_realnvp_resnet", "d6_nsf", "d8_maf", "c1_realnvp_2d"])
+def test_reference_self_consistency_pins(name, tmp_path):
+    """The self-consistency properties the reference's own tests pin at this boundary
+    (SURVEY.md 8c), on the kernels:
+    forward_and_log_prob(x) == (forward(x)[0], log_prob(x)) bit for bit
+    (tests/test_flows/test_included_flows.py:114-126); float64 outputs
+    (tests/test_flowmodel/test_flowmodel_base.py:543-549); sample_and_log_prob(z=z) ==
+    base_log_prob(z) - inverse(z)[1] (:552-570); outputs identical before and after the
+    train() -> eval() cache reset (:751-788, bit-exact)."""
+    from test_gpu_flow import make_model
+
+    g, cfg, sd = load_golden(name)
+    fm = make_model(cfg, sd, tmp_path)
+    x, zz = np.asarray(g["x"], dtype=np.float64), np.asarray(g["z"], dtype=np.float64)
+    z, lp = fm.forward_and_log_prob(x)
+    assert z.dtype == np.float64 and lp.dtype == np.float64 and z.shape == x.shape and lp.shape == (len(x),)
+    xt = fm.numpy_array_to_tensor(x)
+    z2, _ = fm.model.forward(xt)
+    lp2 = fm.model.log_prob(xt)
+    np.testing.assert_array_equal(z, z2.cpu().numpy().astype(np.float64))
+    np.testing.assert_array_equal(lp, lp2.cpu().numpy().astype(np.float64))
+    np.testing.assert_array_equal(fm.log_prob(x), lp)
+    x3, lq = fm.sample_and_log_prob(z=zz)
+    x4, lj = fm.inverse(zz)
+    assert x3.dtype == lq.dtype == x4.dtype == lj.dtype == np.float64
+    base = fm.model.base_distribution_log_prob(fm.numpy_array_to_tensor(zz)).cpu().numpy().astype(np.float64)
+    np.testing.assert_array_equal(x3, x4)
+    ok = np.isfinite(lq)
+    assert ok.mean() > 0.9
+    np.testing.assert_allclose(lq[ok], (base - lj)[ok], rtol=1e-5, atol=1e-4)
+    fm.model.train()
+    fm.model.eval()  # flowmodel/base.py:680-682
+    z5, lp5 = fm.forward_and_log_prob(x)
+    np.testing.assert_array_equal(z5, z)
+    np.testing.assert_array_equal(lp5, lp)
+    # inputs are caller-owned and never mutated; outputs are fresh and writable (SURVEY 8b P2)
+    assert np.array_equal(x, np.asarray(g["x"], dtype=np.float64))
+    lp -= 1.0
+    assert not np.shares_memory(lp, z)
+
+
 @pytest.mark.reference
 @pytest.mark.parametrize("variant", ["logit_and_default", "accumulate", "periodic_angle"])
 def test_flowsampler_variants_run_on_the_device_loop(tmp_path, variant):
@@ -435,69 +502,3 @@ def test_augmented_flow_proposal_on_b200_flows(tmp_path, marginalise):
         prop.rng = np.random.default_rng(1)
         b = prop._marginalise_augment(x.copy())
         assert np.all(np.isfinite(a)) and np.max(np.abs(a - b)) < 0.3
-
-
-@pytest.mark.parametrize("name", ["c2_realnvp_mlp", "c2_realnvp_resnet", "d6_nsf", "d8_maf", "c1_realnvp_2d"])
-def test_reference_self_consistency_pins(name, tmp_path):
-    """The self-consistency properties the reference's own tests pin at this boundary
-    (SURVEY.md 8c), on the kernels:
-    forward_and_log_prob(x) == (forward(x)[0], log_prob(x)) bit for bit
-    (tests/test_flows/test_included_flows.py:114-126); float64 outputs
-    (tests/test_flowmodel/test_flowmodel_base.py:543-549); sample_and_log_prob(z=z) ==
-    base_log_prob(z) - inverse(z)[1] (:552-570); outputs identical before and after the
-    train() -> eval() cache reset (:751-788, bit-exact)."""
-    from test_gpu_flow import make_model
-
-    g, cfg, sd = load_golden(name)
-    fm = make_model(cfg, sd, tmp_path)
-    x, zz = np.asarray(g["x"], dtype=np.float64), np.asarray(g["z"], dtype=np.float64)
-    z, lp = fm.forward_and_log_prob(x)
-    assert z.dtype == np.float64 and lp.dtype == np.float64 and z.shape == x.shape and lp.shape == (len(x),)
-    xt = fm.numpy_array_to_tensor(x)
-    z2, _ = fm.model.forward(xt)
-    lp2 = fm.model.log_prob(xt)
-    np.testing.assert_array_equal(z, z2.cpu().numpy().astype(np.float64))
-    np.testing.assert_array_equal(lp, lp2.cpu().numpy().astype(np.float64))
-    np.testing.assert_array_equal(fm.log_prob(x), lp)
-    x3, lq = fm.sample_and_log_prob(z=zz)
-    x4, lj = fm.inverse(zz)
-    assert x3.dtype == lq.dtype == x4.dtype == lj.dtype == np.float64
-    base = fm.model.base_distribution_log_prob(fm.numpy_array_to_tensor(zz)).cpu().numpy().astype(np.float64)
-    np.testing.assert_array_equal(x3, x4)
-    ok = np.isfinite(lq)
-    assert ok.mean() > 0.9
-    np.testing.assert_allclose(lq[ok], (base - lj)[ok], rtol=1e-5, atol=1e-4)
-    fm.model.train()
-    fm.model.eval()  # flowmodel/base.py:680-682
-    z5, lp5 = fm.forward_and_log_prob(x)
-    np.testing.assert_array_equal(z5, z)
-    np.testing.assert_array_equal(lp5, lp)
-    # inputs are caller-owned and never mutated; outputs are fresh and writable (SURVEY 8b P2)
-    assert np.array_equal(x, np.asarray(g["x"], dtype=np.float64))
-    lp -= 1.0
-    assert not np.shares_memory(lp, z)
-
-
-def test_general_accumulate_reproduces_affine_accumulate(tmp_path):
-    """accumulate_weights over the non-affine tail (slot-offset tail launches, scratch statistics
-    for the draw kernel, float64-row rejection step): with identity maps it must be the affine
-    engine's accumulating loop -- same turns, same expected pool sizes, same pool."""
-    from nessai_b200.proposal import PopulateEngine
-
-    drawsize = 20_000
-    gen, cfg, sd, _ = _general_engine(tmp_path, seed=31)
-    D = cfg["n_inputs"]
-    scale, shift = np.full(D, 1.3), np.linspace(-0.5, 0.5, D)
-    lo, hi, lpc = np.full(D, -4.0), np.full(D, 4.0), -D * np.log(8.0)
-    gen.configure(np.zeros(D, dtype=np.int32), scale, shift, lo, hi, lpc, 4.9, min_log_q=-40.0)
-    aff = PopulateEngine(gen.flow, gen.names, gen.row_dtype)
-    aff.seed = gen.seed
-    aff.configure(scale, shift, lo, hi, lpc, 4.9, min_log_q=-40.0)
-    ra, pa, aa = aff.run_accumulate(3000, drawsize, max_samples=10**7)
-    rg, pg, ag = gen.run_accumulate(3000, drawsize, max_samples=10**7)
-    assert pa == pg and aff.last_accumulate["rejects"] == gen.last_accumulate["rejects"]
-    np.testing.assert_allclose(aff.last_accumulate["n_expected"], gen.last_accumulate["n_expected"], rtol=1e-9)
-    assert abs(aa - ag) <= 2 and len(ra) == len(rg) == 3000  # (a weight within an ulp of log u may flip)
-    if aa == ag:
-        for nm in gen.names:
-            np.testing.assert_allclose(rg[nm], ra[nm], rtol=1e-12, atol=1e-12)
