@@ -36,6 +36,7 @@ static simt_dim3 blockDim, gridDim;
 
 namespace simt {
 constexpr int kWarp = 32;
+alignas(16) inline unsigned char dynamic_smem[64 * 1024];  // what a launch's dynamic shared memory points at
 inline std::unique_ptr<std::barrier<>> block_barrier;
 inline std::vector<std::unique_ptr<std::barrier<>>> warp_barrier;
 inline std::vector<double> shfl_slot;
@@ -55,6 +56,63 @@ inline double __shfl_xor_sync(unsigned, double v, int lane_mask) {
 inline float __shfl_xor_sync(unsigned m, float v, int lane_mask) {
   return (float)__shfl_xor_sync(m, (double)v, lane_mask);  // a float survives the round trip exactly
 }
+
+// generic warp exchange: every lane publishes a 64-bit word, then reads what it needs
+namespace simt {
+inline std::vector<unsigned long long> warp_word;
+template <typename F>
+inline auto warp_collective(unsigned long long mine, F read) {
+  const unsigned tid = threadIdx.x, warp = tid / kWarp;
+  warp_word[tid] = mine;
+  warp_barrier[warp]->arrive_and_wait();
+  auto r = read(&warp_word[warp * kWarp], tid % kWarp);
+  warp_barrier[warp]->arrive_and_wait();
+  return r;
+}
+}  // namespace simt
+
+inline unsigned __ballot_sync(unsigned, int pred) {
+  return simt::warp_collective(pred ? 1ull : 0ull, [](const unsigned long long* w, unsigned) {
+    unsigned m = 0;
+    for (int l = 0; l < simt::kWarp; ++l) m |= (unsigned)(w[l] & 1ull) << l;
+    return m;
+  });
+}
+template <typename T>
+inline T __shfl_sync(unsigned, T v, int src_lane) {
+  static_assert(sizeof(T) <= 8, "shim shuffles move at most 64 bits");
+  unsigned long long bits = 0;
+  std::memcpy(&bits, &v, sizeof(T));
+  const unsigned long long got = simt::warp_collective(
+      bits, [src_lane](const unsigned long long* w, unsigned) { return w[src_lane & (simt::kWarp - 1)]; });
+  T r;
+  std::memcpy(&r, &got, sizeof(T));
+  return r;
+}
+template <typename T>
+inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
+  unsigned long long bits = 0;
+  std::memcpy(&bits, &v, sizeof(T));
+  const unsigned long long got = simt::warp_collective(bits, [delta](const unsigned long long* w, unsigned lane) {
+    return lane >= delta ? w[lane - delta] : w[lane];  // lanes below delta keep their own value
+  });
+  T r;
+  std::memcpy(&r, &got, sizeof(T));
+  return r;
+}
+inline long long __shfl_xor_sync(unsigned, long long v, int lane_mask) {
+  return (long long)simt::warp_collective((unsigned long long)v, [lane_mask](const unsigned long long* w, unsigned lane) {
+    return w[lane ^ (unsigned)lane_mask];
+  });
+}
+inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
+inline unsigned atomicAdd(unsigned* p, unsigned v) {
+  std::lock_guard<std::mutex> g(simt::atomic_mutex);
+  const unsigned old = *p;
+  *p = old + v;
+  return old;
+}
+#define __align__(n) alignas(n)
 
 // cache-hinted loads / stores and the fast-math intrinsics of the device build
 template <typename T>
@@ -115,6 +173,7 @@ void simt_launch(K kernel, unsigned grid, unsigned block, A... args) {
   blockDim.x = block;
   gridDim.x = grid;
   simt::shfl_slot.assign(block, 0.0);
+  simt::warp_word.assign((block + simt::kWarp - 1) / simt::kWarp * simt::kWarp, 0ull);
   for (unsigned b = 0; b < grid; ++b) {
     simt::block_barrier = std::make_unique<std::barrier<>>(block);
     simt::warp_barrier.clear();
