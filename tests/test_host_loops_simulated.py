@@ -537,7 +537,7 @@ def test_gpu_test_bodies_pass_on_the_simulated_device():
     res = subprocess.run([sys.executable, os.path.join(REPO, "tests", "tools", "dryrun_gpu_tests_on_sim.py")],
                          capture_output=True, text=True, cwd=REPO, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert json.loads(res.stdout.strip().splitlines()[-1]) == {"dryrun_failed": 0, "of": 14}
+    assert json.loads(res.stdout.strip().splitlines()[-1]) == {"dryrun_failed": 0, "of": 15}
 
 
 def test_pipelined_loop_logic_equals_serial_loop(monkeypatch):

@@ -57,6 +57,10 @@ class SimB200FlowModel:
     def initialise(self):
         self.model = SimB200Flow(self.flow_config)
 
+    def sample_and_log_prob(self, N=1, z=None):
+        x, lq = self.model._handle.flow.sample_and_log_prob(np.asarray(z, dtype=np.float64))
+        return x, lq
+
     def forward_and_log_prob(self, x):
         nf, D = self.model._handle.flow, self.model._handle.D
         z, lj = nf.forward(np.asarray(x, dtype=np.float64))
@@ -109,6 +113,14 @@ def main():
         ("existing: likelihood threshold", lambda: tp.test_likelihood_threshold_truncation_on_device(tmp())),
         ("existing: pool likelihood", lambda: tp.test_pool_likelihood_on_device(tmp())),
     ]
+    # __graft_entry__.smoke(): the driver's round-end smoke test (flow parity + one fused populate turn)
+    import __graft_entry__ as entry
+    import nessai_b200._lib as nlib
+
+    torch.cuda.is_available = lambda: True
+    nlib.reset_launch_count = lambda: None
+    nlib.launch_count = lambda: len(sim.calls)
+    runs.append(("__graft_entry__.smoke", entry.smoke))
     failed = 0
     for name, fn in runs:
         n0 = len(sim.calls)
