@@ -209,6 +209,16 @@ __device__ __forceinline__ void tr_bgrad(float* __restrict__ g, const float* __r
 // Global -> shared staging uses cp.async (LDGSTS): a thread queues all its copies without waiting,
 // so a tile / a weight matrix costs ONE memory latency instead of one per loop iteration (with a
 // single warp per SM sub-partition there is no other latency hiding).
+#ifdef NB200_SIMT_SHIM
+// host flavour for the CPU SIMT shim of tests/_hostcheck: the copies complete at once
+__device__ __forceinline__ void tr_cp4(float* dst, const float* src) { *dst = *src; }
+__device__ __forceinline__ void tr_cp16(float* dst, const float* src) {
+  dst[0] = src[0], dst[1] = src[1], dst[2] = src[2], dst[3] = src[3];
+}
+__device__ __forceinline__ void tr_cp_commit() {}
+template <int N>
+__device__ __forceinline__ void tr_cp_wait() {}
+#else
 __device__ __forceinline__ uint32_t tr_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tr_cp4(float* dst, const float* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tr_s32(dst)), "l"(src) : "memory");
@@ -221,6 +231,7 @@ template <int N>
 __device__ __forceinline__ void tr_cp_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+#endif
 
 // Store a [n][16] shared tile to global memory (both 16-byte aligned).
 __device__ __forceinline__ void tr_copy(float* __restrict__ dst, const float* __restrict__ src,
@@ -777,7 +788,11 @@ __device__ __forceinline__ float tr_const_logdet(const TrBuffers& Bf, const TrPl
 }
 
 // ============================================================================ FWD(l)
+#ifdef NB200_SIMT_SHIM
+static float* const tr_smem_dyn = reinterpret_cast<float*>(simt::dynamic_smem);
+#else
 extern __shared__ __align__(16) float tr_smem_dyn[];
+#endif
 
 __global__ void __launch_bounds__(TR_THREADS) tr_fwd_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf, TrBatch bt, int l) {
   const TrLayer& ly = P.layer[l];

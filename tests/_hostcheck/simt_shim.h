@@ -23,6 +23,7 @@
 #define __global__
 #define __shared__ static
 #define __launch_bounds__(...)
+#define __grid_constant__
 
 using std::isnan;
 using std::max;  // CUDA's global integer min / max
@@ -36,7 +37,7 @@ static simt_dim3 blockDim, gridDim;
 
 namespace simt {
 constexpr int kWarp = 32;
-alignas(16) inline unsigned char dynamic_smem[64 * 1024];  // what a launch's dynamic shared memory points at
+alignas(16) inline unsigned char dynamic_smem[232 * 1024];  // what a launch's dynamic shared memory points at
 inline std::unique_ptr<std::barrier<>> block_barrier;
 inline std::vector<std::unique_ptr<std::barrier<>>> warp_barrier;
 inline std::vector<double> shfl_slot;
@@ -122,6 +123,7 @@ inline T __ldcs(const T* p) { return *p; }
 template <typename T>
 inline void __stcs(T* p, T v) { *p = v; }
 inline float __fdividef(float a, float b) { return a / b; }
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 inline float __expf(float x) { return expf(x); }
 inline float __logf(float x) { return logf(x); }
 
@@ -167,26 +169,32 @@ inline void atomic_max_double(double* addr, double v) {
 }  // namespace nb200
 #endif
 
-// Run `kernel(args...)` over a 1-D grid of 1-D blocks.
+// Run `kernel(args...)` over a 1-D grid of 1-D blocks.  `block` OS threads are created once per
+// launch and walk the blocks of the grid together (a barrier between blocks keeps the block-shared
+// statics of one block from leaking into the next).
 template <typename K, typename... A>
 void simt_launch(K kernel, unsigned grid, unsigned block, A... args) {
   blockDim.x = block;
   gridDim.x = grid;
   simt::shfl_slot.assign(block, 0.0);
   simt::warp_word.assign((block + simt::kWarp - 1) / simt::kWarp * simt::kWarp, 0ull);
-  for (unsigned b = 0; b < grid; ++b) {
-    simt::block_barrier = std::make_unique<std::barrier<>>(block);
-    simt::warp_barrier.clear();
-    for (unsigned w = 0; w < (block + simt::kWarp - 1) / simt::kWarp; ++w)
-      simt::warp_barrier.push_back(std::make_unique<std::barrier<>>(simt::kWarp));
-    std::vector<std::thread> threads;
-    threads.reserve(block);
-    for (unsigned t = 0; t < block; ++t)
-      threads.emplace_back([=]() {
+  simt::block_barrier = std::make_unique<std::barrier<>>(block);
+  simt::warp_barrier.clear();
+  for (unsigned w = 0; w < (block + simt::kWarp - 1) / simt::kWarp; ++w) {
+    const unsigned lanes = std::min<unsigned>(simt::kWarp, block - w * simt::kWarp);
+    simt::warp_barrier.push_back(std::make_unique<std::barrier<>>(lanes));
+  }
+  std::barrier<> next_block(block);
+  std::vector<std::thread> threads;
+  threads.reserve(block);
+  for (unsigned t = 0; t < block; ++t)
+    threads.emplace_back([&, t]() {
+      for (unsigned b = 0; b < grid; ++b) {
         threadIdx.x = t;
         blockIdx.x = b;
         kernel(args...);
-      });
-    for (auto& th : threads) th.join();
-  }
+        next_block.arrive_and_wait();
+      }
+    });
+  for (auto& th : threads) th.join();
 }
