@@ -69,4 +69,28 @@ extern "C" int simt_train_step(const int32_t* h_plan, int n_plan_ints, const int
   return 0;
 }
 
+// The validation loss (flowmodel/base.py:454-523): eval mode, running statistics, all layers of a
+// tile in one pass; mirrors nb200_eval_loss.  d_loss[1] and / or logp[n].
+extern "C" int simt_eval_loss(const int32_t* h_plan, int n_plan_ints, const int32_t* itab, int n_itab,
+                              const int32_t* reduce_idx, int n_reduce, float* theta_p, float* theta_b, const float* x,
+                              const float* w, int n, const float* pmask, float* d_loss, float* logp, int num_sms) {
+  using namespace nb200;
+  if (n_plan_ints != TR_PLAN_INTS) return 1;
+  TrPlan P;
+  std::memcpy(&P, h_plan, sizeof(TrPlan));
+  if (P.n_itab != n_itab || P.n_reduce != n_reduce) return 2;
+  TrBatch bt;
+  bt.x = x, bt.perm = nullptr, bt.w = w, bt.i0 = 0, bt.B = n, bt.n_tiles = (n + TR_R - 1) / TR_R;
+  const int G = std::min(bt.n_tiles, 2 * num_sms);
+  std::vector<float> eval_part(2 * 2 * num_sms);
+  TrBuffers B{};
+  B.itab = itab, B.reduce_idx = reduce_idx, B.theta_p = theta_p, B.theta_b = theta_b, B.G = G, B.pmask = pmask;
+  if (pmask)
+    simt_launch(tr_mask_params_kernel, (unsigned)std::min((P.n_params + 255) / 256, 2 * num_sms), 256u, theta_p, pmask,
+                P.n_params);
+  simt_launch(tr_eval_kernel, (unsigned)G, (unsigned)TR_THREADS, P, B, bt, eval_part.data(), logp);
+  if (d_loss) simt_launch(tr_eval_final_kernel, 1u, 32u, (const float*)eval_part.data(), G, d_loss);
+  return 0;
+}
+
 extern "C" double nb200_host_erfcinv(double) { return 0.0; }  // declared by the shim; unused here

@@ -35,6 +35,9 @@ def simt_train(tmp_path_factory):
     lib.simt_train_step.restype = C.c_int
     lib.simt_train_step.argtypes = ([C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 6
                                     + [C.c_int, C.c_int] + [C.c_double] * 6 + [C.c_int64] + [C.c_void_p] * 4 + [C.c_int])
+    lib.simt_eval_loss.restype = C.c_int
+    lib.simt_eval_loss.argtypes = ([C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+                                   + [C.c_int] + [C.c_void_p] * 3 + [C.c_int])
     return lib
 
 
@@ -145,3 +148,32 @@ def test_cuda_clip_and_optimiser_steps_match_oracle(simt_train, opt):
         assert np.abs(du - dv).max() < 2 * 3 * lr
     tol = dict(rtol=1e-4, atol=1e-5) if opt == "sgd" else dict(rtol=5e-3, atol=3e-3)
     np.testing.assert_allclose(cur[P:], theta64[P:], **tol)
+
+
+@pytest.mark.parametrize("name", ["c2_realnvp_resnet", "d5_realnvp_perm_tanh", "d6_nsf", "d8_maf"])
+def test_cuda_validation_loss_matches_reference_golden(simt_train, name):
+    """tr_eval_kernel (the validation loss of FlowModel._validate: eval mode, running statistics,
+    straight from the UNFOLDED parameters) against the reference's golden log-probabilities."""
+    g, spec, theta, ints = setup(name)
+    plan, itab, red = build_train_plan(spec, ints)
+    n = spec.n_params
+    theta_p, theta_b = theta[:n].copy(), theta[n:].copy()
+    pm = None
+    segs = param_mask(spec)
+    if segs:
+        pm = np.ones(n, dtype=np.float32)
+        for w_off, m_off, size in segs:
+            pm[w_off : w_off + size] = theta_b[m_off : m_off + size]
+    rows = 40
+    x = np.ascontiguousarray(g["x"][:rows], dtype=np.float32)
+    w = np.random.default_rng(1).uniform(0.5, 1.5, rows).astype(np.float32)
+    loss, logp = np.zeros(1, np.float32), np.zeros(rows, np.float32)
+    rc = simt_train.simt_eval_loss(plan.ctypes.data, int(plan.size), itab.ctypes.data, int(itab.size), red.ctypes.data,
+                                   int(red.size), theta_p.ctypes.data, theta_b.ctypes.data if theta_b.size else None,
+                                   x.ctypes.data, w.ctypes.data, rows, None if pm is None else pm.ctypes.data,
+                                   loss.ctypes.data, logp.ctypes.data, 148)
+    assert rc == 0
+    tol = 5e-4 if "nsf" in name else 1e-4
+    ref = np.asarray(g["fwd_logprob64"][:rows])
+    np.testing.assert_allclose(logp, ref, rtol=tol, atol=tol)
+    np.testing.assert_allclose(loss[0], -np.sum(w * ref) / np.sum(w), rtol=tol, atol=tol)  # base.py:404-407
