@@ -323,6 +323,35 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     engine = prop._engine
     prop.populate(worst, n_samples=100, plot=False)
     assert prop._engine is engine
+    if variant in ("zscore", "logit_mixed", "angle_aux", "accumulate_logit", "likelihood_threshold"):
+        # ... and the same populate with the entry points answered by the product's CUDA sources (SIMT
+        # shim) instead of the oracle: same Philox rows in, the same pool out
+        import _simtdevice
+        from nessai_b200 import _lib
+        from nessai_b200.spec import FlowSpec
+
+        libs = _simtdevice.build(tmp_path)
+        if libs is not None:
+            engine.seed, engine._turn_rows = 777, 0
+            engine._draw_key = engine._accept_key = None  # (the cached argument lists hold the seed)
+            prop.populate(worst, n_samples=150, plot=False)
+            pool_a, acc_a = np.stack([prop.samples[n] for n in names], axis=-1).copy(), prop.population_acceptance
+            spec = FlowSpec(dict(flow_config, n_inputs=len(prop.prime_parameters)))
+            theta = np.zeros(spec.n_theta, np.float32)
+            ints = {}
+            spec.load_state_dict_numpy(sd, theta, ints)
+            prop.flow.model._handle = _simtdevice.SimtHandle(spec, spec.fold(theta, ints).program(True))
+            simt = _simtdevice.SimtLib(libs)
+            monkeypatch.setattr(_lib, "load", lambda: simt)
+            engine._draw_key = engine._accept_key = None  # (cached argument lists hold the old handle)
+            engine._turn_rows = 0
+            prop.populate(worst, n_samples=150, plot=False)
+            assert prop._engine is engine and len(simt.calls) > 0
+            pool_b = np.stack([prop.samples[n] for n in names], axis=-1)
+            # (a row at rounding distance from a threshold may flip between the fp32 kernels and the
+            # float64 oracle; with these seeds none does)
+            assert prop.population_acceptance == acc_a
+            np.testing.assert_allclose(pool_b, pool_a, rtol=5e-4, atol=5e-4)
     # and the proposal still serves the sampler
     new = prop.draw(worst)
     assert new.dtype == ref_dtype and len(prop.indices) == prop.samples.size - 1
