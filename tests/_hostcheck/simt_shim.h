@@ -8,6 +8,7 @@
 #pragma once
 #define __CUDACC__ 1
 #include <algorithm>
+#include <atomic>
 #include <barrier>
 #include <cmath>
 #include <cstdint>
@@ -172,8 +173,38 @@ inline void atomic_max_double(double* addr, double v) {
 // Run `kernel(args...)` over a 1-D grid of 1-D blocks.  `block` OS threads are created once per
 // launch and walk the blocks of the grid together (a barrier between blocks keeps the block-shared
 // statics of one block from leaking into the next).
+namespace simt {
+inline bool launch_failed = false;  // the machine cannot run `block` OS threads at once
+// Can `block` threads exist at the same time here?  (A thread that cannot be created in the middle of
+// a launch would leave the others waiting at a barrier for ever, so this is probed beforehand.)
+inline bool can_run(unsigned block) {
+  static unsigned proven = 0;
+  if (block <= proven) return true;
+  std::atomic<bool> go{false};
+  std::vector<std::thread> probe;
+  bool ok = true;
+  try {
+    probe.reserve(block);
+    for (unsigned t = 0; t < block; ++t)
+      probe.emplace_back([&go]() {
+        while (!go.load()) std::this_thread::yield();
+      });
+  } catch (...) {
+    ok = false;
+  }
+  go.store(true);
+  for (auto& th : probe) th.join();
+  if (ok) proven = block;
+  return ok;
+}
+}  // namespace simt
+
 template <typename K, typename... A>
 void simt_launch(K kernel, unsigned grid, unsigned block, A... args) {
+  if (simt::launch_failed || !simt::can_run(block)) {
+    simt::launch_failed = true;
+    return;
+  }
   blockDim.x = block;
   gridDim.x = grid;
   simt::shfl_slot.assign(block, 0.0);
@@ -198,3 +229,8 @@ void simt_launch(K kernel, unsigned grid, unsigned block, A... args) {
     });
   for (auto& th : threads) th.join();
 }
+
+// Harness entry points report this when a launch could not run (tests skip on it).
+extern "C" int simt_launch_failed() { return simt::launch_failed ? 1 : 0; }
+// 0 when `block` OS threads can exist at once on this machine (fixtures skip otherwise).
+extern "C" int simt_probe(unsigned block) { return simt::can_run(block) ? 0 : 1; }

@@ -47,6 +47,8 @@ def build(tmpdir):
         getattr(libs[lib], fn).restype = i32
     libs["tail"].simt_reparam_tail.restype = None
     libs["tail"].simt_sum_exp.restype = None
+    if any(lib.simt_probe(256) != 0 for lib in libs.values()):
+        return None  # this machine cannot hold a block of OS threads
     return libs
 
 

@@ -47,3 +47,11 @@ def reference_or_skip():
     if not refenv.reference_available():
         pytest.skip("reference not installed under baseline/_ref")
     refenv.activate()
+
+
+def simt_or_skip(lib, block=512):
+    """A harness built on tests/_hostcheck/simt_shim.h runs one OS thread per CUDA thread: skip
+    where the machine cannot hold a whole block of them."""
+    if lib.simt_probe(int(block)) != 0:
+        pytest.skip(f"cannot run {block} threads at once here (SIMT shim)")
+    return lib

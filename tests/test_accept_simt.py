@@ -10,7 +10,7 @@ import subprocess
 
 import numpy as np
 import pytest
-from conftest import REPO
+from conftest import REPO, simt_or_skip
 
 from nessai_b200.livepoint import empty_structured_array, get_dtype
 from oracle.philox_numpy import accept_uniform
@@ -34,7 +34,7 @@ def simt_accept(tmp_path_factory):
     lib.simt_populate_accept.argtypes = ([C.c_int64, C.c_int] + [C.c_void_p] * 7 + [C.c_uint64, C.c_uint64, C.c_double,
                                          C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
                                          C.c_void_p, C.c_void_p])
-    return lib
+    return simt_or_skip(lib, 256)
 
 
 @pytest.mark.parametrize("n", [1, 1023, 1025, 5000])

@@ -9,7 +9,7 @@ import subprocess
 
 import numpy as np
 import pytest
-from conftest import REPO
+from conftest import REPO, simt_or_skip
 from test_gpu_coupling import numpy_coupling
 
 
@@ -29,7 +29,7 @@ def simt_coupling(tmp_path_factory):
     lib = C.CDLL(str(out))
     lib.simt_coupling.restype = C.c_int
     lib.simt_coupling.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int64, C.c_int, C.c_void_p] + [C.c_int] * 4
-    return lib
+    return simt_or_skip(lib, 256)
 
 
 @pytest.mark.parametrize("D,tf,vec", [(16, list(range(1, 16, 2)), 1), (16, [3, 0, 9], 1), (8, [0, 2, 4, 6], 1),

@@ -12,7 +12,7 @@ import subprocess
 
 import numpy as np
 import pytest
-from conftest import REPO, load_golden
+from conftest import REPO, load_golden, simt_or_skip
 
 from nessai_b200.spec import FlowSpec
 
@@ -36,7 +36,7 @@ def simt_interp(tmp_path_factory):
     lib.simt_flow_apply.restype = C.c_int
     lib.simt_flow_apply.argtypes = ([C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_double]
                                     + [C.c_void_p] * 4 + [C.c_int64, C.c_int])
-    return lib
+    return simt_or_skip(lib, 128)
 
 
 def run(lib, spec, prog, rows, lp_mode, grid=2):
@@ -100,7 +100,7 @@ def simt_populate(tmp_path_factory):
     lib.simt_populate_draw.argtypes = ([C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_double, C.c_int64,
                                        C.c_uint64, C.c_uint64, C.c_float, C.c_float] + [C.c_void_p] * 4
                                        + [C.c_double, C.c_double] + [C.c_void_p] * 5)
-    return lib
+    return simt_or_skip(lib, 128)
 
 
 @pytest.mark.parametrize("name,sqrt_t,min_log_q", [("c2_realnvp_mlp", 1.0, None), ("c1_realnvp_2d", 1.0, None),

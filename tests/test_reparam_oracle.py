@@ -12,7 +12,7 @@ import subprocess
 
 import numpy as np
 import pytest
-from conftest import REPO, reference_or_skip
+from conftest import REPO, reference_or_skip, simt_or_skip
 
 D = 4
 NAMES = [f"x{i}" for i in range(D)]
@@ -364,7 +364,7 @@ def simt_kernels(tmp_path_factory):
                                       + [C.c_void_p] * 4)
     lib.simt_sum_exp.restype = None
     lib.simt_sum_exp.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
-    return lib
+    return simt_or_skip(lib, 256)
 
 
 @pytest.mark.parametrize("n,grid,pre", [(1500, 3, True), (700, 4, False), (5, 1, True), (256, 1, True)])

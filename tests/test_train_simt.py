@@ -12,7 +12,7 @@ import subprocess
 
 import numpy as np
 import pytest
-from conftest import REPO, load_golden
+from conftest import REPO, load_golden, simt_or_skip
 
 from nessai_b200.spec import FlowSpec
 from nessai_b200.train_plan import build_train_plan, param_mask
@@ -38,7 +38,7 @@ def simt_train(tmp_path_factory):
     lib.simt_eval_loss.restype = C.c_int
     lib.simt_eval_loss.argtypes = ([C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4
                                    + [C.c_int] + [C.c_void_p] * 3 + [C.c_int])
-    return lib
+    return simt_or_skip(lib, 512)
 
 
 def setup(name):
