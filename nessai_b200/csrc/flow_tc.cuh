@@ -942,19 +942,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParam
 
 inline int tc_prep(const void* kernel, size_t smem) {
   // opt in to > 48 KB dynamic shared memory; remembers the largest size set per kernel
-  static thread_local const void* done[8];
-  static thread_local size_t done_smem[8];
+  // for the current device (the attribute is per device)
+  static thread_local const void* done[32];
+  static thread_local int done_dev[32];
+  static thread_local size_t done_smem[32];
   static thread_local int nd = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 1;
   int slot = -1;
   for (int i = 0; i < nd; ++i)
-    if (done[i] == kernel) slot = i;
+    if (done[i] == kernel && done_dev[i] == dev) slot = i;
   if (slot >= 0 && done_smem[slot] >= smem) return 0;
   if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
       cudaSuccess)
     return 1;
-  if (slot < 0 && nd < 8) slot = nd++;
+  if (slot < 0 && nd < 32) slot = nd++;
   if (slot >= 0) {
     done[slot] = kernel;
+    done_dev[slot] = dev;
     done_smem[slot] = smem;
   }
   return 0;

@@ -277,17 +277,22 @@ template <typename K>
 static int prep_kernel(K kernel, size_t smem) {
   // opt in to > 48 KB dynamic shared memory (static shared memory counts
   // against the 227 KB limit, so ask for what the launch needs, rounded up)
-  static thread_local const void* done[16];
-  static thread_local size_t done_smem[16];
+  // (the attribute is per device: the cache is keyed on kernel AND current device)
+  static thread_local const void* done[64];
+  static thread_local int done_dev[64];
+  static thread_local size_t done_smem[64];
   static thread_local int ndone = 0;
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
   int slot = -1;
   for (int i = 0; i < ndone; ++i)
-    if (done[i] == (const void*)kernel) slot = i;
+    if (done[i] == (const void*)kernel && done_dev[i] == dev) slot = i;
   if (slot >= 0 && done_smem[slot] >= smem) return 0;
   CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (slot < 0 && ndone < 16) slot = ndone++;
+  if (slot < 0 && ndone < 64) slot = ndone++;
   if (slot >= 0) {
     done[slot] = (const void*)kernel;
+    done_dev[slot] = dev;
     done_smem[slot] = smem;
   }
   return 0;
@@ -458,8 +463,12 @@ static int populate_accept_impl(int64_t n, int D, const float* d_xp, const doubl
     return fail(1, "nb200_populate_accept: bad arguments");
   if (row_bytes % 4 || row_bytes <= 0) return fail(1, "row_bytes must be a positive multiple of 4");
   if (D < 1 || D > 256) return fail(1, "nb200_populate_accept: D out of range");
-  if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) {
+    // an empty shard accepts nothing: {accepted, written} = {0, 0}, not the previous turn's
+    CUDA_OK(cudaMemsetAsync(d_counts, 0, 2 * sizeof(int64_t), st));
+    return 0;
+  }
   RowFormat F;
   F.row_words = row_bytes / 4;
   F.D = D;

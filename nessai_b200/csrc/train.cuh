@@ -1289,7 +1289,9 @@ __global__ void __launch_bounds__(256) tr_adam_kernel(TrBuffers Bf, int n_params
       __syncthreads();
     }
     if (threadIdx.x == 0) {
-      s_coef = o.clip > 0.f ? fminf(1.f, o.clip / (gn + 1e-6f)) : 1.f;
+      // torch.nn.utils.clip_grad_norm_: clamp(clip / (norm + 1e-6), max = 1), NaN propagates
+      const float c = o.clip / (gn + 1e-6f);
+      s_coef = o.clip > 0.f ? (c >= 1.f ? 1.f : c) : 1.f;
       if (blockIdx.x == 0) {
         const float loss = red[0];
         if (d_loss) d_loss[0] = loss, d_loss[1] = gn;

@@ -25,6 +25,7 @@ from typing import NamedTuple
 import numpy as np
 from nessai import config as nessai_config
 from nessai.livepoint import empty_structured_array as nessai_empty_structured_array
+from nessai.proposal.augmented import AugmentedFlowProposal
 from nessai.proposal.flowproposal import FlowProposal
 from nessai.reparameterisations import Angle, NullReparameterisation, RescaleToBounds, ScaleAndShift
 from nessai.utils import rescaling as _ref_rescaling
@@ -339,29 +340,23 @@ _check_dtype_surface()
 
 
 # ------------------------------------------------------------------ augmented flows
-def _augmented_class():
-    from nessai.proposal.augmented import AugmentedFlowProposal
+class B200AugmentedFlowProposal(AugmentedFlowProposal):
+    """``AugmentedFlowProposal`` (/root/reference/src/nessai/proposal/augmented.py:21-260) with
+    plugin point P2 swapped: the flow over the ``dims + augment_dims`` inputs (custom mask,
+    augmented.py:91-96) is trained and evaluated by the CUDA kernels, including the ``n_marg``
+    forward passes per proposed row of ``_marginalise_augment`` (:180-200), which reach
+    ``forward_and_log_prob`` as ONE batch of ``n * n_marg`` rows.  The populate loop itself is
+    the reference's host loop (the auxiliary parameters are not model parameters, so the fused
+    loop does not apply).
 
-    class B200AugmentedFlowProposal(AugmentedFlowProposal):
-        """``AugmentedFlowProposal`` (/root/reference/src/nessai/proposal/augmented.py:21-260) with
-        plugin point P2 swapped: the flow over the ``dims + augment_dims`` inputs (custom mask,
-        augmented.py:91-96) is trained and evaluated by the CUDA kernels, including the ``n_marg``
-        forward passes per proposed row of ``_marginalise_augment`` (:180-200), which reach
-        ``forward_and_log_prob`` as ONE batch of ``n * n_marg`` rows.  The populate loop itself is
-        the reference's host loop (the auxiliary parameters are not model parameters, so the fused
-        loop does not apply)."""
+    A module-level class: the sampler's checkpoint pickles the proposal
+    (samplers/base.py:346, utils/io.py:112), which needs a stable ``__module__.__qualname__``."""
 
-        _FlowModelClass = B200FlowModel
-
-    return B200AugmentedFlowProposal
+    _FlowModelClass = B200FlowModel
 
 
 # ------------------------------------------------------------------ importance nested sampler
 def __getattr__(name):
-    if name == "B200AugmentedFlowProposal":
-        cls = _augmented_class()
-        globals()[name] = cls
-        return cls
     # lazily re-exported: importing the importance sampler pulls in more of nessai
     if name in ("B200ImportanceFlowProposal", "B200ImportanceNestedSampler"):
         from . import nessai_ins_plugin

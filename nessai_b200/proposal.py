@@ -597,7 +597,11 @@ class PopulateEngine:
                 break
         self._accept_hint = hint
         if drawn_ahead:
-            self._last = None  # a draw that was not needed: nothing of it is read
+            # a draw that was not needed: nothing of it is read, and the likelihood calls its
+            # _after_draw made are not counted (the reference counts the turns it uses)
+            if self.likelihood is not None and self._last is not None:
+                self.likelihood_evaluations = getattr(self, "likelihood_evaluations", 0) - self._last[0]
+            self._last = None
         if host is not None or shared is not None:
             self._copy_stream.synchronize()  # d_rows is free for the next populate
         if tr is not None:

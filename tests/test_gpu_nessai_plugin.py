@@ -178,3 +178,46 @@ def test_importance_nested_sampler_runs_on_b200_flows(tmp_path):
     assert np.isfinite(ins.log_evidence)
     # analytic log Z = -4 log(16) = -11.09; a handful of levels gets within a few units
     assert -14.0 < ins.log_evidence < -8.0
+
+
+@pytest.mark.parametrize("which", ["b200flowproposal", "b200augmentedflowproposal"])
+def test_sampling_resume_with_b200_proposal(tmp_path, which):
+    """Checkpoint -> ``FlowSampler(resume=True)`` -> continue, with the B200 proposal classes
+    named as the entry-point strings a user would pass
+    (/root/reference/tests/test_sampling/test_standard_sampling.py:198-236; the checkpoint pickles
+    the proposal, samplers/base.py:346, and the flow model's ``__getstate__`` drops the device
+    state, flowmodel/base.py:921-957)."""
+    reference_or_skip()
+    import os
+
+    from nessai.flowsampler import FlowSampler
+
+    from nessai_b200 import nessai_plugin
+    from nessai_b200.flowmodel import B200FlowModel
+
+    cls = dict(b200flowproposal=nessai_plugin.B200NessaiFlowProposal,
+               b200augmentedflowproposal=nessai_plugin.B200AugmentedFlowProposal)[which]
+    extra = dict(augment_dims=1) if which == "b200augmentedflowproposal" else {}
+    output = str(tmp_path / "resume")
+    flow_config = dict(n_blocks=2, n_neurons=8)
+    fs = FlowSampler(
+        make_model(), output=output, resume=True, nlive=100, plot=False, flow_config=flow_config,
+        flow_proposal_class=cls, training_config=dict(max_epochs=20, patience=5),
+        training_frequency=10, maximum_uninformed=9, checkpoint_on_iteration=True,
+        checkpoint_interval=5, seed=1234, max_iteration=11, poolsize=10, **extra,
+    )
+    fs.run(plot=False, save=False)
+    assert os.path.exists(os.path.join(output, "nested_sampler_resume.pkl"))
+    assert isinstance(fs.ns._flow_proposal, cls) and fs.ns._flow_proposal.training_count >= 1
+
+    # a new model instance emulates a new run
+    fs = FlowSampler(make_model(), output=output, resume=True, flow_config=flow_config,
+                     flow_proposal_class=cls, plot=False)
+    assert fs.ns.iteration == 11
+    prop = fs.ns._flow_proposal
+    assert isinstance(prop, cls) and isinstance(prop.flow, B200FlowModel)
+    fs.ns.max_iteration = 21
+    fs.run(plot=False, save=False)
+    assert fs.ns.iteration == 21
+    assert os.path.exists(os.path.join(output, "nested_sampler_resume.pkl.old"))
+    assert np.isfinite(fs.ns.log_evidence)
