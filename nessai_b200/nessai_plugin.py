@@ -354,6 +354,14 @@ class B200AugmentedFlowProposal(AugmentedFlowProposal):
 
     _FlowModelClass = B200FlowModel
 
+    def resume(self, model, flow_config, weights_file=None):
+        """The pickled state keeps the custom mask as the ndarray ``__init__`` built
+        (augmented.py:91-96, flowproposal/base.py:1294-1295), but the reference's ``resume`` only
+        handles a list (base.py:1256-1259 leaves ``m`` unbound otherwise): hand it a list."""
+        if getattr(self, "mask", None) is not None and not isinstance(self.mask, list):
+            self.mask = np.asarray(self.mask).tolist()
+        super().resume(model, flow_config, weights_file=weights_file)
+
 
 # ------------------------------------------------------------------ importance nested sampler
 def __getattr__(name):
