@@ -59,10 +59,17 @@ int nb200_flow_inverse(nb200_flow* flow, const float* d_z, float* d_x, float* d_
 int nb200_flow_forward(nb200_flow* flow, const float* d_x, float* d_z, float* d_logj,
                        float* d_logp, int64_t n, void* stream);
 
-/* flowmodel/base.py:889-904 sample_latent_distribution: d_z[n*D] ~ N(0, I),
+/* Base distribution of the flow: N(0, var I), nessai's MultivariateNormal
+ * (flows/distributions.py:17-73, flow_config["distribution"] = "mvn" / "normal",
+ * flows/utils.py:35-102); var = 1 (the default) is nflows' StandardNormal.  Enters every
+ * log-probability (-0.5 |z|^2 / var - 0.5 D log(2 pi var)) and the draws of
+ * nb200_populate_draw (z = sqrt(T var) v). */
+int nb200_flow_set_base_variance(nb200_flow* flow, double var);
+
+/* flowmodel/base.py:889-904 sample_latent_distribution: d_z[n*D] ~ N(0, std_dev^2 I),
  * Philox4x32-10 keyed by `seed`, counter = row_offset + row. */
 int nb200_sample_latent(float* d_z, int64_t n, int D, uint64_t seed, uint64_t row_offset,
-                        void* stream);
+                        double std_dev, void* stream);
 
 /* One turn of the populate() loop, flowproposal/flowproposal.py:431-469, fused:
  * draw z (Philox; * sqrt_temperature) -> latent-radius truncation
@@ -204,6 +211,24 @@ int nb200_train_epoch(nb200_trainer* trainer, float* d_theta_p, float* d_theta_b
                       int64_t n_rows, int batch_size, int opt_kind, double lr, double beta1,
                       double beta2, double eps, double weight_decay, double clip, int64_t step0,
                       float* d_loss_sum, float* d_step_info, void* stream);
+
+/* flowmodel/base.py:620-680, the epoch loop of FlowModel.train, for up to 64 epochs in ONE
+ * cooperative launch: every optimisation step of every epoch (as nb200_train_epoch; epoch e takes
+ * its rows in the order d_perm[e * n_rows ...] and the learning rate h_lr[e]), the validation
+ * loss of the epoch on d_xv (base.py:454-523; n_val == 0: NaN) and the reference's loop control
+ * on the device: when `validate`, an epoch whose validation loss beats the best so far snapshots
+ * (theta_p, theta_b) into (d_best_p, d_best_b) (base.py:652-656), and the run stops once
+ * epoch - best_epoch > patience (base.py:658-660).  d_hist: float[2 * n_epochs] = {sum of the
+ * batch losses, validation loss} per epoch.  d_ctl: 4 words {float best_val, int best_epoch,
+ * int epochs_done, int stop}, read at the start (the caller initialises {+inf, 0, 0, 0}) and
+ * written at the end; epoch0 = epochs finished before this call. */
+int nb200_train_run(nb200_trainer* trainer, float* d_theta_p, float* d_theta_b, int64_t n_theta_b,
+                    float* d_m, float* d_v, const float* d_x, const float* d_w,
+                    const int64_t* d_perm, int64_t n_rows, int batch_size, const float* d_xv,
+                    const float* d_wv, int64_t n_val, int n_epochs, int epoch0, int validate,
+                    int patience, int opt_kind, const double* h_lr, double beta1, double beta2,
+                    double eps, double weight_decay, double clip, int64_t step0, float* d_hist,
+                    void* d_ctl, float* d_best_p, float* d_best_b, void* stream);
 
 /* flowmodel/base.py:454-523 FlowModel._validate: eval-mode (running statistics) loss of
  * the UNFOLDED parameters, d_loss[0] = -sum(w log_prob)/sum(w); d_logp (may be NULL):

@@ -77,9 +77,10 @@ _SIGS = {
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
     ),
+    "nb200_flow_set_base_variance": (C.c_int, [C.c_void_p, C.c_double]),
     "nb200_sample_latent": (
         C.c_int,
-        [C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p],
+        [C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_double, C.c_void_p],
     ),
     "nb200_populate_draw": (
         C.c_int,
@@ -123,6 +124,13 @@ _SIGS = {
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
          C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
          C.c_double, C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "nb200_train_run": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+         C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+         C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
     "nb200_eval_loss": (
         C.c_int,

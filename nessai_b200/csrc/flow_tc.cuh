@@ -620,6 +620,10 @@ struct TcIO {
   float* out_lp;
   int lp_mode;  // 1: inverse (base(in) - logj), 2: forward (base(out) + logj)
   int64_t n;
+  // base distribution N(0, var I) (flows/distributions.py:17-73; var = 1: StandardNormal):
+  // log p(z) = -0.5 * base_inv_var * |z|^2 - base_log_z,  base_log_z = 0.5 D log(2 pi var)
+  float base_inv_var = 1.f;
+  float base_log_z = 0.f;
 };
 
 // The epilogue-group body shared by the apply and populate kernels: runs the whole
@@ -864,8 +868,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P
       if (valid) {
         if (io.out_logj) io.out_logj[row] = ld;
         if (io.out_lp) {
-          const float c = 0.5f * P.D * TC_LOG_2PI;
-          io.out_lp[row] = (io.lp_mode == 1) ? (-0.5f * ss_in - c) - ld : (-0.5f * ss_out - c) + ld;
+          const float c = io.base_log_z, hv = 0.5f * io.base_inv_var;
+          io.out_lp[row] = (io.lp_mode == 1) ? (-hv * ss_in - c) - ld : (-hv * ss_out - c) + ld;
         }
       }
     }
@@ -987,11 +991,10 @@ inline int tc_grid(int64_t n, int num_sms) {
   return (int)(want < num_sms ? want : num_sms);
 }
 
-inline int tc_launch_apply(TcProgram& t, const float* in, float* out, float* logj, float* lp,
-                           int64_t n, int lp_mode, int num_sms, cudaStream_t st) {
+inline int tc_launch_apply(TcProgram& t, const TcIO& io, int num_sms, cudaStream_t st) {
   const size_t smem = tc_smem_bytes(t.image_bytes);
+  const int64_t n = io.n;
   if (tc_prep((const void*)flow_tc_apply_kernel, smem)) return 1;
-  TcIO io{in, out, logj, lp, lp_mode, n};
   flow_tc_apply_kernel<<<tc_grid(n, num_sms), TC_THREADS, smem, st>>>(
       tc_params(t, t.const_logdet), io);
   return cudaGetLastError() != cudaSuccess;

@@ -523,8 +523,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_res_kernel(RsParams P, 
           }
           if (io.out_logj) io.out_logj[row] = logj;
           if (io.out_lp) {
-            const float cn = 0.5f * P.D * TC_LOG_2PI;
-            io.out_lp[row] = (io.lp_mode == 1) ? (-0.5f * ss - cn) - logj : (-0.5f * ss_out - cn) + logj;
+            const float cn = io.base_log_z, hv = 0.5f * io.base_inv_var;
+            io.out_lp[row] = (io.lp_mode == 1) ? (-hv * ss - cn) - logj : (-hv * ss_out - cn) + logj;
           }
         }
       } else {

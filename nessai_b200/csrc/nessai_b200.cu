@@ -8,6 +8,8 @@
 #include <cstring>
 #include <atomic>
 #include <new>
+#include <cstdlib>
+#include <vector>
 
 #include "../../include/nessai_b200.h"
 #include "flow_interp.cuh"
@@ -69,6 +71,7 @@ struct nb200_flow {
   int D, H, activation;
   int device;
   int num_sms;
+  double base_var = 1.0;  // base distribution N(0, base_var I)
   DirProgram dir[2];
 };
 
@@ -180,7 +183,7 @@ template <int ACT>
 __global__ void __launch_bounds__(128)
 flow_apply_kernel(FlowProgramDev P, const float* __restrict__ in, float* __restrict__ out,
                   float* __restrict__ out_logj, float* __restrict__ out_lp, int64_t n,
-                  int lp_mode) {
+                  int lp_mode, float base_inv_var, float base_log_z) {
   extern __shared__ float4 smem4[];
   float* Ws;
   float* bufs[4];
@@ -207,15 +210,16 @@ flow_apply_kernel(FlowProgramDev P, const float* __restrict__ in, float* __restr
     if (valid) {
       if (out_logj) out_logj[row] = ld;
       if (out_lp) {
-        const float c = 0.5f * P.D * LOG_2PI;
-        out_lp[row] = (lp_mode == 1) ? (-0.5f * ss_in - c) - ld : (-0.5f * ss_out - c) + ld;
+        // log N(z; 0, var I) = -0.5 |z|^2 / var - 0.5 D log(2 pi var)  (flows/distributions.py:45-56)
+        const float c = base_log_z, hv = 0.5f * base_inv_var;
+        out_lp[row] = (lp_mode == 1) ? (-hv * ss_in - c) - ld : (-hv * ss_out - c) + ld;
       }
     }
   }
 }
 
 __global__ void sample_latent_kernel(float* __restrict__ z, int64_t n, int D, uint64_t seed,
-                                     uint64_t row_offset) {
+                                     uint64_t row_offset, float std) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n) return;
   for (int d0 = 0; d0 < D; d0 += 4) {
@@ -223,7 +227,7 @@ __global__ void sample_latent_kernel(float* __restrict__ z, int64_t n, int D, ui
     float v[4];
     box_muller(r.x, r.y, v[0], v[1]);
     box_muller(r.z, r.w, v[2], v[3]);
-    for (int j = 0; j < 4 && d0 + j < D; ++j) z[row * D + d0 + j] = v[j];
+    for (int j = 0; j < 4 && d0 + j < D; ++j) z[row * D + d0 + j] = v[j] * std;
   }
 }
 
@@ -316,21 +320,22 @@ static int launch_apply(nb200_flow* f, int direction, const float* in, float* ou
   DirProgram& p = f->dir[direction];
   if (!p.d_ops) return fail(6, "program for direction %d not set", direction);
   if (n <= 0) return 0;
+  TcIO io{in, out, logj, lp, direction == 1 ? 1 : 2, n};
+  io.base_inv_var = (float)(1.0 / f->base_var);
+  io.base_log_z = (float)(0.5 * f->D * std::log(2.0 * M_PI * f->base_var));
   if (p.tc.valid && tc_enabled()) {
     g_launches += 1;
-    return tc_launch_apply(p.tc, in, out, logj, lp, n, direction == 1 ? 1 : 2, f->num_sms, st)
+    return tc_launch_apply(p.tc, io, f->num_sms, st)
                ? fail(2, "tc kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()))
                : 0;
   }
   if (p.rs.valid && tc_enabled()) {
-    TcIO io{in, out, logj, lp, direction == 1 ? 1 : 2, n};
     const int nl = rs_launch<0>(p.rs, io, PopulateArgs(), n, f->num_sms, st);
     if (!nl) return fail(2, "tc resnet kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     g_launches += nl;
     return 0;
   }
   if (p.ns.valid && tc_enabled()) {
-    TcIO io{in, out, logj, lp, direction == 1 ? 1 : 2, n};
     const int nl = ns_launch<0>(p.ns, io, PopulateArgs(), n, f->num_sms, st);
     if (!nl) return fail(2, "tc nsf kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     g_launches += nl;
@@ -346,7 +351,8 @@ static int launch_apply(nb200_flow* f, int direction, const float* in, float* ou
 #define LAUNCH_APPLY(ACT)                                                               \
   {                                                                                     \
     if (int rc = prep_kernel(flow_apply_kernel<ACT>, smem)) return rc;                  \
-    flow_apply_kernel<ACT><<<grid, BS, smem, st>>>(P, in, out, logj, lp, n, lp_mode);   \
+    flow_apply_kernel<ACT><<<grid, BS, smem, st>>>(P, in, out, logj, lp, n, lp_mode,    \
+                                                   io.base_inv_var, io.base_log_z);      \
   }
   if (f->activation == ACT_RELU) LAUNCH_APPLY(ACT_RELU)
   else if (f->activation == ACT_TANH) LAUNCH_APPLY(ACT_TANH)
@@ -371,13 +377,19 @@ extern "C" int nb200_flow_forward(nb200_flow* f, const float* d_x, float* d_z, f
   return launch_apply(f, 0, d_x, d_z, d_logj, d_logp, n, (cudaStream_t)stream);
 }
 
+extern "C" int nb200_flow_set_base_variance(nb200_flow* f, double var) {
+  if (!f || !(var > 0.0) || !std::isfinite(var)) return fail(1, "nb200_flow_set_base_variance: bad arguments");
+  f->base_var = var;
+  return 0;
+}
+
 extern "C" int nb200_sample_latent(float* d_z, int64_t n, int D, uint64_t seed,
-                                   uint64_t row_offset, void* stream) {
+                                   uint64_t row_offset, double std_dev, void* stream) {
   if (n <= 0) return 0;
-  if (!d_z || D < 1) return fail(1, "nb200_sample_latent: bad arguments");
+  if (!d_z || D < 1 || !(std_dev > 0.0)) return fail(1, "nb200_sample_latent: bad arguments");
   const int bs = 256;
   sample_latent_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
-      d_z, n, D, seed, row_offset);
+      d_z, n, D, seed, row_offset, (float)std_dev);
   g_launches += 1;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -400,7 +412,9 @@ extern "C" int nb200_populate_draw(nb200_flow* f, int64_t n, uint64_t seed, uint
   A.seed = seed;
   A.row_offset = row_offset;
   A.r_max = r_max;
-  A.sqrt_t = sqrt_temperature > 0.f ? sqrt_temperature : 1.f;
+  // z = sqrt(T var) v, v ~ N(0, I): a N(0, var I) base distribution (flows/distributions.py:17-73)
+  // enters the turn exactly like a latent temperature (populate_common.cuh: populate_log_const)
+  A.sqrt_t = (sqrt_temperature > 0.f ? sqrt_temperature : 1.f) * (float)std::sqrt(f->base_var);
   A.scale = d_scale;
   A.shift = d_shift;
   A.lo = d_lo;
@@ -629,8 +643,12 @@ struct nb200_trainer {
   float *wsum_part = nullptr, *loss_part = nullptr, *part = nullptr, *grad = nullptr;
   float *gn_part = nullptr, *eval_part = nullptr, *pmask = nullptr;
   float* stat_n = nullptr;
+  float* run_scalars = nullptr;  // [0] loss accumulator of nb200_train_run
+  unsigned* bar = nullptr;       // grid barrier counter of the persistent kernel
+  long long* trace = nullptr;    // NB200_TR_TRACE: phase timeline of CTA 0
   size_t smem_fwd = 0, smem_bwd = 0;
 };
+constexpr int TR_TRACE_CAP = 4096;
 
 static void trainer_free_rows(nb200_trainer* t) {
   cudaFree(t->ws), cudaFree(t->dout0), cudaFree(t->dout1), cudaFree(t->ldrow), cudaFree(t->crow);
@@ -645,6 +663,7 @@ extern "C" int nb200_trainer_destroy(nb200_trainer* t) {
   cudaFree(t->stat_part), cudaFree(t->stats), cudaFree(t->s_part0), cudaFree(t->s_part1);
   cudaFree(t->wsum_part), cudaFree(t->loss_part), cudaFree(t->part), cudaFree(t->grad);
   cudaFree(t->gn_part), cudaFree(t->eval_part), cudaFree(t->stat_n), cudaFree(t->pmask);
+  cudaFree(t->run_scalars), cudaFree(t->bar), cudaFree(t->trace);
   delete t;
   return 0;
 }
@@ -686,6 +705,18 @@ extern "C" int nb200_trainer_create(nb200_trainer** out, const int32_t* h_plan, 
     delete t;
     return fail(5, "flow too large for the training kernels (%zu KB shared memory)", t->smem_bwd / 1024);
   }
+  {
+    // the REDUCE phase of the persistent kernel borrows the first 3 D^2 floats of the map (LU
+    // chain rule) while S.red and the index tables stay live: they must lie behind it
+    const size_t red_off = tr_smem_floats(P.D, P.vals_floats, P.max_in, P.wmax, 0, true) -
+                           (size_t)TR_MAXG * (2 * P.D + 1) - 3 * TR_THREADS;
+    bool any_lu = false;
+    for (int l = 0; l < P.L; ++l) any_lu |= P.layer[l].lu_bias >= 0;
+    if (any_lu && red_off < (size_t)3 * P.D * P.D) {
+      delete t;
+      return fail(5, "training kernels: shared-memory map too small for the LU gradient (D=%d)", P.D);
+    }
+  }
   const int G = TR_MAXG;
 #define TR_ALLOC(ptr, count) CUDA_OK(cudaMalloc(&(ptr), sizeof(*(ptr)) * (size_t)(count)))
   TR_ALLOC(t->d_plan, 1);
@@ -702,6 +733,10 @@ extern "C" int nb200_trainer_create(nb200_trainer** out, const int32_t* h_plan, 
   TR_ALLOC(t->gn_part, TR_REDUCE_MAXBLOCKS);
   TR_ALLOC(t->eval_part, 2 * 2 * prop.multiProcessorCount);
   TR_ALLOC(t->stat_n, G);
+  TR_ALLOC(t->run_scalars, 4);
+  TR_ALLOC(t->bar, 4);
+  CUDA_OK(cudaMemset(t->run_scalars, 0, 4 * sizeof(float)));
+  if (getenv("NB200_TR_TRACE")) TR_ALLOC(t->trace, 2 * TR_TRACE_CAP);
   CUDA_OK(cudaMemcpy(t->d_plan, &t->h_plan, sizeof(TrPlan), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(t->d_itab, h_itab, sizeof(int) * n_itab, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(t->d_reduce, h_reduce_idx, sizeof(int) * n_reduce, cudaMemcpyHostToDevice));
@@ -770,22 +805,78 @@ extern "C" int nb200_trainer_copy_grad(nb200_trainer* t, float* d_out, void* str
   return 0;
 }
 
+// Cooperative launch of the persistent kernel over `n_epochs` epochs (or one gradient step).
+static int trainer_launch_run(nb200_trainer* t, float* d_theta_p, float* d_theta_b, TrRun& R, cudaStream_t st) {
+  const TrPlan& P = t->h_plan;
+  const int max_b = (int)std::min<int64_t>(R.batch_size, R.n_rows);
+  int max_tiles = (max_b + TR_R - 1) / TR_R;
+  if (int rc = trainer_reserve(t, max_tiles)) return rc;
+  if (int rc = prep_kernel(tr_train_kernel, t->smem_bwd)) return rc;
+  if (R.n_val > 0) max_tiles = std::max<int>(max_tiles, (int)((R.n_val + TR_R - 1) / TR_R));
+  const int G = std::max(1, std::min(max_tiles, std::min(TR_MAXG, t->num_sms)));
+  TrBuffers B = trainer_buffers(t, d_theta_p, d_theta_b, G);
+  B.n_reduce_blocks = G;
+  R.eval_part = t->eval_part;
+  R.bar = t->bar;
+  R.trace = t->trace;
+  R.trace_cap = t->trace ? TR_TRACE_CAP : 0;
+  CUDA_OK(cudaMemsetAsync(t->bar, 0, sizeof(unsigned), st));
+  if (t->trace) CUDA_OK(cudaMemsetAsync(t->trace, 0, sizeof(long long) * 2 * TR_TRACE_CAP, st));
+  void* args[] = {(void*)&t->h_plan, (void*)&B, (void*)&R};
+  CUDA_OK(cudaLaunchCooperativeKernel((const void*)tr_train_kernel, dim3(G), dim3(TR_THREADS), args, t->smem_bwd, st));
+  g_launches += 1;
+  if (t->trace) {
+    // debugging aid: phase timeline of CTA 0, "tag ns-since-start" per line
+    static std::vector<long long> h(2 * TR_TRACE_CAP);
+    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaMemcpy(h.data(), t->trace, sizeof(long long) * 2 * TR_TRACE_CAP, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(getenv("NB200_TR_TRACE"), "a")) {
+      fprintf(f, "# run G=%d epochs=%d rows=%lld batch=%d\n", G, R.n_epochs, (long long)R.n_rows, R.batch_size);
+      for (int i = 0; i < TR_TRACE_CAP && (i == 0 || h[2 * i + 1]); ++i)
+        fprintf(f, "%lld %lld\n", h[2 * i], h[2 * i + 1] - h[1]);
+      fclose(f);
+    }
+  }
+  return 0;
+}
+
+static int trainer_check_args(nb200_trainer* t, float* d_theta_p, float* d_theta_b, float* d_m, float* d_v,
+                              const float* d_x, int64_t n_rows, int batch_size, int opt_kind, const char* who) {
+  if (!t || !d_theta_p || !d_x || n_rows < 1 || batch_size < 1) return fail(1, "%s: bad arguments", who);
+  if (opt_kind < -1 || opt_kind > 2) return fail(1, "%s: unknown optimiser %d", who, opt_kind);
+  if (opt_kind >= 0 && opt_kind <= 1 && (!d_m || !d_v)) return fail(1, "%s: Adam needs its moment buffers", who);
+  const TrPlan& P = t->h_plan;
+  bool any_bn = false;
+  for (int l = 0; l < P.L; ++l) any_bn |= P.layer[l].bn_uw >= 0;
+  if (any_bn && !d_theta_b) return fail(1, "%s: BatchNorm buffers missing", who);
+  const int64_t last = n_rows % batch_size;
+  if (any_bn && (std::min<int64_t>(batch_size, n_rows) < 2 || last == 1))
+    return fail(1, "%s: a batch of one row has no batch variance", who);
+  return 0;
+}
+
 extern "C" int nb200_train_epoch(nb200_trainer* t, float* d_theta_p, float* d_theta_b, float* d_m,
                                  float* d_v, const float* d_x, const float* d_w,
                                  const int64_t* d_perm, int64_t n_rows, int batch_size,
                                  int opt_kind, double lr, double beta1, double beta2, double eps,
                                  double weight_decay, double clip, int64_t step0,
                                  float* d_loss_sum, float* d_step_info, void* stream) {
-  if (!t || !d_theta_p || !d_x || n_rows < 1 || batch_size < 1)
-    return fail(1, "nb200_train_epoch: bad arguments");
-  if (opt_kind < -1 || opt_kind > 2) return fail(1, "nb200_train_epoch: unknown optimiser %d", opt_kind);
-  if (opt_kind >= 0 && opt_kind <= 1 && (!d_m || !d_v))
-    return fail(1, "nb200_train_epoch: Adam needs its moment buffers");
+  if (int rc = trainer_check_args(t, d_theta_p, d_theta_b, d_m, d_v, d_x, n_rows, batch_size, opt_kind,
+                                  "nb200_train_epoch"))
+    return rc;
   const TrPlan& P = t->h_plan;
-  bool any_bn = false;
-  for (int l = 0; l < P.L; ++l) any_bn |= P.layer[l].bn_uw >= 0;
-  if (any_bn && !d_theta_b) return fail(1, "nb200_train_epoch: BatchNorm buffers missing");
   cudaStream_t st = (cudaStream_t)stream;
+  // NB200_TR_CHAIN=1: one launch per phase (the pre-persistent-kernel path; debugging aid)
+  static const bool chain = getenv("NB200_TR_CHAIN") != nullptr;
+  if (!chain) {
+    TrRun R{};
+    R.x = d_x, R.w = d_w, R.perm = d_perm, R.n_rows = n_rows, R.batch_size = batch_size;
+    R.n_epochs = 1, R.kind = opt_kind;
+    R.beta1 = (float)beta1, R.beta2 = (float)beta2, R.eps = (float)eps, R.weight_decay = (float)weight_decay;
+    R.clip = (float)clip, R.beta1d = beta1, R.beta2d = beta2, R.step0 = step0, R.lr[0] = (float)lr;
+    R.m = d_m, R.v = d_v, R.step_info = d_step_info, R.loss_accum = d_loss_sum;
+    return trainer_launch_run(t, d_theta_p, d_theta_b, R, st);
+  }
   const int max_b = (int)std::min<int64_t>(batch_size, n_rows);
   if (int rc = trainer_reserve(t, (max_b + TR_R - 1) / TR_R)) return rc;
   if (int rc = prep_kernel(tr_fwd_kernel, t->smem_fwd)) return rc;
@@ -806,29 +897,12 @@ extern "C" int nb200_train_epoch(nb200_trainer* t, float* d_theta_p, float* d_th
     bt.i0 = i0;
     bt.B = (int)std::min<int64_t>(batch_size, n_rows - i0);
     bt.n_tiles = (bt.B + TR_R - 1) / TR_R;
-    if (bt.B < 2 && any_bn) return fail(1, "nb200_train_epoch: a batch of one row has no batch variance");
     const int G = std::min(bt.n_tiles, std::min(TR_MAXG, t->num_sms));
     TrBuffers B = trainer_buffers(t, d_theta_p, d_theta_b, G);
-    // NB200_TR_SYNC=1: synchronise and report after every launch (debugging aid)
-    static const bool dbg = getenv("NB200_TR_SYNC") != nullptr;
-#define TR_DBG(what, idx)                                                                       \
-  if (dbg) {                                                                                    \
-    fprintf(stderr, "[nb200 train] %s %d ...", what, idx);                                      \
-    cudaError_t e_ = cudaStreamSynchronize(st);                                                 \
-    fprintf(stderr, " %s\n", cudaGetErrorString(e_));                                           \
-  }
-    for (int l = 0; l < P.L; ++l) {
-      tr_fwd_kernel<<<G, TR_THREADS, t->smem_fwd, st>>>(P, B, bt, l);
-      TR_DBG("fwd", l)
-    }
+    for (int l = 0; l < P.L; ++l) tr_fwd_kernel<<<G, TR_THREADS, t->smem_fwd, st>>>(P, B, bt, l);
     tr_loss_kernel<<<G, TR_THREADS, t->smem_fwd, st>>>(P, B, bt);
-    TR_DBG("loss", 0)
-    for (int l = P.L - 1; l >= 0; --l) {
-      tr_bwd_kernel<<<G, TR_THREADS, t->smem_bwd, st>>>(P, B, bt, l);
-      TR_DBG("bwd", l)
-    }
+    for (int l = P.L - 1; l >= 0; --l) tr_bwd_kernel<<<G, TR_THREADS, t->smem_bwd, st>>>(P, B, bt, l);
     tr_reduce_kernel<<<B.n_reduce_blocks, TR_RED_THREADS, 3 * P.D * P.D * sizeof(float), st>>>(P, B);
-    TR_DBG("reduce", 0)
     ++step;
     TrOptim o;
     o.kind = opt_kind;
@@ -847,6 +921,33 @@ extern "C" int nb200_train_epoch(nb200_trainer* t, float* d_theta_p, float* d_th
   }
   CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+extern "C" int nb200_train_run(nb200_trainer* t, float* d_theta_p, float* d_theta_b, int64_t n_theta_b,
+                               float* d_m, float* d_v, const float* d_x, const float* d_w,
+                               const int64_t* d_perm, int64_t n_rows, int batch_size, const float* d_xv,
+                               const float* d_wv, int64_t n_val, int n_epochs, int epoch0, int validate,
+                               int patience, int opt_kind, const double* h_lr, double beta1, double beta2,
+                               double eps, double weight_decay, double clip, int64_t step0, float* d_hist,
+                               void* d_ctl, float* d_best_p, float* d_best_b, void* stream) {
+  if (int rc = trainer_check_args(t, d_theta_p, d_theta_b, d_m, d_v, d_x, n_rows, batch_size, opt_kind,
+                                  "nb200_train_run"))
+    return rc;
+  if (n_epochs < 1 || n_epochs > TR_MAX_CHUNK) return fail(1, "nb200_train_run: 1..%d epochs per call", TR_MAX_CHUNK);
+  if (opt_kind < 0 || !h_lr || !d_hist || !d_ctl) return fail(1, "nb200_train_run: bad arguments");
+  if (validate && (!d_best_p || (n_theta_b > 0 && !d_best_b))) return fail(1, "nb200_train_run: snapshot buffers missing");
+  if (n_val > 0 && !d_xv) return fail(1, "nb200_train_run: validation rows missing");
+  if (n_val > (int64_t)1 << 30) return fail(1, "nb200_train_run: too many validation rows");
+  TrRun R{};
+  R.x = d_x, R.w = d_w, R.perm = d_perm, R.n_rows = n_rows, R.batch_size = batch_size;
+  R.xv = d_xv, R.wv = d_wv, R.n_val = n_val;
+  R.n_epochs = n_epochs, R.epoch0 = epoch0, R.validate = validate, R.patience = patience, R.kind = opt_kind;
+  R.beta1 = (float)beta1, R.beta2 = (float)beta2, R.eps = (float)eps, R.weight_decay = (float)weight_decay;
+  R.clip = (float)clip, R.beta1d = beta1, R.beta2d = beta2, R.step0 = step0;
+  for (int e = 0; e < n_epochs; ++e) R.lr[e] = (float)h_lr[e];
+  R.m = d_m, R.v = d_v, R.hist = d_hist, R.loss_accum = t->run_scalars;
+  R.ctl = (TrCtl*)d_ctl, R.best_p = d_best_p, R.best_b = d_best_b, R.n_b = (int)n_theta_b;
+  return trainer_launch_run(t, d_theta_p, d_theta_b, R, (cudaStream_t)stream);
 }
 
 extern "C" int nb200_eval_loss(nb200_trainer* t, float* d_theta_p, float* d_theta_b, const float* d_x,

@@ -94,7 +94,8 @@ __device__ __forceinline__ void populate_row(const PopulateArgs& A, int D, XP xp
   A.logw[row] = ok ? logw : NAN;
 }
 
-// row constant of log_q: D log sqrt(T) (latent temperature, base.py:401-414) plus the
+// row constant of log_q: D log sqrt(T) (latent temperature, base.py:401-414; a N(0, var I) base
+// distribution, flows/distributions.py:17-73, is the same thing with T var in place of T) plus the
 // log-Jacobian of the diagonal rescale, sum log|scale| (rescale.py:263-291)
 __device__ __forceinline__ double populate_log_const(const PopulateArgs& A, int D) {
   double s = (double)D * log((double)A.sqrt_t);

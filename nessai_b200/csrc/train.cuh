@@ -56,10 +56,12 @@ struct TrPlan {
   int tail_bound;    // float bits of the spline's linear-tail bound
   int hidden;        // conditioner width (nflows divides the unnormalised widths / heights by sqrt of it)
   int max_in;        // max(D, widest linear INPUT): rows of the staged-operand tiles
+  int base_var;      // float bits of the base distribution's variance (N(0, var I); 1: StandardNormal)
+  int pad0, pad1, pad2;
   TrLayer layer[TR_MAXL];
 };
 constexpr int TR_LAYER_INTS = 20 + 2 * TR_MAXBUF + 8 * TR_MAXLIN;
-constexpr int TR_PLAN_INTS = 16 + TR_MAXL * TR_LAYER_INTS;
+constexpr int TR_PLAN_INTS = 20 + TR_MAXL * TR_LAYER_INTS;
 static_assert(sizeof(TrLayer) == 4 * TR_LAYER_INTS, "TrLayer layout");
 static_assert(sizeof(TrPlan) == 4 * TR_PLAN_INTS, "TrPlan layout");
 
@@ -121,6 +123,10 @@ __device__ __forceinline__ float tr_dact(int act, float z) {
   const float s = tr_sigmoid(z);
   return s * (1.f + z * (1.f - s));
 }
+
+// Parameters are rewritten by the optimiser phase of the same (persistent) kernel: never read them
+// through the non-coherent path.
+__device__ __forceinline__ float tr_ldp(const float* p) { return *p; }
 
 // ---------------------------------------------------------------------------- tile GEMMs
 // out[c][r] (=|+=) bias[c] + sum_k W[k*ldw + c] * A[k][r] (+ res[c][r]);  c < N, r < 16.
@@ -478,8 +484,8 @@ __device__ __forceinline__ void tr_bn_setup(const TrBuffers& Bf, const TrLayer& 
     }
   }
   for (int d = threadIdx.x; d < D; d += TR_THREADS) {
-    bn[2 * D + d] = tr_softplus(__ldg(Bf.theta_p + ly.bn_uw + d)) + TR_BN_EPS;
-    bn[3 * D + d] = __ldg(Bf.theta_p + ly.bn_bias + d);
+    bn[2 * D + d] = tr_softplus(tr_ldp(Bf.theta_p + ly.bn_uw + d)) + TR_BN_EPS;
+    bn[3 * D + d] = tr_ldp(Bf.theta_p + ly.bn_bias + d);
   }
   __syncthreads();
 }
@@ -489,8 +495,8 @@ __device__ __forceinline__ void tr_bn_setup_eval(const TrBuffers& Bf, const TrLa
   for (int d = threadIdx.x; d < D; d += TR_THREADS) {
     bn[d] = Bf.theta_b[ly.bn_rm + d];
     bn[D + d] = rsqrtf(Bf.theta_b[ly.bn_rv + d] + TR_BN_EPS);
-    bn[2 * D + d] = tr_softplus(__ldg(Bf.theta_p + ly.bn_uw + d)) + TR_BN_EPS;
-    bn[3 * D + d] = __ldg(Bf.theta_p + ly.bn_bias + d);
+    bn[2 * D + d] = tr_softplus(tr_ldp(Bf.theta_p + ly.bn_uw + d)) + TR_BN_EPS;
+    bn[3 * D + d] = tr_ldp(Bf.theta_p + ly.bn_bias + d);
   }
   __syncthreads();
 }
@@ -778,10 +784,10 @@ __device__ __forceinline__ float tr_const_logdet(const TrBuffers& Bf, const TrPl
   for (int e = threadIdx.x; e < P.L * D; e += TR_THREADS) {
     const int l = e / D, d = e - l * D;
     const TrLayer& ly = P.layer[l];
-    if (ly.lu_bias >= 0) s += logf(tr_softplus(__ldg(Bf.theta_p + ly.lu_diag + d)) + TR_LU_EPS);
+    if (ly.lu_bias >= 0) s += logf(tr_softplus(tr_ldp(Bf.theta_p + ly.lu_diag + d)) + TR_LU_EPS);
     if (ly.bn_uw >= 0) {
       const float var = stats ? stats[(l * 2 + 1) * D + d] : Bf.theta_b[ly.bn_rv + d];
-      s += logf(tr_softplus(__ldg(Bf.theta_p + ly.bn_uw + d)) + TR_BN_EPS) - 0.5f * logf(var + TR_BN_EPS);
+      s += logf(tr_softplus(tr_ldp(Bf.theta_p + ly.bn_uw + d)) + TR_BN_EPS) - 0.5f * logf(var + TR_BN_EPS);
     }
   }
   return tr_block_sum(s, red);
@@ -794,11 +800,13 @@ static float* const tr_smem_dyn = reinterpret_cast<float*>(simt::dynamic_smem);
 extern __shared__ __align__(16) float tr_smem_dyn[];
 #endif
 
-__global__ void __launch_bounds__(TR_THREADS) tr_fwd_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf, TrBatch bt, int l) {
+// Phases are __device__ functions over a carved shared-memory map whose index tables are staged:
+// the persistent kernel (tr_train_kernel) runs them between grid barriers; the one-phase kernels
+// below it launch them one at a time (CPU SIMT shim of tests/_hostcheck, NB200_TR_CHAIN=1).
+__device__ __forceinline__ void tr_fwd_phase(const TrPlan& P, const TrBuffers& Bf, const TrBatch& bt, int l,
+                                             const TrSmem& S) {
   const TrLayer& ly = P.layer[l];
   const int D = P.D;
-  TrSmem S = tr_carve(tr_smem_dyn, P, false);
-  tr_stage_itab(Bf, P, S);
   const int* lperm = ly.perm_off >= 0 ? S.itab + ly.perm_off : nullptr;
   const bool bn_prev = l > 0 && P.layer[l - 1].bn_uw >= 0;
   if (bn_prev) tr_bn_setup(Bf, P.layer[l - 1], l - 1, D, bt.B, S.bn, S.bn + 4 * D, true, S.stage, S.red);
@@ -869,11 +877,10 @@ __global__ void __launch_bounds__(TR_THREADS) tr_fwd_kernel(const __grid_constan
 
 // ============================================================================ LOSS
 // z = BN_{L-1}(y_{L-1}); loss partial; dout_{L-1} = c_r z; BatchNorm backward sums of layer L-1.
-__global__ void __launch_bounds__(TR_THREADS) tr_loss_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf, TrBatch bt) {
+__device__ __forceinline__ void tr_loss_phase(const TrPlan& P, const TrBuffers& Bf, const TrBatch& bt,
+                                              const TrSmem& S) {
   const int D = P.D, L = P.L;
   const TrLayer& ly = P.layer[L - 1];
-  TrSmem S = tr_carve(tr_smem_dyn, P, false);
-  tr_stage_itab(Bf, P, S);
   const bool bn = ly.bn_uw >= 0;
   if (bn) tr_bn_setup(Bf, ly, L - 1, D, bt.B, S.bn, S.bn + 4 * D, true, S.stage, S.red);
   // the last layer's statistics are published by block 0 only: use our own copy for the constant
@@ -883,10 +890,10 @@ __global__ void __launch_bounds__(TR_THREADS) tr_loss_kernel(const __grid_consta
     for (int e = threadIdx.x; e < L * D; e += TR_THREADS) {
       const int l = e / D, d = e - l * D;
       const TrLayer& lq = P.layer[l];
-      if (lq.lu_bias >= 0) s += logf(tr_softplus(__ldg(Bf.theta_p + lq.lu_diag + d)) + TR_LU_EPS);
+      if (lq.lu_bias >= 0) s += logf(tr_softplus(tr_ldp(Bf.theta_p + lq.lu_diag + d)) + TR_LU_EPS);
       if (lq.bn_uw >= 0) {
         const float var = (l == L - 1) ? S.bn[4 * D + d] : Bf.stats[(l * 2 + 1) * D + d];
-        s += logf(tr_softplus(__ldg(Bf.theta_p + lq.bn_uw + d)) + TR_BN_EPS) - 0.5f * logf(var + TR_BN_EPS);
+        s += logf(tr_softplus(tr_ldp(Bf.theta_p + lq.bn_uw + d)) + TR_BN_EPS) - 0.5f * logf(var + TR_BN_EPS);
       }
     }
     cld = tr_block_sum(s, S.red);
@@ -898,6 +905,9 @@ __global__ void __launch_bounds__(TR_THREADS) tr_loss_kernel(const __grid_consta
     csum = tr_block_sum(s, S.red);
   }
   const float inv_csum = 1.f / csum;
+  // base distribution N(0, var I) (flows/distributions.py:45-56)
+  const float bvar = __int_as_float(P.base_var), binv = 1.f / bvar;
+  const float blogz = (float)D * (TR_HALF_LOG_2PI + 0.5f * logf(bvar));
   float s1 = 0.f, s2 = 0.f, loss = 0.f;
   float* dout = Bf.dout[(L - 1) & 1];
   for (int tile = blockIdx.x; tile < bt.n_tiles; tile += gridDim.x) {
@@ -921,14 +931,14 @@ __global__ void __launch_bounds__(TR_THREADS) tr_loss_kernel(const __grid_consta
       }
       S.X[e] = xh;
       S.H1[e] = z;
-      S.H2[e] = S.c[r] * z;
+      S.H2[e] = S.c[r] * z * binv;
     }
     __syncthreads();
     tr_copy(dout + (size_t)tile * D * TR_R, S.H2, D);
     if (threadIdx.x < TR_R) {
       float q = 0.f;
       for (int d = 0; d < D; ++d) q += S.H1[d * TR_R + threadIdx.x] * S.H1[d * TR_R + threadIdx.x];
-      const float logp = -0.5f * q - (float)D * TR_HALF_LOG_2PI + S.ld[threadIdx.x] + cld;
+      const float logp = -0.5f * binv * q - blogz + S.ld[threadIdx.x] + cld;
       loss += S.c[threadIdx.x] * logp;  // c == 0 for padding rows
     }
     if (bn && (int)threadIdx.x < D) {
@@ -950,11 +960,10 @@ __global__ void __launch_bounds__(TR_THREADS) tr_loss_kernel(const __grid_consta
 }
 
 // ============================================================================ BWD(l)
-__global__ void __launch_bounds__(TR_THREADS) tr_bwd_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf, TrBatch bt, int l) {
+__device__ __forceinline__ void tr_bwd_phase(const TrPlan& P, const TrBuffers& Bf, const TrBatch& bt, int l,
+                                             const TrSmem& S) {
   const TrLayer& ly = P.layer[l];
   const int D = P.D, act = P.act;
-  TrSmem S = tr_carve(tr_smem_dyn, P, true);
-  tr_stage_itab(Bf, P, S);
   const int* itab = S.itab;
   const int* lperm = ly.perm_off >= 0 ? S.itab + ly.perm_off : nullptr;
   const bool bn = ly.bn_uw >= 0;
@@ -969,7 +978,7 @@ __global__ void __launch_bounds__(TR_THREADS) tr_bwd_kernel(const __grid_constan
       for (int d = threadIdx.x; d < D; d += TR_THREADS) {
         Bf.grad[ly.bn_bias + d] = sS[d];
         const float dw = sS[D + d] - 1.f / bnp[2 * D + d];
-        Bf.grad[ly.bn_uw + d] = dw * tr_sigmoid(__ldg(Bf.theta_p + ly.bn_uw + d));
+        Bf.grad[ly.bn_uw + d] = dw * tr_sigmoid(tr_ldp(Bf.theta_p + ly.bn_uw + d));
       }
   }
   if (ly.lu_bias >= 0) tr_lu_dense(S.Wlu, S.stage, Bf.theta_p, ly, D, false);
@@ -1102,9 +1111,9 @@ __global__ void __launch_bounds__(TR_THREADS) tr_bwd_kernel(const __grid_constan
           const int d = lperm ? lperm[j] : j;
           const float mean = Bf.stats[((l - 1) * 2) * D + d];
           const float rstd = rsqrtf(Bf.stats[((l - 1) * 2 + 1) * D + d] + TR_BN_EPS);
-          const float w = tr_softplus(__ldg(Bf.theta_p + lp.bn_uw + d)) + TR_BN_EPS;
+          const float w = tr_softplus(tr_ldp(Bf.theta_p + lp.bn_uw + d)) + TR_BN_EPS;
           const float xh = (S.Pf[d * TR_R + r] - mean) * rstd;
-          S.H1[j * TR_R + r] = fmaf(w, xh, __ldg(Bf.theta_p + lp.bn_bias + d));
+          S.H1[j * TR_R + r] = fmaf(w, xh, tr_ldp(Bf.theta_p + lp.bn_bias + d));
           S.X[d * TR_R + r] = xh;
         }
       } else {
@@ -1163,12 +1172,15 @@ __global__ void __launch_bounds__(TR_THREADS) tr_bwd_kernel(const __grid_constan
 
 // ============================================================================ REDUCE
 // grad = sum of the per-CTA partials; LU chain rule (dense dW -> lower / upper / diagonal);
-// per-block sums of squares for the global gradient norm.
-__global__ void __launch_bounds__(TR_RED_THREADS) tr_reduce_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf) {
+// per-block sums of squares for the global gradient norm (gn_part[blockIdx.x]).
+// The caller hands out the work: LU layers l = lu_first, lu_first + lu_stride, ... (< L) and the
+// slice `gen_block` of `gen_blocks` of the ordinary parameters (gen_block < 0: none).
+// smem: >= 3 * D * D floats of scratch (LU layers only); red: >= NT floats.
+template <int NT>
+__device__ __forceinline__ void tr_reduce_phase(const TrPlan& P, const TrBuffers& Bf, float* smem, float* red,
+                                                int lu_first, int lu_stride, int gen_block, int gen_blocks) {
   const int D = P.D, G = Bf.G, n_part = P.n_part;
-  __shared__ float red[TR_RED_THREADS];
   float sq = 0.f;
-  const int b = blockIdx.x;
   // sum over the per-CTA partials with 8 independent loads in flight
   auto psum = [&](const float* src) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1182,26 +1194,27 @@ __global__ void __launch_bounds__(TR_RED_THREADS) tr_reduce_kernel(const __grid_
       if (g + u < G) acc[u] += src[(size_t)(g + u) * n_part];
     return ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
   };
-  if (b < P.L) {
-    const TrLayer& ly = P.layer[b];
+  for (int l = lu_first; l < P.L; l += lu_stride) {
+    const TrLayer& ly = P.layer[l];
     if (ly.bn_uw >= 0)
-      for (int d = threadIdx.x; d < D; d += TR_RED_THREADS) {
+      for (int d = threadIdx.x; d < D; d += NT) {
         const float g0 = Bf.grad[ly.bn_bias + d], g1 = Bf.grad[ly.bn_uw + d];
         sq += g0 * g0 + g1 * g1;
       }
     if (ly.lu_bias >= 0) {
-      float* sdW = tr_smem_dyn;         // [D][D]
+      float* sdW = smem;                 // [D][D]
       float* sLo = sdW + D * D;          // [D][D]
       float* sUp = sLo + D * D;          // [D][D]
-      for (int e = threadIdx.x; e < D * D; e += TR_RED_THREADS) {
+      __syncthreads();
+      for (int e = threadIdx.x; e < D * D; e += NT) {
         sdW[e] = psum(Bf.part + ly.lu_part_off + e);
         const int i = e / D, j = e - i * D;
-        sLo[e] = i == j ? 1.f : (j < i ? __ldg(Bf.theta_p + ly.lu_lower + i * (i - 1) / 2 + j) : 0.f);
-        sUp[e] = i == j ? tr_softplus(__ldg(Bf.theta_p + ly.lu_diag + i)) + TR_LU_EPS
-                        : (i < j ? __ldg(Bf.theta_p + ly.lu_upper + i * D - i * (i + 1) / 2 + (j - i - 1)) : 0.f);
+        sLo[e] = i == j ? 1.f : (j < i ? tr_ldp(Bf.theta_p + ly.lu_lower + i * (i - 1) / 2 + j) : 0.f);
+        sUp[e] = i == j ? tr_softplus(tr_ldp(Bf.theta_p + ly.lu_diag + i)) + TR_LU_EPS
+                        : (i < j ? tr_ldp(Bf.theta_p + ly.lu_upper + i * D - i * (i + 1) / 2 + (j - i - 1)) : 0.f);
       }
       __syncthreads();
-      for (int e = threadIdx.x; e < D * D; e += TR_RED_THREADS) {
+      for (int e = threadIdx.x; e < D * D; e += NT) {
         const int i = e / D, j = e - i * D;
         if (j < i) {  // d lower[i][j] = sum_k dW[i][k] Up[j][k]
           float s = 0.f;
@@ -1212,7 +1225,7 @@ __global__ void __launch_bounds__(TR_RED_THREADS) tr_reduce_kernel(const __grid_
           float s = 0.f;
           for (int k = i; k < D; ++k) s = fmaf(sLo[k * D + i], sdW[k * D + j], s);
           if (i == j) {
-            s = (s - 1.f / sUp[e]) * tr_sigmoid(__ldg(Bf.theta_p + ly.lu_diag + i));
+            s = (s - 1.f / sUp[e]) * tr_sigmoid(tr_ldp(Bf.theta_p + ly.lu_diag + i));
             Bf.grad[ly.lu_diag + i] = s;
           } else {
             Bf.grad[ly.lu_upper + i * D - i * (i + 1) / 2 + (j - i - 1)] = s;
@@ -1221,15 +1234,15 @@ __global__ void __launch_bounds__(TR_RED_THREADS) tr_reduce_kernel(const __grid_
         }
       }
     }
-  } else {
+  }
+  if (gen_block >= 0) {
     // 8 lanes per parameter (each sums every 8th partial, all loads independent), then a
     // 3-step shuffle: one memory latency per parameter instead of G/8
     const int n_reduce = P.n_reduce;
     const int sub = threadIdx.x & 7;
-    const int per_block = TR_RED_THREADS / 8;
+    const int per_block = NT / 8;
     // warp-uniform trip count (the shuffles below need all 32 lanes): 4 parameters per warp
-    for (int base = (b - P.L) * per_block + 4 * (threadIdx.x >> 5); base < n_reduce;
-         base += (gridDim.x - P.L) * per_block) {
+    for (int base = gen_block * per_block + 4 * (threadIdx.x >> 5); base < n_reduce; base += gen_blocks * per_block) {
       const int i = base + ((threadIdx.x & 31) >> 3);
       const bool ok = i < n_reduce;
       const int p = ok ? Bf.reduce_idx[i] : 0;
@@ -1256,53 +1269,46 @@ __global__ void __launch_bounds__(TR_RED_THREADS) tr_reduce_kernel(const __grid_
       }
     }
   }
-  const float tot = tr_block_sum<TR_RED_THREADS>(sq, red);
-  if (threadIdx.x == 0) Bf.gn_part[b] = tot;
+  const float tot = tr_block_sum<NT>(sq, red);
+  if (threadIdx.x == 0) Bf.gn_part[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(TR_RED_THREADS) tr_reduce_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf) {
+  __shared__ float red[TR_RED_THREADS];
+  const int b = blockIdx.x;
+  if (b < P.L) tr_reduce_phase<TR_RED_THREADS>(P, Bf, tr_smem_dyn, red, b, P.L, -1, 0);
+  else tr_reduce_phase<TR_RED_THREADS>(P, Bf, tr_smem_dyn, red, P.L, 1, b - P.L, (int)gridDim.x - P.L);
 }
 
 // ============================================================================ ADAM
 // clip_grad_norm_ + torch.optim.AdamW / Adam / SGD on the flat parameter vector.
-// d_loss[0] = this step's loss, d_loss[1] = gradient norm before clipping.
-__global__ void __launch_bounds__(256) tr_adam_kernel(TrBuffers Bf, int n_params, TrOptim o, float* __restrict__ m,
-                                                      float* __restrict__ v, float* d_loss,
-                                                      float* d_loss_accum) {
-  __shared__ float s_coef;
-  __shared__ float red[256];
+// d_loss[0] = this step's loss, d_loss[1] = gradient norm before clipping.  red: >= NT + 1 floats.
+template <int NT>
+__device__ __forceinline__ void tr_adam_phase(const TrBuffers& Bf, int n_params, const TrOptim& o,
+                                              float* __restrict__ m, float* __restrict__ v, float* d_loss,
+                                              float* d_loss_accum, float* red) {
   {
     float gsum = 0.f;
-    for (int i = threadIdx.x; i < Bf.n_reduce_blocks; i += blockDim.x) gsum += Bf.gn_part[i];
+    for (int i = threadIdx.x; i < Bf.n_reduce_blocks; i += NT) gsum += Bf.gn_part[i];
     float lsum = 0.f;
     if (blockIdx.x == 0)
-      for (int g = threadIdx.x; g < Bf.G; g += blockDim.x) lsum += Bf.loss_part[g];
-    red[threadIdx.x] = gsum;
-    __syncthreads();
-    for (int st = 128; st > 0; st >>= 1) {
-      if ((int)threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
-      __syncthreads();
-    }
-    const float gn = sqrtf(red[0]);
-    __syncthreads();
-    red[threadIdx.x] = lsum;
-    __syncthreads();
-    for (int st = 128; st > 0; st >>= 1) {
-      if ((int)threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
-      __syncthreads();
-    }
+      for (int g = threadIdx.x; g < Bf.G; g += NT) lsum += Bf.loss_part[g];
+    const float gn = sqrtf(tr_block_sum<NT>(gsum, red));
+    const float loss = tr_block_sum<NT>(lsum, red);
     if (threadIdx.x == 0) {
       // torch.nn.utils.clip_grad_norm_: clamp(clip / (norm + 1e-6), max = 1), NaN propagates
       const float c = o.clip / (gn + 1e-6f);
-      s_coef = o.clip > 0.f ? (c >= 1.f ? 1.f : c) : 1.f;
+      red[NT] = o.clip > 0.f ? (c >= 1.f ? 1.f : c) : 1.f;
       if (blockIdx.x == 0) {
-        const float loss = red[0];
         if (d_loss) d_loss[0] = loss, d_loss[1] = gn;
         if (d_loss_accum) d_loss_accum[0] += loss;
       }
     }
     __syncthreads();
   }
-  const float coef = s_coef;
+  const float coef = red[NT];
   const int n = n_params;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT) {
     float g = Bf.grad[i] * coef;
     if (o.kind < 0) {
       Bf.grad[i] = g;
@@ -1323,6 +1329,14 @@ __global__ void __launch_bounds__(256) tr_adam_kernel(TrBuffers Bf, int n_params
     const float denom = sqrtf(vi) / sqrtf(o.bc2) + o.eps;
     Bf.theta_p[i] = p - (o.lr / o.bc1) * (mi / denom);
   }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) tr_adam_kernel(TrBuffers Bf, int n_params, TrOptim o, float* __restrict__ m,
+                                                      float* __restrict__ v, float* d_loss,
+                                                      float* d_loss_accum) {
+  __shared__ float red[256 + 1];
+  tr_adam_phase<256>(Bf, n_params, o, m, v, d_loss, d_loss_accum, red);
 }
 
 // theta_p *= mask: masked MADE weights are kept at exactly zero (they never influence the
@@ -1334,12 +1348,12 @@ __global__ void tr_mask_params_kernel(float* __restrict__ theta_p, const float* 
 // ============================================================================ EVAL
 // Eval-mode loss (FlowModel._validate, flowmodel/base.py:454-523): running statistics, every layer
 // of a tile in one pass.  out_part[g] = {sum c logp, sum c}; also per-row log_prob when d_logp.
-__global__ void __launch_bounds__(TR_THREADS) tr_eval_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf, TrBatch bt, float* out_part,
-                                                             float* d_logp) {
+__device__ __forceinline__ void tr_eval_phase(const TrPlan& P, const TrBuffers& Bf, const TrBatch& bt,
+                                              float* out_part, float* d_logp, const TrSmem& S) {
   const int D = P.D, L = P.L;
-  TrSmem S = tr_carve(tr_smem_dyn, P, false);
-  tr_stage_itab(Bf, P, S);
   const float cld = tr_const_logdet(Bf, P, nullptr, S.red);
+  const float bvar = __int_as_float(P.base_var), binv = 1.f / bvar;
+  const float blogz = (float)D * (TR_HALF_LOG_2PI + 0.5f * logf(bvar));
   float loss = 0.f, csum = 0.f;
   for (int tile = blockIdx.x; tile < bt.n_tiles; tile += gridDim.x) {
     for (int l = 0; l < L; ++l) {
@@ -1376,7 +1390,7 @@ __global__ void __launch_bounds__(TR_THREADS) tr_eval_kernel(const __grid_consta
     if (threadIdx.x < TR_R) {
       float q = 0.f;
       for (int d = 0; d < D; ++d) q += S.H1[d * TR_R + threadIdx.x] * S.H1[d * TR_R + threadIdx.x];
-      const float logp = -0.5f * q - (float)D * TR_HALF_LOG_2PI + S.ld[threadIdx.x] + cld;
+      const float logp = -0.5f * binv * q - blogz + S.ld[threadIdx.x] + cld;
       const int row = tile * TR_R + threadIdx.x;
       if (row < bt.B) {
         loss += S.c[threadIdx.x] * logp;
@@ -1398,5 +1412,206 @@ __global__ void tr_eval_final_kernel(const float* part, int G, float* d_loss) {
     d_loss[0] = -a / b;
   }
 }
+
+// ============================================================================ one-phase kernels
+// One phase per launch: what the CPU SIMT shim of tests/_hostcheck runs (blocks one after the
+// other cannot wait on each other) and the NB200_TR_CHAIN=1 debugging path of nb200_train_epoch.
+__global__ void __launch_bounds__(TR_THREADS) tr_fwd_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf, TrBatch bt, int l) {
+  TrSmem S = tr_carve(tr_smem_dyn, P, false);
+  tr_stage_itab(Bf, P, S);
+  tr_fwd_phase(P, Bf, bt, l, S);
+}
+__global__ void __launch_bounds__(TR_THREADS) tr_loss_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf, TrBatch bt) {
+  TrSmem S = tr_carve(tr_smem_dyn, P, false);
+  tr_stage_itab(Bf, P, S);
+  tr_loss_phase(P, Bf, bt, S);
+}
+__global__ void __launch_bounds__(TR_THREADS) tr_bwd_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf, TrBatch bt, int l) {
+  TrSmem S = tr_carve(tr_smem_dyn, P, true);
+  tr_stage_itab(Bf, P, S);
+  tr_bwd_phase(P, Bf, bt, l, S);
+}
+__global__ void __launch_bounds__(TR_THREADS) tr_eval_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf, TrBatch bt, float* out_part,
+                                                             float* d_logp) {
+  TrSmem S = tr_carve(tr_smem_dyn, P, false);
+  tr_stage_itab(Bf, P, S);
+  tr_eval_phase(P, Bf, bt, out_part, d_logp, S);
+}
+
+// ============================================================================ persistent kernel
+// A run of epochs of FlowModel.train (flowmodel/base.py:620-680) in ONE cooperative launch: every
+// optimisation step of every epoch (phases separated by grid barriers exactly where a grid-wide
+// reduction forces one: the BatchNorm statistics, the loss normaliser, the gradient partials, the
+// gradient norm, the updated parameters), the validation loss, and the loop control of the
+// reference -- best validation loss, best-weights snapshot, patience -- decided identically by
+// every CTA from the same reduced numbers.  The host reads TrCtl / hist once per launch.
+constexpr int TR_MAX_CHUNK = 64;  // epochs per launch
+
+struct TrCtl {
+  float best_val;   // best validation loss so far (+inf at the start of train())
+  int best_epoch;   // 1-based epoch that reached it (0: none)
+  int epochs_done;  // epochs finished so far (1-based index of the last one)
+  int stop;         // patience exceeded
+};
+
+struct TrRun {
+  const float* x;       // training rows [n_rows][D]
+  const float* w;       // their weights or NULL
+  const int64_t* perm;  // [n_epochs][n_rows] row order of every epoch, or NULL
+  int64_t n_rows;
+  int batch_size;
+  const float* xv;      // validation rows [n_val][D] (n_val == 0: none, the validation loss is NaN)
+  const float* wv;
+  int64_t n_val;
+  int n_epochs, epoch0, validate, patience;
+  int kind;             // TrOptim::kind
+  float beta1, beta2, eps, weight_decay, clip;
+  double beta1d, beta2d;
+  int64_t step0;        // optimiser steps taken before this launch
+  float lr[TR_MAX_CHUNK];  // learning rate of every epoch of the launch
+  float* m;
+  float* v;
+  float* step_info;     // [steps][2] = {loss, |grad|} or NULL
+  float* hist;          // [n_epochs][2] = {sum of the batch losses, validation loss} or NULL
+  float* loss_accum;    // scalar: += every batch loss (the caller zeroes it)
+  float* eval_part;     // [2 * G]
+  TrCtl* ctl;           // NULL: no loop control (single steps)
+  float* best_p;        // snapshot of theta_p / theta_b at the best epoch
+  float* best_b;
+  int n_b;              // floats in theta_b
+  unsigned* bar;        // grid barrier counter (zeroed by the host before the launch)
+  long long* trace;     // NULL, or [2 * cap]: (tag, globaltimer ns) of CTA 0 at every phase boundary
+  int trace_cap;
+};
+
+#ifndef NB200_SIMT_SHIM
+// Grid barrier over the co-resident CTAs of a cooperative launch.  `target` counts arrivals since
+// the launch; thread 0 publishes this CTA's writes (fence + release add), waits for everybody's,
+// and its trailing fence invalidates this SM's L1 before the CTA goes on reading.
+__device__ __forceinline__ void tr_grid_sync(unsigned* bar, unsigned& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+    } while ((int)(seen - target) < 0);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void tr_trace(const TrRun& R, int& slot, int tag) {
+  if (R.trace && blockIdx.x == 0 && threadIdx.x == 0 && slot < R.trace_cap) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    R.trace[2 * slot] = tag;
+    R.trace[2 * slot + 1] = t;
+    ++slot;
+  }
+}
+
+__global__ void __launch_bounds__(TR_THREADS) tr_train_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf,
+                                                              const __grid_constant__ TrRun R) {
+  TrSmem S = tr_carve(tr_smem_dyn, P, true);
+  tr_stage_itab(Bf, P, S);
+  const int L = P.L;
+  const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned target = 0;
+  int slot = 0;
+  tr_trace(R, slot, 0);
+  if (Bf.pmask) {
+    for (int i = blockIdx.x * TR_THREADS + threadIdx.x; i < P.n_params; i += gridDim.x * TR_THREADS)
+      Bf.theta_p[i] *= Bf.pmask[i];
+    tr_grid_sync(R.bar, target);
+  }
+  float best_val = R.ctl ? R.ctl->best_val : INFINITY;
+  int best_epoch = R.ctl ? R.ctl->best_epoch : 0;
+  int64_t step = R.step0;
+  int stop = 0, epoch = R.epoch0;
+  for (int e = 0; e < R.n_epochs && !stop; ++e) {
+    TrBatch bt;
+    bt.x = R.x;
+    bt.w = R.w;
+    bt.perm = R.perm ? R.perm + (size_t)e * R.n_rows : nullptr;
+    for (int64_t i0 = 0; i0 < R.n_rows; i0 += R.batch_size) {
+      bt.i0 = i0;
+      bt.B = (int)min((int64_t)R.batch_size, R.n_rows - i0);
+      bt.n_tiles = (bt.B + TR_R - 1) / TR_R;
+      for (int l = 0; l < L; ++l) {
+        tr_fwd_phase(P, Bf, bt, l, S);
+        // the next phase needs layer l's batch statistics (or, before the loss, the weight sum)
+        if (l == L - 1 || P.layer[l].bn_uw >= 0) tr_grid_sync(R.bar, target);
+        else __syncthreads();
+        tr_trace(R, slot, 100 + l);
+      }
+      tr_loss_phase(P, Bf, bt, S);
+      if (P.layer[L - 1].bn_uw >= 0) tr_grid_sync(R.bar, target);
+      else __syncthreads();
+      tr_trace(R, slot, 200);
+      for (int l = L - 1; l >= 0; --l) {
+        tr_bwd_phase(P, Bf, bt, l, S);
+        // BatchNorm backward of layer l - 1 needs its sums over the batch; REDUCE every partial
+        if (l == 0 || P.layer[l - 1].bn_uw >= 0) tr_grid_sync(R.bar, target);
+        else __syncthreads();
+        tr_trace(R, slot, 300 + l);
+      }
+      tr_reduce_phase<TR_THREADS>(P, Bf, tr_smem_dyn, S.red, blockIdx.x, gridDim.x, blockIdx.x, gridDim.x);
+      tr_grid_sync(R.bar, target);
+      tr_trace(R, slot, 400);
+      ++step;
+      TrOptim o;
+      o.kind = R.kind, o.lr = R.lr[e], o.beta1 = R.beta1, o.beta2 = R.beta2, o.eps = R.eps;
+      o.weight_decay = R.weight_decay, o.clip = R.clip;
+      o.bc1 = (float)(1.0 - pow(R.beta1d, (double)step));
+      o.bc2 = (float)(1.0 - pow(R.beta2d, (double)step));
+      tr_adam_phase<TR_THREADS>(Bf, P.n_params, o, R.m, R.v,
+                                R.step_info ? R.step_info + 2 * (step - R.step0 - 1) : nullptr, R.loss_accum,
+                                S.red);
+      tr_grid_sync(R.bar, target);
+      tr_trace(R, slot, 500);
+    }
+    ++epoch;
+    if (!R.ctl) continue;
+    // validation loss (eval mode: running statistics), the same number in every CTA
+    float val = NAN;
+    if (R.n_val > 0) {
+      TrBatch bv;
+      bv.x = R.xv, bv.w = R.wv, bv.perm = nullptr, bv.i0 = 0, bv.B = (int)R.n_val;
+      bv.n_tiles = (bv.B + TR_R - 1) / TR_R;
+      tr_eval_phase(P, Bf, bv, R.eval_part, nullptr, S);
+      tr_grid_sync(R.bar, target);
+      float a = 0.f, b = 0.f;
+      for (int g = 0; g < (int)gridDim.x; ++g) a += R.eval_part[2 * g], b += R.eval_part[2 * g + 1];
+      val = -a / b;
+    }
+    if (lead && R.hist) {
+      R.hist[2 * e] = R.loss_accum[0];
+      R.hist[2 * e + 1] = val;
+      R.loss_accum[0] = 0.f;
+    }
+    if (R.validate) {
+      if (val < best_val) {
+        best_val = val;
+        best_epoch = epoch;
+        for (int i = blockIdx.x * TR_THREADS + threadIdx.x; i < P.n_params; i += gridDim.x * TR_THREADS)
+          R.best_p[i] = Bf.theta_p[i];
+        for (int i = blockIdx.x * TR_THREADS + threadIdx.x; i < R.n_b; i += gridDim.x * TR_THREADS)
+          R.best_b[i] = Bf.theta_b[i];
+      }
+      if (epoch - best_epoch > R.patience) stop = 1;
+    }
+    tr_trace(R, slot, 600);
+  }
+  if (lead && R.ctl) {
+    R.ctl->best_val = best_val;
+    R.ctl->best_epoch = best_epoch;
+    R.ctl->epochs_done = epoch;
+    R.ctl->stop = stop;
+  }
+}
+#endif  // NB200_SIMT_SHIM
 
 }  // namespace nb200

@@ -140,6 +140,9 @@ class B200Flow(torch.nn.Module):
                 lib.nb200_flow_create(C.byref(self._handle), spec.D, spec.H, spec.activation),
                 "nb200_flow_create",
             )
+            if spec.base_var != 1.0:
+                _lib.check(lib.nb200_flow_set_base_variance(self._handle, float(spec.base_var)),
+                           "nb200_flow_set_base_variance")
 
     def __del__(self):
         try:
@@ -283,15 +286,18 @@ class B200Flow(torch.nn.Module):
         seed, offset = self._next_rng(n)
         with torch.cuda.device(self.device):
             _lib.check(
-                _lib.load().nb200_sample_latent(_ptr(z), n, self.spec.D, seed, offset, _stream()),
+                _lib.load().nb200_sample_latent(_ptr(z), n, self.spec.D, seed, offset,
+                                                float(np.sqrt(self.spec.base_var)), _stream()),
                 "nb200_sample_latent",
             )
         return z
 
     def base_distribution_log_prob(self, z, context=None):
-        """StandardNormal log-pdf (flows/base.py:248-257); tiny, torch on device."""
+        """Log-pdf of the base distribution N(0, var I) (flows/base.py:248-257,
+        flows/distributions.py:45-56; var = 1: StandardNormal); tiny, torch on device."""
         z = z.to(self.device)
-        return -0.5 * torch.sum(z * z, dim=-1) - 0.5 * self.spec.D * np.log(2 * np.pi)
+        var = self.spec.base_var
+        return -(0.5 / var) * torch.sum(z * z, dim=-1) - 0.5 * self.spec.D * np.log(2 * np.pi * var)
 
     def sample_and_log_prob(self, N, context=None):
         z = self.sample_latent_distribution(int(N))
@@ -422,23 +428,24 @@ class B200FlowModel:
         /root/reference/tests/test_flowmodel/test_flowmodel_base.py:145-183)."""
         if batch_size == 1:
             raise ValueError("Cannot use a batch size of 1!")
-        min_batch_size = int(min_fraction * batch_size)
-        final_batch_size = len(x) % batch_size
-        if final_batch_size and (final_batch_size < min_batch_size):
-            while True:
-                batch_size -= 1
-                final_batch_size = len(x) % batch_size
-                if batch_size < 2:
-                    raise RuntimeError("Could not find a valid batch size")
-                elif (final_batch_size == 0) or (final_batch_size >= min_batch_size):
-                    break
-                elif (batch_size <= min_batch_size) and final_batch_size > 1:
-                    logger.warning(
-                        f"Batch size is less than {min_batch_size} but valid. "
-                        f"Setting batch size to: {batch_size}"
-                    )
-                    break
-        return batch_size
+        n = len(x)
+        smallest_tail = int(min_fraction * batch_size)
+
+        def tail_ok(b):
+            tail = n % b
+            return tail == 0 or tail >= smallest_tail
+
+        if tail_ok(batch_size):
+            return batch_size
+        # shrink until the last batch is empty or large enough; below the threshold a tail of
+        # more than one row is accepted with a warning
+        for b in range(batch_size - 1, 1, -1):
+            if tail_ok(b):
+                return b
+            if b <= smallest_tail and n % b > 1:
+                logger.warning(f"Batch size is less than {smallest_tail} but valid. Setting batch size to: {b}")
+                return b
+        raise RuntimeError("Could not find a valid batch size")
 
     def prep_data(self, samples, val_size, batch_size, weights=None, use_dataloader=False, conditional=None):
         """flowmodel/base.py:238-352; tensors live on the GPU (no DataLoader)."""
@@ -512,6 +519,59 @@ class B200FlowModel:
         self._pending_train_loss = (total, n_batches)
         return None
 
+    def _train_on_device(self, fused, train_data, val_data, weighted, max_epochs, patience, validate, history,
+                         first_chunk=8):
+        """The epoch loop of flowmodel/base.py:620-662 in chunks of epochs, one cooperative launch
+        and one host synchronisation per chunk.  Every epoch's row order is ``torch.randperm``
+        from torch's CPU generator, drawn in the reference's order; when the device stops on
+        patience inside a chunk the generator is put back to where the reference's would be
+        (the permutations of epochs that never ran are not consumed).  Returns the last epoch;
+        appends to ``history``; the model holds the best weights when ``validate``."""
+        x_all, w_all = (train_data if weighted else (train_data, None))
+        x_val, w_val = (val_data if weighted else (val_data, None))
+        if x_val is not None and not len(x_val):
+            x_val = w_val = None
+        n_rows = int(x_all.shape[0])
+        n_batches = -(-n_rows // self._batch_size)
+        annealing = self.training_config["annealing"]
+        from .trainer import cosine_annealing_lr
+
+        lr_now = float(self._optimiser.param_groups[0]["lr"])
+        clip = self.training_config["clip_grad_norm"]
+        self.model.train()
+        fused.begin_run()
+        epoch, chunk = 0, int(first_chunk)
+        while epoch < max_epochs:
+            n = min(chunk, max_epochs - epoch, fused.MAX_CHUNK)
+            chunk = min(2 * chunk, fused.MAX_CHUNK)
+            perms, states = [], []
+            for _ in range(n):
+                perms.append(torch.randperm(n_rows))
+                states.append(torch.get_rng_state())
+            perms = torch.stack(perms).to(self.device, non_blocking=True)
+            lrs = [cosine_annealing_lr(self._base_lr, epoch + k, self._t_max) if annealing else lr_now
+                   for k in range(n)]
+            done, stop, _, hist = fused.run(x_all, w_all, perms, self._batch_size, x_val, w_val, self._optimiser,
+                                            clip, lrs, epoch, validate, patience)
+            n_run = done - epoch
+            history["loss"].extend((hist[:, 0].astype(np.float64) / n_batches).tolist())
+            history["val_loss"].extend(hist[:, 1].astype(np.float64).tolist())
+            if n_run < n:
+                torch.set_rng_state(states[n_run - 1])
+            for _ in range(n_run):
+                self.end_iteration()
+            epoch = done
+            if annealing:
+                self._epochs_done = epoch
+                for g in self._optimiser.param_groups:
+                    g["lr"] = cosine_annealing_lr(self._base_lr, epoch, self._t_max)
+            if stop:
+                logger.debug(f"Epoch {epoch}: Reached patience")
+                break
+        if validate:
+            fused.restore_best()
+        return epoch
+
     def _validate(self, val_data, is_dataloader=False, weighted=False, is_conditional=False):
         """flowmodel/base.py:454-523: eval mode (running statistics); returns the
         device scalar (read back together with the training loss)."""
@@ -570,26 +630,36 @@ class B200FlowModel:
         history = dict(loss=[], val_loss=[])
         current_weights_file = os.path.join(output, "model.pt")
         epoch = 0
-        for epoch in range(1, max_epochs + 1):
-            self._train(train_data, noise_scale=noise_scale, weighted=weighted)
-            val_dev = self._validate(val_data, weighted=weighted)
-            # the single host synchronisation of the epoch: both losses in one read
-            total, n_batches = self._pending_train_loss
-            both = self._fused._loss.cpu().numpy()
-            loss = float(both[0]) / n_batches
-            val_loss = float(both[1]) if val_dev is not None else np.nan
-            history["loss"].append(loss)
-            history["val_loss"].append(val_loss)
-            if validate and (val_loss < best_val_loss):
-                best_epoch = epoch
-                best_val_loss = val_loss
-                best = (model.theta_p.detach().clone(), model.theta_b.clone())
-            if validate and (epoch - best_epoch > patience):
-                logger.debug(f"Epoch {epoch}: Reached patience")
-                break
+        fused = self._trainer()
+        on_device = (fused._kernel_optimiser(self._optimiser) is not None and not noise_scale
+                     and getattr(self, "_device_loop", True))
+        if on_device:
+            # the whole loop on the device: optimisation steps, validation loss, best-weights
+            # snapshot and patience inside one persistent kernel per chunk of epochs
+            epoch = self._train_on_device(fused, train_data, val_data, weighted, max_epochs, patience, validate,
+                                          history)
+        else:
+            # input noise / an optimiser the kernels do not implement: epoch by epoch from the host
+            for epoch in range(1, max_epochs + 1):
+                self._train(train_data, noise_scale=noise_scale, weighted=weighted)
+                val_dev = self._validate(val_data, weighted=weighted)
+                # the single host synchronisation of the epoch: both losses in one read
+                total, n_batches = self._pending_train_loss
+                both = self._fused._loss.cpu().numpy()
+                loss = float(both[0]) / n_batches
+                val_loss = float(both[1]) if val_dev is not None else np.nan
+                history["loss"].append(loss)
+                history["val_loss"].append(val_loss)
+                if validate and (val_loss < best_val_loss):
+                    best_epoch = epoch
+                    best_val_loss = val_loss
+                    best = (model.theta_p.detach().clone(), model.theta_b.clone())
+                if validate and (epoch - best_epoch > patience):
+                    logger.debug(f"Epoch {epoch}: Reached patience")
+                    break
         model.train()
         model.eval()
-        if validate:
+        if validate and not on_device:
             with torch.no_grad():
                 model.theta_p.copy_(best[0])
                 model.theta_b.copy_(best[1])

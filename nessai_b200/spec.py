@@ -136,12 +136,27 @@ class FlowSpec:
                 "nessai_b200: custom flow classes (flow_config['flow']) are not "
                 "supported; use ftype='realnvp' or 'nsf'"
             )
-        if cfg.pop("distribution", None) is not None:
-            raise NotImplementedError(
-                "nessai_b200: only the default StandardNormal base distribution "
-                "is implemented"
-            )
-        cfg.pop("distribution_kwargs", None)
+        # base distribution (/root/reference/src/nessai/flows/utils.py:35-102): None is nflows'
+        # StandardNormal; "mvn" / "normal" is nessai's MultivariateNormal, N(0, var I)
+        # (flows/distributions.py:17-73), var from distribution_kwargs
+        dist = cfg.pop("distribution", None)
+        dist_kwargs = dict(cfg.pop("distribution_kwargs", None) or {})
+        self.base_var = 1.0
+        if dist is not None:
+            name = dist.lower() if isinstance(dist, str) else getattr(dist, "__name__", str(dist))
+            if name in ("mvn", "normal", "MultivariateNormal"):
+                self.base_var = float(dist_kwargs.pop("var", 1))
+                if not (self.base_var > 0.0 and np.isfinite(self.base_var)):
+                    raise ValueError(f"MultivariateNormal needs a positive finite variance, got {self.base_var}")
+                if dist_kwargs:
+                    raise TypeError(f"MultivariateNormal got unexpected arguments: {sorted(dist_kwargs)}")
+            elif isinstance(dist, str) and name not in ("lars", "resampled", "uniform"):
+                raise ValueError(f"Unknown distribution: {dist}")
+            else:
+                raise NotImplementedError(
+                    f"nessai_b200: base distribution {dist!r} is not implemented "
+                    "(StandardNormal and MultivariateNormal are)"
+                )
         n_inputs = cfg.pop("n_inputs")
         if not isinstance(n_inputs, (int, np.integer)) or isinstance(n_inputs, bool):
             raise TypeError("Number of inputs (n_inputs) must be an int")

@@ -21,7 +21,7 @@ TR_MAXBUF = 12
 TR_MAXLIN = 12
 TR_MAXD = 64
 TR_LAYER_INTS = 20 + 2 * TR_MAXBUF + 8 * TR_MAXLIN
-TR_PLAN_INTS = 16 + TR_MAXL * TR_LAYER_INTS
+TR_PLAN_INTS = 20 + TR_MAXL * TR_LAYER_INTS
 
 
 class TrainPlanUnsupported(NotImplementedError):
@@ -129,7 +129,8 @@ def build_train_plan(spec: FlowSpec, ints: dict) -> Tuple[np.ndarray, np.ndarray
         ws_off += rec
         max_dim = max(max_dim, max(buf_dim))
         vals_floats = max(vals_floats, sum(buf_dim))
-    head = np.zeros(16, dtype=np.int64)
+    head = np.zeros(20, dtype=np.int64)
+    head[16] = int(np.float32(getattr(spec, "base_var", 1.0)).view(np.int32))
     head[:16] = [
         D, L, spec.activation, 2 if spec.ftype == "maf" else int(spec.volume_preserving),
         spec.n_params, n_part, ws_off, max_dim,

@@ -139,6 +139,72 @@ class FusedTrainer:
                     self.step += 1
         return loss_sum
 
+    # ------------------------------------------------------------ epoch runs
+    MAX_CHUNK = 64  # TR_MAX_CHUNK of csrc/train.cuh
+
+    def begin_run(self):
+        """Loop-control block and best-weights snapshot of one ``train()`` call
+        (flowmodel/base.py:608-618: ``best_val_loss = inf``, ``best_epoch = 0``, initial weights)."""
+        model = self.model
+        ctl = np.zeros(4, dtype=np.int32)
+        ctl[:1].view(np.float32)[0] = np.inf
+        self._ctl = torch.from_numpy(ctl).to(self.device)
+        self._best_p = model.theta_p.detach().clone()
+        self._best_b = model.theta_b.detach().clone()
+        n = 2 * self.MAX_CHUNK + 4
+        if getattr(self, "_run_dev", None) is None:
+            self._run_dev = torch.zeros(n, device=self.device, dtype=torch.float32)
+            self._run_host = torch.zeros(n, dtype=torch.float32, pin_memory=True)
+
+    def run(self, x, w, perms, batch_size, xv, wv, optimiser, clip, lrs, epoch0, validate, patience):
+        """Up to ``MAX_CHUNK`` epochs -- optimisation steps, validation loss, best-weights
+        snapshot and patience -- in one cooperative launch (``nb200_train_run``), then ONE
+        read-back.  ``perms``: ``(n_epochs, n_rows)`` int64 device tensor, ``lrs``: the learning
+        rate of every epoch.  Returns ``(epochs_done, stop, best_epoch, hist)`` with
+        ``epochs_done`` the total number of epochs finished and ``hist`` the float32
+        ``(n_run, 2)`` array of {sum of batch losses, validation loss} of the epochs that ran."""
+        model = self.model
+        self._bind(optimiser)
+        cfg = self._kernel_optimiser(optimiser)
+        if cfg is None:
+            raise RuntimeError("optimiser not implemented by the training kernels")
+        kind, _, b1, b2, eps, wd = cfg
+        n_epochs, n_rows = int(perms.shape[0]), int(x.shape[0])
+        assert 1 <= n_epochs <= self.MAX_CHUNK and perms.shape[1] == n_rows and perms.dtype == torch.int64
+        lrs = np.ascontiguousarray(lrs, dtype=np.float64)
+        assert lrs.shape == (n_epochs,)
+        n_val = 0 if xv is None else int(xv.shape[0])
+        hist, ctl = self._run_dev[: 2 * self.MAX_CHUNK], self._ctl
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        with torch.cuda.device(self.device):
+            _lib.check(
+                _lib.load().nb200_train_run(
+                    self._handle, _ptr(model.theta_p), _ptr(model.theta_b), int(model.theta_b.numel()),
+                    _ptr(self.m), _ptr(self.v), _ptr(x), _ptr(w), _ptr(perms), n_rows, int(batch_size),
+                    _ptr(xv) if n_val else None, _ptr(wv) if n_val else None, n_val, n_epochs, int(epoch0),
+                    int(bool(validate)), int(patience), kind, lrs.ctypes.data_as(C.c_void_p), b1, b2, eps, wd,
+                    float(clip) if clip else 0.0, self.step, _ptr(hist), _ptr(ctl), _ptr(self._best_p),
+                    _ptr(self._best_b), st,
+                ),
+                "nb200_train_run",
+            )
+            # the single host synchronisation of the run: history + loop control in one read
+            self._run_dev[2 * self.MAX_CHUNK :].copy_(ctl.view(torch.float32))
+            self._run_host.copy_(self._run_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        out = self._run_host.numpy()
+        c = out[2 * self.MAX_CHUNK :].view(np.int32)
+        epochs_done, stop, best_epoch = int(c[2]), bool(c[3]), int(c[1])
+        n_run = epochs_done - int(epoch0)
+        self.step += n_run * ((n_rows + batch_size - 1) // batch_size)
+        return epochs_done, stop, best_epoch, out[: 2 * n_run].reshape(n_run, 2).copy()
+
+    def restore_best(self):
+        """Best-epoch weights back into the model (flowmodel/base.py:664-667)."""
+        with torch.no_grad():
+            self.model.theta_p.copy_(self._best_p)
+            self.model.theta_b.copy_(self._best_b)
+
     def _grad_step(self, x_all, w_all, perm, i0, n_b, clip, loss_sum, info, st):
         """Loss + clipped gradient of the batch ``perm[i0 : i0 + n_b]`` (no update)."""
         if perm is not None:

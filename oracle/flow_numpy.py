@@ -63,7 +63,11 @@ class NumpyFlow:
         num_bins=8,
         tail_bound=5.0,
         hidden_features=None,
+        base_var=1.0,
     ):
+        # base distribution N(0, base_var I): nessai's MultivariateNormal
+        # (/root/reference/src/nessai/flows/distributions.py:17-73); 1 = nflows' StandardNormal
+        self.base_var = float(base_var)
         self.sd = _sd64(state_dict)
         self.ftype = ftype
         self.net = net
@@ -317,10 +321,10 @@ class NumpyFlow:
             ld = ld + l
         return z, ld
 
-    @staticmethod
-    def base_log_prob(z):
+    def base_log_prob(self, z):
         D = z.shape[1]
-        return -0.5 * np.sum(z**2, axis=1) - 0.5 * D * np.log(2 * np.pi)
+        var = getattr(self, "base_var", 1.0)  # (also callable as NumpyFlow.base_log_prob(None, z))
+        return -(0.5 / var) * np.sum(z**2, axis=1) - 0.5 * D * np.log(2 * np.pi * var)
 
     def forward_and_log_prob(self, x):
         z, ld = self.forward(x)

@@ -295,7 +295,8 @@ class TrainStepOracle:
                     rv += BN_MOMENTUM * var
             saved.append(S)
         z = h
-        logp = -0.5 * np.sum(z * z, axis=1) - 0.5 * D * math.log(2 * math.pi) + ld_rows + ld_const
+        bvar = float(getattr(sp, "base_var", 1.0))  # N(0, var I) base (flows/distributions.py:17-73)
+        logp = -(0.5 / bvar) * np.sum(z * z, axis=1) - 0.5 * D * math.log(2 * math.pi * bvar) + ld_rows + ld_const
         loss = -np.sum(c * logp)
 
         # ------------------------------------------------------------ backward
@@ -305,7 +306,7 @@ class TrainStepOracle:
             e = sp.by_key[key]
             g[e.offset : e.offset + e.size] += np.asarray(val).ravel()
 
-        dh = c[:, None] * z  # d loss / d z
+        dh = c[:, None] * z / bvar  # d loss / d z
         g_ld = -1.0  # sum over rows of d loss / d ld_row (= -sum c)
         for ls, S in zip(reversed(sp.layers), reversed(saved)):
             if ls.bn_prefix is not None:

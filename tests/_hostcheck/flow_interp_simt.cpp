@@ -20,7 +20,7 @@ alignas(16) float g_smem[64 * 1024];  // 256 KB >= the 226 KB the launcher allow
 
 template <int ACT>
 void apply_kernel(nb200::FlowProgramDev P, const float* in, float* out, float* out_logj, float* out_lp, int64_t n,
-                  int lp_mode) {
+                  int lp_mode, float base_inv_var, float base_log_z) {
   using namespace nb200;
   float* Ws;
   float* bufs[4];
@@ -47,8 +47,8 @@ void apply_kernel(nb200::FlowProgramDev P, const float* in, float* out, float* o
     if (valid) {
       if (out_logj) out_logj[row] = ld;
       if (out_lp) {
-        const float c = 0.5f * P.D * LOG_2PI;
-        out_lp[row] = (lp_mode == 1) ? (-0.5f * ss_in - c) - ld : (-0.5f * ss_out - c) + ld;
+        const float c = base_log_z, hv = 0.5f * base_inv_var;
+        out_lp[row] = (lp_mode == 1) ? (-hv * ss_in - c) - ld : (-hv * ss_out - c) + ld;
       }
     }
   }
@@ -58,8 +58,12 @@ void apply_kernel(nb200::FlowProgramDev P, const float* in, float* out, float* o
 // ops: int32[n_ops][16] and blob: float32[n_blob] exactly as nb200_flow_set_program receives them.
 extern "C" int simt_flow_apply(int grid, const int32_t* ops, int n_ops, const float* blob, int D, int H,
                                int activation, int final_buf, double const_logdet, const float* in, float* out,
-                               float* logj, float* lp, int64_t n, int lp_mode) {
+                               float* logj, float* lp, int64_t n, int lp_mode, double base_var) {
   using namespace nb200;
+  // as launch_apply of nessai_b200.cu forms the base-distribution constants
+  const float base_inv_var = (float)(1.0 / base_var);
+  const float base_log_z = (float)(0.5 * D * std::log(2.0 * M_PI * base_var));
+  (void)LOG_2PI;
   FlowProgramDev P;
   P.ops = reinterpret_cast<const FlowOp*>(ops);
   P.blob = blob;
@@ -76,9 +80,9 @@ extern "C" int simt_flow_apply(int grid, const int32_t* ops, int n_ops, const fl
   for (int bs : {128, 64, 32})
     if (!BS && interp_smem_bytes(P, bs) <= 226 * 1024) BS = bs;
   if (!BS || interp_smem_bytes(P, BS) > sizeof(g_smem)) return 5;
-  if (activation == ACT_RELU) simt_launch(apply_kernel<ACT_RELU>, (unsigned)grid, (unsigned)BS, P, in, out, logj, lp, n, lp_mode);
-  else if (activation == ACT_TANH) simt_launch(apply_kernel<ACT_TANH>, (unsigned)grid, (unsigned)BS, P, in, out, logj, lp, n, lp_mode);
-  else simt_launch(apply_kernel<ACT_SILU>, (unsigned)grid, (unsigned)BS, P, in, out, logj, lp, n, lp_mode);
+  if (activation == ACT_RELU) simt_launch(apply_kernel<ACT_RELU>, (unsigned)grid, (unsigned)BS, P, in, out, logj, lp, n, lp_mode, base_inv_var, base_log_z);
+  else if (activation == ACT_TANH) simt_launch(apply_kernel<ACT_TANH>, (unsigned)grid, (unsigned)BS, P, in, out, logj, lp, n, lp_mode, base_inv_var, base_log_z);
+  else simt_launch(apply_kernel<ACT_SILU>, (unsigned)grid, (unsigned)BS, P, in, out, logj, lp, n, lp_mode, base_inv_var, base_log_z);
   return 0;
 }
 

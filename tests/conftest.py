@@ -17,6 +17,7 @@ GOLDEN_NAMES = [
     "c1_realnvp_2d",
     "d6_nsf",
     "d8_maf",
+    "d5_realnvp_mvn",
 ]
 
 

@@ -72,7 +72,10 @@ def make(name, flow_config, data, n_eval, epochs, tmp):
     model.eval()
     state = {k: v.detach().clone() for k, v in model.state_dict().items()}
     g = torch.Generator().manual_seed(SEED + 1)
+    base_var = float((flow_config.get("distribution_kwargs") or {}).get("var", 1.0))
     z = torch.randn(n_eval, xp.shape[1], generator=g)
+    if base_var != 1.0:
+        z = z * float(np.sqrt(base_var))
     x = torch.from_numpy(xp[:n_eval]).float()
     with torch.inference_mode():
         fwd_z, fwd_lp = model.forward_and_log_prob(x)
@@ -87,6 +90,7 @@ def make(name, flow_config, data, n_eval, epochs, tmp):
         num_bins=flow_config.get("num_bins", 8),
         tail_bound=flow_config.get("tail_bound", 5.0),
         hidden_features=flow_config["n_neurons"],
+        base_var=base_var,
     )
     nf = NumpyFlow(state, **kw)
     z64, lj64 = nf.forward(x.numpy())
@@ -163,6 +167,13 @@ def main():
              linear_transform=None, batch_norm_between_layers=False,
              use_volume_preserving=True, activation="swish"),
         live5[:, :4], 100, 30, tmp,
+    )
+    # MultivariateNormal base distribution, N(0, 2.5 I) (flows/distributions.py:17-73)
+    make(
+        "d5_realnvp_mvn",
+        dict(n_inputs=5, n_neurons=10, n_blocks=3, n_layers=1, ftype="realnvp", net="mlp",
+             distribution="mvn", distribution_kwargs=dict(var=2.5)),
+        live5, 257, 30, tmp,
     )
     # config 1: 2-D, 2 coupling layers, all defaults (resnet, LU, BN, n_neurons=4)
     make(

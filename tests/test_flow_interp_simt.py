@@ -35,7 +35,7 @@ def simt_interp(tmp_path_factory):
     lib = C.CDLL(str(out))
     lib.simt_flow_apply.restype = C.c_int
     lib.simt_flow_apply.argtypes = ([C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_double]
-                                    + [C.c_void_p] * 4 + [C.c_int64, C.c_int])
+                                    + [C.c_void_p] * 4 + [C.c_int64, C.c_int, C.c_double])
     return simt_or_skip(lib, 128)
 
 
@@ -49,7 +49,7 @@ def run(lib, spec, prog, rows, lp_mode, grid=2):
     lp = np.full(n, np.nan, dtype=np.float32)
     rc = lib.simt_flow_apply(grid, ops.ctypes.data, int(ops.shape[0]), blob.ctypes.data, spec.D, spec.H, spec.activation,
                              int(prog.final_buf), float(prog.const_logdet), x.ctypes.data, out.ctypes.data,
-                             logj.ctypes.data, lp.ctypes.data, n, lp_mode)
+                             logj.ctypes.data, lp.ctypes.data, n, lp_mode, float(spec.base_var))
     assert rc == 0
     return out.astype(np.float64), logj.astype(np.float64), lp.astype(np.float64)
 

@@ -13,7 +13,7 @@ from conftest import load_golden
 pytestmark = pytest.mark.gpu
 
 CASES = ["c2_realnvp_mlp", "c2_realnvp_resnet", "d5_realnvp_perm_tanh", "d4_realnvp_additive_silu", "c1_realnvp_2d",
-         "d6_nsf", "d8_maf"]
+         "d6_nsf", "d8_maf", "d5_realnvp_mvn"]
 
 
 def make_model(cfg, sd, tmp_path, **training):
@@ -169,3 +169,42 @@ def test_gradient_matches_device_autograd(name, tmp_path):
     assert abs(float(loss) - float(loss_t)) < 2e-5 * abs(float(loss_t))
     ref = tp.grad.cpu().numpy()
     assert rel_err(grad.cpu().numpy(), ref) < 1e-4
+
+
+@pytest.mark.parametrize("name,patience,annealing,weighted", [
+    ("c2_realnvp_mlp", 3, False, False),
+    ("c2_realnvp_resnet", 2, True, False),
+    ("d6_nsf", 2, False, True),
+    ("d8_maf", 50, False, False),
+])
+def test_device_epoch_loop_equals_host_epoch_loop(name, patience, annealing, weighted, tmp_path):
+    """``FlowModel.train`` with the epoch loop on the device (persistent kernel: steps, validation
+    loss, best-weights snapshot, patience -- flowmodel/base.py:620-667) against the same loop driven
+    epoch by epoch from the host: same history, same stopping epoch, same final weights, and torch's
+    CPU generator left where the reference's loop would leave it (one ``randperm`` per epoch run)."""
+    from nessai_b200.flowmodel import B200FlowModel
+
+    g, cfg, sd = load_golden(name)
+    x = np.asarray(g["train_data"], dtype=np.float64)
+    w = np.random.default_rng(5).uniform(0.5, 1.5, size=len(x)) if weighted else None
+    out = {}
+    for device_loop in (True, False):
+        torch.manual_seed(1234)
+        fm = B200FlowModel(
+            flow_config=cfg, output=str(tmp_path / str(device_loop)), rng=np.random.default_rng(7),
+            training_config=dict(max_epochs=40, patience=patience, batch_size=700, lr=0.01, annealing=annealing))
+        fm.initialise()
+        fm._device_loop = device_loop
+        hist = fm.train(x, weights=w, plot=False)
+        out[device_loop] = (hist, fm.model.theta_numpy().copy(), fm.model.theta_b.cpu().numpy().copy(),
+                            torch.get_rng_state().clone(), float(fm._optimiser.param_groups[0]["lr"]))
+    (h1, p1, b1, r1, lr1), (h0, p0, b0, r0, lr0) = out[True], out[False]
+    assert len(h1["loss"]) == len(h0["loss"]) and len(h1["loss"]) >= 2
+    if patience < 10:
+        assert len(h1["loss"]) < 40  # the run stopped on patience, inside a chunk of epochs
+    np.testing.assert_allclose(h1["loss"], h0["loss"], rtol=1e-6)
+    np.testing.assert_allclose(h1["val_loss"], h0["val_loss"], rtol=1e-6)
+    np.testing.assert_allclose(p1, p0, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(b1, b0, rtol=1e-5, atol=1e-7)
+    assert torch.equal(r1, r0)
+    assert lr1 == pytest.approx(lr0, rel=1e-12)

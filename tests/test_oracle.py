@@ -26,6 +26,7 @@ def numpy_flow(cfg, sd):
         num_bins=cfg.get("num_bins", 8),
         tail_bound=cfg.get("tail_bound", 5.0),
         hidden_features=cfg["n_neurons"],
+        base_var=(cfg.get("distribution_kwargs") or {}).get("var", 1.0),
     )
 
 

@@ -49,7 +49,8 @@ def test_program_fp32_within_stated_tolerance(golden):
     sp, theta, ints = load_spec(cfg, sd)
     ff = sp.fold(theta, ints)
     z, lj = run_program(ff.program(False), g["x"], np.float32)
-    lp = -0.5 * (z.astype(np.float64) ** 2).sum(1) - 0.5 * sp.D * np.log(2 * np.pi) + lj
+    var = sp.base_var  # N(0, var I) base distribution (1 except for the "mvn" fixture)
+    lp = -(0.5 / var) * (z.astype(np.float64) ** 2).sum(1) - 0.5 * sp.D * np.log(2 * np.pi * var) + lj
     np.testing.assert_allclose(lp, g["fwd_logprob"], rtol=1e-4, atol=1e-4)
 
 
@@ -147,7 +148,7 @@ def test_train_plan_packs_every_golden_realnvp():
         D = spec.D
         ntri = D * (D - 1) // 2
         for l in range(spec.L):
-            row = plan[16 + l * TR_LAYER_INTS : 16 + (l + 1) * TR_LAYER_INTS]
+            row = plan[20 + l * TR_LAYER_INTS : 20 + (l + 1) * TR_LAYER_INTS]
             if row[1] >= 0:
                 covered[row[2] : row[2] + ntri] += 1
                 covered[row[3] : row[3] + ntri] += 1

@@ -15,7 +15,7 @@ from nessai_b200.spec import FlowSpec
 from oracle.train_numpy import TrainStepOracle
 
 CASES = ["c2_realnvp_mlp", "c2_realnvp_resnet", "d5_realnvp_perm_tanh", "d4_realnvp_additive_silu", "c1_realnvp_2d",
-         "d6_nsf", "d8_maf"]
+         "d6_nsf", "d8_maf", "d5_realnvp_mvn"]
 
 
 def _reference_model(cfg, sd):

@@ -83,7 +83,8 @@ def rel_err(a, b):
 @pytest.mark.parametrize("name,n_rows,weighted", [("c2_realnvp_mlp", 70, False), ("c2_realnvp_resnet", 19, True),
                                                   ("d5_realnvp_perm_tanh", 100, False),
                                                   ("d4_realnvp_additive_silu", 64, True), ("c1_realnvp_2d", 33, False),
-                                                  ("d6_nsf", 50, False), ("d8_maf", 21, True)])
+                                                  ("d6_nsf", 50, False), ("d8_maf", 21, True),
+                                                  ("d5_realnvp_mvn", 40, False)])
 def test_cuda_training_step_matches_oracle(simt_train, name, n_rows, weighted):
     from oracle.train_numpy import TrainStepOracle
 
@@ -150,7 +151,7 @@ def test_cuda_clip_and_optimiser_steps_match_oracle(simt_train, opt):
     np.testing.assert_allclose(cur[P:], theta64[P:], **tol)
 
 
-@pytest.mark.parametrize("name", ["c2_realnvp_resnet", "d5_realnvp_perm_tanh", "d6_nsf", "d8_maf"])
+@pytest.mark.parametrize("name", ["c2_realnvp_resnet", "d5_realnvp_perm_tanh", "d6_nsf", "d8_maf", "d5_realnvp_mvn"])
 def test_cuda_validation_loss_matches_reference_golden(simt_train, name):
     """tr_eval_kernel (the validation loss of FlowModel._validate: eval mode, running statistics,
     straight from the UNFOLDED parameters) against the reference's golden log-probabilities."""
