@@ -648,7 +648,7 @@ struct nb200_trainer {
   long long* trace = nullptr;    // NB200_TR_TRACE: phase timeline of CTA 0
   size_t smem_fwd = 0, smem_bwd = 0;
 };
-constexpr int TR_TRACE_CAP = 4096;
+constexpr int TR_TRACE_CAP = 16384;
 
 static void trainer_free_rows(nb200_trainer* t) {
   cudaFree(t->ws), cudaFree(t->dout0), cudaFree(t->dout1), cudaFree(t->ldrow), cudaFree(t->crow);
@@ -705,18 +705,6 @@ extern "C" int nb200_trainer_create(nb200_trainer** out, const int32_t* h_plan, 
     delete t;
     return fail(5, "flow too large for the training kernels (%zu KB shared memory)", t->smem_bwd / 1024);
   }
-  {
-    // the REDUCE phase of the persistent kernel borrows the first 3 D^2 floats of the map (LU
-    // chain rule) while S.red and the index tables stay live: they must lie behind it
-    const size_t red_off = tr_smem_floats(P.D, P.vals_floats, P.max_in, P.wmax, 0, true) -
-                           (size_t)TR_MAXG * (2 * P.D + 1) - 3 * TR_THREADS;
-    bool any_lu = false;
-    for (int l = 0; l < P.L; ++l) any_lu |= P.layer[l].lu_bias >= 0;
-    if (any_lu && red_off < (size_t)3 * P.D * P.D) {
-      delete t;
-      return fail(5, "training kernels: shared-memory map too small for the LU gradient (D=%d)", P.D);
-    }
-  }
   const int G = TR_MAXG;
 #define TR_ALLOC(ptr, count) CUDA_OK(cudaMalloc(&(ptr), sizeof(*(ptr)) * (size_t)(count)))
   TR_ALLOC(t->d_plan, 1);
@@ -728,19 +716,21 @@ extern "C" int nb200_trainer_create(nb200_trainer** out, const int32_t* h_plan, 
   TR_ALLOC(t->s_part1, (size_t)G * 2 * P.D);
   TR_ALLOC(t->wsum_part, G);
   TR_ALLOC(t->loss_part, G);
-  TR_ALLOC(t->part, (size_t)G * P.n_part);
-  TR_ALLOC(t->grad, P.n_params);
-  TR_ALLOC(t->gn_part, TR_REDUCE_MAXBLOCKS);
+  const size_t part_stride = ((size_t)P.n_part + 3) & ~(size_t)3, n_grad = ((size_t)P.n_params + 3) & ~(size_t)3;
+  TR_ALLOC(t->part, (size_t)G * part_stride);
+  TR_ALLOC(t->grad, n_grad);
+  TR_ALLOC(t->gn_part, G);
+  CUDA_OK(cudaMemset(t->part, 0, sizeof(float) * G * part_stride));
   TR_ALLOC(t->eval_part, 2 * 2 * prop.multiProcessorCount);
   TR_ALLOC(t->stat_n, G);
   TR_ALLOC(t->run_scalars, 4);
   TR_ALLOC(t->bar, 4);
   CUDA_OK(cudaMemset(t->run_scalars, 0, 4 * sizeof(float)));
-  if (getenv("NB200_TR_TRACE")) TR_ALLOC(t->trace, 2 * TR_TRACE_CAP);
+  if (getenv("NB200_TR_TRACE")) TR_ALLOC(t->trace, 2 * TR_TRACE_CAP + 1);
   CUDA_OK(cudaMemcpy(t->d_plan, &t->h_plan, sizeof(TrPlan), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(t->d_itab, h_itab, sizeof(int) * n_itab, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(t->d_reduce, h_reduce_idx, sizeof(int) * n_reduce, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemset(t->grad, 0, sizeof(float) * P.n_params));
+  CUDA_OK(cudaMemset(t->grad, 0, sizeof(float) * n_grad));
   *out = t;
   return 0;
 }
@@ -778,11 +768,12 @@ static TrBuffers trainer_buffers(nb200_trainer* t, float* theta_p, float* theta_
   B.wsum_part = t->wsum_part;
   B.loss_part = t->loss_part;
   B.part = t->part;
+  B.part_stride = (t->h_plan.n_part + 3) & ~3;
   B.grad = t->grad;
   B.gn_part = t->gn_part;
   B.G = G;
   B.pmask = t->pmask;
-  B.n_reduce_blocks = std::min(TR_REDUCE_MAXBLOCKS, t->h_plan.L + std::max(1, (t->h_plan.n_reduce * 8 + TR_RED_THREADS - 1) / TR_RED_THREADS));
+  B.n_reduce_blocks = G;  // the REDUCE phase runs on the row kernels' grid
   return B;
 }
 
@@ -815,13 +806,12 @@ static int trainer_launch_run(nb200_trainer* t, float* d_theta_p, float* d_theta
   if (R.n_val > 0) max_tiles = std::max<int>(max_tiles, (int)((R.n_val + TR_R - 1) / TR_R));
   const int G = std::max(1, std::min(max_tiles, std::min(TR_MAXG, t->num_sms)));
   TrBuffers B = trainer_buffers(t, d_theta_p, d_theta_b, G);
-  B.n_reduce_blocks = G;
   R.eval_part = t->eval_part;
   R.bar = t->bar;
-  R.trace = t->trace;
-  R.trace_cap = t->trace ? TR_TRACE_CAP : 0;
+  B.trace = t->trace;
+  B.trace_cap = t->trace ? TR_TRACE_CAP : 0;
   CUDA_OK(cudaMemsetAsync(t->bar, 0, sizeof(unsigned), st));
-  if (t->trace) CUDA_OK(cudaMemsetAsync(t->trace, 0, sizeof(long long) * 2 * TR_TRACE_CAP, st));
+  if (t->trace) CUDA_OK(cudaMemsetAsync(t->trace, 0, sizeof(long long) * (2 * TR_TRACE_CAP + 1), st));
   void* args[] = {(void*)&t->h_plan, (void*)&B, (void*)&R};
   CUDA_OK(cudaLaunchCooperativeKernel((const void*)tr_train_kernel, dim3(G), dim3(TR_THREADS), args, t->smem_bwd, st));
   g_launches += 1;
@@ -874,6 +864,7 @@ extern "C" int nb200_train_epoch(nb200_trainer* t, float* d_theta_p, float* d_th
     R.n_epochs = 1, R.kind = opt_kind;
     R.beta1 = (float)beta1, R.beta2 = (float)beta2, R.eps = (float)eps, R.weight_decay = (float)weight_decay;
     R.clip = (float)clip, R.beta1d = beta1, R.beta2d = beta2, R.step0 = step0, R.lr[0] = (float)lr;
+    R.b1pow0 = std::pow(beta1, (double)step0), R.b2pow0 = std::pow(beta2, (double)step0);
     R.m = d_m, R.v = d_v, R.step_info = d_step_info, R.loss_accum = d_loss_sum;
     return trainer_launch_run(t, d_theta_p, d_theta_b, R, st);
   }
@@ -902,7 +893,7 @@ extern "C" int nb200_train_epoch(nb200_trainer* t, float* d_theta_p, float* d_th
     for (int l = 0; l < P.L; ++l) tr_fwd_kernel<<<G, TR_THREADS, t->smem_fwd, st>>>(P, B, bt, l);
     tr_loss_kernel<<<G, TR_THREADS, t->smem_fwd, st>>>(P, B, bt);
     for (int l = P.L - 1; l >= 0; --l) tr_bwd_kernel<<<G, TR_THREADS, t->smem_bwd, st>>>(P, B, bt, l);
-    tr_reduce_kernel<<<B.n_reduce_blocks, TR_RED_THREADS, 3 * P.D * P.D * sizeof(float), st>>>(P, B);
+    tr_reduce_kernel<<<G, TR_THREADS, 0, st>>>(P, B);
     ++step;
     TrOptim o;
     o.kind = opt_kind;
@@ -945,6 +936,7 @@ extern "C" int nb200_train_run(nb200_trainer* t, float* d_theta_p, float* d_thet
   R.beta1 = (float)beta1, R.beta2 = (float)beta2, R.eps = (float)eps, R.weight_decay = (float)weight_decay;
   R.clip = (float)clip, R.beta1d = beta1, R.beta2d = beta2, R.step0 = step0;
   for (int e = 0; e < n_epochs; ++e) R.lr[e] = (float)h_lr[e];
+  R.b1pow0 = std::pow(beta1, (double)step0), R.b2pow0 = std::pow(beta2, (double)step0);
   R.m = d_m, R.v = d_v, R.hist = d_hist, R.loss_accum = t->run_scalars;
   R.ctl = (TrCtl*)d_ctl, R.best_p = d_best_p, R.best_b = d_best_b, R.n_b = (int)n_theta_b;
   return trainer_launch_run(t, d_theta_p, d_theta_b, R, (cudaStream_t)stream);

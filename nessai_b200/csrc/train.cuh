@@ -23,14 +23,12 @@ constexpr int TR_R = 16;         // rows per tile
 constexpr int TR_THREADS = 512;  // threads per CTA of the row kernels (latency-bound: 4 warps / SMSP)
 constexpr int TR_RG = TR_THREADS / 64;   // row groups of the tile GEMM
 constexpr int TR_RT = TR_R / TR_RG;      // rows per thread
-constexpr int TR_RED_THREADS = 128;      // threads per CTA of the REDUCE kernel
 constexpr int TR_CHUNK = 64;             // output columns per staged weight unit
 constexpr int TR_MAXL = 16;      // coupling layers
 constexpr int TR_MAXBUF = 12;    // conditioner buffers per layer
 constexpr int TR_MAXLIN = 12;    // linears per conditioner
 constexpr int TR_MAXD = 64;      // features
 constexpr int TR_MAXG = 148;     // CTAs per launch (one per SM)
-constexpr int TR_REDUCE_MAXBLOCKS = 2048;
 
 // ---- plan: ints only; packed by nessai_b200/train_plan.py in exactly this order ----------------
 struct TrLinear {
@@ -80,12 +78,16 @@ struct TrBuffers {
   float* s_part[2];   // [G][2][D] BatchNorm backward sums
   float* wsum_part;   // [G]
   float* loss_part;   // [G]
-  float* part;        // [G][n_part] gradient partials
-  float* grad;        // [n_params]
+  float* part;        // [G][part_stride] gradient partials (part_stride = n_part rounded up to 4 floats)
+  int part_stride;
+  float* grad;        // [n_params rounded up to 4]
   float* gn_part;     // [n_reduce_blocks]
   int n_reduce_blocks;
   const float* pmask; // [n_params] or NULL: MADE masks (1 elsewhere); masked weights stay exactly 0
   int G;              // CTAs of the row kernels
+  // NB200_TR_TRACE (debugging aid): [2 * trace_cap + 1] = (tag, globaltimer ns) marks of CTA 0, then the mark count
+  long long* trace = nullptr;
+  int trace_cap = 0;
 };
 
 struct TrBatch {
@@ -102,6 +104,29 @@ struct TrOptim {
   float lr, beta1, beta2, eps, weight_decay, clip;
   float bc1, bc2;  // 1 - beta^t
 };
+
+#ifndef NB200_SIMT_SHIM
+__device__ __forceinline__ void tr_mark(const TrBuffers& Bf, int tag) {
+  if (Bf.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long slot = Bf.trace[2 * Bf.trace_cap];
+    if (slot < Bf.trace_cap) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      Bf.trace[2 * slot] = tag;
+      Bf.trace[2 * slot + 1] = t;
+      Bf.trace[2 * Bf.trace_cap] = slot + 1;
+    }
+  }
+}
+#else
+__device__ __forceinline__ void tr_mark(const TrBuffers&, int) {}
+#endif
+// -DNB200_TR_FINE: marks inside the phases as well (tags 1000+)
+#ifdef NB200_TR_FINE
+#define TR_T(tag) tr_mark(Bf, tag)
+#else
+#define TR_T(tag)
+#endif
 
 constexpr float TR_LU_EPS = 1e-3f, TR_BN_EPS = 1e-5f, TR_BN_MOM = 0.1f;
 constexpr float TR_HALF_LOG_2PI = 0.91893853320467274178f;
@@ -278,37 +303,68 @@ __device__ __forceinline__ void tr_load_w_async(float* sW, const float* W, int n
 }
 
 // Dense W = Lo Up of nflows' LULinear (unit lower x upper with softplus diagonal) into shared
-// memory.  The triangles are staged in `stage` (>= D*D floats) first.  transposed as above.
+// memory, transposed as above.  The two triangles are first expanded into dense D x D matrices
+// Lo = stage[0 .. D*D), Up = stage[D*D .. 2*D*D) (zeros included), which stay valid for the
+// caller (the backward phase applies the chain rule with them): every global load independent,
+// then a branch-free D x D x D product.
 __device__ __forceinline__ void tr_lu_dense(float* __restrict__ sW, float* __restrict__ stage,
                                             const float* __restrict__ theta, const TrLayer& ly,
                                             int D, bool transposed) {
-  const int ntri = D * (D - 1) / 2;
-  float* lower = stage;
-  float* upper = stage + ntri;
-  float* diag = stage + 2 * ntri;
-  tr_copy_async4(lower, theta + ly.lu_lower, ntri);
-  tr_copy_async4(upper, theta + ly.lu_upper, ntri);
-  tr_copy_async4(diag, theta + ly.lu_diag, D);
-  tr_copy_async4(sW + D * (D | 1), theta + ly.lu_bias, D);
-  tr_cp_commit();
-  tr_cp_wait<0>();
-  __syncthreads();
-  for (int m = threadIdx.x; m < D; m += TR_THREADS) diag[m] = tr_softplus(diag[m]) + TR_LU_EPS;
+  float* Lo = stage;
+  float* Up = stage + D * D;
+  for (int e = threadIdx.x; e < D * D; e += TR_THREADS) {
+    const int i = e / D, j = e - i * D;
+    float lo = 0.f, up = 0.f;
+    if (i == j) {
+      lo = 1.f;
+      up = tr_softplus(tr_ldp(theta + ly.lu_diag + i)) + TR_LU_EPS;
+    } else if (j < i) {
+      lo = tr_ldp(theta + ly.lu_lower + i * (i - 1) / 2 + j);
+    } else {
+      up = tr_ldp(theta + ly.lu_upper + i * D - i * (i + 1) / 2 + (j - i - 1));
+    }
+    Lo[e] = lo;
+    Up[e] = up;
+  }
+  for (int j = threadIdx.x; j < D; j += TR_THREADS) sW[D * (D | 1) + j] = tr_ldp(theta + ly.lu_bias + j);
   __syncthreads();
   const int ld = transposed ? (D | 1) : D;
   for (int e = threadIdx.x; e < D * D; e += TR_THREADS) {
     const int i = e / D, j = e - i * D;
     const int mmax = i < j ? i : j;
     float s = 0.f;
-    for (int m = 0; m <= mmax; ++m) {
-      const float lo = (m == i) ? 1.f : lower[i * (i - 1) / 2 + m];
-      const float up = (m == j) ? diag[m] : upper[m * D - m * (m + 1) / 2 + (j - m - 1)];
-      s = fmaf(lo, up, s);
-    }
+    for (int m = 0; m <= mmax; ++m) s = fmaf(Lo[i * D + m], Up[m * D + j], s);
     if (transposed) sW[j * ld + i] = s;
     else sW[i * ld + j] = s;
   }
   __syncthreads();
+}
+
+// Chain rule of the LU parametrisation for this CTA's dense partial dW (D x D, row-major) into the
+// partial gradients of the lower / upper / unconstrained-diagonal entries (linear in dW, so it
+// commutes with the sum over CTAs); Lo / Up as tr_lu_dense left them.  `once`: this CTA also adds
+// the row-constant log|det| term of the loss, d(-sum_i log Up_ii) (the row weights sum to 1).
+__device__ __forceinline__ void tr_lu_chain(float* __restrict__ part, const float* __restrict__ dW,
+                                            const float* __restrict__ Lo, const float* __restrict__ Up,
+                                            const float* __restrict__ theta, const TrLayer& ly, int D,
+                                            bool once) {
+  for (int e = threadIdx.x; e < D * D; e += TR_THREADS) {
+    const int i = e / D, j = e - i * D;
+    if (j < i) {  // d lower[i][j] = sum_k dW[i][k] Up[j][k]
+      float s = 0.f;
+      for (int k = j; k < D; ++k) s = fmaf(dW[i * D + k], Up[j * D + k], s);
+      part[ly.lu_lower + i * (i - 1) / 2 + j] = s;
+    } else {  // d upper[i][j] = sum_k Lo[k][i] dW[k][j]
+      float s = 0.f;
+      for (int k = i; k < D; ++k) s = fmaf(Lo[k * D + i], dW[k * D + j], s);
+      if (i == j) {
+        if (once) s -= 1.f / Up[e];
+        part[ly.lu_diag + i] = s * tr_sigmoid(tr_ldp(theta + ly.lu_diag + i));
+      } else {
+        part[ly.lu_upper + i * D - i * (i + 1) / 2 + (j - i - 1)] = s;
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------- shared memory map
@@ -379,64 +435,74 @@ __device__ __forceinline__ void tr_stage_itab(const TrBuffers& Bf, const TrPlan&
   __syncthreads();
 }
 
+__device__ __forceinline__ float tr_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the block (fixed order: lanes by shuffle, then the warps' sums by every thread).
 template <int NT = TR_THREADS>
 __device__ __forceinline__ float tr_block_sum(float v, float* red) {
+  v = tr_warp_sum(v);
   __syncthreads();
-  red[threadIdx.x] = v;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  for (int s = NT / 2; s > 0; s >>= 1) {
-    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-    __syncthreads();
-  }
-  const float r = red[0];
+  float r = 0.f;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) r += red[w];
   __syncthreads();
   return r;
 }
 
-// Combine the per-CTA (n, mean, M2) partials of BatchNorm layer `l` (Chan et al.) into
-// bn[0][d] = mean, bn[1][d] = 1/sqrt(var + eps), and return the unbiased variance through var_out.
-// The partials are first staged in shared memory with independent coalesced loads (one L2
-// latency instead of G dependent ones).
+
+// Pool the per-CTA (n, mean, M2) partials of BatchNorm layer `l` into bn[0][d] = mean,
+// bn[1][d] = 1/sqrt(var + eps), and the unbiased variance through var_out:
+//   mean = sum_g n_g mean_g / N,   M2 = sum_g (M2_g + n_g (mean_g - mean)^2)
+// (the exact pooled form of Chan et al.'s update, without its sequential chain: one warp per
+// feature, lanes over the CTAs, every load independent).
+constexpr int TR_STAT_PER_LANE = (TR_MAXG + 31) / 32;
 __device__ __forceinline__ void tr_reduce_stats(const TrBuffers& Bf, int l, int D, int B, float* bn,
                                                 float* var_out, float* stage, float* red) {
+  (void)stage, (void)red;
   const int G = Bf.G;
-  float* sn = stage + G * 2 * D;
-  tr_copy_async4(stage, Bf.stat_part + (size_t)l * G * 2 * D, G * 2 * D);
-  tr_copy_async4(sn, Bf.stat_n, G);
-  tr_cp_commit();
-  tr_cp_wait<0>();
-  __syncthreads();
-  const int nsl = TR_THREADS / D;
-  const int d = threadIdx.x % D, sl = threadIdx.x / D;
-  float n = 0.f, mean = 0.f, m2 = 0.f;
-  if (sl < nsl)
-    for (int g = sl; g < G; g += nsl) {
-      const float nb = sn[g];
-      if (nb == 0.f) continue;
-      const float mb = stage[g * 2 * D + d], m2b = stage[g * 2 * D + D + d];
-      const float nn = n + nb, delta = mb - mean;
-      mean += delta * (nb / nn);
-      m2 += m2b + delta * delta * (n * nb / nn);
-      n = nn;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* part = Bf.stat_part + (size_t)l * G * 2 * D;
+  float nb[TR_STAT_PER_LANE];
+#pragma unroll
+  for (int q = 0; q < TR_STAT_PER_LANE; ++q) {
+    const int g = lane + 32 * q;
+    nb[q] = g < G ? Bf.stat_n[g] : 0.f;
+  }
+  for (int d = warp; d < D; d += TR_THREADS / 32) {
+    float mg[TR_STAT_PER_LANE], qg[TR_STAT_PER_LANE];
+    float sn = 0.f, sm = 0.f;
+#pragma unroll
+    for (int q = 0; q < TR_STAT_PER_LANE; ++q) {
+      const int g = lane + 32 * q;
+      // (every CTA of the grid writes its partial, rows or not: the loads need not wait for nb)
+      const bool ok = g < G;
+      mg[q] = ok ? part[(size_t)g * 2 * D + d] : 0.f;
+      qg[q] = ok ? part[(size_t)g * 2 * D + D + d] : 0.f;
+      sn += nb[q];
+      sm = fmaf(nb[q], mg[q], sm);
     }
-  red[threadIdx.x] = n, red[TR_THREADS + threadIdx.x] = mean, red[2 * TR_THREADS + threadIdx.x] = m2;
-  __syncthreads();
-  if ((int)threadIdx.x < D) {
-    n = 0.f, mean = 0.f, m2 = 0.f;
-    for (int q = 0; q < nsl; ++q) {
-      const int t = q * D + threadIdx.x;
-      const float nb = red[t];
-      if (nb == 0.f) continue;
-      const float mb = red[TR_THREADS + t], m2b = red[2 * TR_THREADS + t];
-      const float nn = n + nb, delta = mb - mean;
-      mean += delta * (nb / nn);
-      m2 += m2b + delta * delta * (n * nb / nn);
-      n = nn;
+    sn = tr_warp_sum(sn);
+    sm = tr_warp_sum(sm);
+    const float mean = sm / sn;
+    float m2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < TR_STAT_PER_LANE; ++q) {
+      const float delta = mg[q] - mean;
+      m2 += qg[q] + nb[q] * delta * delta;
     }
-    const float var = m2 / (float)(B - 1);
-    bn[threadIdx.x] = mean;
-    bn[D + threadIdx.x] = rsqrtf(var + TR_BN_EPS);
-    if (var_out) var_out[threadIdx.x] = var;
+    m2 = tr_warp_sum(m2);
+    if (lane == 0) {
+      const float var = m2 / (float)(B - 1);
+      bn[d] = mean;
+      bn[D + d] = rsqrtf(var + TR_BN_EPS);
+      if (var_out) var_out[d] = var;
+    }
   }
   __syncthreads();
 }
@@ -461,33 +527,35 @@ __device__ __forceinline__ void tr_colsum(const float* __restrict__ src, int G, 
   __syncthreads();
 }
 
-// Load BatchNorm layer l's (mean, rstd, w, beta) into bn[0..3][D] for the training pass.
-// first_use: the statistics are still per-CTA partials (reduce them; block 0 publishes them and
-// EMA-updates the running buffers); otherwise read the published values.
-__device__ __forceinline__ void tr_bn_setup(const TrBuffers& Bf, const TrLayer& ly, int l, int D, int B,
-                                            float* bn, float* scratch, bool first_use, float* stage, float* red) {
-  if (first_use) {
-    tr_reduce_stats(Bf, l, D, B, bn, scratch, stage, red);
-    if (blockIdx.x == 0)
-      for (int d = threadIdx.x; d < D; d += TR_THREADS) {
-        Bf.stats[(l * 2) * D + d] = bn[d];
-        Bf.stats[(l * 2 + 1) * D + d] = scratch[d];
-        float* rm = Bf.theta_b + ly.bn_rm;
-        float* rv = Bf.theta_b + ly.bn_rv;
-        rm[d] = (1.f - TR_BN_MOM) * rm[d] + TR_BN_MOM * bn[d];
-        rv[d] = (1.f - TR_BN_MOM) * rv[d] + TR_BN_MOM * scratch[d];
-      }
-  } else {
-    for (int d = threadIdx.x; d < D; d += TR_THREADS) {
-      bn[d] = Bf.stats[(l * 2) * D + d];
-      bn[D + d] = rsqrtf(Bf.stats[(l * 2 + 1) * D + d] + TR_BN_EPS);
-    }
-  }
+// BatchNorm layer l for the training pass: bn[0..3][D] = mean, rstd, w, beta.
+// The affine parameters do not depend on the batch (they can be loaded while a grid barrier is pending):
+__device__ __forceinline__ void tr_bn_affine(const TrBuffers& Bf, const TrLayer& ly, int D, float* bn) {
   for (int d = threadIdx.x; d < D; d += TR_THREADS) {
     bn[2 * D + d] = tr_softplus(tr_ldp(Bf.theta_p + ly.bn_uw + d)) + TR_BN_EPS;
     bn[3 * D + d] = tr_ldp(Bf.theta_p + ly.bn_bias + d);
   }
-  __syncthreads();
+}
+// first use of the layer's batch statistics: pool the per-CTA partials (scratch[D] receives the
+// variance); the last CTA publishes them and EMA-updates the running buffers (nflows BatchNorm)
+__device__ __forceinline__ void tr_bn_stats_first(const TrBuffers& Bf, const TrLayer& ly, int l, int D, int B,
+                                                  float* bn, float* scratch) {
+  tr_reduce_stats(Bf, l, D, B, bn, scratch, nullptr, nullptr);
+  if (blockIdx.x == gridDim.x - 1)
+    for (int d = threadIdx.x; d < D; d += TR_THREADS) {
+      Bf.stats[(l * 2) * D + d] = bn[d];
+      Bf.stats[(l * 2 + 1) * D + d] = scratch[d];
+      float* rm = Bf.theta_b + ly.bn_rm;
+      float* rv = Bf.theta_b + ly.bn_rv;
+      rm[d] = (1.f - TR_BN_MOM) * rm[d] + TR_BN_MOM * bn[d];
+      rv[d] = (1.f - TR_BN_MOM) * rv[d] + TR_BN_MOM * scratch[d];
+    }
+}
+// later uses: the published statistics
+__device__ __forceinline__ void tr_bn_stats_published(const TrBuffers& Bf, int l, int D, float* bn) {
+  for (int d = threadIdx.x; d < D; d += TR_THREADS) {
+    bn[d] = Bf.stats[(l * 2) * D + d];
+    bn[D + d] = rsqrtf(Bf.stats[(l * 2 + 1) * D + d] + TR_BN_EPS);
+  }
 }
 
 // Eval-mode BatchNorm constants (running statistics).
@@ -698,12 +766,14 @@ __device__ __forceinline__ void tr_layer_forward(const TrBuffers& Bf, const TrPl
     for (int e = threadIdx.x; e < D * TR_R; e += TR_THREADS) S.H2[e] = S.H1[e];
   }
   __syncthreads();
+  TR_T(1004);
   if (save) tr_copy(save, S.H2, D);
   for (int e = threadIdx.x; e < ly.d_id * TR_R; e += TR_THREADS) {
     const int i = e / TR_R, r = e - i * TR_R;
     S.V[e] = S.H2[itab[ly.id_off + i] * TR_R + r];
   }
   __syncthreads();
+  TR_T(1005);
   int u = 0;
   for (int j = 0; j < ly.n_lin; ++j) {
     const TrLinear& ln = ly.lin[j];
@@ -728,6 +798,7 @@ __device__ __forceinline__ void tr_layer_forward(const TrBuffers& Bf, const TrPl
       tr_gemm(S.V + (ly.buf_off[ln.out_buf] + c0) * TR_R, Aop, buf, nc | 1, buf + S.wbuf - TR_CHUNK,
               ln.res_buf >= 0 ? S.V + (ly.buf_off[ln.res_buf] + c0) * TR_R : nullptr, nc, ln.n_in, false);
       __syncthreads();
+      TR_T(1010 + j);
     }
   }
   const float* prm = S.V + ly.buf_off[ly.n_buf - 1] * TR_R;
@@ -762,6 +833,7 @@ __device__ __forceinline__ void tr_layer_forward(const TrBuffers& Bf, const TrPl
     }
   }
   __syncthreads();
+  TR_T(1006);
   if (threadIdx.x < TR_R) {
     float s = 0.f;
     for (int i = 0; i < ly.d_tr; ++i) s += S.A[i * TR_R + threadIdx.x];
@@ -803,15 +875,26 @@ extern __shared__ __align__(16) float tr_smem_dyn[];
 // Phases are __device__ functions over a carved shared-memory map whose index tables are staged:
 // the persistent kernel (tr_train_kernel) runs them between grid barriers; the one-phase kernels
 // below it launch them one at a time (CPU SIMT shim of tests/_hostcheck, NB200_TR_CHAIN=1).
+// `part`: TR_PROLOGUE = what does not depend on the other CTAs' previous phase (the persistent kernel
+// runs it while the grid barrier is pending), TR_MAIN = the rest, TR_WHOLE = both.
+constexpr int TR_PROLOGUE = 1, TR_MAIN = 2, TR_WHOLE = 3;
+constexpr int TR_KEEP_BN = 4;  // (backward prologue) bn[0..3][D] of this layer is still in shared memory
+
 __device__ __forceinline__ void tr_fwd_phase(const TrPlan& P, const TrBuffers& Bf, const TrBatch& bt, int l,
-                                             const TrSmem& S) {
+                                             const TrSmem& S, int part = TR_WHOLE) {
   const TrLayer& ly = P.layer[l];
   const int D = P.D;
   const int* lperm = ly.perm_off >= 0 ? S.itab + ly.perm_off : nullptr;
   const bool bn_prev = l > 0 && P.layer[l - 1].bn_uw >= 0;
-  if (bn_prev) tr_bn_setup(Bf, P.layer[l - 1], l - 1, D, bt.B, S.bn, S.bn + 4 * D, true, S.stage, S.red);
-  if (ly.lu_bias >= 0) tr_lu_dense(S.Wlu, S.stage, Bf.theta_p, ly, D, true);
+  if (part & TR_PROLOGUE) {
+    if (ly.lu_bias >= 0) tr_lu_dense(S.Wlu, S.stage, Bf.theta_p, ly, D, true);
+    if (bn_prev) tr_bn_affine(Bf, P.layer[l - 1], D, S.bn);
+    TR_T(1001);
+  }
+  if (!(part & TR_MAIN)) return;
+  if (bn_prev) tr_bn_stats_first(Bf, P.layer[l - 1], l - 1, D, bt.B, S.bn, S.bn + 4 * D);
   __syncthreads();
+  TR_T(1002);
   float n_run = 0.f, mean_run = 0.f, m2_run = 0.f;  // BatchNorm partials of feature threadIdx.x
   float wsum = 0.f;
   int rows_cta = 0;
@@ -844,7 +927,9 @@ __device__ __forceinline__ void tr_fwd_phase(const TrPlan& P, const TrBuffers& B
       }
       __syncthreads();
     }
+    TR_T(1003);
     tr_layer_forward(Bf, P, ly, S, rec);
+    TR_T(1009);
     if (threadIdx.x < TR_R) Bf.ldrow[tile * TR_R + threadIdx.x] = S.ld[threadIdx.x];
     const int nv = min(TR_R, bt.B - tile * TR_R);
     rows_cta += nv;
@@ -878,12 +963,15 @@ __device__ __forceinline__ void tr_fwd_phase(const TrPlan& P, const TrBuffers& B
 // ============================================================================ LOSS
 // z = BN_{L-1}(y_{L-1}); loss partial; dout_{L-1} = c_r z; BatchNorm backward sums of layer L-1.
 __device__ __forceinline__ void tr_loss_phase(const TrPlan& P, const TrBuffers& Bf, const TrBatch& bt,
-                                              const TrSmem& S) {
+                                              const TrSmem& S, int part = TR_WHOLE) {
   const int D = P.D, L = P.L;
   const TrLayer& ly = P.layer[L - 1];
   const bool bn = ly.bn_uw >= 0;
-  if (bn) tr_bn_setup(Bf, ly, L - 1, D, bt.B, S.bn, S.bn + 4 * D, true, S.stage, S.red);
-  // the last layer's statistics are published by block 0 only: use our own copy for the constant
+  if ((part & TR_PROLOGUE) && bn) tr_bn_affine(Bf, ly, D, S.bn);
+  if (!(part & TR_MAIN)) return;
+  if (bn) tr_bn_stats_first(Bf, ly, L - 1, D, bt.B, S.bn, S.bn + 4 * D);
+  __syncthreads();
+  // the last layer's statistics are published by one block only: use our own copy for the constant
   float cld = 0.f;
   {
     float s = 0.f;
@@ -961,7 +1049,7 @@ __device__ __forceinline__ void tr_loss_phase(const TrPlan& P, const TrBuffers& 
 
 // ============================================================================ BWD(l)
 __device__ __forceinline__ void tr_bwd_phase(const TrPlan& P, const TrBuffers& Bf, const TrBatch& bt, int l,
-                                             const TrSmem& S) {
+                                             const TrSmem& S, int part_sel = TR_WHOLE) {
   const TrLayer& ly = P.layer[l];
   const int D = P.D, act = P.act;
   const int* itab = S.itab;
@@ -970,19 +1058,28 @@ __device__ __forceinline__ void tr_bwd_phase(const TrPlan& P, const TrBuffers& B
   const bool bn_prev = l > 0 && P.layer[l - 1].bn_uw >= 0;
   float* bnp = S.bn;            // this layer: mean, rstd, w, beta
   float* sS = S.bn + 4 * D;     // S1, S2 of this layer
-  float* part = Bf.part + (size_t)blockIdx.x * P.n_part;
-  if (bn) {
-    tr_bn_setup(Bf, ly, l, D, bt.B, bnp, nullptr, false, nullptr, nullptr);
-    tr_colsum(Bf.s_part[l & 1], Bf.G, 2 * D, sS, S.red);
-    if (blockIdx.x == 0)
-      for (int d = threadIdx.x; d < D; d += TR_THREADS) {
-        Bf.grad[ly.bn_bias + d] = sS[d];
-        const float dw = sS[D + d] - 1.f / bnp[2 * D + d];
-        Bf.grad[ly.bn_uw + d] = dw * tr_sigmoid(tr_ldp(Bf.theta_p + ly.bn_uw + d));
-      }
+  float* part = Bf.part + (size_t)blockIdx.x * Bf.part_stride;
+  if (part_sel & TR_PROLOGUE) {
+    if (bn && !(part_sel & TR_KEEP_BN)) {
+      tr_bn_stats_published(Bf, l, D, bnp);
+      tr_bn_affine(Bf, ly, D, bnp);
+    }
+    if (ly.lu_bias >= 0) tr_lu_dense(S.Wlu, S.stage, Bf.theta_p, ly, D, false);
+    TR_T(2001);
   }
-  if (ly.lu_bias >= 0) tr_lu_dense(S.Wlu, S.stage, Bf.theta_p, ly, D, false);
+  if (!(part_sel & TR_MAIN)) return;
   __syncthreads();
+  if (bn) {
+    tr_colsum(Bf.s_part[l & 1], Bf.G, 2 * D, sS, S.red);
+    // the gradient of the BatchNorm parameters is complete here: CTA 0's partial carries it
+    for (int d = threadIdx.x; d < D; d += TR_THREADS) {
+      const float dw = sS[D + d] - 1.f / bnp[2 * D + d];
+      part[ly.bn_bias + d] = blockIdx.x == 0 ? sS[d] : 0.f;
+      part[ly.bn_uw + d] = blockIdx.x == 0 ? dw * tr_sigmoid(tr_ldp(Bf.theta_p + ly.bn_uw + d)) : 0.f;
+    }
+  }
+  __syncthreads();
+  TR_T(2002);
   const float invB = 1.f / (float)bt.B, invBm1 = 1.f / (float)(bt.B - 1);
   float p1 = 0.f, p2 = 0.f;  // BatchNorm backward sums of layer l-1 (feature threadIdx.x)
   bool first = true;
@@ -1006,6 +1103,7 @@ __device__ __forceinline__ void tr_bwd_phase(const TrPlan& P, const TrBuffers& B
     for (int e = threadIdx.x; e < P.vals_floats * TR_R; e += TR_THREADS) S.Gv[e] = 0.f;
     tr_cp_wait<1>();
     __syncthreads();
+    TR_T(2003);
     // dy (in place in X): BatchNorm backward
     if (bn) {
       for (int e = threadIdx.x; e < D * TR_R; e += TR_THREADS) {
@@ -1056,6 +1154,7 @@ __device__ __forceinline__ void tr_bwd_phase(const TrPlan& P, const TrBuffers& B
       }
     }
     __syncthreads();
+    TR_T(2004);
     // conditioner backward
     int u = 0;
     for (int j = ly.n_lin - 1; j >= 0; --j) {
@@ -1092,6 +1191,7 @@ __device__ __forceinline__ void tr_bwd_phase(const TrPlan& P, const TrBuffers& B
         for (int e = threadIdx.x; e < ln.n_out * TR_R; e += TR_THREADS) gres[e] += delta[e];
       }
       __syncthreads();
+      TR_T(2010 + j);
     }
     // d h2 (identity half) = dy + d(net input)
     for (int e = threadIdx.x; e < ly.d_id * TR_R; e += TR_THREADS) {
@@ -1124,6 +1224,7 @@ __device__ __forceinline__ void tr_bwd_phase(const TrPlan& P, const TrBuffers& B
       }
     }
     __syncthreads();
+    TR_T(2005);
     const float* dh1 = S.Y;
     if (ly.lu_bias >= 0) {
       tr_wgrad(part + ly.lu_part_off, S.Y, S.H1, D, D, first);
@@ -1150,6 +1251,7 @@ __device__ __forceinline__ void tr_bwd_phase(const TrPlan& P, const TrBuffers& B
     }
     first = false;
     __syncthreads();
+    TR_T(2006);
   }
   if (first) {
     // this CTA had no tile: its partial vector must still be defined for REDUCE
@@ -1163,6 +1265,11 @@ __device__ __forceinline__ void tr_bwd_phase(const TrPlan& P, const TrBuffers& B
       for (int e = threadIdx.x; e < D; e += TR_THREADS) part[ly.lu_bias + e] = 0.f;
     }
   }
+  if (ly.lu_bias >= 0) {
+    // dense dW of this CTA (accumulated over its tiles above) -> lower / upper / diagonal partials
+    __syncthreads();
+    tr_lu_chain(part, part + ly.lu_part_off, S.stage, S.stage + D * D, Bf.theta_p, ly, D, blockIdx.x == 0);
+  }
   if (bn_prev && (int)threadIdx.x < D) {
     float* sp = Bf.s_part[(l - 1) & 1] + (size_t)blockIdx.x * 2 * D;
     sp[threadIdx.x] = p1;
@@ -1171,142 +1278,94 @@ __device__ __forceinline__ void tr_bwd_phase(const TrPlan& P, const TrBuffers& B
 }
 
 // ============================================================================ REDUCE
-// grad = sum of the per-CTA partials; LU chain rule (dense dW -> lower / upper / diagonal);
-// per-block sums of squares for the global gradient norm (gn_part[blockIdx.x]).
-// The caller hands out the work: LU layers l = lu_first, lu_first + lu_stride, ... (< L) and the
-// slice `gen_block` of `gen_blocks` of the ordinary parameters (gen_block < 0: none).
-// smem: >= 3 * D * D floats of scratch (LU layers only); red: >= NT floats.
-template <int NT>
-__device__ __forceinline__ void tr_reduce_phase(const TrPlan& P, const TrBuffers& Bf, float* smem, float* red,
-                                                int lu_first, int lu_stride, int gen_block, int gen_blocks) {
-  const int D = P.D, G = Bf.G, n_part = P.n_part;
+// grad[i] = sum over the CTAs of part[g][i] for every parameter (times the MADE mask), and
+// gn_part[blockIdx.x] = this block's share of |grad|^2.  Every parameter's partial is complete in
+// the partial vectors (the backward phases apply the LU chain rule and carry the BatchNorm
+// gradients themselves), so this is one dense, fixed-order, vectorised sum: columns of four
+// parameters are dealt out in contiguous slices, one per CTA; inside a CTA the G partials of a
+// column are split over `nsub` threads -- every 16-byte load independent -- and combined through
+// shared memory in a fixed order (no atomics: bit-reproducible for a given grid).
+// scratch: >= TR_THREADS float4; red: >= TR_THREADS floats.
+__device__ __forceinline__ void tr_reduce_phase(const TrPlan& P, const TrBuffers& Bf, float4* scratch, float* red) {
+  const int n = P.n_params, n4 = (n + 3) / 4, G = Bf.G;
+  const int per = (n4 + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int c_begin = blockIdx.x * per, c_end = min(n4, c_begin + per);
   float sq = 0.f;
-  // sum over the per-CTA partials with 8 independent loads in flight
-  auto psum = [&](const float* src) {
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int g = 0;
-    for (; g + 8 <= G; g += 8) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) acc[u] += src[(size_t)(g + u) * n_part];
+  for (int c0 = c_begin; c0 < c_end; c0 += TR_THREADS) {
+    const int ncol = min(TR_THREADS, c_end - c0);
+    const int nsub = min(TR_THREADS / ncol, 16);
+    const int sub = threadIdx.x / ncol, col = threadIdx.x - sub * ncol;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sub < nsub) {
+      const float4* src = reinterpret_cast<const float4*>(Bf.part) + (c0 + col);
+      const size_t stride4 = (size_t)Bf.part_stride / 4;
+#pragma unroll 4
+      for (int g = sub; g < G; g += nsub) {
+        const float4 v = src[(size_t)g * stride4];
+        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+      }
     }
+    scratch[threadIdx.x] = acc;  // [sub][col]
+    __syncthreads();
+    if ((int)threadIdx.x < ncol) {
+      float4 t = scratch[threadIdx.x];
+      for (int q = 1; q < nsub; ++q) {
+        const float4 v = scratch[q * ncol + threadIdx.x];
+        t.x += v.x, t.y += v.y, t.z += v.z, t.w += v.w;
+      }
+      const int i = 4 * (c0 + threadIdx.x);
+      float g4[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-    for (int u = 0; u < 7; ++u)
-      if (g + u < G) acc[u] += src[(size_t)(g + u) * n_part];
-    return ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-  };
-  for (int l = lu_first; l < P.L; l += lu_stride) {
-    const TrLayer& ly = P.layer[l];
-    if (ly.bn_uw >= 0)
-      for (int d = threadIdx.x; d < D; d += NT) {
-        const float g0 = Bf.grad[ly.bn_bias + d], g1 = Bf.grad[ly.bn_uw + d];
-        sq += g0 * g0 + g1 * g1;
-      }
-    if (ly.lu_bias >= 0) {
-      float* sdW = smem;                 // [D][D]
-      float* sLo = sdW + D * D;          // [D][D]
-      float* sUp = sLo + D * D;          // [D][D]
-      __syncthreads();
-      for (int e = threadIdx.x; e < D * D; e += NT) {
-        sdW[e] = psum(Bf.part + ly.lu_part_off + e);
-        const int i = e / D, j = e - i * D;
-        sLo[e] = i == j ? 1.f : (j < i ? tr_ldp(Bf.theta_p + ly.lu_lower + i * (i - 1) / 2 + j) : 0.f);
-        sUp[e] = i == j ? tr_softplus(tr_ldp(Bf.theta_p + ly.lu_diag + i)) + TR_LU_EPS
-                        : (i < j ? tr_ldp(Bf.theta_p + ly.lu_upper + i * D - i * (i + 1) / 2 + (j - i - 1)) : 0.f);
-      }
-      __syncthreads();
-      for (int e = threadIdx.x; e < D * D; e += NT) {
-        const int i = e / D, j = e - i * D;
-        if (j < i) {  // d lower[i][j] = sum_k dW[i][k] Up[j][k]
-          float s = 0.f;
-          for (int k = j; k < D; ++k) s = fmaf(sdW[i * D + k], sUp[j * D + k], s);
-          Bf.grad[ly.lu_lower + i * (i - 1) / 2 + j] = s;
-          sq += s * s;
-        } else {  // d upper[i][j] = sum_k Lo[k][i] dW[k][j]
-          float s = 0.f;
-          for (int k = i; k < D; ++k) s = fmaf(sLo[k * D + i], sdW[k * D + j], s);
-          if (i == j) {
-            s = (s - 1.f / sUp[e]) * tr_sigmoid(tr_ldp(Bf.theta_p + ly.lu_diag + i));
-            Bf.grad[ly.lu_diag + i] = s;
-          } else {
-            Bf.grad[ly.lu_upper + i * D - i * (i + 1) / 2 + (j - i - 1)] = s;
-          }
-          sq += s * s;
+      for (int k = 0; k < 4; ++k) {
+        if (i + k < n) {
+          if (Bf.pmask) g4[k] *= Bf.pmask[i + k];
+          sq = fmaf(g4[k], g4[k], sq);
+        } else {
+          g4[k] = 0.f;
         }
       }
+      reinterpret_cast<float4*>(Bf.grad)[c0 + threadIdx.x] = make_float4(g4[0], g4[1], g4[2], g4[3]);
     }
+    __syncthreads();
   }
-  if (gen_block >= 0) {
-    // 8 lanes per parameter (each sums every 8th partial, all loads independent), then a
-    // 3-step shuffle: one memory latency per parameter instead of G/8
-    const int n_reduce = P.n_reduce;
-    const int sub = threadIdx.x & 7;
-    const int per_block = NT / 8;
-    // warp-uniform trip count (the shuffles below need all 32 lanes): 4 parameters per warp
-    for (int base = gen_block * per_block + 4 * (threadIdx.x >> 5); base < n_reduce; base += gen_blocks * per_block) {
-      const int i = base + ((threadIdx.x & 31) >> 3);
-      const bool ok = i < n_reduce;
-      const int p = ok ? Bf.reduce_idx[i] : 0;
-      const float* src = Bf.part + p;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      if (ok) {
-        int g = sub;
-        for (; g + 24 < G; g += 32) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) acc[u] += src[(size_t)(g + 8 * u) * n_part];
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (g + 8 * u < G) acc[u] += src[(size_t)(g + 8 * u) * n_part];
-      }
-      float sgm = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-      sgm += __shfl_xor_sync(0xffffffffu, sgm, 1);
-      sgm += __shfl_xor_sync(0xffffffffu, sgm, 2);
-      sgm += __shfl_xor_sync(0xffffffffu, sgm, 4);
-      if (ok && sub == 0) {
-        if (Bf.pmask) sgm *= Bf.pmask[p];
-        Bf.grad[p] = sgm;
-        sq += sgm * sgm;
-      }
-    }
-  }
-  const float tot = tr_block_sum<NT>(sq, red);
+  const float tot = tr_block_sum<TR_THREADS>(sq, red);
   if (threadIdx.x == 0) Bf.gn_part[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(TR_RED_THREADS) tr_reduce_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf) {
-  __shared__ float red[TR_RED_THREADS];
-  const int b = blockIdx.x;
-  if (b < P.L) tr_reduce_phase<TR_RED_THREADS>(P, Bf, tr_smem_dyn, red, b, P.L, -1, 0);
-  else tr_reduce_phase<TR_RED_THREADS>(P, Bf, tr_smem_dyn, red, P.L, 1, b - P.L, (int)gridDim.x - P.L);
+__global__ void __launch_bounds__(TR_THREADS) tr_reduce_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf) {
+  __shared__ float4 scratch[TR_THREADS];
+  __shared__ float red[TR_THREADS];
+  tr_reduce_phase(P, Bf, scratch, red);
 }
 
 // ============================================================================ ADAM
 // clip_grad_norm_ + torch.optim.AdamW / Adam / SGD on the flat parameter vector.
-// d_loss[0] = this step's loss, d_loss[1] = gradient norm before clipping.  red: >= NT + 1 floats.
+// d_loss[0] = this step's loss, d_loss[1] = gradient norm before clipping.  red: >= 2 floats.
 template <int NT>
 __device__ __forceinline__ void tr_adam_phase(const TrBuffers& Bf, int n_params, const TrOptim& o,
                                               float* __restrict__ m, float* __restrict__ v, float* d_loss,
                                               float* d_loss_accum, float* red) {
-  {
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    // warp 0: |grad| from the REDUCE blocks' shares (fixed order), and the clip coefficient
     float gsum = 0.f;
-    for (int i = threadIdx.x; i < Bf.n_reduce_blocks; i += NT) gsum += Bf.gn_part[i];
-    float lsum = 0.f;
-    if (blockIdx.x == 0)
-      for (int g = threadIdx.x; g < Bf.G; g += NT) lsum += Bf.loss_part[g];
-    const float gn = sqrtf(tr_block_sum<NT>(gsum, red));
-    const float loss = tr_block_sum<NT>(lsum, red);
-    if (threadIdx.x == 0) {
-      // torch.nn.utils.clip_grad_norm_: clamp(clip / (norm + 1e-6), max = 1), NaN propagates
-      const float c = o.clip / (gn + 1e-6f);
-      red[NT] = o.clip > 0.f ? (c >= 1.f ? 1.f : c) : 1.f;
-      if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < Bf.n_reduce_blocks; i += 32) gsum += Bf.gn_part[i];
+    const float gn = sqrtf(tr_warp_sum(gsum));
+    // torch.nn.utils.clip_grad_norm_: clamp(clip / (norm + 1e-6), max = 1), NaN propagates
+    const float c = o.clip / (gn + 1e-6f);
+    if (threadIdx.x == 0) red[0] = o.clip > 0.f ? (c >= 1.f ? 1.f : c) : 1.f;
+    if (blockIdx.x == 0) {
+      float lsum = 0.f;
+      for (int g = threadIdx.x; g < Bf.G; g += 32) lsum += Bf.loss_part[g];
+      const float loss = tr_warp_sum(lsum);
+      if (threadIdx.x == 0) {
         if (d_loss) d_loss[0] = loss, d_loss[1] = gn;
         if (d_loss_accum) d_loss_accum[0] += loss;
       }
     }
-    __syncthreads();
   }
-  const float coef = red[NT];
+  __syncthreads();
+  const float coef = red[0];
   const int n = n_params;
   for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT) {
     float g = Bf.grad[i] * coef;
@@ -1335,7 +1394,7 @@ __device__ __forceinline__ void tr_adam_phase(const TrBuffers& Bf, int n_params,
 __global__ void __launch_bounds__(256) tr_adam_kernel(TrBuffers Bf, int n_params, TrOptim o, float* __restrict__ m,
                                                       float* __restrict__ v, float* d_loss,
                                                       float* d_loss_accum) {
-  __shared__ float red[256 + 1];
+  __shared__ float red[2];
   tr_adam_phase<256>(Bf, n_params, o, m, v, d_loss, d_loss_accum, red);
 }
 
@@ -1467,6 +1526,7 @@ struct TrRun {
   int kind;             // TrOptim::kind
   float beta1, beta2, eps, weight_decay, clip;
   double beta1d, beta2d;
+  double b1pow0, b2pow0;  // beta^step0 (the bias corrections 1 - beta^step continue from there)
   int64_t step0;        // optimiser steps taken before this launch
   float lr[TR_MAX_CHUNK];  // learning rate of every epoch of the launch
   float* m;
@@ -1480,37 +1540,40 @@ struct TrRun {
   float* best_b;
   int n_b;              // floats in theta_b
   unsigned* bar;        // grid barrier counter (zeroed by the host before the launch)
-  long long* trace;     // NULL, or [2 * cap]: (tag, globaltimer ns) of CTA 0 at every phase boundary
-  int trace_cap;
 };
 
 #ifndef NB200_SIMT_SHIM
 // Grid barrier over the co-resident CTAs of a cooperative launch.  `target` counts arrivals since
-// the launch; thread 0 publishes this CTA's writes (fence + release add), waits for everybody's,
-// and its trailing fence invalidates this SM's L1 before the CTA goes on reading.
+// the launch; thread 0 publishes this CTA's writes (release add) and waits for everybody's (acquire loads).
+__device__ __forceinline__ void tr_grid_arrive(unsigned* bar, unsigned& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+  }
+}
+__device__ __forceinline__ void tr_grid_wait(unsigned* bar, const unsigned& target) {
+  if (threadIdx.x == 0) {
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+    } while ((int)(seen - target) < 0);
+  }
+  __syncthreads();
+}
 __device__ __forceinline__ void tr_grid_sync(unsigned* bar, unsigned& target) {
   __syncthreads();
   if (threadIdx.x == 0) {
     target += gridDim.x;
-    __threadfence();
+    // release: cumulative over the CTA's writes ordered before it by the bar.sync above;
+    // acquire + the bar.sync below order every thread's later reads after the other CTAs' writes
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     unsigned seen;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
     } while ((int)(seen - target) < 0);
-    __threadfence();
   }
   __syncthreads();
-}
-
-__device__ __forceinline__ void tr_trace(const TrRun& R, int& slot, int tag) {
-  if (R.trace && blockIdx.x == 0 && threadIdx.x == 0 && slot < R.trace_cap) {
-    long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    R.trace[2 * slot] = tag;
-    R.trace[2 * slot + 1] = t;
-    ++slot;
-  }
 }
 
 __global__ void __launch_bounds__(TR_THREADS) tr_train_kernel(const __grid_constant__ TrPlan P, TrBuffers Bf,
@@ -1520,8 +1583,7 @@ __global__ void __launch_bounds__(TR_THREADS) tr_train_kernel(const __grid_const
   const int L = P.L;
   const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
   unsigned target = 0;
-  int slot = 0;
-  tr_trace(R, slot, 0);
+  tr_mark(Bf, 0);
   if (Bf.pmask) {
     for (int i = blockIdx.x * TR_THREADS + threadIdx.x; i < P.n_params; i += gridDim.x * TR_THREADS)
       Bf.theta_p[i] *= Bf.pmask[i];
@@ -1530,6 +1592,7 @@ __global__ void __launch_bounds__(TR_THREADS) tr_train_kernel(const __grid_const
   float best_val = R.ctl ? R.ctl->best_val : INFINITY;
   int best_epoch = R.ctl ? R.ctl->best_epoch : 0;
   int64_t step = R.step0;
+  double b1pow = R.b1pow0, b2pow = R.b2pow0;
   int stop = 0, epoch = R.epoch0;
   for (int e = 0; e < R.n_epochs && !stop; ++e) {
     TrBatch bt;
@@ -1540,38 +1603,51 @@ __global__ void __launch_bounds__(TR_THREADS) tr_train_kernel(const __grid_const
       bt.i0 = i0;
       bt.B = (int)min((int64_t)R.batch_size, R.n_rows - i0);
       bt.n_tiles = (bt.B + TR_R - 1) / TR_R;
+      // Between two phases the barrier is split: arrive, then the next phase's prologue (dense LU
+      // matrix, BatchNorm affine constants: nothing another CTA is still producing), then wait.
       for (int l = 0; l < L; ++l) {
-        tr_fwd_phase(P, Bf, bt, l, S);
+        // (FWD(0) follows the optimiser step: its parameters only exist after that barrier)
+        tr_fwd_phase(P, Bf, bt, l, S, l == 0 ? TR_WHOLE : TR_MAIN);
         // the next phase needs layer l's batch statistics (or, before the loss, the weight sum)
-        if (l == L - 1 || P.layer[l].bn_uw >= 0) tr_grid_sync(R.bar, target);
+        const bool grid = l == L - 1 || P.layer[l].bn_uw >= 0;
+        if (grid) tr_grid_arrive(R.bar, target);
         else __syncthreads();
-        tr_trace(R, slot, 100 + l);
+        if (l + 1 < L) tr_fwd_phase(P, Bf, bt, l + 1, S, TR_PROLOGUE);
+        else tr_loss_phase(P, Bf, bt, S, TR_PROLOGUE);
+        if (grid) tr_grid_wait(R.bar, target);
+        else __syncthreads();
+        tr_mark(Bf, 100 + l);
       }
-      tr_loss_phase(P, Bf, bt, S);
-      if (P.layer[L - 1].bn_uw >= 0) tr_grid_sync(R.bar, target);
-      else __syncthreads();
-      tr_trace(R, slot, 200);
+      tr_loss_phase(P, Bf, bt, S, TR_MAIN);
       for (int l = L - 1; l >= 0; --l) {
-        tr_bwd_phase(P, Bf, bt, l, S);
-        // BatchNorm backward of layer l - 1 needs its sums over the batch; REDUCE every partial
-        if (l == 0 || P.layer[l - 1].bn_uw >= 0) tr_grid_sync(R.bar, target);
+        // BatchNorm backward of layer l needs its sums over the batch (from the loss / BWD(l + 1))
+        const bool grid = P.layer[l].bn_uw >= 0;
+        if (grid) tr_grid_arrive(R.bar, target);
         else __syncthreads();
-        tr_trace(R, slot, 300 + l);
+        // (after the loss phase the last layer's BatchNorm constants are still in shared memory)
+        tr_bwd_phase(P, Bf, bt, l, S, TR_PROLOGUE | (l == L - 1 ? TR_KEEP_BN : 0));
+        if (grid) tr_grid_wait(R.bar, target);
+        else __syncthreads();
+        tr_mark(Bf, l == L - 1 ? 200 : 301 + l);
+        tr_bwd_phase(P, Bf, bt, l, S, TR_MAIN);
       }
-      tr_reduce_phase<TR_THREADS>(P, Bf, tr_smem_dyn, S.red, blockIdx.x, gridDim.x, blockIdx.x, gridDim.x);
+      tr_grid_sync(R.bar, target);  // REDUCE reads every CTA's partial vector
+      tr_mark(Bf, 300);
+      tr_reduce_phase(P, Bf, reinterpret_cast<float4*>(tr_smem_dyn), S.red);
       tr_grid_sync(R.bar, target);
-      tr_trace(R, slot, 400);
+      tr_mark(Bf, 400);
       ++step;
+      b1pow *= R.beta1d, b2pow *= R.beta2d;  // beta^step
       TrOptim o;
       o.kind = R.kind, o.lr = R.lr[e], o.beta1 = R.beta1, o.beta2 = R.beta2, o.eps = R.eps;
       o.weight_decay = R.weight_decay, o.clip = R.clip;
-      o.bc1 = (float)(1.0 - pow(R.beta1d, (double)step));
-      o.bc2 = (float)(1.0 - pow(R.beta2d, (double)step));
+      o.bc1 = (float)(1.0 - b1pow);
+      o.bc2 = (float)(1.0 - b2pow);
       tr_adam_phase<TR_THREADS>(Bf, P.n_params, o, R.m, R.v,
                                 R.step_info ? R.step_info + 2 * (step - R.step0 - 1) : nullptr, R.loss_accum,
                                 S.red);
       tr_grid_sync(R.bar, target);
-      tr_trace(R, slot, 500);
+      tr_mark(Bf, 500);
     }
     ++epoch;
     if (!R.ctl) continue;
@@ -1603,7 +1679,7 @@ __global__ void __launch_bounds__(TR_THREADS) tr_train_kernel(const __grid_const
       }
       if (epoch - best_epoch > R.patience) stop = 1;
     }
-    tr_trace(R, slot, 600);
+    tr_mark(Bf, 600);
   }
   if (lead && R.ctl) {
     R.ctl->best_val = best_val;

@@ -34,7 +34,7 @@ import numpy as np
 def populate_turn(flow, z, *, scale, shift, lo, hi, log_prior_const, r_max=0.0, sqrt_t=1.0, min_log_q=None,
                   log_likelihood=None, log_l_threshold=None):
     """One turn up to the weights.  ``flow``: ``oracle.flow_numpy.NumpyFlow``; ``z``: ``(n, D)``
-    latent draws BEFORE the temperature scaling.  Returns a dict of per-row arrays over all
+    latent draws from the flow's base distribution, BEFORE the temperature scaling.  Returns a dict of per-row arrays over all
     ``n`` rows: ``valid`` (bool), ``x``, ``log_q``, ``log_w`` (NaN where not valid), ``log_l``."""
     z = np.asarray(z, dtype=np.float64) * float(sqrt_t)
     n, D = z.shape
@@ -44,7 +44,9 @@ def populate_turn(flow, z, *, scale, shift, lo, hi, log_prior_const, r_max=0.0, 
     with np.errstate(all="ignore"):
         xp, log_j = flow.inverse(z)
         # base.py:401-414: log N(z / sqrt T) - D log sqrt T
-        base = -0.5 * np.sum((z / sqrt_t) ** 2, axis=1) - 0.5 * D * np.log(2 * np.pi) - D * np.log(sqrt_t)
+        # (base: N(0, I), or N(0, var I) for flow_config["distribution"] = "mvn", flows/distributions.py:45-56;
+        # z0 = z / sqrt T is then a draw from THAT distribution)
+        base = flow.base_log_prob(z / sqrt_t) - D * np.log(sqrt_t)
         log_q = base - log_j
         valid &= np.isfinite(log_q)  # flowproposal.py:366-368
         x = xp * scale + shift

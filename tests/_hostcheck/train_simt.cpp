@@ -36,8 +36,8 @@ extern "C" int simt_train_step(const int32_t* h_plan, int n_plan_ints, const int
   std::vector<float> ws((size_t)n_tiles * P.rec_total * TR_R), dout0((size_t)n_tiles * P.D * TR_R),
       dout1((size_t)n_tiles * P.D * TR_R), ldrow((size_t)n_tiles * TR_R), crow((size_t)n_tiles * TR_R),
       stat_part((size_t)P.L * Gmax * 2 * P.D), stats((size_t)P.L * 2 * P.D), s_part0((size_t)Gmax * 2 * P.D),
-      s_part1((size_t)Gmax * 2 * P.D), wsum_part(Gmax), loss_part(Gmax), part((size_t)Gmax * P.n_part),
-      grad(P.n_params, 0.f), gn_part(TR_REDUCE_MAXBLOCKS), stat_n(Gmax);
+      s_part1((size_t)Gmax * 2 * P.D), wsum_part(Gmax), loss_part(Gmax), part((size_t)Gmax * ((P.n_part + 3) & ~3), 0.f),
+      grad((P.n_params + 3) & ~3, 0.f), gn_part(Gmax), stat_n(Gmax);
   TrBatch bt;
   bt.x = x, bt.perm = nullptr, bt.w = w, bt.i0 = 0, bt.B = n_rows, bt.n_tiles = n_tiles;
   const int G = std::min(n_tiles, std::min(TR_MAXG, num_sms));
@@ -48,15 +48,15 @@ extern "C" int simt_train_step(const int32_t* h_plan, int n_plan_ints, const int
   B.s_part[0] = s_part0.data(), B.s_part[1] = s_part1.data(), B.wsum_part = wsum_part.data();
   B.loss_part = loss_part.data(), B.part = part.data(), B.grad = grad.data(), B.gn_part = gn_part.data();
   B.G = G, B.pmask = pmask;
-  B.n_reduce_blocks =
-      std::min(TR_REDUCE_MAXBLOCKS, P.L + std::max(1, (P.n_reduce * 8 + TR_RED_THREADS - 1) / TR_RED_THREADS));
+  B.part_stride = (P.n_part + 3) & ~3;
+  B.n_reduce_blocks = G;
   if (pmask)
     simt_launch(tr_mask_params_kernel, (unsigned)std::min((P.n_params + 255) / 256, 2 * num_sms), 256u, theta_p, pmask,
                 P.n_params);
   for (int l = 0; l < P.L; ++l) simt_launch(tr_fwd_kernel, (unsigned)G, (unsigned)TR_THREADS, P, B, bt, l);
   simt_launch(tr_loss_kernel, (unsigned)G, (unsigned)TR_THREADS, P, B, bt);
   for (int l = P.L - 1; l >= 0; --l) simt_launch(tr_bwd_kernel, (unsigned)G, (unsigned)TR_THREADS, P, B, bt, l);
-  simt_launch(tr_reduce_kernel, (unsigned)B.n_reduce_blocks, (unsigned)TR_RED_THREADS, P, B);
+  simt_launch(tr_reduce_kernel, (unsigned)G, (unsigned)TR_THREADS, P, B);
   const int64_t step = step0 + 1;
   TrOptim o;
   o.kind = opt_kind, o.lr = (float)lr, o.beta1 = (float)beta1, o.beta2 = (float)beta2, o.eps = (float)eps;

@@ -105,7 +105,8 @@ def simt_populate(tmp_path_factory):
 
 @pytest.mark.parametrize("name,sqrt_t,min_log_q", [("c2_realnvp_mlp", 1.0, None), ("c1_realnvp_2d", 1.0, None),
                                                    ("d5_realnvp_perm_tanh", 1.3, None), ("c2_realnvp_resnet", 1.0, -24.0),
-                                                   ("d6_nsf", 1.0, None), ("d8_maf", 1.0, None)])
+                                                   ("d6_nsf", 1.0, None), ("d8_maf", 1.0, None),
+                                                   ("d5_realnvp_mvn", 1.2, None)])
 def test_cuda_fused_populate_turn_matches_oracle(simt_populate, name, sqrt_t, min_log_q):
     """One fused turn of the generic kernel -- the CUDA sources of the Philox draw, the flow
     interpreter and the float64 tail, on the CPU -- against the float64 oracle driven by the
@@ -125,7 +126,8 @@ def test_cuda_fused_populate_turn_matches_oracle(simt_populate, name, sqrt_t, mi
     rng = np.random.default_rng(3)
     scale, shift = rng.uniform(0.8, 1.6, D), rng.uniform(-0.3, 0.3, D)
     lo, hi = np.full(D, -3.5), np.full(D, 3.5)
-    lpc, r_max = -D * np.log(7.0), 1.15 * np.sqrt(D) * sqrt_t
+    std = float(np.sqrt(sp.base_var))  # N(0, var I) base: z0 = std v, handed to the kernel as sqrt(T var)
+    lpc, r_max = -D * np.log(7.0), 1.15 * np.sqrt(D) * sqrt_t * std
     ops = np.ascontiguousarray(prog.ops, dtype=np.int32)
     blob = np.ascontiguousarray(prog.blob, dtype=np.float32)
     xp = np.full((n, D), np.nan, dtype=np.float32)
@@ -134,14 +136,14 @@ def test_cuda_fused_populate_turn_matches_oracle(simt_populate, name, sqrt_t, mi
     stats = np.array([-np.inf, 0.0])
     rc = simt_populate.simt_populate_draw(
         3, ops.ctypes.data, int(ops.shape[0]), blob.ctypes.data, D, sp.H, sp.activation, int(prog.final_buf),
-        float(prog.const_logdet), n, seed, offset, r_max, sqrt_t, scale.ctypes.data, shift.ctypes.data, lo.ctypes.data,
+        float(prog.const_logdet), n, seed, offset, r_max, sqrt_t * std, scale.ctypes.data, shift.ctypes.data, lo.ctypes.data,
         hi.ctypes.data, lpc, float("nan") if min_log_q is None else min_log_q, xp.ctypes.data, logq.ctypes.data,
         logw.ctypes.data, z.ctypes.data, stats.ctypes.data)
     assert rc == 0
-    z_ref = latent_normals(seed, offset + np.arange(n), D)
+    z_ref = latent_normals(seed, offset + np.arange(n), D) * std
     np.testing.assert_allclose(z, z_ref * sqrt_t, rtol=1e-5, atol=2e-5)  # the draw is the Philox stream
     kw = {k: v for k, v in dict(ftype=sp.ftype, net=sp.net, activation_name=cfg.get("activation", "relu"),
-                                hidden_features=sp.H).items()}
+                                hidden_features=sp.H, base_var=sp.base_var).items()}
     if sp.ftype == "nsf":
         kw.update(num_bins=sp.num_bins, tail_bound=sp.tail_bound)
     nf = NumpyFlow(sd, **kw)

@@ -48,7 +48,7 @@ def make_proposal(name, tmp_path, pool, lo=-10.0, hi=10.0, **kw):
     return prop, model, g, cfg, sd, live
 
 
-@pytest.mark.parametrize("name", ["c2_realnvp_mlp", "c1_realnvp_2d", "d5_realnvp_perm_tanh"])
+@pytest.mark.parametrize("name", ["c2_realnvp_mlp", "c1_realnvp_2d", "d5_realnvp_perm_tanh", "d5_realnvp_mvn"])
 def test_fused_turn_matches_numpy_restatement(name, tmp_path):
     from oracle.flow_numpy import NumpyFlow
     from oracle.philox_numpy import accept_uniform, latent_normals
@@ -65,11 +65,12 @@ def test_fused_turn_matches_numpy_restatement(name, tmp_path):
     logw = eng.d_logw[:n].cpu().numpy()
     stats = eng.d_stats.cpu().numpy()
     # (1) the latent draw is the Philox stream
-    z_ref = latent_normals(eng.seed, np.arange(n), d)
+    base_var = float((cfg.get("distribution_kwargs") or {}).get("var", 1.0))  # "mvn": N(0, var I) base
+    z_ref = latent_normals(eng.seed, np.arange(n), d) * np.sqrt(base_var)
     np.testing.assert_allclose(z, z_ref, atol=2e-5, rtol=1e-5)
     # (2) restate the turn in float64 from the same z
     nf = NumpyFlow(sd, ftype="realnvp", net=cfg.get("net", "resnet"),
-                   activation_name=cfg.get("activation", "relu"), hidden_features=cfg["n_neurons"])
+                   activation_name=cfg.get("activation", "relu"), hidden_features=cfg["n_neurons"], base_var=base_var)
     xp, lq = nf.sample_and_log_prob(z)
     x_ref = xp * prop.scale + prop.shift
     lq = lq - np.sum(np.log(np.abs(prop.scale)))
