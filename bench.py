@@ -38,6 +38,7 @@ POOL = 1_000_000
 FLOPS_PER_ROW = 47.7e3  # SURVEY.md 8(d), C2 RealNVP/MLP
 BYTES_PER_ROW = 68.0  # sample_and_log_prob, in-kernel RNG, z not returned
 SEED = 20251017
+TRAFFIC_BYTES = 36.85e6  # per launch of the dominant kernel, ncu --set full (profiles/)
 
 
 def load_c2():
@@ -145,13 +146,134 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------ ours
-def run_ours(args):
+def load_fixture(name):
+    g = np.load(os.path.join(REPO, "tests", "golden", f"{name}.npz"))
+    cfg = json.loads(str(g["flow_config"]))
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
+    return cfg, sd
+
+
+def build_proposal(fixture, model, live_s, local_rank, pool):
+    """B200FlowProposal on the reference-trained golden weights of ``fixture``."""
+    import torch
+
+    from nessai_b200.proposal import B200FlowProposal
+
+    cfg, sd = load_fixture(fixture)
+    torch.manual_seed(SEED)
+    prop = B200FlowProposal(
+        model, rng=np.random.default_rng(SEED), flow_config=cfg,
+        training_config=dict(device_tag=f"cuda:{local_rank}"),
+        output=tempfile.mkdtemp(), poolsize=pool, drawsize=pool, device_prior="auto",
+    )
+    prop.initialise()
+    prop.check_state(live_s)  # z-score statistics
+    prop.flow.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    prop.flow.model.eval()
+    return prop
+
+
+def quartiles(v):
+    q = np.percentile(np.asarray(v, dtype=np.float64), [25, 50, 75])
+    return float(q[1]), float(q[2] - q[0])
+
+
+def measure(prop, worst, pool, steps, warmup, repeats, world, dev, kernel_reps=20):
+    """One configuration through the three lenses of the bench line.  Every timed region is exactly
+    ``steps`` steps between two barrier + synchronize brackets; the region is repeated ``repeats``
+    times (>= 1 s of timed work in total) and the MEDIAN region is reported, with the inter-quartile
+    range beside it.  Returns a dict; collective-safe (every rank calls it with the same arguments)."""
     import torch
     import torch.distributed as dist
 
     from nessai_b200 import _lib
+
+    eng = prop._get_engine()
+    max_samples = pool
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        # populate()'s loop, device side only: the same turn loop as the e2e call
+        # (PopulateEngine.run) with the accepted records left in HBM
+        return eng.run(pool, pool, max_samples=max_samples, to_host=False)[1]
+
+    eng._ensure(1, pool, False)
+    for _ in range(warmup):
+        device_step()
+    # ---- device pipeline (value)
+    region_ms, region_rows = [], []
+    launches = 0
+    for r in range(repeats):
+        barrier()
+        _lib.reset_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        n_prop = 0
+        for _ in range(steps):
+            n_prop += device_step()
+        ev1.record()
+        barrier()
+        launches = _lib.launch_count()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        region_ms.append(float(ms.item()))
+        region_rows.append(n_prop)
+    rates = [n / (ms * 1e-3) for n, ms in zip(region_rows, region_ms)]
+    # ---- dominant kernel alone: the fused draw kernel, CUDA events on its stream
+    n_local = eng._shard(pool)[0]
+    kt = []
+    for _ in range(kernel_reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.draw_turn(pool)
+        b.record()
+        torch.cuda.synchronize()
+        kt.append(a.elapsed_time(b))
+    # ---- end to end through the plugin-facing call (host arrays in/out)
+    for _ in range(min(warmup, 2)):
+        prop.populate(worst, n_samples=pool, max_samples=max_samples)
+    e2e_rates, d2h, wall = [], 0, 0.0
+    for r in range(repeats):
+        barrier()
+        prop.population_time *= 0
+        n_prop = 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            if world > 1:
+                # align the ranks: between two populates every rank evaluates the pool's likelihood on
+                # its host, and the first collective of a populate would otherwise charge the skew of
+                # that phase to population_time (the reference's own timer, flowproposal.py:400,518)
+                dist.barrier()
+            prop.populate(worst, n_samples=pool, max_samples=max_samples)
+            n_prop += prop.n_proposed
+            d2h = prop.samples.nbytes
+        torch.cuda.synchronize()
+        wall += time.perf_counter() - t0
+        pop_s = torch.tensor([prop.population_time.total_seconds()], device=dev)
+        if world > 1:
+            dist.all_reduce(pop_s, op=dist.ReduceOp.MAX)
+        e2e_rates.append(n_prop / float(pop_s.item()))
+    v_med, v_iqr = quartiles(rates)
+    ms_med, _ = quartiles(region_ms)
+    e_med, e_iqr = quartiles(e2e_rates)
+    k_med, k_iqr = quartiles(kt)
+    return dict(value=v_med, value_iqr=v_iqr, ms_per_step=ms_med / steps, e2e=e_med, e2e_iqr=e_iqr,
+                kernel_ms=k_med, kernel_ms_iqr=k_iqr, n_local=n_local, launches=int(launches),
+                turns_per_step=int(round(region_rows[-1] / steps / pool)), d2h_bytes=int(d2h), repeats=repeats,
+                timed_s=dict(device=sum(region_ms) * 1e-3, e2e_wall=wall),
+                population_acceptance=prop.population_acceptance)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
     from nessai_b200.livepoint import numpy_array_to_live_points
-    from nessai_b200.proposal import B200FlowProposal
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -161,111 +283,36 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    g, cfg, sd = load_c2()
     live, _ = live_points()
     model = GaussianModel()
-    torch.manual_seed(SEED)
-    pool = args.pool * world  # weak scaling: 1e6 rows per GPU per turn
-    prop = B200FlowProposal(
-        model, rng=np.random.default_rng(SEED), flow_config=cfg,
-        training_config=dict(device_tag=f"cuda:{local_rank}"),
-        output=tempfile.mkdtemp(), poolsize=pool, drawsize=pool, device_prior="auto",
-    )
-    prop.initialise()
     live_s = numpy_array_to_live_points(live, model.names)
     live_s["logL"] = model.log_likelihood(live_s)
-    prop.check_state(live_s)  # z-score statistics
-    prop.flow.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
-    prop.flow.model.eval()
     worst = live_s[np.argmin(live_s["logL"])]
-    eng = prop._get_engine()
-    max_samples = pool
-
-    def device_step():
-        """populate()'s loop, device side only: the same turn loop as the e2e call
-        (PopulateEngine.run) with the accepted records left in HBM."""
-        _, n_prop, _ = eng.run(pool, pool, max_samples=max_samples, to_host=False)
-        return n_prop
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    eng._ensure(1, pool, False)
-    for _ in range(args.warmup):
-        device_step()
+    pool = args.pool * world  # weak scaling: 1e6 rows per GPU per turn
+    prop = build_proposal("c2_realnvp_mlp", model, live_s, local_rank, pool)
+    # >= 1000 timed steps (>= 1 s of timed work) per lens, in regions of exactly `steps` steps
+    repeats = int(min(200, max(5, -(-args.min_steps // args.steps))))
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    # ---- device-only timing (value) + dominant-kernel timing for the roofline
-    barrier()
-    _lib.reset_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    n_prop_total = 0
-    for _ in range(args.steps):
-        n_prop_total += device_step()
-    ev1.record()
-    barrier()
-    launches = _lib.launch_count()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    # dominant kernel alone: the fused draw kernel, CUDA events on its stream
-    n_local = eng._shard(pool)[0]
-    kt = []
-    for _ in range(max(args.steps, 3)):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        eng.draw_turn(pool)
-        b.record()
-        torch.cuda.synchronize()
-        kt.append(a.elapsed_time(b))
-    k_ms = float(np.mean(kt))
-    # ---- end to end through the plugin-facing call (host arrays in/out)
-    for _ in range(min(args.warmup, 2)):
-        prop.populate(worst, n_samples=pool, max_samples=max_samples)
-    barrier()
-    prop.population_time *= 0
-    t_e2e_prop, d2h = 0, 0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        if world > 1:
-            # align the ranks: between two populates every rank evaluates the pool's likelihood on
-            # its host, and the first collective of a populate would otherwise charge the skew of
-            # that phase to population_time (the reference's own timer, flowproposal.py:400,518)
-            dist.barrier()
-        prop.populate(worst, n_samples=pool, max_samples=max_samples)
-        t_e2e_prop += prop.n_proposed
-        d2h += prop.samples.nbytes
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    if os.environ.get("NB200_TIMING") and rank == 0:
-        print(f"[nb200 timing] last gather (all-gather + D2H) {1e3 * getattr(eng, 'last_gather_s', float('nan')):.2f} ms; "
-              f"population_time per populate {1e3 * prop.population_time.total_seconds() / args.steps:.2f} ms; "
-              f"phases of the last populate (ms): { {k: round(1e3 * v, 3) for k, v in getattr(eng, 'last_phase_s', {}).items()} }", file=sys.stderr)
-    pop_s = torch.tensor([prop.population_time.total_seconds()], device=dev)
-    if world > 1:
-        dist.all_reduce(pop_s, op=dist.ReduceOp.MAX)
-    pop_s = float(pop_s.item())
+    m = measure(prop, worst, pool, args.steps, args.warmup, repeats, world, dev)
     clk = clocks.stop() if rank == 0 else None
 
     if rank == 0:
         peaks, which = measured_peaks()
-        rows_s = n_prop_total / (ms_total * 1e-3)
-        k_rows_s = n_local / (k_ms * 1e-3)
+        k_rows_s = m["n_local"] / (m["kernel_ms"] * 1e-3)
         tf = k_rows_s * FLOPS_PER_ROW / 1e12
-        peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        # the dominant kernel is event-timed on its own (launch, synchronise): the burst figure is
+        # the denominator; the sustained one is quoted beside it
+        peak_tf = peaks["bf16_tflops"]
         out = {
             "metric": "proposed live-points/sec (FlowProposal.populate, 16-D, pool 1e6)",
-            "value": rows_s,
+            "value": m["value"],
             "unit": "rows/s",
             "n_gpus": world,
             "steps": args.steps,
             "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps,
+            "ms_per_step": m["ms_per_step"],
             "higher_is_better": True,
             "scaling": "weak",
             "vs_baseline": None,
@@ -275,24 +322,27 @@ def run_ours(args):
                 "workload": "C2: 16-D RealNVP 4x[64,64] MLP, poolsize=drawsize=1e6 per GPU, "
                             "zscore, constant-volume radius 0.95, uniform box prior",
                 "rows_per_turn_per_gpu": args.pool,
-                "turns_per_step": int(round(n_prop_total / args.steps / pool)),
+                "turns_per_step": m["turns_per_step"],
                 "l2": "each turn writes 80 MB of fresh outputs; L2 (126 MB) is flushed between steps by the accept kernels and the next turn; inputs are generated in-kernel",
                 "tc_kernel": bool(os.environ.get("NB200_DISABLE_TC", "0") != "1"),
+                "timing": f"value / e2e / kernel_ms are MEDIANS over {m['repeats']} timed regions of exactly "
+                          f"{args.steps} steps each (barrier + synchronize on both sides of every region, CUDA events, "
+                          "max over ranks); *_iqr = inter-quartile range over the regions",
                 "e2e_note": "n_proposed / population_time of B200FlowProposal.populate (max over ranks); N>1: ranks "
                             "aligned by a barrier before each populate, pool assembled in node-local shared pinned "
                             "host memory, d2h_bytes_per_step = bytes of the whole pool (each rank copies its own share)",
             },
+            "spread": {"value_iqr": m["value_iqr"], "e2e_iqr": m["e2e_iqr"], "kernel_ms_iqr": m["kernel_ms_iqr"],
+                       "regions": m["repeats"], "timed_s": m["timed_s"]},
             "clocks": clk,
             "e2e": {
-                "value": t_e2e_prop / pop_s,
+                "value": m["e2e"],
                 "unit": "rows/s",
                 "h2d_bytes_per_step": 4 * D * 8,
-                "d2h_bytes_per_step": d2h / args.steps,
-                "population_time_s": pop_s,
-                "wall_s": wall,
-                "population_acceptance": prop.population_acceptance,
+                "d2h_bytes_per_step": m["d2h_bytes"],
+                "population_acceptance": m["population_acceptance"],
             },
-            "gpu_launches": int(launches),
+            "gpu_launches": m["launches"],
             "roofline": {
                 "kernel": "populate_draw (fused draw + inverse flow + rescale + weights)",
                 "bound": "tensor",
@@ -300,13 +350,14 @@ def run_ours(args):
                 "peak": peak_tf,
                 "unit": "TFLOP/s",
                 "frac": tf / peak_tf,
-                "peak_source": f"{which} bf16 sustained",
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full,
-                # profiles/r1_ncu_populate_tcgen05_v7_fp16_split.txt): below the 80 MB the
-                # kernel writes because the tail of the output is still in the 126 MB L2 at kernel end
-                "traffic": 36.85e6,
-                "kernel_ms": k_ms,
-                "rows_per_launch": n_local,
+                "peak_source": f"{which} bf16 burst (kernel timed alone); sustained: "
+                               f"{peaks.get('bf16_tflops_sustained')} -> frac {tf / peaks.get('bf16_tflops_sustained', peak_tf):.4f}",
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/):
+                # below the 80 MB the kernel writes because the tail of the output is still in the
+                # 126 MB L2 at kernel end
+                "traffic": TRAFFIC_BYTES,
+                "kernel_ms": m["kernel_ms"],
+                "rows_per_launch": m["n_local"],
                 "hbm": {
                     "achieved": k_rows_s * BYTES_PER_ROW / 1e9,
                     "peak": peaks["hbm_gbs"],
@@ -316,16 +367,46 @@ def run_ours(args):
                 },
             },
         }
-        if world == 1 and not args.no_extras:
-            out["coupling_forward"] = coupling_roofline(dev, peaks, which)
-            out["variants"] = {"c2_resnet_default_conditioner": resnet_variant(prop, args.pool, dev),
-                               "c3_nsf_32d": nsf_variant(dev),
-                               "nonaffine_tail_and_accumulate": isolated_variants(args.pool)}
+    if world == 1 and not args.no_extras:
+        # nessai's DEFAULT conditioner (ResidualNet, 2 blocks of 64) through the same call
+        prop_r = build_proposal("c2_realnvp_resnet", model, live_s, local_rank, pool)
+        mr = measure(prop_r, worst, pool, args.steps, args.warmup, max(5, repeats // 4), world, dev, kernel_reps=10)
+        kr = mr["n_local"] / (mr["kernel_ms"] * 1e-3)
+        resnet = {
+            "workload": "C2': same as the headline with nessai's default ResidualNet conditioner (2 blocks x 64), "
+                        "through B200FlowProposal.populate",
+            "value": mr["value"], "value_iqr": mr["value_iqr"], "ms_per_step": mr["ms_per_step"],
+            "e2e": mr["e2e"], "e2e_iqr": mr["e2e_iqr"], "kernel_ms": mr["kernel_ms"],
+            "roofline": {"bound": "tensor", "achieved": kr * 146e3 / 1e12, "peak": peaks["bf16_tflops"],
+                         "unit": "TFLOP/s", "frac": kr * 146e3 / 1e12 / peaks["bf16_tflops"], "flops_per_row": 146e3,
+                         "peak_source": f"{which} bf16 burst"},
+        }
+        if not args.no_cpu_baseline:
+            resnet["cpu_baseline"] = cpu_baseline(threads=1, pool=min(args.cpu_pool, 200_000), fixture="c2_realnvp_resnet")
+        out["coupling_forward"] = coupling_roofline(dev, peaks, which)
+        out["variants"] = {"c2_resnet_default_conditioner": resnet,
+                           "train": train_variant("ours"),
+                           "c3_nsf_32d": nsf_variant(dev),
+                           "nonaffine_tail_and_accumulate": isolated_variants(args.pool)}
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(threads=1, pool=args.cpu_pool)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_variant(impl):
+    """FlowModel.train on the C2 live points (scripts/train_bench.py) in a subprocess."""
+    try:
+        res = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "train_bench.py"), impl],
+                             capture_output=True, text=True, timeout=600, cwd=REPO)
+        lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+        if res.returncode == 0 and lines:
+            return json.loads(lines[-1])
+        return {"error": f"exit {res.returncode}: {(res.stderr or res.stdout)[-400:]}"}
+    except Exception as e:  # noqa: BLE001 - a variant must never break the bench line
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def coupling_roofline(dev, peaks, which, n=8_000_000):
@@ -359,47 +440,6 @@ def coupling_roofline(dev, peaks, which, n=8_000_000):
         "frac": gbs / peaks["hbm_gbs"], "peak_source": f"{which} copy bandwidth",
         "bytes_per_row": 196, "rows_per_launch": n, "kernel_ms": ms,
         "note": "includes the two torch.empty output allocations of the Python wrapper",
-    }
-
-
-def resnet_variant(prop, pool, dev):
-    """BASELINE.json's "4x[64,64] conditioner" is ambiguous between net="mlp" (the headline
-    above) and nessai's DEFAULT net="resnet" (2 residual blocks of width 64): the same fused
-    draw turn timed on the resnet flow (reference-trained golden weights), device only."""
-    import torch
-
-    from nessai_b200.flowmodel import B200FlowModel
-    from nessai_b200.proposal import PopulateEngine
-
-    g = np.load(os.path.join(REPO, "tests", "golden", "c2_realnvp_resnet.npz"))
-    cfg = json.loads(str(g["flow_config"]))
-    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
-    fm = B200FlowModel(flow_config=cfg, training_config=dict(device_tag=str(dev)), output=tempfile.mkdtemp())
-    fm.initialise()
-    fm.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
-    fm.model.eval()
-    e0 = prop._get_engine()
-    eng = PopulateEngine(fm, e0.names, e0.row_dtype)
-    eng.configure(*e0._cfg_host, e0.log_prior_const, e0.r_max, e0.sqrt_t)
-    eng._ensure(pool, pool, False)
-    for _ in range(3):
-        eng.draw_turn(pool)
-    torch.cuda.synchronize()
-    kt = []
-    for _ in range(5):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        eng.draw_turn(pool)
-        b.record()
-        torch.cuda.synchronize()
-        kt.append(a.elapsed_time(b))
-    ms = float(np.mean(kt))
-    return {
-        "kernel": "populate_draw, ResidualNet conditioner (2 tcgen05 passes of 2 layers)",
-        "kernel_ms": ms,
-        "rows_per_s": pool / (ms * 1e-3),
-        "tflops_algorithmic": pool / (ms * 1e-3) * 146e3 / 1e12,
-        "flops_per_row": 146e3,
     }
 
 
@@ -450,7 +490,7 @@ def nsf_variant(dev, n=2_000_000):
 
 
 # ------------------------------------------------------------------------- reference
-def reference_populate(threads, pool, steps=1, warmup=0):
+def reference_populate(threads, pool, steps=1, warmup=0, fixture="c2_realnvp_mlp"):
     """Time the UNMODIFIED reference's FlowProposal.populate on the host cores."""
     import oracle.refenv as refenv
 
@@ -461,7 +501,7 @@ def reference_populate(threads, pool, steps=1, warmup=0):
     from nessai.proposal import FlowProposal
 
     torch.set_num_threads(threads)
-    g, cfg, sd = load_c2()
+    cfg, sd = load_fixture(fixture)
     live, cov = live_points()
 
     class RefModel(Model):
@@ -520,21 +560,21 @@ def reference_populate(threads, pool, steps=1, warmup=0):
     return n_prop, pop_s, wall, prop.population_acceptance
 
 
-def cpu_baseline(threads, pool):
+def cpu_baseline(threads, pool, fixture="c2_realnvp_mlp"):
     import oracle.refenv as refenv
 
     if not refenv.reference_available():
         return {"value": None, "unit": "rows/s", "cores": threads, "kind": "reference",
                 "sample": "baseline/_ref not present"}
-    n_prop, pop_s, wall, acc = reference_populate(threads, pool, steps=1, warmup=0)
+    n_prop, pop_s, wall, acc = reference_populate(threads, pool, steps=1, warmup=1, fixture=fixture)
     return {
         "value": n_prop / pop_s,
         "unit": "rows/s",
         "cores": threads,
         "kind": "reference",
         "sample": f"one populate(n_samples={pool}, drawsize={pool}) = {n_prop} proposed rows in "
-                  f"{pop_s:.1f} s; unmodified nessai FlowProposal (baseline/_ref) on the restated "
-                  "glasflow.nflows shim (oracle/shims), same weights/live points as the GPU arm",
+                  f"{pop_s:.1f} s after one warm-up populate; unmodified nessai FlowProposal (baseline/_ref) on the "
+                  f"restated glasflow.nflows shim (oracle/shims), {fixture} weights / live points as the GPU arm",
         "population_acceptance": acc,
     }
 
@@ -567,8 +607,8 @@ def run_reference(args):
         "dtype": "f32",
         "data": "synthetic",
         "config": {
-            "workload": "C2: 16-D RealNVP 4x[64,64] MLP, zscore, constant-volume radius 0.95, "
-                        f"bounded sample: poolsize=drawsize={pool} per populate() (linear in rows)",
+            "workload": "C2: 16-D RealNVP 4x[64,64] MLP, zscore, constant-volume radius 0.95, uniform box prior, "
+                        f"poolsize=drawsize={pool} per populate()",
         },
         "cpu_baseline": {
             "value": v, "unit": "rows/s", "cores": threads, "kind": "reference",
@@ -578,6 +618,8 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "population_acceptance": acc,
     }
+    if not args.no_extras:
+        out["variants"] = {"train": train_variant("reference")}
     print(json.dumps(out), flush=True)
 
 
@@ -588,7 +630,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pool", type=int, default=POOL)
-    ap.add_argument("--cpu-pool", type=int, default=200_000)
+    ap.add_argument("--cpu-pool", type=int, default=1_000_000,
+                    help="poolsize = drawsize of the reference arm and of the 1-thread cpu_baseline (the GPU arm's 1e6)")
+    ap.add_argument("--min-steps", type=int, default=1000,
+                    help="timed steps per lens in total (regions of --steps steps are repeated up to this)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the secondary measurements (coupling roofline, ResidualNet variant): "
