@@ -367,6 +367,10 @@ def run_ours(args):
                 },
             },
         }
+    if world > 1 and not args.no_extras:
+        extras = multi_gpu_extras(prop, model, live_s, worst, args, pool, repeats, world, rank, local_rank, dev)
+        if rank == 0:
+            out.update(extras)
     if world == 1 and not args.no_extras:
         # nessai's DEFAULT conditioner (ResidualNet, 2 blocks of 64) through the same call
         prop_r = build_proposal("c2_realnvp_resnet", model, live_s, local_rank, pool)
@@ -394,6 +398,57 @@ def run_ours(args):
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_gpu_extras(prop, model, live_s, worst, args, pool, repeats, world, rank, local_rank, dev):
+    """N > 1 only (collective: every rank calls it).  Beside the weak-scaling headline:
+    ``strong``          one pool of ``args.pool`` rows per turn partitioned over the N GPUs (SURVEY 8e);
+    ``nccl_allgather``  the headline workload with the accepted records all-gathered over NCCL / NVLink
+                        (north_star's data plane) instead of the node-local shared host pool;
+    ``parity_vs_n1``    the pool the N ranks return against the pool ONE rank returns for the same seed
+                        (the claim that the pool does not depend on the number of GPUs), byte for byte."""
+    import torch
+    import torch.distributed as dist
+
+    from nessai_b200.proposal import PopulateEngine
+
+    few = max(5, repeats // 4)
+    out = {}
+    prop_s = build_proposal("c2_realnvp_mlp", model, live_s, local_rank, args.pool)
+    ms = measure(prop_s, worst, args.pool, args.steps, args.warmup, few, world, dev, kernel_reps=5)
+    out["strong"] = {"workload": f"ONE pool of {args.pool} rows per turn partitioned over {world} GPUs", "scaling": "strong",
+                     "value": ms["value"], "value_iqr": ms["value_iqr"], "ms_per_step": ms["ms_per_step"],
+                     "e2e": ms["e2e"], "e2e_iqr": ms["e2e_iqr"], "rows_per_gpu_per_turn": ms["n_local"],
+                     "kernel_ms": ms["kernel_ms"]}
+    del prop_s
+    eng = prop._get_engine()
+    # the accepted records cross NVLink: one all_gather_into_tensor per populate (gather_records)
+    eng._pool_ok, eng._pool = False, None
+    mg = measure(prop, worst, pool, args.steps, args.warmup, few, world, dev, kernel_reps=5)
+    out["nccl_allgather"] = {"workload": "headline workload, accepted records all-gathered over NCCL (no shared host pool)",
+                             "value": mg["value"], "ms_per_step": mg["ms_per_step"], "e2e": mg["e2e"], "e2e_iqr": mg["e2e_iqr"]}
+    eng._pool_ok = None  # back to the shared host pool
+    # same seed, N ranks vs one rank
+    seed = 424242
+    eng.set_seed(seed)
+    dist.barrier()
+    rows_n, p_n, a_n = eng.run(pool, pool, max_samples=pool)
+    rows_n = np.array(rows_n, copy=True)
+    verdict = None
+    if rank == 0:
+        e1 = PopulateEngine(prop.flow, eng.names, eng.row_dtype)
+        e1.rank, e1.world, e1.group = 0, 1, None
+        e1.configure(*eng._cfg_host, eng.log_prior_const, eng.r_max, eng.sqrt_t)
+        e1.set_seed(seed)
+        rows_1, p_1, a_1 = e1.run(pool, pool, max_samples=pool)
+        verdict = {"seed": seed, "rows_n": int(len(rows_n)), "rows_1": int(len(rows_1)),
+                   "n_proposed": [int(p_n), int(p_1)], "n_accepted": [int(a_n), int(a_1)],
+                   "pool_bytes_equal": bool(len(rows_n) == len(rows_1) and rows_n.tobytes() == rows_1.tobytes())}
+        del e1
+    torch.cuda.synchronize()
+    dist.barrier()
+    out["parity_vs_n1"] = verdict
+    return out
 
 
 def train_variant(impl):

@@ -553,8 +553,11 @@ extern "C" int nb200_reparam_tail(int64_t n, int D, const float* d_xp, const int
   int dev = 0, sms = 148;
   CUDA_OK(cudaGetDevice(&dev));
   CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = (int)std::min<int64_t>((n + TAIL_THREADS - 1) / TAIL_THREADS, (int64_t)sms * 8);
-  reparam_tail_kernel<<<grid, TAIL_THREADS, 0, (cudaStream_t)stream>>>(
+  const size_t smem = tail_smem_bytes(D);
+  if (int rc = prep_kernel(reparam_tail_kernel, smem)) return rc;
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 4096)));
+  const int grid = (int)std::min<int64_t>((n + TAIL_THREADS - 1) / TAIL_THREADS, (int64_t)sms * per_sm);
+  reparam_tail_kernel<<<grid, TAIL_THREADS, smem, (cudaStream_t)stream>>>(
       n, D, d_xp, d_kind, d_src, d_pre_scale, d_pre_shift, d_scale, d_shift, d_lo, d_hi,
       isnan(log_prior_const) ? 0.0 : log_prior_const, isnan(min_log_q) ? -INFINITY : min_log_q,
       d_logq, d_logw, d_x64, d_stats);

@@ -142,11 +142,24 @@ NB200_HD double tail_log_affine_sum(int D, const int32_t* kind, const double* pr
 }
 
 #ifdef __CUDACC__
-#define TAIL_THREADS 256
+#define TAIL_THREADS 128
 #define TAIL_MAXD 64
 
-// One thread per row: 4 D + 8 bytes in, 8 D + 16 bytes out per row (HBM-bound, a fraction of
-// the draw kernel's time).  The per-feature constants sit in shared memory.
+// Dynamic shared memory of the kernel: per warp one tile of 32 rows, x' (floats, row stride D + 1)
+// and x (doubles, row stride D + 1) -- the odd strides keep a warp's per-row accesses conflict-free.
+__host__ __device__ inline size_t tail_smem_bytes(int D) {
+  return (size_t)(TAIL_THREADS / 32) * 32 * (D + 1) * (sizeof(double) + sizeof(float)) + 16;
+}
+#ifdef NB200_SIMT_SHIM
+static unsigned char* const tail_smem_dyn = simt::dynamic_smem;
+#else
+extern __shared__ __align__(16) unsigned char tail_smem_dyn[];
+#endif
+
+// One thread per row; a warp moves its 32 rows between global and shared memory cooperatively, so
+// that every global access is a run of consecutive addresses: 4 D + 8 bytes in, 8 D + 16 bytes out
+// per row (HBM class; the float64 transcendental functions of the non-identity kinds share the
+// time).  The per-feature constants sit in shared memory.
 __global__ void __launch_bounds__(TAIL_THREADS)
 reparam_tail_kernel(int64_t n, int D, const float* __restrict__ xp, const int32_t* __restrict__ kind,
                     const int32_t* __restrict__ src, const double* __restrict__ pre_a, const double* __restrict__ pre_b,
@@ -171,21 +184,48 @@ reparam_tail_kernel(int64_t n, int D, const float* __restrict__ xp, const int32_
   }
   if (threadIdx.x == 0) lss_s = tail_log_affine_sum(D, kind, pre_a, scale);
   __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ld = D + 1;
+  double* xt = reinterpret_cast<double*>(tail_smem_dyn) + (size_t)warp * 32 * ld;
+  float* pt = reinterpret_cast<float*>(reinterpret_cast<double*>(tail_smem_dyn) + (size_t)(TAIL_THREADS / 32) * 32 * ld) +
+              (size_t)warp * 32 * ld;
   double vmax = -INFINITY, vcount = 0.0;
-  for (int64_t row = (int64_t)blockIdx.x * TAIL_THREADS + threadIdx.x; row < n;
-       row += (int64_t)gridDim.x * TAIL_THREADS) {
-    // x is written straight to global memory (every row: the accept kernel only reads the
-    // rows it keeps, and a device likelihood may read them all)
-    double lq, lw;
-    const bool ok = tail_row(D, xp + row * D, k_s, src_s, c_s + 4 * TAIL_MAXD, c_s + 5 * TAIL_MAXD, c_s,
-                             c_s + TAIL_MAXD, c_s + 2 * TAIL_MAXD, c_s + 3 * TAIL_MAXD, lss_s,
-                             log_prior_const, min_log_q, logq[row], x64 + row * D, lq, lw);
-    logq[row] = lq;
-    logw[row] = lw;
+  const int64_t n_chunks = (n + 31) / 32;
+  for (int64_t chunk = (int64_t)blockIdx.x * (TAIL_THREADS / 32) + warp; chunk < n_chunks;
+       chunk += (int64_t)gridDim.x * (TAIL_THREADS / 32)) {
+    const int64_t row0 = chunk * 32, row = row0 + lane;
+    const int rows = (int)min((int64_t)32, n - row0);
+    // x' of the chunk: consecutive lanes read consecutive floats
+    const float* gsrc = xp + row0 * D;
+    for (int i = lane; i < rows * D; i += 32) {
+      const int r = i / D;
+      pt[r * ld + (i - r * D)] = gsrc[i];
+    }
+    const double lq_in = row < n ? logq[row] : NAN;
+    __syncwarp();
+    bool ok = false;
+    double lq = NAN, lw = NAN;
+    if (row < n)
+      ok = tail_row(D, pt + lane * ld, k_s, src_s, c_s + 4 * TAIL_MAXD, c_s + 5 * TAIL_MAXD, c_s, c_s + TAIL_MAXD,
+                    c_s + 2 * TAIL_MAXD, c_s + 3 * TAIL_MAXD, lss_s, log_prior_const, min_log_q, lq_in,
+                    xt + lane * ld, lq, lw);
+    __syncwarp();
+    // x of every row (the accept kernel only reads the rows it keeps, a device likelihood may
+    // read them all): consecutive lanes write consecutive doubles
+    double* gdst = x64 + row0 * D;
+    for (int i = lane; i < rows * D; i += 32) {
+      const int r = i / D;
+      gdst[i] = xt[r * ld + (i - r * D)];
+    }
+    if (row < n) {
+      logq[row] = lq;
+      logw[row] = lw;
+    }
     if (ok) {
       vmax = fmax(vmax, lw);
       vcount += 1.0;
     }
+    __syncwarp();
   }
   // same publication as the draw kernels (populate_common.cuh: populate_publish)
   for (int o = 16; o > 0; o >>= 1) {

@@ -108,15 +108,38 @@ class B200ImportanceFlowModel(B200FlowModel):
         out = torch.empty((n_models, per), device=dev, dtype=torch.float32)
         if hi > lo:
             xd = self._device_rows(x[lo:hi], self.model)
-            for i, m in enumerate(self.models[:n_models]):
+            models = self.models[:n_models]
+            for m in models:
                 if m.training:
                     m.eval()
-                out[i, : hi - lo] = m._forward(xd)[2]
+                m._ready()  # fold + upload outside the fan-out below
+            # The K flows are independent and each leaves most SMs idle on a level's worth of rows:
+            # fan the K forward kernels out over a few streams (x stays resident, one weight image
+            # per flow), then join -- the kernels of different flows overlap on the device.
+            main = torch.cuda.current_stream(dev)
+            streams = self._lp_streams(dev, min(n_models, 8))
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for i, m in enumerate(models):
+                st = streams[i % len(streams)]
+                if i < len(streams):
+                    st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    out[i, : hi - lo] = m._forward(xd)[2]
+            for st in streams:
+                main.wait_stream(st)
+            xd.record_stream(main)
         if world > 1:
             full = torch.empty((world, n_models, per), device=dev, dtype=torch.float32)
             dist.all_gather_into_tensor(full, out)
             out = full.permute(1, 0, 2).reshape(n_models, world * per)[:, :N]
         return out.t().contiguous().cpu().numpy().astype(np.float64)
+
+    def _lp_streams(self, dev, n):
+        cur = getattr(self, "_streams", None)
+        if cur is None or len(cur) < n or cur[0].device != dev:
+            self._streams = cur = [torch.cuda.Stream(device=dev) for _ in range(n)]
+        return cur[:n]
 
     def sample_ith(self, i, N=1):
         """importance.py:131-142."""
@@ -170,7 +193,7 @@ class B200ImportanceFlowModel(B200FlowModel):
 
     def __getstate__(self):
         d = self.__dict__
-        exclude = {"models", "_optimiser", "flow_config", "_fused", "_fused_key", "_pending_train_loss", "scheduler"}
+        exclude = {"models", "_optimiser", "flow_config", "_fused", "_fused_key", "_pending_train_loss", "scheduler", "_streams"}
         state = {k: d[k] for k in d.keys() - exclude}
         state["initialised"] = False
         state["models"] = None

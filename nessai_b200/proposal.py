@@ -320,6 +320,13 @@ class PopulateEngine:
         self.likelihood = likelihood
         self.log_l_threshold = -float("inf") if log_l_threshold is None else float(log_l_threshold)
 
+    def set_seed(self, seed: int) -> None:
+        """Restart the Philox streams: ``seed`` keys them, the row counter starts at zero (the
+        cached argument lists of the draw / accept calls carry the seed, so they are dropped)."""
+        self.seed = int(seed)
+        self._turn_rows = 0
+        self._draw_key = self._accept_key = None
+
     def _seed(self):
         if self.seed is None:
             s = torch.randint(0, 2**62, (1,), dtype=torch.int64)

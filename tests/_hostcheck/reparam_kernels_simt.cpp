@@ -4,6 +4,7 @@
 // statistics) is executed and compared with the numpy oracle on a machine without a GPU.
 // (its own namespace: reparam_host.cpp, linked into the same library for nb200_host_erfcinv,
 // compiles the header's host flavour under the name nb200)
+#define NB200_SIMT_SHIM 1
 #define nb200 nb200_simt
 #include "simt_shim.h"
 

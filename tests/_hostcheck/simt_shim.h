@@ -46,6 +46,7 @@ inline std::mutex atomic_mutex;
 }  // namespace simt
 
 inline void __syncthreads() { simt::block_barrier->arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_barrier[threadIdx.x / simt::kWarp]->arrive_and_wait(); }
 
 inline double __shfl_xor_sync(unsigned, double v, int lane_mask) {
   const unsigned tid = threadIdx.x, warp = tid / simt::kWarp;

@@ -187,6 +187,13 @@ def main():
         dict(n_inputs=6, n_neurons=16, n_blocks=3, n_layers=2, ftype="nsf"),
         rosenbrock_like(2000, 6, rng), 512, 60, tmp,
     )
+    # C3 at the configuration's own size (BASELINE.json configs[2]): 32-D neural-spline flow, 6 coupling
+    # layers, ResidualNet(64), trained by the reference on a curved 32-D live-point set
+    make(
+        "c3_nsf_trained",
+        dict(n_inputs=32, n_neurons=64, n_blocks=6, n_layers=2, ftype="nsf"),
+        rosenbrock_like(2000, 32, np.random.default_rng(SEED + 32)), 512, 80, tmp,
+    )
     # masked autoregressive flow: MADE with residual blocks, reverse permutations
     make(
         "d8_maf",
