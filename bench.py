@@ -78,6 +78,45 @@ class GaussianModel:
         return self._norm - 0.5 * np.einsum("...i,ij,...j->...", a, self._icov, a)
 
 
+def rosenbrock_live_points(n=2000, d=32):
+    """The curved live-point set the C3 fixture was trained on (tests/golden/make_golden.py:
+    rosenbrock_chain with default_rng(SEED + 32)): the ridge x_{i+1} ~ x_i^2 around (1, ..., 1)."""
+    rng = np.random.default_rng(SEED + 32)
+    x = np.empty((n, d))
+    x[:, 0] = rng.normal(1.0, 0.3, n)
+    for i in range(1, d):
+        x[:, i] = 0.25 * x[:, i - 1] ** 2 + 0.75 + rng.normal(0, 0.1, n)
+    return np.clip(x, -4.9, 4.9)
+
+
+class RosenbrockModel:
+    """32-D Rosenbrock likelihood, uniform prior on [-5, 5]^32 (/root/reference/examples/rosenbrock.py:20-45)."""
+
+    def __init__(self, d=32):
+        self.names = [f"x{i}" for i in range(d)]
+        self.bounds = {n: [-5.0, 5.0] for n in self.names}
+        self.d = d
+
+    def _arr(self, x):
+        return np.stack([x[n] for n in self.names], axis=-1)
+
+    def log_prior(self, x):
+        a = self._arr(x)
+        lp = np.full(a.shape[0] if a.ndim > 1 else 1, -self.d * np.log(10.0))
+        return np.where(np.all((a >= -5) & (a <= 5), axis=-1), lp, -np.inf)
+
+    def log_likelihood(self, x):
+        a = self._arr(x)
+        return -np.sum(100.0 * (a[..., 1:] - a[..., :-1] ** 2.0) ** 2.0 + (1.0 - a[..., :-1]) ** 2.0, axis=-1)
+
+
+def problem(fixture):
+    """(model, raw live points) of a fixture's configuration."""
+    if fixture.startswith("c3"):
+        return RosenbrockModel(32), rosenbrock_live_points()
+    return GaussianModel(), live_points()[0]
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
 
@@ -266,6 +305,7 @@ def measure(prop, worst, pool, steps, warmup, repeats, world, dev, kernel_reps=2
                 kernel_ms=k_med, kernel_ms_iqr=k_iqr, n_local=n_local, launches=int(launches),
                 turns_per_step=int(round(region_rows[-1] / steps / pool)), d2h_bytes=int(d2h), repeats=repeats,
                 timed_s=dict(device=sum(region_ms) * 1e-3, e2e_wall=wall),
+                regions_value=[float(f"{v:.4g}") for v in rates], regions_e2e=[float(f"{v:.4g}") for v in e2e_rates],
                 population_acceptance=prop.population_acceptance)
 
 
@@ -333,7 +373,8 @@ def run_ours(args):
                             "host memory, d2h_bytes_per_step = bytes of the whole pool (each rank copies its own share)",
             },
             "spread": {"value_iqr": m["value_iqr"], "e2e_iqr": m["e2e_iqr"], "kernel_ms_iqr": m["kernel_ms_iqr"],
-                       "regions": m["repeats"], "timed_s": m["timed_s"]},
+                       "regions": m["repeats"], "timed_s": m["timed_s"],
+                       "regions_value": m["regions_value"], "regions_e2e": m["regions_e2e"]},
             "clocks": clk,
             "e2e": {
                 "value": m["e2e"],
@@ -390,7 +431,8 @@ def run_ours(args):
         out["coupling_forward"] = coupling_roofline(dev, peaks, which)
         out["variants"] = {"c2_resnet_default_conditioner": resnet,
                            "train": train_variant("ours"),
-                           "c3_nsf_32d": nsf_variant(dev),
+                           "c3": c3_block(args, local_rank, dev, repeats, peaks, which),
+                           "c5": c5_variant("ours"),
                            "nonaffine_tail_and_accumulate": isolated_variants(args.pool)}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
@@ -448,7 +490,84 @@ def multi_gpu_extras(prop, model, live_s, worst, args, pool, repeats, world, ran
     torch.cuda.synchronize()
     dist.barrier()
     out["parity_vs_n1"] = verdict
+    out["c5"] = c5_variant("ours", world)  # collective: log_prob_all shards its rows over the ranks
     return out
+
+
+def c5_levels(ModelClass, levels, n_train, n_draw, training_config, dev_sync=None):
+    """Config C5 (BASELINE.json configs[4]): the flow work of the importance nested sampler, level by
+    level as /root/reference/src/nessai/proposal/importance.py:250-440 drives it: add a flow
+    (importance.py:80-99 of the flow model), train it on the level's weighted samples, draw the next
+    level's samples from it, and evaluate EVERY stored flow on ALL samples drawn so far
+    (``log_prob_all``: the meta-proposal density).  The same loop runs either arm: ``ModelClass`` is
+    ``B200ImportanceFlowModel`` or the reference's ``ImportanceFlowModel``.  Returns per-phase seconds."""
+    import torch
+
+    sync = dev_sync or (lambda: None)
+    torch.manual_seed(SEED)
+    rng = np.random.default_rng(SEED)
+    fm = ModelClass(flow_config=dict(n_inputs=D, n_neurons=64, n_blocks=4, n_layers=2),
+                    training_config=dict(training_config), output=tempfile.mkdtemp(), rng=rng)
+    fm.initialise()
+    idx = np.arange(D)
+    cov = 0.5 ** np.abs(idx[:, None] - idx[None, :])
+    x_all = rng.multivariate_normal(np.zeros(D), 4.0 * cov, size=n_train)  # level 0: a broad prior-like set
+    t = dict(train=0.0, draw=0.0, log_prob_all=0.0)
+    rows_evaluated = 0
+    for level in range(levels):
+        fm.add_new_flow(reset=True)
+        cur = x_all[-n_train:]
+        w = rng.uniform(0.5, 1.5, size=len(cur))
+        xs = (cur - cur.mean(0)) / cur.std(0)
+        sync()
+        t0 = time.perf_counter()
+        fm.train(xs, weights=w, max_epochs=50, patience=50, plot=False,
+                 output=os.path.join(fm.output, f"level_{level}"))
+        sync()
+        t1 = time.perf_counter()
+        new = fm.sample_ith(level, N=n_draw)
+        sync()
+        t2 = time.perf_counter()
+        x_all = np.concatenate([x_all, np.asarray(new, dtype=np.float64)])
+        lp = fm.log_prob_all(x_all)
+        sync()
+        t3 = time.perf_counter()
+        assert lp.shape == (len(x_all), level + 1)
+        rows_evaluated += lp.size
+        if level:  # the first level carries the one-off costs (allocations, module load)
+            t["train"] += t1 - t0
+            t["draw"] += t2 - t1
+            t["log_prob_all"] += t3 - t2
+    n = max(levels - 1, 1)
+    return {"levels_timed": n, "train_s_per_level": t["train"] / n, "draw_s_per_level": t["draw"] / n,
+            "log_prob_all_s_per_level": t["log_prob_all"] / n, "level_s": sum(t.values()) / n,
+            "n_train": n_train, "n_draw": n_draw, "flow_evaluations_total": int(rows_evaluated),
+            "finite_fraction_last": float(np.isfinite(lp).mean())}
+
+
+def c5_variant(impl, world=1):
+    """``variants.c5``: seconds per level of the importance sampler's flow work (see c5_levels)."""
+    try:
+        if impl == "reference":
+            import oracle.refenv as refenv
+
+            refenv.activate()
+            from nessai.flowmodel.importance import ImportanceFlowModel
+
+            out = c5_levels(ImportanceFlowModel, 3, 2000, 20_000, dict())
+            out["note"] = "reference ImportanceFlowModel on the host cores; bounded: 3 levels, 2e4 draws per level"
+            return out
+        import torch
+
+        from nessai_b200.importance import B200ImportanceFlowModel
+
+        out = c5_levels(B200ImportanceFlowModel, 9, 2000, 200_000,
+                        dict(device_tag=f"cuda:{torch.cuda.current_device()}"), dev_sync=torch.cuda.synchronize)
+        out["note"] = (f"B200ImportanceFlowModel, 9 levels, 2e5 draws per level, 16-D RealNVP (default ResidualNet conditioner); "
+                       f"log_prob_all rows sharded over {world} rank(s), training replicated")
+        return out
+    except Exception as e:  # noqa: BLE001 - a variant must never break the bench line
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def train_variant(impl):
@@ -513,35 +632,39 @@ def isolated_variants(pool):
         return {"error": f"{type(e).__name__}: {e}"}
 
 
-def nsf_variant(dev, n=2_000_000):
-    """Config C3 (32-D NSF, 6 layers, ResidualNet 64, 8 bins): sample_and_log_prob of a pool of
-    2e6 rows through the tcgen05 spline kernel (csrc/flow_tc_nsf.cuh: one launch per layer, row
-    state in TMEM, randomly initialised flow)."""
-    import torch
+def c3_block(args, local_rank, dev, repeats, peaks, which):
+    """Config C3 (BASELINE.json configs[2]): 32-D Rosenbrock, neural-spline flow with 6 coupling
+    layers (ResidualNet 64, 8 bins) TRAINED BY THE REFERENCE on the live points
+    (tests/golden/c3_nsf_trained.npz), ``populate(n_samples=2e6)`` through B200FlowProposal --
+    the same three lenses as the headline, plus the reference's CPU populate on a bounded pool."""
+    from nessai_b200.livepoint import numpy_array_to_live_points
 
-    from nessai_b200.flowmodel import B200FlowModel
-
-    torch.manual_seed(3)
-    fm = B200FlowModel(flow_config=dict(n_inputs=32, ftype="nsf", n_blocks=6, n_layers=2, n_neurons=64),
-                       training_config=dict(device_tag=str(dev)), output=tempfile.mkdtemp())
-    fm.initialise()
-    fm.model.eval()
-    z = torch.randn(n, 32, device=dev)
-    for _ in range(2):
-        fm.model._inverse(z)
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(3):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        fm.model._inverse(z)
-        b.record()
-        torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
-    ms = float(np.mean(ts))
-    return {"kernel": "flow_tc_nsf_kernel (tcgen05 conditioner + fused RQ-spline epilogue, 6 launches)", "kernel_ms": ms,
-            "rows_per_s": n / (ms * 1e-3), "rows": n, "flops_per_row": 0.50e6,
-            "tflops_algorithmic": n / (ms * 1e-3) * 0.50e6 / 1e12}
+    pool = args.c3_pool
+    model, live = problem("c3_nsf_trained")
+    live_s = numpy_array_to_live_points(live, model.names)
+    live_s["logL"] = model.log_likelihood(live_s)
+    worst = live_s[np.argmin(live_s["logL"])]
+    prop = build_proposal("c3_nsf_trained", model, live_s, local_rank, pool)
+    m = measure(prop, worst, pool, max(2, args.steps // 4), 3, max(3, repeats // 10), 1, dev, kernel_reps=5)
+    k_rows_s = m["n_local"] / (m["kernel_ms"] * 1e-3)
+    tf = k_rows_s * 0.50e6 / 1e12
+    out = {
+        "workload": f"C3: 32-D Rosenbrock, reference-trained NSF (6 coupling layers, ResidualNet 64, 8 bins), "
+                    f"poolsize=drawsize={pool}, zscore, constant-volume radius 0.95, uniform box prior",
+        "value": m["value"], "value_iqr": m["value_iqr"], "unit": "rows/s", "ms_per_step": m["ms_per_step"],
+        "turns_per_step": m["turns_per_step"], "gpu_launches": m["launches"],
+        "e2e": {"value": m["e2e"], "iqr": m["e2e_iqr"], "unit": "rows/s", "h2d_bytes_per_step": 4 * 32 * 8,
+                "d2h_bytes_per_step": m["d2h_bytes"], "population_acceptance": m["population_acceptance"]},
+        "roofline": {"kernel": "flow_tc_nsf_kernel x 6 (one launch per coupling layer: tcgen05 conditioner + RQ-spline epilogue)",
+                     "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": tf / peaks["bf16_tflops"], "peak_source": f"{which} bf16 burst", "flops_per_row": 0.50e6,
+                     "kernel_ms": m["kernel_ms"], "rows_per_launch": m["n_local"], "traffic": None,
+                     "hbm": {"achieved": k_rows_s * 260.0 / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": k_rows_s * 260.0 / 1e9 / peaks["hbm_gbs"], "bytes_per_row": 260}},
+    }
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(threads=1, pool=50_000, fixture="c3_nsf_trained")
+    return out
 
 
 # ------------------------------------------------------------------------- reference
@@ -557,24 +680,23 @@ def reference_populate(threads, pool, steps=1, warmup=0, fixture="c2_realnvp_mlp
 
     torch.set_num_threads(threads)
     cfg, sd = load_fixture(fixture)
-    live, cov = live_points()
+    ours, live = problem(fixture)
 
     class RefModel(Model):
+        """The same problem as a nessai Model (names, bounds, uniform prior, likelihood)."""
+
         def __init__(self):
-            self.names = [f"x{i}" for i in range(D)]
-            self.bounds = {n: [-10.0, 10.0] for n in self.names}
-            self._icov = np.linalg.inv(cov)
-            self._norm = -0.5 * (D * np.log(2 * np.pi) + np.linalg.slogdet(cov)[1])
+            self.names = list(ours.names)
+            self.bounds = {n: list(b) for n, b in ours.bounds.items()}
 
         def log_prior(self, x):
             lp = np.log(self.in_bounds(x), dtype="float")
             for n in self.names:
-                lp -= np.log(20.0)
+                lp -= np.log(self.bounds[n][1] - self.bounds[n][0])
             return lp
 
         def log_likelihood(self, x):
-            a = self.unstructured_view(x)
-            return self._norm - 0.5 * np.einsum("...i,ij,...j->...", a, self._icov, a)
+            return ours.log_likelihood(x)
 
     model = RefModel()
     rng = np.random.default_rng(SEED)
@@ -674,7 +796,11 @@ def run_reference(args):
         "population_acceptance": acc,
     }
     if not args.no_extras:
-        out["variants"] = {"train": train_variant("reference")}
+        n3, s3, _, a3 = reference_populate(threads, 100_000, steps=1, warmup=1, fixture="c3_nsf_trained")
+        out["variants"] = {"train": train_variant("reference"), "c5": c5_variant("reference"),
+                           "c3": {"value": n3 / s3, "unit": "rows/s", "cores": threads, "population_acceptance": a3,
+                                  "sample": f"one populate(n_samples=100000, drawsize=100000) = {n3} proposed rows in {s3:.1f} s "
+                                            "after one warm-up; reference-trained 32-D NSF (c3_nsf_trained)"}}
     print(json.dumps(out), flush=True)
 
 
@@ -687,6 +813,7 @@ def main():
     ap.add_argument("--pool", type=int, default=POOL)
     ap.add_argument("--cpu-pool", type=int, default=1_000_000,
                     help="poolsize = drawsize of the reference arm and of the 1-thread cpu_baseline (the GPU arm's 1e6)")
+    ap.add_argument("--c3-pool", type=int, default=2_000_000)
     ap.add_argument("--min-steps", type=int, default=1000,
                     help="timed steps per lens in total (regions of --steps steps are repeated up to this)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -234,12 +234,13 @@ class B200Flow(torch.nn.Module):
         z, logj, _ = self._forward(x, want_logp=False)
         return z, logj
 
-    def _forward(self, x, want_logp=True):
+    def _forward(self, x, want_logp=True, want_z=True, want_logj=True):
         self._ready()
         x = self._prep(x)
         n = x.shape[0]
-        z = torch.empty_like(x)
-        logj = torch.empty(n, device=self.device, dtype=torch.float32)
+        # (outputs nobody asked for are not written: log_prob alone saves 4 D + 4 bytes per row)
+        z = torch.empty_like(x) if want_z else None
+        logj = torch.empty(n, device=self.device, dtype=torch.float32) if want_logj else None
         logp = torch.empty(n, device=self.device, dtype=torch.float32) if want_logp else None
         with torch.cuda.device(self.device):
             _lib.check(
@@ -272,7 +273,7 @@ class B200Flow(torch.nn.Module):
         return x, logj, logq
 
     def log_prob(self, x, context=None):
-        return self._forward(x)[2]
+        return self._forward(x, want_z=False, want_logj=False)[2]
 
     def forward_and_log_prob(self, x, context=None):
         z, _, logp = self._forward(x)
@@ -490,7 +491,16 @@ class B200FlowModel:
         if getattr(self, "_fused", None) is None or self._fused_key != key:
             from .trainer import FusedTrainer
 
-            self._fused = FusedTrainer(model)
+            # a new flow of the SAME architecture and index tables (every level of the importance
+            # sampler adds one) reuses the trainer: its plan and workspaces only depend on those
+            arch = (json.dumps(self.flow_config, sort_keys=True, default=str), str(model.device),
+                    tuple((k, np.asarray(v).tobytes()) for k, v in sorted(model.ints.items())))
+            old = getattr(self, "_fused", None)
+            if old is not None and getattr(self, "_fused_arch", None) == arch and old.rebind(model):
+                pass
+            else:
+                self._fused = FusedTrainer(model)
+            self._fused_arch = arch
             self._fused_key = key
         return self._fused
 
@@ -718,11 +728,22 @@ class B200FlowModel:
     # -------------------------------------------------------------- inference
     def numpy_array_to_tensor(self, array: np.ndarray, /) -> torch.Tensor:
         """flowmodel/base.py:774-780."""
-        return torch.from_numpy(np.ascontiguousarray(array)).to(torch.float32).to(self.model.device)
+        # the rows cross PCIe in the caller's dtype and are rounded to fp32 on the device (the same
+        # round-to-nearest as the reference's host-side ``.type(torch.float32)``, without a host pass)
+        return torch.from_numpy(np.ascontiguousarray(array)).to(self.model.device).to(torch.float32)
 
     @staticmethod
     def _to_numpy(t: torch.Tensor) -> np.ndarray:
-        return t.detach().cpu().numpy().astype(np.float64)
+        """Device tensor -> float64 numpy array (what the reference returns): widened on the device,
+        ONE copy into page-locked host memory that the returned array aliases (no host-side pass)."""
+        t = t.detach()
+        if t.device.type != "cuda" or t.numel() < 4096:
+            return t.cpu().numpy().astype(np.float64)
+        t = t.to(torch.float64).contiguous()
+        host = torch.empty(t.shape, dtype=torch.float64, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return host.numpy()
 
     def forward_and_log_prob(self, x: np.ndarray, conditional=None) -> Tuple[np.ndarray, np.ndarray]:
         if conditional is not None:
@@ -774,6 +795,6 @@ class B200FlowModel:
         state.pop("model", None)
         state.pop("flow_config", None)
         state.pop("scheduler", None)
-        for k in ("_fused", "_fused_key", "_pending_train_loss"):
+        for k in ("_fused", "_fused_key", "_fused_arch", "_pending_train_loss"):
             state.pop(k, None)
         return state

@@ -82,7 +82,7 @@ class B200ImportanceFlowModel(B200FlowModel):
 
     # ------------------------------------------------------------- inference
     def _device_rows(self, x: np.ndarray, model: B200Flow) -> torch.Tensor:
-        return torch.from_numpy(np.ascontiguousarray(x)).to(torch.float32).to(model.device)
+        return torch.from_numpy(np.ascontiguousarray(x)).to(model.device).to(torch.float32)
 
     def log_prob_ith(self, x, i):
         """importance.py:101-113."""
@@ -125,7 +125,7 @@ class B200ImportanceFlowModel(B200FlowModel):
                 if i < len(streams):
                     st.wait_event(fork)
                 with torch.cuda.stream(st):
-                    out[i, : hi - lo] = m._forward(xd)[2]
+                    out[i, : hi - lo] = m._forward(xd, want_z=False, want_logj=False)[2]
             for st in streams:
                 main.wait_stream(st)
             xd.record_stream(main)
@@ -133,7 +133,7 @@ class B200ImportanceFlowModel(B200FlowModel):
             full = torch.empty((world, n_models, per), device=dev, dtype=torch.float32)
             dist.all_gather_into_tensor(full, out)
             out = full.permute(1, 0, 2).reshape(n_models, world * per)[:, :N]
-        return out.t().contiguous().cpu().numpy().astype(np.float64)
+        return self._to_numpy(out.t())
 
     def _lp_streams(self, dev, n):
         cur = getattr(self, "_streams", None)
@@ -193,7 +193,7 @@ class B200ImportanceFlowModel(B200FlowModel):
 
     def __getstate__(self):
         d = self.__dict__
-        exclude = {"models", "_optimiser", "flow_config", "_fused", "_fused_key", "_pending_train_loss", "scheduler", "_streams"}
+        exclude = {"models", "_optimiser", "flow_config", "_fused", "_fused_key", "_fused_arch", "_pending_train_loss", "scheduler", "_streams"}
         state = {k: d[k] for k in d.keys() - exclude}
         state["initialised"] = False
         state["models"] = None

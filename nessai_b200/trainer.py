@@ -60,6 +60,20 @@ class FusedTrainer:
         self._opt_id = None
         self._loss = torch.zeros(2, device=self.device, dtype=torch.float32)
 
+    def rebind(self, model) -> bool:
+        """Point the trainer at another flow of the same architecture (same plan, same index
+        tables): fresh optimiser state, same kernels and workspaces.  False if it cannot."""
+        if model.spec.n_params != self.model.spec.n_params or model.device != self.device:
+            return False
+        if param_mask(model.spec):
+            return False  # MADE masks are uploaded per trainer
+        self.model = model
+        self.m.zero_()
+        self.v.zero_()
+        self.step = 0
+        self._opt_id = None
+        return True
+
     def __del__(self):
         try:
             if getattr(self, "_handle", None) and self._handle.value:

@@ -18,6 +18,7 @@ GOLDEN_NAMES = [
     "d6_nsf",
     "d8_maf",
     "d5_realnvp_mvn",
+    "c3_nsf_trained",
 ]
 
 

@@ -54,6 +54,17 @@ def rosenbrock_like(n, d, rng):
     return np.clip(x, -4.9, 4.9)
 
 
+def rosenbrock_chain(n, d, rng):
+    """Curved, non-Gaussian live points for any d (the quadratic recursion of rosenbrock_like
+    diverges beyond a few dimensions): x_i = 0.25 x_{i-1}^2 + 0.75 + noise contracts to the
+    Rosenbrock ridge x_{i+1} ~ x_i^2 around (1, ..., 1); inside [-5, 5]^d."""
+    x = np.empty((n, d))
+    x[:, 0] = rng.normal(1.0, 0.3, n)
+    for i in range(1, d):
+        x[:, i] = 0.25 * x[:, i - 1] ** 2 + 0.75 + rng.normal(0, 0.1, n)
+    return np.clip(x, -4.9, 4.9)
+
+
 def make(name, flow_config, data, n_eval, epochs, tmp):
     rng = np.random.default_rng(SEED)
     torch.manual_seed(SEED)
@@ -192,7 +203,7 @@ def main():
     make(
         "c3_nsf_trained",
         dict(n_inputs=32, n_neurons=64, n_blocks=6, n_layers=2, ftype="nsf"),
-        rosenbrock_like(2000, 32, np.random.default_rng(SEED + 32)), 512, 80, tmp,
+        rosenbrock_chain(2000, 32, np.random.default_rng(SEED + 32)), 512, 80, tmp,
     )
     # masked autoregressive flow: MADE with residual blocks, reverse permutations
     make(

@@ -68,3 +68,37 @@ def test_train_save_and_reload_all(tmp_path):
     state.resume(cfg, weights_path=str(tmp_path))
     assert state.n_models == 2
     np.testing.assert_allclose(state.log_prob_all(x), before, rtol=1e-6, atol=1e-6)
+
+
+def test_levels_reuse_the_trainer_and_match_fresh_trainers(tmp_path):
+    """Every level of the importance sampler adds a flow of the same architecture
+    (flowmodel/importance.py:80-99) and trains it: the trainer (plan, workspaces) is reused across
+    the levels with fresh optimiser state, and gives exactly what a fresh trainer per level gives."""
+    from nessai_b200.importance import B200ImportanceFlowModel
+
+    g, cfg, sd = load_golden("c2_realnvp_resnet")
+    data = np.asarray(g["train_data"])
+    rng = np.random.default_rng(3)
+    sets = [data[rng.permutation(len(data))[:1500]] * s for s in (1.0, 1.3, 0.8)]
+    out = {}
+    for reuse in (True, False):
+        torch.manual_seed(11)
+        ifm = B200ImportanceFlowModel(flow_config=cfg, training_config=dict(device_tag="cuda:0", max_epochs=4, patience=4),
+                                      output=str(tmp_path / str(reuse)), rng=np.random.default_rng(5))
+        ifm.initialise()
+        trainers, hists = [], []
+        for level, xs in enumerate(sets):
+            ifm.add_new_flow(reset=True)
+            if not reuse:
+                ifm._fused = None  # a fresh trainer per level
+            hists.append(ifm.train(xs, output=os.path.join(ifm.output, f"level_{level}"), plot=False))
+            trainers.append(ifm._fused)
+        if reuse:
+            assert trainers[0] is trainers[1] is trainers[2]
+        out[reuse] = (hists, ifm.log_prob_all(np.asarray(g["x"], dtype=np.float64)))
+    for ha, hb in zip(out[True][0], out[False][0]):
+        np.testing.assert_array_equal(ha["loss"], hb["loss"])
+        np.testing.assert_array_equal(ha["val_loss"], hb["val_loss"])
+    np.testing.assert_array_equal(out[True][1], out[False][1])
+    lp = out[True][1]
+    assert lp.shape[1] == 3 and np.isfinite(lp).all() and not np.allclose(lp[:, 0], lp[:, 1])
