@@ -176,6 +176,25 @@ int nb200_coupling_transform(const float* d_x, const float* d_params, float* d_y
                              int64_t n, int D, const int32_t* h_transform_features, int d_tr,
                              int additive, int inverse, void* stream);
 
+/* ------------------------------------------------------------------ peer-memory exchange
+ * The scalar exchanges of a populate turn sharded over the GPUs of ONE node --
+ * the max log-weight of the turn before the rejection step (flowproposal.py:491-494 normalises by
+ * the maximum over the whole turn) and every rank's {accepted, written} counts after it -- as
+ * direct NVLink stores into the peers' slot buffers (CUDA IPC), polled locally: no NCCL
+ * collective, no host round trip.  create: this rank's slot buffer + its 64-byte IPC handle
+ * (exchanged by the caller); open: a peer's buffer mapped into this process.
+ * allgather: publish n_words (<= 3) 64-bit words from d_src to every rank, collect every rank's
+ * into d_gathered[world][n_words] (may be NULL); d_max_out (may be NULL) = max over the ranks of
+ * word 0 read as a double.  kind: 0 max, 1 counts; seq: 1, 2, ... the same on every rank for
+ * the same exchange.  d_err is set to 1 if a peer did not answer within the spin limit. */
+int nb200_xchg_create(void** d_buf, unsigned char* handle64);
+int nb200_xchg_open(const unsigned char* handle64, void** d_peer);
+int nb200_xchg_close(void* d_peer);
+int nb200_xchg_destroy(void* d_buf);
+int nb200_xchg_allgather(const void* const* d_peers, int world, int rank, int kind, uint64_t seq,
+                         const void* d_src, int n_words, void* d_gathered, double* d_max_out,
+                         int* d_err, void* stream);
+
 /* ------------------------------------------------------------------ training
  * flowmodel/base.py:365-452 FlowModel._train: one EPOCH of optimisation steps on a
  * RealNVP flow, fused: train-mode forward (batch-statistics BatchNorm with running-

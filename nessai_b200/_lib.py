@@ -112,6 +112,15 @@ _SIGS = {
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int,
          C.c_int, C.c_int, C.c_void_p],
     ),
+    "nb200_xchg_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p]),
+    "nb200_xchg_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "nb200_xchg_close": (C.c_int, [C.c_void_p]),
+    "nb200_xchg_destroy": (C.c_int, [C.c_void_p]),
+    "nb200_xchg_allgather": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_void_p],
+    ),
     "nb200_trainer_create": (
         C.c_int,
         [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int],

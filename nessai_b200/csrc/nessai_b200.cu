@@ -631,6 +631,59 @@ extern "C" int nb200_debug_trace(long long* h_out, int* h_n) {
 }
 #endif
 
+// ============================================================================= peer-memory exchange
+#include "xchg.cuh"
+
+extern "C" int nb200_xchg_create(void** d_buf, unsigned char* handle64) {
+  if (!d_buf || !handle64) return fail(1, "nb200_xchg_create: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  void* p = nullptr;
+  CUDA_OK(cudaMalloc(&p, XCHG_BYTES));
+  CUDA_OK(cudaMemset(p, 0, XCHG_BYTES));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(2, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  }
+  memcpy(handle64, &h, 64);
+  *d_buf = p;
+  return 0;
+}
+
+extern "C" int nb200_xchg_open(const unsigned char* handle64, void** d_peer) {
+  if (!handle64 || !d_peer) return fail(1, "nb200_xchg_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(d_peer, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return fail(2, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int nb200_xchg_close(void* d_peer) {
+  if (d_peer) CUDA_OK(cudaIpcCloseMemHandle(d_peer));
+  return 0;
+}
+
+extern "C" int nb200_xchg_destroy(void* d_buf) {
+  if (d_buf) CUDA_OK(cudaFree(d_buf));
+  return 0;
+}
+
+extern "C" int nb200_xchg_allgather(const void* const* d_peers, int world, int rank, int kind, uint64_t seq,
+                                    const void* d_src, int n_words, void* d_gathered, double* d_max_out,
+                                    int* d_err, void* stream) {
+  if (!d_peers || !d_src || !d_err || world < 1 || world > XCHG_MAXW || rank < 0 || rank >= world ||
+      kind < 0 || kind >= XCHG_KINDS || n_words < 1 || n_words > XCHG_WORDS || seq == 0)
+    return fail(1, "nb200_xchg_allgather: bad arguments");
+  xchg_allgather_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(
+      (void* const*)d_peers, world, rank, kind, (unsigned long long)seq, (const unsigned long long*)d_src, n_words,
+      (unsigned long long*)d_gathered, d_max_out, d_err);
+  g_launches += 1;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // ============================================================================= training
 #include "train.cuh"
 

@@ -435,9 +435,14 @@ class PopulateEngine:
         accepted on this rank (device scalar tensor ``d_counts``)."""
         n_local, start = self._last
         if self.world > 1:
-            import torch.distributed as dist
+            # the rejection step normalises by the maximum over the WHOLE turn
+            x = self._peer_exchange()
+            if x is not None:
+                x.allgather(x.KIND_MAX, self.d_stats, 1, None, self.d_stats)
+            else:
+                import torch.distributed as dist
 
-            dist.all_reduce(self.d_stats[0:1], op=dist.ReduceOp.MAX, group=self.group)
+                dist.all_reduce(self.d_stats[0:1], op=dist.ReduceOp.MAX, group=self.group)
         with_logl = self.likelihood is not None and getattr(self, "d_logl", None) is not None and self.logl_offset >= 0
         key = (n_local, self._gen, self.log_prior_const, with_logl)
         if getattr(self, "_accept_key", None) != key:
@@ -458,6 +463,15 @@ class PopulateEngine:
         args[20] = torch.cuda.current_stream(self.device).cuda_stream
         self._call(self._accept_fn, args, "nb200_populate_accept")
         return self.d_counts
+
+    def _peer_exchange(self):
+        """The peer-memory exchange of this engine's ranks (xchg.py), set up collectively on first
+        use; None when it is unavailable (another node, no CUDA IPC, NB200_NO_XCHG=1, CPU tests)."""
+        if not hasattr(self, "_xchg"):
+            from .xchg import make_peer_exchange
+
+            self._xchg = make_peer_exchange(self.device, self.group) if self.device.type == "cuda" else None
+        return self._xchg
 
     def run(self, n_samples: int, drawsize: int, max_samples: int = 1_000_000, host_prior=None,
             to_host: bool = True):
@@ -539,7 +553,12 @@ class PopulateEngine:
                 # every rank's {accepted, written}: the global count and this rank's offset
                 if getattr(self, "_d_allc", None) is None:
                     self._d_allc = torch.empty(2 * self.world, dtype=torch.int64, device=dev)
-                dist.all_gather_into_tensor(self._d_allc, counts, group=self.group)
+                x = self._peer_exchange()
+                if x is not None:
+                    x.allgather(x.KIND_COUNTS, counts, 2, self._d_allc, None)
+                    x.stage_error_flag()
+                else:
+                    dist.all_gather_into_tensor(self._d_allc, counts, group=self.group)
                 self._h_counts[: 2 * self.world].copy_(self._d_allc, non_blocking=True)
             self._ev_counts.record(main)
             if tr is not None:
@@ -561,6 +580,8 @@ class PopulateEngine:
             if tr is not None:
                 tr.append(("ahead", time.perf_counter()))
             self._ev_counts.synchronize()
+            if self.world > 1 and self._peer_exchange() is not None:
+                self._peer_exchange().check()
             if tr is not None:
                 tr.append(("counts", time.perf_counter()))
             if self.world == 1:
