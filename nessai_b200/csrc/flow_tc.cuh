@@ -71,7 +71,15 @@ constexpr int TC_COL_AL = 96;   // activations lo
 #define NB200_TC_NG 4
 #endif
 constexpr int TC_NG = NB200_TC_NG;
-constexpr int TC_THREADS = TC_NG * 128 + TC_NG * 32;
+// NB200_TC_SELFISSUE: no issuer warps -- the first warp of every epilogue group issues the group's
+// MMAs itself right after the group's named barrier (one mbarrier hop less per GEMM round trip).
+#ifdef NB200_TC_SELFISSUE
+constexpr bool TC_SELF = true;
+#else
+constexpr bool TC_SELF = false;
+#endif
+constexpr int TC_THREADS = TC_NG * 128 + (TC_SELF ? 0 : TC_NG * 32);
+constexpr int TC_ALLOC_WARP = TC_SELF ? 0 : TC_NG * 4;  // the warp that owns the TMEM allocation
 constexpr int TC_TMEM_COLS = (TC_NG * TC_COLS <= 128) ? 128 : (TC_NG * TC_COLS <= 256 ? 256 : 512);
 
 struct TcProgram {
@@ -626,12 +634,75 @@ struct TcIO {
   float base_log_z = 0.f;
 };
 
+// The MMAs of one conditioner GEMM of layer l (which = 1, 2, 3) for the group whose TMEM base is
+// tgu (lane field 0, warp-uniform); the WHOLE warp runs this converged, one elected lane fires.
+__device__ __forceinline__ void tc_issue_gemm(const TcParams& P, uint32_t img_s, uint32_t tgu, int l,
+                                              int which, uint32_t bar_out) {
+  constexpr uint32_t ID64 = tc_idesc(128, TC_H), ID16 = tc_idesc(128, TC_N3);
+  const uint32_t d = tgu + TC_COL_D, ah = tgu + TC_COL_AH, al = tgu + TC_COL_AL;
+  const uint32_t ones_s = img_s + P.L * TC_LAYER_BYTES + (P.L + 1) * TC_AFF_BYTES;
+  const uint32_t zero_s = ones_s + TC_ONES_BYTES;
+  const uint64_t ones = tc_desc(ones_s, 2048, 128);
+  auto adv = [](uint64_t desc, uint32_t off) { return desc + (uint64_t)(off >> 4); };
+  const uint32_t lb = img_s + l * TC_LAYER_BYTES;
+  if (which == 1) {
+    const uint64_t d64 = tc_desc(lb, TC_H * 16, 128);
+    const uint64_t b1 = tc_desc(lb + TC_OFF_B1, zero_s - (lb + TC_OFF_B1), 128);
+    tc_mma_ss_e(d, ones, b1, ID64, 0);
+    tc_mma_ts_e(d, ah, adv(d64, TC_OFF_W1HI), ID64, 1);
+    tc_mma_ts_e(d, al, adv(d64, TC_OFF_W1HI), ID64, 1);
+    tc_mma_ts_e(d, ah, adv(d64, TC_OFF_W1LO), ID64, 1);
+  } else if (which == 2) {
+    const uint64_t d64 = tc_desc(lb, TC_H * 16, 128);
+    const uint64_t b2 = tc_desc(lb + TC_OFF_B2, zero_s - (lb + TC_OFF_B2), 128);
+    tc_mma_ss_e(d, ones, b2, ID64, 0);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      tc_mma_ts_e(d, ah + 8 * ks, adv(d64, TC_OFF_W2HI + ks * 2 * TC_H * 16), ID64, 1);
+      tc_mma_ts_e(d, al + 8 * ks, adv(d64, TC_OFF_W2HI + ks * 2 * TC_H * 16), ID64, 1);
+      tc_mma_ts_e(d, ah + 8 * ks, adv(d64, TC_OFF_W2LO + ks * 2 * TC_H * 16), ID64, 1);
+    }
+  } else {
+    const uint64_t d16 = tc_desc(lb, TC_N3 * 16, 128);
+    const uint64_t b3 = tc_desc(lb + TC_OFF_B3, zero_s - (lb + TC_OFF_B3), 128);
+    tc_mma_ss_e(d, ones, b3, ID16, 0);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      tc_mma_ts_e(d, ah + 8 * ks, adv(d16, TC_OFF_W3HI + ks * 2 * TC_N3 * 16), ID16, 1);
+      tc_mma_ts_e(d, al + 8 * ks, adv(d16, TC_OFF_W3HI + ks * 2 * TC_N3 * 16), ID16, 1);
+      tc_mma_ts_e(d, ah + 8 * ks, adv(d16, TC_OFF_W3LO + ks * 2 * TC_N3 * 16), ID16, 1);
+    }
+  }
+  tc_commit_e(bar_out);
+}
+
+// Hand a GEMM's A operand over to the tensor core.  Default: arrive at the issuer warp's
+// mbarrier.  Self-issue: the group's named barrier, then the group's first warp issues.
+struct TcGroup {
+  uint32_t bar_in, bar_out;
+  uint32_t img_s;   // shared-memory address of the weight image
+  uint32_t tgu;     // the group's TMEM base (lane field 0), warp-uniform
+  int g;            // group index
+  bool first_warp;  // warp-uniform: this warp issues the group's MMAs (self-issue only)
+};
+__device__ __forceinline__ void tc_submit(const TcParams& P, const TcGroup& G, int l, int which) {
+  if (TC_SELF) {
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + G.g) : "memory");
+    if (G.first_warp) {
+      tc_fence_after();
+      tc_issue_gemm(P, G.img_s, G.tgu, l, which, G.bar_out);
+    }
+  } else {
+    tc_mbar_arrive(G.bar_in);
+  }
+}
+
 // The epilogue-group body shared by the apply and populate kernels: runs the whole
 // program for one row held in h[] and returns the row log|det J| (without const).
 // tg: the group's TMEM base with this warp's lane quarter in the upper half-word.
 __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* img, uint32_t tg,
-                                            uint32_t bar_in, uint32_t bar_out, uint32_t& ph_out,
-                                            float (&h)[TC_DP]) {
+                                            const TcGroup& G, uint32_t& ph_out, float (&h)[TC_DP]) {
+  const uint32_t bar_out = G.bar_out;
   const float* aff = reinterpret_cast<const float*>(img + (size_t)P.L * TC_LAYER_BYTES);
   float ld = 0.f;
   for (int l = 0; l < P.L; ++l) {
@@ -649,7 +720,7 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
     }
     tc_fence_before();
     TC_STAMP_E(1);
-    tc_mbar_arrive(bar_in);
+    tc_submit(P, G, l, 1);
     // the fp32 affine in front of the coupling, in the shadow of GEMM1
 #ifndef NB200_ABL_NO_AFFINE
     tc_affine(aff + (size_t)l * (TC_AFF_BYTES / 4), h);
@@ -662,7 +733,7 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
     tc_hidden_epilogue(tg);
     tc_fence_before();
     TC_STAMP_E(3);
-    tc_mbar_arrive(bar_in);
+    tc_submit(P, G, l, 2);
     // ---- E2: hidden layer 2
     tc_mbar_wait(bar_out, ph_out);
     TC_STAMP_E(4);
@@ -671,7 +742,7 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
     tc_hidden_epilogue(tg);
     tc_fence_before();
     TC_STAMP_E(5);
-    tc_mbar_arrive(bar_in);
+    tc_submit(P, G, l, 3);
     // ---- E3: coupling on the transformed half, then the next affine
     tc_mbar_wait(bar_out, ph_out);
     TC_STAMP_E(6);
@@ -783,7 +854,7 @@ __device__ __forceinline__ void tc_prologue(const TcParams& P, uint8_t* smem, Tc
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if ((tid >> 5) == TC_NG * 4) {  // first issuer warp owns the TMEM allocation
+  if ((tid >> 5) == TC_ALLOC_WARP) {  // this warp owns the TMEM allocation
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      tc_smem_u32(&sh->tmem_base)),
                  "r"((uint32_t)TC_TMEM_COLS)
@@ -799,7 +870,7 @@ __device__ __forceinline__ void tc_prologue(const TcParams& P, uint8_t* smem, Tc
 __device__ __forceinline__ void tc_epilogue_end(TcShared* sh) {
   tc_fence_before();
   __syncthreads();
-  if ((threadIdx.x >> 5) == TC_NG * 4) {
+  if ((threadIdx.x >> 5) == TC_ALLOC_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sh->tmem_base),
                  "r"((uint32_t)TC_TMEM_COLS)
@@ -829,7 +900,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P
   if (warp < TC_NG * 4) {
     const int g = warp >> 2, t = threadIdx.x & 127;
     const uint32_t tg = tmem + g * TC_COLS + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t bar_in = tc_smem_u32(&sh->bar_in[g]), bar_out = tc_smem_u32(&sh->bar_out[g]);
+    const TcGroup G{tc_smem_u32(&sh->bar_in[g]), tc_smem_u32(&sh->bar_out[g]), tc_smem_u32(tc_smem),
+                    __shfl_sync(0xffffffffu, tmem, 0) + g * TC_COLS, g, (warp & 3) == 0};
     uint32_t ph_out = 0;
     const int64_t stride = (int64_t)gridDim.x * TC_NG;
     for (int64_t tile = (int64_t)blockIdx.x * TC_NG + g; tile < ntiles; tile += stride) {
@@ -850,7 +922,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P
       }
 #pragma unroll
       for (int d = 0; d < TC_DP; ++d) ss_in = fmaf(h[d], h[d], ss_in);
-      const float ld = tc_run_row(P, tc_smem, tg, bar_in, bar_out, ph_out, h) + P.const_logdet;
+      const float ld = tc_run_row(P, tc_smem, tg, G, ph_out, h) + P.const_logdet;
       float ss_out = 0.f;
 #pragma unroll
       for (int d = 0; d < TC_DP; ++d) ss_out = d < P.D ? fmaf(h[d], h[d], ss_out) : ss_out;
@@ -873,7 +945,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P
         }
       }
     }
-  } else {
+  } else if (!TC_SELF) {
     // issuer warp g: all 32 lanes converged, one elected lane fires each MMA
     const int g = __shfl_sync(0xffffffffu, warp - TC_NG * 4, 0);
     tc_issuer(P, tc_smem_u32(tc_smem), __shfl_sync(0xffffffffu, tmem, 0) + g * TC_COLS,
@@ -899,7 +971,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParam
   if (warp < TC_NG * 4) {
     const int g = warp >> 2, t = threadIdx.x & 127;
     const uint32_t tg = tmem + g * TC_COLS + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t bar_in = tc_smem_u32(&sh->bar_in[g]), bar_out = tc_smem_u32(&sh->bar_out[g]);
+    const TcGroup G{tc_smem_u32(&sh->bar_in[g]), tc_smem_u32(&sh->bar_out[g]), tc_smem_u32(tc_smem),
+                    __shfl_sync(0xffffffffu, tmem, 0) + g * TC_COLS, g, (warp & 3) == 0};
     uint32_t ph_out = 0;
     double vmax = -INFINITY, vcount = 0.0;
     const double *c_scale = sh->cst[0], *c_shift = sh->cst[1], *c_lo = sh->cst[2], *c_hi = sh->cst[3];
@@ -928,13 +1001,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParam
       }
       const float rad = sqrtf(ss) * A.sqrt_t;
       const bool alive = !(A.r_max > 0.f) || (rad <= A.r_max);
-      const float logj = tc_run_row(P, tc_smem, tg, bar_in, bar_out, ph_out, h) + P.const_logdet;
+      const float logj = tc_run_row(P, tc_smem, tg, G, ph_out, h) + P.const_logdet;
       const float base_lp = -0.5f * ss - 0.5f * P.D * TC_LOG_2PI;
       populate_row<TC_DP>(A, P.D, [&](int d) { return h[d]; }, row, alive, base_lp, logj, vmax,
                           vcount, c_scale, c_shift, c_lo, c_hi, log_const);
     }
     populate_publish(A, vmax, vcount);
-  } else {
+  } else if (!TC_SELF) {
     // issuer warp g: all 32 lanes converged, one elected lane fires each MMA
     const int g = __shfl_sync(0xffffffffu, warp - TC_NG * 4, 0);
     tc_issuer(P, tc_smem_u32(tc_smem), __shfl_sync(0xffffffffu, tmem, 0) + g * TC_COLS,

@@ -108,8 +108,12 @@ class B200Flow(torch.nn.Module):
 
     Presents the surface of the reference's ``BaseFlow``
     (/root/reference/src/nessai/flows/base.py:11-167) on torch tensors; the
-    ``state_dict`` uses the reference key layout so ``model.pt`` files
-    interchange with ``nessai.flows.RealNVP`` / ``NeuralSplineFlow``.
+    ``state_dict`` uses the reference key layout so ``model.pt`` files are meant to
+    interchange with ``nessai.flows.RealNVP`` / ``NeuralSplineFlow``.  That is VERIFIED against
+    the reference running on the restated nflows layer (``oracle/shims/glasflow``, both
+    directions, ``tests/test_gpu_nessai_plugin.py``); against a real ``glasflow`` install it is
+    checked by ``tests/test_spec.py::test_interchange_with_real_glasflow`` wherever one exists
+    (this image has none).
     """
 
     def __init__(self, spec: FlowSpec, device: torch.device):

@@ -10,7 +10,9 @@ the parameters in a ``torch.nn.Module`` tree.  Here a flow is
 * ONE flat fp32 buffer ``theta`` holding every trainable parameter followed by
   the float buffers (BatchNorm running statistics), laid out in the order of the
   reference ``state_dict`` so weight files interchange (SURVEY.md section 8c,
-  "State-dict key layout");
+  "State-dict key layout"; pinned against the reference on the restated nflows layer of
+  ``oracle/shims`` -- real glasflow is absent from this image, see
+  ``tests/test_spec.py::test_interchange_with_real_glasflow``);
 * a *program*: the eval-mode flow folded on the host (float64) into the op
   list the CUDA kernels interpret (``csrc/flow_program.h``).  Every
   row-constant transform (permutation, LU, eval-mode BatchNorm) between two
