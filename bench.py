@@ -77,6 +77,16 @@ class GaussianModel:
         a = self._arr(x)
         return self._norm - 0.5 * np.einsum("...i,ij,...j->...", a, self._icov, a)
 
+    def log_likelihood_torch(self, x):
+        """The same likelihood on (n, D) float64 device rows: the pool's logL is
+        evaluated on the accepted records while they are still in HBM -- outside population_time
+        in both arms, as flowproposal.py:518-523 times it."""
+        import torch
+
+        if getattr(self, "_icov_t", None) is None or self._icov_t.device != x.device:
+            self._icov_t = torch.from_numpy(self._icov).to(x.device)
+        return self._norm - 0.5 * ((x @ self._icov_t) * x).sum(dim=1)
+
 
 def rosenbrock_live_points(n=2000, d=32):
     """The curved live-point set the C3 fixture was trained on (tests/golden/make_golden.py:
@@ -217,7 +227,7 @@ def quartiles(v):
     return float(q[1]), float(q[2] - q[0])
 
 
-def measure(prop, worst, pool, steps, warmup, repeats, world, dev, kernel_reps=20):
+def measure(prop, worst, pool, steps, warmup, repeats, world, dev, kernel_reps=20, e2e_repeats=None):
     """One configuration through the three lenses of the bench line.  Every timed region is exactly
     ``steps`` steps between two barrier + synchronize brackets; the region is repeated ``repeats``
     times (>= 1 s of timed work in total) and the MEDIAN region is reported, with the inter-quartile
@@ -276,8 +286,10 @@ def measure(prop, worst, pool, steps, warmup, repeats, world, dev, kernel_reps=2
     # ---- end to end through the plugin-facing call (host arrays in/out)
     for _ in range(min(warmup, 2)):
         prop.populate(worst, n_samples=pool, max_samples=max_samples)
+    # (a populate's WALL time is dominated by what the sampler does between two populates -- the
+    # host likelihood of the whole pool, outside population_time -- so its regions are fewer)
     e2e_rates, d2h, wall = [], 0, 0.0
-    for r in range(repeats):
+    for r in range(e2e_repeats or repeats):
         barrier()
         prop.population_time *= 0
         n_prop = 0
@@ -304,7 +316,7 @@ def measure(prop, worst, pool, steps, warmup, repeats, world, dev, kernel_reps=2
     return dict(value=v_med, value_iqr=v_iqr, ms_per_step=ms_med / steps, e2e=e_med, e2e_iqr=e_iqr,
                 kernel_ms=k_med, kernel_ms_iqr=k_iqr, n_local=n_local, launches=int(launches),
                 turns_per_step=int(round(region_rows[-1] / steps / pool)), d2h_bytes=int(d2h), repeats=repeats,
-                timed_s=dict(device=sum(region_ms) * 1e-3, e2e_wall=wall),
+                e2e_regions=len(e2e_rates), timed_s=dict(device=sum(region_ms) * 1e-3, e2e_wall=wall),
                 regions_value=[float(f"{v:.4g}") for v in rates], regions_e2e=[float(f"{v:.4g}") for v in e2e_rates],
                 population_acceptance=prop.population_acceptance)
 
@@ -335,7 +347,8 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    m = measure(prop, worst, pool, args.steps, args.warmup, repeats, world, dev)
+    e2e_repeats = int(min(repeats, max(5, -(-(400 if world == 1 else 100) // args.steps))))
+    m = measure(prop, worst, pool, args.steps, args.warmup, repeats, world, dev, e2e_repeats=e2e_repeats)
     clk = clocks.stop() if rank == 0 else None
 
     if rank == 0:
@@ -365,7 +378,7 @@ def run_ours(args):
                 "turns_per_step": m["turns_per_step"],
                 "l2": "each turn writes 80 MB of fresh outputs; L2 (126 MB) is flushed between steps by the accept kernels and the next turn; inputs are generated in-kernel",
                 "tc_kernel": bool(os.environ.get("NB200_DISABLE_TC", "0") != "1"),
-                "timing": f"value / e2e / kernel_ms are MEDIANS over {m['repeats']} timed regions of exactly "
+                "timing": f"value / kernel_ms are MEDIANS over {m['repeats']} (e2e: {m['e2e_regions']}) timed regions of exactly "
                           f"{args.steps} steps each (barrier + synchronize on both sides of every region, CUDA events, "
                           "max over ranks); *_iqr = inter-quartile range over the regions",
                 "e2e_note": "n_proposed / population_time of B200FlowProposal.populate (max over ranks); N>1: ranks "
@@ -373,7 +386,7 @@ def run_ours(args):
                             "host memory, d2h_bytes_per_step = bytes of the whole pool (each rank copies its own share)",
             },
             "spread": {"value_iqr": m["value_iqr"], "e2e_iqr": m["e2e_iqr"], "kernel_ms_iqr": m["kernel_ms_iqr"],
-                       "regions": m["repeats"], "timed_s": m["timed_s"],
+                       "regions": m["repeats"], "e2e_regions": m["e2e_regions"], "timed_s": m["timed_s"],
                        "regions_value": m["regions_value"], "regions_e2e": m["regions_e2e"]},
             "clocks": clk,
             "e2e": {
@@ -454,7 +467,7 @@ def multi_gpu_extras(prop, model, live_s, worst, args, pool, repeats, world, ran
 
     from nessai_b200.proposal import PopulateEngine
 
-    few = max(5, repeats // 4)
+    few = max(5, min(repeats // 4, -(-100 // args.steps)))
     out = {}
     prop_s = build_proposal("c2_realnvp_mlp", model, live_s, local_rank, args.pool)
     ms = measure(prop_s, worst, args.pool, args.steps, args.warmup, few, world, dev, kernel_reps=5)

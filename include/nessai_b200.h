@@ -211,6 +211,10 @@ int nb200_trainer_create(nb200_trainer** out, const int32_t* h_plan, int n_plan_
                          const int32_t* h_itab, int n_itab, const int32_t* h_reduce_idx,
                          int n_reduce);
 int nb200_trainer_destroy(nb200_trainer* trainer);
+/* Replace the index tables (permutations, mask index lists) of a trainer: a NEW flow of the same
+ * architecture (flows/utils.py:249-292 reset_permutations; every level of the importance sampler,
+ * flowmodel/importance.py:80-99) reuses the trainer's plan and workspaces. */
+int nb200_trainer_set_itab(nb200_trainer* trainer, const int32_t* h_itab, int n_itab, void* stream);
 /* MADE masks (flows/maf.py -> nflows MaskedLinear): h_mask float[n_params], the mask value for
  * masked-linear weights and 1 elsewhere (NULL: none).  Masked weights are held at exactly zero
  * (theta_p *= mask at the start of every epoch) and their gradients are masked. */

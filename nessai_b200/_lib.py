@@ -127,6 +127,7 @@ _SIGS = {
     ),
     "nb200_trainer_destroy": (C.c_int, [C.c_void_p]),
     "nb200_trainer_set_param_mask": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nb200_trainer_set_itab": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "nb200_trainer_copy_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nb200_train_epoch": (
         C.c_int,

@@ -39,19 +39,29 @@ constexpr int TC_DP = 16;           // padded feature count (registers per row)
 constexpr int TC_N3 = 16;           // padded 2*d_tr
 constexpr int TC_TR0 = 8;           // register slot of the first transformed feature
 constexpr int TC_MAXL = 8;
-constexpr int TC_W1_BYTES = TC_H * 16 * 2;            // 2 K-chunks x (64 rows x 16 B): K = 16 state slots
+// NB200_TC_AFFMMA: the D x D affine in front of every coupling rides GEMM1 as 16 extra output
+// columns (B operand [16 x 80] = W1' | A^T, same split-fp16 passes): the row's new state comes
+// back with one tcgen05.ld instead of 128 FFMA2 + 64 broadcast LDS.128 per row and layer.
+// (measured on B200, C2: 0.293 -> 0.247 ms per 1e6 rows; -DNB200_TC_NO_AFFMMA keeps the fp32 FFMA2 affine)
+#ifdef NB200_TC_NO_AFFMMA
+constexpr bool TC_AFFMMA = false;
+#else
+constexpr bool TC_AFFMMA = true;
+#endif
+constexpr int TC_N1 = TC_H + (TC_AFFMMA ? TC_DP : 0);  // GEMM1 output columns
+constexpr int TC_W1_BYTES = TC_N1 * 16 * 2;           // 2 K-chunks x (N1 rows x 16 B): K = 16 state slots
 constexpr int TC_W2_BYTES = TC_H * 16 * (TC_H / 8);   // 8 chunks x 1 KB
 constexpr int TC_W3_BYTES = TC_N3 * 16 * (TC_H / 8);  // 8 chunks x 256 B
 // Biases enter as ONE extra K=16 step against a constant "ones" A operand whose elements
 // k = 0, 1 are 1: the B operand carries bias_hi at k = 0 and bias_lo at k = 1 (K-chunk 0 only;
 // its K-chunk 1 is a shared all-zero chunk reached through the descriptor's LBO).
-constexpr int TC_B1_BYTES = TC_H * 16;
+constexpr int TC_B1_BYTES = TC_N1 * 16;
 constexpr int TC_B2_BYTES = TC_H * 16;
 constexpr int TC_B3_BYTES = TC_N3 * 16;
 constexpr int TC_LAYER_BYTES =
     2 * (TC_W1_BYTES + TC_W2_BYTES + TC_W3_BYTES) + TC_B1_BYTES + TC_B2_BYTES + TC_B3_BYTES;
 constexpr int TC_ONES_BYTES = 2 * 2048;               // A operand [128 x 16] bf16, shared by all groups
-constexpr int TC_ZERO_BYTES = TC_H * 16;              // all-zero K-chunk 1 of the bias operands
+constexpr int TC_ZERO_BYTES = TC_N1 * 16;             // all-zero K-chunk 1 of the bias operands
 constexpr int TC_OFF_W1HI = 0;
 constexpr int TC_OFF_W1LO = TC_W1_BYTES;
 constexpr int TC_OFF_W2HI = 2 * TC_W1_BYTES;
@@ -67,6 +77,11 @@ constexpr int TC_COLS = 128;
 constexpr int TC_COL_D = 0;     // accumulator, 64 fp32 columns
 constexpr int TC_COL_AH = 64;   // activations hi: 64 bf16 = 32 columns (A1 hi aliases the first 8)
 constexpr int TC_COL_AL = 96;   // activations lo
+// GEMM1's A operand (the 16 state slots, 8 + 8 columns).  With the affine on the tensor core
+// GEMM1's accumulator is 80 columns wide, so its A operand moves to the top of the group's columns.
+constexpr int TC_COL_A1H = TC_AFFMMA ? 112 : TC_COL_AH;
+constexpr int TC_COL_A1L = TC_AFFMMA ? 120 : TC_COL_AL;
+constexpr int TC_COL_AFF = TC_H;  // (TC_AFFMMA) the affine's 16 output columns of GEMM1
 #ifndef NB200_TC_NG
 #define NB200_TC_NG 4
 #endif
@@ -265,12 +280,22 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
         double acc = 0.0;
         for (int j = 0; j < a.K; ++j)
           acc += (double)blob[a.w_off + j * a.Npad + n] * (double)blob[f.w_off + k * f.Npad + j];
-        tc_put(lb + TC_OFF_W1HI, lb + TC_OFF_W1LO, TC_H, n, slot(l - 1, k), (float)acc);
+        tc_put(lb + TC_OFF_W1HI, lb + TC_OFF_W1LO, TC_N1, n, slot(l - 1, k), (float)acc);
       }
       double bacc = blob[a.b_off + n];
       for (int j = 0; j < a.K; ++j)
         bacc += (double)blob[a.w_off + j * a.Npad + n] * (double)blob[f.b_off + j];
       put_bias(lb + TC_OFF_B1, n, (float)bacc);
+    }
+    if (TC_AFFMMA) {
+      // rows 64 .. 79 of GEMM1's B operand: the affine itself, output slot n_s = slot(l, n) from
+      // input slot slot(l - 1, k); its bias joins b1'
+      for (int n = 0; n < D; ++n) {
+        for (int k = 0; k < D; ++k)
+          tc_put(lb + TC_OFF_W1HI, lb + TC_OFF_W1LO, TC_N1, TC_H + slot(l, n), slot(l - 1, k),
+                 blob[f.w_off + k * f.Npad + n]);
+        put_bias(lb + TC_OFF_B1, TC_H + slot(l, n), blob[f.b_off + n]);
+      }
     }
     for (int n = 0; n < TC_H; ++n) {
       for (int k = 0; k < TC_H; ++k)
@@ -646,12 +671,14 @@ __device__ __forceinline__ void tc_issue_gemm(const TcParams& P, uint32_t img_s,
   auto adv = [](uint64_t desc, uint32_t off) { return desc + (uint64_t)(off >> 4); };
   const uint32_t lb = img_s + l * TC_LAYER_BYTES;
   if (which == 1) {
-    const uint64_t d64 = tc_desc(lb, TC_H * 16, 128);
+    constexpr uint32_t ID1 = tc_idesc(128, TC_N1);
+    const uint32_t a1h = tgu + TC_COL_A1H, a1l = tgu + TC_COL_A1L;
+    const uint64_t d1 = tc_desc(lb, TC_N1 * 16, 128);
     const uint64_t b1 = tc_desc(lb + TC_OFF_B1, zero_s - (lb + TC_OFF_B1), 128);
-    tc_mma_ss_e(d, ones, b1, ID64, 0);
-    tc_mma_ts_e(d, ah, adv(d64, TC_OFF_W1HI), ID64, 1);
-    tc_mma_ts_e(d, al, adv(d64, TC_OFF_W1HI), ID64, 1);
-    tc_mma_ts_e(d, ah, adv(d64, TC_OFF_W1LO), ID64, 1);
+    tc_mma_ss_e(d, ones, b1, ID1, 0);
+    tc_mma_ts_e(d, a1h, adv(d1, TC_OFF_W1HI), ID1, 1);
+    tc_mma_ts_e(d, a1l, adv(d1, TC_OFF_W1HI), ID1, 1);
+    tc_mma_ts_e(d, a1h, adv(d1, TC_OFF_W1LO), ID1, 1);
   } else if (which == 2) {
     const uint64_t d64 = tc_desc(lb, TC_H * 16, 128);
     const uint64_t b2 = tc_desc(lb + TC_OFF_B2, zero_s - (lb + TC_OFF_B2), 128);
@@ -714,8 +741,8 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
 #pragma unroll
       for (int j = 0; j < 8; ++j) tc_split2<false>(h[2 * j], h[2 * j + 1], hi[j], lo[j]);
       TC_STAMP_E(9);
-      tc_st8(tg + TC_COL_AH, hi);
-      tc_st8(tg + TC_COL_AL, lo);
+      tc_st8(tg + TC_COL_A1H, hi);
+      tc_st8(tg + TC_COL_A1L, lo);
       tc_wait_st();
     }
     tc_fence_before();
@@ -723,13 +750,23 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
     tc_submit(P, G, l, 1);
     // the fp32 affine in front of the coupling, in the shadow of GEMM1
 #ifndef NB200_ABL_NO_AFFINE
-    tc_affine(aff + (size_t)l * (TC_AFF_BYTES / 4), h);
+    if (!TC_AFFMMA) tc_affine(aff + (size_t)l * (TC_AFF_BYTES / 4), h);
 #endif
     // ---- E1: hidden layer 1
     tc_mbar_wait(bar_out, ph_out);
     TC_STAMP_E(2);
     ph_out ^= 1;
     tc_fence_after();
+    if (TC_AFFMMA) {
+      // the state after this layer's affine: GEMM1's columns 64 .. 79 (read before the hidden
+      // epilogue overwrites them with the next A operand)
+      uint32_t r[16];
+      tc_ld16(tg + TC_COL_AFF, r);
+      tc_wait_ld();
+      tc_pin16(r);
+#pragma unroll
+      for (int d = 0; d < TC_DP; ++d) h[d] = __uint_as_float(r[d]);
+    }
     tc_hidden_epilogue(tg);
     tc_fence_before();
     TC_STAMP_E(3);
@@ -787,10 +824,12 @@ __device__ __forceinline__ void tc_issuer(const TcParams& P, uint32_t img_s, uin
       TC_STAMP_I(11);
       ph_in ^= 1;
       tc_fence_after();
-      tc_mma_ss_e(d, ones, b1, ID64, 0);
-      tc_mma_ts_e(d, ah, adv(d64, TC_OFF_W1HI), ID64, 1);
-      tc_mma_ts_e(d, al, adv(d64, TC_OFF_W1HI), ID64, 1);
-      tc_mma_ts_e(d, ah, adv(d64, TC_OFF_W1LO), ID64, 1);
+      constexpr uint32_t ID1 = tc_idesc(128, TC_N1);
+      const uint64_t d1 = tc_desc(lb, TC_N1 * 16, 128);
+      tc_mma_ss_e(d, ones, b1, ID1, 0);
+      tc_mma_ts_e(d, tg + TC_COL_A1H, adv(d1, TC_OFF_W1HI), ID1, 1);
+      tc_mma_ts_e(d, tg + TC_COL_A1L, adv(d1, TC_OFF_W1HI), ID1, 1);
+      tc_mma_ts_e(d, tg + TC_COL_A1H, adv(d1, TC_OFF_W1LO), ID1, 1);
       tc_commit_e(bar_out);
       TC_STAMP_I(12);
       // GEMM2: bias + [128 x 64] x [64 x 64]

@@ -29,7 +29,8 @@ constexpr int RS_COL_D = 0;                   // residual stream
 constexpr int RS_COL_D2 = 64;                 // block-internal / final-layer accumulator
 constexpr int RS_COL_AH = 128;                // A operand, hi
 constexpr int RS_COL_AL = 160;                // A operand, lo
-constexpr int RS_W_SMALL = TC_H * 16 * 2;     // K = 16 operand, 64 rows: 2 KB
+constexpr int RS_W_SMALL = TC_N1 * 16 * 2;    // K = 16 operand of G0: 64 rows (+ 16: the affine, flow_tc.cuh TC_AFFMMA)
+constexpr int RS_BIAS0 = TC_N1 * 16;          // G0's bias operand
 constexpr int RS_W_BIG = TC_H * 16 * (TC_H / 8);    // 64 x 64: 8 KB
 constexpr int RS_W_FIN = TC_N3 * 16 * (TC_H / 8);   // 16 x 64: 2 KB
 constexpr int RS_BIAS = TC_H * 16;            // bias operand (K-chunk 0 only): 1 KB
@@ -45,7 +46,7 @@ __host__ __device__ inline RsLayout rs_layout(int NB) {
   o.wfhi = o.blk + NB * 4 * RS_W_BIG;
   o.wflo = o.wfhi + RS_W_FIN;
   o.b0 = o.wflo + RS_W_FIN;
-  o.bblk = o.b0 + RS_BIAS;                // per block: bA, bB
+  o.bblk = o.b0 + RS_BIAS0;               // per block: bA, bB
   o.bf = o.bblk + NB * 2 * RS_BIAS;
   o.layer_bytes = o.bf + TC_N3 * 16;
   return o;
@@ -185,12 +186,21 @@ inline int rs_build(RsProgram& t, const FlowOp* ops, int n_ops, const float* blo
           double acc = 0.0;
           for (int j = 0; j < a.K; ++j)
             acc += (double)blob[a.w_off + j * a.Npad + n] * (double)blob[f.w_off + k * f.Npad + j];
-          tc_put(lb + lay.w0hi, lb + lay.w0lo, TC_H, n, slot(l - 1, k), (float)acc);
+          tc_put(lb + lay.w0hi, lb + lay.w0lo, TC_N1, n, slot(l - 1, k), (float)acc);
         }
         double bacc = blob[a.b_off + n];
         for (int j = 0; j < a.K; ++j)
           bacc += (double)blob[a.w_off + j * a.Npad + n] * (double)blob[f.b_off + j];
         put_bias(lb + lay.b0, n, (float)bacc);
+      }
+      if (TC_AFFMMA) {
+        // rows 64 .. 79 of G0's B operand: the affine itself (slots of layer l - 1 -> slots of layer l)
+        for (int n = 0; n < D; ++n) {
+          for (int k = 0; k < D; ++k)
+            tc_put(lb + lay.w0hi, lb + lay.w0lo, TC_N1, TC_H + slot(l, n), slot(l - 1, k),
+                   blob[f.w_off + k * f.Npad + n]);
+          put_bias(lb + lay.b0, TC_H + slot(l, n), blob[f.b_off + n]);
+        }
       }
       for (int b = 0; b < NB; ++b) {
         uint8_t* wb = lb + lay.blk + (size_t)b * 4 * RS_W_BIG;
@@ -295,9 +305,19 @@ __device__ __forceinline__ float rs_run_row(const RsParams& P, const uint8_t* im
       tc_wait_st();
     }
     rs_arrive(bar_in);                                           // -> G0: D = W0' h + b0'
-    if (c == 0) tc_affine(aff + (size_t)li * (TC_AFF_BYTES / 4), h);  // in the shadow of G0
+    if (c == 0 && !TC_AFFMMA) tc_affine(aff + (size_t)li * (TC_AFF_BYTES / 4), h);  // in the shadow of G0
     for (int b = 0; b < P.NB; ++b) {
       rs_wait(bar_out, ph);
+      if (TC_AFFMMA && b == 0 && c == 0) {
+        // the state after this layer's affine: G0's columns 64 .. 79 (the first columns of D2,
+        // which the first block's GEMM overwrites only after this epilogue has arrived)
+        uint32_t r[16];
+        tc_ld16(tg + RS_COL_D2, r);
+        tc_wait_ld();
+        tc_pin16(r);
+#pragma unroll
+        for (int d = 0; d < TC_DP; ++d) h[d] = __uint_as_float(r[d]);
+      }
       rs_hidden_half<true>(tg, RS_COL_D, c);
       rs_arrive(bar_in);                                         // -> Ga: D2 = Wa relu(D) + ba
       rs_wait(bar_out, ph);
@@ -352,10 +372,12 @@ __device__ __forceinline__ void rs_issuer(const RsParams& P, const RsLayout& lay
       tc_mbar_wait(bar_in, ph);
       ph ^= 1;
       tc_fence_after();
-      tc_mma_ss_e(d, ones, bias(lb + lay.b0), ID64, 0);
-      tc_mma_ts_e(d, ah, adv(d64, lay.w0hi), ID64, 1);
-      tc_mma_ts_e(d, al, adv(d64, lay.w0hi), ID64, 1);
-      tc_mma_ts_e(d, ah, adv(d64, lay.w0lo), ID64, 1);
+      constexpr uint32_t ID1 = tc_idesc(128, TC_N1);
+      const uint64_t d1 = tc_desc(lb, TC_N1 * 16, 128);
+      tc_mma_ss_e(d, ones, bias(lb + lay.b0), ID1, 0);
+      tc_mma_ts_e(d, ah, adv(d1, lay.w0hi), ID1, 1);
+      tc_mma_ts_e(d, al, adv(d1, lay.w0hi), ID1, 1);
+      tc_mma_ts_e(d, ah, adv(d1, lay.w0lo), ID1, 1);
       tc_commit_e(bar_out);
       for (int b = 0; b < P.NB; ++b) {
         const uint32_t wb = lay.blk + b * 4 * RS_W_BIG;

@@ -833,6 +833,14 @@ static TrBuffers trainer_buffers(nb200_trainer* t, float* theta_p, float* theta_
   return B;
 }
 
+extern "C" int nb200_trainer_set_itab(nb200_trainer* t, const int32_t* h_itab, int n_itab, void* stream) {
+  if (!t || !h_itab || n_itab != t->h_plan.n_itab) return fail(1, "nb200_trainer_set_itab: bad arguments");
+  // (stream-ordered against the trainer's previous launches; the host array is pageable: the copy
+  // has left it when the call returns)
+  CUDA_OK(cudaMemcpyAsync(t->d_itab, h_itab, sizeof(int) * n_itab, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
 extern "C" int nb200_trainer_set_param_mask(nb200_trainer* t, const float* h_mask) {
   if (!t) return fail(1, "nb200_trainer_set_param_mask: bad arguments");
   if (!h_mask) {

@@ -495,10 +495,10 @@ class B200FlowModel:
         if getattr(self, "_fused", None) is None or self._fused_key != key:
             from .trainer import FusedTrainer
 
-            # a new flow of the SAME architecture and index tables (every level of the importance
-            # sampler adds one) reuses the trainer: its plan and workspaces only depend on those
-            arch = (json.dumps(self.flow_config, sort_keys=True, default=str), str(model.device),
-                    tuple((k, np.asarray(v).tobytes()) for k, v in sorted(model.ints.items())))
+            # a new flow of the SAME architecture (every level of the importance sampler adds one)
+            # reuses the trainer -- plan and workspaces only depend on the architecture; the new
+            # flow's permutations are uploaded into it
+            arch = (json.dumps(self.flow_config, sort_keys=True, default=str), str(model.device))
             old = getattr(self, "_fused", None)
             if old is not None and getattr(self, "_fused_arch", None) == arch and old.rebind(model):
                 pass

@@ -307,9 +307,13 @@ class B200NessaiFlowProposal(FlowProposal):
         else:
             logger.debug("Evaluating log-likelihoods")
             fn = getattr(self.model, "log_likelihood_torch", None)
-            if fn is not None and self._engine.world == 1 and host_prior is None and not aux and len(rows):
+            device_ok = fn is not None and host_prior is None and not aux and len(rows)
+            if device_ok and self._engine.world == 1:
                 # the accepted records are still on the device: 8 bytes per row come back
                 self.samples["logL"] = self._engine.device_log_likelihood(len(rows), fn).cpu().numpy()
+                self.model.likelihood_evaluations += len(rows)
+            elif device_ok and self._engine.sharded_pool_likelihood(self.samples, fn):
+                # several GPUs, pool in shared host memory: every rank evaluated its own records
                 self.model.likelihood_evaluations += len(rows)
             else:
                 self.samples["logL"] = self.model.batch_evaluate_log_likelihood(self.samples)

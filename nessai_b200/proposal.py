@@ -401,6 +401,30 @@ class PopulateEngine:
         x = rows32.index_select(1, self._param_cols).contiguous().view(torch.float64)
         return torch.as_tensor(fn(x), device=self.device).to(torch.float64).reshape(n_written)
 
+    def sharded_pool_likelihood(self, rows: np.ndarray, fn) -> bool:
+        """logL of a pool that the ranks of a node assembled in shared host memory: every rank
+        evaluates ``fn`` on the records IT accepted -- still resident in its HBM -- and writes their
+        ``logL`` fields in place, instead of every rank evaluating the whole pool on its host
+        (flowproposal.py:519-523).  Collective; False when the last populate did not use the shared pool."""
+        shared = getattr(self, "_last_shared", None)
+        if self.world == 1 or shared is None:
+            return False
+        n_local = sum(hi - lo for lo, hi, _ in self._segments)
+        if n_local:
+            first = min(src for _, _, src in self._segments)
+            last = max(src + hi - lo for lo, hi, src in self._segments)
+            ll = self.device_log_likelihood(last, fn)
+            host = torch.empty(last, dtype=torch.float64, pin_memory=True)
+            host.copy_(ll, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            vals = host.numpy()
+            assert first >= 0
+            col = rows["logL"]
+            for lo, hi, src in self._segments:
+                col[lo:hi] = vals[src : src + hi - lo]
+        shared.barrier()  # every rank's values have landed
+        return True
+
     def _apply_device_likelihood(self, n: int):
         """logL of every proposed row on the device (flowproposal.py:456-467 without the host
         round trip); rows at or below the threshold leave the turn, and the statistics of the
@@ -525,6 +549,8 @@ class PopulateEngine:
             pool_host = shared.tensors[self._pool_turn % shared.n_buffers]
             self._pool_turn += 1
         placed = 0  # records of all ranks placed in the shared pool so far
+        self._segments = []  # (pool row lo, hi, first local record) of this rank's share, per turn
+        self._last_shared = shared
         # pinned destination of the accepted records (one GPU): sized for what the turns are
         # expected to add; if that turns out too small the records are copied once at the end
         host, host_cap, overflow, copied = None, 0, False, 0
@@ -596,6 +622,7 @@ class PopulateEngine:
                     lo = placed + int(allc[: self.rank, 1].sum())
                     hi = min(lo + c_written, n_samples)
                     if hi > lo:
+                        self._segments.append((lo, hi, n_local_written))
                         cs.wait_event(self._ev_counts)
                         with torch.cuda.stream(cs):
                             pool_host[lo * rb : hi * rb].copy_(
@@ -1334,6 +1361,8 @@ class B200FlowProposal:
             fn = getattr(self.model, "log_likelihood_torch", None)
             if fn is not None and eng.world == 1:
                 self.samples["logL"] = eng.device_log_likelihood(len(rows), fn).cpu().numpy()
+            elif fn is not None and host_prior is None and eng.sharded_pool_likelihood(self.samples, fn):
+                pass  # several GPUs: every rank evaluated the records it accepted itself
             else:
                 self.samples["logL"] = np.asarray(self.model.log_likelihood(self.samples))
         if self.check_acceptance:

@@ -31,6 +31,7 @@ class FusedTrainer:
         self.model = model
         self.device = model.device
         plan, itab, reduce_idx = build_train_plan(model.spec, model.ints)
+        self._plan, self._itab, self._reduce = plan, itab, reduce_idx
         self._handle = C.c_void_p()
         lib = _lib.load()
         with torch.cuda.device(self.device):
@@ -67,6 +68,17 @@ class FusedTrainer:
             return False
         if param_mask(model.spec):
             return False  # MADE masks are uploaded per trainer
+        plan, itab, reduce_idx = build_train_plan(model.spec, model.ints)
+        if not (np.array_equal(plan, self._plan) and np.array_equal(reduce_idx, self._reduce)
+                and itab.shape == self._itab.shape):
+            return False
+        if not np.array_equal(itab, self._itab):
+            # the new flow's own permutations / index lists (reset_permutations draws new ones)
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.load().nb200_trainer_set_itab(self._handle, itab.ctypes.data_as(C.c_void_p),
+                                                              int(itab.size), st), "nb200_trainer_set_itab")
+            self._itab = itab
         self.model = model
         self.m.zero_()
         self.v.zero_()
