@@ -155,12 +155,15 @@ __device__ __forceinline__ float tr_ldp(const float* p) { return *p; }
 
 // ---------------------------------------------------------------------------- tile GEMMs
 // out[c][r] (=|+=) bias[c] + sum_k W[k*ldw + c] * A[k][r] (+ res[c][r]);  c < N, r < 16.
-// Thread (c = tid & 63, rows TR_RT*(tid >> 6) .. +TR_RT); callers synchronise.
+// Callers synchronise.
+// Thread (c = tid & 63, rows 2 (tid >> 6) .. + 2).
 __device__ __forceinline__ void tr_gemm(float* __restrict__ out, const float* __restrict__ A,
                                         const float* __restrict__ W, int ldw,
                                         const float* __restrict__ bias,
                                         const float* __restrict__ res, int N, int K, bool accum) {
-  static_assert(TR_RT == 2, "tile GEMM register tile");
+  static_assert(TR_RT == 2 && TR_R == 16 && TR_THREADS == 512, "tile GEMM register tiles");
+  // (a 4-row x 256-thread mapping halves the shared-memory wavefronts but measured slower: with one
+  // tile per CTA the GEMM is latency-bound and wants every warp)
   const int rg = threadIdx.x >> 6, cl = threadIdx.x & 63;
   for (int c0 = 0; c0 < N; c0 += 64) {
     const int c = c0 + cl;
@@ -380,7 +383,7 @@ struct TrSmem {
   float* V;     // [vals][16] conditioner buffers
   float* Gv;    // [vals][16] their gradients (backward only)
   float* A;     // [max_in][16] staged GEMM operand
-  float* A2;    // [max_in][16] input-gradient accumulator over output chunks (backward only)
+  float* A2;    // [max_in][16] second operand stage (forward) / input-gradient accumulator over output chunks (backward)
   float* bn;    // [4][D]: mean, rstd, w, beta  (+ [2][D] S1,S2 in backward)
   float* c;     // [16] row weights
   float* ld;    // [16]
@@ -395,7 +398,7 @@ __host__ __device__ inline size_t tr_smem_floats(int D, int vals, int max_in, in
   n += tr_align4(D * (D | 1) + D);
   n += 5 * (size_t)D * TR_R;
   n += (size_t)vals * TR_R * (backward ? 2 : 1);
-  n += (size_t)max_in * TR_R * (backward ? 2 : 1);
+  n += (size_t)max_in * TR_R * 2;
   n += tr_align4(6 * D);
   n += 2 * TR_R + 3 * TR_THREADS;
   n += (size_t)TR_MAXG * (2 * D + 1);
@@ -416,8 +419,7 @@ __device__ __forceinline__ TrSmem tr_carve(float* s, const TrPlan& P, bool backw
   m.Gv = s;
   if (backward) s += P.vals_floats * TR_R;
   m.A = s, s += P.max_in * TR_R;
-  m.A2 = s;
-  if (backward) s += P.max_in * TR_R;
+  m.A2 = s, s += P.max_in * TR_R;
   m.bn = s, s += tr_align4(6 * D);
   m.c = s, s += TR_R;
   m.ld = s, s += TR_R;
@@ -507,22 +509,21 @@ __device__ __forceinline__ void tr_reduce_stats(const TrBuffers& Bf, int l, int 
   __syncthreads();
 }
 
-// out[c] = sum_g src[g * ncol + c]  (ncol <= TR_THREADS): the G partials are split over
-// TR_THREADS / ncol thread slices so every thread issues independent loads.
+// out[c] = sum_g src[g * ncol + c]: one warp per column, lanes over the G partials (every load
+// independent, fixed order), one barrier.
 __device__ __forceinline__ void tr_colsum(const float* __restrict__ src, int G, int ncol, float* out,
                                           float* red) {
-  const int nsl = TR_THREADS / ncol;
-  const int c = threadIdx.x % ncol, sl = threadIdx.x / ncol;
-  float s = 0.f;
-  if (sl < nsl)
-    for (int g = sl; g < G; g += nsl) s += src[(size_t)g * ncol + c];
-  __syncthreads();
-  red[threadIdx.x] = s;
-  __syncthreads();
-  if ((int)threadIdx.x < ncol) {
-    float t = 0.f;
-    for (int q = 0; q < nsl; ++q) t += red[q * ncol + threadIdx.x];
-    out[threadIdx.x] = t;
+  (void)red;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = warp; c < ncol; c += TR_THREADS / 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < TR_STAT_PER_LANE; ++q) {
+      const int g = lane + 32 * q;
+      s += g < G ? src[(size_t)g * ncol + c] : 0.f;
+    }
+    s = tr_warp_sum(s);
+    if (lane == 0) out[c] = s;
   }
   __syncthreads();
 }
@@ -780,6 +781,8 @@ __device__ __forceinline__ void tr_layer_forward(const TrBuffers& Bf, const TrPl
     const float* src = S.V + ly.buf_off[ln.in_buf] * TR_R;
     const float* Aop = src;
     if (ln.pre_act) {
+      // (writing the activated operand from the producing GEMM's epilogue instead of in this pass
+      // was measured SLOWER: +0.4 us per linear)
       for (int e = threadIdx.x; e < ln.n_in * TR_R; e += TR_THREADS) S.A[e] = tr_act(act, src[e]);
       Aop = S.A;
     }
@@ -1048,6 +1051,24 @@ __device__ __forceinline__ void tr_loss_phase(const TrPlan& P, const TrBuffers& 
 }
 
 // ============================================================================ BWD(l)
+// Queue (one commit group) the loads of a tile for BWD(l): the layer's record h2 | buffers | y, the
+// gradient w.r.t. the layer's output, and the previous layer's output.
+__device__ __forceinline__ void tr_bwd_loads(const TrPlan& P, const TrBuffers& Bf, const TrLayer& ly, int l,
+                                             const TrSmem& S, int tile) {
+  const int D = P.D;
+  const float* rec = Bf.ws + ((size_t)tile * P.rec_total + ly.ws_off) * TR_R;
+  const int nb = ly.rec_floats - 2 * D;
+  tr_copy_async(S.H2, rec, D);
+  tr_copy_async(S.V + ly.buf_off[1] * TR_R, rec + D * TR_R, nb);
+  tr_copy_async(S.Y, rec + (D + nb) * TR_R, D);
+  tr_copy_async(S.X, Bf.dout[l & 1] + (size_t)tile * D * TR_R, D);
+  if (l > 0) {
+    const TrLayer& lp = P.layer[l - 1];
+    tr_copy_async(S.Pf, Bf.ws + ((size_t)tile * P.rec_total + lp.ws_off + lp.rec_floats - D) * TR_R, D);
+  }
+  tr_cp_commit();
+}
+
 __device__ __forceinline__ void tr_bwd_phase(const TrPlan& P, const TrBuffers& Bf, const TrBatch& bt, int l,
                                              const TrSmem& S, int part_sel = TR_WHOLE) {
   const TrLayer& ly = P.layer[l];
@@ -1065,6 +1086,10 @@ __device__ __forceinline__ void tr_bwd_phase(const TrPlan& P, const TrBuffers& B
       tr_bn_affine(Bf, ly, D, bnp);
     }
     if (ly.lu_bias >= 0) tr_lu_dense(S.Wlu, S.stage, Bf.theta_p, ly, D, false);
+    // this CTA's first tile: its saved activations and the gradient arriving from the layer
+    // above are its OWN data (written by its earlier phases), so their loads can be in flight
+    // while the grid barrier is pending
+    if ((int)blockIdx.x < bt.n_tiles) tr_bwd_loads(P, Bf, ly, l, S, blockIdx.x);
     TR_T(2001);
   }
   if (!(part_sel & TR_MAIN)) return;
@@ -1086,17 +1111,7 @@ __device__ __forceinline__ void tr_bwd_phase(const TrPlan& P, const TrBuffers& B
   const float* dout_in = Bf.dout[l & 1];
   float* dout_out = Bf.dout[(l - 1) & 1];
   for (int tile = blockIdx.x; tile < bt.n_tiles; tile += gridDim.x) {
-    const float* rec = Bf.ws + ((size_t)tile * P.rec_total + ly.ws_off) * TR_R;
-    const int nb = ly.rec_floats - 2 * D;
-    tr_copy_async(S.H2, rec, D);
-    tr_copy_async(S.V + ly.buf_off[1] * TR_R, rec + D * TR_R, nb);
-    tr_copy_async(S.Y, rec + (D + nb) * TR_R, D);
-    tr_copy_async(S.X, dout_in + (size_t)tile * D * TR_R, D);
-    if (l > 0) {
-      const TrLayer& lp = P.layer[l - 1];
-      tr_copy_async(S.Pf, Bf.ws + ((size_t)tile * P.rec_total + lp.ws_off + lp.rec_floats - D) * TR_R, D);
-    }
-    tr_cp_commit();
+    if (tile != (int)blockIdx.x) tr_bwd_loads(P, Bf, ly, l, S, tile);  // (the first tile: by the prologue)
     tr_prefetch_unit(Bf, ly, S, ly.n_lin - 1, 0, 0, false, P.max_dim);
     if (l == 0) tr_load_x(bt, tile, D, lperm, S.H1, S.ld);  // S.ld: scratch for the row weights
     if (threadIdx.x < TR_R) S.c[threadIdx.x] = Bf.crow[tile * TR_R + threadIdx.x];
