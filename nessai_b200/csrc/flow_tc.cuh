@@ -354,6 +354,24 @@ __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
       ::"r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
 }
+// The weight image into shared memory as bulk asynchronous copies (the TMA engine: cp.async.bulk,
+// SASS UBLKCP) that complete on an mbarrier -- no register staging, the threads go on to set up
+// barriers / tensor memory meanwhile.  ONE thread calls this; every thread that reads the image
+// (or issues MMAs on it) waits on `bar` (phase 0) after the block barrier that publishes its init.
+__device__ __forceinline__ void tc_image_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  tc_mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  const char* src = reinterpret_cast<const char*>(gsrc);
+  for (uint32_t off = 0; off < bytes; off += 32768u) {
+    const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst + off),
+        "l"(src + off), "r"(n), "r"(bar)
+        : "memory");
+  }
+}
+
 __device__ __forceinline__ void tc_fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -867,6 +885,7 @@ __device__ __forceinline__ void tc_issuer(const TcParams& P, uint32_t img_s, uin
 struct TcShared {
   uint64_t bar_in[TC_NG];
   uint64_t bar_out[TC_NG];
+  uint64_t bar_img;  // completion of the weight image's bulk copy
   uint32_t tmem_base;
   uint32_t pad;
   double cst[4][TC_DP];  // populate: scale, shift, lo, hi
@@ -881,12 +900,8 @@ __device__ __forceinline__ size_t tc_image_pad(int image_bytes) {
 __device__ __forceinline__ void tc_prologue(const TcParams& P, uint8_t* smem, TcShared*& sh) {
   sh = reinterpret_cast<TcShared*>(smem + tc_image_pad(P.image_bytes));
   const int tid = threadIdx.x;
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(P.image);
-    uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (int i = tid; i < P.image_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
-  }
   if (tid == 0) {
+    tc_image_load(tc_smem_u32(smem), P.image, (uint32_t)P.image_bytes, tc_smem_u32(&sh->bar_img));
     for (int g = 0; g < TC_NG; ++g) {
       tc_mbar_init(tc_smem_u32(&sh->bar_in[g]), 128);
       tc_mbar_init(tc_smem_u32(&sh->bar_out[g]), 1);
@@ -900,10 +915,10 @@ __device__ __forceinline__ void tc_prologue(const TcParams& P, uint8_t* smem, Tc
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  tc_fence_async_smem();  // weights were written with generic stores, the MMA reads them via the async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  tc_mbar_wait(tc_smem_u32(&sh->bar_img), 0);  // the weight image has landed
 }
 
 __device__ __forceinline__ void tc_epilogue_end(TcShared* sh) {

@@ -271,6 +271,7 @@ __device__ __forceinline__ void rs_hidden_half(uint32_t tg, int src_col, int c) 
 struct RsShared {
   uint64_t bar_in[RS_NG];
   uint64_t bar_out[RS_NG];
+  uint64_t bar_img;  // completion of the weight image's bulk copy
   uint32_t tmem_base;
   uint32_t pad;
   double cst[4][TC_DP];
@@ -425,12 +426,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_res_kernel(RsParams P, 
     }
     if (tid == 4 * TC_DP) sh->log_const = populate_log_const(A, P.D);
   }
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(P.image);
-    uint4* dst = reinterpret_cast<uint4*>(rs_smem);
-    for (int i = tid; i < P.image_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
-  }
   if (tid == 0) {
+    tc_image_load(tc_smem_u32(rs_smem), P.image, (uint32_t)P.image_bytes, tc_smem_u32(&sh->bar_img));
     for (int g = 0; g < RS_NG; ++g) {
       tc_mbar_init(tc_smem_u32(&sh->bar_in[g]), RS_EW * 32);
       tc_mbar_init(tc_smem_u32(&sh->bar_out[g]), 1);
@@ -445,10 +442,10 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_res_kernel(RsParams P, 
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  tc_fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  tc_mbar_wait(tc_smem_u32(&sh->bar_img), 0);  // the weight image has landed
   const int64_t n = MODE == 1 ? A.n : io.n;
   const int64_t ntiles = (n + 127) / 128;
   const uint32_t tmem = sh->tmem_base;

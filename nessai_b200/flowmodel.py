@@ -99,6 +99,20 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_PINNED_STAGE = [None]
+
+
+def _pinned_stage(nbytes: int) -> torch.Tensor:
+    """A page-locked uint8 staging buffer of at least ``nbytes`` (module-wide, grow-only)."""
+    buf = _PINNED_STAGE[0]
+    if buf is None or buf.numel() < nbytes:
+        size = max(int(1.5 * nbytes), 8 << 20)
+        _PINNED_STAGE[0] = None  # release the old block before page-locking the new one
+        buf = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+        _PINNED_STAGE[0] = buf
+    return buf
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -738,16 +752,17 @@ class B200FlowModel:
 
     @staticmethod
     def _to_numpy(t: torch.Tensor) -> np.ndarray:
-        """Device tensor -> float64 numpy array (what the reference returns): widened on the device,
-        ONE copy into page-locked host memory that the returned array aliases (no host-side pass)."""
+        """Device tensor -> a fresh float64 numpy array (what the reference returns): widened on the
+        device, copied once into a page-locked staging buffer that is kept and grown geometrically
+        (page-locking a new block per call costs more than the copy), then one host memcpy."""
         t = t.detach()
         if t.device.type != "cuda" or t.numel() < 4096:
             return t.cpu().numpy().astype(np.float64)
         t = t.to(torch.float64).contiguous()
-        host = torch.empty(t.shape, dtype=torch.float64, pin_memory=True)
-        host.copy_(t, non_blocking=True)
+        view = _pinned_stage(t.numel() * 8)[: t.numel() * 8].view(torch.float64).view(t.shape)
+        view.copy_(t, non_blocking=True)
         torch.cuda.current_stream(t.device).synchronize()
-        return host.numpy()
+        return view.numpy().copy()
 
     def forward_and_log_prob(self, x: np.ndarray, conditional=None) -> Tuple[np.ndarray, np.ndarray]:
         if conditional is not None:

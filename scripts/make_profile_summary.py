@@ -1,7 +1,7 @@
 """Turn gpurun_out/ ncu artefacts into the tracked text summaries under profiles/."""
 import collections, csv, os, subprocess, sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(REPO, "profiles")
+OUT = os.environ.get("PROFILE_OUT") or os.path.join(REPO, "profiles")  # PROFILE_OUT: summarise on the GPU box
 G = os.path.join(REPO, "gpurun_out")
 
 def launches(path, dst, title):
@@ -42,12 +42,24 @@ jobs = [
     ("prof_r1_coupling.ncu-rep", "r1_ncu_coupling_transform.txt", full, "coupling_vec_kernel<4> (affine coupling transform alone, 8e6 rows x 196 B)"),
     ("prof_r1_tc_v2.ncu-rep", "r1_ncu_apply_tcgen05_v2.txt", full, "flow_tc_apply_kernel v2 (FlowModel.inverse, z supplied), 1e6 rows"),
 ]
+jobs += [  # round 2
+    ("launches_r2.csv", "r2_launches_bench_step.csv", launches, "bench.py steps (C2 MLP, populate through PopulateEngine.run), round 2"),
+    ("launches_r2_train.csv", "r2_train_launches.csv", launches, "FlowModel.train on C2 (persistent kernel: one launch per chunk of epochs), round 2"),
+    ("prof_r2_tc_pop.ncu-rep", "r2_ncu_populate_tcgen05_affmma.txt", full, "flow_tc_populate_kernel, round 2 (affine on the tensor core: GEMM1 N = 80), 1e6 rows"),
+    ("prof_r2_tc_res.ncu-rep", "r2_ncu_populate_tcgen05_resnet.txt", full, "flow_tc_res_kernel<1> round 2 (fp16-split build, affine on the tensor core), ResidualNet conditioner, 1e6 rows"),
+    ("prof_r2_tc_nsf.ncu-rep", "r2_ncu_nsf_tcgen05.txt", full, "flow_tc_nsf_kernel<1> (C3: reference-trained 32-D spline flow, one layer of 6), 2e6 rows"),
+    ("prof_r2_tail.ncu-rep", "r2_ncu_reparam_tail.txt", full, "reparam_tail_kernel (logit on 8 of 16 parameters; coalesced tile IO), 1e6 rows"),
+    ("prof_r2_sumexp.ncu-rep", "r2_ncu_sum_exp.txt", full, "sum_exp_kernel, 8e6 rows"),
+    ("prof_r2_accept64.ncu-rep", "r2_ncu_accept_x64.txt", full, "accept_fused_kernel, float64-row flavour, 1e6 rows"),
+    ("prof_r2_train.ncu-rep", "r2_ncu_train_persistent.txt", full, "tr_train_kernel (persistent cooperative training kernel, 8 epochs x 2 steps, C2 MLP)"),
+]
 for src, dst, fn, title in jobs:
     p = os.path.join(G, src)
     if os.path.exists(p):
         fn(p, os.path.join(OUT, dst), title)
         print("wrote", dst)
-for j in ("bench_r1_n1.json", "bench_r1_ref.json", "bench_r1_n2.json", "bench_r1_n4.json", "bench_r1_n8.json",
+for j in ("bench_r2_n1.json", "bench_r2_ref.json", "gputest_r2.log", "tr_fine.txt",
+          "bench_r1_n1.json", "bench_r1_ref.json", "bench_r1_n2.json", "bench_r1_n4.json", "bench_r1_n8.json",
           "r1_tc_phase_timeline.txt"):
     p = os.path.join(G, j)
     if os.path.exists(p):
