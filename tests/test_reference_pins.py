@@ -157,18 +157,26 @@ def test_reset_weights_batch_norm_constants():
     assert seen == 2
 
 
-# ---- tests/test_flows/test_distributions/test_multivariate_normal.py:34-38 (var = 1: the base
-# distribution of every flow here), 6 decimals against scipy
-def test_standard_normal_base_log_prob():
+# ---- tests/test_flows/test_distributions/test_multivariate_normal.py:8-38: the base distribution
+# N(0, var I) (var = 1 is the default StandardNormal of every other flow here) against scipy
+@pytest.mark.parametrize("dims", [2, 4])
+@pytest.mark.parametrize("var", [1, 2, 4])
+def test_base_distribution_log_prob(dims, var):
     from scipy import stats
 
+    from oracle.flow_numpy import NumpyFlow
     from oracle.populate_numpy import populate_turn
 
     class Identity:  # a flow that does nothing: log q is the base density
+        base_var = float(var)
+        base_log_prob = NumpyFlow.base_log_prob
+
         @staticmethod
         def inverse(z):
             return z.copy(), np.zeros(len(z))
 
-    z = np.random.default_rng(2).standard_normal((50, 3))
-    t = populate_turn(Identity(), z, scale=np.ones(3), shift=np.zeros(3), lo=-np.inf, hi=np.inf, log_prior_const=0.0)
-    np.testing.assert_array_almost_equal(t["log_q"], stats.multivariate_normal(np.zeros(3), np.eye(3)).logpdf(z), 6)
+    z = np.random.default_rng(2).random((1000, dims))
+    t = populate_turn(Identity(), z, scale=np.ones(dims), shift=np.zeros(dims), lo=-np.inf, hi=np.inf,
+                      log_prior_const=0.0)
+    ref = stats.multivariate_normal(mean=np.zeros(dims), cov=var * np.eye(dims)).logpdf(z)
+    np.testing.assert_array_almost_equal(t["log_q"], ref)
