@@ -1,5 +1,6 @@
 set -x
 mkdir -p gpurun_out/prof
+python -c "import __graft_entry__ as g; g.build(); g.smoke()" 2>&1 | tail -2
 python -m pytest tests -m gpu -q > gpurun_out/gputest_r2.log 2>&1; tail -3 gpurun_out/gputest_r2.log
 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r2_n1.json 2> gpurun_out/bench_r2_n1.err; tail -c 300 gpurun_out/bench_r2_n1.err
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_r2_ref.json 2> gpurun_out/bench_r2_ref.err
