@@ -44,7 +44,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-lcuda", "-o", LIB_PATH, *srcs]
+    # NB200_NVCC_FLAGS: extra -D switches of an experiment build (together with NB200_LIB)
+    extra = os.environ.get("NB200_NVCC_FLAGS", "").split()
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-lcuda", "-o", LIB_PATH, *srcs]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -19,7 +19,10 @@
 
 namespace nb200 {
 
-constexpr int TR_R = 16;         // rows per tile
+#ifndef NB200_TR_R
+#define NB200_TR_R 16
+#endif
+constexpr int TR_R = NB200_TR_R;  // rows per tile
 constexpr int TR_THREADS = 512;  // threads per CTA of the row kernels (latency-bound: 4 warps / SMSP)
 constexpr int TR_RG = TR_THREADS / 64;   // row groups of the tile GEMM
 constexpr int TR_RT = TR_R / TR_RG;      // rows per thread
@@ -161,7 +164,7 @@ __device__ __forceinline__ void tr_gemm(float* __restrict__ out, const float* __
                                         const float* __restrict__ W, int ldw,
                                         const float* __restrict__ bias,
                                         const float* __restrict__ res, int N, int K, bool accum) {
-  static_assert(TR_RT == 2 && TR_R == 16 && TR_THREADS == 512, "tile GEMM register tiles");
+  static_assert(TR_THREADS == 512 && (TR_RT == 2 || TR_RT % 4 == 0), "tile GEMM register tiles");
   // (a 4-row x 256-thread mapping halves the shared-memory wavefronts but measured slower: with one
   // tile per CTA the GEMM is latency-bound and wants every warp)
   const int rg = threadIdx.x >> 6, cl = threadIdx.x & 63;
@@ -169,23 +172,41 @@ __device__ __forceinline__ void tr_gemm(float* __restrict__ out, const float* __
     const int c = c0 + cl;
     if (c < N) {
       const float b = bias ? bias[c] : 0.f;
-      float acc0 = b, acc1 = b;
-      const float2* A2 = reinterpret_cast<const float2*>(A + rg * TR_RT);
+      float acc[TR_RT];
+#pragma unroll
+      for (int i = 0; i < TR_RT; ++i) acc[i] = b;
+      const float* Ar = A + rg * TR_RT;
       const float* w = W + c;
 #pragma unroll 4
       for (int k = 0; k < K; ++k) {
         const float wk = w[k * ldw];
-        const float2 a = A2[k * (TR_R / 2)];
-        acc0 = fmaf(wk, a.x, acc0);
-        acc1 = fmaf(wk, a.y, acc1);
+        if constexpr (TR_RT == 2) {
+          const float2 a = *reinterpret_cast<const float2*>(Ar + k * TR_R);
+          acc[0] = fmaf(wk, a.x, acc[0]);
+          acc[1] = fmaf(wk, a.y, acc[1]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < TR_RT / 4; ++q) {
+            const float4 a = *reinterpret_cast<const float4*>(Ar + k * TR_R + 4 * q);
+            acc[4 * q] = fmaf(wk, a.x, acc[4 * q]);
+            acc[4 * q + 1] = fmaf(wk, a.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(wk, a.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(wk, a.w, acc[4 * q + 3]);
+          }
+        }
       }
       float* o = out + c * TR_R + rg * TR_RT;
       if (res) {
         const float* rr = res + c * TR_R + rg * TR_RT;
-        acc0 += rr[0], acc1 += rr[1];
+#pragma unroll
+        for (int i = 0; i < TR_RT; ++i) acc[i] += rr[i];
       }
-      if (accum) acc0 += o[0], acc1 += o[1];
-      o[0] = acc0, o[1] = acc1;
+      if (accum) {
+#pragma unroll
+        for (int i = 0; i < TR_RT; ++i) acc[i] += o[i];
+      }
+#pragma unroll
+      for (int i = 0; i < TR_RT; ++i) o[i] = acc[i];
     }
   }
 }
@@ -199,7 +220,7 @@ __device__ __forceinline__ void tr_wgrad(float* __restrict__ g, const float* __r
     float a[TR_R];
     const float4* A4 = reinterpret_cast<const float4*>(A + k * TR_R);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < TR_R / 4; ++q) {
       const float4 v = A4[q];
       a[4 * q] = v.x, a[4 * q + 1] = v.y, a[4 * q + 2] = v.z, a[4 * q + 3] = v.w;
     }
@@ -207,7 +228,7 @@ __device__ __forceinline__ void tr_wgrad(float* __restrict__ g, const float* __r
       const float4* d4 = reinterpret_cast<const float4*>(delta + c * TR_R);
       float s = 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < TR_R / 4; ++q) {
         const float4 v = d4[q];
         s = fmaf(v.x, a[4 * q], s);
         s = fmaf(v.y, a[4 * q + 1], s);
@@ -272,11 +293,11 @@ __device__ __forceinline__ void tr_copy(float* __restrict__ dst, const float* __
                                         int n_feat) {
   float4* d = reinterpret_cast<float4*>(dst);
   const float4* s = reinterpret_cast<const float4*>(src);
-  for (int i = threadIdx.x; i < n_feat * 4; i += TR_THREADS) d[i] = s[i];
+  for (int i = threadIdx.x; i < n_feat * (TR_R / 4); i += TR_THREADS) d[i] = s[i];
 }
 // Queue the load of a [n][16] global tile into shared memory (caller commits and waits).
 __device__ __forceinline__ void tr_copy_async(float* dst, const float* src, int n_feat) {
-  for (int i = threadIdx.x; i < n_feat * 4; i += TR_THREADS) tr_cp16(dst + 4 * i, src + 4 * i);
+  for (int i = threadIdx.x; i < n_feat * (TR_R / 4); i += TR_THREADS) tr_cp16(dst + 4 * i, src + 4 * i);
 }
 // Queue n floats (no alignment assumed).
 __device__ __forceinline__ void tr_copy_async4(float* dst, const float* src, int n) {
