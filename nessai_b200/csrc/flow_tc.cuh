@@ -104,6 +104,7 @@ struct TcProgram {
   int L = 0, D = 0;
   int d_id[TC_MAXL] = {0}, d_tr[TC_MAXL] = {0};
   int additive = 0, inverse = 0;
+  int narrow = 0;  // conditioner width <= 32: the hidden GEMMs run two K-steps, the epilogues 32 columns
   float const_logdet = 0.f;
 };
 
@@ -113,6 +114,7 @@ struct TcParams {
   int L, D;
   int d_id[TC_MAXL], d_tr[TC_MAXL];
   int additive, inverse;
+  int narrow;
   float const_logdet;
 };
 
@@ -213,7 +215,7 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
                     int activation, int final_buf) {
   t.valid = false;
   (void)final_buf;
-  if (D > TC_DP || H != TC_H || activation != ACT_RELU) return 0;
+  if (D > TC_DP || H < 1 || H > TC_H || activation != ACT_RELU) return 0;
   if (n_ops < 5 || (n_ops - 1) % 4 != 0) return 0;
   const int L = (n_ops - 1) / 4;
   if (L > TC_MAXL) return 0;
@@ -228,13 +230,13 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
     const FlowOp& b = ops[2 + 4 * l];
     const FlowOp& c = ops[3 + 4 * l];
     const FlowOp& f = ops[4 + 4 * l];
-    if (a.type != OP_LINEAR || a.src > BUF_X1 || a.dst < BUF_A0 || a.N != TC_H ||
+    if (a.type != OP_LINEAR || a.src > BUF_X1 || a.dst < BUF_A0 || a.N != H ||
         a.flags != FLAG_OUT_ACT || a.src_off != 0 || a.K < 1 || a.K > TC_TR0)
       return 0;
-    if (b.type != OP_LINEAR || b.src < BUF_A0 || b.dst < BUF_A0 || b.K != TC_H || b.N != TC_H ||
+    if (b.type != OP_LINEAR || b.src < BUF_A0 || b.dst < BUF_A0 || b.K != H || b.N != H ||
         b.flags != FLAG_OUT_ACT)
       return 0;
-    if (c.type != OP_COUPLING_AFFINE || c.K != TC_H || c.d_id != a.K || c.d_tr < 1 ||
+    if (c.type != OP_COUPLING_AFFINE || c.K != H || c.d_id != a.K || c.d_tr < 1 ||
         2 * c.d_tr > TC_N3 || c.d_id + c.d_tr != D || c.N != 2 * c.d_tr)
       return 0;
     const int inv = (c.flags & FLAG_INVERSE) ? 1 : 0, add = (c.flags & FLAG_ADDITIVE) ? 1 : 0;
@@ -275,7 +277,7 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
     const FlowOp& c = ops[3 + 4 * l];
     // GEMM1 consumes the state BEFORE the affine (so the fp32 affine runs on the CUDA cores
     // while the tensor core works): W1' = W1 A[:, identity], b1' = b1 + W1 b[identity], float64
-    for (int n = 0; n < TC_H; ++n) {
+    for (int n = 0; n < H; ++n) {
       for (int k = 0; k < D; ++k) {
         double acc = 0.0;
         for (int j = 0; j < a.K; ++j)
@@ -297,15 +299,15 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
         put_bias(lb + TC_OFF_B1, TC_H + slot(l, n), blob[f.b_off + n]);
       }
     }
-    for (int n = 0; n < TC_H; ++n) {
-      for (int k = 0; k < TC_H; ++k)
+    for (int n = 0; n < H; ++n) {
+      for (int k = 0; k < H; ++k)
         tc_put(lb + TC_OFF_W2HI, lb + TC_OFF_W2LO, TC_H, n, k, blob[b.w_off + k * b.Npad + n]);
     }
     for (int n = 0; n < c.N; ++n) {
-      for (int k = 0; k < TC_H; ++k)
+      for (int k = 0; k < H; ++k)
         tc_put(lb + TC_OFF_W3HI, lb + TC_OFF_W3LO, TC_N3, n, k, blob[c.w_off + k * c.Npad + n]);
     }
-    for (int n = 0; n < TC_H; ++n) put_bias(lb + TC_OFF_B2, n, blob[b.b_off + n]);
+    for (int n = 0; n < H; ++n) put_bias(lb + TC_OFF_B2, n, blob[b.b_off + n]);
     for (int n = 0; n < c.N; ++n) put_bias(lb + TC_OFF_B3, n, blob[c.b_off + n]);
   }
   // Affines, re-laid-out to the kernel's register slots: inside coupling layer l the
@@ -328,6 +330,7 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
   t.D = D;
   t.inverse = inverse;
   t.additive = additive;
+  t.narrow = H <= TC_H / 2;
   t.valid = true;
   return 0;
 }
@@ -590,16 +593,19 @@ __device__ __forceinline__ float tc_coupling(const uint32_t (&r)[16], float (&h)
 
 // hidden-layer epilogue: 64 accumulator columns (bias already accumulated by the
 // GEMM) -> ReLU -> split -> the row's A operand in TMEM (hi: 32 columns, lo: 32).
+// NQ: groups of 16 columns that carry hidden units (4; 2 for a conditioner of width <= 32, whose
+// other columns are the zero padding of the weight image and are not an operand of any MMA).
+template <int NQ = 4>
 __device__ __forceinline__ void tc_hidden_epilogue(uint32_t tg) {
   uint32_t ra[16], rb[16];
   tc_ld16(tg + TC_COL_D, ra);
   tc_wait_ld();
   tc_pin16(ra);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < NQ; ++q) {
     uint32_t(&cur)[16] = (q & 1) ? rb : ra;
     uint32_t(&nxt)[16] = (q & 1) ? ra : rb;
-    if (q < 3) tc_ld16(tg + TC_COL_D + 16 * (q + 1), nxt);  // in flight while `cur` is processed
+    if (q < NQ - 1) tc_ld16(tg + TC_COL_D + 16 * (q + 1), nxt);  // in flight while `cur` is processed
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -611,7 +617,7 @@ __device__ __forceinline__ void tc_hidden_epilogue(uint32_t tg) {
     }
     tc_st8(tg + TC_COL_AH + 8 * q, hi);
     tc_st8(tg + TC_COL_AL + 8 * q, lo);
-    if (q < 3) {
+    if (q < NQ - 1) {
       tc_wait_ld();
       tc_pin16(nxt);
     }
@@ -679,8 +685,9 @@ struct TcIO {
 
 // The MMAs of one conditioner GEMM of layer l (which = 1, 2, 3) for the group whose TMEM base is
 // tgu (lane field 0, warp-uniform); the WHOLE warp runs this converged, one elected lane fires.
-__device__ __forceinline__ void tc_issue_gemm(const TcParams& P, uint32_t img_s, uint32_t tgu, int l,
-                                              int which, uint32_t bar_out) {
+template <int NKS>
+__device__ __forceinline__ void tc_issue_gemm_n(const TcParams& P, uint32_t img_s, uint32_t tgu, int l,
+                                                int which, uint32_t bar_out) {
   constexpr uint32_t ID64 = tc_idesc(128, TC_H), ID16 = tc_idesc(128, TC_N3);
   const uint32_t d = tgu + TC_COL_D, ah = tgu + TC_COL_AH, al = tgu + TC_COL_AL;
   const uint32_t ones_s = img_s + P.L * TC_LAYER_BYTES + (P.L + 1) * TC_AFF_BYTES;
@@ -688,6 +695,7 @@ __device__ __forceinline__ void tc_issue_gemm(const TcParams& P, uint32_t img_s,
   const uint64_t ones = tc_desc(ones_s, 2048, 128);
   auto adv = [](uint64_t desc, uint32_t off) { return desc + (uint64_t)(off >> 4); };
   const uint32_t lb = img_s + l * TC_LAYER_BYTES;
+  constexpr int nks = NKS;  // K-steps of 16 hidden units (4; 2 for a conditioner of width <= 32)
   if (which == 1) {
     constexpr uint32_t ID1 = tc_idesc(128, TC_N1);
     const uint32_t a1h = tgu + TC_COL_A1H, a1l = tgu + TC_COL_A1L;
@@ -702,7 +710,7 @@ __device__ __forceinline__ void tc_issue_gemm(const TcParams& P, uint32_t img_s,
     const uint64_t b2 = tc_desc(lb + TC_OFF_B2, zero_s - (lb + TC_OFF_B2), 128);
     tc_mma_ss_e(d, ones, b2, ID64, 0);
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
+    for (int ks = 0; ks < nks; ++ks) {
       tc_mma_ts_e(d, ah + 8 * ks, adv(d64, TC_OFF_W2HI + ks * 2 * TC_H * 16), ID64, 1);
       tc_mma_ts_e(d, al + 8 * ks, adv(d64, TC_OFF_W2HI + ks * 2 * TC_H * 16), ID64, 1);
       tc_mma_ts_e(d, ah + 8 * ks, adv(d64, TC_OFF_W2LO + ks * 2 * TC_H * 16), ID64, 1);
@@ -712,7 +720,7 @@ __device__ __forceinline__ void tc_issue_gemm(const TcParams& P, uint32_t img_s,
     const uint64_t b3 = tc_desc(lb + TC_OFF_B3, zero_s - (lb + TC_OFF_B3), 128);
     tc_mma_ss_e(d, ones, b3, ID16, 0);
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
+    for (int ks = 0; ks < nks; ++ks) {
       tc_mma_ts_e(d, ah + 8 * ks, adv(d16, TC_OFF_W3HI + ks * 2 * TC_N3 * 16), ID16, 1);
       tc_mma_ts_e(d, al + 8 * ks, adv(d16, TC_OFF_W3HI + ks * 2 * TC_N3 * 16), ID16, 1);
       tc_mma_ts_e(d, ah + 8 * ks, adv(d16, TC_OFF_W3LO + ks * 2 * TC_N3 * 16), ID16, 1);
@@ -730,12 +738,13 @@ struct TcGroup {
   int g;            // group index
   bool first_warp;  // warp-uniform: this warp issues the group's MMAs (self-issue only)
 };
+template <bool NARROW>
 __device__ __forceinline__ void tc_submit(const TcParams& P, const TcGroup& G, int l, int which) {
   if (TC_SELF) {
     asm volatile("bar.sync %0, 128;" ::"r"(1 + G.g) : "memory");
     if (G.first_warp) {
       tc_fence_after();
-      tc_issue_gemm(P, G.img_s, G.tgu, l, which, G.bar_out);
+      tc_issue_gemm_n<NARROW ? 2 : 4>(P, G.img_s, G.tgu, l, which, G.bar_out);
     }
   } else {
     tc_mbar_arrive(G.bar_in);
@@ -745,6 +754,7 @@ __device__ __forceinline__ void tc_submit(const TcParams& P, const TcGroup& G, i
 // The epilogue-group body shared by the apply and populate kernels: runs the whole
 // program for one row held in h[] and returns the row log|det J| (without const).
 // tg: the group's TMEM base with this warp's lane quarter in the upper half-word.
+template <bool NARROW>
 __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* img, uint32_t tg,
                                             const TcGroup& G, uint32_t& ph_out, float (&h)[TC_DP]) {
   const uint32_t bar_out = G.bar_out;
@@ -765,7 +775,7 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
     }
     tc_fence_before();
     TC_STAMP_E(1);
-    tc_submit(P, G, l, 1);
+    tc_submit<NARROW>(P, G, l, 1);
     // the fp32 affine in front of the coupling, in the shadow of GEMM1
 #ifndef NB200_ABL_NO_AFFINE
     if (!TC_AFFMMA) tc_affine(aff + (size_t)l * (TC_AFF_BYTES / 4), h);
@@ -785,19 +795,19 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
 #pragma unroll
       for (int d = 0; d < TC_DP; ++d) h[d] = __uint_as_float(r[d]);
     }
-    tc_hidden_epilogue(tg);
+    tc_hidden_epilogue<NARROW ? 2 : 4>(tg);
     tc_fence_before();
     TC_STAMP_E(3);
-    tc_submit(P, G, l, 2);
+    tc_submit<NARROW>(P, G, l, 2);
     // ---- E2: hidden layer 2
     tc_mbar_wait(bar_out, ph_out);
     TC_STAMP_E(4);
     ph_out ^= 1;
     tc_fence_after();
-    tc_hidden_epilogue(tg);
+    tc_hidden_epilogue<NARROW ? 2 : 4>(tg);
     tc_fence_before();
     TC_STAMP_E(5);
-    tc_submit(P, G, l, 3);
+    tc_submit<NARROW>(P, G, l, 3);
     // ---- E3: coupling on the transformed half, then the next affine
     tc_mbar_wait(bar_out, ph_out);
     TC_STAMP_E(6);
@@ -818,8 +828,9 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
 
 // MMA issuer for one epilogue group: the WHOLE warp runs this (converged); descriptors are
 // uniform arithmetic on the shared-memory image base.
-__device__ __forceinline__ void tc_issuer(const TcParams& P, uint32_t img_s, uint32_t tg,
-                                          uint32_t bar_in, uint32_t bar_out, int64_t my_tiles) {
+template <int NKS>
+__device__ __forceinline__ void tc_issuer_n(const TcParams& P, uint32_t img_s, uint32_t tg,
+                                            uint32_t bar_in, uint32_t bar_out, int64_t my_tiles) {
   constexpr uint32_t ID64 = tc_idesc(128, TC_H), ID16 = tc_idesc(128, TC_N3);
   const uint32_t d = tg + TC_COL_D, ah = tg + TC_COL_AH, al = tg + TC_COL_AL;
   const uint32_t ones_s = img_s + P.L * TC_LAYER_BYTES + (P.L + 1) * TC_AFF_BYTES;
@@ -827,6 +838,7 @@ __device__ __forceinline__ void tc_issuer(const TcParams& P, uint32_t img_s, uin
   const uint64_t ones = tc_desc(ones_s, 2048, 128);
   // a descriptor `off` bytes further into the image: the start address field is bits [0, 14) >> 4
   auto adv = [](uint64_t desc, uint32_t off) { return desc + (uint64_t)(off >> 4); };
+  constexpr int nks = NKS;  // K-steps of 16 hidden units (4; 2 for a conditioner of width <= 32)
   uint32_t ph_in = 0;
   for (int64_t it = 0; it < my_tiles; ++it) {
     for (int l = 0; l < P.L; ++l) {
@@ -857,7 +869,7 @@ __device__ __forceinline__ void tc_issuer(const TcParams& P, uint32_t img_s, uin
       tc_fence_after();
       tc_mma_ss_e(d, ones, b2, ID64, 0);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
+      for (int ks = 0; ks < nks; ++ks) {
         tc_mma_ts_e(d, ah + 8 * ks, adv(d64, TC_OFF_W2HI + ks * 2 * TC_H * 16), ID64, 1);
         tc_mma_ts_e(d, al + 8 * ks, adv(d64, TC_OFF_W2HI + ks * 2 * TC_H * 16), ID64, 1);
         tc_mma_ts_e(d, ah + 8 * ks, adv(d64, TC_OFF_W2LO + ks * 2 * TC_H * 16), ID64, 1);
@@ -871,7 +883,7 @@ __device__ __forceinline__ void tc_issuer(const TcParams& P, uint32_t img_s, uin
       tc_fence_after();
       tc_mma_ss_e(d, ones, b3, ID16, 0);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
+      for (int ks = 0; ks < nks; ++ks) {
         tc_mma_ts_e(d, ah + 8 * ks, adv(d16, TC_OFF_W3HI + ks * 2 * TC_N3 * 16), ID16, 1);
         tc_mma_ts_e(d, al + 8 * ks, adv(d16, TC_OFF_W3HI + ks * 2 * TC_N3 * 16), ID16, 1);
         tc_mma_ts_e(d, ah + 8 * ks, adv(d16, TC_OFF_W3LO + ks * 2 * TC_N3 * 16), ID16, 1);
@@ -944,6 +956,10 @@ __device__ __forceinline__ int64_t tc_my_tiles(int64_t ntiles, int g) {
 
 #define TC_LOG_2PI 1.8378770664093453f
 
+// NARROW: conditioner width <= 32 (two K-steps in the hidden GEMMs, 32-column hidden epilogues); a
+// compile-time switch so that each instantiation's hot loop holds one variant only (both variants
+// inlined behind a run-time branch cost the wide kernels 6 - 27 %: instruction cache).
+template <bool NARROW>
 __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P, TcIO io) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   TcShared* sh;
@@ -976,7 +992,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P
       }
 #pragma unroll
       for (int d = 0; d < TC_DP; ++d) ss_in = fmaf(h[d], h[d], ss_in);
-      const float ld = tc_run_row(P, tc_smem, tg, G, ph_out, h) + P.const_logdet;
+      const float ld = tc_run_row<NARROW>(P, tc_smem, tg, G, ph_out, h) + P.const_logdet;
       float ss_out = 0.f;
 #pragma unroll
       for (int d = 0; d < TC_DP; ++d) ss_out = d < P.D ? fmaf(h[d], h[d], ss_out) : ss_out;
@@ -1002,13 +1018,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P
   } else if (!TC_SELF) {
     // issuer warp g: all 32 lanes converged, one elected lane fires each MMA
     const int g = __shfl_sync(0xffffffffu, warp - TC_NG * 4, 0);
-    tc_issuer(P, tc_smem_u32(tc_smem), __shfl_sync(0xffffffffu, tmem, 0) + g * TC_COLS,
+    tc_issuer_n<NARROW ? 2 : 4>(P, tc_smem_u32(tc_smem), __shfl_sync(0xffffffffu, tmem, 0) + g * TC_COLS,
               tc_smem_u32(&sh->bar_in[g]), tc_smem_u32(&sh->bar_out[g]), tc_my_tiles(ntiles, g));
     __syncwarp();
   }
   tc_epilogue_end(sh);
 }
 
+template <bool NARROW>
 __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParams P, PopulateArgs A) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   TcShared* sh = reinterpret_cast<TcShared*>(tc_smem + tc_image_pad(P.image_bytes));
@@ -1055,7 +1072,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParam
       }
       const float rad = sqrtf(ss) * A.sqrt_t;
       const bool alive = !(A.r_max > 0.f) || (rad <= A.r_max);
-      const float logj = tc_run_row(P, tc_smem, tg, G, ph_out, h) + P.const_logdet;
+      const float logj = tc_run_row<NARROW>(P, tc_smem, tg, G, ph_out, h) + P.const_logdet;
       const float base_lp = -0.5f * ss - 0.5f * P.D * TC_LOG_2PI;
       populate_row<TC_DP>(A, P.D, [&](int d) { return h[d]; }, row, alive, base_lp, logj, vmax,
                           vcount, c_scale, c_shift, c_lo, c_hi, log_const);
@@ -1064,7 +1081,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParam
   } else if (!TC_SELF) {
     // issuer warp g: all 32 lanes converged, one elected lane fires each MMA
     const int g = __shfl_sync(0xffffffffu, warp - TC_NG * 4, 0);
-    tc_issuer(P, tc_smem_u32(tc_smem), __shfl_sync(0xffffffffu, tmem, 0) + g * TC_COLS,
+    tc_issuer_n<NARROW ? 2 : 4>(P, tc_smem_u32(tc_smem), __shfl_sync(0xffffffffu, tmem, 0) + g * TC_COLS,
               tc_smem_u32(&sh->bar_in[g]), tc_smem_u32(&sh->bar_out[g]), tc_my_tiles(ntiles, g));
     __syncwarp();
   }
@@ -1108,6 +1125,7 @@ inline TcParams tc_params(const TcProgram& t, float const_logdet) {
   }
   P.additive = t.additive;
   P.inverse = t.inverse;
+  P.narrow = t.narrow;
   P.const_logdet = const_logdet;
   return P;
 }
@@ -1121,17 +1139,25 @@ inline int tc_grid(int64_t n, int num_sms) {
 inline int tc_launch_apply(TcProgram& t, const TcIO& io, int num_sms, cudaStream_t st) {
   const size_t smem = tc_smem_bytes(t.image_bytes);
   const int64_t n = io.n;
-  if (tc_prep((const void*)flow_tc_apply_kernel, smem)) return 1;
-  flow_tc_apply_kernel<<<tc_grid(n, num_sms), TC_THREADS, smem, st>>>(
-      tc_params(t, t.const_logdet), io);
+  if (t.narrow) {
+    if (tc_prep((const void*)flow_tc_apply_kernel<true>, smem)) return 1;
+    flow_tc_apply_kernel<true><<<tc_grid(n, num_sms), TC_THREADS, smem, st>>>(tc_params(t, t.const_logdet), io);
+  } else {
+    if (tc_prep((const void*)flow_tc_apply_kernel<false>, smem)) return 1;
+    flow_tc_apply_kernel<false><<<tc_grid(n, num_sms), TC_THREADS, smem, st>>>(tc_params(t, t.const_logdet), io);
+  }
   return cudaGetLastError() != cudaSuccess;
 }
 
 inline int tc_launch_populate(TcProgram& t, const PopulateArgs& A, int num_sms, cudaStream_t st) {
   const size_t smem = tc_smem_bytes(t.image_bytes);
-  if (tc_prep((const void*)flow_tc_populate_kernel, smem)) return 1;
-  flow_tc_populate_kernel<<<tc_grid(A.n, num_sms), TC_THREADS, smem, st>>>(
-      tc_params(t, t.const_logdet), A);
+  if (t.narrow) {
+    if (tc_prep((const void*)flow_tc_populate_kernel<true>, smem)) return 1;
+    flow_tc_populate_kernel<true><<<tc_grid(A.n, num_sms), TC_THREADS, smem, st>>>(tc_params(t, t.const_logdet), A);
+  } else {
+    if (tc_prep((const void*)flow_tc_populate_kernel<false>, smem)) return 1;
+    flow_tc_populate_kernel<false><<<tc_grid(A.n, num_sms), TC_THREADS, smem, st>>>(tc_params(t, t.const_logdet), A);
+  }
   return cudaGetLastError() != cudaSuccess;
 }
 

@@ -103,7 +103,7 @@ inline bool ns_perm_of(const FlowOp& f, const float* blob, int D, int* perm) {
 inline int ns_build(NsProgram& t, const FlowOp* ops, int n_ops, const float* blob, int D, int H,
                     int activation) {
   t.valid = false;
-  if (D > NS_DP || D < 2 || H != TC_H || activation != ACT_RELU || n_ops < 6) return 0;
+  if (D > NS_DP || D < 2 || H < 1 || H > TC_H || activation != ACT_RELU || n_ops < 6) return 0;
   int NB = -1;
   for (int nb = 1; nb <= RS_MAXNB; ++nb)
     if ((n_ops - 1) % (2 * nb + 3) == 0 && ops[2 * nb + 2].type == OP_COUPLING_SPLINE) NB = nb;
@@ -120,21 +120,21 @@ inline int ns_build(NsProgram& t, const FlowOp* ops, int n_ops, const float* blo
   for (int l = 0; l < L; ++l) {
     const FlowOp* o = ops + 1 + per * l;
     const FlowOp& a = o[0];
-    if (a.type != OP_LINEAR || a.src > BUF_X1 || a.dst < BUF_A0 || a.N != TC_H || a.flags != 0 ||
+    if (a.type != OP_LINEAR || a.src > BUF_X1 || a.dst < BUF_A0 || a.N != H || a.flags != 0 ||
         a.src_off != 0 || a.K < 1 || a.K > D)
       return 0;
     for (int b = 0; b < NB; ++b) {
       const FlowOp& x = o[1 + 2 * b];
       const FlowOp& y = o[2 + 2 * b];
-      if (x.type != OP_LINEAR || x.src != a.dst || x.dst == a.dst || x.dst < BUF_A0 || x.K != TC_H ||
-          x.N != TC_H || x.flags != (FLAG_IN_ACT | FLAG_OUT_ACT))
+      if (x.type != OP_LINEAR || x.src != a.dst || x.dst == a.dst || x.dst < BUF_A0 || x.K != H ||
+          x.N != H || x.flags != (FLAG_IN_ACT | FLAG_OUT_ACT))
         return 0;
-      if (y.type != OP_LINEAR || y.src != x.dst || y.dst != a.dst || y.K != TC_H || y.N != TC_H ||
+      if (y.type != OP_LINEAR || y.src != x.dst || y.dst != a.dst || y.K != H || y.N != H ||
           y.flags != FLAG_ACCUM)
         return 0;
     }
     const FlowOp& c = o[1 + 2 * NB];
-    if (c.type != OP_COUPLING_SPLINE || c.src != a.dst || c.K != TC_H || c.d_id != a.K || c.d_tr < 1 ||
+    if (c.type != OP_COUPLING_SPLINE || c.src != a.dst || c.K != H || c.d_id != a.K || c.d_tr < 1 ||
         c.d_id + c.d_tr != D || c.e0 != NS_K || c.e1 != NS_G || c.N != c.d_tr * NS_G || c.x_buf != c.dst)
       return 0;
     if ((c.flags & ~FLAG_INVERSE) != 0) return 0;
@@ -176,7 +176,7 @@ inline int ns_build(NsProgram& t, const FlowOp* ops, int n_ops, const float* blo
       };
       uint8_t* lb = img.data();
       // initial layer: identity feature i sits in physical slot m[i]
-      for (int n = 0; n < TC_H; ++n) {
+      for (int n = 0; n < H; ++n) {
         for (int i = 0; i < a.K; ++i)
           tc_put(lb + ly.w0hi, lb + ly.w0lo, TC_H, n, pm[i], blob[a.w_off + i * a.Npad + n]);
         put_bias(lb + ly.b0, n, blob[a.b_off + n]);
@@ -185,12 +185,12 @@ inline int ns_build(NsProgram& t, const FlowOp* ops, int n_ops, const float* blo
         uint8_t* wb = lb + ly.blk + (size_t)b * 4 * RS_W_BIG;
         const FlowOp& x = o[1 + 2 * b];
         const FlowOp& y = o[2 + 2 * b];
-        for (int n = 0; n < TC_H; ++n)
-          for (int k = 0; k < TC_H; ++k) {
+        for (int n = 0; n < H; ++n)
+          for (int k = 0; k < H; ++k) {
             tc_put(wb, wb + RS_W_BIG, TC_H, n, k, blob[x.w_off + k * x.Npad + n]);
             tc_put(wb + 2 * RS_W_BIG, wb + 3 * RS_W_BIG, TC_H, n, k, blob[y.w_off + k * y.Npad + n]);
           }
-        for (int n = 0; n < TC_H; ++n) {
+        for (int n = 0; n < H; ++n) {
           put_bias(lb + ly.bblk + (size_t)(2 * b) * RS_BIAS, n, blob[x.b_off + n]);
           put_bias(lb + ly.bblk + (size_t)(2 * b + 1) * RS_BIAS, n, blob[y.b_off + n]);
         }
@@ -200,7 +200,7 @@ inline int ns_build(NsProgram& t, const FlowOp* ops, int n_ops, const float* blo
         for (int n = 0; n < NS_CN; ++n) {
           const int col = j * NS_CN + n;  // column of the program's final layer
           if (col >= c.N) continue;
-          for (int k = 0; k < TC_H; ++k) tc_put(wh, wh + NS_WF, NS_CN, n, k, blob[c.w_off + k * c.Npad + col]);
+          for (int k = 0; k < H; ++k) tc_put(wh, wh + NS_WF, NS_CN, n, k, blob[c.w_off + k * c.Npad + col]);
           put_bias(lb + ly.bf + (size_t)j * NS_BF, n, blob[c.b_off + col]);
         }
       }

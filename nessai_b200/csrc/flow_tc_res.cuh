@@ -1,6 +1,7 @@
 // tcgen05 / TMEM kernel for RealNVP with the DEFAULT conditioner, nflows' ResidualNet
-// (/root/reference/src/nessai/flows/realnvp.py:133-146):  d_id -> 64, NB residual blocks
-// h += lin1(relu(lin0(relu(h)))), 64 -> 2*d_tr  (ReLU, D <= 16).
+// (/root/reference/src/nessai/flows/realnvp.py:133-146):  d_id -> H, NB <= 3 residual blocks
+// h += lin1(relu(lin0(relu(h)))), H -> 2*d_tr  (ReLU, D <= 16, H <= 64: narrower nets -- the
+// reference's default is H = 2 D -- are zero-padded to 64 hidden units in the weight image).
 //
 // Same scheme as flow_tc.cuh (row == TMEM lane, activations as the A operand in tensor memory,
 // split-bf16 3-pass MMAs, converged issuer warps), plus what the residual net needs:
@@ -18,7 +19,7 @@
 
 namespace nb200 {
 
-constexpr int RS_MAXNB = 2;
+constexpr int RS_MAXNB = 3;                    // residual blocks per conditioner (n_layers of the reference)
 constexpr int RS_MAXPASS = 8;
 constexpr int RS_NG = 2;                      // tiles in flight per SM
 constexpr int RS_EW = 8;                      // epilogue warps per tile
@@ -62,6 +63,7 @@ struct RsProgram {
   int L = 0, D = 0, NB = 0, n_pass = 0;
   int d_id[TC_MAXL] = {0}, d_tr[TC_MAXL] = {0};
   int additive = 0, inverse = 0;
+  int narrow = 0;  // conditioner width <= 32 (see rs_hidden_quarter)
   float const_logdet = 0.f;
   RsPass pass[RS_MAXPASS];
   float* d_scratch = nullptr;  // [rows][16] state | [rows] log|det| | [rows] sum z^2 (sign: alive)
@@ -80,6 +82,7 @@ struct RsParams {
   int l0, nl, L, D, NB;
   int d_id[TC_MAXL], d_tr[TC_MAXL];
   int additive, inverse, first, last;
+  int narrow;
   float const_logdet;
   float* sc_h;
   float* sc_ld;
@@ -90,7 +93,7 @@ struct RsParams {
 inline int rs_build(RsProgram& t, const FlowOp* ops, int n_ops, const float* blob, int D, int H,
                     int activation) {
   t.valid = false;
-  if (D > TC_DP || H != TC_H || activation != ACT_RELU || n_ops < 6) return 0;
+  if (D > TC_DP || H < 1 || H > TC_H || activation != ACT_RELU || n_ops < 6) return 0;
   // ops per layer: affine, initial linear, 2 per block, coupling
   int NB = -1;
   for (int nb = 1; nb <= RS_MAXNB; ++nb)
@@ -110,21 +113,21 @@ inline int rs_build(RsProgram& t, const FlowOp* ops, int n_ops, const float* blo
   for (int l = 0; l < L; ++l) {
     const FlowOp* o = ops + 1 + per * l;
     const FlowOp& a = o[0];
-    if (a.type != OP_LINEAR || a.src > BUF_X1 || a.dst < BUF_A0 || a.N != TC_H || a.flags != 0 ||
+    if (a.type != OP_LINEAR || a.src > BUF_X1 || a.dst < BUF_A0 || a.N != H || a.flags != 0 ||
         a.src_off != 0 || a.K < 1 || a.K > TC_TR0)
       return 0;
     for (int b = 0; b < NB; ++b) {
       const FlowOp& x = o[1 + 2 * b];
       const FlowOp& y = o[2 + 2 * b];
-      if (x.type != OP_LINEAR || x.src != a.dst || x.dst == a.dst || x.dst < BUF_A0 || x.K != TC_H ||
-          x.N != TC_H || x.flags != (FLAG_IN_ACT | FLAG_OUT_ACT))
+      if (x.type != OP_LINEAR || x.src != a.dst || x.dst == a.dst || x.dst < BUF_A0 || x.K != H ||
+          x.N != H || x.flags != (FLAG_IN_ACT | FLAG_OUT_ACT))
         return 0;
-      if (y.type != OP_LINEAR || y.src != x.dst || y.dst != a.dst || y.K != TC_H || y.N != TC_H ||
+      if (y.type != OP_LINEAR || y.src != x.dst || y.dst != a.dst || y.K != H || y.N != H ||
           y.flags != FLAG_ACCUM)
         return 0;
     }
     const FlowOp& c = o[1 + 2 * NB];
-    if (c.type != OP_COUPLING_AFFINE || c.src != a.dst || c.K != TC_H || c.d_id != a.K || c.d_tr < 1 ||
+    if (c.type != OP_COUPLING_AFFINE || c.src != a.dst || c.K != H || c.d_id != a.K || c.d_tr < 1 ||
         2 * c.d_tr > TC_N3 || c.d_id + c.d_tr != D || c.N != 2 * c.d_tr)
       return 0;
     const int inv = (c.flags & FLAG_INVERSE) ? 1 : 0, add = (c.flags & FLAG_ADDITIVE) ? 1 : 0;
@@ -181,7 +184,7 @@ inline int rs_build(RsProgram& t, const FlowOp* ops, int n_ops, const float* blo
       const FlowOp* o = ops + 1 + per * l;
       const FlowOp& a = o[0];
       // initial layer with the preceding affine folded in (float64): consumes the pre-affine state
-      for (int n = 0; n < TC_H; ++n) {
+      for (int n = 0; n < H; ++n) {
         for (int k = 0; k < D; ++k) {
           double acc = 0.0;
           for (int j = 0; j < a.K; ++j)
@@ -206,19 +209,19 @@ inline int rs_build(RsProgram& t, const FlowOp* ops, int n_ops, const float* blo
         uint8_t* wb = lb + lay.blk + (size_t)b * 4 * RS_W_BIG;
         const FlowOp& x = o[1 + 2 * b];
         const FlowOp& y = o[2 + 2 * b];
-        for (int n = 0; n < TC_H; ++n)
-          for (int k = 0; k < TC_H; ++k) {
+        for (int n = 0; n < H; ++n)
+          for (int k = 0; k < H; ++k) {
             tc_put(wb, wb + RS_W_BIG, TC_H, n, k, blob[x.w_off + k * x.Npad + n]);
             tc_put(wb + 2 * RS_W_BIG, wb + 3 * RS_W_BIG, TC_H, n, k, blob[y.w_off + k * y.Npad + n]);
           }
-        for (int n = 0; n < TC_H; ++n) {
+        for (int n = 0; n < H; ++n) {
           put_bias(lb + lay.bblk + (size_t)(2 * b) * RS_BIAS, n, blob[x.b_off + n]);
           put_bias(lb + lay.bblk + (size_t)(2 * b + 1) * RS_BIAS, n, blob[y.b_off + n]);
         }
       }
       const FlowOp& c = o[1 + 2 * NB];
       for (int n = 0; n < c.N; ++n) {
-        for (int k = 0; k < TC_H; ++k)
+        for (int k = 0; k < H; ++k)
           tc_put(lb + lay.wfhi, lb + lay.wflo, TC_N3, n, k, blob[c.w_off + k * c.Npad + n]);
         put_bias(lb + lay.bf, n, blob[c.b_off + n]);
       }
@@ -239,6 +242,7 @@ inline int rs_build(RsProgram& t, const FlowOp* ops, int n_ops, const float* blo
   t.n_pass = n_pass;
   t.inverse = inverse;
   t.additive = additive;
+  t.narrow = H <= TC_H / 2;
   t.valid = true;
   return 0;
 }
@@ -268,6 +272,29 @@ __device__ __forceinline__ void rs_hidden_half(uint32_t tg, int src_col, int c) 
   tc_wait_st();
 }
 
+// Conditioner width <= 32: only accumulator columns 0 .. 31 carry hidden units (the rest is the
+// zero padding of the weight image, never an MMA operand: the hidden GEMMs run K-steps 0 and 1).
+// The twin warps split those 32 columns: warp column-half c handles K chunk c.
+template <bool RELU>
+__device__ __forceinline__ void rs_hidden_quarter(uint32_t tg, int src_col, int c) {
+  uint32_t ra[16];
+  tc_ld16(tg + src_col + 16 * c, ra);
+  tc_wait_ld();
+  tc_pin16(ra);
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    tc_split2<RELU>(__uint_as_float(ra[2 * j]), __uint_as_float(ra[2 * j + 1]), hi[j], lo[j]);
+  tc_st8(tg + RS_COL_AH + 8 * c, hi);
+  tc_st8(tg + RS_COL_AL + 8 * c, lo);
+  tc_wait_st();
+}
+template <bool RELU, bool NARROW>
+__device__ __forceinline__ void rs_hidden(uint32_t tg, int src_col, int c) {
+  if (NARROW) rs_hidden_quarter<RELU>(tg, src_col, c);
+  else rs_hidden_half<RELU>(tg, src_col, c);
+}
+
 struct RsShared {
   uint64_t bar_in[RS_NG];
   uint64_t bar_out[RS_NG];
@@ -290,6 +317,7 @@ __device__ __forceinline__ void rs_arrive(uint32_t bar_in) {
 
 // All layers of this pass for one row.  c == 0 threads own the row state h[]; c == 1 threads
 // only help with the hidden epilogues.  Returns the row log|det J| accumulated in this pass.
+template <bool NARROW>
 __device__ __forceinline__ float rs_run_row(const RsParams& P, const uint8_t* img, const RsLayout& lay,
                                             uint32_t tg, int c, uint32_t bar_in, uint32_t bar_out,
                                             uint32_t& ph, float (&h)[TC_DP]) {
@@ -319,14 +347,14 @@ __device__ __forceinline__ float rs_run_row(const RsParams& P, const uint8_t* im
 #pragma unroll
         for (int d = 0; d < TC_DP; ++d) h[d] = __uint_as_float(r[d]);
       }
-      rs_hidden_half<true>(tg, RS_COL_D, c);
+      rs_hidden<true, NARROW>(tg, RS_COL_D, c);
       rs_arrive(bar_in);                                         // -> Ga: D2 = Wa relu(D) + ba
       rs_wait(bar_out, ph);
-      rs_hidden_half<true>(tg, RS_COL_D2, c);
+      rs_hidden<true, NARROW>(tg, RS_COL_D2, c);
       rs_arrive(bar_in);                                         // -> Gb: D += Wb relu(D2) + bb
     }
     rs_wait(bar_out, ph);
-    rs_hidden_half<false>(tg, RS_COL_D, c);
+    rs_hidden<false, NARROW>(tg, RS_COL_D, c);
     rs_arrive(bar_in);                                           // -> Gf: D2[0:16] = Wf D + bf
     rs_wait(bar_out, ph);
     if (c == 0) {
@@ -341,9 +369,10 @@ __device__ __forceinline__ float rs_run_row(const RsParams& P, const uint8_t* im
   return ld;
 }
 
-__device__ __forceinline__ void rs_issuer(const RsParams& P, const RsLayout& lay, uint32_t img_s,
-                                          uint32_t tg, uint32_t bar_in, uint32_t bar_out,
-                                          int64_t my_tiles) {
+template <int NKS>
+__device__ __forceinline__ void rs_issuer_n(const RsParams& P, const RsLayout& lay, uint32_t img_s,
+                                            uint32_t tg, uint32_t bar_in, uint32_t bar_out,
+                                            int64_t my_tiles) {
   constexpr uint32_t ID64 = tc_idesc(128, TC_H), ID16 = tc_idesc(128, TC_N3);
   const uint32_t d = tg + RS_COL_D, d2 = tg + RS_COL_D2, ah = tg + RS_COL_AH, al = tg + RS_COL_AL;
   const int n_aff = P.nl + (P.last ? 1 : 0);
@@ -352,12 +381,13 @@ __device__ __forceinline__ void rs_issuer(const RsParams& P, const RsLayout& lay
   const uint64_t ones = tc_desc(ones_s, 2048, 128);
   auto adv = [](uint64_t desc, uint32_t off) { return desc + (uint64_t)(off >> 4); };
   auto bias = [&](uint32_t addr) { return tc_desc(addr, zero_s - addr, 128); };
+  constexpr int nks = NKS;  // K-steps of 16 hidden units (4; 2 for a conditioner of width <= 32)
   // one K = 64 GEMM: acc0 = accumulate flag of the bias MMA
   auto gemm64 = [&](uint32_t dst, uint64_t bdesc, uint64_t whi, uint64_t wlo, uint32_t rows,
                     uint32_t idesc, uint32_t acc0) {
     tc_mma_ss_e(dst, ones, bdesc, idesc, acc0);
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
+    for (int ks = 0; ks < nks; ++ks) {
       tc_mma_ts_e(dst, ah + 8 * ks, adv(whi, ks * 2 * rows * 16), idesc, 1);
       tc_mma_ts_e(dst, al + 8 * ks, adv(whi, ks * 2 * rows * 16), idesc, 1);
       tc_mma_ts_e(dst, ah + 8 * ks, adv(wlo, ks * 2 * rows * 16), idesc, 1);
@@ -412,7 +442,8 @@ __device__ __forceinline__ int64_t rs_my_tiles(int64_t ntiles, int g) {
 
 // MODE 0: apply (rows supplied), MODE 1: populate (Philox draw in the first pass, float64 tail
 // in the last).  A must be valid for MODE 1, io for MODE 0.
-template <int MODE>
+// NARROW: conditioner width <= 32, a compile-time switch (see flow_tc.cuh).
+template <int MODE, bool NARROW>
 __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_res_kernel(RsParams P, TcIO io, PopulateArgs A) {
   extern __shared__ __align__(1024) uint8_t rs_smem[];
   RsShared* sh = reinterpret_cast<RsShared*>(rs_smem + tc_image_pad(P.image_bytes));
@@ -513,7 +544,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_res_kernel(RsParams P, 
           alive = !(A.r_max > 0.f) || (rad <= A.r_max);
         }
       }
-      const float ld = ld0 + rs_run_row(P, rs_smem, lay, tg, c, bar_in, bar_out, ph, h);
+      const float ld = ld0 + rs_run_row<NARROW>(P, rs_smem, lay, tg, c, bar_in, bar_out, ph, h);
       if (c != 0) continue;
       if (!P.last) {
         if (valid) {
@@ -556,7 +587,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_res_kernel(RsParams P, 
     if (MODE == 1 && P.last && c == 0) populate_publish(A, vmax, vcount);
   } else {
     const int g = __shfl_sync(0xffffffffu, warp - RS_NG * RS_EW, 0);
-    rs_issuer(P, lay, tc_smem_u32(rs_smem), __shfl_sync(0xffffffffu, tmem, 0) + g * RS_COLS,
+    rs_issuer_n<NARROW ? 2 : 4>(P, lay, tc_smem_u32(rs_smem), __shfl_sync(0xffffffffu, tmem, 0) + g * RS_COLS,
               tc_smem_u32(&sh->bar_in[g]), tc_smem_u32(&sh->bar_out[g]), rs_my_tiles(ntiles, g));
     __syncwarp();
   }
@@ -596,7 +627,8 @@ inline int rs_launch(RsProgram& t, const TcIO& io, const PopulateArgs& A, int64_
   for (int p = 0; p < t.n_pass; ++p) {
     const RsPass& ps = t.pass[p];
     const size_t smem = rs_smem_bytes(ps.image_bytes);
-    if (tc_prep((const void*)flow_tc_res_kernel<MODE>, smem)) return 0;
+    if (tc_prep(t.narrow ? (const void*)flow_tc_res_kernel<MODE, true> : (const void*)flow_tc_res_kernel<MODE, false>, smem))
+      return 0;
     RsParams P;
     P.image = ps.d_image;
     P.image_bytes = ps.image_bytes;
@@ -610,11 +642,13 @@ inline int rs_launch(RsProgram& t, const TcIO& io, const PopulateArgs& A, int64_
     P.inverse = t.inverse;
     P.first = p == 0;
     P.last = p == t.n_pass - 1;
+    P.narrow = t.narrow;
     P.const_logdet = t.const_logdet;
     P.sc_h = t.d_scratch;
     P.sc_ld = t.d_scratch ? t.d_scratch + (size_t)t.scratch_rows * TC_DP : nullptr;
     P.sc_ss = t.d_scratch ? t.d_scratch + (size_t)t.scratch_rows * (TC_DP + 1) : nullptr;
-    flow_tc_res_kernel<MODE><<<rs_grid(n, num_sms), RS_THREADS, smem, st>>>(P, io, A);
+    if (t.narrow) flow_tc_res_kernel<MODE, true><<<rs_grid(n, num_sms), RS_THREADS, smem, st>>>(P, io, A);
+    else flow_tc_res_kernel<MODE, false><<<rs_grid(n, num_sms), RS_THREADS, smem, st>>>(P, io, A);
     if (cudaGetLastError() != cudaSuccess) return 0;
   }
   return t.n_pass;

@@ -190,3 +190,70 @@ def test_tensor_core_paths_match_generic_kernel(name, launches, n, tmp_path):
         np.testing.assert_allclose(a, b, rtol=RTOL, atol=ATOL)
     # round trip through the tensor-core kernels
     np.testing.assert_allclose(out[1][3], z.cpu().numpy(), rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("ftype,net,D,H,n_layers,launches", [
+    ("realnvp", "mlp", 16, 32, 2, 1),     # nessai's default width: 2 * n_inputs
+    ("realnvp", "mlp", 4, 8, 2, 1),
+    ("realnvp", "resnet", 16, 32, 2, 2),  # the default conditioner at its default width
+    ("realnvp", "resnet", 7, 14, 2, 2),
+    ("realnvp", "resnet", 12, 40, 1, 1),
+    ("realnvp", "resnet", 8, 16, 3, 3),   # three residual blocks: 113 KB of weights a layer, one layer a pass
+    ("realnvp", "resnet", 16, 64, 3, 3),
+    ("nsf", "resnet", 10, 20, 2, 3),
+    ("nsf", "resnet", 32, 48, 2, 3),
+])
+def test_hidden_width_below_64_runs_on_the_tensor_core_kernels(ftype, net, D, H, n_layers, launches, tmp_path):
+    """The reference's DEFAULT conditioner width is 2 * n_inputs
+    (/root/reference/src/nessai/flows/utils.py:105-165, flowmodel/utils.py:39-42), not the 64 of
+    BASELINE's C2: the tcgen05 kernels take every width <= 64 (hidden units zero-padded to 64 in the
+    weight images).  Checked against the float64 oracle and the generic fp32 kernel; the launch
+    count proves which path ran."""
+    from nessai_b200 import _lib
+    from nessai_b200.flowmodel import B200FlowModel
+    from test_oracle import numpy_flow
+
+    cfg = dict(n_inputs=D, n_neurons=H, n_blocks=3, n_layers=n_layers, ftype=ftype)
+    if ftype == "realnvp":
+        cfg["net"] = net
+    torch.manual_seed(100 * D + H)
+    fm = B200FlowModel(flow_config=cfg, training_config=dict(device_tag="cuda:0"), output=str(tmp_path))
+    fm.initialise()
+    rng = np.random.default_rng(D * H)
+    sd = {}
+    for k, v in fm.model.state_dict().items():
+        a = v.cpu().numpy()
+        if a.dtype.kind == "f":
+            a = a + (0.05 * rng.standard_normal(a.shape)).astype(np.float32)  # (kept well conditioned)
+            if "running_var" in k:
+                a = np.abs(a) + 0.5
+        sd[k] = a
+    fm.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    fm.model.eval()
+    lib = _lib.load()
+    n = 1000
+    z = rng.normal(size=(n, D)).astype(np.float32)
+    zt = torch.from_numpy(z).cuda()
+    out = {}
+    try:
+        for tc in (1, 0):
+            lib.nb200_set_tensor_core_path(tc)
+            _lib.reset_launch_count()
+            x, logj, logq = fm.model._inverse(zt)
+            n_launch = _lib.launch_count()
+            zz, flogj, logp = fm.model._forward(x)
+            torch.cuda.synchronize()
+            out[tc] = [t.cpu().numpy() for t in (x, logj, logq, zz, flogj, logp)]
+            assert n_launch == (launches if tc else 1)
+    finally:
+        lib.nb200_set_tensor_core_path(1)
+    nf = numpy_flow(cfg, sd)
+    x64, ilj64 = nf.inverse(z.astype(np.float64))
+    tol = dict(rtol=2e-4, atol=2e-4) if ftype == "nsf" else dict(rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(out[1][0], x64, **tol)
+    np.testing.assert_allclose(out[1][1], ilj64, **tol)
+    np.testing.assert_allclose(out[1][5], nf.log_prob(out[1][0].astype(np.float64)), **tol)
+    for a, b in zip(out[1], out[0]):
+        assert np.isfinite(a).all()
+        np.testing.assert_allclose(a, b, **tol)
+    np.testing.assert_allclose(out[1][3], z, rtol=5e-4, atol=5e-4)
