@@ -55,6 +55,7 @@ struct NsLayerInfo {
 };
 struct NsProgram {
   bool valid = false;
+  int narrow = 0;  // conditioner width <= 32: two K-steps, 32-column hidden epilogues (flow_tc.cuh)
   int L = 0, D = 0, NB = 0, nch = 0, inverse = 0;
   float tail_bound = 0.f, const_logdet = 0.f;
   NsLayerInfo layer[TC_MAXL];
@@ -220,6 +221,7 @@ inline int ns_build(NsProgram& t, const FlowOp* ops, int n_ops, const float* blo
   t.nch = nch;
   t.inverse = inverse;
   t.tail_bound = B;
+  t.narrow = H <= TC_H / 2;
   t.valid = true;
   return 0;
 }
@@ -386,6 +388,7 @@ __device__ __forceinline__ void ns_chunk(const NsParams& P, uint32_t tg, int c, 
 
 // One layer pass for one row; the state is in TMEM columns NS_COL_ST.., the log|det| partial of
 // this thread is returned (c == 0 and c == 1 threads of a row each sum their own features).
+template <bool NARROW>
 __device__ __forceinline__ float ns_run_layer(const NsParams& P, const NsLayout& lay, uint32_t tg, int g, int c,
                                               NsBars& B) {
   float ld = 0.f;
@@ -404,14 +407,14 @@ __device__ __forceinline__ float ns_run_layer(const NsParams& P, const NsLayout&
   rs_arrive(B.in);  // -> G0
   for (int b = 0; b < P.NB; ++b) {
     rs_wait(B.out, B.ph);
-    rs_hidden_half<true>(tg, NS_COL_D, c);
+    rs_hidden<true, NARROW>(tg, NS_COL_D, c);
     rs_arrive(B.in);
     rs_wait(B.out, B.ph);
-    rs_hidden_half<true>(tg, NS_COL_D2, c);
+    rs_hidden<true, NARROW>(tg, NS_COL_D2, c);
     rs_arrive(B.in);
   }
   rs_wait(B.out, B.ph);
-  rs_hidden_half<false>(tg, NS_COL_D, c);
+  rs_hidden<false, NARROW>(tg, NS_COL_D, c);
   // The final layer's chunks alternate between the two accumulators (the residual stream in D is
   // dead once its activation is the A operand), so chunk j + 1 is computed while chunk j's
   // splines run: Gf chunk j: (D2 | D)[0:48] = Wf_j a + bf_j
@@ -424,6 +427,7 @@ __device__ __forceinline__ float ns_run_layer(const NsParams& P, const NsLayout&
   return ld;
 }
 
+template <int NKS>
 __device__ __forceinline__ void ns_issuer(const NsParams& P, const NsLayout& lay, uint32_t img_s, uint32_t tg,
                                           const NsBars& B, int64_t my_tiles) {
   const uint32_t bar_in = B.in, bar_out = B.out;
@@ -438,7 +442,7 @@ __device__ __forceinline__ void ns_issuer(const NsParams& P, const NsLayout& lay
                     uint32_t acc0) {
     tc_mma_ss_e(dst, ones, bdesc, idesc, acc0);
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
+    for (int ks = 0; ks < NKS; ++ks) {  // K-steps of 16 hidden units (4; 2 for a conditioner of width <= 32)
       tc_mma_ts_e(dst, ah + 8 * ks, adv(whi, ks * 2 * rows * 16), idesc, 1);
       tc_mma_ts_e(dst, al + 8 * ks, adv(whi, ks * 2 * rows * 16), idesc, 1);
       tc_mma_ts_e(dst, ah + 8 * ks, adv(wlo, ks * 2 * rows * 16), idesc, 1);
@@ -498,7 +502,7 @@ __device__ __forceinline__ void ns_issuer(const NsParams& P, const NsLayout& lay
 }
 
 // MODE 0: apply (rows supplied), MODE 1: populate.  One coupling layer per launch.
-template <int MODE>
+template <int MODE, bool NARROW>
 __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_nsf_kernel(NsParams P, TcIO io, PopulateArgs A) {
   extern __shared__ __align__(1024) uint8_t ns_smem[];
   NsShared* sh = reinterpret_cast<NsShared*>(ns_smem + tc_image_pad(P.image_bytes));
@@ -617,7 +621,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_nsf_kernel(NsParams P, 
           ns_tile_sync(g);  // LD columns are reused below
         }
       }
-      float ld = ns_run_layer(P, lay, tg, g, c, B);
+      float ld = ns_run_layer<NARROW>(P, lay, tg, g, c, B);
       // ---- combine the two halves' log|det| and hand the row on
       ns_st1(tg + NS_COL_LD + c, __float_as_uint(ld));
       tc_wait_st();
@@ -691,7 +695,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_nsf_kernel(NsParams P, 
     const NsBars B{tc_smem_u32(&sh->bar_in[g]),    tc_smem_u32(&sh->bar_out[g]),   tc_smem_u32(&sh->bar_cr[g][0]),
                    tc_smem_u32(&sh->bar_cr[g][1]), tc_smem_u32(&sh->bar_cf[g][0]), tc_smem_u32(&sh->bar_cf[g][1]),
                    0u, 0u, 0u};
-    ns_issuer(P, lay, tc_smem_u32(ns_smem), __shfl_sync(0xffffffffu, tmem, 0) + g * NS_COLS, B,
+    ns_issuer<NARROW ? 2 : 4>(P, lay, tc_smem_u32(ns_smem), __shfl_sync(0xffffffffu, tmem, 0) + g * NS_COLS, B,
               rs_my_tiles(ntiles, g));
     __syncwarp();
   }
@@ -723,7 +727,8 @@ template <int MODE>
 inline int ns_launch(NsProgram& t, const TcIO& io, const PopulateArgs& A, int64_t n, int num_sms, cudaStream_t st) {
   if (ns_reserve(t, n)) return 0;
   const size_t smem = ns_smem_bytes(t.image_bytes);
-  if (tc_prep((const void*)flow_tc_nsf_kernel<MODE>, smem)) return 0;
+  if (tc_prep(t.narrow ? (const void*)flow_tc_nsf_kernel<MODE, true> : (const void*)flow_tc_nsf_kernel<MODE, false>, smem))
+    return 0;
   for (int l = 0; l < t.L; ++l) {
     NsParams P;
     P.image = t.d_image[l];
@@ -742,7 +747,8 @@ inline int ns_launch(NsProgram& t, const TcIO& io, const PopulateArgs& A, int64_
     P.sc_h = t.d_scratch;
     P.sc_ld = t.d_scratch ? t.d_scratch + (size_t)t.scratch_rows * NS_DP : nullptr;
     P.sc_ss = t.d_scratch ? t.d_scratch + (size_t)t.scratch_rows * (NS_DP + 1) : nullptr;
-    flow_tc_nsf_kernel<MODE><<<rs_grid(n, num_sms), RS_THREADS, smem, st>>>(P, io, A);
+    if (t.narrow) flow_tc_nsf_kernel<MODE, true><<<rs_grid(n, num_sms), RS_THREADS, smem, st>>>(P, io, A);
+    else flow_tc_nsf_kernel<MODE, false><<<rs_grid(n, num_sms), RS_THREADS, smem, st>>>(P, io, A);
     if (cudaGetLastError() != cudaSuccess) return 0;
   }
   return t.L;

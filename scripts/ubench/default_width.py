@@ -7,8 +7,10 @@ from nessai_b200 import _lib
 from nessai_b200.flowmodel import B200FlowModel
 lib = _lib.load()
 n = 1_000_000
-for D, net in ((16, "resnet"), (8, "resnet"), (4, "resnet"), (2, "resnet"), (16, "mlp")):
+for D, net in ((16, "resnet"), (8, "resnet"), (4, "resnet"), (2, "resnet"), (16, "mlp"), (16, "nsf"), (8, "nsf")):
     cfg = dict(n_inputs=D, n_blocks=4, n_layers=2, ftype="realnvp", net=net)  # n_neurons: the default
+    if net == "nsf":
+        cfg = dict(n_inputs=D, n_blocks=4, n_layers=2, ftype="nsf")
     torch.manual_seed(D)
     fm = B200FlowModel(flow_config=cfg, training_config=dict(device_tag="cuda:0"), output=tempfile.mkdtemp())
     fm.initialise(); fm.model.eval()
