@@ -208,7 +208,8 @@ def build_proposal(fixture, model, live_s, local_rank, pool):
 
     from nessai_b200.proposal import B200FlowProposal
 
-    cfg, sd = load_fixture(fixture)
+    # (a dict: that flow_config, freshly initialised -- the reference's init -- instead of fixture weights)
+    cfg, sd = (dict(fixture), None) if isinstance(fixture, dict) else load_fixture(fixture)
     torch.manual_seed(SEED)
     prop = B200FlowProposal(
         model, rng=np.random.default_rng(SEED), flow_config=cfg,
@@ -217,7 +218,8 @@ def build_proposal(fixture, model, live_s, local_rank, pool):
     )
     prop.initialise()
     prop.check_state(live_s)  # z-score statistics
-    prop.flow.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    if sd is not None:
+        prop.flow.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
     prop.flow.model.eval()
     return prop
 
@@ -441,8 +443,21 @@ def run_ours(args):
         }
         if not args.no_cpu_baseline:
             resnet["cpu_baseline"] = cpu_baseline(threads=1, pool=min(args.cpu_pool, 200_000), fixture="c2_realnvp_resnet")
+        # the reference's DEFAULT flow for a 16-parameter model: ResidualNet conditioner of width
+        # 2 * n_inputs = 32 (flowmodel/utils.py:39-42); freshly initialised weights (no fixture of that shape)
+        del prop_r
+        prop_d = build_proposal(dict(n_inputs=D, n_blocks=4, n_layers=2, ftype="realnvp"), model, live_s, local_rank, pool)
+        md = measure(prop_d, worst, pool, args.steps, args.warmup, max(5, repeats // 4), world, dev, kernel_reps=10)
+        default_flow = {
+            "workload": "C2'': the headline call with the reference's default flow_config for 16 parameters "
+                        "(ResidualNet, n_neurons = 2 * n_inputs = 32; freshly initialised), through B200FlowProposal.populate",
+            "value": md["value"], "value_iqr": md["value_iqr"], "ms_per_step": md["ms_per_step"],
+            "e2e": md["e2e"], "e2e_iqr": md["e2e_iqr"], "kernel_ms": md["kernel_ms"],
+        }
+        del prop_d
         out["coupling_forward"] = coupling_roofline(dev, peaks, which)
         out["variants"] = {"c2_resnet_default_conditioner": resnet,
+                           "c2_default_width": default_flow,
                            "train": train_variant("ours"),
                            "c3": c3_block(args, local_rank, dev, repeats, peaks, which),
                            "c5": c5_variant("ours"),
