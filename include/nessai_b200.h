@@ -144,12 +144,22 @@ int nb200_populate_accept_x64(int64_t n, int D, const double* d_x64, const doubl
  * for rows outside d_lo/d_hi, with non-finite log_q or log_q <= min_log_q), writes
  * d_x64 float64[n*D], and accumulates d_stats = {max log_w, n_valid} (reset by the caller).
  * Pair kinds, reparameterisations/angle.py:17-186 (Angle.inverse_reparameterise): output slot d
- * reads TWO flow features (u0, u1) = (x'[d_src[2d]], x'[d_src[2d+1]]): kind 7 the angle
+ * reads TWO flow features (u0, u1) = (x'[d_src[3d]], x'[d_src[3d+1]]): kind 7 the angle
  * atan2(u1, u0) * scale + shift (scale = 1 / Angle.scale; no log|J| for that constant, as in the
  * reference), 8 the same modulo 2 pi (prior starting at zero, angle.py:158-166), 9 the radius
  * sqrt(u0^2 + u1^2) with log|J| -= log r (:172), 10 the same for an AUXILIARY radius whose chi(2)
- * prior log r - r^2/2 (:183-185) is added to log_w.  d_src int32[2*D] or NULL (slot d reads
- * feature d); for the other kinds only d_src[2d] is used.
+ * prior log r - r^2/2 (:183-185) is added to log_w.
+ * Kind 11 (single feature): floor(u), no log|J| -- Dequantise's pre-rescaling inverse
+ * (reparameterisations/discrete.py:66-78).  Kind 12, ToCartesian (angle.py:189-232):
+ * |atan2(u1, u0) * a| * scale + shift with a = d_pre_scale[d] = 1 / ToCartesian.scale and
+ * scale = hi - lo, shift = lo of the prior bounds, log|J| += log(hi - lo).
+ * Triple kinds, AnglePair (angle.py:235-538): (u0, u1, u2) = the Cartesian (x, y, z); the horizontal
+ * angle is kind 7 / 8 of (u0, u1); 13 the zenith atan2(sqrt(u0^2 + u1^2), u2) with
+ * log|J| -= log sin(.), 14 the declination atan2(u2, sqrt(u0^2 + u1^2)) with log|J| -= log cos(.),
+ * 15 the radius sqrt(u0^2 + u1^2 + u2^2) with log|J| -= 2 log r, 16 the same for an auxiliary
+ * radius whose chi(3) prior (:529-537) is added to log_w.
+ * d_src int32[3*D] or NULL (slot d reads feature d): the flow features output slot d reads; the
+ * single-feature kinds use d_src[3d] only, the pair kinds d_src[3d], d_src[3d+1].
  * d_kind int32[D], d_scale/d_shift/d_lo/d_hi float64[D] on the device; d_pre_scale /
  * d_pre_shift float64[D] or both NULL (a = 1, b = 0); D <= 64. */
 int nb200_reparam_tail(int64_t n, int D, const float* d_xp, const int32_t* d_kind,

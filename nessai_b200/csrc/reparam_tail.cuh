@@ -42,8 +42,22 @@ enum TailKind : int32_t {
   TAIL_RADIUS = 9,      // sqrt(u0^2 + u1^2), log|J| -= log r
   TAIL_RADIUS_CHI = 10, // the same for an AUXILIARY radius: its chi(2) prior log r - r^2 / 2 is
                         // added to the log prior (angle.py:183-185)
-  TAIL_N_KINDS = 11
+  // a single-feature kind again: Dequantise (reparameterisations/discrete.py:66-78), whose
+  // pre-rescaling inverse is floor(.) with no log-Jacobian
+  TAIL_FLOOR = 11,
+  // ToCartesian (angle.py:189-232): |atan2(u1, u0) * a| * scale + shift with a = 1 / ToCartesian.scale,
+  // scale = hi - lo, shift = lo of the prior bounds; log|J| += log(hi - lo) (inverse_rescale_zero_to_one)
+  TAIL_ANGLE_ABS = 12,
+  // AnglePair (angle.py:235-538): THREE flow features (u0, u1, u2) = Cartesian (x, y, z); the
+  // horizontal angle is TAIL_ANGLE / TAIL_ANGLE_MOD of (u0, u1)
+  TAIL_ZENITH = 13,       // az-zen: atan2(sqrt(u0^2 + u1^2), u2), log|J| -= log sin(.)   (:418-452)
+  TAIL_DECLINATION = 14,  // ra-dec: atan2(u2, sqrt(u0^2 + u1^2)), log|J| -= log cos(.)   (:454-489)
+  TAIL_RADIUS3 = 15,      // sqrt(u0^2 + u1^2 + u2^2), log|J| -= 2 log r
+  TAIL_RADIUS3_CHI = 16,  // the same for an AUXILIARY radius with its chi(3) prior (:529-537)
+  TAIL_N_KINDS = 17
 };
+// kinds that read two or three flow features
+NB200_HD bool tail_is_multi(int32_t kind) { return kind >= TAIL_PAIR_FIRST && kind != TAIL_FLOOR; }
 
 #ifdef __CUDACC__
 #define NB200_ERFCINV erfcinv
@@ -76,20 +90,38 @@ NB200_HD double tail_feature(int32_t kind, double a, double b, double scale, dou
   } else if (kind == TAIL_NORMAL_QUANTILE) {
     h = -1.4142135623730951 * NB200_ERFCINV(2.0 * u);
     logj += 0.9189385332046727 + 0.5 * h * h;
+  } else if (kind == TAIL_FLOOR) {
+    h = floor(u);
   }
   return h * scale + shift;
 }
 
-// A pair kind: x from (u0, u1); the constant factor of the angle has NO log-Jacobian in the
-// reference (angle.py:120-128,157-170), so scale / shift of pair kinds stay out of the row constant.
-NB200_HD double tail_pair(int32_t kind, double scale, double shift, double u0, double u1, double& logj,
-                          double& logp_extra) {
+// A pair / triple kind: x from (u0, u1[, u2]); the constant factor of the angle has NO log-Jacobian
+// in the reference (angle.py:120-128,157-170), so scale / shift of these kinds stay out of the row
+// constant -- except TAIL_ANGLE_ABS, whose map back to the prior bounds has one (tail_log_affine_sum).
+NB200_HD double tail_pair(int32_t kind, double a, double scale, double shift, double u0, double u1, double u2,
+                          double& logj, double& logp_extra) {
   if (kind == TAIL_ANGLE || kind == TAIL_ANGLE_MOD) {
     double th = atan2(u1, u0);
     // numpy's `% (2 pi)` of a value in [-pi, pi]: fmod, then + 2 pi when negative (a tiny
     // negative angle therefore gives exactly 2 pi, as it does in the reference)
     if (kind == TAIL_ANGLE_MOD && th < 0.0) th += 6.283185307179586;
     return th * scale + shift;
+  }
+  if (kind == TAIL_ANGLE_ABS) return fabs(atan2(u1, u0) * a) * scale + shift;
+  if (kind == TAIL_ZENITH || kind == TAIL_DECLINATION) {
+    const double rho = sqrt(u0 * u0 + u1 * u1);
+    const double v = kind == TAIL_ZENITH ? atan2(rho, u2) : atan2(u2, rho);
+    logj -= log(kind == TAIL_ZENITH ? sin(v) : cos(v));
+    return v * scale + shift;
+  }
+  if (kind == TAIL_RADIUS3 || kind == TAIL_RADIUS3_CHI) {
+    const double r = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
+    const double lr = log(r);
+    logj -= 2.0 * lr;
+    // scipy.stats.chi(3).logpdf(r) = log sqrt(2 / pi) + 2 log r - r^2 / 2
+    if (kind == TAIL_RADIUS3_CHI) logp_extra += -0.22579135264472744 + 2.0 * lr - 0.5 * r * r;
+    return r * scale + shift;
   }
   const double r = sqrt(u0 * u0 + u1 * u1);
   const double lr = log(r);
@@ -99,9 +131,9 @@ NB200_HD double tail_pair(int32_t kind, double scale, double shift, double u0, d
 }
 
 // One row.  logq_flow: log q of the flow alone (NaN: the row was already dropped by the draw
-// kernel).  log_affine_sum = sum over the non-pair slots of (log|scale_d| + log|a_d|).  pre_a /
-// pre_b may be NULL (a = 1, b = 0); src (int32[2 D]: the one or two flow features output slot d
-// reads) may be NULL (slot d reads feature d).  Writes x[D]; returns true when the row survives
+// kernel).  log_affine_sum = tail_log_affine_sum.  pre_a / pre_b may be NULL (a = 1, b = 0); src
+// (int32[3 D]: the one, two or three flow features output slot d reads) may be NULL (slot d
+// reads feature d).  Writes x[D]; returns true when the row survives
 // and then logq_out / logw_out are its log q / log weight.
 NB200_HD bool tail_row(int D, const float* xp, const int32_t* kind, const int32_t* src,
                        const double* pre_a, const double* pre_b, const double* scale,
@@ -111,11 +143,11 @@ NB200_HD bool tail_row(int D, const float* xp, const int32_t* kind, const int32_
   double logj = log_affine_sum, logp_extra = 0.0;
   bool inb = true;
   for (int d = 0; d < D; ++d) {
-    const int i0 = src ? src[2 * d] : d;
+    const int i0 = src ? src[3 * d] : d;
     double xv;
-    if (kind[d] >= TAIL_PAIR_FIRST) {
-      xv = tail_pair(kind[d], scale[d], shift[d], (double)xp[i0], (double)xp[src ? src[2 * d + 1] : d],
-                     logj, logp_extra);
+    if (tail_is_multi(kind[d])) {
+      xv = tail_pair(kind[d], pre_a ? pre_a[d] : 1.0, scale[d], shift[d], (double)xp[i0],
+                     (double)xp[src ? src[3 * d + 1] : d], (double)xp[src ? src[3 * d + 2] : d], logj, logp_extra);
     } else {
       xv = tail_feature(kind[d], pre_a ? pre_a[d] : 1.0, pre_b ? pre_b[d] : 0.0, scale[d], shift[d],
                         (double)xp[i0], logj);
@@ -133,11 +165,14 @@ NB200_HD bool tail_row(int D, const float* xp, const int32_t* kind, const int32_
   return ok;
 }
 
-// The row constant of log|J|: the affine parts of the non-pair slots.
+// The row constant of log|J|: the affine parts of the single-feature slots, and ToCartesian's map
+// back to its prior bounds.
 NB200_HD double tail_log_affine_sum(int D, const int32_t* kind, const double* pre_a, const double* scale) {
   double s = 0.0;
-  for (int d = 0; d < D; ++d)
-    if (kind[d] < TAIL_PAIR_FIRST) s += log(fabs(scale[d])) + (pre_a ? log(fabs(pre_a[d])) : 0.0);
+  for (int d = 0; d < D; ++d) {
+    if (!tail_is_multi(kind[d])) s += log(fabs(scale[d])) + (pre_a ? log(fabs(pre_a[d])) : 0.0);
+    else if (kind[d] == TAIL_ANGLE_ABS) s += log(fabs(scale[d]));
+  }
   return s;
 }
 
@@ -169,7 +204,7 @@ reparam_tail_kernel(int64_t n, int D, const float* __restrict__ xp, const int32_
                     double* __restrict__ logw, double* __restrict__ x64, double* __restrict__ stats) {
   __shared__ double c_s[6 * TAIL_MAXD];  // scale | shift | lo | hi | a | b
   __shared__ int32_t k_s[TAIL_MAXD];
-  __shared__ int32_t src_s[2 * TAIL_MAXD];
+  __shared__ int32_t src_s[3 * TAIL_MAXD];
   __shared__ double lss_s;
   for (int d = threadIdx.x; d < D; d += TAIL_THREADS) {
     c_s[d] = scale[d];
@@ -179,8 +214,7 @@ reparam_tail_kernel(int64_t n, int D, const float* __restrict__ xp, const int32_
     c_s[4 * TAIL_MAXD + d] = pre_a ? pre_a[d] : 1.0;
     c_s[5 * TAIL_MAXD + d] = pre_b ? pre_b[d] : 0.0;
     k_s[d] = kind[d];
-    src_s[2 * d] = src ? src[2 * d] : d;
-    src_s[2 * d + 1] = src ? src[2 * d + 1] : d;
+    for (int j = 0; j < 3; ++j) src_s[3 * d + j] = src ? src[3 * d + j] : d;
   }
   if (threadIdx.x == 0) lss_s = tail_log_affine_sum(D, kind, pre_a, scale);
   __syncthreads();

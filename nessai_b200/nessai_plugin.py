@@ -27,7 +27,15 @@ from nessai import config as nessai_config
 from nessai.livepoint import empty_structured_array as nessai_empty_structured_array
 from nessai.proposal.augmented import AugmentedFlowProposal
 from nessai.proposal.flowproposal import FlowProposal
-from nessai.reparameterisations import Angle, NullReparameterisation, RescaleToBounds, ScaleAndShift
+from nessai.reparameterisations import (
+    Angle,
+    AnglePair,
+    Dequantise,
+    NullReparameterisation,
+    RescaleToBounds,
+    ScaleAndShift,
+    ToCartesian,
+)
 from nessai.utils import rescaling as _ref_rescaling
 
 from .flowmodel import B200FlowModel
@@ -38,7 +46,8 @@ logger = logging.getLogger(__name__)
 
 # per-parameter map kinds of the device tail (csrc/reparam_tail.cuh: TailKind)
 (KIND_IDENTITY, KIND_SIGMOID, KIND_ABS, KIND_EXP, KIND_LOG, KIND_NORMAL_CDF,
- KIND_NORMAL_QUANTILE, KIND_ANGLE, KIND_ANGLE_MOD, KIND_RADIUS, KIND_RADIUS_CHI) = range(11)
+ KIND_NORMAL_QUANTILE, KIND_ANGLE, KIND_ANGLE_MOD, KIND_RADIUS, KIND_RADIUS_CHI, KIND_FLOOR,
+ KIND_ANGLE_ABS, KIND_ZENITH, KIND_DECLINATION, KIND_RADIUS3, KIND_RADIUS3_CHI) = range(17)
 
 # the INVERSE function of a named rescaling (utils/rescaling.py:410-417) -> the kind of h
 _INVERSE_KINDS = (
@@ -59,14 +68,15 @@ def _kind_of(fn):
 
 class ParameterMaps(NamedTuple):
     """``x = h(pre_scale * x'[src] + pre_shift) * scale + shift`` per x-space parameter ``names[d]``
-    (``src[d]``: the one or, for the pair kinds of ``Angle``, two prime parameters it reads)."""
+    (``src[d]``: the one, two -- ``Angle``, ``ToCartesian`` -- or three -- ``AnglePair`` -- prime
+    parameters it reads)."""
 
     kind: np.ndarray
     scale: np.ndarray
     shift: np.ndarray
     pre_scale: np.ndarray
     pre_shift: np.ndarray
-    src: np.ndarray  # (D, 2) indices into the prime parameters
+    src: np.ndarray  # (D, 3) indices into the prime parameters
     names: list  # x-space parameters: the model's, then auxiliary ones (flowproposal/base.py:539-546)
 
     @property
@@ -106,9 +116,15 @@ def parameter_maps(rep, prime_parameters, model_names, x_parameters=None):
       ``r = sqrt(x'^2 + y'^2)`` with ``log|J| -= log r``; ``r`` is the model's radial parameter or an
       auxiliary one with a ``chi(2)`` prior.
 
+    * the stock ``ToCartesian`` (angle.py:189-232): a non-periodic parameter as the angle of a
+      Cartesian pair, inverse ``|atan2(y', x') / scale| * (hi - lo) + lo``, ``log|J| += log(hi - lo)``;
+    * the stock ``AnglePair`` (angle.py:235-538): two angles (+ a radial parameter, or an auxiliary
+      one with a ``chi(3)`` prior) as a Cartesian triple, conventions "az-zen" and "ra-dec";
+    * the stock ``Dequantise`` (discrete.py): ``RescaleToBounds`` over ``[lo, hi + 1]`` whose
+      pre-rescaling inverse is ``floor``.
+
     Anything else (user rescaling callables, two non-linear stages on one parameter, an edge
-    not detected yet, ``AnglePair`` / ``ToCartesian`` / ``Dequantise``, user classes) keeps the
-    reference's host loop."""
+    not detected yet, user classes) keeps the reference's host loop."""
     if rep is None:
         return None
     prime_parameters = list(prime_parameters)
@@ -119,19 +135,38 @@ def parameter_maps(rep, prime_parameters, model_names, x_parameters=None):
     for r in rep.values():
         if isinstance(r, NullReparameterisation):
             for p, pp in zip(r.parameters, r.output_parameters):
-                specs[p] = (KIND_IDENTITY, 1.0, 0.0, 1.0, 0.0, (pp, pp))
+                specs[p] = (KIND_IDENTITY, 1.0, 0.0, 1.0, 0.0, (pp, pp, pp))
             continue
-        if type(r) is Angle:
+        if type(r) in (Angle, ToCartesian):
             if len(r.output_parameters) != 2 or not np.isfinite(r.scale) or r.scale == 0:
                 return None
-            pair = (r.x, r.y)
-            specs[r.angle] = (KIND_ANGLE_MOD if r._zero_bound else KIND_ANGLE, 1.0 / float(r.scale), 0.0, 1.0, 0.0, pair)
+            pair = (r.x, r.y, r.x)
+            if type(r) is ToCartesian:
+                lo, hi = (float(b) for b in r.prior_bounds[r.angle])
+                if not (np.isfinite(lo) and np.isfinite(hi) and hi > lo):
+                    return None
+                specs[r.angle] = (KIND_ANGLE_ABS, hi - lo, lo, 1.0 / float(r.scale), 0.0, pair)
+            else:
+                specs[r.angle] = (KIND_ANGLE_MOD if r._zero_bound else KIND_ANGLE, 1.0 / float(r.scale), 0.0, 1.0, 0.0,
+                                  pair)
             specs[r.radial] = (KIND_RADIUS_CHI if r.chi else KIND_RADIUS, 1.0, 0.0, 1.0, 0.0, pair)
             continue
-        if not (isinstance(r, ScaleAndShift) or type(r) is RescaleToBounds) or not r.one_to_one:
-            # (RescaleToBounds subclasses may override the rescaling hooks: stock class only)
+        if type(r) is AnglePair:
+            if len(r.output_parameters) != 3 or r.convention not in ("az-zen", "ra-dec"):
+                return None
+            triple = (r.x, r.y, r.z)
+            specs[r.angles[0]] = (KIND_ANGLE_MOD if r._modulo_2pi else KIND_ANGLE, 1.0, 0.0, 1.0, 0.0, triple)
+            specs[r.angles[1]] = (KIND_ZENITH if r.convention == "az-zen" else KIND_DECLINATION, 1.0, 0.0, 1.0, 0.0,
+                                  triple)
+            specs[r.radial] = (KIND_RADIUS3_CHI if r.chi else KIND_RADIUS3, 1.0, 0.0, 1.0, 0.0, triple)
+            continue
+        if not (isinstance(r, ScaleAndShift) or type(r) in (RescaleToBounds, Dequantise)) or not r.one_to_one:
+            # (RescaleToBounds subclasses may override the rescaling hooks: stock classes only)
             return None
-        pre = _kind_of(r.pre_rescaling_inv) if r.has_pre_rescaling else KIND_IDENTITY
+        if type(r) is Dequantise:
+            pre = KIND_FLOOR  # discrete.py:77-78
+        else:
+            pre = _kind_of(r.pre_rescaling_inv) if r.has_pre_rescaling else KIND_IDENTITY
         post = _kind_of(r.post_rescaling_inv) if r.has_post_rescaling else KIND_IDENTITY
         if pre is None or post is None or (pre != KIND_IDENTITY and post != KIND_IDENTITY):
             return None
@@ -158,9 +193,9 @@ def parameter_maps(rep, prime_parameters, model_names, x_parameters=None):
                     s = (hi - lo) / float(r._rescale_factor[p])
                     t = lo + off - s * float(r._rescale_shift[p])
             if pre != KIND_IDENTITY:
-                specs[p] = (pre, 1.0, 0.0, s, t, (pp, pp))  # the affine map first, then P^-1
+                specs[p] = (pre, 1.0, 0.0, s, t, (pp, pp, pp))  # the affine map first, then P^-1
             else:
-                specs[p] = (k, s, t, 1.0, 0.0, (pp, pp))
+                specs[p] = (k, s, t, 1.0, 0.0, (pp, pp, pp))
     if set(specs) != set(x_parameters) or len(x_parameters) != len(prime_parameters):
         return None
     if list(x_parameters[: len(model_names)]) != list(model_names):

@@ -934,7 +934,7 @@ class GeneralPopulateEngine(PopulateEngine):
     The loop, its pipelining and the multi-GPU exchange are the base class's."""
 
     MAX_D = 64  # TAIL_MAXD
-    N_KINDS = 11  # TAIL_N_KINDS
+    N_KINDS = 17  # TAIL_N_KINDS
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
@@ -948,11 +948,17 @@ class GeneralPopulateEngine(PopulateEngine):
         """As ``PopulateEngine.configure`` with the per-parameter ``kind`` of ``h`` in front
         (0 identity, 1 sigmoid, 2 abs, 3 exp, 4 log, 5 normal CDF, 6 normal quantile) and the
         optional affine map applied BEFORE ``h``: ``x = h(pre_scale x' + pre_shift) scale + shift``.
-        ``src`` (``(D, 2)`` ints): the flow feature(s) output slot ``d`` reads (default ``d``); the
-        pair kinds of ``Angle`` read two (7 angle, 8 angle mod 2 pi, 9 radius, 10 auxiliary radius
-        with its chi(2) prior)."""
+        ``src`` (``(D, 3)`` ints; ``(D, 2)`` is padded): the flow feature(s) output slot ``d`` reads
+        (default ``d``); the pair kinds of ``Angle`` read two (7 angle, 8 angle mod 2 pi, 9 radius,
+        10 auxiliary radius with its chi(2) prior; 12 ``ToCartesian``), the kinds of ``AnglePair``
+        three (13 zenith, 14 declination, 15 radius, 16 auxiliary radius with its chi(3) prior);
+        11 is ``floor`` (``Dequantise``).  See include/nessai_b200.h: nb200_reparam_tail."""
         D = self.D
-        src = np.stack([np.arange(D)] * 2, axis=1) if src is None else np.asarray(src).reshape(-1, 2)
+        src = np.stack([np.arange(D)] * 3, axis=1) if src is None else np.asarray(src)
+        if src.ndim != 2:
+            src = src.reshape(D, -1)
+        if src.shape[1] == 2:
+            src = np.concatenate([src, src[:, :1]], axis=1)
         pre_scale = np.ones(D) if pre_scale is None else pre_scale
         pre_shift = np.zeros(D) if pre_shift is None else pre_shift
         if getattr(self, "_identity", None) is None:
@@ -967,8 +973,8 @@ class GeneralPopulateEngine(PopulateEngine):
         if np.any((new[0] < 0) | (new[0] >= self.N_KINDS)):
             raise ValueError("unknown per-parameter map kind")
         new.append(np.ascontiguousarray(src, dtype=np.int32))
-        if new[-1].shape != (D, 2) or np.any((new[-1] < 0) | (new[-1] >= D)):
-            raise ValueError("src must hold two flow-feature indices per parameter")
+        if new[-1].shape != (D, 3) or np.any((new[-1] < 0) | (new[-1] >= D)):
+            raise ValueError("src must hold two or three flow-feature indices per parameter")
         old = getattr(self, "_tail_host", None)
         if old is None or not all(np.array_equal(a, b) for a, b in zip(new, old)):
             self.t_kind = torch.from_numpy(new[0]).to(self.device)

@@ -19,6 +19,13 @@ function, as ``x = h(a x' + b) * scale + shift`` per parameter:
   ``(r cos(scale * angle), r sin(scale * angle))``; inverse ``r = sqrt(x'^2 + y'^2)``,
   ``angle = atan2(y', x') [% 2 pi] / scale``, ``log|J| -= log r``; ``r`` is either a model parameter or
   an auxiliary one with a ``chi(2)`` prior;
+* ``ToCartesian`` (angle.py:189-232): the same Cartesian pair for a NON-periodic parameter mapped to
+  ``[0, scale]`` (and mirrored); inverse ``|atan2(y', x') / scale| * (hi - lo) + lo``,
+  ``log|J| += log(hi - lo) - log r``;
+* ``AnglePair`` (angle.py:235-538): the flow sees the Cartesian triple of two angles and a radius
+  (a model parameter or an auxiliary one with a ``chi(3)`` prior), convention "az-zen" or "ra-dec";
+* ``Dequantise`` (reparameterisations/discrete.py): ``RescaleToBounds`` whose pre-rescaling inverse
+  is ``floor`` with no log-Jacobian;
 * ``h = identity``: the diagonal affine of ``oracle/populate_numpy.py``;
 
 followed by ``log_q -= log|J|`` (flowproposal.py:378-383), the prior-bounds check
@@ -35,17 +42,32 @@ import numpy as np
 IDENTITY, SIGMOID, ABS, EXP, LOG, NORMAL_CDF, NORMAL_QUANTILE = range(7)
 # pair kinds: functions of two flow features, reparameterisations/angle.py:149-181
 ANGLE, ANGLE_MOD, RADIUS, RADIUS_CHI = 7, 8, 9, 10
+FLOOR = 11  # single feature (Dequantise)
+ANGLE_ABS = 12  # pair (ToCartesian)
+ZENITH, DECLINATION, RADIUS3, RADIUS3_CHI = 13, 14, 15, 16  # triples (AnglePair)
+
+
+def is_multi(kind):
+    """Kinds that read two or three flow features."""
+    kind = np.asarray(kind)
+    return (kind >= ANGLE) & (kind != FLOOR)
+
 
 
 def inverse_maps(xp, kind, scale, shift, pre_scale=None, pre_shift=None, src=None, return_log_prior=False):
     """``x' (n, D) -> (x (n, D), log|J| (n,))`` for ``x = h(a x' + b) * scale + shift`` with the
     per-parameter ``kind`` of ``h``, ``a = pre_scale`` (default 1) and ``b = pre_shift`` (0).
-    ``src`` (``(D, 2)`` ints, default ``[d, d]``): the flow feature(s) output slot ``d`` reads; the
-    pair kinds read two -- ``ANGLE``: ``atan2(u1, u0) * scale + shift`` (``ANGLE_MOD``: modulo
+    ``src`` (``(D, 3)`` ints -- ``(D, 2)`` is padded --, default ``[d, d, d]``): the flow feature(s)
+    output slot ``d`` reads; the pair kinds read two -- ``ANGLE``: ``atan2(u1, u0) * scale + shift`` (``ANGLE_MOD``: modulo
     ``2 pi`` first), no log-Jacobian for the constant factor (angle.py:120-128,157-170);
     ``RADIUS``: ``sqrt(u0^2 + u1^2)``, ``log|J| -= log r`` (angle.py:172); ``RADIUS_CHI``: the same for
     an auxiliary radius, whose ``chi(2)`` prior ``log r - r^2 / 2`` (angle.py:183-185) is returned
-    as a third array with ``return_log_prior``."""
+    as a third array with ``return_log_prior``.  ``ANGLE_ABS`` (ToCartesian, angle.py:221-231):
+    ``|atan2(u1, u0) * a| * scale + shift``, ``log|J| += log|scale|``.  Triples (AnglePair,
+    angle.py:418-489): ``ZENITH`` ``atan2(sqrt(u0^2 + u1^2), u2)`` with ``log|J| -= log sin``;
+    ``DECLINATION`` ``atan2(u2, sqrt(u0^2 + u1^2))`` with ``log|J| -= log cos``; ``RADIUS3(_CHI)``
+    ``sqrt(u0^2 + u1^2 + u2^2)`` with ``log|J| -= 2 log r`` (and the ``chi(3)`` prior, :529-537).
+    ``FLOOR`` (Dequantise): ``floor(u)``, no log-Jacobian."""
     from scipy.special import erfc, erfcinv
 
     xp = np.asarray(xp, dtype=np.float64)
@@ -53,17 +75,33 @@ def inverse_maps(xp, kind, scale, shift, pre_scale=None, pre_shift=None, src=Non
     D = xp.shape[1]
     a = np.ones(D) if pre_scale is None else np.asarray(pre_scale, dtype=np.float64)
     b = np.zeros(D) if pre_shift is None else np.asarray(pre_shift, dtype=np.float64)
-    src = np.stack([np.arange(D)] * 2, axis=1) if src is None else np.asarray(src).reshape(D, 2)
+    src = np.stack([np.arange(D)] * 3, axis=1) if src is None else np.asarray(src).reshape(D, -1)
+    if src.shape[1] == 2:
+        src = np.concatenate([src, src[:, :1]], axis=1)
     x = np.empty_like(xp)
-    single = kind < ANGLE
+    single = ~is_multi(kind)
     log_j = np.full(xp.shape[0], float(np.sum(np.log(np.abs(np.asarray(scale)[single])))
-                                       + np.sum(np.log(np.abs(a[single])))))
+                                       + np.sum(np.log(np.abs(a[single])))
+                                       + np.sum(np.log(np.abs(np.asarray(scale)[kind == ANGLE_ABS])))))
     log_p = np.zeros(xp.shape[0])
     with np.errstate(all="ignore"):
         for d in range(D):
-            if kind[d] >= ANGLE:
-                u0, u1 = xp[:, src[d, 0]], xp[:, src[d, 1]]
-                if kind[d] in (ANGLE, ANGLE_MOD):
+            if is_multi(kind[d]):
+                u0, u1, u2 = xp[:, src[d, 0]], xp[:, src[d, 1]], xp[:, src[d, 2]]
+                if kind[d] == ANGLE_ABS:
+                    h = np.abs(np.arctan2(u1, u0) * a[d])
+                elif kind[d] == ZENITH:
+                    h = np.arctan2(np.sqrt(u0**2 + u1**2), u2)
+                    log_j = log_j - np.log(np.sin(h))
+                elif kind[d] == DECLINATION:
+                    h = np.arctan2(u2, np.sqrt(u0**2 + u1**2))
+                    log_j = log_j - np.log(np.cos(h))
+                elif kind[d] in (RADIUS3, RADIUS3_CHI):
+                    h = np.sqrt(u0**2 + u1**2 + u2**2)
+                    log_j = log_j - 2.0 * np.log(h)
+                    if kind[d] == RADIUS3_CHI:
+                        log_p = log_p + 0.5 * np.log(2.0 / np.pi) + 2.0 * np.log(h) - 0.5 * h**2
+                elif kind[d] in (ANGLE, ANGLE_MOD):
                     h = np.arctan2(u1, u0)
                     if kind[d] == ANGLE_MOD:
                         h = h % (2.0 * np.pi)
@@ -94,6 +132,8 @@ def inverse_maps(xp, kind, scale, shift, pre_scale=None, pre_shift=None, src=Non
             elif kind[d] == NORMAL_QUANTILE:  # utils/rescaling.py:403-407
                 h = -np.sqrt(2.0) * erfcinv(2.0 * u)
                 log_j = log_j + 0.5 * np.log(2 * np.pi) + 0.5 * h**2
+            elif kind[d] == FLOOR:  # reparameterisations/discrete.py:77-78
+                h = np.floor(u)
             elif kind[d] == IDENTITY:
                 h = u
             else:

@@ -93,7 +93,7 @@ class SimLib:
                                    scale=_view(sc, D, "f8"), shift=_view(sh, D, "f8"), lo=_view(lo, D, "f8"),
                                    hi=_view(hi, D, "f8"), log_prior_const=0.0 if np.isnan(lpc) else float(lpc),
                                    min_log_q=mlq, pre_scale=_view(pa, D, "f8"), pre_shift=_view(pb, D, "f8"),
-                                   src=_view(src, 2 * D, "i4"))
+                                   src=_view(src, 3 * D, "i4"))
         _view(x64, n * D, "f8")[:] = x.ravel()
         lq[:] = q
         _view(logw, n, "f8")[:] = w

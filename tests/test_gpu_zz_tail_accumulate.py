@@ -430,12 +430,12 @@ def test_reference_self_consistency_pins(name, tmp_path):
 
 
 @pytest.mark.reference
-@pytest.mark.parametrize("variant", ["logit_and_default", "accumulate", "periodic_angle"])
+@pytest.mark.parametrize("variant", ["logit_and_default", "accumulate", "periodic_angle", "to_cartesian"])
 def test_flowsampler_variants_run_on_the_device_loop(tmp_path, variant):
     """The reference's FlowSampler, unmodified, with a logit + rescale-to-bounds
     reparameterisation (GeneralPopulateEngine), with accumulate_weights=True (run_accumulate)
-    and with an Angle reparameterisation (Cartesian pair + auxiliary radius with its chi prior,
-    GeneralPopulateEngine over three flow features): the device loop is the one that runs."""
+    and with an Angle / ToCartesian reparameterisation (Cartesian pair + auxiliary radius with its
+    chi prior, GeneralPopulateEngine over three flow features): the device loop is the one that runs."""
     reference_or_skip()
     from nessai.flowsampler import FlowSampler
     from test_gpu_nessai_plugin import make_model
@@ -445,7 +445,8 @@ def test_flowsampler_variants_run_on_the_device_loop(tmp_path, variant):
 
     kw = dict(logit_and_default=dict(reparameterisations={"x": "logit", "y": "default"}),
               accumulate=dict(accumulate_weights=True),
-              periodic_angle=dict(reparameterisations={"x": "periodic", "y": "default"}))[variant]
+              periodic_angle=dict(reparameterisations={"x": "periodic", "y": "default"}),
+              to_cartesian=dict(reparameterisations={"x": "to-cartesian", "y": "default"}))[variant]
     fs = FlowSampler(
         make_model(), output=str(tmp_path), resume=False, seed=1234, nlive=200, plot=False,
         flow_proposal_class=B200NessaiFlowProposal, flow_config=dict(n_blocks=2),
@@ -457,7 +458,7 @@ def test_flowsampler_variants_run_on_the_device_loop(tmp_path, variant):
     assert prop.training_count >= 1 and prop.populated_count >= 1
     if variant == "logit_and_default":
         assert type(prop._engine) is GeneralPopulateEngine
-    elif variant == "periodic_angle":
+    elif variant in ("periodic_angle", "to_cartesian"):
         assert type(prop._engine) is GeneralPopulateEngine and prop._engine.names == ["x", "y", "x_radial"]
         assert prop.flow.model.spec.D == 3 and prop.samples.dtype.names[:2] == ("x", "y")
         assert "x_radial" in prop.x.dtype.names and "x_radial" not in prop.samples.dtype.names

@@ -98,7 +98,7 @@ def test_parameter_maps_and_oracle_match_reference_inverse_rescale(tmp_path, cas
     assert maps is not None
     kind, scale, shift, pre_scale, pre_shift = maps[:5]
     assert set(kind.tolist()) == kinds and maps.has_pre_affine == (case in BOX)
-    assert maps.names == list(model.names) and np.array_equal(maps.src, np.stack([np.arange(D)] * 2, axis=1))
+    assert maps.names == list(model.names) and np.array_equal(maps.src, np.stack([np.arange(D)] * 3, axis=1))
     assert diagonal_rescaling(prop._reparameterisation, prop.prime_parameters, model.names) is None
     rng = np.random.default_rng(0)
     n = 200
@@ -171,19 +171,31 @@ def test_host_erfcinv_helper(host_tail):
     assert np.isnan(host_tail.nb200_host_erfcinv(-0.5)) and np.isnan(host_tail.nb200_host_erfcinv(2.5))
 
 
+PI = np.pi
 TAIL_CASE = dict(
-    #              0  1  2  3  4  5  6  7  8  9 10 11 | angle, aux radius, radius, angle mod 2 pi
-    kind=np.array([0, 1, 2, 3, 1, 2, 0, 4, 5, 6, 1, 3, 7, 10, 9, 8], dtype=np.int32),
-    scale=np.array([1.5, 8.0, -3.0, 2.0, 0.5, 4.0, -0.7, 1.2, 6.0, 0.9, 1.0, 1.0, 0.5, 1.0, 1.0, 1.0]),
-    shift=np.array([0.2, -4.0, 5.0, -1.0, 0.0, -2.0, 0.3, 0.1, -3.0, 0.4, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]),
-    lo=np.array([-3.0, -4.0, 2.0, -1.0, 0.0, -2.0, -2.0, -3.0, -3.0, -2.0, 0.0, 0.0, -1.5, -np.inf, 0.0, 0.0]),
-    hi=np.array([3.0, 4.0, 5.0, 9.0, 0.5, 1.5, 2.0, 2.0, 3.0, 2.5, 1.0, 9.0, 1.5, np.inf, 3.5, 2 * np.pi]),
-    pre_scale=np.array([1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.3, 1.0, 0.2, 1.7, 0.6, 1.0, 1.0, 1.0, 1.0]),
-    pre_shift=np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.5, 0.0, 0.5, -0.3, 0.2, 0.0, 0.0, 0.0, 0.0]),
+    # slots 0 .. 11: the single-feature kinds; 12 .. 15: Angle (angle, aux radius, radius, angle mod 2 pi);
+    # 16: floor (Dequantise); 17, 18: ToCartesian + its auxiliary radius; 19 .. 21: AnglePair az-zen with an
+    # auxiliary radius; 22 .. 24: AnglePair ra-dec with a radial parameter
+    kind=np.array([0, 1, 2, 3, 1, 2, 0, 4, 5, 6, 1, 3, 7, 10, 9, 8, 11, 12, 10, 8, 13, 16, 7, 14, 15], dtype=np.int32),
+    scale=np.array([1.5, 8.0, -3.0, 2.0, 0.5, 4.0, -0.7, 1.2, 6.0, 0.9, 1.0, 1.0, 0.5, 1.0, 1.0, 1.0,
+                    1.0, 2.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0]),
+    shift=np.array([0.2, -4.0, 5.0, -1.0, 0.0, -2.0, 0.3, 0.1, -3.0, 0.4, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0,
+                    0.0, -1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]),
+    lo=np.array([-3.0, -4.0, 2.0, -1.0, 0.0, -2.0, -2.0, -3.0, -3.0, -2.0, 0.0, 0.0, -1.5, -np.inf, 0.0, 0.0,
+                 -6.0, -1.0, -np.inf, 0.0, 0.0, -np.inf, -PI, -PI / 2, 0.0]),
+    hi=np.array([3.0, 4.0, 5.0, 9.0, 0.5, 1.5, 2.0, 2.0, 3.0, 2.5, 1.0, 9.0, 1.5, np.inf, 3.5, 2 * PI,
+                 9.0, 1.0, np.inf, 2 * PI, PI, np.inf, PI, PI / 2, 4.0]),
+    pre_scale=np.array([1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.3, 1.0, 0.2, 1.7, 0.6, 1.0, 1.0, 1.0, 1.0,
+                        3.0, 1.0 / PI, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0]),
+    pre_shift=np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.5, 0.0, 0.5, -0.3, 0.2, 0.0, 0.0, 0.0, 0.0,
+                        2.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]),
     # slots 12 / 13 read the flow features (13, 12) as (x', y'), slots 14 / 15 the features (14, 15);
-    # slots 2 and 5 are swapped to exercise the permutation of single-feature kinds
-    src=np.array([[0, 0], [1, 1], [5, 5], [3, 3], [4, 4], [2, 2], [6, 6], [7, 7], [8, 8], [9, 9], [10, 10], [11, 11],
-                  [13, 12], [13, 12], [14, 15], [14, 15]], dtype=np.int32),
+    # slots 2 and 5 are swapped to exercise the permutation of single-feature kinds; the triples read
+    # (19, 20, 21) and, permuted, (24, 22, 23)
+    src=np.array([[0, 0, 0], [1, 1, 1], [5, 5, 5], [3, 3, 3], [4, 4, 4], [2, 2, 2], [6, 6, 6], [7, 7, 7], [8, 8, 8],
+                  [9, 9, 9], [10, 10, 10], [11, 11, 11], [13, 12, 13], [13, 12, 13], [14, 15, 14], [14, 15, 14],
+                  [16, 16, 16], [17, 18, 17], [17, 18, 17], [19, 20, 21], [19, 20, 21], [19, 20, 21],
+                  [24, 22, 23], [24, 22, 23], [24, 22, 23]], dtype=np.int32),
 )
 
 
@@ -308,19 +320,42 @@ def test_angle_maps_and_oracle_match_reference(tmp_path, case):
     np.testing.assert_allclose(back[:, 1], live["x"], rtol=1e-9, atol=1e-9)
 
 
+PAIR_CASES = {
+    # name: (model names, bounds, reparameterisations, expected kinds in x-space order)
+    "to_cartesian": (["a", "x"], {"a": [0.5, 3.0], "x": [0.5, 4.0]}, {"a": "to-cartesian", "x": "default"},
+                     [12, 0, 10]),
+    "angle_pair_az_zen_aux_radius": (["az", "zen", "x"], {"az": [0.0, 2 * np.pi], "zen": [0.0, np.pi], "x": [0.5, 4.0]},
+                                     {"angle-pair": {"parameters": ["az", "zen"]}, "x": "default"}, [8, 13, 0, 16]),
+    "angle_pair_ra_dec_radial": (["d", "dec", "ra"],
+                                 {"ra": [-np.pi, np.pi], "dec": [-np.pi / 2, np.pi / 2], "d": [0.5, 4.0]},
+                                 {"angle-pair": {"parameters": ["ra", "dec", "d"]}}, [15, 14, 7]),
+    "angle_pair_sky_zero_bound": (["ra", "dec"], {"ra": [0.0, 2 * np.pi], "dec": [-np.pi / 2, np.pi / 2]},
+                                  {"angle-pair": {"parameters": ["ra", "dec"]}}, [8, 14, 16]),
+    "dequantise": (["k", "x"], {"k": [0.0, 5.0], "x": [0.5, 4.0]}, {"k": "dequantise", "x": "default"}, [11, 0]),
+}
+
+
 @pytest.mark.reference
-def test_other_angle_classes_are_refused(tmp_path):
+@pytest.mark.parametrize("case", list(PAIR_CASES))
+def test_cartesian_pair_and_dequantise_maps_match_reference(tmp_path, case):
+    """``ToCartesian`` (angle.py:189-232), ``AnglePair`` (angle.py:235-538, both conventions, with a
+    radial parameter or the auxiliary chi(3) one) and ``Dequantise`` (discrete.py): ``parameter_maps``
+    + the oracle against the reference's ``inverse_rescale`` and the reparameterisation's own
+    ``log_prior``; the forward map of the reference, then our inverse, gives the parameters back."""
     reference_or_skip()
-    from nessai.livepoint import numpy_array_to_live_points
+    from nessai.livepoint import empty_structured_array, numpy_array_to_live_points
     from nessai.model import Model
     from nessai.proposal import FlowProposal
 
     from nessai_b200.nessai_plugin import parameter_maps
+    from oracle.reparam_numpy import inverse_maps
+
+    names, bounds, reparams, kinds = PAIR_CASES[case]
 
     class M(Model):
         def __init__(self):
-            self.names = ["a", "b"]
-            self.bounds = {"a": [0.0, 2 * np.pi], "b": [-np.pi / 2, np.pi / 2]}
+            self.names = list(names)
+            self.bounds = {k: list(v) for k, v in bounds.items()}
 
         def log_prior(self, x):
             return np.log(self.in_bounds(x), dtype="float")
@@ -328,16 +363,48 @@ def test_other_angle_classes_are_refused(tmp_path):
         def log_likelihood(self, x):
             return np.zeros(x.size)
 
-    for reparams in ({"a": "to-cartesian", "b": "default"}, {"angle-pair": {"parameters": ["a", "b"]}}):
-        model = M()
-        rng = np.random.default_rng(4)
-        model.set_rng(rng)
-        prop = FlowProposal(model, rng=rng, flow_config=dict(n_blocks=2, n_neurons=8), output=str(tmp_path),
-                            poolsize=100, plot=False, reparameterisations=reparams)
-        prop.initialise()
-        live = numpy_array_to_live_points(np.stack([rng.uniform(0, 6, 50), rng.uniform(-1, 1, 50)], axis=1), model.names)
-        prop.check_state(live)
-        assert parameter_maps(prop._reparameterisation, prop.prime_parameters, model.names, prop.parameters) is None
+        def new_point(self, N=1):
+            x = super().new_point(N)
+            if "k" in self.names:  # a discrete parameter (the proposal verifies its rescaling on these draws)
+                x["k"] = np.floor(x["k"])
+            return x
+
+    model = M()
+    rng = np.random.default_rng(4)
+    model.set_rng(rng)
+    prop = FlowProposal(model, rng=rng, flow_config=dict(n_blocks=2, n_neurons=8), output=str(tmp_path), poolsize=100,
+                        plot=False, reparameterisations=reparams)
+    prop.initialise()
+    cols = []
+    for nm in names:
+        lo, hi = bounds[nm]
+        v = rng.uniform(lo + 0.02 * (hi - lo), hi - 0.02 * (hi - lo), 300)
+        cols.append(np.floor(rng.uniform(lo, hi + 1.0, 300)) if nm == "k" else v)
+    live = numpy_array_to_live_points(np.stack(cols, axis=1), model.names)
+    prop.check_state(live)
+    maps = parameter_maps(prop._reparameterisation, prop.prime_parameters, model.names, prop.parameters)
+    assert maps is not None and maps.names == list(prop.parameters) and not maps.affine
+    assert maps.kind.tolist() == kinds
+    n, Dp = 500, len(prop.prime_parameters)
+    assert Dp == len(prop.parameters)
+    a = rng.normal(0.0, 1.0, size=(n, Dp))
+    xp = empty_structured_array(n, names=prop.prime_parameters)
+    for i, p in enumerate(prop.prime_parameters):
+        xp[p] = a[:, i]
+    x_ref, log_j_ref = prop.inverse_rescale(xp.copy())
+    x, log_j, log_p = inverse_maps(a, maps.kind, maps.scale, maps.shift, maps.pre_scale, maps.pre_shift, maps.src,
+                                   return_log_prior=True)
+    ref = np.stack([x_ref[nm] for nm in prop.parameters], axis=-1)
+    np.testing.assert_allclose(x, ref, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(log_j, log_j_ref, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(log_p, prop._reparameterisation.log_prior(x_ref), rtol=1e-12, atol=1e-12)
+    assert bool(log_p.any()) == any(r.has_prior for r in prop._reparameterisation.values())
+    # forward (training data) then inverse gives the parameters back
+    x_prime, _ = prop.rescale(live.copy())
+    back = inverse_maps(np.stack([x_prime[p] for p in prop.prime_parameters], axis=-1), maps.kind, maps.scale,
+                        maps.shift, maps.pre_scale, maps.pre_shift, maps.src)[0]
+    for i, nm in enumerate(names):
+        np.testing.assert_allclose(back[:, i], live[nm], rtol=1e-9, atol=1e-9)
 
 
 # ------------------------------------------------------------------ the CUDA kernels under a CPU SIMT shim
