@@ -1,0 +1,81 @@
+"""Randomised parity sweep: flow configurations drawn over the reference's ``flow_config`` space
+(/root/reference/src/nessai/flowmodel/config.py:12-24, flows/realnvp.py:76-214, flows/nsf.py:60-130,
+flows/maf.py:62-104) -- features, conditioner width (the default 2 * n_inputs, narrower, wider than
+the tensor-core kernels take), blocks, conditioner depth and type, linear transform, BatchNorm,
+activation, coupling type -- each evaluated by whichever kernel the library picks (tcgen05 wide /
+narrow instantiations, or the generic fp32 interpreter) against the float64 oracle on the same
+weights: inverse, forward, log-prob, round trip.  Seeds are fixed: the sweep is deterministic."""
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def draw_config(seed):
+    rng = np.random.default_rng(1000 + seed)
+    ftype = rng.choice(["realnvp", "realnvp", "realnvp", "nsf", "maf"])
+    D = int(rng.integers(2, 21)) if ftype != "nsf" else int(rng.integers(2, 34))
+    cfg = dict(n_inputs=D, n_blocks=int(rng.integers(1, 6)), n_layers=int(rng.integers(1, 4)), ftype=str(ftype))
+    width = rng.choice(["default", "narrow", "sixty-four", "wide"], p=[0.4, 0.25, 0.25, 0.1])
+    if width == "narrow":
+        cfg["n_neurons"] = int(rng.integers(4, 33))
+    elif width == "sixty-four":
+        cfg["n_neurons"] = 64
+    elif width == "wide":
+        cfg["n_neurons"] = int(rng.integers(65, 97))
+    if ftype == "realnvp":
+        cfg["net"] = str(rng.choice(["resnet", "resnet", "mlp"]))
+        cfg["linear_transform"] = [None, "lu", "lu", "permutation"][int(rng.integers(0, 4))]
+        cfg["batch_norm_between_layers"] = bool(rng.integers(0, 2))
+        cfg["use_volume_preserving"] = bool(rng.random() < 0.15)
+        cfg["activation"] = str(rng.choice(["relu", "relu", "relu", "tanh", "swish"]))
+    elif ftype == "nsf":
+        cfg["batch_norm_between_layers"] = bool(rng.random() < 0.3)
+        if rng.random() < 0.2:
+            cfg["num_bins"] = int(rng.integers(4, 13))
+    else:
+        cfg["batch_norm_between_layers"] = bool(rng.integers(0, 2))
+    return cfg
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_random_flow_config_matches_oracle(seed, tmp_path):
+    from nessai_b200.flowmodel import B200FlowModel
+    from test_oracle import numpy_flow
+
+    cfg = draw_config(seed)
+    D = cfg["n_inputs"]
+    torch.manual_seed(seed)
+    fm = B200FlowModel(flow_config=dict(cfg), training_config=dict(device_tag="cuda:0"), output=str(tmp_path))
+    fm.initialise()
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for k, v in fm.model.state_dict().items():
+        a = v.cpu().numpy()
+        if a.dtype.kind == "f" and not k.endswith(".mask"):
+            a = a + (0.04 * rng.standard_normal(a.shape)).astype(np.float32)
+            if "running_var" in k:
+                a = np.abs(a) + 0.5
+        sd[k] = a
+    fm.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    fm.model.eval()
+    ocfg = dict(cfg)
+    ocfg.setdefault("n_neurons", fm.model.spec.H)
+    nf = numpy_flow(ocfg, sd)
+    n = 777
+    z = rng.normal(size=(n, D))
+    x, logj = fm.inverse(z)
+    x64, logj64 = nf.inverse(z.astype(np.float32).astype(np.float64))
+    # the spline flow's fp32 evaluation is the loosest (tests/test_gpu_c3_nsf.py); MAF's inverse is D sequential passes
+    tol = dict(rtol=3e-4, atol=3e-4) if cfg["ftype"] in ("nsf", "maf") else dict(rtol=1e-4, atol=1e-4)
+    ok = np.isfinite(logj64) & (np.abs(x64).max(axis=1) < 50.0)  # (rows a random flow throws far out are ill-conditioned)
+    assert ok.mean() > 0.9, cfg
+    np.testing.assert_allclose(x[ok], x64[ok], err_msg=str(cfg), **tol)
+    np.testing.assert_allclose(logj[ok], logj64[ok], err_msg=str(cfg), **tol)
+    xs = x64[ok].astype(np.float32).astype(np.float64)
+    zz, logp = fm.forward_and_log_prob(xs)
+    np.testing.assert_allclose(logp, nf.log_prob(xs), err_msg=str(cfg), **tol)
+    np.testing.assert_allclose(zz, z[ok], rtol=1e-3, atol=1e-3, err_msg=str(cfg))
+    np.testing.assert_allclose(fm.log_prob(xs), logp, rtol=0, atol=0)
