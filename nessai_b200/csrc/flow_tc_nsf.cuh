@@ -14,9 +14,19 @@
 //   * the wide final layer (d_tr x 24 outputs) runs in chunks of 48 columns = 2 features, each
 //     followed by the rational-quadratic spline epilogue of those two features (raw SFU ops,
 //     branch-free bin selection).
-// Covered: D <= 32, width 64, ReLU, 1-2 residual blocks, 8 bins, permutation / no linear
+// Covered: D <= 32, width <= 64, ReLU, 1-2 residual blocks, 8 bins, permutation / no linear
 // transform, no BatchNorm between layers (nessai's NSF defaults).  Everything else runs the
 // generic kernel.
+//
+// AC mode (template parameter): the same tile machinery for RealNVP's AFFINE coupling with the
+// default ResidualNet conditioner at 17 .. 32 features (flows/realnvp.py:76-214; up to 16 features
+// flow_tc_res.cuh keeps the state in registers).  Differences: the dense D x D affine in front of
+// every coupling (LU x permutation x BatchNorm, folded) rides the first conditioner GEMM as 32
+// extra output columns (N = 96: hidden pre-activations | the state after the affine), which the
+// epilogue copies into the state columns; identity features live in slots 0 .. 15 and transformed
+// ones in 16 .. 31 of every layer (the affines are re-laid-out on the host); the final layer is ONE
+// chunk (shift | unconstrained scale) followed by the coupling on the transformed slots, eight per
+// twin warp; the affine after the last coupling runs on the CUDA cores of the output stage.
 #pragma once
 #include "flow_tc_res.cuh"
 
@@ -33,19 +43,27 @@ constexpr int NS_W0 = TC_H * 16 * (NS_DP / 8);        // 64 rows, K = 32: 4 KB
 constexpr int NS_WF = NS_CN * 16 * (TC_H / 8);        // 48 rows, K = 64: 6 KB
 constexpr int NS_BF = NS_CN * 16;                     // bias operand of a chunk: 768 B
 
+constexpr int AC_ROWS0 = TC_H + NS_DP;    // AC mode: rows of the first GEMM's B operand (hidden | affine)
+constexpr int AC_TR0 = 16;                // AC mode: first state slot of the transformed features
+constexpr int AC_ZERO_BYTES = AC_ROWS0 * 16;  // the bias operands' all-zero K-chunk must cover 96 rows
+constexpr int AC_AFF_BYTES = (NS_DP * NS_DP + NS_DP) * 4;  // fp32 affine after the last coupling, k-major + bias
+
 struct NsLayout {
-  int w0hi, w0lo, blk, wf, b0, bblk, bf, layer_bytes;
+  int w0hi, w0lo, blk, wf, b0, bblk, bf, aff, layer_bytes;
 };
-__host__ __device__ inline NsLayout ns_layout(int NB, int nch) {
+__host__ __device__ inline NsLayout ns_layout(int NB, int nch, bool ac = false) {
   NsLayout o;
+  const int rows0 = ac ? AC_ROWS0 : TC_H;
+  const int w0 = rows0 * 16 * (NS_DP / 8);
   o.w0hi = 0;
-  o.w0lo = NS_W0;
-  o.blk = 2 * NS_W0;
+  o.w0lo = w0;
+  o.blk = 2 * w0;
   o.wf = o.blk + NB * 4 * RS_W_BIG;      // per chunk: hi, lo
   o.b0 = o.wf + nch * 2 * NS_WF;
-  o.bblk = o.b0 + RS_BIAS;
+  o.bblk = o.b0 + rows0 * 16;
   o.bf = o.bblk + NB * 2 * RS_BIAS;
-  o.layer_bytes = o.bf + nch * NS_BF;
+  o.aff = o.bf + nch * NS_BF;
+  o.layer_bytes = o.aff + (ac ? AC_AFF_BYTES : 0);
   return o;
 }
 
@@ -56,6 +74,8 @@ struct NsLayerInfo {
 struct NsProgram {
   bool valid = false;
   int narrow = 0;  // conditioner width <= 32: two K-steps, 32-column hidden epilogues (flow_tc.cuh)
+  int ac = 0;      // RealNVP affine coupling (AC mode) instead of the spline coupling
+  int additive = 0;
   int L = 0, D = 0, NB = 0, nch = 0, inverse = 0;
   float tail_bound = 0.f, const_logdet = 0.f;
   NsLayerInfo layer[TC_MAXL];
@@ -76,6 +96,7 @@ struct NsParams {
   const uint8_t* image;
   int image_bytes;
   int D, NB, nch, inverse, first, last;
+  int additive;
   NsLayerInfo ly;
   int8_t out_slot[NS_DP];
   float tail_bound, const_logdet;
@@ -222,6 +243,149 @@ inline int ns_build(NsProgram& t, const FlowOp* ops, int n_ops, const float* blo
   t.inverse = inverse;
   t.tail_bound = B;
   t.narrow = H <= TC_H / 2;
+  t.valid = true;
+  return 0;
+}
+
+// AC mode: recognise  affine (resnet-coupling affine)*  as rs_build does, for 17 .. 32 features (up to
+// 16 the register-state kernel of flow_tc_res.cuh is faster), and build one image per layer.
+inline int ac_build(NsProgram& t, const FlowOp* ops, int n_ops, const float* blob, int D, int H, int activation) {
+  t.valid = false;
+  if (D > NS_DP || D <= TC_DP || H < 1 || H > TC_H || activation != ACT_RELU || n_ops < 6) return 0;
+  int NB = -1;
+  for (int nb = 1; nb <= 2; ++nb)
+    if ((n_ops - 1) % (2 * nb + 3) == 0 && ops[2].type == OP_LINEAR && ops[2 * nb + 2].type == OP_COUPLING_AFFINE)
+      NB = nb;
+  if (NB < 0) return 0;
+  const int per = 2 * NB + 3;
+  const int L = (n_ops - 1) / per;
+  if (L < 1 || L > TC_MAXL) return 0;
+  auto is_affine = [&](const FlowOp& o) {
+    return o.type == OP_LINEAR && o.src <= BUF_X1 && o.dst <= BUF_X1 && o.K == D && o.N == D && o.flags == 0 &&
+           o.src_off == 0;
+  };
+  if (!is_affine(ops[0])) return 0;
+  int inverse = -1, additive = -1;
+  int d_id[TC_MAXL], d_tr[TC_MAXL];
+  for (int l = 0; l < L; ++l) {
+    const FlowOp* o = ops + 1 + per * l;
+    const FlowOp& a = o[0];
+    if (a.type != OP_LINEAR || a.src > BUF_X1 || a.dst < BUF_A0 || a.N != H || a.flags != 0 || a.src_off != 0 ||
+        a.K < 1 || a.K > AC_TR0)
+      return 0;
+    for (int b = 0; b < NB; ++b) {
+      const FlowOp& x = o[1 + 2 * b];
+      const FlowOp& y = o[2 + 2 * b];
+      if (x.type != OP_LINEAR || x.src != a.dst || x.dst == a.dst || x.dst < BUF_A0 || x.K != H || x.N != H ||
+          x.flags != (FLAG_IN_ACT | FLAG_OUT_ACT))
+        return 0;
+      if (y.type != OP_LINEAR || y.src != x.dst || y.dst != a.dst || y.K != H || y.N != H || y.flags != FLAG_ACCUM)
+        return 0;
+    }
+    const FlowOp& c = o[1 + 2 * NB];
+    if (c.type != OP_COUPLING_AFFINE || c.src != a.dst || c.K != H || c.d_id != a.K || c.d_tr < 1 ||
+        c.d_tr > NS_DP - AC_TR0 || c.d_id + c.d_tr != D || c.N != 2 * c.d_tr)
+      return 0;
+    const int inv = (c.flags & FLAG_INVERSE) ? 1 : 0, add = (c.flags & FLAG_ADDITIVE) ? 1 : 0;
+    if ((c.flags & ~(FLAG_INVERSE | FLAG_ADDITIVE)) != 0) return 0;
+    if ((inverse >= 0 && inverse != inv) || (additive >= 0 && additive != add)) return 0;
+    inverse = inv;
+    additive = add;
+    if (!is_affine(o[2 + 2 * NB])) return 0;
+    d_id[l] = c.d_id;
+    d_tr[l] = c.d_tr;
+  }
+  // state slot of natural feature j inside coupling layer `layer` (the flow's input / output: natural)
+  auto slot = [&](int layer, int j) {
+    if (layer < 0 || layer >= L) return j;
+    return j < d_id[layer] ? j : AC_TR0 + (j - d_id[layer]);
+  };
+  auto put_bias = [&](uint8_t* base, int n, float bv) {
+    if (!tc_h16_representable(bv)) tc_put_overflow() = true;
+    const uint16_t hi = tc_h16_rn(bv);
+    const uint16_t lo = tc_h16_rn(bv - tc_h16_to_f(hi));
+    memcpy(base + (size_t)n * 16, &hi, 2);
+    memcpy(base + (size_t)n * 16 + 2, &lo, 2);
+  };
+  tc_put_overflow() = false;
+  const NsLayout ly = ns_layout(NB, 1, true);
+  const int ones_off = ly.layer_bytes;
+  const int bytes = ones_off + TC_ONES_BYTES + AC_ZERO_BYTES;
+  if (((bytes + 1023) & ~1023) + 4096 > 227 * 1024) return 0;
+  for (int l = 0; l < L; ++l) {
+    const FlowOp& f = ops[per * l];  // the affine in front of coupling l
+    const FlowOp* o = ops + 1 + per * l;
+    const FlowOp& a = o[0];
+    std::vector<uint8_t> img((size_t)bytes, 0);
+    for (int r = 0; r < 128; ++r) {
+      const uint16_t one[2] = {TC_ONE16, TC_ONE16};
+      memcpy(img.data() + ones_off + (size_t)r * 16, one, 4);
+    }
+    uint8_t* lb = img.data();
+    // first conditioner layer with the affine folded in (float64): consumes the state BEFORE the affine
+    for (int n = 0; n < H; ++n) {
+      for (int k = 0; k < D; ++k) {
+        double acc = 0.0;
+        for (int j = 0; j < a.K; ++j)
+          acc += (double)blob[a.w_off + j * a.Npad + n] * (double)blob[f.w_off + k * f.Npad + j];
+        tc_put(lb + ly.w0hi, lb + ly.w0lo, AC_ROWS0, n, slot(l - 1, k), (float)acc);
+      }
+      double bacc = blob[a.b_off + n];
+      for (int j = 0; j < a.K; ++j) bacc += (double)blob[a.w_off + j * a.Npad + n] * (double)blob[f.b_off + j];
+      put_bias(lb + ly.b0, n, (float)bacc);
+    }
+    // rows 64 .. 95: the affine itself, slots of layer l - 1 -> slots of layer l
+    for (int n = 0; n < D; ++n) {
+      for (int k = 0; k < D; ++k)
+        tc_put(lb + ly.w0hi, lb + ly.w0lo, AC_ROWS0, TC_H + slot(l, n), slot(l - 1, k), blob[f.w_off + k * f.Npad + n]);
+      put_bias(lb + ly.b0, TC_H + slot(l, n), blob[f.b_off + n]);
+    }
+    for (int b = 0; b < NB; ++b) {
+      uint8_t* wb = lb + ly.blk + (size_t)b * 4 * RS_W_BIG;
+      const FlowOp& x = o[1 + 2 * b];
+      const FlowOp& y = o[2 + 2 * b];
+      for (int n = 0; n < H; ++n)
+        for (int k = 0; k < H; ++k) {
+          tc_put(wb, wb + RS_W_BIG, TC_H, n, k, blob[x.w_off + k * x.Npad + n]);
+          tc_put(wb + 2 * RS_W_BIG, wb + 3 * RS_W_BIG, TC_H, n, k, blob[y.w_off + k * y.Npad + n]);
+        }
+      for (int n = 0; n < H; ++n) {
+        put_bias(lb + ly.bblk + (size_t)(2 * b) * RS_BIAS, n, blob[x.b_off + n]);
+        put_bias(lb + ly.bblk + (size_t)(2 * b + 1) * RS_BIAS, n, blob[y.b_off + n]);
+      }
+    }
+    // final layer: the program's columns are (shift_i, scale_i) pairs -> rows i and 16 + i of ONE chunk
+    const FlowOp& c = o[1 + 2 * NB];
+    for (int i = 0; i < c.d_tr; ++i)
+      for (int part = 0; part < (additive ? 1 : 2); ++part) {
+        const int col = 2 * i + part, row = 16 * part + i;  // (additive coupling: the scale column is unused)
+        for (int k = 0; k < H; ++k) tc_put(lb + ly.wf, lb + ly.wf + NS_WF, NS_CN, row, k, blob[c.w_off + k * c.Npad + col]);
+        put_bias(lb + ly.bf, row, blob[c.b_off + col]);
+      }
+    if (l == L - 1) {
+      // the affine after the last coupling: fp32, k-major over the slots of the last layer
+      const FlowOp& fl = ops[per * L];
+      float* A = reinterpret_cast<float*>(lb + ly.aff);
+      for (int k = 0; k < D; ++k)
+        for (int n = 0; n < D; ++n) A[slot(L - 1, k) * NS_DP + n] = blob[fl.w_off + k * fl.Npad + n];
+      for (int n = 0; n < D; ++n) A[NS_DP * NS_DP + n] = blob[fl.b_off + n];
+    }
+    if (tc_put_overflow()) return 0;
+    if (cudaMalloc(&t.d_image[l], bytes) != cudaSuccess) return 2;
+    if (cudaMemcpy(t.d_image[l], img.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) return 2;
+    t.layer[l].d_tr = d_tr[l];
+  }
+  t.image_bytes = bytes;
+  for (int j = 0; j < NS_DP; ++j) t.out_slot[j] = (int8_t)j;
+  t.L = L;
+  t.D = D;
+  t.NB = NB;
+  t.nch = 1;
+  t.inverse = inverse;
+  t.additive = additive;
+  t.ac = 1;
+  t.narrow = H <= TC_H / 2;
+  t.tail_bound = 0.f;
   t.valid = true;
   return 0;
 }
@@ -386,9 +550,40 @@ __device__ __forceinline__ void ns_chunk(const NsParams& P, uint32_t tg, int c, 
   }
 }
 
+// AC mode: nflows' AffineCouplingTransform on the transformed slots AC_TR0 + i, i = 8 c .. 8 c + 7 of
+// this thread; the final layer's single chunk holds shift_i in column i and the unconstrained
+// scale_i in column 16 + i (scale = sigmoid(u + 2) + 1e-3; additive coupling: scale = 1).  Slots
+// >= d_tr carry zero weights and a zero state: only their log-scale has to be masked.
+__device__ __forceinline__ void ac_coupling(const NsParams& P, uint32_t tg, int c, uint32_t bar_cr, uint32_t& pc,
+                                            float& ld) {
+  rs_wait(bar_cr, pc);
+  uint32_t sh[8], sc[8], st[8];
+  ns_ld8(tg + NS_COL_D2 + 8 * c, sh);
+  ns_ld8(tg + NS_COL_D2 + 16 + 8 * c, sc);
+  ns_ld8(tg + NS_COL_ST + AC_TR0 + 8 * c, st);
+  tc_wait_ld();
+  float s[8];
+#pragma unroll
+  for (int f = 0; f < 8; ++f) s[f] = tc_ex2((__uint_as_float(sc[f]) + 2.f) * -1.4426950408889634f);
+#pragma unroll
+  for (int f = 0; f < 8; ++f) s[f] = P.additive ? 1.f : tc_rcp(1.f + s[f]) + 1e-3f;
+  float acc = 0.f;
+#pragma unroll
+  for (int f = 0; f < 8; ++f) {
+    const float t = __uint_as_float(sh[f]), x = __uint_as_float(st[f]);
+    const float y = P.inverse ? (x - t) * tc_rcp(s[f]) : fmaf(x, s[f], t);
+    st[f] = __float_as_uint(y);
+    const float ls = tc_lg2(s[f]) * 0.6931471805599453f;
+    acc += (8 * c + f < P.ly.d_tr && !P.additive) ? ls : 0.f;
+  }
+  ld += P.inverse ? -acc : acc;
+  tc_st8(tg + NS_COL_ST + AC_TR0 + 8 * c, st);
+  tc_wait_st();
+}
+
 // One layer pass for one row; the state is in TMEM columns NS_COL_ST.., the log|det| partial of
 // this thread is returned (c == 0 and c == 1 threads of a row each sum their own features).
-template <bool NARROW>
+template <bool NARROW, bool AC>
 __device__ __forceinline__ float ns_run_layer(const NsParams& P, const NsLayout& lay, uint32_t tg, int g, int c,
                                               NsBars& B) {
   float ld = 0.f;
@@ -407,6 +602,15 @@ __device__ __forceinline__ float ns_run_layer(const NsParams& P, const NsLayout&
   rs_arrive(B.in);  // -> G0
   for (int b = 0; b < P.NB; ++b) {
     rs_wait(B.out, B.ph);
+    if (AC && b == 0) {
+      // the state after this layer's affine: G0's columns 64 .. 95 (the first columns of D2, which
+      // the first block's GEMM overwrites only after this epilogue has arrived) -> own state slots
+      uint32_t r[16];
+      tc_ld16(tg + NS_COL_D2 + 16 * c, r);
+      tc_wait_ld();
+      tc_pin16(r);
+      ns_st16(tg + NS_COL_ST + 16 * c, r);
+    }
     rs_hidden<true, NARROW>(tg, NS_COL_D, c);
     rs_arrive(B.in);
     rs_wait(B.out, B.ph);
@@ -419,15 +623,19 @@ __device__ __forceinline__ float ns_run_layer(const NsParams& P, const NsLayout&
   // dead once its activation is the A operand), so chunk j + 1 is computed while chunk j's
   // splines run: Gf chunk j: (D2 | D)[0:48] = Wf_j a + bf_j
   rs_arrive(B.in);
-  for (int j = 0; j < P.nch; j += 2) {
-    ns_chunk(P, tg, c, j, NS_COL_D2, B.cr0, B.pc0, B.cf0, ld);
-    if (j + 1 < P.nch) ns_chunk(P, tg, c, j + 1, NS_COL_D, B.cr1, B.pc1, B.cf1, ld);
+  if (AC) {
+    ac_coupling(P, tg, c, B.cr0, B.pc0, ld);
+  } else {
+    for (int j = 0; j < P.nch; j += 2) {
+      ns_chunk(P, tg, c, j, NS_COL_D2, B.cr0, B.pc0, B.cf0, ld);
+      if (j + 1 < P.nch) ns_chunk(P, tg, c, j + 1, NS_COL_D, B.cr1, B.pc1, B.cf1, ld);
+    }
   }
   ns_tile_sync(g);  // the state written by the twin warp is visible before the next split
   return ld;
 }
 
-template <int NKS>
+template <int NKS, bool AC>
 __device__ __forceinline__ void ns_issuer(const NsParams& P, const NsLayout& lay, uint32_t img_s, uint32_t tg,
                                           const NsBars& B, int64_t my_tiles) {
   const uint32_t bar_in = B.in, bar_out = B.out;
@@ -457,12 +665,16 @@ __device__ __forceinline__ void ns_issuer(const NsParams& P, const NsLayout& lay
     tc_mbar_wait(bar_in, ph);
     ph ^= 1;
     tc_fence_after();
-    tc_mma_ss_e(d, ones, bias(lb + lay.b0), ID64, 0);
+    // (AC: N = 96 -- columns 64 .. 95, the first of D2, receive the state after the layer's affine)
+    constexpr int ROWS0 = AC ? AC_ROWS0 : TC_H;
+    constexpr uint32_t ID0 = tc_idesc(128, ROWS0);
+    const uint64_t d0 = tc_desc(lb, ROWS0 * 16, 128);
+    tc_mma_ss_e(d, ones, bias(lb + lay.b0), ID0, 0);
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
-      tc_mma_ts_e(d, ah + 8 * ks, adv(d64, lay.w0hi + ks * 2 * TC_H * 16), ID64, 1);
-      tc_mma_ts_e(d, al + 8 * ks, adv(d64, lay.w0hi + ks * 2 * TC_H * 16), ID64, 1);
-      tc_mma_ts_e(d, ah + 8 * ks, adv(d64, lay.w0lo + ks * 2 * TC_H * 16), ID64, 1);
+      tc_mma_ts_e(d, ah + 8 * ks, adv(d0, lay.w0hi + ks * 2 * ROWS0 * 16), ID0, 1);
+      tc_mma_ts_e(d, al + 8 * ks, adv(d0, lay.w0hi + ks * 2 * ROWS0 * 16), ID0, 1);
+      tc_mma_ts_e(d, ah + 8 * ks, adv(d0, lay.w0lo + ks * 2 * ROWS0 * 16), ID0, 1);
     }
     tc_commit_e(bar_out);
     for (int b = 0; b < P.NB; ++b) {
@@ -502,12 +714,12 @@ __device__ __forceinline__ void ns_issuer(const NsParams& P, const NsLayout& lay
 }
 
 // MODE 0: apply (rows supplied), MODE 1: populate.  One coupling layer per launch.
-template <int MODE, bool NARROW>
+template <int MODE, bool NARROW, bool AC>
 __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_nsf_kernel(NsParams P, TcIO io, PopulateArgs A) {
   extern __shared__ __align__(1024) uint8_t ns_smem[];
   NsShared* sh = reinterpret_cast<NsShared*>(ns_smem + tc_image_pad(P.image_bytes));
   const int tid = threadIdx.x;
-  const NsLayout lay = ns_layout(P.NB, P.nch);
+  const NsLayout lay = ns_layout(P.NB, P.nch, AC);
   if (MODE == 1 && P.last) {
     if (tid < 4 * NS_DP) {
       const int which = tid / NS_DP, d = tid % NS_DP;
@@ -621,7 +833,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_nsf_kernel(NsParams P, 
           ns_tile_sync(g);  // LD columns are reused below
         }
       }
-      float ld = ns_run_layer<NARROW>(P, lay, tg, g, c, B);
+      float ld = ns_run_layer<NARROW, AC>(P, lay, tg, g, c, B);
       // ---- combine the two halves' log|det| and hand the row on
       ns_st1(tg + NS_COL_LD + c, __float_as_uint(ld));
       tc_wait_st();
@@ -652,6 +864,34 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_nsf_kernel(NsParams P, 
           // output feature j = state slot out_slot[j]: gather through registers with a
           // compile-time sweep (no dynamic register indexing)
           float outv[NS_DP];
+          if (AC) {
+            // the affine after the last coupling (slots of the last layer -> natural order), fp32 on
+            // the CUDA cores: k-major [32][32] + bias in the image, warp-wide broadcast loads
+            const float* aff = reinterpret_cast<const float*>(ns_smem + lay.aff);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              float o[16];
+              const float4* b4 = reinterpret_cast<const float4*>(aff + NS_DP * NS_DP + 16 * half);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 b = b4[q];
+                o[4 * q] = b.x, o[4 * q + 1] = b.y, o[4 * q + 2] = b.z, o[4 * q + 3] = b.w;
+              }
+#pragma unroll
+              for (int k = 0; k < NS_DP; ++k) {
+                const float hk = __uint_as_float(k < 16 ? s0[k & 15] : s1[k & 15]);
+                const float4* w4 = reinterpret_cast<const float4*>(aff + k * NS_DP + 16 * half);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 w = w4[q];
+                  tc_fma2(o[4 * q + 0], o[4 * q + 1], w.x, w.y, hk, hk);
+                  tc_fma2(o[4 * q + 2], o[4 * q + 3], w.z, w.w, hk, hk);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) outv[16 * half + j] = o[j];
+            }
+          } else {
 #pragma unroll
           for (int j = 0; j < NS_DP; ++j) {
             float v = 0.f;
@@ -662,6 +902,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_nsf_kernel(NsParams P, 
               v = s == 16 + k ? __uint_as_float(s1[k]) : v;
             }
             outv[j] = v;
+          }
           }
           const float logj = ld + P.const_logdet;
           if (MODE == 0) {
@@ -695,7 +936,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_nsf_kernel(NsParams P, 
     const NsBars B{tc_smem_u32(&sh->bar_in[g]),    tc_smem_u32(&sh->bar_out[g]),   tc_smem_u32(&sh->bar_cr[g][0]),
                    tc_smem_u32(&sh->bar_cr[g][1]), tc_smem_u32(&sh->bar_cf[g][0]), tc_smem_u32(&sh->bar_cf[g][1]),
                    0u, 0u, 0u};
-    ns_issuer<NARROW ? 2 : 4>(P, lay, tc_smem_u32(ns_smem), __shfl_sync(0xffffffffu, tmem, 0) + g * NS_COLS, B,
+    ns_issuer<NARROW ? 2 : 4, AC>(P, lay, tc_smem_u32(ns_smem), __shfl_sync(0xffffffffu, tmem, 0) + g * NS_COLS, B,
               rs_my_tiles(ntiles, g));
     __syncwarp();
   }
@@ -727,13 +968,17 @@ template <int MODE>
 inline int ns_launch(NsProgram& t, const TcIO& io, const PopulateArgs& A, int64_t n, int num_sms, cudaStream_t st) {
   if (ns_reserve(t, n)) return 0;
   const size_t smem = ns_smem_bytes(t.image_bytes);
-  if (tc_prep(t.narrow ? (const void*)flow_tc_nsf_kernel<MODE, true> : (const void*)flow_tc_nsf_kernel<MODE, false>, smem))
-    return 0;
+  const void* kern = t.ac ? (t.narrow ? (const void*)flow_tc_nsf_kernel<MODE, true, true>
+                                      : (const void*)flow_tc_nsf_kernel<MODE, false, true>)
+                          : (t.narrow ? (const void*)flow_tc_nsf_kernel<MODE, true, false>
+                                      : (const void*)flow_tc_nsf_kernel<MODE, false, false>);
+  if (tc_prep(kern, smem)) return 0;
   for (int l = 0; l < t.L; ++l) {
     NsParams P;
     P.image = t.d_image[l];
-    const NsLayout lay = ns_layout(t.NB, t.nch);
-    P.image_bytes = lay.layer_bytes + TC_ONES_BYTES + TC_ZERO_BYTES;
+    const NsLayout lay = ns_layout(t.NB, t.nch, t.ac);
+    P.image_bytes = lay.layer_bytes + TC_ONES_BYTES + (t.ac ? AC_ZERO_BYTES : TC_ZERO_BYTES);
+    P.additive = t.additive;
     P.D = t.D;
     P.NB = t.NB;
     P.nch = t.nch;
@@ -747,8 +992,11 @@ inline int ns_launch(NsProgram& t, const TcIO& io, const PopulateArgs& A, int64_
     P.sc_h = t.d_scratch;
     P.sc_ld = t.d_scratch ? t.d_scratch + (size_t)t.scratch_rows * NS_DP : nullptr;
     P.sc_ss = t.d_scratch ? t.d_scratch + (size_t)t.scratch_rows * (NS_DP + 1) : nullptr;
-    if (t.narrow) flow_tc_nsf_kernel<MODE, true><<<rs_grid(n, num_sms), RS_THREADS, smem, st>>>(P, io, A);
-    else flow_tc_nsf_kernel<MODE, false><<<rs_grid(n, num_sms), RS_THREADS, smem, st>>>(P, io, A);
+    const int grid = rs_grid(n, num_sms);
+    if (t.ac && t.narrow) flow_tc_nsf_kernel<MODE, true, true><<<grid, RS_THREADS, smem, st>>>(P, io, A);
+    else if (t.ac) flow_tc_nsf_kernel<MODE, false, true><<<grid, RS_THREADS, smem, st>>>(P, io, A);
+    else if (t.narrow) flow_tc_nsf_kernel<MODE, true, false><<<grid, RS_THREADS, smem, st>>>(P, io, A);
+    else flow_tc_nsf_kernel<MODE, false, false><<<grid, RS_THREADS, smem, st>>>(P, io, A);
     if (cudaGetLastError() != cudaSuccess) return 0;
   }
   return t.L;

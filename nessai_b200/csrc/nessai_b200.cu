@@ -155,6 +155,9 @@ extern "C" int nb200_flow_set_program(nb200_flow* f, int direction, const int32_
     if (!p.rs.valid) {
       if (int rc = ns_build(p.ns, p.h_ops, n_ops, h_blob, f->D, f->H, f->activation))
         return fail(rc, "ns_build failed: %s", cudaGetErrorString(cudaGetLastError()));
+      if (!p.ns.valid)  // RealNVP with the ResidualNet conditioner at 17 .. 32 features
+        if (int rc = ac_build(p.ns, p.h_ops, n_ops, h_blob, f->D, f->H, f->activation))
+          return fail(rc, "ac_build failed: %s", cudaGetErrorString(cudaGetLastError()));
       p.ns.const_logdet = (float)const_logdet;
     }
   }

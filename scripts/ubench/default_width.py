@@ -7,7 +7,8 @@ from nessai_b200 import _lib
 from nessai_b200.flowmodel import B200FlowModel
 lib = _lib.load()
 n = 1_000_000
-for D, net in ((16, "resnet"), (8, "resnet"), (4, "resnet"), (2, "resnet"), (16, "mlp"), (16, "nsf"), (8, "nsf")):
+for D, net in ((16, "resnet"), (8, "resnet"), (4, "resnet"), (2, "resnet"), (16, "mlp"), (16, "nsf"), (8, "nsf"),
+               (20, "resnet"), (24, "resnet"), (32, "resnet")):
     cfg = dict(n_inputs=D, n_blocks=4, n_layers=2, ftype="realnvp", net=net)  # n_neurons: the default
     if net == "nsf":
         cfg = dict(n_inputs=D, n_blocks=4, n_layers=2, ftype="nsf")

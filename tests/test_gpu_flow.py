@@ -202,6 +202,12 @@ def test_tensor_core_paths_match_generic_kernel(name, launches, n, tmp_path):
     ("realnvp", "resnet", 16, 64, 3, 3),
     ("nsf", "resnet", 10, 20, 2, 3),
     ("nsf", "resnet", 32, 48, 2, 3),
+    # RealNVP with the default conditioner at 17 .. 32 features: the tile machinery of the spline kernel
+    # with an affine coupling (one launch per layer)
+    ("realnvp", "resnet", 20, 40, 2, 3),
+    ("realnvp", "resnet", 32, 64, 2, 3),
+    ("realnvp", "resnet", 17, 34, 1, 3),
+    ("realnvp", "resnet", 24, 30, 2, 3),
 ])
 def test_hidden_width_below_64_runs_on_the_tensor_core_kernels(ftype, net, D, H, n_layers, launches, tmp_path):
     """The reference's DEFAULT conditioner width is 2 * n_inputs

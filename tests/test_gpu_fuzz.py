@@ -139,6 +139,11 @@ def test_random_flow_config_fused_populate_turn_matches_oracle(seed, tmp_path):
     if seed % 3 == 0:  # make sure the narrow MLP draw kernel is in the sweep
         cfg.update(net="mlp", n_layers=2, activation="relu", n_neurons=int(rng.integers(4, 33)),
                    n_inputs=int(rng.integers(2, 17)))
+    elif seed % 3 == 1:  # ... and the 17 .. 32-feature ResidualNet draw kernel
+        cfg.update(net="resnet", n_layers=int(rng.integers(1, 3)), activation="relu", n_inputs=int(rng.integers(17, 33)))
+        cfg.pop("n_neurons", None)
+        if seed % 2:
+            cfg["n_neurons"] = int(rng.integers(8, 33))
     D = cfg["n_inputs"]
     torch.manual_seed(seed)
     fm = B200FlowModel(flow_config=dict(cfg), training_config=dict(device_tag="cuda:0"), output=str(tmp_path))
