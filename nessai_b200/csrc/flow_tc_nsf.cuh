@@ -253,7 +253,7 @@ inline int ac_build(NsProgram& t, const FlowOp* ops, int n_ops, const float* blo
   t.valid = false;
   if (D > NS_DP || D <= TC_DP || H < 1 || H > TC_H || activation != ACT_RELU || n_ops < 6) return 0;
   int NB = -1;
-  for (int nb = 1; nb <= 2; ++nb)
+  for (int nb = 1; nb <= RS_MAXNB; ++nb)
     if ((n_ops - 1) % (2 * nb + 3) == 0 && ops[2].type == OP_LINEAR && ops[2 * nb + 2].type == OP_COUPLING_AFFINE)
       NB = nb;
   if (NB < 0) return 0;

@@ -208,6 +208,7 @@ def test_tensor_core_paths_match_generic_kernel(name, launches, n, tmp_path):
     ("realnvp", "resnet", 32, 64, 2, 3),
     ("realnvp", "resnet", 17, 34, 1, 3),
     ("realnvp", "resnet", 24, 30, 2, 3),
+    ("realnvp", "resnet", 19, 38, 3, 3),
 ])
 def test_hidden_width_below_64_runs_on_the_tensor_core_kernels(ftype, net, D, H, n_layers, launches, tmp_path):
     """The reference's DEFAULT conditioner width is 2 * n_inputs
