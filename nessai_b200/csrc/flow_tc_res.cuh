@@ -38,17 +38,24 @@ constexpr int RS_BIAS = TC_H * 16;            // bias operand (K-chunk 0 only): 
 
 struct RsLayout {  // byte offsets inside one layer of the image
   int w0hi, w0lo, blk, wfhi, wflo, b0, bblk, bf, layer_bytes;
+  int hrows, wbig, wfin, bias;  // hidden rows of a B operand; bytes of a hidden / final weight matrix, a bias operand
 };
-__host__ __device__ inline RsLayout rs_layout(int NB) {
+// narrow (conditioner width <= 32): the hidden operands are 32 rows x 32 K (2 KB instead of 8 KB), so a
+// layer is 27 KB instead of 77 KB and the whole flow fits ONE pass (no scratch hand-off)
+__host__ __device__ inline RsLayout rs_layout(int NB, bool narrow = false) {
   RsLayout o;
+  o.hrows = narrow ? TC_H / 2 : TC_H;
+  o.wbig = o.hrows * 16 * (o.hrows / 8);
+  o.wfin = TC_N3 * 16 * (o.hrows / 8);
+  o.bias = o.hrows * 16;
   o.w0hi = 0;
   o.w0lo = RS_W_SMALL;
-  o.blk = 2 * RS_W_SMALL;                 // per block: WA hi, WA lo, WB hi, WB lo (4 x 8 KB)
-  o.wfhi = o.blk + NB * 4 * RS_W_BIG;
-  o.wflo = o.wfhi + RS_W_FIN;
-  o.b0 = o.wflo + RS_W_FIN;
+  o.blk = 2 * RS_W_SMALL;                 // per block: WA hi, WA lo, WB hi, WB lo
+  o.wfhi = o.blk + NB * 4 * o.wbig;
+  o.wflo = o.wfhi + o.wfin;
+  o.b0 = o.wflo + o.wfin;
   o.bblk = o.b0 + RS_BIAS0;               // per block: bA, bB
-  o.bf = o.bblk + NB * 2 * RS_BIAS;
+  o.bf = o.bblk + NB * 2 * o.bias;
   o.layer_bytes = o.bf + TC_N3 * 16;
   return o;
 }
@@ -140,7 +147,8 @@ inline int rs_build(RsProgram& t, const FlowOp* ops, int n_ops, const float* blo
     t.d_tr[l] = c.d_tr;
   }
   tc_put_overflow() = false;
-  const RsLayout lay = rs_layout(NB);
+  const bool narrow = H <= TC_H / 2;
+  const RsLayout lay = rs_layout(NB, narrow);
   const int fixed = 2 * TC_AFF_BYTES + TC_ONES_BYTES + TC_ZERO_BYTES + 4096;
   int per_pass = (227 * 1024 - fixed) / (lay.layer_bytes + TC_AFF_BYTES);
   if (per_pass < 1) return 0;
@@ -206,17 +214,17 @@ inline int rs_build(RsProgram& t, const FlowOp* ops, int n_ops, const float* blo
         }
       }
       for (int b = 0; b < NB; ++b) {
-        uint8_t* wb = lb + lay.blk + (size_t)b * 4 * RS_W_BIG;
+        uint8_t* wb = lb + lay.blk + (size_t)b * 4 * lay.wbig;
         const FlowOp& x = o[1 + 2 * b];
         const FlowOp& y = o[2 + 2 * b];
         for (int n = 0; n < H; ++n)
           for (int k = 0; k < H; ++k) {
-            tc_put(wb, wb + RS_W_BIG, TC_H, n, k, blob[x.w_off + k * x.Npad + n]);
-            tc_put(wb + 2 * RS_W_BIG, wb + 3 * RS_W_BIG, TC_H, n, k, blob[y.w_off + k * y.Npad + n]);
+            tc_put(wb, wb + lay.wbig, lay.hrows, n, k, blob[x.w_off + k * x.Npad + n]);
+            tc_put(wb + 2 * lay.wbig, wb + 3 * lay.wbig, lay.hrows, n, k, blob[y.w_off + k * y.Npad + n]);
           }
         for (int n = 0; n < H; ++n) {
-          put_bias(lb + lay.bblk + (size_t)(2 * b) * RS_BIAS, n, blob[x.b_off + n]);
-          put_bias(lb + lay.bblk + (size_t)(2 * b + 1) * RS_BIAS, n, blob[y.b_off + n]);
+          put_bias(lb + lay.bblk + (size_t)(2 * b) * lay.bias, n, blob[x.b_off + n]);
+          put_bias(lb + lay.bblk + (size_t)(2 * b + 1) * lay.bias, n, blob[y.b_off + n]);
         }
       }
       const FlowOp& c = o[1 + 2 * NB];
@@ -242,7 +250,7 @@ inline int rs_build(RsProgram& t, const FlowOp* ops, int n_ops, const float* blo
   t.n_pass = n_pass;
   t.inverse = inverse;
   t.additive = additive;
-  t.narrow = H <= TC_H / 2;
+  t.narrow = narrow;
   t.valid = true;
   return 0;
 }
@@ -373,7 +381,9 @@ template <int NKS>
 __device__ __forceinline__ void rs_issuer_n(const RsParams& P, const RsLayout& lay, uint32_t img_s,
                                             uint32_t tg, uint32_t bar_in, uint32_t bar_out,
                                             int64_t my_tiles) {
-  constexpr uint32_t ID64 = tc_idesc(128, TC_H), ID16 = tc_idesc(128, TC_N3);
+  // hidden operands: 64 rows (N = 64), or 32 (N = 32) in the narrow instantiation
+  constexpr int HROWS = NKS == 2 ? TC_H / 2 : TC_H;
+  constexpr uint32_t ID64 = tc_idesc(128, HROWS), ID16 = tc_idesc(128, TC_N3);
   const uint32_t d = tg + RS_COL_D, d2 = tg + RS_COL_D2, ah = tg + RS_COL_AH, al = tg + RS_COL_AL;
   const int n_aff = P.nl + (P.last ? 1 : 0);
   const uint32_t ones_s = img_s + P.nl * lay.layer_bytes + n_aff * TC_AFF_BYTES;
@@ -397,7 +407,7 @@ __device__ __forceinline__ void rs_issuer_n(const RsParams& P, const RsLayout& l
   for (int64_t it = 0; it < my_tiles; ++it) {
     for (int li = 0; li < P.nl; ++li) {
       const uint32_t lb = img_s + li * lay.layer_bytes;
-      const uint64_t d64 = tc_desc(lb, TC_H * 16, 128);
+      const uint64_t d64 = tc_desc(lb, HROWS * 16, 128);
       const uint64_t d16 = tc_desc(lb, TC_N3 * 16, 128);
       // G0
       tc_mbar_wait(bar_in, ph);
@@ -411,18 +421,18 @@ __device__ __forceinline__ void rs_issuer_n(const RsParams& P, const RsLayout& l
       tc_mma_ts_e(d, ah, adv(d1, lay.w0lo), ID1, 1);
       tc_commit_e(bar_out);
       for (int b = 0; b < P.NB; ++b) {
-        const uint32_t wb = lay.blk + b * 4 * RS_W_BIG;
+        const uint32_t wb = lay.blk + b * 4 * lay.wbig;
         tc_mbar_wait(bar_in, ph);
         ph ^= 1;
         tc_fence_after();
-        gemm64(d2, bias(lb + lay.bblk + 2 * b * RS_BIAS), adv(d64, wb), adv(d64, wb + RS_W_BIG), TC_H,
+        gemm64(d2, bias(lb + lay.bblk + 2 * b * lay.bias), adv(d64, wb), adv(d64, wb + lay.wbig), HROWS,
                ID64, 0);
         tc_commit_e(bar_out);
         tc_mbar_wait(bar_in, ph);
         ph ^= 1;
         tc_fence_after();
-        gemm64(d, bias(lb + lay.bblk + (2 * b + 1) * RS_BIAS), adv(d64, wb + 2 * RS_W_BIG),
-               adv(d64, wb + 3 * RS_W_BIG), TC_H, ID64, 1);
+        gemm64(d, bias(lb + lay.bblk + (2 * b + 1) * lay.bias), adv(d64, wb + 2 * lay.wbig),
+               adv(d64, wb + 3 * lay.wbig), HROWS, ID64, 1);
         tc_commit_e(bar_out);
       }
       tc_mbar_wait(bar_in, ph);
@@ -448,7 +458,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_res_kernel(RsParams P, 
   extern __shared__ __align__(1024) uint8_t rs_smem[];
   RsShared* sh = reinterpret_cast<RsShared*>(rs_smem + tc_image_pad(P.image_bytes));
   const int tid = threadIdx.x;
-  const RsLayout lay = rs_layout(P.NB);
+  const RsLayout lay = rs_layout(P.NB, NARROW);
   if (MODE == 1 && P.last) {
     if (tid < 4 * TC_DP) {
       const int which = tid / TC_DP, d = tid % TC_DP;

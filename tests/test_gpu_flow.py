@@ -195,10 +195,10 @@ def test_tensor_core_paths_match_generic_kernel(name, launches, n, tmp_path):
 @pytest.mark.parametrize("ftype,net,D,H,n_layers,launches", [
     ("realnvp", "mlp", 16, 32, 2, 1),     # nessai's default width: 2 * n_inputs
     ("realnvp", "mlp", 4, 8, 2, 1),
-    ("realnvp", "resnet", 16, 32, 2, 2),  # the default conditioner at its default width
-    ("realnvp", "resnet", 7, 14, 2, 2),
+    ("realnvp", "resnet", 16, 32, 2, 1),  # the default conditioner at its default width: 27 KB of weights a
+    ("realnvp", "resnet", 7, 14, 2, 1),   # layer in the narrow image, the whole flow in one pass
     ("realnvp", "resnet", 12, 40, 1, 1),
-    ("realnvp", "resnet", 8, 16, 3, 3),   # three residual blocks: 113 KB of weights a layer, one layer a pass
+    ("realnvp", "resnet", 8, 16, 3, 1),   # three residual blocks (wide image: 113 KB of weights a layer, one layer a pass)
     ("realnvp", "resnet", 16, 64, 3, 3),
     ("nsf", "resnet", 10, 20, 2, 3),
     ("nsf", "resnet", 32, 48, 2, 3),
