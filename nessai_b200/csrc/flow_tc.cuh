@@ -105,6 +105,7 @@ struct TcProgram {
   int d_id[TC_MAXL] = {0}, d_tr[TC_MAXL] = {0};
   int additive = 0, inverse = 0;
   int narrow = 0;  // conditioner width <= 32: the hidden GEMMs run two K-steps, the epilogues 32 columns
+  int act = ACT_RELU;  // conditioner activation (a compile-time parameter of the kernels)
   float const_logdet = 0.f;
 };
 
@@ -215,7 +216,7 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
                     int activation, int final_buf) {
   t.valid = false;
   (void)final_buf;
-  if (D > TC_DP || H < 1 || H > TC_H || activation != ACT_RELU) return 0;
+  if (D > TC_DP || H < 1 || H > TC_H || activation < ACT_RELU || activation > ACT_SILU) return 0;
   if (n_ops < 5 || (n_ops - 1) % 4 != 0) return 0;
   const int L = (n_ops - 1) / 4;
   if (L > TC_MAXL) return 0;
@@ -331,6 +332,7 @@ inline int tc_build(TcProgram& t, const FlowOp* ops, int n_ops, const float* blo
   t.inverse = inverse;
   t.additive = additive;
   t.narrow = H <= TC_H / 2;
+  t.act = activation;
   t.valid = true;
   return 0;
 }
@@ -549,6 +551,22 @@ __device__ __forceinline__ float tc_lg2(float x) {
   return y;
 }
 
+// The conditioner's activation fused into the split: ReLU is free (cvt .relu); tanh and SiLU
+// (flows/utils.py:24-32, 200-205) cost two SFU operations per value -- ex2 + rcp, absolute error
+// ~2e-7 -- before the split.  ACT: ACT_RELU / ACT_TANH / ACT_SILU of flow_program.h, or TC_ACT_NONE.
+constexpr int TC_ACT_NONE = -1;
+template <int ACT>
+__device__ __forceinline__ float tc_act(float v) {
+  if (ACT == ACT_TANH) return 1.f - 2.f * tc_rcp(1.f + tc_ex2(v * 2.8853900817779268f));
+  if (ACT == ACT_SILU) return v * tc_rcp(1.f + tc_ex2(v * -1.4426950408889634f));
+  return v;
+}
+template <int ACT>
+__device__ __forceinline__ void tc_split_act2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  if (ACT == ACT_TANH || ACT == ACT_SILU) tc_split2<false>(tc_act<ACT>(a), tc_act<ACT>(b), hi, lo);
+  else tc_split2<ACT == ACT_RELU>(a, b, hi, lo);
+}
+
 // The affine coupling on the 8 transformed slots h[TC_TR0 ..], branch-free so that the eight
 // SFU chains (ex2 -> rcp -> lg2 / rcp) interleave instead of running one after the other:
 // r[2f] = shift, r[2f+1] = unconstrained scale, scale = sigmoid(u + 2) + 1e-3.  Slots >= d_tr
@@ -595,7 +613,7 @@ __device__ __forceinline__ float tc_coupling(const uint32_t (&r)[16], float (&h)
 // GEMM) -> ReLU -> split -> the row's A operand in TMEM (hi: 32 columns, lo: 32).
 // NQ: groups of 16 columns that carry hidden units (4; 2 for a conditioner of width <= 32, whose
 // other columns are the zero padding of the weight image and are not an operand of any MMA).
-template <int NQ = 4>
+template <int NQ = 4, int ACT = ACT_RELU>
 __device__ __forceinline__ void tc_hidden_epilogue(uint32_t tg) {
   uint32_t ra[16], rb[16];
   tc_ld16(tg + TC_COL_D, ra);
@@ -612,7 +630,7 @@ __device__ __forceinline__ void tc_hidden_epilogue(uint32_t tg) {
 #ifdef NB200_ABL_NO_SPLIT
       hi[j] = cur[2 * j] & 0xffff0000u; lo[j] = cur[2 * j + 1];
 #else
-      tc_split2<true>(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1]), hi[j], lo[j]);
+      tc_split_act2<ACT>(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1]), hi[j], lo[j]);
 #endif
     }
     tc_st8(tg + TC_COL_AH + 8 * q, hi);
@@ -754,7 +772,7 @@ __device__ __forceinline__ void tc_submit(const TcParams& P, const TcGroup& G, i
 // The epilogue-group body shared by the apply and populate kernels: runs the whole
 // program for one row held in h[] and returns the row log|det J| (without const).
 // tg: the group's TMEM base with this warp's lane quarter in the upper half-word.
-template <bool NARROW>
+template <bool NARROW, int ACT>
 __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* img, uint32_t tg,
                                             const TcGroup& G, uint32_t& ph_out, float (&h)[TC_DP]) {
   const uint32_t bar_out = G.bar_out;
@@ -795,7 +813,7 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
 #pragma unroll
       for (int d = 0; d < TC_DP; ++d) h[d] = __uint_as_float(r[d]);
     }
-    tc_hidden_epilogue<NARROW ? 2 : 4>(tg);
+    tc_hidden_epilogue<NARROW ? 2 : 4, ACT>(tg);
     tc_fence_before();
     TC_STAMP_E(3);
     tc_submit<NARROW>(P, G, l, 2);
@@ -804,7 +822,7 @@ __device__ __forceinline__ float tc_run_row(const TcParams& P, const uint8_t* im
     TC_STAMP_E(4);
     ph_out ^= 1;
     tc_fence_after();
-    tc_hidden_epilogue<NARROW ? 2 : 4>(tg);
+    tc_hidden_epilogue<NARROW ? 2 : 4, ACT>(tg);
     tc_fence_before();
     TC_STAMP_E(5);
     tc_submit<NARROW>(P, G, l, 3);
@@ -959,7 +977,7 @@ __device__ __forceinline__ int64_t tc_my_tiles(int64_t ntiles, int g) {
 // NARROW: conditioner width <= 32 (two K-steps in the hidden GEMMs, 32-column hidden epilogues); a
 // compile-time switch so that each instantiation's hot loop holds one variant only (both variants
 // inlined behind a run-time branch cost the wide kernels 6 - 27 %: instruction cache).
-template <bool NARROW>
+template <bool NARROW, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P, TcIO io) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   TcShared* sh;
@@ -992,7 +1010,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P
       }
 #pragma unroll
       for (int d = 0; d < TC_DP; ++d) ss_in = fmaf(h[d], h[d], ss_in);
-      const float ld = tc_run_row<NARROW>(P, tc_smem, tg, G, ph_out, h) + P.const_logdet;
+      const float ld = tc_run_row<NARROW, ACT>(P, tc_smem, tg, G, ph_out, h) + P.const_logdet;
       float ss_out = 0.f;
 #pragma unroll
       for (int d = 0; d < TC_DP; ++d) ss_out = d < P.D ? fmaf(h[d], h[d], ss_out) : ss_out;
@@ -1025,7 +1043,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_apply_kernel(TcParams P
   tc_epilogue_end(sh);
 }
 
-template <bool NARROW>
+template <bool NARROW, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParams P, PopulateArgs A) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   TcShared* sh = reinterpret_cast<TcShared*>(tc_smem + tc_image_pad(P.image_bytes));
@@ -1072,7 +1090,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_populate_kernel(TcParam
       }
       const float rad = sqrtf(ss) * A.sqrt_t;
       const bool alive = !(A.r_max > 0.f) || (rad <= A.r_max);
-      const float logj = tc_run_row<NARROW>(P, tc_smem, tg, G, ph_out, h) + P.const_logdet;
+      const float logj = tc_run_row<NARROW, ACT>(P, tc_smem, tg, G, ph_out, h) + P.const_logdet;
       const float base_lp = -0.5f * ss - 0.5f * P.D * TC_LOG_2PI;
       populate_row<TC_DP>(A, P.D, [&](int d) { return h[d]; }, row, alive, base_lp, logj, vmax,
                           vcount, c_scale, c_shift, c_lo, c_hi, log_const);
@@ -1130,6 +1148,18 @@ inline TcParams tc_params(const TcProgram& t, float const_logdet) {
   return P;
 }
 
+// run LAUNCH(NARROW, ACT) for the run-time (narrow, act): one kernel instantiation per combination
+#define NB200_TC_DISPATCH(LAUNCH, narrow, act)                \
+  if (narrow) {                                                \
+    if ((act) == ACT_TANH) LAUNCH(true, ACT_TANH)              \
+    else if ((act) == ACT_SILU) LAUNCH(true, ACT_SILU)         \
+    else LAUNCH(true, ACT_RELU)                                \
+  } else {                                                     \
+    if ((act) == ACT_TANH) LAUNCH(false, ACT_TANH)             \
+    else if ((act) == ACT_SILU) LAUNCH(false, ACT_SILU)        \
+    else LAUNCH(false, ACT_RELU)                               \
+  }
+
 inline int tc_grid(int64_t n, int num_sms) {
   const int64_t ntiles = (n + 127) / 128;
   const int64_t want = (ntiles + TC_NG - 1) / TC_NG;
@@ -1139,25 +1169,25 @@ inline int tc_grid(int64_t n, int num_sms) {
 inline int tc_launch_apply(TcProgram& t, const TcIO& io, int num_sms, cudaStream_t st) {
   const size_t smem = tc_smem_bytes(t.image_bytes);
   const int64_t n = io.n;
-  if (t.narrow) {
-    if (tc_prep((const void*)flow_tc_apply_kernel<true>, smem)) return 1;
-    flow_tc_apply_kernel<true><<<tc_grid(n, num_sms), TC_THREADS, smem, st>>>(tc_params(t, t.const_logdet), io);
-  } else {
-    if (tc_prep((const void*)flow_tc_apply_kernel<false>, smem)) return 1;
-    flow_tc_apply_kernel<false><<<tc_grid(n, num_sms), TC_THREADS, smem, st>>>(tc_params(t, t.const_logdet), io);
+#define NB200_TC_APPLY(NARROW, ACT)                                                                            \
+  {                                                                                                              \
+    if (tc_prep((const void*)flow_tc_apply_kernel<NARROW, ACT>, smem)) return 1;                                \
+    flow_tc_apply_kernel<NARROW, ACT><<<tc_grid(n, num_sms), TC_THREADS, smem, st>>>(tc_params(t, t.const_logdet), io); \
   }
+  NB200_TC_DISPATCH(NB200_TC_APPLY, t.narrow, t.act)
+#undef NB200_TC_APPLY
   return cudaGetLastError() != cudaSuccess;
 }
 
 inline int tc_launch_populate(TcProgram& t, const PopulateArgs& A, int num_sms, cudaStream_t st) {
   const size_t smem = tc_smem_bytes(t.image_bytes);
-  if (t.narrow) {
-    if (tc_prep((const void*)flow_tc_populate_kernel<true>, smem)) return 1;
-    flow_tc_populate_kernel<true><<<tc_grid(A.n, num_sms), TC_THREADS, smem, st>>>(tc_params(t, t.const_logdet), A);
-  } else {
-    if (tc_prep((const void*)flow_tc_populate_kernel<false>, smem)) return 1;
-    flow_tc_populate_kernel<false><<<tc_grid(A.n, num_sms), TC_THREADS, smem, st>>>(tc_params(t, t.const_logdet), A);
+#define NB200_TC_POPULATE(NARROW, ACT)                                                                            \
+  {                                                                                                                 \
+    if (tc_prep((const void*)flow_tc_populate_kernel<NARROW, ACT>, smem)) return 1;                                \
+    flow_tc_populate_kernel<NARROW, ACT><<<tc_grid(A.n, num_sms), TC_THREADS, smem, st>>>(tc_params(t, t.const_logdet), A); \
   }
+  NB200_TC_DISPATCH(NB200_TC_POPULATE, t.narrow, t.act)
+#undef NB200_TC_POPULATE
   return cudaGetLastError() != cudaSuccess;
 }
 

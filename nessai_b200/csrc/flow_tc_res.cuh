@@ -71,6 +71,7 @@ struct RsProgram {
   int d_id[TC_MAXL] = {0}, d_tr[TC_MAXL] = {0};
   int additive = 0, inverse = 0;
   int narrow = 0;  // conditioner width <= 32 (see rs_hidden_quarter)
+  int act = ACT_RELU;  // conditioner activation (a compile-time parameter of the kernel)
   float const_logdet = 0.f;
   RsPass pass[RS_MAXPASS];
   float* d_scratch = nullptr;  // [rows][16] state | [rows] log|det| | [rows] sum z^2 (sign: alive)
@@ -100,7 +101,7 @@ struct RsParams {
 inline int rs_build(RsProgram& t, const FlowOp* ops, int n_ops, const float* blob, int D, int H,
                     int activation) {
   t.valid = false;
-  if (D > TC_DP || H < 1 || H > TC_H || activation != ACT_RELU || n_ops < 6) return 0;
+  if (D > TC_DP || H < 1 || H > TC_H || activation < ACT_RELU || activation > ACT_SILU || n_ops < 6) return 0;
   // ops per layer: affine, initial linear, 2 per block, coupling
   int NB = -1;
   for (int nb = 1; nb <= RS_MAXNB; ++nb)
@@ -251,6 +252,7 @@ inline int rs_build(RsProgram& t, const FlowOp* ops, int n_ops, const float* blo
   t.inverse = inverse;
   t.additive = additive;
   t.narrow = narrow;
+  t.act = activation;
   t.valid = true;
   return 0;
 }
@@ -258,7 +260,7 @@ inline int rs_build(RsProgram& t, const FlowOp* ops, int n_ops, const float* blo
 // ------------------------------------------------------------------ device
 // One half (32 columns) of a 64-column accumulator -> (ReLU) -> split -> the matching half of
 // the A operand.  Warp column-half c handles K chunks 2c and 2c + 1.
-template <bool RELU>
+template <int ACT>
 __device__ __forceinline__ void rs_hidden_half(uint32_t tg, int src_col, int c) {
   uint32_t ra[16], rb[16];
   tc_ld16(tg + src_col + 32 * c, ra);
@@ -269,12 +271,12 @@ __device__ __forceinline__ void rs_hidden_half(uint32_t tg, int src_col, int c) 
   uint32_t hi[8], lo[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j)
-    tc_split2<RELU>(__uint_as_float(ra[2 * j]), __uint_as_float(ra[2 * j + 1]), hi[j], lo[j]);
+    tc_split_act2<ACT>(__uint_as_float(ra[2 * j]), __uint_as_float(ra[2 * j + 1]), hi[j], lo[j]);
   tc_st8(tg + RS_COL_AH + 8 * (2 * c), hi);
   tc_st8(tg + RS_COL_AL + 8 * (2 * c), lo);
 #pragma unroll
   for (int j = 0; j < 8; ++j)
-    tc_split2<RELU>(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1]), hi[j], lo[j]);
+    tc_split_act2<ACT>(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1]), hi[j], lo[j]);
   tc_st8(tg + RS_COL_AH + 8 * (2 * c + 1), hi);
   tc_st8(tg + RS_COL_AL + 8 * (2 * c + 1), lo);
   tc_wait_st();
@@ -283,7 +285,7 @@ __device__ __forceinline__ void rs_hidden_half(uint32_t tg, int src_col, int c) 
 // Conditioner width <= 32: only accumulator columns 0 .. 31 carry hidden units (the rest is the
 // zero padding of the weight image, never an MMA operand: the hidden GEMMs run K-steps 0 and 1).
 // The twin warps split those 32 columns: warp column-half c handles K chunk c.
-template <bool RELU>
+template <int ACT>
 __device__ __forceinline__ void rs_hidden_quarter(uint32_t tg, int src_col, int c) {
   uint32_t ra[16];
   tc_ld16(tg + src_col + 16 * c, ra);
@@ -292,15 +294,19 @@ __device__ __forceinline__ void rs_hidden_quarter(uint32_t tg, int src_col, int 
   uint32_t hi[8], lo[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j)
-    tc_split2<RELU>(__uint_as_float(ra[2 * j]), __uint_as_float(ra[2 * j + 1]), hi[j], lo[j]);
+    tc_split_act2<ACT>(__uint_as_float(ra[2 * j]), __uint_as_float(ra[2 * j + 1]), hi[j], lo[j]);
   tc_st8(tg + RS_COL_AH + 8 * c, hi);
   tc_st8(tg + RS_COL_AL + 8 * c, lo);
   tc_wait_st();
 }
+template <int ACT, bool NARROW>
+__device__ __forceinline__ void rs_hidden_act(uint32_t tg, int src_col, int c) {
+  if (NARROW) rs_hidden_quarter<ACT>(tg, src_col, c);
+  else rs_hidden_half<ACT>(tg, src_col, c);
+}
 template <bool RELU, bool NARROW>
 __device__ __forceinline__ void rs_hidden(uint32_t tg, int src_col, int c) {
-  if (NARROW) rs_hidden_quarter<RELU>(tg, src_col, c);
-  else rs_hidden_half<RELU>(tg, src_col, c);
+  rs_hidden_act<RELU ? (int)ACT_RELU : TC_ACT_NONE, NARROW>(tg, src_col, c);
 }
 
 struct RsShared {
@@ -325,7 +331,7 @@ __device__ __forceinline__ void rs_arrive(uint32_t bar_in) {
 
 // All layers of this pass for one row.  c == 0 threads own the row state h[]; c == 1 threads
 // only help with the hidden epilogues.  Returns the row log|det J| accumulated in this pass.
-template <bool NARROW>
+template <bool NARROW, int ACT>
 __device__ __forceinline__ float rs_run_row(const RsParams& P, const uint8_t* img, const RsLayout& lay,
                                             uint32_t tg, int c, uint32_t bar_in, uint32_t bar_out,
                                             uint32_t& ph, float (&h)[TC_DP]) {
@@ -355,14 +361,14 @@ __device__ __forceinline__ float rs_run_row(const RsParams& P, const uint8_t* im
 #pragma unroll
         for (int d = 0; d < TC_DP; ++d) h[d] = __uint_as_float(r[d]);
       }
-      rs_hidden<true, NARROW>(tg, RS_COL_D, c);
+      rs_hidden_act<ACT, NARROW>(tg, RS_COL_D, c);
       rs_arrive(bar_in);                                         // -> Ga: D2 = Wa relu(D) + ba
       rs_wait(bar_out, ph);
-      rs_hidden<true, NARROW>(tg, RS_COL_D2, c);
+      rs_hidden_act<ACT, NARROW>(tg, RS_COL_D2, c);
       rs_arrive(bar_in);                                         // -> Gb: D += Wb relu(D2) + bb
     }
     rs_wait(bar_out, ph);
-    rs_hidden<false, NARROW>(tg, RS_COL_D, c);
+    rs_hidden_act<TC_ACT_NONE, NARROW>(tg, RS_COL_D, c);
     rs_arrive(bar_in);                                           // -> Gf: D2[0:16] = Wf D + bf
     rs_wait(bar_out, ph);
     if (c == 0) {
@@ -453,7 +459,7 @@ __device__ __forceinline__ int64_t rs_my_tiles(int64_t ntiles, int g) {
 // MODE 0: apply (rows supplied), MODE 1: populate (Philox draw in the first pass, float64 tail
 // in the last).  A must be valid for MODE 1, io for MODE 0.
 // NARROW: conditioner width <= 32, a compile-time switch (see flow_tc.cuh).
-template <int MODE, bool NARROW>
+template <int MODE, bool NARROW, int ACT>
 __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_res_kernel(RsParams P, TcIO io, PopulateArgs A) {
   extern __shared__ __align__(1024) uint8_t rs_smem[];
   RsShared* sh = reinterpret_cast<RsShared*>(rs_smem + tc_image_pad(P.image_bytes));
@@ -554,7 +560,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) flow_tc_res_kernel(RsParams P, 
           alive = !(A.r_max > 0.f) || (rad <= A.r_max);
         }
       }
-      const float ld = ld0 + rs_run_row<NARROW>(P, rs_smem, lay, tg, c, bar_in, bar_out, ph, h);
+      const float ld = ld0 + rs_run_row<NARROW, ACT>(P, rs_smem, lay, tg, c, bar_in, bar_out, ph, h);
       if (c != 0) continue;
       if (!P.last) {
         if (valid) {
@@ -637,8 +643,7 @@ inline int rs_launch(RsProgram& t, const TcIO& io, const PopulateArgs& A, int64_
   for (int p = 0; p < t.n_pass; ++p) {
     const RsPass& ps = t.pass[p];
     const size_t smem = rs_smem_bytes(ps.image_bytes);
-    if (tc_prep(t.narrow ? (const void*)flow_tc_res_kernel<MODE, true> : (const void*)flow_tc_res_kernel<MODE, false>, smem))
-      return 0;
+
     RsParams P;
     P.image = ps.d_image;
     P.image_bytes = ps.image_bytes;
@@ -657,8 +662,13 @@ inline int rs_launch(RsProgram& t, const TcIO& io, const PopulateArgs& A, int64_
     P.sc_h = t.d_scratch;
     P.sc_ld = t.d_scratch ? t.d_scratch + (size_t)t.scratch_rows * TC_DP : nullptr;
     P.sc_ss = t.d_scratch ? t.d_scratch + (size_t)t.scratch_rows * (TC_DP + 1) : nullptr;
-    if (t.narrow) flow_tc_res_kernel<MODE, true><<<rs_grid(n, num_sms), RS_THREADS, smem, st>>>(P, io, A);
-    else flow_tc_res_kernel<MODE, false><<<rs_grid(n, num_sms), RS_THREADS, smem, st>>>(P, io, A);
+#define NB200_RS_LAUNCH(NARROW, ACT)                                                              \
+  {                                                                                                 \
+    if (tc_prep((const void*)flow_tc_res_kernel<MODE, NARROW, ACT>, smem)) return 0;                \
+    flow_tc_res_kernel<MODE, NARROW, ACT><<<rs_grid(n, num_sms), RS_THREADS, smem, st>>>(P, io, A); \
+  }
+    NB200_TC_DISPATCH(NB200_RS_LAUNCH, t.narrow, t.act)
+#undef NB200_RS_LAUNCH
     if (cudaGetLastError() != cudaSuccess) return 0;
   }
   return t.n_pass;

@@ -192,7 +192,7 @@ def test_tensor_core_paths_match_generic_kernel(name, launches, n, tmp_path):
     np.testing.assert_allclose(out[1][3], z.cpu().numpy(), rtol=2e-4, atol=2e-4)
 
 
-@pytest.mark.parametrize("ftype,net,D,H,n_layers,launches", [
+@pytest.mark.parametrize("ftype,net,D,H,n_layers,launches,act", [(*c, "relu") if len(c) == 6 else c for c in [
     ("realnvp", "mlp", 16, 32, 2, 1),     # nessai's default width: 2 * n_inputs
     ("realnvp", "mlp", 4, 8, 2, 1),
     ("realnvp", "resnet", 16, 32, 2, 1),  # the default conditioner at its default width: 27 KB of weights a
@@ -209,8 +209,14 @@ def test_tensor_core_paths_match_generic_kernel(name, launches, n, tmp_path):
     ("realnvp", "resnet", 17, 34, 1, 3),
     ("realnvp", "resnet", 24, 30, 2, 3),
     ("realnvp", "resnet", 19, 38, 3, 3),
-])
-def test_hidden_width_below_64_runs_on_the_tensor_core_kernels(ftype, net, D, H, n_layers, launches, tmp_path):
+    # tanh / SiLU conditioners (flows/utils.py:200-205): the activation is a compile-time parameter of the
+    # MLP and ResidualNet kernels (two SFU operations per value in front of the fp16 split)
+    ("realnvp", "mlp", 16, 64, 2, 1, "tanh"),
+    ("realnvp", "mlp", 9, 18, 2, 1, "swish"),
+    ("realnvp", "resnet", 16, 64, 2, 2, "swish"),
+    ("realnvp", "resnet", 12, 24, 2, 1, "tanh"),
+]])
+def test_hidden_width_below_64_runs_on_the_tensor_core_kernels(ftype, net, D, H, n_layers, launches, act, tmp_path):
     """The reference's DEFAULT conditioner width is 2 * n_inputs
     (/root/reference/src/nessai/flows/utils.py:105-165, flowmodel/utils.py:39-42), not the 64 of
     BASELINE's C2: the tcgen05 kernels take every width <= 64 (hidden units zero-padded to 64 in the
@@ -223,6 +229,7 @@ def test_hidden_width_below_64_runs_on_the_tensor_core_kernels(ftype, net, D, H,
     cfg = dict(n_inputs=D, n_neurons=H, n_blocks=3, n_layers=n_layers, ftype=ftype)
     if ftype == "realnvp":
         cfg["net"] = net
+        cfg["activation"] = act
     torch.manual_seed(100 * D + H)
     fm = B200FlowModel(flow_config=cfg, training_config=dict(device_tag="cuda:0"), output=str(tmp_path))
     fm.initialise()
