@@ -1,4 +1,5 @@
-"""The reference's DEFAULT flow (ResidualNet conditioner, width 2 * n_inputs, flowmodel/utils.py:39-42) on the
+"""usage: default_width.py [n_inputs ...]   (default: the whole table)
+The reference's DEFAULT flow (ResidualNet conditioner, width 2 * n_inputs, flowmodel/utils.py:39-42) on the
 tcgen05 kernels (hidden units zero-padded to 64) against the generic fp32 kernel: inverse + log-prob of 1e6 rows."""
 import os, sys, tempfile
 import numpy as np, torch
@@ -7,8 +8,11 @@ from nessai_b200 import _lib
 from nessai_b200.flowmodel import B200FlowModel
 lib = _lib.load()
 n = 1_000_000
+only = [int(a) for a in sys.argv[1:]]
 for D, net in ((16, "resnet"), (8, "resnet"), (4, "resnet"), (2, "resnet"), (16, "mlp"), (16, "nsf"), (8, "nsf"),
                (20, "resnet"), (24, "resnet"), (32, "resnet")):
+    if only and D not in only:
+        continue
     cfg = dict(n_inputs=D, n_blocks=4, n_layers=2, ftype="realnvp", net=net)  # n_neurons: the default
     if net == "nsf":
         cfg = dict(n_inputs=D, n_blocks=4, n_layers=2, ftype="nsf")
