@@ -85,14 +85,27 @@ static void free_dir(DirProgram& p) {
   p = DirProgram();
 }
 
+// Compute capability and SM count of a device.  (cudaGetDeviceProperties fills ~100 fields, some of
+// them through slow driver queries: tens of milliseconds per call -- paid by every flow and trainer
+// created; the three attributes below are microseconds.)
+struct DeviceInfo {
+  int major = 0, minor = 0, sms = 0;
+};
+static int device_info(int dev, DeviceInfo& d) {
+  CUDA_OK(cudaDeviceGetAttribute(&d.major, cudaDevAttrComputeCapabilityMajor, dev));
+  CUDA_OK(cudaDeviceGetAttribute(&d.minor, cudaDevAttrComputeCapabilityMinor, dev));
+  CUDA_OK(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+  return 0;
+}
+
 extern "C" int nb200_flow_create(nb200_flow** out, int D, int H, int activation) {
   if (!out) return fail(1, "nb200_flow_create: out is NULL");
   if (D < 1 || D > 1024 || H < 1 || H > 4096) return fail(1, "nb200_flow_create: bad sizes D=%d H=%d", D, H);
   if (activation < 0 || activation > 2) return fail(1, "nb200_flow_create: bad activation %d", activation);
   int dev = 0;
   CUDA_OK(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  DeviceInfo prop;
+  if (int rc = device_info(dev, prop)) return rc;
   if (prop.major != 10)
     return fail(3, "nessai_b200 kernels are built for sm_100a only; device %d is sm_%d%d", dev,
                 prop.major, prop.minor);
@@ -102,7 +115,7 @@ extern "C" int nb200_flow_create(nb200_flow** out, int D, int H, int activation)
   f->H = H;
   f->activation = activation;
   f->device = dev;
-  f->num_sms = prop.multiProcessorCount;
+  f->num_sms = prop.sms;
   *out = f;
   return 0;
 }
@@ -736,8 +749,8 @@ extern "C" int nb200_trainer_create(nb200_trainer** out, const int32_t* h_plan, 
     return fail(1, "nb200_trainer_create: plan has %d ints, expected %d", n_plan_ints, TR_PLAN_INTS);
   int dev = 0;
   CUDA_OK(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  DeviceInfo prop;
+  if (int rc = device_info(dev, prop)) return rc;
   if (prop.major != 10)
     return fail(3, "nessai_b200 kernels are built for sm_100a only; device %d is sm_%d%d", dev,
                 prop.major, prop.minor);
@@ -757,7 +770,7 @@ extern "C" int nb200_trainer_create(nb200_trainer** out, const int32_t* h_plan, 
       return fail(1, "nb200_trainer_create: layer %d has %d linears / %d buffers", l, ly.n_lin, ly.n_buf);
     }
   }
-  t->num_sms = prop.multiProcessorCount;
+  t->num_sms = prop.sms;
   t->smem_fwd = 4 * tr_smem_floats(P.D, P.vals_floats, P.max_in, P.wmax, P.n_itab, false);
   t->smem_bwd = 4 * tr_smem_floats(P.D, P.vals_floats, P.max_in, P.wmax, P.n_itab, true);
   if (t->smem_bwd > 226 * 1024) {
@@ -780,7 +793,7 @@ extern "C" int nb200_trainer_create(nb200_trainer** out, const int32_t* h_plan, 
   TR_ALLOC(t->grad, n_grad);
   TR_ALLOC(t->gn_part, G);
   CUDA_OK(cudaMemset(t->part, 0, sizeof(float) * G * part_stride));
-  TR_ALLOC(t->eval_part, 2 * 2 * prop.multiProcessorCount);
+  TR_ALLOC(t->eval_part, 2 * 2 * prop.sms);
   TR_ALLOC(t->stat_n, G);
   TR_ALLOC(t->run_scalars, 4);
   TR_ALLOC(t->bar, 4);
