@@ -25,6 +25,7 @@ from typing import NamedTuple
 import numpy as np
 from nessai import config as nessai_config
 from nessai.livepoint import empty_structured_array as nessai_empty_structured_array
+from nessai.model import Model as _ReferenceModel
 from nessai.proposal.augmented import AugmentedFlowProposal
 from nessai.proposal.flowproposal import FlowProposal
 from nessai.reparameterisations import (
@@ -247,8 +248,6 @@ class B200NessaiFlowProposal(FlowProposal):
     def _parameter_maps(self):
         """(kind, scale, shift) in prime-parameter order if the rescaling is made of
         per-parameter maps the device evaluates, else None."""
-        if self.map_to_unit_hypercube:
-            return None
         return parameter_maps(self._reparameterisation, self.prime_parameters, self.model.names, self.parameters)
 
     def _fused_rules(self):
@@ -274,6 +273,12 @@ class B200NessaiFlowProposal(FlowProposal):
         eligible = maps is not None and rules is not None
         if eligible and not maps.affine and len(maps.kind) > GeneralPopulateEngine.MAX_D:
             eligible = False
+        # map_to_unit_hypercube (flowproposal/base.py:744-745,781-782, flowproposal.py:441-446): the loop
+        # works on unit-hypercube values -- bounds [0, 1), the model's unit-hypercube prior -- and
+        # convert_to_samples maps the pool to the physical space afterwards (base.py:1122-1123)
+        hyper = bool(self.map_to_unit_hypercube)
+        if eligible and hyper and "likelihood_threshold" in rules:
+            eligible = False  # (a device likelihood takes physical parameters)
         if eligible:
             affine = maps.affine
             # auxiliary x-space parameters (the radius of a lone Angle): fields of the population
@@ -288,11 +293,14 @@ class B200NessaiFlowProposal(FlowProposal):
                     self.flow, maps.names, self.population_dtype,
                     row_template=nessai_empty_structured_array(1, dtype=self.population_dtype),
                 )
-                self._log_prior_const = (
-                    detect_uniform_box_prior(self.model, self.rng)
-                    if self.device_prior in ("auto", True, "uniform")
-                    else None
-                )
+                if self.device_prior not in ("auto", True, "uniform"):
+                    self._log_prior_const = None
+                elif hyper:
+                    # the stock Model.log_prior_unit_hypercube is log(1) inside the cube (model.py:593-601)
+                    stock = type(self.model).log_prior_unit_hypercube is _ReferenceModel.log_prior_unit_hypercube
+                    self._log_prior_const = 0.0 if stock else None
+                else:
+                    self._log_prior_const = detect_uniform_box_prior(self.model, self.rng)
             self._engine.n_model = len(self.model.names)
             if (self.accumulate_weights or aux) and self._log_prior_const is None:
                 # the accumulating loop keeps everything on the device; the prior of an auxiliary
@@ -306,8 +314,10 @@ class B200NessaiFlowProposal(FlowProposal):
             logger.debug("Existing pool of samples is not empty. Discarding existing samples.")
         self.indices = []
         unbounded = (-np.inf, np.inf)
-        lo = [self.model.bounds.get(n, unbounded)[0] for n in maps.names]
-        hi = [self.model.bounds.get(n, unbounded)[1] for n in maps.names]
+        bounds = ({n: (0.0, float(np.nextafter(1.0, 0.0))) for n in self.model.names} if hyper  # (x >= 1 is outside)
+                  else self.model.bounds)
+        lo = [bounds.get(n, unbounded)[0] for n in maps.names]
+        hi = [bounds.get(n, unbounded)[1] for n in maps.names]
         t = self.latent_temperature
         in_loop = "likelihood_threshold" in rules
         extra = {} if affine else dict(pre_scale=maps.pre_scale, pre_shift=maps.pre_shift, src=maps.src)
@@ -321,7 +331,8 @@ class B200NessaiFlowProposal(FlowProposal):
             log_l_threshold=rules["likelihood_threshold"].threshold if in_loop else None,
             **extra,
         )
-        host_prior = None if self._log_prior_const is not None else self.log_prior
+        host_prior = None if self._log_prior_const is not None else (
+            self.unit_hypercube_log_prior if hyper else self.log_prior)
         evals0 = getattr(self._engine, "likelihood_evaluations", 0)
         if self.accumulate_weights:
             rows, n_proposed, n_accepted = self._engine.run_accumulate(
@@ -333,7 +344,7 @@ class B200NessaiFlowProposal(FlowProposal):
             )
         self.x = rows
         # (with auxiliary parameters the reference's own repacking drops them and sets logP)
-        self.samples = self.convert_to_samples(self.x, plot=plot) if (host_prior is not None or aux) else rows
+        self.samples = self.convert_to_samples(self.x, plot=plot) if (host_prior is not None or aux or hyper) else rows
         if self._plot_pool and plot:
             self.plot_pool(self.samples)
         self.population_time += datetime.datetime.now() - st
@@ -342,7 +353,7 @@ class B200NessaiFlowProposal(FlowProposal):
         else:
             logger.debug("Evaluating log-likelihoods")
             fn = getattr(self.model, "log_likelihood_torch", None)
-            device_ok = fn is not None and host_prior is None and not aux and len(rows)
+            device_ok = fn is not None and host_prior is None and not aux and not hyper and len(rows)
             if device_ok and self._engine.world == 1:
                 # the accepted records are still on the device: 8 bytes per row come back
                 self.samples["logL"] = self._engine.device_log_likelihood(len(rows), fn).cpu().numpy()

@@ -430,7 +430,8 @@ def test_reference_self_consistency_pins(name, tmp_path):
 
 
 @pytest.mark.reference
-@pytest.mark.parametrize("variant", ["logit_and_default", "accumulate", "periodic_angle", "to_cartesian"])
+@pytest.mark.parametrize("variant", ["logit_and_default", "accumulate", "periodic_angle", "to_cartesian",
+                                     "unit_hypercube"])
 def test_flowsampler_variants_run_on_the_device_loop(tmp_path, variant):
     """The reference's FlowSampler, unmodified, with a logit + rescale-to-bounds
     reparameterisation (GeneralPopulateEngine), with accumulate_weights=True (run_accumulate)
@@ -446,9 +447,26 @@ def test_flowsampler_variants_run_on_the_device_loop(tmp_path, variant):
     kw = dict(logit_and_default=dict(reparameterisations={"x": "logit", "y": "default"}),
               accumulate=dict(accumulate_weights=True),
               periodic_angle=dict(reparameterisations={"x": "periodic", "y": "default"}),
-              to_cartesian=dict(reparameterisations={"x": "to-cartesian", "y": "default"}))[variant]
+              to_cartesian=dict(reparameterisations={"x": "to-cartesian", "y": "default"}),
+              unit_hypercube=dict(map_to_unit_hypercube=True))[variant]
+    model = make_model()
+    if variant == "unit_hypercube":  # the two maps the reference asks the user for (model.py:603-614)
+        class WithHypercube(type(model)):
+            def to_unit_hypercube(self, x):
+                u = x.copy()
+                for n in self.names:
+                    u[n] = (x[n] - self.bounds[n][0]) / (self.bounds[n][1] - self.bounds[n][0])
+                return u
+
+            def from_unit_hypercube(self, u):
+                x = u.copy()
+                for n in self.names:
+                    x[n] = u[n] * (self.bounds[n][1] - self.bounds[n][0]) + self.bounds[n][0]
+                return x
+
+        model = WithHypercube()
     fs = FlowSampler(
-        make_model(), output=str(tmp_path), resume=False, seed=1234, nlive=200, plot=False,
+        model, output=str(tmp_path), resume=False, seed=1234, nlive=200, plot=False,
         flow_proposal_class=B200NessaiFlowProposal, flow_config=dict(n_blocks=2),
         training_config=dict(max_epochs=50, patience=10), maximum_uninformed=200,
         max_iteration=700, poolsize=2000, checkpointing=False, **kw,
@@ -462,6 +480,10 @@ def test_flowsampler_variants_run_on_the_device_loop(tmp_path, variant):
         assert type(prop._engine) is GeneralPopulateEngine and prop._engine.names == ["x", "y", "x_radial"]
         assert prop.flow.model.spec.D == 3 and prop.samples.dtype.names[:2] == ("x", "y")
         assert "x_radial" in prop.x.dtype.names and "x_radial" not in prop.samples.dtype.names
+    elif variant == "unit_hypercube":
+        assert type(prop._engine) is PopulateEngine and prop.map_to_unit_hypercube
+        u = np.stack([prop.x[n] for n in ("x", "y")], axis=-1)
+        assert np.all((u >= 0) & (u < 1)) and np.all(np.abs(prop.samples["x"]) <= 10)
     else:
         assert type(prop._engine) is PopulateEngine and getattr(prop._engine, "last_accumulate", None)
     # truncated at max_iteration (the reference's own CPU proposal gives -7.3 here; analytic -5.99)

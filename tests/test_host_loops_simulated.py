@@ -178,7 +178,9 @@ def test_general_engine_accumulate(monkeypatch):
                                      "accumulate_min_log_q", "likelihood_threshold", "logit_likelihood_threshold",
                                      "zscore_gaussian_cdf", "angle_aux", "angle_and_radial_parameter",
                                      "accumulate_logit", "accumulate_likelihood_threshold",
-                                     "angle_aux_likelihood_threshold", "accumulate_angle_likelihood_threshold"])
+                                     "angle_aux_likelihood_threshold", "accumulate_angle_likelihood_threshold",
+                                     "to_cartesian", "angle_pair_aux", "dequantise", "unit_hypercube",
+                                     "unit_hypercube_logit"])
 def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     """``B200NessaiFlowProposal.populate`` end to end with the reference's own proposal object
     (reparameterisations, truncation scheme, live-point dtype): engine selection, configuration
@@ -203,7 +205,27 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
             self.bounds = {n: [-5.0, 5.0] for n in names}
             if "angle" in variant:  # x0: an angle in [0, 2 pi]; x1: a radius-like parameter
                 self.bounds["x0"] = [0.0, 2 * np.pi]
-                self.bounds["x1"] = [0.0, 5.0]
+                self.bounds["x1"] = [0.0, np.pi] if variant == "angle_pair_aux" else [0.0, 5.0]  # (a zenith angle)
+            if variant == "dequantise":  # x0: a discrete parameter 0 .. 4
+                self.bounds["x0"] = [0.0, 4.0]
+
+        def new_point(self, N=1):
+            x = super().new_point(N)
+            if variant == "dequantise":
+                x["x0"] = np.floor(x["x0"])
+            return x
+
+        def to_unit_hypercube(self, x):  # map_to_unit_hypercube (model.py:603-614: the user supplies both maps)
+            u = x.copy()
+            for n in self.names:
+                u[n] = (x[n] - self.bounds[n][0]) / (self.bounds[n][1] - self.bounds[n][0])
+            return u
+
+        def from_unit_hypercube(self, u):
+            x = u.copy()
+            for n in self.names:
+                x[n] = u[n] * (self.bounds[n][1] - self.bounds[n][0]) + self.bounds[n][0]
+            return x
 
         def log_prior(self, x):
             return np.log(self.in_bounds(x), dtype="float") + LOG_P
@@ -243,6 +265,13 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
         angle_aux=dict(reparameterisations={"x0": "angle", "x1": "default", "x2": "z-score", "x3": "logit"}),
         angle_and_radial_parameter=dict(reparameterisations={"angle": {"parameters": ["x0", "x1"]},
                                                              "x2": "default", "x3": "default"}),
+        unit_hypercube=dict(map_to_unit_hypercube=True),
+        unit_hypercube_logit=dict(map_to_unit_hypercube=True,
+                                  reparameterisations={"x0": "logit", "x1": "default", "x2": "z-score", "x3": "logit"}),
+        to_cartesian=dict(reparameterisations={"x0": "to-cartesian", "x1": "default", "x2": "z-score", "x3": "logit"}),
+        angle_pair_aux=dict(reparameterisations={"angle-pair": {"parameters": ["x0", "x1"]}, "x2": "default",
+                                                 "x3": "logit"}),
+        dequantise=dict(reparameterisations={"x0": "dequantise", "x1": "default", "x2": "z-score", "x3": "logit"}),
         likelihood_threshold=dict(truncation_methods=["latent_radius", "likelihood_threshold"]),
         logit_likelihood_threshold=dict(truncation_methods=["latent_radius", "likelihood_threshold"],
                                         reparameterisations={"x0": "logit", "x1": "logit", "x2": "default",
@@ -250,6 +279,10 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     )[variant]
     contour = variant.endswith("likelihood_threshold")
     LOG_P = -D * np.log(10.0) if "angle" not in variant else -np.log(2 * np.pi * 5.0 * 100.0)
+    if variant == "angle_pair_aux":
+        LOG_P = -np.log(2 * np.pi * np.pi * 100.0)
+    if variant == "dequantise":
+        LOG_P = -np.log(4.0 * 1000.0)
     model = Box()
     rng = np.random.default_rng(9)
     model.set_rng(rng)
@@ -262,7 +295,9 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     pts = np.clip(1.2 * rng.standard_normal((600, D)) + 0.5, -4.9, 4.9)
     if "angle" in variant:
         pts[:, 0] = (1.0 + 0.8 * rng.standard_normal(600)) % (2 * np.pi)
-        pts[:, 1] = np.clip(np.abs(1.0 + 0.7 * rng.standard_normal(600)), 0.05, 4.9)
+        pts[:, 1] = np.clip(np.abs(1.0 + 0.7 * rng.standard_normal(600)), 0.05, 3.0 if variant == "angle_pair_aux" else 4.9)
+    if variant == "dequantise":
+        pts[:, 0] = rng.integers(0, 5, 600)
     live = numpy_array_to_live_points(pts, names)
     live["logL"] = model.log_likelihood(live)
     prop.train(live, plot=False)
@@ -286,7 +321,17 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     assert prop._engine is not None and len(sim.calls) > 0  # not the host loop
     general = variant in ("logit_mixed", "inversion_edges", "logit_likelihood_threshold", "zscore_gaussian_cdf",
                           "angle_aux", "angle_and_radial_parameter", "accumulate_logit",
-                          "angle_aux_likelihood_threshold", "accumulate_angle_likelihood_threshold")
+                          "angle_aux_likelihood_threshold", "accumulate_angle_likelihood_threshold",
+                          "to_cartesian", "angle_pair_aux", "dequantise", "unit_hypercube_logit")
+    if variant.startswith("unit_hypercube"):  # the loop ran on unit-hypercube values, the sampler gets physical ones
+        u = np.stack([prop.x[n] for n in names], axis=-1)
+        assert np.all((u >= 0.0) & (u < 1.0)) and prop.x.size == prop.samples.size
+        np.testing.assert_allclose(np.stack([prop.samples[n] for n in names], axis=-1), 10.0 * u - 5.0, rtol=0, atol=1e-12)
+    if variant in ("to_cartesian", "angle_pair_aux"):
+        aux = "x0_radial" if variant == "to_cartesian" else "x0_x1_radial"
+        assert prop._engine.names == names + [aux] and aux in prop.x.dtype.names and aux not in prop.samples.dtype.names
+    if variant == "dequantise":
+        assert set(np.unique(prop.samples["x0"])) <= {0.0, 1.0, 2.0, 3.0, 4.0}
     if "angle_aux" in variant or variant == "accumulate_angle_likelihood_threshold":  # the auxiliary radius never reaches the sampler (flowproposal/base.py:1100-1128)
         assert prop._engine.names == names + ["x0_radial"] and prop.samples.dtype.names[:D] == tuple(names)
         assert "x0_radial" in prop.x.dtype.names and "x0_radial" not in prop.samples.dtype.names
