@@ -54,10 +54,15 @@ enum TailKind : int32_t {
   TAIL_DECLINATION = 14,  // ra-dec: atan2(u2, sqrt(u0^2 + u1^2)), log|J| -= log cos(.)   (:454-489)
   TAIL_RADIUS3 = 15,      // sqrt(u0^2 + u1^2 + u2^2), log|J| -= 2 log r
   TAIL_RADIUS3_CHI = 16,  // the same for an AUXILIARY radius with its chi(3) prior (:529-537)
-  TAIL_N_KINDS = 17
+  // a single-feature kind: an augment parameter of AugmentedFlowProposal (proposal/augmented.py:150-178),
+  // passed through unchanged, whose standard-normal prior is added to the log prior
+  TAIL_GAUSS_AUX = 17,
+  TAIL_N_KINDS = 18
 };
 // kinds that read two or three flow features
-NB200_HD bool tail_is_multi(int32_t kind) { return kind >= TAIL_PAIR_FIRST && kind != TAIL_FLOOR; }
+NB200_HD bool tail_is_multi(int32_t kind) {
+  return kind >= TAIL_PAIR_FIRST && kind != TAIL_FLOOR && kind != TAIL_GAUSS_AUX;
+}
 
 #ifdef __CUDACC__
 #define NB200_ERFCINV erfcinv
@@ -70,7 +75,7 @@ extern "C" double nb200_host_erfcinv(double);
 // One feature: u = a v + b, returns h(u) * scale + shift and adds the log-Jacobian of h (NOT of
 // the two affine parts, which are row constants) to logj.
 NB200_HD double tail_feature(int32_t kind, double a, double b, double scale, double shift, double v,
-                             double& logj) {
+                             double& logj, double& logp_extra) {
   const double u = a * v + b;
   double h = u;
   if (kind == TAIL_SIGMOID) {
@@ -92,6 +97,8 @@ NB200_HD double tail_feature(int32_t kind, double a, double b, double scale, dou
     logj += 0.9189385332046727 + 0.5 * h * h;
   } else if (kind == TAIL_FLOOR) {
     h = floor(u);
+  } else if (kind == TAIL_GAUSS_AUX) {
+    logp_extra += -0.5 * u * u - 0.9189385332046727;
   }
   return h * scale + shift;
 }
@@ -150,7 +157,7 @@ NB200_HD bool tail_row(int D, const float* xp, const int32_t* kind, const int32_
                      (double)xp[src ? src[3 * d + 1] : d], (double)xp[src ? src[3 * d + 2] : d], logj, logp_extra);
     } else {
       xv = tail_feature(kind[d], pre_a ? pre_a[d] : 1.0, pre_b ? pre_b[d] : 0.0, scale[d], shift[d],
-                        (double)xp[i0], logj);
+                        (double)xp[i0], logj, logp_extra);
     }
     x[d] = xv;
     inb = inb && !(xv < lo[d]) && !(xv > hi[d]);

@@ -48,7 +48,7 @@ logger = logging.getLogger(__name__)
 # per-parameter map kinds of the device tail (csrc/reparam_tail.cuh: TailKind)
 (KIND_IDENTITY, KIND_SIGMOID, KIND_ABS, KIND_EXP, KIND_LOG, KIND_NORMAL_CDF,
  KIND_NORMAL_QUANTILE, KIND_ANGLE, KIND_ANGLE_MOD, KIND_RADIUS, KIND_RADIUS_CHI, KIND_FLOOR,
- KIND_ANGLE_ABS, KIND_ZENITH, KIND_DECLINATION, KIND_RADIUS3, KIND_RADIUS3_CHI) = range(17)
+ KIND_ANGLE_ABS, KIND_ZENITH, KIND_DECLINATION, KIND_RADIUS3, KIND_RADIUS3_CHI, KIND_GAUSS_AUX) = range(18)
 
 # the INVERSE function of a named rescaling (utils/rescaling.py:410-417) -> the kind of h
 _INVERSE_KINDS = (
@@ -390,19 +390,42 @@ _check_dtype_surface()
 
 
 # ------------------------------------------------------------------ augmented flows
-class B200AugmentedFlowProposal(AugmentedFlowProposal):
-    """``AugmentedFlowProposal`` (/root/reference/src/nessai/proposal/augmented.py:21-260) with
-    plugin point P2 swapped: the flow over the ``dims + augment_dims`` inputs (custom mask,
-    augmented.py:91-96) is trained and evaluated by the CUDA kernels, including the ``n_marg``
-    forward passes per proposed row of ``_marginalise_augment`` (:180-200), which reach
-    ``forward_and_log_prob`` as ONE batch of ``n * n_marg`` rows.  The populate loop itself is
-    the reference's host loop (the auxiliary parameters are not model parameters, so the fused
-    loop does not apply).
+class B200AugmentedFlowProposal(B200NessaiFlowProposal, AugmentedFlowProposal):
+    """``AugmentedFlowProposal`` (/root/reference/src/nessai/proposal/augmented.py:21-260) on the
+    B200: the flow over the ``dims + augment_dims`` inputs (custom mask, augmented.py:91-96) is
+    trained and evaluated by the CUDA kernels, and the populate loop runs on the device as for
+    ``B200NessaiFlowProposal`` -- the augment parameters ``e_i`` are extra x-space parameters passed
+    through unchanged whose N(0, 1) prior (augmented.py:162-178) the tail kernel adds to the log
+    prior (kind 17); like the auxiliary radius of ``Angle`` they are fields of the population
+    records that ``convert_to_samples`` drops.  With ``marginalise_augment=True`` the proposal
+    density of every row is a Monte-Carlo marginal over ``n_marg`` forward passes (:180-200): that
+    loop stays the reference's, its passes reach ``forward_and_log_prob`` as ONE batch of
+    ``n * n_marg`` rows.
 
     A module-level class: the sampler's checkpoint pickles the proposal
     (samplers/base.py:346, utils/io.py:112), which needs a stable ``__module__.__qualname__``."""
 
     _FlowModelClass = B200FlowModel
+
+    def _parameter_maps(self):
+        if self.marginalise_augment or self.map_to_unit_hypercube:
+            # (log q is the marginal estimate of augmented.py:180-200: the reference's loop; the reference
+            # itself refuses the unit hypercube with augment parameters, :150-154)
+            return None
+        aug = list(self.augment_parameters)
+        n = len(aug)
+        if n == 0 or self.prime_parameters[-n:] != aug or self.parameters[-n:] != aug:
+            return None
+        base = parameter_maps(self._reparameterisation, self.prime_parameters[:-n], self.model.names,
+                              self.parameters[:-n])
+        if base is None:
+            return None
+        d0 = len(base.kind)
+        src = np.concatenate([base.src, np.repeat(np.arange(d0, d0 + n, dtype=np.int32)[:, None], 3, axis=1)])
+        cat = lambda a, v, dt: np.concatenate([a, np.full(n, v, dtype=dt)])  # noqa: E731
+        return ParameterMaps(cat(base.kind, KIND_GAUSS_AUX, np.int32), cat(base.scale, 1.0, np.float64),
+                             cat(base.shift, 0.0, np.float64), cat(base.pre_scale, 1.0, np.float64),
+                             cat(base.pre_shift, 0.0, np.float64), src, list(base.names) + aug)
 
     def resume(self, model, flow_config, weights_file=None):
         """The pickled state keeps the custom mask as the ndarray ``__init__`` built

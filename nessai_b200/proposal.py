@@ -934,7 +934,7 @@ class GeneralPopulateEngine(PopulateEngine):
     The loop, its pipelining and the multi-GPU exchange are the base class's."""
 
     MAX_D = 64  # TAIL_MAXD
-    N_KINDS = 17  # TAIL_N_KINDS
+    N_KINDS = 18  # TAIL_N_KINDS
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
@@ -952,7 +952,8 @@ class GeneralPopulateEngine(PopulateEngine):
         (default ``d``); the pair kinds of ``Angle`` read two (7 angle, 8 angle mod 2 pi, 9 radius,
         10 auxiliary radius with its chi(2) prior; 12 ``ToCartesian``), the kinds of ``AnglePair``
         three (13 zenith, 14 declination, 15 radius, 16 auxiliary radius with its chi(3) prior);
-        11 is ``floor`` (``Dequantise``).  See include/nessai_b200.h: nb200_reparam_tail."""
+        11 is ``floor`` (``Dequantise``), 17 an augment parameter of ``AugmentedFlowProposal`` (identity,
+        N(0, 1) prior).  See include/nessai_b200.h: nb200_reparam_tail."""
         D = self.D
         src = np.stack([np.arange(D)] * 3, axis=1) if src is None else np.asarray(src)
         if src.ndim != 2:

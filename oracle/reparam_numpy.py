@@ -45,12 +45,13 @@ ANGLE, ANGLE_MOD, RADIUS, RADIUS_CHI = 7, 8, 9, 10
 FLOOR = 11  # single feature (Dequantise)
 ANGLE_ABS = 12  # pair (ToCartesian)
 ZENITH, DECLINATION, RADIUS3, RADIUS3_CHI = 13, 14, 15, 16  # triples (AnglePair)
+GAUSS_AUX = 17  # single feature: an augment parameter with its N(0, 1) prior (proposal/augmented.py:162-178)
 
 
 def is_multi(kind):
     """Kinds that read two or three flow features."""
     kind = np.asarray(kind)
-    return (kind >= ANGLE) & (kind != FLOOR)
+    return (kind >= ANGLE) & (kind != FLOOR) & (kind != GAUSS_AUX)
 
 
 
@@ -134,6 +135,9 @@ def inverse_maps(xp, kind, scale, shift, pre_scale=None, pre_shift=None, src=Non
                 log_j = log_j + 0.5 * np.log(2 * np.pi) + 0.5 * h**2
             elif kind[d] == FLOOR:  # reparameterisations/discrete.py:77-78
                 h = np.floor(u)
+            elif kind[d] == GAUSS_AUX:  # proposal/augmented.py:150-178
+                h = u
+                log_p = log_p - 0.5 * u**2 - 0.5 * np.log(2 * np.pi)
             elif kind[d] == IDENTITY:
                 h = u
             else:

@@ -516,6 +516,15 @@ def test_augmented_flow_proposal_on_b200_flows(tmp_path, marginalise):
     assert prop.flow.model.spec.D == 3 and list(prop.flow_config["mask"]) == [1.0, 1.0, -1.0]
     assert prop.training_count >= 1 and prop.populated_count >= 1
     assert np.isfinite(fs.ns.log_evidence)
+    if not marginalise:
+        # the populate loop ran on the device: the augment parameter is a field of the population records
+        # (kind 17 of the tail: identity + its N(0, 1) prior) that never reaches the sampler
+        from nessai_b200.proposal import GeneralPopulateEngine
+
+        assert type(prop._engine) is GeneralPopulateEngine and prop._engine.names == ["x", "y", "e_0"]
+        assert "e_0" in prop.x.dtype.names and "e_0" not in prop.samples.dtype.names
+    else:
+        assert prop._engine is None  # the marginal estimate of log q: the reference's loop over our flow kernels
     # the marginalised density of a point agrees with a brute-force estimate from the same flow
     if marginalise:
         x = np.array([[0.3, -0.2, 0.0]] * 4)

@@ -180,7 +180,7 @@ def test_general_engine_accumulate(monkeypatch):
                                      "accumulate_logit", "accumulate_likelihood_threshold",
                                      "angle_aux_likelihood_threshold", "accumulate_angle_likelihood_threshold",
                                      "to_cartesian", "angle_pair_aux", "dequantise", "unit_hypercube",
-                                     "unit_hypercube_logit"])
+                                     "unit_hypercube_logit", "augmented", "augmented_logit"])
 def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     """``B200NessaiFlowProposal.populate`` end to end with the reference's own proposal object
     (reparameterisations, truncation scheme, live-point dtype): engine selection, configuration
@@ -192,7 +192,7 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     from nessai.livepoint import numpy_array_to_live_points
     from nessai.model import Model
 
-    from nessai_b200.nessai_plugin import B200NessaiFlowProposal
+    from nessai_b200.nessai_plugin import B200AugmentedFlowProposal, B200NessaiFlowProposal
     from nessai_b200.proposal import GeneralPopulateEngine, PopulateEngine
     from oracle.flow_numpy import NumpyFlow
 
@@ -242,7 +242,7 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
                 return torch.cos(x[:, 0] - 1.0) - 0.5 * ((x[:, 1:] - 1.0) ** 2).sum(dim=1)
             return -0.5 * (x * x).sum(dim=1)
 
-    class CpuFlowB200Proposal(B200NessaiFlowProposal):
+    class CpuFlowB200Proposal(B200AugmentedFlowProposal if variant.startswith("augmented") else B200NessaiFlowProposal):
         _FlowModelClass = FlowModel  # the reference's CPU flow; the simulated device evaluates its weights
 
     kw = dict(
@@ -265,6 +265,9 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
         angle_aux=dict(reparameterisations={"x0": "angle", "x1": "default", "x2": "z-score", "x3": "logit"}),
         angle_and_radial_parameter=dict(reparameterisations={"angle": {"parameters": ["x0", "x1"]},
                                                              "x2": "default", "x3": "default"}),
+        augmented=dict(augment_dims=2),  # proposal/augmented.py: two augment parameters e_0, e_1
+        augmented_logit=dict(augment_dims=1, reparameterisations={"x0": "logit", "x1": "default", "x2": "z-score",
+                                                                  "x3": "logit"}),
         unit_hypercube=dict(map_to_unit_hypercube=True),
         unit_hypercube_logit=dict(map_to_unit_hypercube=True,
                                   reparameterisations={"x0": "logit", "x1": "default", "x2": "z-score", "x3": "logit"}),
@@ -322,7 +325,12 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     general = variant in ("logit_mixed", "inversion_edges", "logit_likelihood_threshold", "zscore_gaussian_cdf",
                           "angle_aux", "angle_and_radial_parameter", "accumulate_logit",
                           "angle_aux_likelihood_threshold", "accumulate_angle_likelihood_threshold",
-                          "to_cartesian", "angle_pair_aux", "dequantise", "unit_hypercube_logit")
+                          "to_cartesian", "angle_pair_aux", "dequantise", "unit_hypercube_logit", "augmented",
+                          "augmented_logit")
+    if variant.startswith("augmented"):  # the augment parameters never reach the sampler (augmented.py, base.py:1100-1128)
+        aug = [f"e_{i}" for i in range(prop.augment_dims)]
+        assert prop._engine.names == names + aug and prop.samples.dtype.names[:D] == tuple(names)
+        assert all(a in prop.x.dtype.names and a not in prop.samples.dtype.names for a in aug)
     if variant.startswith("unit_hypercube"):  # the loop ran on unit-hypercube values, the sampler gets physical ones
         u = np.stack([prop.x[n] for n in names], axis=-1)
         assert np.all((u >= 0.0) & (u < 1.0)) and prop.x.size == prop.samples.size

@@ -175,27 +175,28 @@ PI = np.pi
 TAIL_CASE = dict(
     # slots 0 .. 11: the single-feature kinds; 12 .. 15: Angle (angle, aux radius, radius, angle mod 2 pi);
     # 16: floor (Dequantise); 17, 18: ToCartesian + its auxiliary radius; 19 .. 21: AnglePair az-zen with an
-    # auxiliary radius; 22 .. 24: AnglePair ra-dec with a radial parameter
-    kind=np.array([0, 1, 2, 3, 1, 2, 0, 4, 5, 6, 1, 3, 7, 10, 9, 8, 11, 12, 10, 8, 13, 16, 7, 14, 15], dtype=np.int32),
+    # auxiliary radius; 22 .. 24: AnglePair ra-dec with a radial parameter; 25: an augment parameter
+    kind=np.array([0, 1, 2, 3, 1, 2, 0, 4, 5, 6, 1, 3, 7, 10, 9, 8, 11, 12, 10, 8, 13, 16, 7, 14, 15, 17],
+                  dtype=np.int32),
     scale=np.array([1.5, 8.0, -3.0, 2.0, 0.5, 4.0, -0.7, 1.2, 6.0, 0.9, 1.0, 1.0, 0.5, 1.0, 1.0, 1.0,
-                    1.0, 2.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0]),
+                    1.0, 2.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0]),
     shift=np.array([0.2, -4.0, 5.0, -1.0, 0.0, -2.0, 0.3, 0.1, -3.0, 0.4, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0,
-                    0.0, -1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]),
+                    0.0, -1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]),
     lo=np.array([-3.0, -4.0, 2.0, -1.0, 0.0, -2.0, -2.0, -3.0, -3.0, -2.0, 0.0, 0.0, -1.5, -np.inf, 0.0, 0.0,
-                 -6.0, -1.0, -np.inf, 0.0, 0.0, -np.inf, -PI, -PI / 2, 0.0]),
+                 -6.0, -1.0, -np.inf, 0.0, 0.0, -np.inf, -PI, -PI / 2, 0.0, -np.inf]),
     hi=np.array([3.0, 4.0, 5.0, 9.0, 0.5, 1.5, 2.0, 2.0, 3.0, 2.5, 1.0, 9.0, 1.5, np.inf, 3.5, 2 * PI,
-                 9.0, 1.0, np.inf, 2 * PI, PI, np.inf, PI, PI / 2, 4.0]),
+                 9.0, 1.0, np.inf, 2 * PI, PI, np.inf, PI, PI / 2, 4.0, np.inf]),
     pre_scale=np.array([1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.3, 1.0, 0.2, 1.7, 0.6, 1.0, 1.0, 1.0, 1.0,
-                        3.0, 1.0 / PI, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0]),
+                        3.0, 1.0 / PI, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0]),
     pre_shift=np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.5, 0.0, 0.5, -0.3, 0.2, 0.0, 0.0, 0.0, 0.0,
-                        2.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]),
+                        2.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]),
     # slots 12 / 13 read the flow features (13, 12) as (x', y'), slots 14 / 15 the features (14, 15);
     # slots 2 and 5 are swapped to exercise the permutation of single-feature kinds; the triples read
     # (19, 20, 21) and, permuted, (24, 22, 23)
     src=np.array([[0, 0, 0], [1, 1, 1], [5, 5, 5], [3, 3, 3], [4, 4, 4], [2, 2, 2], [6, 6, 6], [7, 7, 7], [8, 8, 8],
                   [9, 9, 9], [10, 10, 10], [11, 11, 11], [13, 12, 13], [13, 12, 13], [14, 15, 14], [14, 15, 14],
                   [16, 16, 16], [17, 18, 17], [17, 18, 17], [19, 20, 21], [19, 20, 21], [19, 20, 21],
-                  [24, 22, 23], [24, 22, 23], [24, 22, 23]], dtype=np.int32),
+                  [24, 22, 23], [24, 22, 23], [24, 22, 23], [25, 25, 25]], dtype=np.int32),
 )
 
 
