@@ -302,10 +302,8 @@ class B200NessaiFlowProposal(FlowProposal):
                 else:
                     self._log_prior_const = detect_uniform_box_prior(self.model, self.rng)
             self._engine.n_model = len(self.model.names)
-            if (self.accumulate_weights or aux) and self._log_prior_const is None:
-                # the accumulating loop keeps everything on the device; the prior of an auxiliary
-                # parameter is added by the tail kernel, a host-side prior would count it twice
-                eligible = False
+            if self.accumulate_weights and self._log_prior_const is None:
+                eligible = False  # the accumulating loop keeps everything on the device
         if not eligible:
             logger.debug("B200: configuration not eligible for the fused loop; using the host loop")
             return super().populate(worst_point, n_samples=n_samples, plot=plot, r=r, max_samples=max_samples)
@@ -331,8 +329,17 @@ class B200NessaiFlowProposal(FlowProposal):
             log_l_threshold=rules["likelihood_threshold"].threshold if in_loop else None,
             **extra,
         )
-        host_prior = None if self._log_prior_const is not None else (
-            self.unit_hypercube_log_prior if hyper else self.log_prior)
+        # A prior that is not a constant is evaluated on the host each turn.  The priors of auxiliary
+        # parameters (the chi radius of Angle / AnglePair / ToCartesian, the augment parameters) are
+        # added by the tail kernel, so with those only the MODEL's prior is asked for here
+        # (flowproposal/base.py:1040-1067: log_prior = model prior + reparameterisation priors).
+        if self._log_prior_const is not None:
+            host_prior = None
+        elif aux:
+            host_prior = (self.model.batch_evaluate_log_prior_unit_hypercube if hyper
+                          else self.model.batch_evaluate_log_prior)
+        else:
+            host_prior = self.unit_hypercube_log_prior if hyper else self.log_prior
         evals0 = getattr(self._engine, "likelihood_evaluations", 0)
         if self.accumulate_weights:
             rows, n_proposed, n_accepted = self._engine.run_accumulate(

@@ -180,7 +180,8 @@ def test_general_engine_accumulate(monkeypatch):
                                      "accumulate_logit", "accumulate_likelihood_threshold",
                                      "angle_aux_likelihood_threshold", "accumulate_angle_likelihood_threshold",
                                      "to_cartesian", "angle_pair_aux", "dequantise", "unit_hypercube",
-                                     "unit_hypercube_logit", "augmented", "augmented_logit"])
+                                     "unit_hypercube_logit", "augmented", "augmented_logit",
+                                     "angle_aux_host_prior", "augmented_host_prior"])
 def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     """``B200NessaiFlowProposal.populate`` end to end with the reference's own proposal object
     (reparameterisations, truncation scheme, live-point dtype): engine selection, configuration
@@ -228,7 +229,10 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
             return x
 
         def log_prior(self, x):
-            return np.log(self.in_bounds(x), dtype="float") + LOG_P
+            lp = np.log(self.in_bounds(x), dtype="float") + LOG_P
+            if "host_prior" in variant:  # not a constant: evaluated on the host every turn
+                lp = lp - 0.08 * (x["x2"] - 1.0) ** 2
+            return lp
 
         def log_likelihood(self, x):
             a = self.unstructured_view(x)
@@ -265,6 +269,8 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
         angle_aux=dict(reparameterisations={"x0": "angle", "x1": "default", "x2": "z-score", "x3": "logit"}),
         angle_and_radial_parameter=dict(reparameterisations={"angle": {"parameters": ["x0", "x1"]},
                                                              "x2": "default", "x3": "default"}),
+        angle_aux_host_prior=dict(reparameterisations={"x0": "angle", "x1": "default", "x2": "z-score", "x3": "logit"}),
+        augmented_host_prior=dict(augment_dims=1),
         augmented=dict(augment_dims=2),  # proposal/augmented.py: two augment parameters e_0, e_1
         augmented_logit=dict(augment_dims=1, reparameterisations={"x0": "logit", "x1": "default", "x2": "z-score",
                                                                   "x3": "logit"}),
@@ -326,7 +332,7 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
                           "angle_aux", "angle_and_radial_parameter", "accumulate_logit",
                           "angle_aux_likelihood_threshold", "accumulate_angle_likelihood_threshold",
                           "to_cartesian", "angle_pair_aux", "dequantise", "unit_hypercube_logit", "augmented",
-                          "augmented_logit")
+                          "augmented_logit", "angle_aux_host_prior", "augmented_host_prior")
     if variant.startswith("augmented"):  # the augment parameters never reach the sampler (augmented.py, base.py:1100-1128)
         aug = [f"e_{i}" for i in range(prop.augment_dims)]
         assert prop._engine.names == names + aug and prop.samples.dtype.names[:D] == tuple(names)
@@ -357,7 +363,9 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
         assert len(got) == 400
     assert prop.samples.dtype == ref_dtype and prop.x.dtype == ref_x_dtype == prop.population_dtype
     assert np.all((got >= -5) & (got <= 2 * np.pi)) and np.all(np.isfinite(prop.samples["logL"]))
-    np.testing.assert_allclose(prop.samples["logP"], LOG_P)
+    np.testing.assert_allclose(prop.samples["logP"], model.log_prior(prop.samples) if "host_prior" in variant else LOG_P)
+    if "host_prior" in variant:
+        assert prop._log_prior_const is None  # the model's prior really was evaluated on the host
     np.testing.assert_allclose(prop.samples["logL"], model.log_likelihood(prop.samples))
     if variant == "zscore_gaussian_cdf":
         # The flow proposes x' outside (0, 1), where the quantile function is NaN.  The reference keeps
