@@ -158,6 +158,8 @@ int nb200_populate_accept_x64(int64_t n, int D, const double* d_x64, const doubl
  * log|J| -= log sin(.), 14 the declination atan2(u2, sqrt(u0^2 + u1^2)) with log|J| -= log cos(.),
  * 15 the radius sqrt(u0^2 + u1^2 + u2^2) with log|J| -= 2 log r, 16 the same for an auxiliary
  * radius whose chi(3) prior (:529-537) is added to log_w.
+ * A single-feature kind OR-ed with 0x100: floor(.) of the final value, x = floor(h(a x' + b) * scale
+ * + shift), no log|J| -- Dequantise with a post-rescaling ("dequantise-logit").
  * Kind 17 (single feature): an augment parameter of AugmentedFlowProposal (proposal/augmented.py:
  * 150-178), passed through unchanged, whose N(0, 1) log-density is added to log_w.
  * d_src int32[3*D] or NULL (slot d reads feature d): the flow features output slot d reads; the

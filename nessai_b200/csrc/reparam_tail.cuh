@@ -57,10 +57,15 @@ enum TailKind : int32_t {
   // a single-feature kind: an augment parameter of AugmentedFlowProposal (proposal/augmented.py:150-178),
   // passed through unchanged, whose standard-normal prior is added to the log prior
   TAIL_GAUSS_AUX = 17,
-  TAIL_N_KINDS = 18
+  TAIL_N_KINDS = 18,
+  // flag on a single-feature kind: floor(.) of the FINAL value, x = floor(h(a x' + b) * scale + shift) --
+  // "dequantise-logit": Dequantise with a post-rescaling (discrete.py + rescale.py:635-660); no log-Jacobian
+  TAIL_FLOOR_AFTER = 0x100,
+  TAIL_KIND_MASK = 0xff
 };
 // kinds that read two or three flow features
 NB200_HD bool tail_is_multi(int32_t kind) {
+  kind &= TAIL_KIND_MASK;
   return kind >= TAIL_PAIR_FIRST && kind != TAIL_FLOOR && kind != TAIL_GAUSS_AUX;
 }
 
@@ -76,6 +81,8 @@ extern "C" double nb200_host_erfcinv(double);
 // the two affine parts, which are row constants) to logj.
 NB200_HD double tail_feature(int32_t kind, double a, double b, double scale, double shift, double v,
                              double& logj, double& logp_extra) {
+  const bool floor_after = (kind & TAIL_FLOOR_AFTER) != 0;
+  kind &= TAIL_KIND_MASK;
   const double u = a * v + b;
   double h = u;
   if (kind == TAIL_SIGMOID) {
@@ -100,7 +107,8 @@ NB200_HD double tail_feature(int32_t kind, double a, double b, double scale, dou
   } else if (kind == TAIL_GAUSS_AUX) {
     logp_extra += -0.5 * u * u - 0.9189385332046727;
   }
-  return h * scale + shift;
+  const double r = h * scale + shift;
+  return floor_after ? floor(r) : r;
 }
 
 // A pair / triple kind: x from (u0, u1[, u2]); the constant factor of the angle has NO log-Jacobian
@@ -178,7 +186,7 @@ NB200_HD double tail_log_affine_sum(int D, const int32_t* kind, const double* pr
   double s = 0.0;
   for (int d = 0; d < D; ++d) {
     if (!tail_is_multi(kind[d])) s += log(fabs(scale[d])) + (pre_a ? log(fabs(pre_a[d])) : 0.0);
-    else if (kind[d] == TAIL_ANGLE_ABS) s += log(fabs(scale[d]));
+    else if ((kind[d] & TAIL_KIND_MASK) == TAIL_ANGLE_ABS) s += log(fabs(scale[d]));
   }
   return s;
 }

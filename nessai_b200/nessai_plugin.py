@@ -49,6 +49,7 @@ logger = logging.getLogger(__name__)
 (KIND_IDENTITY, KIND_SIGMOID, KIND_ABS, KIND_EXP, KIND_LOG, KIND_NORMAL_CDF,
  KIND_NORMAL_QUANTILE, KIND_ANGLE, KIND_ANGLE_MOD, KIND_RADIUS, KIND_RADIUS_CHI, KIND_FLOOR,
  KIND_ANGLE_ABS, KIND_ZENITH, KIND_DECLINATION, KIND_RADIUS3, KIND_RADIUS3_CHI, KIND_GAUSS_AUX) = range(18)
+KIND_FLOOR_AFTER = 0x100  # flag: floor of the final value (Dequantise with a post-rescaling)
 
 # the INVERSE function of a named rescaling (utils/rescaling.py:410-417) -> the kind of h
 _INVERSE_KINDS = (
@@ -169,6 +170,11 @@ def parameter_maps(rep, prime_parameters, model_names, x_parameters=None):
         else:
             pre = _kind_of(r.pre_rescaling_inv) if r.has_pre_rescaling else KIND_IDENTITY
         post = _kind_of(r.post_rescaling_inv) if r.has_post_rescaling else KIND_IDENTITY
+        floor_after = 0
+        if pre == KIND_FLOOR and post not in (None, KIND_IDENTITY):
+            # "dequantise-logit": x = floor(Q^-1(x') * scale + shift) -- floor has no log-Jacobian, so it is a
+            # flag on the post-rescaling's kind rather than a second stage
+            pre, floor_after = KIND_IDENTITY, KIND_FLOOR_AFTER
         if pre is None or post is None or (pre != KIND_IDENTITY and post != KIND_IDENTITY):
             return None
         for p, pp in zip(r.parameters, r.output_parameters):
@@ -196,7 +202,7 @@ def parameter_maps(rep, prime_parameters, model_names, x_parameters=None):
             if pre != KIND_IDENTITY:
                 specs[p] = (pre, 1.0, 0.0, s, t, (pp, pp, pp))  # the affine map first, then P^-1
             else:
-                specs[p] = (k, s, t, 1.0, 0.0, (pp, pp, pp))
+                specs[p] = (k | floor_after, s, t, 1.0, 0.0, (pp, pp, pp))
     if set(specs) != set(x_parameters) or len(x_parameters) != len(prime_parameters):
         return None
     if list(x_parameters[: len(model_names)]) != list(model_names):

@@ -971,7 +971,7 @@ class GeneralPopulateEngine(PopulateEngine):
             np.array(a, dtype=np.float64) for a in (scale, shift, lo, hi, pre_scale, pre_shift)]
         if any(a.shape != (D,) for a in new):
             raise ValueError("kind / scale / shift / lo / hi / pre_scale / pre_shift: one entry per parameter")
-        if np.any((new[0] < 0) | (new[0] >= self.N_KINDS)):
+        if np.any((new[0] < 0) | ((new[0] & 0xFF) >= self.N_KINDS) | ((new[0] & ~0x1FF) != 0)):
             raise ValueError("unknown per-parameter map kind")
         new.append(np.ascontiguousarray(src, dtype=np.int32))
         if new[-1].shape != (D, 3) or np.any((new[-1] < 0) | (new[-1] >= D)):

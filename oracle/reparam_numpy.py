@@ -46,11 +46,13 @@ FLOOR = 11  # single feature (Dequantise)
 ANGLE_ABS = 12  # pair (ToCartesian)
 ZENITH, DECLINATION, RADIUS3, RADIUS3_CHI = 13, 14, 15, 16  # triples (AnglePair)
 GAUSS_AUX = 17  # single feature: an augment parameter with its N(0, 1) prior (proposal/augmented.py:162-178)
+FLOOR_AFTER = 0x100  # flag on a single-feature kind: floor of the final value ("dequantise-logit")
+KIND_MASK = 0xFF
 
 
 def is_multi(kind):
     """Kinds that read two or three flow features."""
-    kind = np.asarray(kind)
+    kind = np.asarray(kind) & KIND_MASK
     return (kind >= ANGLE) & (kind != FLOOR) & (kind != GAUSS_AUX)
 
 
@@ -72,7 +74,8 @@ def inverse_maps(xp, kind, scale, shift, pre_scale=None, pre_shift=None, src=Non
     from scipy.special import erfc, erfcinv
 
     xp = np.asarray(xp, dtype=np.float64)
-    kind = np.asarray(kind)
+    floor_after = (np.asarray(kind) & FLOOR_AFTER) != 0
+    kind = np.asarray(kind) & KIND_MASK
     D = xp.shape[1]
     a = np.ones(D) if pre_scale is None else np.asarray(pre_scale, dtype=np.float64)
     b = np.zeros(D) if pre_shift is None else np.asarray(pre_shift, dtype=np.float64)
@@ -143,6 +146,8 @@ def inverse_maps(xp, kind, scale, shift, pre_scale=None, pre_shift=None, src=Non
             else:
                 raise ValueError(f"unknown kind {kind[d]}")
             x[:, d] = h * scale[d] + shift[d]
+            if floor_after[d]:  # Dequantise with a post-rescaling: floor last, no log-Jacobian
+                x[:, d] = np.floor(x[:, d])
     if return_log_prior:
         return x, log_j, log_p
     return x, log_j

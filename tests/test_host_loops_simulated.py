@@ -181,7 +181,7 @@ def test_general_engine_accumulate(monkeypatch):
                                      "angle_aux_likelihood_threshold", "accumulate_angle_likelihood_threshold",
                                      "to_cartesian", "angle_pair_aux", "dequantise", "unit_hypercube",
                                      "unit_hypercube_logit", "augmented", "augmented_logit",
-                                     "angle_aux_host_prior", "augmented_host_prior"])
+                                     "angle_aux_host_prior", "augmented_host_prior", "dequantise_logit"])
 def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     """``B200NessaiFlowProposal.populate`` end to end with the reference's own proposal object
     (reparameterisations, truncation scheme, live-point dtype): engine selection, configuration
@@ -207,12 +207,12 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
             if "angle" in variant:  # x0: an angle in [0, 2 pi]; x1: a radius-like parameter
                 self.bounds["x0"] = [0.0, 2 * np.pi]
                 self.bounds["x1"] = [0.0, np.pi] if variant == "angle_pair_aux" else [0.0, 5.0]  # (a zenith angle)
-            if variant == "dequantise":  # x0: a discrete parameter 0 .. 4
+            if variant.startswith("dequantise"):  # x0: a discrete parameter 0 .. 4
                 self.bounds["x0"] = [0.0, 4.0]
 
         def new_point(self, N=1):
             x = super().new_point(N)
-            if variant == "dequantise":
+            if variant.startswith("dequantise"):
                 x["x0"] = np.floor(x["x0"])
             return x
 
@@ -281,6 +281,8 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
         angle_pair_aux=dict(reparameterisations={"angle-pair": {"parameters": ["x0", "x1"]}, "x2": "default",
                                                  "x3": "logit"}),
         dequantise=dict(reparameterisations={"x0": "dequantise", "x1": "default", "x2": "z-score", "x3": "logit"}),
+        dequantise_logit=dict(reparameterisations={"x0": "dequantise-logit", "x1": "default", "x2": "z-score",
+                                                   "x3": "logit"}),
         likelihood_threshold=dict(truncation_methods=["latent_radius", "likelihood_threshold"]),
         logit_likelihood_threshold=dict(truncation_methods=["latent_radius", "likelihood_threshold"],
                                         reparameterisations={"x0": "logit", "x1": "logit", "x2": "default",
@@ -290,7 +292,7 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     LOG_P = -D * np.log(10.0) if "angle" not in variant else -np.log(2 * np.pi * 5.0 * 100.0)
     if variant == "angle_pair_aux":
         LOG_P = -np.log(2 * np.pi * np.pi * 100.0)
-    if variant == "dequantise":
+    if variant.startswith("dequantise"):
         LOG_P = -np.log(4.0 * 1000.0)
     model = Box()
     rng = np.random.default_rng(9)
@@ -305,7 +307,7 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     if "angle" in variant:
         pts[:, 0] = (1.0 + 0.8 * rng.standard_normal(600)) % (2 * np.pi)
         pts[:, 1] = np.clip(np.abs(1.0 + 0.7 * rng.standard_normal(600)), 0.05, 3.0 if variant == "angle_pair_aux" else 4.9)
-    if variant == "dequantise":
+    if variant.startswith("dequantise"):
         pts[:, 0] = rng.integers(0, 5, 600)
     live = numpy_array_to_live_points(pts, names)
     live["logL"] = model.log_likelihood(live)
@@ -332,7 +334,7 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
                           "angle_aux", "angle_and_radial_parameter", "accumulate_logit",
                           "angle_aux_likelihood_threshold", "accumulate_angle_likelihood_threshold",
                           "to_cartesian", "angle_pair_aux", "dequantise", "unit_hypercube_logit", "augmented",
-                          "augmented_logit", "angle_aux_host_prior", "augmented_host_prior")
+                          "augmented_logit", "angle_aux_host_prior", "augmented_host_prior", "dequantise_logit")
     if variant.startswith("augmented"):  # the augment parameters never reach the sampler (augmented.py, base.py:1100-1128)
         aug = [f"e_{i}" for i in range(prop.augment_dims)]
         assert prop._engine.names == names + aug and prop.samples.dtype.names[:D] == tuple(names)
@@ -344,7 +346,7 @@ def test_plugin_populate_on_simulated_device(tmp_path, monkeypatch, variant):
     if variant in ("to_cartesian", "angle_pair_aux"):
         aux = "x0_radial" if variant == "to_cartesian" else "x0_x1_radial"
         assert prop._engine.names == names + [aux] and aux in prop.x.dtype.names and aux not in prop.samples.dtype.names
-    if variant == "dequantise":
+    if variant.startswith("dequantise"):
         assert set(np.unique(prop.samples["x0"])) <= {0.0, 1.0, 2.0, 3.0, 4.0}
     if "angle_aux" in variant or variant == "accumulate_angle_likelihood_threshold":  # the auxiliary radius never reaches the sampler (flowproposal/base.py:1100-1128)
         assert prop._engine.names == names + ["x0_radial"] and prop.samples.dtype.names[:D] == tuple(names)

@@ -176,7 +176,8 @@ TAIL_CASE = dict(
     # slots 0 .. 11: the single-feature kinds; 12 .. 15: Angle (angle, aux radius, radius, angle mod 2 pi);
     # 16: floor (Dequantise); 17, 18: ToCartesian + its auxiliary radius; 19 .. 21: AnglePair az-zen with an
     # auxiliary radius; 22 .. 24: AnglePair ra-dec with a radial parameter; 25: an augment parameter
-    kind=np.array([0, 1, 2, 3, 1, 2, 0, 4, 5, 6, 1, 3, 7, 10, 9, 8, 11, 12, 10, 8, 13, 16, 7, 14, 15, 17],
+    # (slot 1: floor of the final value, the 0x100 flag of "dequantise-logit")
+    kind=np.array([0, 1 | 0x100, 2, 3, 1, 2, 0, 4, 5, 6, 1, 3, 7, 10, 9, 8, 11, 12, 10, 8, 13, 16, 7, 14, 15, 17],
                   dtype=np.int32),
     scale=np.array([1.5, 8.0, -3.0, 2.0, 0.5, 4.0, -0.7, 1.2, 6.0, 0.9, 1.0, 1.0, 0.5, 1.0, 1.0, 1.0,
                     1.0, 2.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0]),
@@ -333,6 +334,8 @@ PAIR_CASES = {
     "angle_pair_sky_zero_bound": (["ra", "dec"], {"ra": [0.0, 2 * np.pi], "dec": [-np.pi / 2, np.pi / 2]},
                                   {"angle-pair": {"parameters": ["ra", "dec"]}}, [8, 14, 16]),
     "dequantise": (["k", "x"], {"k": [0.0, 5.0], "x": [0.5, 4.0]}, {"k": "dequantise", "x": "default"}, [11, 0]),
+    "dequantise_logit": (["k", "x"], {"k": [0.0, 5.0], "x": [0.5, 4.0]}, {"k": "dequantise-logit", "x": "default"},
+                         [1 | 0x100, 0]),
 }
 
 
