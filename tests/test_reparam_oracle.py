@@ -490,3 +490,86 @@ def test_sum_exp_kernel_source_runs_under_simt_shim(simt_kernels, n, grid):
     again = np.full(grid, np.nan)
     simt_kernels.simt_sum_exp(grid, logw.ctypes.data, n, mx.ctypes.data, again.ctypes.data)
     np.testing.assert_array_equal(partials, again)  # no atomics: reproducible
+
+
+# ------------------------------------------------------------------ every named reparameterisation
+@pytest.mark.reference
+def test_every_named_reparameterisation_maps_to_the_device_tail(tmp_path):
+    """Every name the reference registers (reparameterisations/__init__.py:40-200) is recognised by
+    ``parameter_maps`` -- none of them falls back to the reference's host loop -- and its inverse
+    agrees with the reference's ``inverse_rescale`` on random prime points."""
+    reference_or_skip()
+    from nessai.livepoint import empty_structured_array, numpy_array_to_live_points
+    from nessai.model import Model
+    from nessai.proposal import FlowProposal
+    from nessai.reparameterisations import default_reparameterisations
+
+    from nessai_b200.nessai_plugin import parameter_maps
+    from oracle.reparam_numpy import inverse_maps
+
+    registered = sorted(k for k in default_reparameterisations.keys() if isinstance(k, str))
+    assert len(registered) >= 30
+    unit = {"z-score-logit", "zscore-logit", "z-score-inv-gaussian-cdf", "zscore-inv-gaussian-cdf"}  # domain (0, 1)
+    for name in registered:
+        pair = name == "angle-pair"
+        if pair:
+            bounds = {"a": [0.0, 2 * np.pi], "b": [0.0, np.pi]}
+        elif name in unit:
+            bounds = {"a": [0.0, 1.0], "b": [0.5, 3.0]}
+        elif name == "angle-pi":
+            bounds = {"a": [0.0, np.pi], "b": [0.5, 3.0]}
+        elif name.startswith("dequantise"):
+            bounds = {"a": [0.0, 5.0], "b": [0.5, 3.0]}
+        else:
+            bounds = {"a": [0.0, 3.0] if name == "periodic" else [0.5, 3.0], "b": [0.5, 3.0]}
+
+        class M(Model):
+            def __init__(self):
+                self.names = ["a", "b"]
+                self.bounds = {k: list(v) for k, v in bounds.items()}
+
+            def log_prior(self, x):
+                return np.log(self.in_bounds(x), dtype="float")
+
+            def log_likelihood(self, x):
+                return np.zeros(x.size)
+
+            def new_point(self, N=1):
+                x = super().new_point(N)
+                if name.startswith("dequantise"):
+                    x["a"] = np.floor(x["a"])
+                return x
+
+        model = M()
+        rng = np.random.default_rng(1)
+        model.set_rng(rng)
+        kwargs = {"scale": 2.0} if name in ("scale", "rescale", "scaleandshift") else {}
+        rep = ({name: {"parameters": ["a", "b"]}} if pair
+               else {name: {"parameters": ["a"], **kwargs}, "default": {"parameters": ["b"]}})
+        prop = FlowProposal(model, rng=rng, flow_config=dict(n_blocks=2, n_neurons=8), output=str(tmp_path / name),
+                            poolsize=100, plot=False, reparameterisations=rep)
+        prop.initialise()
+        cols = []
+        for nm in model.names:
+            lo, hi = bounds[nm]
+            cols.append(rng.uniform(lo + 0.05 * (hi - lo), hi - 0.05 * (hi - lo), 300))
+        if name.startswith("dequantise"):
+            cols[0] = np.floor(rng.uniform(0.0, 6.0, 300))
+        live = numpy_array_to_live_points(np.stack(cols, axis=1), model.names)
+        prop.check_state(live)
+        prop.rescale(live.copy())  # (boundary inversion detects its edges here)
+        maps = parameter_maps(prop._reparameterisation, prop.prime_parameters, model.names, prop.parameters)
+        assert maps is not None, f"{name} falls back to the host loop"
+        n = 200
+        a = rng.normal(0.0, 0.7, size=(n, len(prop.prime_parameters)))
+        xp = empty_structured_array(n, names=prop.prime_parameters)
+        for i, p in enumerate(prop.prime_parameters):
+            xp[p] = a[:, i]
+        with np.errstate(all="ignore"):
+            x_ref, log_j_ref = prop.inverse_rescale(xp.copy())
+            x, log_j = inverse_maps(a, maps.kind, maps.scale, maps.shift, maps.pre_scale, maps.pre_shift, maps.src)
+        ref = np.stack([x_ref[nm] for nm in prop.parameters], axis=-1)
+        ok = np.isfinite(log_j_ref) & np.all(np.isfinite(ref), axis=1)
+        assert ok.mean() > 0.3, name
+        np.testing.assert_allclose(x[ok], ref[ok], rtol=1e-11, atol=1e-11, err_msg=name)
+        np.testing.assert_allclose(log_j[ok], log_j_ref[ok], rtol=1e-11, atol=1e-11, err_msg=name)
