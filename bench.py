@@ -38,7 +38,7 @@ POOL = 1_000_000
 FLOPS_PER_ROW = 47.7e3  # SURVEY.md 8(d), C2 RealNVP/MLP
 BYTES_PER_ROW = 68.0  # sample_and_log_prob, in-kernel RNG, z not returned
 SEED = 20251017
-TRAFFIC_BYTES = 33.2e6  # dram read + write per launch of the dominant kernel, ncu --set full (profiles/r2_ncu_populate_tcgen05_affmma.txt)
+TRAFFIC_BYTES = 33.7e6  # dram read + write per launch of the dominant kernel, ncu --set full (profiles/r2_ncu_populate_tcgen05_final.txt)
 
 
 def load_c2():
