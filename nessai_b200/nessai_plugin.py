@@ -6,10 +6,13 @@ Importing this module requires ``nessai`` to be importable.  It defines
   ``_FlowModelClass = B200FlowModel`` -- every flow evaluation of the unmodified
   reference proposal (train / forward_pass / backward_pass / truncation rules)
   runs on the CUDA kernels -- and a ``populate`` override that runs the fused
-  device loop whenever the configuration allows it (``parameter_maps``: z-score /
-  null / scale / rescale-to-bounds reparameterisations incl. logit / log
-  post-rescaling and boundary inversion; the three truncation rules; weight
-  accumulation for affine maps) and otherwise defers to the reference's host loop;
+  device loop whenever the configuration allows it (``parameter_maps``: every
+  reparameterisation name the reference registers -- z-score / null / scale /
+  rescale-to-bounds incl. the named pre- / post-rescalings and boundary inversion,
+  ``Angle``, ``ToCartesian``, ``AnglePair``, ``Dequantise``; ``map_to_unit_hypercube``; the
+  three truncation rules; weight accumulation) and otherwise defers to the reference's
+  host loop;
+* ``B200AugmentedFlowProposal``: the same for ``AugmentedFlowProposal``;
 * the entry point ``nessai.proposals: b200flowproposal``, so
   ``FlowSampler(model, flow_proposal_class="b200flowproposal")`` picks it up
   through ``nessai.proposal.utils.get_flow_proposal_class``
