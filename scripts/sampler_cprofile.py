@@ -11,7 +11,7 @@ from nessai.flowsampler import FlowSampler
 from nessai.model import Model
 from nessai_b200.nessai_plugin import B200NessaiFlowProposal
 
-D = 8
+D = int(os.environ.get("NB200_PROFILE_D", 8))
 class Gaussian(Model):
     def __init__(self):
         self.names = [f"x{i}" for i in range(D)]
@@ -22,7 +22,8 @@ class Gaussian(Model):
         return -0.5 * np.sum(self.unstructured_view(x) ** 2, axis=-1) - 0.5 * D * np.log(2 * np.pi)
 
 fs = FlowSampler(Gaussian(), output=tempfile.mkdtemp(), resume=False, seed=1234, nlive=1000, plot=False,
-                 flow_proposal_class=B200NessaiFlowProposal, checkpointing=False, max_iteration=int(sys.argv[1]) if len(sys.argv) > 1 else 6000)
+                 flow_proposal_class=B200NessaiFlowProposal, checkpointing=False, max_iteration=int(sys.argv[1]) if len(sys.argv) > 1 else 6000,
+                 **({"drawsize": int(os.environ["NB200_PROFILE_DRAWSIZE"])} if os.environ.get("NB200_PROFILE_DRAWSIZE") else {}))
 pr = cProfile.Profile(); t0 = time.perf_counter(); pr.enable(); fs.run(plot=False, save=False); pr.disable()
 wall = time.perf_counter() - t0
 prop = fs.ns._flow_proposal
