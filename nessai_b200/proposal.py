@@ -540,7 +540,9 @@ class PopulateEngine:
         drawn_ahead = False
         rb = self.row_bytes
         max_turns = int(max_samples) // drawsize + 1
-        single = self.world == 1 and to_host
+        # (a small pool -- the reference's default poolsize is nlive -- is copied once at the end: a
+        # pinned block and a copy-stream hop per turn cost more than its few hundred KB are worth)
+        single = self.world == 1 and to_host and n_samples * rb > (2 << 20)
         cs = self._copy_stream
         # several GPUs on one node: the pool is assembled in host memory shared by the ranks,
         # each rank copying only its own records (hostpool.py); else all-gather at the end
