@@ -158,3 +158,49 @@ def test_cuda_draw_source_matches_numpy_restatement(philox_source):
     got = [philox_source.accept_uniform_host(seed, int(r)) for r in rows]
     np.testing.assert_array_equal(got, u)
     assert np.all((u > 0) & (u < 1))
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("seed", range(12))
+def test_numpy_oracle_matches_the_reference_over_the_config_space(seed):
+    """The checker of the GPU sweeps (tests/test_gpu_fuzz.py) is itself pinned here: the float64 numpy
+    oracle against the UNMODIFIED reference's own flow classes (configure_model on the glasflow shim,
+    fp32) for random configurations over the same space -- incl. 17 .. 32-feature RealNVP flows, the
+    default conditioner width, three residual blocks, tanh / SiLU -- with perturbed weights."""
+    reference_or_skip()
+    import torch
+    from nessai.flows import configure_model
+    from nessai.flowmodel.utils import update_flow_config
+    from test_gpu_fuzz import draw_config
+
+    cfg = draw_config(300 + seed)
+    if seed % 3 == 0:  # make sure the 17 .. 32-feature RealNVP flows are in
+        cfg = dict(n_inputs=int(17 + seed), n_blocks=3, n_layers=int(1 + seed % 3), ftype="realnvp")
+    torch.manual_seed(seed)
+    full = update_flow_config(dict(cfg))
+    m = configure_model(dict(full))
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for k, v in m.state_dict().items():
+        a = v.numpy().copy()
+        if a.dtype.kind == "f" and not k.endswith(".mask"):
+            a = a + (0.04 * rng.standard_normal(a.shape)).astype(np.float32)
+            if "running_var" in k:
+                a = np.abs(a) + 0.5
+        sd[k] = a
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m.eval()
+    D = cfg["n_inputs"]
+    z = rng.normal(size=(400, D)).astype(np.float32)
+    with torch.inference_mode():
+        x_ref, ilj_ref = m.inverse(torch.from_numpy(z))
+        lp_ref = m.log_prob(x_ref)
+    ocfg = dict(full)
+    nf = numpy_flow(ocfg, sd)
+    x, ilj = nf.inverse(z.astype(np.float64))
+    ok = np.isfinite(ilj) & (np.abs(x).max(axis=1) < 50.0)
+    assert ok.mean() > 0.9, cfg
+    tol = dict(rtol=3e-4, atol=3e-4) if cfg["ftype"] in ("nsf", "maf") else dict(rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(x_ref.numpy()[ok], x[ok], err_msg=str(cfg), **tol)
+    np.testing.assert_allclose(ilj_ref.numpy()[ok], ilj[ok], err_msg=str(cfg), **tol)
+    np.testing.assert_allclose(lp_ref.numpy()[ok], nf.log_prob(x_ref.numpy().astype(np.float64))[ok], err_msg=str(cfg), **tol)
