@@ -95,3 +95,50 @@ def test_clip_and_adam_match_torch(opt):
         TrainStepOracle.clip_(gn, 5.0)
         TrainStepOracle.adam_step_(pn, gn, m, v, t, 1e-3, **kw)
         np.testing.assert_allclose(pn, p.detach().numpy(), rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_loss_and_grad_match_reference_autograd_over_the_config_space(seed):
+    """The checker of the GPU training sweep (tests/test_gpu_fuzz.py) pinned over the same space:
+    float64 autograd through the reference's own module tree for random configurations (features,
+    conditioner width / depth / type, linear transform, BatchNorm, activation, coupling type), ragged
+    and weighted batches."""
+    reference_or_skip()
+    from nessai.flowmodel.utils import update_flow_config
+    from nessai.flows.utils import configure_model
+    from test_gpu_fuzz import draw_config
+
+    cfg = draw_config(400 + seed)
+    torch.manual_seed(seed)
+    full = update_flow_config(dict(cfg))
+    model = configure_model(copy.deepcopy(full))
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for k, v in model.state_dict().items():
+        a = v.numpy().copy()
+        if a.dtype.kind == "f" and not k.endswith(".mask"):
+            a = a + (0.04 * rng.standard_normal(a.shape)).astype(np.float32)
+            if "running_var" in k:
+                a = np.abs(a) + 0.5
+        sd[k] = a
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    model = model.double()
+    model.train()
+    spec = FlowSpec(dict(cfg))
+    theta = np.zeros(spec.n_theta, dtype=np.float32)
+    ints = {}
+    spec.load_state_dict_numpy(sd, theta, ints)
+    theta = theta.astype(np.float64)
+    D = cfg["n_inputs"]
+    x = 1.2 * rng.standard_normal((int(rng.integers(40, 400)), D)) + 0.3
+    w = rng.uniform(0.2, 2.0, size=len(x)) if seed % 2 else None
+    lp = model.log_prob(torch.from_numpy(x))
+    loss_t = -lp.mean() if w is None else -torch.sum(lp * torch.from_numpy(w)) / float(np.sum(w))
+    loss_t.backward()
+    loss, grad = TrainStepOracle(spec, ints).loss_and_grad(theta, x, weights=w)
+    assert abs(loss - float(loss_t)) < 1e-9 * max(1.0, abs(loss)), cfg
+    named = dict(model.named_parameters())
+    for e in spec.entries:
+        if e.kind == "param":
+            np.testing.assert_allclose(grad[e.offset : e.offset + e.size], named[e.key].grad.numpy().ravel(), rtol=1e-6,
+                                       atol=1e-9, err_msg=f"{cfg} {e.key}")
